@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of gkirgizov/die on B200: agent.forward + env.step per iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl die_b200|reference]
+
+N = 1 : PhysarumAgent on a single 4096x4096 field, agent_ratio 0.1  (BASELINE.json configs[2])
+N > 1 : 4096 independent 256x256 Physarum envs sharded over the ranks, no data-path collective
+        (BASELINE.json configs[3]); launched by torchrun, one rank per GPU.
+Rank 0 prints ONE JSON line.  `value` = cell-updates/s of the whole job with state resident in
+HBM; `e2e` = the same loop through the host-buffer API (numpy obs/action cross PCIe every call);
+`roofline` = the dominant kernel's algorithmic bytes / CUDA-event time against the measured HBM
+peak; `cpu_baseline` = the numpy oracle (a port of the reference's CPU path) on this host.
+`--impl reference` times that CPU path alone on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+PHYS = dict(scale=0.007, turn_angle=30, sense_offset=0.04)      # reference README.md:45-48
+AGENT_RATIO = 0.1
+METRIC = "env cell-updates/sec (agent.forward + env.step, Physarum)"
+UNIT = "cell-updates/s"
+
+# Algorithmic bytes (float64 fields and agents, s_f = s_a = 8):
+#   physarum_forward  R{x,y,theta} W{theta,dx,dy,dep} + gathers{4 chem, 1 food}        = 96 B / slot
+#   move_claim        R{x,y,alive,dx,dy} W{x,y}                                          = 56 B / slot
+#   deposit_feed      R{agent_food,dep} W{agent_food} + gathers{food,occ} (+16 B/alive)  = 40 B / slot
+#   field_step        chem R+W, food R+W, occupancy R+W                                  = 48 B / cell
+BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "deposit_feed": 40.0, "field_step": 48.0,
+         "finalize_stats": 0.0}
+ALIVE_EXTRA = {"deposit_feed": 16.0, "field_step": 8.0}        # chem RMW, occupancy write of alive cells
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload, kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def reader():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------
+def build_host_state(field, n_distinct, seed):
+    """`n_distinct` seeded initial states (food = gradient noise with 256^2-like texture, i.e.
+    8 lattice periods per 256 cells; occupancy Bernoulli(0.1); chem = 0)."""
+    from die_b200 import data_init
+    periods = max(8, 8 * field[0] // 256)
+    mediums, agents = [], []
+    for k in range(n_distinct):
+        np.random.seed(seed + k)
+        m = data_init.init_medium(field, AGENT_RATIO, noise_seed=seed + k, periods=periods)
+        mediums.append(m)
+        agents.append(data_init.agents_from_medium(m))
+    return np.stack(mediums), np.stack(agents)
+
+
+def lattice_theta_device(B, M, turn_angle, seed, device):
+    """theta_0 uniform on the turn lattice (what discretize(angle(N(0,.4)^2)) gives), drawn on device."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    tr = float(np.radians(turn_angle))
+    nlat = int(round(2 * np.pi / tr))
+    k = torch.randint(-nlat // 2, nlat - nlat // 2, (B, M), generator=g, device=device)
+    return k.to(torch.float64) * tr
+
+
+def run_die_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (die_b200 has no CPU fallback); "
+                         "use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n_gpus = world
+    if args.gpus != n_gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    import die_b200 as D
+
+    workload = args.workload
+    if workload == "auto":
+        workload = "field4096" if n_gpus == 1 else "batch256"
+    if workload == "field4096":
+        field, B_total = (args.field, args.field), 1
+        scaling = "weak"
+    else:
+        field, B_total = (256, 256), args.batch
+        scaling = "strong"
+    if B_total % n_gpus != 0 and workload != "field4096":
+        raise SystemExit(f"batch {B_total} not divisible by {n_gpus} ranks")
+    B_local = B_total // n_gpus if workload != "field4096" else 1
+    batched = workload != "field4096"
+
+    # ---- state ---------------------------------------------------------------------------
+    t0 = time.time()
+    n_distinct = 1 if not batched else min(B_local, 16)
+    med_h, ag_h = build_host_state(field, n_distinct, seed=1000 * rank)
+    if batched:
+        reps = (B_local + n_distinct - 1) // n_distinct
+        med_h = np.tile(med_h, (reps, 1, 1, 1))[:B_local]
+        ag_h = np.tile(ag_h, (reps, 1, 1))[:B_local]
+    env = D.Env(field, D.Dynamics(init_agent_ratio=AGENT_RATIO), batch=(B_local if batched else None),
+                init_state=(med_h, ag_h), device=device)
+    M = env.max_agents
+    C = field[0] * field[1]
+    alive_local = int((ag_h[:, 2] > 0).sum())
+    del med_h, ag_h
+    agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
+    agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
+    setup_s = time.time() - t0
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def loop(n, obs):
+        for _ in range(n):
+            action = agent.forward(obs)
+            obs, _, _ = env.step_async(action)
+        return obs
+
+    # ---- warm-up + timed region (device resident) ------------------------------------------------
+    obs = env._get_current_obs
+    obs = loop(args.warmup, obs)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    obs = loop(args.steps, obs)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    cells_per_step = C * B_total
+    value = cells_per_step / (ms_per_step * 1e-3)
+
+    # ---- per-kernel breakdown with CUDA events on the launching stream ---------------------------
+    env.set_profiling(True)
+    fwd_events = []
+    n_prof = min(args.steps, 200)
+    for _ in range(n_prof):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        action = agent.forward(obs)
+        e1.record()
+        obs, _, _ = env.step_async(action)
+        fwd_events.append((e0, e1))
+    torch.cuda.synchronize()
+    kms, nprof = env.kernel_times()
+    env.set_profiling(False)
+    kernel_ms = {"physarum_forward": sum(a.elapsed_time(b) for a, b in fwd_events) / n_prof}
+    kernel_ms.update({k: v / max(nprof, 1) for k, v in kms.items()})
+    peak, peak_src = measured_hbm_peak()
+    slots_local, cells_local = M * B_local, C * B_local
+    kernels = {}
+    for k, t_ms in kernel_ms.items():
+        units = cells_local if k == "field_step" else slots_local
+        nbytes = BYTES[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
+        gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        kernels[k] = {"ms": round(t_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1),
+                      "frac": round(gbs / peak, 4)}
+    dominant = max((k for k in kernels if BYTES[k] > 0), key=lambda k: kernels[k]["ms"])
+    step_bytes = sum(v["algorithmic_bytes"] for v in kernels.values())
+    wl_name = ("physarum_single_field_%dx%d" % field) if not batched else f"physarum_batched_{B_total}x256x256"
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dominant]["frac"], "peak_source": peak_src,
+                "traffic": ncu_traffic(wl_name, dominant),
+                "kernels": kernels,
+                "step": {"algorithmic_bytes": step_bytes,
+                         "gbs": round(step_bytes / (ms_per_step * 1e-3) / 1e9 * (1 if batched else 1), 1),
+                         "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                         "frac_of_8TBs_nominal": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)}}
+
+    # ---- e2e: the same loop through the host-buffer API -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = max(3, min(args.steps, args.e2e_steps))
+        hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
+        for _ in range(2):                                   # warm the pinned staging buffers
+            hact = agent.forward(hobs)
+            hobs, *_ = env.step(hact)
+        sync_all()
+        t_start = time.perf_counter()
+        for _ in range(k_e2e):
+            hact = agent.forward(hobs)                       # H2D obs, kernel, D2H action
+            hobs, hr, _, _, _ = env.step(hact)               # H2D action, kernels, D2H obs + reward
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t_start
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        h2d_step, d2h_step = env.host_io_bytes_per_step()
+        fwd_h2d = 8 * B_local * (4 * M + 3 * C)
+        fwd_d2h = 8 * B_local * 3 * M
+        e2e = {"value": cells_per_step * k_e2e / t_e2e, "unit": UNIT, "steps": k_e2e,
+               "ms_per_step": t_e2e / k_e2e * 1e3,
+               "h2d_bytes_per_step": (h2d_step + fwd_h2d) * n_gpus, "d2h_bytes_per_step": (d2h_step + fwd_d2h) * n_gpus,
+               "api": "numpy obs/action across Agent.forward and Env.step (die_env_step_host)"}
+
+    # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        cpu = time_oracle(args.cpu_field, args.cpu_steps, warmup=2)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (gradient-noise food, Bernoulli(0.1) agents, seeded)",
+            "config": {"workload": wl_name, "field": list(field), "envs": B_total, "envs_per_gpu": B_local,
+                       "agent": "PhysarumAgent", **PHYS, "agent_ratio": AGENT_RATIO, "max_agents_per_env": M,
+                       "alive_agents_per_gpu": alive_local, "rng": "philox (in-kernel)",
+                       "l2": "per-step working set %.2f GB per GPU >> 126 MB L2 (inputs larger than L2, no flush)"
+                             % (step_bytes / 1e9)},
+            "agent_steps_per_s": M * B_total / (ms_per_step * 1e-3),
+            "alive_agent_steps_per_s": alive_local * n_gpus / (ms_per_step * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": args.steps * 5 * 1, "launches_per_step": 5, "clocks": clocks,
+            "setup_s": round(setup_s, 1),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference)
+# --------------------------------------------------------------------------------------------
+def time_oracle(field_n, steps, warmup):
+    from oracle import die_ref as R
+    field = (field_n, field_n)
+    np.random.seed(0)
+    env = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=0)
+    m = env.agents.shape[-1]
+    agent = R.PhysarumAgent(max_agents=m, **PHYS)
+    obs = env._get_current_obs
+    for _ in range(warmup):
+        obs, *_ = env.step(agent.forward(obs))
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        obs, *_ = env.step(agent.forward(obs))
+        times.append(time.perf_counter() - t)
+    per = float(np.mean(times))
+    return {"value": field_n * field_n / per, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{steps} steps of PhysarumAgent on a {field_n}x{field_n} field (numpy/scipy oracle, "
+                      f"single thread like the reference), after {warmup} warm-up steps",
+            "ms_per_step": per * 1e3, "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference
+    itself cannot be imported here) on the host cores; each step is one Physarum iteration on a
+    bounded-size field with the same per-cell work as the GPU arm's workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    from oracle import die_ref as R
+    field_n = args.cpu_field
+    field = (field_n, field_n)
+    np.random.seed(0)
+    env = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=0)
+    m = env.agents.shape[-1]
+    agent = R.PhysarumAgent(max_agents=m, **PHYS)
+    obs = env._get_current_obs
+    for _ in range(args.warmup):
+        obs, *_ = env.step(agent.forward(obs))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        obs, *_ = env.step(agent.forward(obs))
+    dt = time.perf_counter() - t0
+    value = field_n * field_n * args.steps / dt
+    sample = (f"each step = one PhysarumAgent.forward + Env.step on a {field_n}x{field_n} field "
+              f"(same per-cell work as the GPU arm's workload), numpy/scipy oracle port, 1 thread "
+              f"(the reference is single-threaded)")
+    wl = "physarum_single_field_4096x4096" if n_gpus == 1 else "physarum_batched_4096x256x256"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak" if n_gpus == 1 else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": wl, "sample_field": list(field),
+                                                            "agent": "PhysarumAgent", **PHYS,
+                                                            "agent_ratio": AGENT_RATIO},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="die_b200", choices=["die_b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "field4096", "batch256"])
+    ap.add_argument("--field", type=int, default=4096, help="side of the single field (field4096 workload)")
+    ap.add_argument("--batch", type=int, default=4096, help="total number of 256x256 envs (batch256 workload)")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-field", type=int, default=512, help="side of the CPU sample field")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_die_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""ctypes binding of libdie_sm100a.so (include/die_b200.h).  There is no fallback: if the
+library is missing this module raises, and so does everything that imports it."""
+import ctypes as C
+import os
+
+from ._build import LIB_PATH
+
+DIE_MAX_RADIUS = 8
+BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
+
+
+class DieDynamics(C.Structure):
+    _fields_ = [
+        ("rate_feed", C.c_double),
+        ("rate_decay_chem", C.c_double),
+        ("cost_w_deposit", C.c_double),
+        ("cost_w_dist", C.c_double),
+        ("blur_w", C.c_double * (2 * DIE_MAX_RADIUS + 1)),
+        ("blur_radius", C.c_int32),
+        ("boundary", C.c_int32),
+        ("food_infinite", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class DieGradientParams(C.Structure):
+    _fields_ = [
+        ("scale", C.c_double),
+        ("deposit", C.c_double),
+        ("inertia", C.c_double),
+        ("sense_offset", C.c_double),
+        ("noise_scale", C.c_double),
+        ("grad_clip", C.c_double),
+        ("turn_radians", C.c_double),
+        ("sense_radians", C.c_double),
+        ("turn_tolerance", C.c_double),
+        ("normalized_grad", C.c_int32),
+        ("use_grad_clip", C.c_int32),
+        ("discrete_turn", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class DieError(RuntimeError):
+    pass
+
+
+# every symbol include/die_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "die_version": (C.c_char_p, []),
+    "die_last_error": (C.c_char_p, []),
+    "die_env_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(DieDynamics), C.POINTER(_P)]),
+    "die_env_destroy": (C.c_int, [_P]),
+    "die_env_set_dynamics": (C.c_int, [_P, C.POINTER(DieDynamics)]),
+    "die_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_env_cells": (_P, [_P]),
+    "die_env_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_brownian_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P,
+                                       C.c_uint64, C.c_uint64, _P]),
+    "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
+    "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                       _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. die_b200 has no CPU / PyTorch fallback: build the CUDA library "
+            f"with `python die_b200/_build.py` (needs nvcc) before use.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DieError(f"libdie_sm100a error {rc}: {load().die_last_error().decode()}")

@@ -1,0 +1,209 @@
+"""GradientAgent / PhysarumAgent -- drop-ins for core/agent/gradient.py:13-219.
+
+Agent-private state (``_direction_rads`` = theta, ``_prev_grad``) lives on the device; one
+``forward`` is one launch of ``die_gradient_forward``.  The reference materialises the
+normalised gradient of the whole chem1 field every call; the kernel evaluates the same
+np.gradient stencil only at each slot's sensed cell.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..base_types import ActType, ObsType
+from .static import _DeviceAgent, _split_obs
+
+
+def _renormalize_radians(r):
+    return (r - np.pi) % (-2 * np.pi) + np.pi
+
+
+class GradientAgent(_DeviceAgent):
+    """core/agent/gradient.py:13-124.
+
+    ``rng='philox'`` (default): coin flips / momentum noise are drawn in-kernel.
+    ``rng='numpy'`` (validation mode): drawn on the host exactly where the reference draws them
+    -- ``np.random.randint(0, 2, M)`` from the GLOBAL legacy RNG for Physarum turns
+    (core/agent/gradient.py:181) and ``rng.normal(0, .4, (2, M))`` from the agent's private
+    generator for the momentum noise (:50-53) -- and uploaded.
+    """
+    _discrete_turn = False
+
+    def __init__(self,
+                 max_agents: int = 10 ** 6,
+                 scale: float = 0.01,
+                 deposit: float = 4.0,
+                 inertia: float = 0.9,
+                 sense_offset: float = 0.,
+                 noise_scale: float = 0.025,
+                 normalized_grad: bool = True,
+                 grad_clip: Optional[float] = 1e-5,
+                 *, rng: str = 'philox', seed: int = 0):
+        super().__init__()
+        self._init_params = dict(max_agents=max_agents, scale=scale, deposit=deposit, inertia=inertia,
+                                 sense_offset=sense_offset, noise_scale=noise_scale,
+                                 normalized_grad=normalized_grad, grad_clip=grad_clip)
+        if rng not in ('philox', 'numpy'):
+            raise ValueError("rng must be 'philox' or 'numpy'")
+        self._size = int(max_agents)
+        self._rng_mode = rng
+        self._seed = int(seed)
+        self._rng = np.random.default_rng(None if rng == 'numpy' else seed)
+        self._noise_scale = float(noise_scale)
+        self._scale = float(scale)
+        self._deposit = float(deposit)
+        self._inertia = float(inertia)
+        self._sense_offset_scale = float(sense_offset)
+        self._normalized = bool(normalized_grad)
+        self._grad_clip = grad_clip
+        self._turn_radians = 0.0
+        self._sense_radians = 0.0
+        self._rtol = 0.0
+        self._theta = None          # [B, M] device
+        self._prev_grad = None      # [B, 2, M] device (only when it can matter)
+        self._coin_host = self._coin_dev = None
+        self._noise_host = self._noise_dev = None
+        self._sense_cells = None
+        self.record_sense_cells = False
+
+    # -- state ------------------------------------------------------------------------------
+    def _needs_prev(self) -> bool:
+        return self._inertia != 0.0 or self._noise_scale != 0.0
+
+    def _initial_theta(self, prev_grad: np.ndarray) -> np.ndarray:
+        """get_radians(prev_grad), core/agent/gradient.py:42-43."""
+        return np.angle(prev_grad[..., 0, :] + np.multiply(1j, prev_grad[..., 1, :]))
+
+    def _lazy_init(self, B: int, M: int, device):
+        if self._theta is not None and tuple(self._theta.shape) == (B, M):
+            return
+        if M != self._size:
+            raise ValueError(f"agent was built with max_agents={self._size} but the env has {M} slots "
+                             f"(the reference needs them equal too, core/agent/gradient.py:105)")
+        prev = self._rng.normal(loc=0., scale=0.4, size=(B, 2, M))       # _get_some_noise, :50-53
+        self.set_state(theta=self._initial_theta(prev), prev_grad=prev, device=device)
+
+    def set_state(self, theta=None, prev_grad=None, device=None):
+        """Inject agent-private state (validation / checkpoint aid)."""
+        device = device or (self._theta.device if self._theta is not None else
+                            torch.device('cuda', torch.cuda.current_device()))
+        if theta is not None:
+            t = np.asarray(theta, dtype=np.float64)
+            t = t.reshape(-1, t.shape[-1])
+            self._theta = torch.from_numpy(np.ascontiguousarray(t)).to(device)
+        if prev_grad is not None and self._needs_prev():
+            p = np.asarray(prev_grad, dtype=np.float64)
+            p = p.reshape(-1, 2, p.shape[-1])
+            self._prev_grad = torch.from_numpy(np.ascontiguousarray(p)).to(device)
+
+    def get_state(self):
+        th = self._theta.cpu().numpy()
+        pg = self._prev_grad.cpu().numpy() if self._prev_grad is not None else None
+        if th.shape[0] == 1:
+            th = th[0]
+            pg = pg[0] if pg is not None else None
+        return th, pg
+
+    @property
+    def sense_cells(self) -> Optional[torch.Tensor]:
+        return self._sense_cells
+
+    def _params_c(self) -> _lib.DieGradientParams:
+        p = _lib.DieGradientParams()
+        p.scale = self._scale
+        p.deposit = self._deposit
+        p.inertia = self._inertia
+        p.sense_offset = self._sense_offset_scale
+        p.noise_scale = self._noise_scale
+        p.grad_clip = 0.0 if self._grad_clip is None else float(self._grad_clip)
+        p.turn_radians = self._turn_radians
+        p.sense_radians = self._sense_radians
+        p.turn_tolerance = self._rtol
+        p.normalized_grad = int(self._normalized)
+        p.use_grad_clip = int(self._grad_clip is not None)
+        p.discrete_turn = int(self._discrete_turn)
+        return p
+
+    # -- forward ------------------------------------------------------------------------------
+    def _upload(self, name: str, arr: np.ndarray, shape, dtype, device):
+        host, dev = getattr(self, f'_{name}_host'), getattr(self, f'_{name}_dev')
+        if host is None or tuple(host.shape) != tuple(shape):
+            host = torch.empty(shape, dtype=dtype).pin_memory()
+            dev = torch.empty(shape, dtype=dtype, device=device)
+            setattr(self, f'_{name}_host', host)
+            setattr(self, f'_{name}_dev', dev)
+        host.numpy()[...] = np.asarray(arr).reshape(shape)
+        dev.copy_(host, non_blocking=True)
+        return dev.data_ptr()
+
+    def forward(self, obs: ObsType, coin: Optional[np.ndarray] = None,
+                noise: Optional[np.ndarray] = None) -> ActType:
+        """core/agent/gradient.py:96-124.  ``coin`` ([B,] M in {0,1}) / ``noise`` ([B,] 2, M):
+        explicitly injected draws (override ``rng``)."""
+        if isinstance(obs[0], np.ndarray):
+            return self._forward_host(obs)
+        agents, medium, _, B, M = _split_obs(obs)
+        self._check(agents)
+        self._check(medium)
+        H, W = medium.shape[-2:]
+        self._lazy_init(B, M, agents.device)
+        action = self._action_for(agents)
+
+        coin_ptr = noise_ptr = None
+        if self._discrete_turn:
+            if coin is None and self._rng_mode == 'numpy':
+                coin = np.stack([np.random.randint(0, 2, M) for _ in range(B)])
+            if coin is not None:
+                coin_ptr = self._upload('coin', np.asarray(coin).astype(np.uint8), (B, M), torch.uint8, agents.device)
+        if self._needs_prev():
+            if noise is None and self._rng_mode == 'numpy':
+                noise = self._rng.normal(loc=0., scale=0.4, size=(B, 2, M))
+            if noise is not None:
+                noise_ptr = self._upload('noise', noise, (B, 2, M), torch.float64, agents.device)
+        cells_ptr = None
+        if self.record_sense_cells:
+            if self._sense_cells is None or tuple(self._sense_cells.shape) != (B, M):
+                self._sense_cells = torch.empty((B, M), dtype=torch.int32, device=agents.device)
+            cells_ptr = self._sense_cells.data_ptr()
+
+        p = self._params_c()
+        with torch.cuda.device(agents.device):
+            _lib.check(self._lib.die_gradient_forward(
+                _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(),
+                self._theta.data_ptr(),
+                self._prev_grad.data_ptr() if self._prev_grad is not None else None,
+                action.data_ptr(), coin_ptr, noise_ptr, cells_ptr,
+                self._seed, self._step, torch.cuda.current_stream().cuda_stream))
+        self._step += 1
+        return action
+
+
+class PhysarumAgent(GradientAgent):
+    """core/agent/gradient.py:138-219."""
+    _discrete_turn = True
+
+    def __init__(self,
+                 max_agents: int = 10 ** 6,
+                 scale: float = 0.005,
+                 deposit: float = 4.0,
+                 inertia: float = 0.0,
+                 sense_offset: float = 0.03,
+                 noise_scale: float = 0.0,
+                 normalized_grad: bool = True,
+                 grad_clip: Optional[float] = 1e-5,
+                 turn_angle: float = 30,
+                 sense_angle: float = 90,
+                 turn_tolerance: float = 0.1,
+                 *, rng: str = 'philox', seed: int = 0):
+        super().__init__(max_agents, scale, deposit, inertia, sense_offset, noise_scale,
+                         normalized_grad, grad_clip, rng=rng, seed=seed)
+        self._init_params.update(turn_angle=turn_angle, sense_angle=sense_angle, turn_tolerance=turn_tolerance)
+        self._turn_radians = float(np.radians(turn_angle))
+        self._sense_radians = float(np.radians(sense_angle))
+        self._rtol = float(turn_tolerance)
+
+    def _initial_theta(self, prev_grad: np.ndarray) -> np.ndarray:
+        """_discretize_grad, core/agent/gradient.py:162,165-166."""
+        rads = super()._initial_theta(prev_grad)
+        return (rads // self._turn_radians) * self._turn_radians

@@ -1,0 +1,334 @@
+// die_agent_kernels.cuh -- per-slot kernels: policies (Brownian / Const / Gradient / Physarum)
+// and the agent half of Env.step (move + claim, deposit + feed + reduce).
+//
+// One thread per agent slot, grid-stride over all B*M slots; every per-slot array is
+// channel-major ([B][ch][M]) so consecutive threads read consecutive doubles (coalesced,
+// 256 B per warp per channel).  Field accesses are data-dependent gathers (one 32 B sector
+// each).  Citations are file:line under /root/reference.
+#pragma once
+#include "die_device.cuh"
+#include "../../include/die_b200.h"
+
+namespace die {
+
+constexpr int kAgentThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// BrownianAgent.forward  (core/agent/static.py:40-50; core/data_init.py:159-169,218-220,248-253)
+//   chan = ((b - a) * round(u, 3) + a) * alive,  u drawn in the order dx, dy, deposit1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAgentThreads)
+brownian_forward_kernel(const double* __restrict__ agents, double* __restrict__ action,
+                        int64_t M, int64_t total, double s, double dep_scale,
+                        const double* __restrict__ u, uint64_t seed, uint64_t step) {
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = gid / M, i = gid - b * M;
+        const double alive = agents[(b * 4 + 2) * M + i];
+        double u0, u1, u2;
+        if (u != nullptr) {
+            const double* ub = u + b * 3 * M;
+            u0 = ub[i];
+            u1 = ub[M + i];
+            u2 = ub[2 * M + i];
+        } else {
+            const uint4 r0 = philox_draw(seed, step, (uint64_t)gid, 0u);
+            const uint4 r1 = philox_draw(seed, step, (uint64_t)gid, 1u);
+            u0 = u53(r0.x, r0.y);
+            u1 = u53(r0.z, r0.w);
+            u2 = u53(r1.x, r1.y);
+        }
+        // np.round(u, 3) == rint(u * 1000) / 1000   
+        const double q0 = rint(u0 * 1000.0) / 1000.0;
+        const double q1 = rint(u1 * 1000.0) / 1000.0;
+        const double q2 = rint(u2 * 1000.0) / 1000.0;
+        const double span = s - (-s);                       // (b - a) with a = -s, b = s
+        double* ab = action + b * 3 * M;
+        ab[i]         = (span * q0 + (-s)) * alive;
+        ab[M + i]     = (span * q1 + (-s)) * alive;
+        ab[2 * M + i] = ((dep_scale - 0.0) * q2 + 0.0) * alive;
+    }
+}
+
+// ConstAgent.forward (core/agent/static.py:19-28)
+__global__ void __launch_bounds__(kAgentThreads)
+const_forward_kernel(double* __restrict__ action, int64_t M, int64_t total,
+                     double dx, double dy, double dep) {
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = gid / M, i = gid - b * M;
+        double* ab = action + b * 3 * M;
+        ab[i] = dx;
+        ab[M + i] = dy;
+        ab[2 * M + i] = dep;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GradientAgent.forward / PhysarumAgent.forward  (core/agent/gradient.py:96-124)
+//
+// The reference materialises the normalised gradient of the whole chem1 field
+// (_get_gradient, :55-71) and then samples it at ONE cell per slot.  Here the np.gradient
+// stencil is evaluated only at the sampled cell: identical arithmetic per sample, 4 chem
+// gathers instead of ~10 full-field passes.
+// ---------------------------------------------------------------------------------------------
+struct GradientArgs {
+    die_gradient_params_t p;
+    int H, W;
+    int64_t M, total;
+    const double* agents;
+    const double* medium;
+    double* theta;
+    double* prev_grad;          // may be null (inertia == 0 && noise_scale == 0)
+    double* action;
+    const uint8_t* coin;        // may be null -> Philox
+    const double* noise;        // may be null -> Philox Box-Muller (only if noise_scale != 0)
+    int32_t* sense_cells;       // may be null
+    uint64_t seed, step;
+};
+
+template <bool DISCRETE_TURN>
+__global__ void __launch_bounds__(kAgentThreads)
+gradient_forward_kernel(const GradientArgs a) {
+    const die_gradient_params_t& p = a.p;
+    const Axis ax = make_axis(a.H), ay = make_axis(a.W);
+    const int64_t M = a.M;
+    const int64_t C = (int64_t)a.H * a.W;
+    const int H = a.H, W = a.W;
+
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < a.total;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = gid / M, i = gid - b * M;
+        const double* ag = a.agents + b * 4 * M;
+        const double x = ag[i], y = ag[M + i];
+        const double th = a.theta[gid];
+        const double* food = a.medium + (b * 3 + 1) * C;
+        const double* chem = a.medium + (b * 3 + 2) * C;
+
+        // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double px = x + p.sense_offset * cs;
+        const double py = y + p.sense_offset * sn;
+        // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
+        const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
+        if (a.sense_cells != nullptr) a.sense_cells[gid] = sx * W + sy;
+
+        // np.gradient at (sx, sy): central interior, one-sided edges, non-periodic (Q5)
+        const double* row = chem + (int64_t)sx * W;
+        double gx, gy;
+        if (sx == 0)            gx = chem[(int64_t)W + sy] - row[sy];
+        else if (sx == H - 1)   gx = row[sy] - row[sy - W];
+        else                    gx = (row[sy + W] - row[sy - W]) / 2.0;
+        if (sy == 0)            gy = row[1] - row[0];
+        else if (sy == W - 1)   gy = row[sy] - row[sy - 1];
+        else                    gy = (row[sy + 1] - row[sy - 1]) / 2.0;
+
+        // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling)
+        const double norm = sqrt(gx * gx + gy * gy);
+        if (p.normalized_grad) {
+            gx = div_nan_to_num(gx, norm);
+            gy = div_nan_to_num(gy, norm);
+        }
+        if (p.use_grad_clip) {                       // grad *= (norm >= clip): keeps signed zeros
+            const double m = (norm >= p.grad_clip) ? 1.0 : 0.0;
+            gx *= m;
+            gy *= m;
+        }
+
+        bool deposit_mask = true;
+        if (DISCRETE_TURN) {
+            // PhysarumAgent._discrete_turn / _choose_turn (:168-208)
+            const double dr = p.normalized_grad ? 1.0 : hypot(gx, gy);
+            const double drads = angle_xy(gx, gy);
+            double dd = renormalize_radians(th - drads);
+            const double atol = p.turn_radians * p.turn_tolerance;
+            const bool und_grad = fabs(0.0 - drads) <= 1e-8 + 1e-5 * fabs(drads);
+            const bool und_turn = fabs(0.0 - dd) <= atol + 1e-2 * fabs(dd);
+            const bool unseen = fabs(dd) > p.sense_radians;
+            const bool und = und_grad || und_turn || unseen;
+            int c;
+            if (a.coin != nullptr) c = a.coin[gid] ? 1 : 0;
+            else c = (int)(philox_draw(a.seed, a.step, (uint64_t)gid, 2u).x >> 31);
+            double turn = ((double)c - 0.5) * 2.0;
+            dd *= und ? 0.0 : 1.0;
+            if (dd > atol) turn = -1.0;
+            if (dd < -atol) turn = 1.0;
+            turn *= p.turn_radians;
+            deposit_mask = !(und_grad || und_turn);
+            const double dirn = renormalize_radians(th + turn);
+            double s2, c2;
+            sincos(dirn, &s2, &c2);
+            gx = dr * c2;
+            gy = dr * s2;
+        }
+
+        // _process_momentum (:82-91)
+        if (a.prev_grad != nullptr) {
+            double* pg = a.prev_grad + b * 2 * M;
+            gx = (1.0 - p.inertia) * gx + p.inertia * pg[i];
+            gy = (1.0 - p.inertia) * gy + p.inertia * pg[M + i];
+            if (a.noise != nullptr) {
+                const double* nz = a.noise + b * 2 * M;
+                gx += p.noise_scale * nz[i];
+                gy += p.noise_scale * nz[M + i];
+            } else if (p.noise_scale != 0.0) {
+                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)gid, 3u);
+                const double u1 = 1.0 - u53(r.x, r.y), u2 = u53(r.z, r.w);
+                const double rad = 0.4 * sqrt(-2.0 * log(u1));
+                double sn3, cs3;
+                sincos(kTwoPi * u2, &sn3, &cs3);
+                gx += p.noise_scale * (rad * cs3);
+                gy += p.noise_scale * (rad * sn3);
+            }
+            pg[i] = gx;
+            pg[M + i] = gy;
+        }
+        a.theta[gid] = angle_xy(gx, gy);                       // :110
+
+        // deposit relative to food under the agent (:113-117, :210-214)
+        const int ix = nearest_cell(x, ax), iy = nearest_cell(y, ay);
+        double dep = p.deposit * food[(int64_t)ix * W + iy];
+        if (DISCRETE_TURN) dep = dep * (deposit_mask ? 1.0 : 0.1);
+
+        double* ab = a.action + b * 3 * M;                     // unmasked (Q8)
+        ab[i] = gx * p.scale;
+        ab[M + i] = gy * p.scale;
+        ab[2 * M + i] = dep;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Env._agent_move (core/env.py:152-172) + cell resolution (core/utils.py:39-54) + the claim
+// that resolves "last writer wins" (core/env.py:211): the winner of a cell is the
+// highest slot index among the alive agents on it -- atomicMax is order-independent, so the
+// result is deterministic and bit-exact.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAgentThreads)
+move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action,
+                  int32_t* __restrict__ winner, int32_t* __restrict__ cells,
+                  int H, int W, int64_t M, int64_t total, int boundary) {
+    const Axis ax = make_axis(H), ay = make_axis(W);
+    const int64_t C = (int64_t)H * W;
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = gid / M, i = gid - b * M;
+        double* ag = agents + b * 4 * M;
+        const double* ac = action + b * 3 * M;
+        double x = ag[i] + ac[i];
+        double y = ag[M + i] + ac[M + i];
+        if (boundary == DIE_BOUNDARY_WRAP) {
+            x = mod1(x);
+            y = mod1(y);
+        } else if (boundary == DIE_BOUNDARY_LIMIT) {          // np.clip(0., 1.)
+            x = fmin(fmax(x, 0.0), 1.0);
+            y = fmin(fmax(y, 0.0), 1.0);
+        }
+        ag[i] = x;
+        ag[M + i] = y;
+        const int cell = nearest_cell(x, ax) * W + nearest_cell(y, ay);
+        cells[gid] = cell;
+        if (ag[2 * M + i] > 0.0) atomicMax(winner + b * C + cell, (int32_t)i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Env._agent_deposit_and_layout (chem part, core/env.py:204-211) + Env._agent_feed per-slot
+// part (core/env.py:220-234, cost :29-35) + the reward / num_agents reduction (:118-121).
+// Block partials are written in a fixed layout and summed in a fixed order by
+// finalize_stats_kernel, so the reward is run-to-run deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFeedItems = 4;      // slots per thread
+
+__global__ void __launch_bounds__(kAgentThreads)
+deposit_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
+                    double* __restrict__ medium, const int32_t* __restrict__ winner,
+                    const int32_t* __restrict__ cells,
+                    double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
+                    int H, int W, int64_t M, int nblk,
+                    double rate_feed, double w_dep, double w_dist) {
+    const int64_t C = (int64_t)H * W;
+    const int64_t b = blockIdx.x / nblk;
+    const int blk = blockIdx.x - (int)b * nblk;
+    double* ag = agents + b * 4 * M;
+    const double* ac = action + b * 3 * M;
+    const double* food = medium + (b * 3 + 1) * C;
+    double* chem = medium + (b * 3 + 2) * C;
+    const int32_t* win = winner + b * C;
+    const int32_t* cl = cells + b * M;
+
+    double gain_sum = 0.0;
+    int alive_cnt = 0;
+    const int64_t base = (int64_t)blk * (kAgentThreads * kFeedItems);
+#pragma unroll
+    for (int k = 0; k < kFeedItems; ++k) {
+        const int64_t i = base + (int64_t)k * kAgentThreads + threadIdx.x;
+        if (i < M) {
+            const int cell = cl[i];
+            const int w = win[cell];
+            const bool alive = ag[2 * M + i] > 0.0;
+            const double dx = ac[i], dy = ac[M + i], dep = ac[2 * M + i];
+            if (alive && w == (int)i) chem[cell] = chem[cell] + dep;   // winner's deposit lands once
+            const double consumed = (rate_feed * food[cell]) * ((w >= 0) ? 1.0 : 0.0);   // Q1, Q7
+            const double burned = w_dep * fabs(dep) + w_dist * sqrt(dx * dx + dy * dy);
+            const double gained = consumed - burned;
+            ag[3 * M + i] += gained;
+            gain_sum += gained;
+            alive_cnt += alive ? 1 : 0;
+        }
+    }
+    __shared__ double s_gain[kAgentThreads / 32];
+    __shared__ int s_alive[kAgentThreads / 32];
+    gain_sum = warp_sum(gain_sum);
+    alive_cnt = warp_sum(alive_cnt);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_gain[wid] = gain_sum;
+        s_alive[wid] = alive_cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double g = 0.0;
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < kAgentThreads / 32; ++k) {
+            g += s_gain[k];
+            n += s_alive[k];
+        }
+        part_gain[blockIdx.x] = g;
+        part_alive[blockIdx.x] = n;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __restrict__ part_alive,
+                      int nblk, double* __restrict__ reward, int64_t* __restrict__ alive) {
+    const int b = blockIdx.x;
+    double g = 0.0;
+    long long n = 0;
+    for (int k = threadIdx.x; k < nblk; k += 256) {
+        g += part_gain[(int64_t)b * nblk + k];
+        n += part_alive[(int64_t)b * nblk + k];
+    }
+    __shared__ double s_g[8];
+    __shared__ long long s_n[8];
+    g = warp_sum(g);
+    n = warp_sum(n);
+    if ((threadIdx.x & 31) == 0) {
+        s_g[threadIdx.x >> 5] = g;
+        s_n[threadIdx.x >> 5] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double gg = 0.0;
+        long long nn = 0;
+        for (int k = 0; k < 8; ++k) {
+            gg += s_g[k];
+            nn += s_n[k];
+        }
+        reward[b] = gg;
+        alive[b] = nn;
+    }
+}
+
+}  // namespace die

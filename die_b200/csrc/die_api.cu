@@ -1,0 +1,332 @@
+// die_api.cu -- the C ABI of libdie_sm100a.so (declared in include/die_b200.h): argument
+// checking, workspace ownership, launch geometry.  No torch, no C++ types in signatures.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "die_agent_kernels.cuh"
+#include "die_field_kernels.cuh"
+
+using namespace die;
+
+// ------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define DIE_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (expr);                                                    \
+        if (e_ != cudaSuccess) return fail(DIE_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define DIE_REQUIRE(cond)                                                           \
+    do {                                                                            \
+        if (!(cond)) return fail(DIE_E_INVALID, "invalid argument: %s%s", #cond);   \
+    } while (0)
+
+struct die_env {
+    int32_t H, W, B;
+    int64_t M;
+    die_dynamics_t dyn;
+    int32_t* winner;       // [B][H*W]  claim table, -1 = empty
+    int32_t* cells;        // [B][M]    linear cell of every slot after the move
+    double* part_gain;     // [B][nblk]
+    int32_t* part_alive;   // [B][nblk]
+    int nblk;
+    double* action_stage;  // [B][3][M] device staging for die_env_step_host (lazy)
+    double* reward_dev;    // [B] (host path)
+    int64_t* alive_dev;    // [B] (host path)
+    int num_sms;
+    int profiling;                     // record events between the step's kernels
+    int prof_steps;                    // steps recorded so far
+    cudaEvent_t* prof_events;          // [DIE_MAX_PROFILED_STEPS][DIE_NUM_STEP_KERNELS + 1]
+};
+
+static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
+    if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS)
+        cudaEventRecord(e->prof_events[(size_t)e->prof_steps * (DIE_NUM_STEP_KERNELS + 1) + k], st);
+}
+
+extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
+extern "C" const char* die_last_error(void) { return g_err; }
+
+static int check_dynamics(const die_dynamics_t* d) {
+    DIE_REQUIRE(d != nullptr);
+    DIE_REQUIRE(d->blur_radius >= 0 && d->blur_radius <= DIE_MAX_RADIUS);
+    DIE_REQUIRE(d->boundary >= DIE_BOUNDARY_WRAP && d->boundary <= DIE_BOUNDARY_NONE);
+    return DIE_OK;
+}
+
+static inline int grid_for(int64_t total, int threads, int num_sms) {
+    // enough CTAs for full occupancy, grid-stride beyond that: a multiple of the SM count
+    const int64_t want = (total + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms * 32;
+    int64_t g = want < cap ? want : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
+                              const die_dynamics_t* dyn, die_env_t** out) {
+    DIE_REQUIRE(out != nullptr);
+    *out = nullptr;
+    DIE_REQUIRE(H >= 2 && W >= 2);
+    DIE_REQUIRE(M >= 1 && M <= 0x7fffffffLL);
+    DIE_REQUIRE(B >= 1);
+    DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
+    if (int rc = check_dynamics(dyn)) return rc;
+
+    die_env* e = new (std::nothrow) die_env();
+    if (e == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
+    memset(e, 0, sizeof(*e));
+    e->H = H; e->W = W; e->B = B; e->M = M;
+    e->dyn = *dyn;
+    e->nblk = (int)((M + (int64_t)kAgentThreads * kFeedItems - 1) / ((int64_t)kAgentThreads * kFeedItems));
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t C = (size_t)H * W;
+    if (err == cudaSuccess) err = cudaMalloc(&e->winner, sizeof(int32_t) * C * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->cells, sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double) * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->alive_dev, sizeof(int64_t) * B);
+    if (err == cudaSuccess) err = cudaMemset(e->winner, 0xFF, sizeof(int32_t) * C * B);
+    if (err == cudaSuccess) err = cudaMemset(e->cells, 0, sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        die_env_destroy(e);
+        return fail(DIE_E_CUDA, "die_env_create: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return DIE_OK;
+}
+
+extern "C" int die_env_destroy(die_env_t* e) {
+    if (e == nullptr) return DIE_OK;
+    cudaFree(e->winner);
+    cudaFree(e->cells);
+    cudaFree(e->part_gain);
+    cudaFree(e->part_alive);
+    cudaFree(e->action_stage);
+    cudaFree(e->reward_dev);
+    cudaFree(e->alive_dev);
+    if (e->prof_events != nullptr) {
+        for (size_t k = 0; k < (size_t)DIE_MAX_PROFILED_STEPS * (DIE_NUM_STEP_KERNELS + 1); ++k)
+            if (e->prof_events[k]) cudaEventDestroy(e->prof_events[k]);
+        delete[] e->prof_events;
+    }
+    delete e;
+    return DIE_OK;
+}
+
+extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
+    DIE_REQUIRE(e != nullptr);
+    if (int rc = check_dynamics(dyn)) return rc;
+    e->dyn = *dyn;
+    return DIE_OK;
+}
+
+extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells : nullptr; }
+
+extern "C" int die_env_set_profiling(die_env_t* e, int32_t on) {
+    DIE_REQUIRE(e != nullptr);
+    if (on && e->prof_events == nullptr) {
+        const size_t n = (size_t)DIE_MAX_PROFILED_STEPS * (DIE_NUM_STEP_KERNELS + 1);
+        e->prof_events = new (std::nothrow) cudaEvent_t[n]();
+        if (e->prof_events == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
+        for (size_t k = 0; k < n; ++k) DIE_CUDA(cudaEventCreate(&e->prof_events[k]));
+    }
+    e->profiling = on ? 1 : 0;
+    e->prof_steps = 0;
+    return DIE_OK;
+}
+
+extern "C" int die_env_kernel_times(die_env_t* e, double* ms_out, int64_t* steps_out) {
+    DIE_REQUIRE(e != nullptr && ms_out != nullptr && steps_out != nullptr);
+    for (int k = 0; k < DIE_NUM_STEP_KERNELS; ++k) ms_out[k] = 0.0;
+    *steps_out = e->prof_steps;
+    for (int s = 0; s < e->prof_steps; ++s) {
+        cudaEvent_t* ev = e->prof_events + (size_t)s * (DIE_NUM_STEP_KERNELS + 1);
+        DIE_CUDA(cudaEventSynchronize(ev[DIE_NUM_STEP_KERNELS]));
+        for (int k = 0; k < DIE_NUM_STEP_KERNELS; ++k) {
+            float ms = 0.f;
+            DIE_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            ms_out[k] += (double)ms;
+        }
+    }
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// field pass launch
+// ------------------------------------------------------------------------------------------
+template <int R>
+static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
+    constexpr int TH = 32, TW = 64, NT = 256;
+    FieldArgs a = fa;
+    a.tiles_i = (a.H + TH - 1) / TH;
+    a.tiles_j = (a.W + TW - 1) / TW;
+    const size_t smem = sizeof(double) * (size_t)((TH + 2 * R) * (TW + 2 * R) + TH * (TW + 2 * R));
+    auto kern = field_step_kernel<R, TH, TW, NT>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int64_t grid = (int64_t)a.tiles_i * a.tiles_j * B;
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_field_any(const die_env* e, const double* min, double* mout, cudaStream_t st) {
+    FieldArgs a;
+    memset(&a, 0, sizeof(a));
+    a.medium_in = min;
+    a.medium_out = mout;
+    a.winner = e->winner;
+    a.H = e->H;
+    a.W = e->W;
+    a.rate_feed = e->dyn.rate_feed;
+    a.keep = 1.0 - e->dyn.rate_decay_chem;
+    a.food_infinite = e->dyn.food_infinite;
+    for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
+    switch (e->dyn.blur_radius) {
+        case 0: {
+            const int64_t total = (int64_t)e->H * e->W * e->B;
+            field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
+            return cudaGetLastError();
+        }
+        case 1: return launch_field<1>(a, e->B, st);
+        case 2: return launch_field<2>(a, e->B, st);
+        case 3: return launch_field<3>(a, e->B, st);
+        case 4: return launch_field<4>(a, e->B, st);
+        case 5: return launch_field<5>(a, e->B, st);
+        case 6: return launch_field<6>(a, e->B, st);
+        case 7: return launch_field<7>(a, e->B, st);
+        case 8: return launch_field<8>(a, e->B, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// Env.step
+// ------------------------------------------------------------------------------------------
+extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
+                            double* agents, const double* action,
+                            double* reward_dev, int64_t* alive_dev, void* stream) {
+    DIE_REQUIRE(e != nullptr);
+    DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out);
+    DIE_REQUIRE(agents != nullptr && action != nullptr);
+    DIE_REQUIRE(reward_dev != nullptr && alive_dev != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = e->M * e->B;
+
+    prof_mark(e, 0, st);
+    move_claim_kernel<<<grid_for(total, kAgentThreads, e->num_sms), kAgentThreads, 0, st>>>(
+        agents, action, e->winner, e->cells, e->H, e->W, e->M, total, e->dyn.boundary);
+    DIE_CUDA(cudaGetLastError());
+    prof_mark(e, 1, st);
+
+    deposit_feed_kernel<<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
+        agents, action, medium_in, e->winner, e->cells, e->part_gain, e->part_alive,
+        e->H, e->W, e->M, e->nblk, e->dyn.rate_feed, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
+    DIE_CUDA(cudaGetLastError());
+    prof_mark(e, 2, st);
+
+    DIE_CUDA(launch_field_any(e, medium_in, medium_out, st));
+    prof_mark(e, 3, st);
+
+    finalize_stats_kernel<<<e->B, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, reward_dev, alive_dev);
+    DIE_CUDA(cudaGetLastError());
+    prof_mark(e, 4, st);
+    if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
+    return DIE_OK;
+}
+
+extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
+                                 double* agents, const double* action_host,
+                                 double* agents_host, double* medium_host,
+                                 double* reward_host, int64_t* alive_host, void* stream) {
+    DIE_REQUIRE(e != nullptr && action_host != nullptr);
+    DIE_REQUIRE(reward_host != nullptr && alive_host != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t act_bytes = sizeof(double) * 3 * (size_t)e->M * e->B;
+    if (e->action_stage == nullptr) DIE_CUDA(cudaMalloc(&e->action_stage, act_bytes));
+    DIE_CUDA(cudaMemcpyAsync(e->action_stage, action_host, act_bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = die_env_step(e, medium_in, medium_out, agents, e->action_stage, e->reward_dev, e->alive_dev, stream))
+        return rc;
+    if (agents_host != nullptr)
+        DIE_CUDA(cudaMemcpyAsync(agents_host, agents, sizeof(double) * 4 * (size_t)e->M * e->B,
+                                 cudaMemcpyDeviceToHost, st));
+    if (medium_host != nullptr)
+        DIE_CUDA(cudaMemcpyAsync(medium_host, medium_out, sizeof(double) * 3 * (size_t)e->H * e->W * e->B,
+                                 cudaMemcpyDeviceToHost, st));
+    DIE_CUDA(cudaMemcpyAsync(reward_host, e->reward_dev, sizeof(double) * e->B, cudaMemcpyDeviceToHost, st));
+    DIE_CUDA(cudaMemcpyAsync(alive_host, e->alive_dev, sizeof(int64_t) * e->B, cudaMemcpyDeviceToHost, st));
+    DIE_CUDA(cudaStreamSynchronize(st));
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Agent.forward
+// ------------------------------------------------------------------------------------------
+static int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+extern "C" int die_brownian_forward(const double* agents, double* action, int64_t M, int32_t B,
+                                    double move_scale, double deposit_scale,
+                                    const double* u, uint64_t seed, uint64_t step, void* stream) {
+    DIE_REQUIRE(agents != nullptr && action != nullptr);
+    DIE_REQUIRE(M >= 1 && B >= 1);
+    const int64_t total = M * B;
+    brownian_forward_kernel<<<grid_for(total, kAgentThreads, sm_count()), kAgentThreads, 0, (cudaStream_t)stream>>>(
+        agents, action, M, total, move_scale, deposit_scale, u, seed, step);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
+                                 double dx, double dy, double deposit, void* stream) {
+    DIE_REQUIRE(action != nullptr);
+    DIE_REQUIRE(M >= 1 && B >= 1);
+    const int64_t total = M * B;
+    const_forward_kernel<<<grid_for(total, kAgentThreads, sm_count()), kAgentThreads, 0, (cudaStream_t)stream>>>(
+        action, M, total, dx, dy, deposit);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+extern "C" int die_gradient_forward(const die_gradient_params_t* p,
+                                    int32_t H, int32_t W, int64_t M, int32_t B,
+                                    const double* agents, const double* medium,
+                                    double* theta, double* prev_grad, double* action,
+                                    const uint8_t* coin, const double* noise,
+                                    int32_t* sense_cells,
+                                    uint64_t seed, uint64_t step, void* stream) {
+    DIE_REQUIRE(p != nullptr);
+    DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
+    DIE_REQUIRE(agents != nullptr && medium != nullptr && theta != nullptr && action != nullptr);
+    // prev_grad may only be omitted when it cannot influence any output
+    DIE_REQUIRE(prev_grad != nullptr || (p->inertia == 0.0 && p->noise_scale == 0.0));
+    GradientArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = *p;
+    a.H = H; a.W = W; a.M = M; a.total = M * B;
+    a.agents = agents; a.medium = medium; a.theta = theta; a.prev_grad = prev_grad;
+    a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
+    a.seed = seed; a.step = step;
+    const int grid = grid_for(a.total, kAgentThreads, sm_count());
+    if (p->discrete_turn)
+        gradient_forward_kernel<true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    else
+        gradient_forward_kernel<false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}

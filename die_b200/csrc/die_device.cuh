@@ -1,0 +1,133 @@
+// die_device.cuh -- device-side arithmetic shared by the agent and field kernels.
+//
+// Every function here restates one numpy / pandas expression of the reference in IEEE
+// float64 with the SAME operation order, so integer results (cell indices, turn
+// decisions) are bit-exact.  The library is compiled with -fmad=false: no mul+add is ever
+// contracted into an FMA, as in numpy.  Citations are file:line under /root/reference.
+#pragma once
+#include <cstdint>
+#include <cfloat>
+#include <cuda_runtime.h>
+
+namespace die {
+
+constexpr double kPi    = 3.141592653589793;    // np.pi
+constexpr double kTwoPi = 6.283185307179586;    // 2 * np.pi (exact doubling)
+
+// ---- nearest grid cell ------------------------------------------------------------------
+// xarray .sel(method='nearest') -> pandas.Index.get_indexer(method='nearest') on
+// np.linspace(0, 1, n)  (core/utils.py:39-54, core/data_init.py:99-100).
+// g(i) = i * (1/(n-1)), g(n-1) = 1.0 exactly.  L = last g <= c, R = first g >= c; L wins iff
+// (c - g[L]) < (g[R] - c) strictly; below/above range clamps.
+struct Axis {
+    int    n;
+    double step;     // 1.0 / (n - 1)
+    double nm1;      // (double)(n - 1)
+};
+
+__host__ __device__ inline Axis make_axis(int n) {
+    Axis a;
+    a.n = n;
+    a.nm1 = (double)(n - 1);
+    a.step = 1.0 / a.nm1;
+    return a;
+}
+
+__device__ __forceinline__ double grid_coord(const Axis& a, int i) {
+    return (i >= a.n - 1) ? 1.0 : __dmul_rn((double)i, a.step);
+}
+
+__device__ __forceinline__ int nearest_cell(double c, const Axis& a) {
+    if (!(c > 0.0)) return 0;                 // c <= 0 (and NaN): first cell
+    if (c >= 1.0) return a.n - 1;
+    int i = (int)(c * a.nm1);                 // floor estimate, off by at most one
+    if (i > a.n - 2) i = a.n - 2;
+    while (i > 0 && grid_coord(a, i) > c) --i;
+    while (i < a.n - 2 && grid_coord(a, i + 1) <= c) ++i;
+    const double gl = grid_coord(a, i);
+    if (gl == c) return i;
+    const double gr = grid_coord(a, i + 1);
+    return (__dsub_rn(c, gl) < __dsub_rn(gr, c)) ? i : i + 1;
+}
+
+// ---- numpy float remainder ----------------------------------------------------------------
+// exact fmod for |a| < 2|b| (Sterbenz), generic fmod otherwise
+__device__ __forceinline__ double fmod_small(double a, double b) {
+    const double fa = fabs(a), fb = fabs(b);
+    if (fa < fb) return a;
+    if (fa < 2.0 * fb) return copysign(__dsub_rn(fa, fb), a);
+    return fmod(a, b);
+}
+
+// np.remainder(a, b): sign of b; exact zero gets the sign of b.
+__device__ __forceinline__ double np_remainder(double a, double b) {
+    double m = fmod_small(a, b);
+    if (m != 0.0) {
+        if ((b < 0.0) != (m < 0.0)) m = __dadd_rn(m, b);
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+// coords % 1.  (core/env.py:155) -- returns exactly 1.0 for tiny negatives.
+__device__ __forceinline__ double mod1(double a) { return np_remainder(a, 1.0); }
+
+// renormalize_radians (core/utils.py:177-179): (r - pi) % (-2 pi) + pi, in (-pi, pi].
+__device__ __forceinline__ double renormalize_radians(double r) {
+    return __dadd_rn(np_remainder(__dsub_rn(r, kPi), -kTwoPi), kPi);
+}
+
+// np.angle(x + np.multiply(1j, y))  (core/utils.py:158-168).  The complex construction
+// yields re = x + (0*y - 0), im = 0 + y, which is what makes (-0., -0.) -> +pi and every
+// other all-zero pair -> 0.
+__device__ __forceinline__ double angle_xy(double x, double y) {
+    const double re = __dadd_rn(x, __dsub_rn(__dmul_rn(0.0, y), 0.0));
+    const double im = __dadd_rn(0.0, y);
+    return atan2(im, re);
+}
+
+// np.nan_to_num(a / n)  (core/agent/gradient.py:62)
+__device__ __forceinline__ double div_nan_to_num(double a, double n) {
+    double q = a / n;
+    if (isnan(q)) return 0.0;
+    if (isinf(q)) return copysign(DBL_MAX, q);
+    return q;
+}
+
+// ---- Philox4x32-10 counter RNG (perf mode; validation mode injects the host's draws) -------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 philox_draw(uint64_t seed, uint64_t step, uint64_t slot, uint32_t stream) {
+    // counter = (slot lo, slot hi, step lo, step hi ^ stream<<24); key = seed
+    const uint4 ctr = make_uint4((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)step,
+                                 (uint32_t)(step >> 32) ^ (stream << 24));
+    return philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// uniform in [0, 1) with 53 random bits, like numpy's random_sample
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ---- block reduction (fixed order => deterministic) ------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace die

@@ -1,0 +1,81 @@
+"""Initial-state construction on the host (reference: core/data_init.py:92-253,
+core/utils.py:140-151, core/env.py:74-86).  Init-time only, not part of the per-step path.
+
+Draw order on the GLOBAL legacy numpy RNG follows the reference, so ``np.random.seed(s)``
+before ``Env(...)`` reproduces the same occupancy / agent_food draws:
+    with_agents:         random_sample(field_size).round(3)          core/data_init.py:222-224
+    agents_from_medium:  0.9 * random_sample(A).round(3) + 0.1       core/data_init.py:141
+The food texture is a vectorised single-frequency gradient noise standing in for the
+reference's unseeded pure-Python ``PerlinNoise(octaves=8)`` (not reproducible even there).
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def get_random(size, a=0., b=1.) -> np.ndarray:
+    """core/data_init.py:167-169."""
+    return (b - a) * np.random.random_sample(size).round(3) + a
+
+
+def gradient_noise(field_size: Tuple[int, int], periods: int = 8, seed: Optional[int] = None) -> np.ndarray:
+    """Perlin-style gradient noise on linspace(0,1)^2: `periods` lattice cells per axis,
+    quintic fade, rounded to 3 dp (core/data_init.py:190-196)."""
+    h, w = field_size
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0., 2. * np.pi, size=(periods + 2, periods + 2))
+    gx, gy = np.cos(ang), np.sin(ang)
+    xs = np.linspace(0., 1., h) * periods
+    ys = np.linspace(0., 1., w) * periods
+    x0 = np.floor(xs).astype(np.int64)
+    y0 = np.floor(ys).astype(np.int64)
+    fx = (xs - x0)[:, None]
+    fy = (ys - y0)[None, :]
+    x0 = x0[:, None]
+    y0 = y0[None, :]
+
+    def fade(t):
+        return t * t * t * (t * (t * 6. - 15.) + 10.)
+
+    def corner(ix, iy, dx, dy):
+        return gx[ix, iy] * dx + gy[ix, iy] * dy
+
+    n00 = corner(x0, y0, fx, fy)
+    n10 = corner(x0 + 1, y0, fx - 1., fy)
+    n01 = corner(x0, y0 + 1, fx, fy - 1.)
+    n11 = corner(x0 + 1, y0 + 1, fx - 1., fy - 1.)
+    u, v = fade(fx), fade(fy)
+    nx0 = n00 + u * (n10 - n00)
+    nx1 = n01 + u * (n11 - n01)
+    return (nx0 + v * (nx1 - nx0)).round(3)
+
+
+def _mask(sampled, mask_below=0.0, mask_above=1.0):
+    """core/data_init.py:181-185."""
+    return sampled * ((mask_below <= sampled) & (sampled <= mask_above))
+
+
+def init_medium(field_size: Tuple[int, int], agent_ratio: float,
+                noise_seed: Optional[int] = None, periods: int = 8) -> np.ndarray:
+    """core/env.py:74-79 -> float64 [3, H, W] (agents, env_food, chem1)."""
+    medium = np.zeros((3, *field_size))
+    medium[1] = _mask(gradient_noise(field_size, periods, noise_seed), mask_above=1.0)
+    medium[0] = np.ceil(_mask(get_random(field_size), mask_above=agent_ratio))
+    return medium
+
+
+def agents_from_medium(medium: np.ndarray, max_agents: Optional[int] = None,
+                       food_ratio: float = 1.0) -> np.ndarray:
+    """core/data_init.py:132-150: alive agents in row-major nonzero order in slots 0..A-1,
+    exactly on grid coordinates; the remaining slots are all-zero ghosts at (0, 0)."""
+    h, w = medium.shape[-2:]
+    ix, iy = (medium[0] > 0).nonzero()
+    n_alive = ix.shape[0]
+    if not max_agents:
+        max_agents = h * w
+    agents = np.zeros((4, max_agents))
+    agents[0, :n_alive] = np.linspace(0., 1., h)[ix]
+    agents[1, :n_alive] = np.linspace(0., 1., w)[iy]
+    agents[2, :n_alive] = 1.
+    agents[3, :n_alive] = get_random(n_alive, 0.1, food_ratio)
+    return agents

@@ -1,0 +1,371 @@
+"""Env / Dynamics -- drop-in for the reference's ``core/env.py`` on the per-step path.
+
+Same class names, constructor, ``step`` signature and return tuple as the reference
+(core/env.py:42-131).  State lives in HBM as float64 torch tensors in the reference's
+channel-major layout and every ``step`` is four kernel launches of ``libdie_sm100a.so``
+through its C ABI (``include/die_b200.h``): move+claim, deposit+feed+reduce, the fused
+field pass, and the stats finalisation.  There is no CPU fallback.
+
+Differences a caller of the reference can observe (all documented in DESIGN.md):
+  * obs / action are ``torch`` CUDA tensors (or pinned ``numpy`` arrays on the host-buffer
+    path) instead of ``xarray.DataArray``; ``die_b200.base_types.channel`` replaces
+    ``.sel(channel=...)``.
+  * ``obs[1]`` (the medium) is a zero-copy view of the env's current buffer, valid until the
+    next ``step`` (the reference makes a fresh copy, core/env.py:290-294); ``obs[0]`` is the
+    env's live ``agents`` tensor exactly as in the reference (core/env.py:298).
+  * ``batch=B`` runs B independent environments in one set of launches (leading axis B).
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from enum import Enum
+from typing import Callable, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import data_init
+from .base_types import ActType, ObsType
+
+
+class BoundaryCondition(Enum):
+    """core/env.py:24-26."""
+    wrap = 'wrap'
+    limit = 'limit'
+
+
+def linear_action_cost(action, weights=(0.02, 0.01)):
+    """core/env.py:29-35.  Inside ``Env.step`` this is evaluated in the feed kernel; the
+    Python body exists so callers can still evaluate the operator on an action tensor."""
+    act = torch.as_tensor(action)
+    dist = torch.sqrt(act[..., 0, :] * act[..., 0, :] + act[..., 1, :] * act[..., 1, :])
+    return weights[0] * act[..., 2, :].abs() + weights[1] * dist
+
+
+def zero_cost(action):
+    """core/env.py:38-39."""
+    act = torch.as_tensor(action)
+    return torch.zeros_like(act[..., 0, :])
+
+
+def identity_food_flow(food):
+    """Default ``op_food_flow`` (core/env.py:45)."""
+    return food
+
+
+linear_action_cost._die_weights = (0.02, 0.01)
+zero_cost._die_weights = (0.0, 0.0)
+
+
+@dataclass
+class Dynamics:
+    """core/env.py:42-61 (same fields, same defaults)."""
+    op_action_cost: Callable = linear_action_cost
+    op_food_flow: Callable = identity_food_flow
+    rate_feed: float = 0.1
+    rate_decay_chem: float = 0.1
+    boundary: BoundaryCondition = BoundaryCondition.wrap
+    diffuse_mode: str = 'wrap'
+    diffuse_sigma: float = .5
+
+    apply_sense_mask: bool = False
+    strict_cost: bool = True        # declared but unused by the reference (core/env.py:55)
+    food_infinite: bool = False
+    agents_die: bool = False
+    agents_born: bool = False       # unimplemented in the reference (core/env.py:256-261)
+
+    init_agent_ratio: float = 0.1
+
+
+def gaussian_kernel1d(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """The weights ``scipy.ndimage.gaussian_filter1d`` builds (what ``skimage.filters.gaussian``
+    uses, core/env.py:140-143): radius = int(truncate * sigma + .5)."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
+    weights = getattr(d.op_action_cost, '_die_weights', None)
+    if weights is None:
+        raise NotImplementedError(
+            "op_action_cost must be die_b200.env.linear_action_cost or zero_cost: the cost is "
+            "evaluated inside the CUDA feed kernel, arbitrary Python operators are not supported")
+    if d.op_food_flow is not identity_food_flow and d.op_food_flow is not None:
+        raise NotImplementedError("op_food_flow other than identity is not on the GPU path yet")
+    if d.diffuse_mode != 'wrap':
+        raise NotImplementedError("only diffuse_mode='wrap' (the reference default) is implemented")
+    if d.apply_sense_mask or d.agents_die:
+        raise NotImplementedError("apply_sense_mask / agents_die are off by default in the reference and "
+                                  "not implemented on the GPU path")
+    c = _lib.DieDynamics()
+    c.rate_feed = d.rate_feed
+    c.rate_decay_chem = d.rate_decay_chem
+    c.cost_w_deposit, c.cost_w_dist = weights
+    w = gaussian_kernel1d(d.diffuse_sigma)
+    radius = (len(w) - 1) // 2
+    if radius > _lib.DIE_MAX_RADIUS:
+        raise NotImplementedError(f"diffuse_sigma={d.diffuse_sigma} needs blur radius {radius} > {_lib.DIE_MAX_RADIUS}")
+    for k, v in enumerate(w):
+        c.blur_w[k] = float(v)
+    c.blur_radius = radius
+    if d.boundary == BoundaryCondition.wrap:
+        c.boundary = _lib.BOUNDARY_WRAP
+    elif d.boundary == BoundaryCondition.limit:
+        c.boundary = _lib.BOUNDARY_LIMIT
+    else:
+        logging.warning(f'Unfamiliar boundary condition: {d.boundary}! Doing nothing with boundary...')
+        c.boundary = _lib.BOUNDARY_NONE
+    c.food_infinite = int(bool(d.food_infinite))
+    return c
+
+
+class Env:
+    """core/env.py:64-298."""
+
+    def __init__(self,
+                 field_size: Tuple[int, int],
+                 dynamics: Optional[Dynamics] = None,
+                 *,
+                 batch: Optional[int] = None,
+                 device: Optional[Union[int, str, torch.device]] = None,
+                 noise_seed: Optional[int] = None,
+                 init_state: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("die_b200.Env needs a CUDA device: there is no CPU fallback")
+        self._lib = _lib.load()
+        self._field_size = (int(field_size[0]), int(field_size[1]))
+        self.dynamics = dynamics or Dynamics()
+        self._batched = batch is not None
+        self._B = int(batch) if batch is not None else 1
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self._noise_seed = noise_seed
+        self._handle = None
+        self._host = None
+        self._init_data(self._field_size, init_state)
+
+    # -- construction ---------------------------------------------------------------------
+    def _init_data(self, field_size, init_state=None):
+        """core/env.py:74-86."""
+        h, w = field_size
+        B = self._B
+        if init_state is None:
+            mediums, agentss = [], []
+            for b in range(B):
+                seed = None if self._noise_seed is None else self._noise_seed + b
+                m = data_init.init_medium(field_size, self.dynamics.init_agent_ratio, noise_seed=seed)
+                mediums.append(m)
+                agentss.append(data_init.agents_from_medium(m))
+            medium, agents = np.stack(mediums), np.stack(agentss)
+        else:
+            medium, agents = (np.asarray(a, dtype=np.float64) for a in init_state)
+            medium = medium.reshape(B, 3, h, w)
+            agents = agents.reshape(B, 4, -1)
+        self._M = int(agents.shape[-1])
+        with torch.cuda.device(self.device):
+            self._medium_buf = [torch.from_numpy(np.ascontiguousarray(medium)).to(self.device),
+                                torch.empty((B, 3, h, w), dtype=torch.float64, device=self.device)]
+            self._cur = 0
+            self._agents = torch.from_numpy(np.ascontiguousarray(agents)).to(self.device)
+            self._reward_dev = torch.zeros(B, dtype=torch.float64, device=self.device)
+            self._alive_dev = torch.zeros(B, dtype=torch.int64, device=self.device)
+            self._stats_host = torch.zeros(2 * B, dtype=torch.float64).pin_memory()
+            if self._handle is not None:
+                _lib.check(self._lib.die_env_destroy(self._handle))
+                self._handle = None
+            handle = _lib.C.c_void_p()
+            cdyn = _dynamics_to_c(self.dynamics)
+            _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
+            self._handle = handle
+            self._alive_count = (self._agents[:, 2] > 0).sum(dim=1)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_handle', None) is not None:
+                self._lib.die_env_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None) -> Tuple[ObsType, dict]:
+        """core/env.py:94-99 (``seed`` is ignored there too)."""
+        self._init_data(self._field_size)
+        return self._get_current_obs, {}
+
+    # -- state access ---------------------------------------------------------------------
+    def _unbatch(self, t):
+        return t if self._batched else t[0]
+
+    @property
+    def medium(self) -> torch.Tensor:
+        return self._unbatch(self._medium_buf[self._cur])
+
+    @property
+    def agents(self) -> torch.Tensor:
+        return self._unbatch(self._agents)
+
+    @property
+    def field_size(self) -> Tuple[int, int]:
+        return self._field_size
+
+    @property
+    def max_agents(self) -> int:
+        return self._M
+
+    @property
+    def batch(self) -> int:
+        return self._B
+
+    @property
+    def _num_alive_agents(self):
+        """core/env.py:263-265."""
+        n = (self._agents[:, 2] > 0).sum(dim=1)
+        return n.cpu().numpy() if self._batched else int(n.item())
+
+    @property
+    def _get_current_obs(self) -> ObsType:
+        """core/env.py:296-298."""
+        return self.agents, self.medium
+
+    def get_state(self) -> Tuple[np.ndarray, np.ndarray]:
+        """Host copies (medium, agents) -- checkpoint / parity aid (the reference never saves Env state)."""
+        return self.medium.cpu().numpy(), self.agents.cpu().numpy()
+
+    def set_state(self, medium=None, agents=None) -> None:
+        if medium is not None:
+            src = torch.as_tensor(np.asarray(medium, dtype=np.float64)).reshape(self._medium_buf[0].shape)
+            self._medium_buf[self._cur].copy_(src)
+        if agents is not None:
+            src = torch.as_tensor(np.asarray(agents, dtype=np.float64)).reshape(self._agents.shape)
+            self._agents.copy_(src)
+
+    def last_cells(self) -> torch.Tensor:
+        """int32 [B, M] (or [M]) linear cell index ix*W+iy of every slot after the last move
+        (validation aid; a copy of the library's per-slot cell cache)."""
+        view = _DevicePtrView(self._lib.die_env_cells(self._handle), (self._B, self._M), '<i4')
+        with torch.cuda.device(self.device):
+            out = torch.as_tensor(view, device=self.device).clone()
+        return self._unbatch(out)
+
+    # -- the step -------------------------------------------------------------------------
+    def _check_action(self, action: torch.Tensor) -> torch.Tensor:
+        if not isinstance(action, torch.Tensor):
+            raise TypeError("action must be a torch CUDA tensor (device path) or a numpy array (host path)")
+        expect = (self._B, 3, self._M) if self._batched else (3, self._M)
+        if tuple(action.shape) != expect:
+            raise ValueError(f"action shape {tuple(action.shape)} != {expect}")
+        if action.dtype != torch.float64 or action.device != self.device:
+            raise ValueError("action must be float64 on the env's device")
+        return action if action.is_contiguous() else action.contiguous()
+
+    def step_async(self, action: ActType):
+        """``step`` without the host synchronisation: returns (obs, reward_dev[B], alive_dev[B])
+        as device tensors, everything enqueued on the current stream."""
+        action = self._check_action(action)
+        nxt = 1 - self._cur
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._lib.die_env_step(
+                self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
+                self._agents.data_ptr(), action.data_ptr(),
+                self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), stream))
+        self._cur = nxt
+        return self._get_current_obs, self._reward_dev, self._alive_dev
+
+    def step(self, action: ActType):
+        """core/env.py:101-131 -> (obs, reward, terminated, truncated, info)."""
+        if isinstance(action, np.ndarray):
+            return self._step_host(action)
+        obs, _, _ = self.step_async(action)
+        B = self._B
+        with torch.cuda.device(self.device):
+            self._stats_host[:B].copy_(self._reward_dev, non_blocking=True)
+            self._stats_host[B:].copy_(self._alive_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return (obs, *self._summarise(self._stats_host[:B].numpy().copy(),
+                                      self._stats_host[B:].numpy().astype(np.int64)))
+
+    def _summarise(self, reward: np.ndarray, alive: np.ndarray):
+        """core/env.py:117-131."""
+        if self._batched:
+            mean = np.divide(reward, alive, out=np.zeros_like(reward), where=alive > 0)
+            info = {'num_agents': alive, 'reward': np.round(reward, 3), 'mean_reward': np.round(mean, 5)}
+            return reward, bool((alive == 0).all()), False, info
+        r, n = float(reward[0]), int(alive[0])
+        mean = r / n if n > 0 else 0.
+        info = {'num_agents': n, 'reward': np.round(r, 3), 'mean_reward': np.round(mean, 5)}
+        return r, n == 0, False, info
+
+    # -- host-buffer path (what a host-side caller of the reference would bind) -----------------
+    def host_buffers(self):
+        """Pinned host arrays (action, agents, medium x2) used by the host path.  Filling
+        ``action`` in place and passing it to ``step`` avoids one host memcpy."""
+        if self._host is None:
+            B, M = self._B, self._M
+            h, w = self._field_size
+            mk = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
+            self._host = {
+                'action': mk(B, 3, M), 'agents': mk(B, 4, M),
+                'medium': [mk(B, 3, h, w), mk(B, 3, h, w)], 'flip': 0,
+                'reward': mk(B), 'alive': torch.empty(B, dtype=torch.int64).pin_memory(),
+            }
+        return self._host
+
+    def _step_host(self, action: np.ndarray):
+        hb = self.host_buffers()
+        B, M = self._B, self._M
+        act_t = hb['action']
+        act_np = act_t.numpy()
+        src = np.asarray(action, dtype=np.float64).reshape(B, 3, M)
+        if not np.shares_memory(src, act_np):
+            np.copyto(act_np, src)
+        hb['flip'] ^= 1
+        med_t = hb['medium'][hb['flip']]
+        nxt = 1 - self._cur
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._lib.die_env_step_host(
+                self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
+                self._agents.data_ptr(), act_t.data_ptr(),
+                hb['agents'].data_ptr(), med_t.data_ptr(),
+                hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
+        self._cur = nxt
+        obs = (self._unbatch(hb['agents'].numpy()), self._unbatch(med_t.numpy()))
+        return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))
+
+    def host_io_bytes_per_step(self) -> Tuple[int, int]:
+        """(H2D, D2H) bytes one host-path ``step`` moves."""
+        B, M = self._B, self._M
+        h, w = self._field_size
+        return 8 * B * 3 * M, 8 * B * (4 * M + 3 * h * w) + 16 * B
+
+    # -- measurement aid ----------------------------------------------------------------------
+    STEP_KERNELS = ('move_claim', 'deposit_feed', 'field_step', 'finalize_stats')
+
+    def set_profiling(self, on: bool) -> None:
+        """Record CUDA events between the step's kernels (bench.py's per-kernel roofline)."""
+        _lib.check(self._lib.die_env_set_profiling(self._handle, int(on)))
+
+    def kernel_times(self):
+        """-> ({kernel: accumulated ms}, profiled steps) since profiling was enabled."""
+        ms = (_lib.C.c_double * len(self.STEP_KERNELS))()
+        n = _lib.C.c_int64()
+        _lib.check(self._lib.die_env_kernel_times(self._handle, ms, _lib.C.byref(n)))
+        return dict(zip(self.STEP_KERNELS, list(ms))), int(n.value)
+
+    def render(self):
+        """core/env.py:133-134 -- visualisation is out of scope of the hot path."""
+        raise NotImplementedError("rendering is not part of the B200 hot path; read env.medium / env.agents")
+
+
+class _DevicePtrView:
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr,
+                                         'data': (int(ptr), False), 'version': 2}

@@ -1,0 +1,149 @@
+/* die_b200.h -- C ABI of libdie_sm100a.so: the per-step hot path of gkirgizov/die
+ * (Env.step, BrownianAgent.forward, GradientAgent/PhysarumAgent.forward) as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * The reference has no FFI: its "operator API" for this path is the Python protocol
+ *     Env.step(action)            /root/reference/core/env.py:101-131
+ *     Agent.forward(obs)          /root/reference/core/agent/base.py:13-16
+ * so each entry point below names the reference method(s) it replaces.  The binding a
+ * maintainer of the reference would add (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns DIE_OK (0) or a DIE_E_* code and never throws;
+ *     die_last_error() gives the message of the calling thread's last failure;
+ *   - "dev" pointers are device memory owned by the caller (borrowed for the call, stream-
+ *     ordered); "host" pointers are host memory (pinned for full copy speed);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - everything is float64, channel-major, exactly the reference's layouts
+ *     (core/base_types.py:31-36, core/data_init.py:94-130):
+ *         medium [B][3][H][W]  channels (agents, env_food, chem1)
+ *         agents [B][4][M]     channels (x, y, alive, agent_food)
+ *         action [B][3][M]     channels (dx, dy, deposit1)
+ *     B = number of independent environments in the batch (1 = the reference's case).
+ */
+#ifndef DIE_B200_H
+#define DIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIE_OK          0
+#define DIE_E_INVALID   1   /* bad argument */
+#define DIE_E_CUDA      2   /* a CUDA runtime call failed; see die_last_error() */
+#define DIE_E_NOMEM     3
+
+#define DIE_MAX_RADIUS  8   /* blur radius int(4*sigma+.5) <= 8  <=>  sigma <= 2.1 */
+
+#define DIE_BOUNDARY_WRAP   0   /* BoundaryCondition.wrap  core/env.py:154-155 */
+#define DIE_BOUNDARY_LIMIT  1   /* BoundaryCondition.limit core/env.py:156-157 */
+#define DIE_BOUNDARY_NONE   2   /* unknown enum: warn + leave as is, core/env.py:158-161 */
+
+/* Dynamics, core/env.py:42-61, as a POD.  op_action_cost is restricted to the reference's
+ * two operators: linear_action_cost (weights 0.02, 0.01; core/env.py:29-35) and zero_cost
+ * (both weights 0; core/env.py:38-39).  op_food_flow is identity (core/env.py:45).
+ * blur_w holds the 2*blur_radius+1 weights scipy.ndimage.gaussian_filter1d builds for
+ * diffuse_sigma (w[k] = exp(-.5/sigma^2 k^2)/sum, k=-r..r); diffuse_mode is 'wrap'. */
+typedef struct die_dynamics {
+    double  rate_feed;
+    double  rate_decay_chem;
+    double  cost_w_deposit;
+    double  cost_w_dist;
+    double  blur_w[2 * DIE_MAX_RADIUS + 1];
+    int32_t blur_radius;
+    int32_t boundary;
+    int32_t food_infinite;
+    int32_t reserved;
+} die_dynamics_t;
+
+/* GradientAgent / PhysarumAgent constructor state, core/agent/gradient.py:19-45,139-163. */
+typedef struct die_gradient_params {
+    double  scale;
+    double  deposit;
+    double  inertia;
+    double  sense_offset;
+    double  noise_scale;
+    double  grad_clip;        /* used iff use_grad_clip */
+    double  turn_radians;     /* np.radians(turn_angle)   (Physarum) */
+    double  sense_radians;    /* np.radians(sense_angle)  (Physarum) */
+    double  turn_tolerance;   /* rtol                     (Physarum) */
+    int32_t normalized_grad;
+    int32_t use_grad_clip;    /* grad_clip is not None */
+    int32_t discrete_turn;    /* 1 = PhysarumAgent._process_gradient, 0 = GradientAgent */
+    int32_t reserved;
+} die_gradient_params_t;
+
+typedef struct die_env die_env_t;
+
+const char* die_version(void);
+const char* die_last_error(void);
+
+/* Env.__init__ workspace (core/env.py:65-72): per-cell claim table, per-slot cell cache,
+ * reduction partials.  Must be called with the target device current. */
+int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
+                   const die_dynamics_t* dyn, die_env_t** out);
+int die_env_destroy(die_env_t* env);
+int die_env_set_dynamics(die_env_t* env, const die_dynamics_t* dyn);
+
+/* Env.step, core/env.py:101-131: move -> deposit + layout -> feed -> food flow ->
+ * diffuse*decay -> reward / num_agents.  Reads medium_in (its chem1 channel is updated
+ * in place by the deposit), writes the next medium into medium_out (a different buffer),
+ * updates agents in place.  reward_dev[B] = sum over ALL M slots of gained; alive_dev[B] =
+ * #(alive > 0).  die_env_cells() exposes the int32 [B][M] linear cell index ix*W+iy of
+ * every slot after the move (validation aid). */
+int die_env_step(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+                 double* agents_dev, const double* action_dev,
+                 double* reward_dev, int64_t* alive_dev, void* stream);
+const int32_t* die_env_cells(const die_env_t* env);   /* device ptr, int32 [B][M], valid after a step */
+
+/* Per-kernel timing of Env.step with CUDA events recorded on the launching stream between
+ * the step's kernels (measurement aid for bench.py's roofline; off by default).
+ * die_env_kernel_times synchronises the recorded events and returns the accumulated
+ * milliseconds of {move_claim, deposit_feed, field_step, finalize_stats} and the number of
+ * profiled steps since profiling was (re-)enabled; at most DIE_MAX_PROFILED_STEPS are kept. */
+#define DIE_NUM_STEP_KERNELS     4
+#define DIE_MAX_PROFILED_STEPS   2048
+int die_env_set_profiling(die_env_t* env, int32_t on);
+int die_env_kernel_times(die_env_t* env, double* ms_out /*[DIE_NUM_STEP_KERNELS]*/, int64_t* steps_out);
+
+/* Env.step through HOST buffers: H2D of action_host[B][3][M], the step, D2H of the new
+ * observation (agents_host[B][4][M], medium_host[B][3][H][W]; either may be NULL to skip)
+ * and of reward_host[B] / alive_host[B]; synchronises `stream` before returning. */
+int die_env_step_host(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+                      double* agents_dev, const double* action_host,
+                      double* agents_host, double* medium_host,
+                      double* reward_host, int64_t* alive_host, void* stream);
+
+/* BrownianAgent.forward, core/agent/static.py:40-50 (+ core/data_init.py:159-169,218-220,
+ * 248-253).  u_dev[B][3][M] = the three uniform draws in the reference's order
+ * (dx, dy, deposit1); NULL = draw in-kernel (Philox4x32-10 keyed on seed, step, slot). */
+int die_brownian_forward(const double* agents_dev, double* action_dev, int64_t M, int32_t B,
+                         double move_scale, double deposit_scale,
+                         const double* u_dev, uint64_t seed, uint64_t step, void* stream);
+
+/* ConstAgent.forward, core/agent/static.py:19-28 (not alive-masked). */
+int die_const_forward(double* action_dev, int64_t M, int32_t B,
+                      double dx, double dy, double deposit, void* stream);
+
+/* GradientAgent.forward / PhysarumAgent.forward, core/agent/gradient.py:96-124 (+ :55-91,
+ * :168-219).  theta_dev[B][M] (in/out) = _direction_rads.  prev_grad_dev[B][2][M] (in/out)
+ * = _prev_grad; may be NULL when inertia == 0 and noise_scale == 0 (its value then cannot
+ * reach any output).  coin_dev[B][M] uint8 in {0,1} = np.random.randint(0, 2, M); NULL =
+ * Philox.  noise_dev[B][2][M] = rng.normal(0, .4, (2, M)); NULL = Philox Box-Muller
+ * (skipped entirely when noise_scale == 0).  sense_cells_dev (optional) int32 [B][M]:
+ * linear index of the cell each slot sensed (validation aid). */
+int die_gradient_forward(const die_gradient_params_t* p,
+                         int32_t H, int32_t W, int64_t M, int32_t B,
+                         const double* agents_dev, const double* medium_dev,
+                         double* theta_dev, double* prev_grad_dev, double* action_dev,
+                         const uint8_t* coin_dev, const double* noise_dev,
+                         int32_t* sense_cells_dev,
+                         uint64_t seed, uint64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIE_B200_H */

@@ -1,0 +1,121 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/die_b200.h
+declares (no compute calls without a GPU); host-side logic of the Python mirror."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "die_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(die_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared_functions()
+    for must in ("die_env_create", "die_env_destroy", "die_env_step", "die_env_step_host",
+                 "die_brownian_forward", "die_gradient_forward", "die_const_forward", "die_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from die_b200._build import LIB_PATH
+    assert os.path.exists(LIB_PATH), "build with `python die_b200/_build.py`"
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/die_b200.h but not exported"
+
+
+def test_ctypes_signatures_cover_the_header():
+    from die_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_functions()
+    lib = _lib.load()
+    assert b"sm_100a" in lib.die_version()
+
+
+def test_struct_layouts_match_header():
+    from die_b200 import _lib
+    assert ctypes.sizeof(_lib.DieDynamics) == 8 * 4 + 8 * 17 + 4 * 4
+    assert ctypes.sizeof(_lib.DieGradientParams) == 8 * 9 + 4 * 4
+
+
+def test_argument_errors_are_codes_not_crashes():
+    from die_b200 import _lib
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    dyn = _lib.DieDynamics()
+    assert lib.die_env_create(1, 1, 1, 1, ctypes.byref(dyn), ctypes.byref(out)) == 1      # DIE_E_INVALID
+    assert b"invalid argument" in lib.die_last_error()
+    dyn.blur_radius = 99
+    assert lib.die_env_create(8, 8, 64, 1, ctypes.byref(dyn), ctypes.byref(out)) == 1
+    assert lib.die_env_destroy(None) == 0
+    assert lib.die_brownian_forward(None, None, 1, 1, 0.1, 0.1, None, 0, 0, None) == 1
+
+
+def test_dynamics_to_c_defaults():
+    from die_b200 import env as E
+    c = E._dynamics_to_c(E.Dynamics())
+    assert (c.rate_feed, c.rate_decay_chem) == (0.1, 0.1)
+    assert (c.cost_w_deposit, c.cost_w_dist) == (0.02, 0.01)
+    assert c.blur_radius == 2 and c.boundary == 0 and c.food_infinite == 0
+    import scipy.ndimage
+    imp = np.zeros(9)
+    imp[4] = 1.0
+    w = scipy.ndimage.gaussian_filter1d(imp, 0.5, mode='constant')[2:7]
+    assert np.array_equal(np.array(list(c.blur_w)[:5]), w)
+
+
+def test_dynamics_rejects_what_is_not_on_the_gpu_path():
+    from die_b200 import env as E
+    with pytest.raises(NotImplementedError):
+        E._dynamics_to_c(E.Dynamics(op_action_cost=lambda a: 0))
+    with pytest.raises(NotImplementedError):
+        E._dynamics_to_c(E.Dynamics(diffuse_mode='reflect'))
+    with pytest.raises(NotImplementedError):
+        E._dynamics_to_c(E.Dynamics(diffuse_sigma=5.0))
+    assert E._dynamics_to_c(E.Dynamics(op_action_cost=E.zero_cost)).cost_w_dist == 0.0
+    assert E._dynamics_to_c(E.Dynamics(boundary=E.BoundaryCondition.limit)).boundary == 1
+
+
+def test_env_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has CUDA")
+    import die_b200 as D
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D.Env((16, 16))
+
+
+def test_host_init_matches_oracle_init():
+    """die_b200.data_init (product) and oracle.die_ref (checker) are separate implementations of
+    core/data_init.py; on the same seeds they must build the same state."""
+    from die_b200 import data_init
+    from oracle import die_ref as R
+    np.random.seed(3)
+    m1 = data_init.init_medium((40, 56), 0.1, noise_seed=5)
+    a1 = data_init.agents_from_medium(m1)
+    np.random.seed(3)
+    m2 = R.init_medium((40, 56), 0.1, noise_seed=5)
+    a2 = R.agents_from_medium(m2)
+    assert np.array_equal(m1, m2) and np.array_equal(a1, a2)
+    n = int(a1[2].sum())
+    assert 0.05 < n / (40 * 56) < 0.15
+    assert (a1[:, n:] == 0).all()                       # ghosts: all-zero slots at (0, 0)
+    assert ((a1[3, :n] >= 0.1) & (a1[3, :n] <= 1.0)).all()
+    ix = np.rint(a1[0, :n] * 39).astype(int) * 56 + np.rint(a1[1, :n] * 55).astype(int)
+    assert (np.diff(ix) > 0).all()                      # row-major nonzero order
+
+
+def test_agent_params_roundtrip(tmp_path):
+    import die_b200 as D
+    a = D.PhysarumAgent(max_agents=64, scale=0.007, turn_angle=30, sense_offset=0.04)
+    f = tmp_path / "agent.json"
+    a.save(str(f))
+    b = D.PhysarumAgent.load(str(f))
+    assert b.init_params() == a.init_params()
+    assert D.BrownianAgent.load.__self__ is D.BrownianAgent
