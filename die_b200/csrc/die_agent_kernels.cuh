@@ -13,37 +13,64 @@ namespace die {
 
 constexpr int kAgentThreads = 256;
 
+// Per-slot kernels cut every environment's M slots into chunks of kAgentThreads * ITEMS
+// consecutive slots, one chunk per CTA (thread t handles slots base + k*256 + t): coalesced,
+// no 64-bit division per slot, and a fixed slot -> (CTA, thread, k) map that the in-kernel RNG
+// is keyed on (so the random stream does not depend on the launch geometry or the SM count).
+struct SlotChunk {
+    int64_t b;        // environment
+    int64_t base;     // first slot of the chunk within the environment
+};
+
+template <int ITEMS>
+__device__ __forceinline__ SlotChunk slot_chunk(int nchunk) {
+    SlotChunk c;
+    const unsigned blk = blockIdx.x;
+    const unsigned b = blk / (unsigned)nchunk;
+    c.b = b;
+    c.base = (int64_t)(blk - b * (unsigned)nchunk) * (kAgentThreads * ITEMS);
+    return c;
+}
+
+static inline int chunks_for(int64_t M, int items) {
+    return (int)((M + (int64_t)kAgentThreads * items - 1) / ((int64_t)kAgentThreads * items));
+}
+
 // ---------------------------------------------------------------------------------------------
 // BrownianAgent.forward  (core/agent/static.py:40-50; core/data_init.py:159-169,218-220,248-253)
 //   chan = ((b - a) * round(u, 3) + a) * alive,  u drawn in the order dx, dy, deposit1.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBrownItems = 4;
+
 __global__ void __launch_bounds__(kAgentThreads)
 brownian_forward_kernel(const double* __restrict__ agents, double* __restrict__ action,
-                        int64_t M, int64_t total, double s, double dep_scale,
+                        int64_t M, int nchunk, double s, double dep_scale,
                         const double* __restrict__ u, uint64_t seed, uint64_t step) {
-    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = gid / M, i = gid - b * M;
-        const double alive = agents[(b * 4 + 2) * M + i];
+    const SlotChunk ch = slot_chunk<kBrownItems>(nchunk);
+    const double* alive_p = agents + (ch.b * 4 + 2) * M;
+    const double* ub = (u != nullptr) ? u + ch.b * 3 * M : nullptr;
+    double* ab = action + ch.b * 3 * M;
+    const double span = s - (-s);                           // (b - a) with a = -s, b = s
+#pragma unroll
+    for (int k = 0; k < kBrownItems; ++k) {
+        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
+        if (i >= M) break;
+        const double alive = alive_p[i];
         double u0, u1, u2;
-        if (u != nullptr) {
-            const double* ub = u + b * 3 * M;
+        if (ub != nullptr) {
             u0 = ub[i];
             u1 = ub[M + i];
             u2 = ub[2 * M + i];
-        } else {
-            const uint4 r0 = philox_draw(seed, step, (uint64_t)gid, 0u);
-            const uint4 r1 = philox_draw(seed, step, (uint64_t)gid, 1u);
-            u0 = u53(r0.x, r0.y);
-            u1 = u53(r0.z, r0.w);
-            u2 = u53(r1.x, r1.y);
+        } else {                                            // one Philox block = 3 x 32-bit uniforms
+            const uint4 r = philox_draw(seed, step, (uint64_t)(ch.b * M + i), 0u);
+            u0 = u32(r.x);
+            u1 = u32(r.y);
+            u2 = u32(r.z);
         }
         // np.round(u, 3) == rint(u * 1000) / 1000   
         const double q0 = rint(u0 * 1000.0) / 1000.0;
         const double q1 = rint(u1 * 1000.0) / 1000.0;
         const double q2 = rint(u2 * 1000.0) / 1000.0;
-        const double span = s - (-s);                       // (b - a) with a = -s, b = s
-        double* ab = action + b * 3 * M;
         ab[i]         = (span * q0 + (-s)) * alive;
         ab[M + i]     = (span * q1 + (-s)) * alive;
         ab[2 * M + i] = ((dep_scale - 0.0) * q2 + 0.0) * alive;
@@ -52,12 +79,14 @@ brownian_forward_kernel(const double* __restrict__ agents, double* __restrict__ 
 
 // ConstAgent.forward (core/agent/static.py:19-28)
 __global__ void __launch_bounds__(kAgentThreads)
-const_forward_kernel(double* __restrict__ action, int64_t M, int64_t total,
+const_forward_kernel(double* __restrict__ action, int64_t M, int nchunk,
                      double dx, double dy, double dep) {
-    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = gid / M, i = gid - b * M;
-        double* ab = action + b * 3 * M;
+    const SlotChunk ch = slot_chunk<kBrownItems>(nchunk);
+    double* ab = action + ch.b * 3 * M;
+#pragma unroll
+    for (int k = 0; k < kBrownItems; ++k) {
+        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
+        if (i >= M) break;
         ab[i] = dx;
         ab[M + i] = dy;
         ab[2 * M + i] = dep;
@@ -70,12 +99,16 @@ const_forward_kernel(double* __restrict__ action, int64_t M, int64_t total,
 // The reference materialises the normalised gradient of the whole chem1 field
 // (_get_gradient, :55-71) and then samples it at ONE cell per slot.  Here the np.gradient
 // stencil is evaluated only at the sampled cell: identical arithmetic per sample, 4 chem
-// gathers instead of ~10 full-field passes.
+// gathers instead of ~10 full-field passes.  sin / cos / atan2 are die_math.h's
+// bit-reproducible routines (see that file for why).
 // ---------------------------------------------------------------------------------------------
+constexpr int kFwdItems = 8;     // one 32-bit Philox word serves a thread's 8 coin flips
+
 struct GradientArgs {
     die_gradient_params_t p;
     int H, W;
-    int64_t M, total;
+    int64_t M;
+    int nchunk;
     const double* agents;
     const double* medium;
     double* theta;
@@ -95,61 +128,79 @@ gradient_forward_kernel(const GradientArgs a) {
     const int64_t M = a.M;
     const int64_t C = (int64_t)a.H * a.W;
     const int H = a.H, W = a.W;
+    const SlotChunk ch = slot_chunk<kFwdItems>(a.nchunk);
 
-    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < a.total;
-         gid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = gid / M, i = gid - b * M;
-        const double* ag = a.agents + b * 4 * M;
+    const double* ag = a.agents + ch.b * 4 * M;
+    const double* food = a.medium + (ch.b * 3 + 1) * C;
+    const double* chem = a.medium + (ch.b * 3 + 2) * C;
+    double* th_p = a.theta + ch.b * M;
+    double* ab = a.action + ch.b * 3 * M;
+    double* pg = (a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M : nullptr;
+    const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M : nullptr;
+    const double* nz = (a.noise != nullptr) ? a.noise + ch.b * 2 * M : nullptr;
+    int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M : nullptr;
+
+    uint32_t coin_bits = 0;
+    if (DISCRETE_TURN && coin_p == nullptr)      // coin of slot (CTA, t, k) = bit k of this word
+        coin_bits = philox_draw(a.seed, a.step, (uint64_t)blockIdx.x * kAgentThreads + threadIdx.x, 2u).x;
+    const double atol = p.turn_radians * p.turn_tolerance;
+
+    for (int k = 0; k < kFwdItems; ++k) {
+        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
+        if (i >= M) break;
         const double x = ag[i], y = ag[M + i];
-        const double th = a.theta[gid];
-        const double* food = a.medium + (b * 3 + 1) * C;
-        const double* chem = a.medium + (b * 3 + 2) * C;
+        const double th = th_p[i];
 
         // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
         double sn, cs;
-        sincos(th, &sn, &cs);
+        die_sincos(th, &sn, &cs);
         const double px = x + p.sense_offset * cs;
         const double py = y + p.sense_offset * sn;
         // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
-        if (a.sense_cells != nullptr) a.sense_cells[gid] = sx * W + sy;
+        if (sc_p != nullptr) sc_p[i] = sx * W + sy;
+        // food under the agent (:113-115), issued early: independent of the turn arithmetic
+        const int ix = nearest_cell(x, ax), iy = nearest_cell(y, ay);
+        const double food_here = food[(int64_t)ix * W + iy];
 
         // np.gradient at (sx, sy): central interior, one-sided edges, non-periodic (Q5)
         const double* row = chem + (int64_t)sx * W;
         double gx, gy;
-        if (sx == 0)            gx = chem[(int64_t)W + sy] - row[sy];
+        if (sx == 0)            gx = row[W + sy] - row[sy];
         else if (sx == H - 1)   gx = row[sy] - row[sy - W];
         else                    gx = (row[sy + W] - row[sy - W]) / 2.0;
         if (sy == 0)            gy = row[1] - row[0];
         else if (sy == W - 1)   gy = row[sy] - row[sy - 1];
         else                    gy = (row[sy + 1] - row[sy - 1]) / 2.0;
 
-        // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling)
+        // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling);
+        // grad = nan_to_num(grad / norm) (:62); grad *= (norm >= clip) (:65) keeps signed zeros
         const double norm = sqrt(gx * gx + gy * gy);
+        const bool clipped = p.use_grad_clip && !(norm >= p.grad_clip);
         if (p.normalized_grad) {
-            gx = div_nan_to_num(gx, norm);
-            gy = div_nan_to_num(gy, norm);
-        }
-        if (p.use_grad_clip) {                       // grad *= (norm >= clip): keeps signed zeros
-            const double m = (norm >= p.grad_clip) ? 1.0 : 0.0;
-            gx *= m;
-            gy *= m;
+            if (clipped) {          // (+-q) * 0.0: only the zero's sign survives; 0/0 -> nan -> +0
+                gx = (norm == 0.0 && gx == 0.0) ? 0.0 : copysign(0.0, gx);
+                gy = (norm == 0.0 && gy == 0.0) ? 0.0 : copysign(0.0, gy);
+            } else {
+                gx = div_nan_to_num(gx, norm);
+                gy = div_nan_to_num(gy, norm);
+            }
+        } else if (clipped) {
+            gx *= 0.0;
+            gy *= 0.0;
         }
 
         bool deposit_mask = true;
         if (DISCRETE_TURN) {
             // PhysarumAgent._discrete_turn / _choose_turn (:168-208)
             const double dr = p.normalized_grad ? 1.0 : hypot(gx, gy);
-            const double drads = angle_xy(gx, gy);
+            const double drads = angle_xy<true>(gx, gy);
             double dd = renormalize_radians(th - drads);
-            const double atol = p.turn_radians * p.turn_tolerance;
             const bool und_grad = fabs(0.0 - drads) <= 1e-8 + 1e-5 * fabs(drads);
             const bool und_turn = fabs(0.0 - dd) <= atol + 1e-2 * fabs(dd);
             const bool unseen = fabs(dd) > p.sense_radians;
             const bool und = und_grad || und_turn || unseen;
-            int c;
-            if (a.coin != nullptr) c = a.coin[gid] ? 1 : 0;
-            else c = (int)(philox_draw(a.seed, a.step, (uint64_t)gid, 2u).x >> 31);
+            const int c = (coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
             double turn = ((double)c - 0.5) * 2.0;
             dd *= und ? 0.0 : 1.0;
             if (dd > atol) turn = -1.0;
@@ -158,41 +209,37 @@ gradient_forward_kernel(const GradientArgs a) {
             deposit_mask = !(und_grad || und_turn);
             const double dirn = renormalize_radians(th + turn);
             double s2, c2;
-            sincos(dirn, &s2, &c2);
+            die_sincos(dirn, &s2, &c2);
             gx = dr * c2;
             gy = dr * s2;
         }
 
         // _process_momentum (:82-91)
-        if (a.prev_grad != nullptr) {
-            double* pg = a.prev_grad + b * 2 * M;
+        if (pg != nullptr) {
             gx = (1.0 - p.inertia) * gx + p.inertia * pg[i];
             gy = (1.0 - p.inertia) * gy + p.inertia * pg[M + i];
-            if (a.noise != nullptr) {
-                const double* nz = a.noise + b * 2 * M;
+            if (nz != nullptr) {
                 gx += p.noise_scale * nz[i];
                 gy += p.noise_scale * nz[M + i];
             } else if (p.noise_scale != 0.0) {
-                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)gid, 3u);
+                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)(ch.b * M + i), 3u);
                 const double u1 = 1.0 - u53(r.x, r.y), u2 = u53(r.z, r.w);
                 const double rad = 0.4 * sqrt(-2.0 * log(u1));
                 double sn3, cs3;
-                sincos(kTwoPi * u2, &sn3, &cs3);
+                die_sincos(kTwoPi * u2, &sn3, &cs3);
                 gx += p.noise_scale * (rad * cs3);
                 gy += p.noise_scale * (rad * sn3);
             }
             pg[i] = gx;
             pg[M + i] = gy;
         }
-        a.theta[gid] = angle_xy(gx, gy);                       // :110
+        th_p[i] = angle_xy<false>(gx, gy);                     // :110
 
-        // deposit relative to food under the agent (:113-117, :210-214)
-        const int ix = nearest_cell(x, ax), iy = nearest_cell(y, ay);
-        double dep = p.deposit * food[(int64_t)ix * W + iy];
+        // deposit relative to the food under the agent (:113-117, :210-214)
+        double dep = p.deposit * food_here;
         if (DISCRETE_TURN) dep = dep * (deposit_mask ? 1.0 : 0.1);
 
-        double* ab = a.action + b * 3 * M;                     // unmasked (Q8)
-        ab[i] = gx * p.scale;
+        ab[i] = gx * p.scale;                                  // unmasked (Q8)
         ab[M + i] = gy * p.scale;
         ab[2 * M + i] = dep;
     }
@@ -204,19 +251,26 @@ gradient_forward_kernel(const GradientArgs a) {
 // highest slot index among the alive agents on it -- atomicMax is order-independent, so the
 // result is deterministic and bit-exact.
 // ---------------------------------------------------------------------------------------------
+constexpr int kMoveItems = 4;
+
 __global__ void __launch_bounds__(kAgentThreads)
 move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   int32_t* __restrict__ winner, int32_t* __restrict__ cells,
-                  int H, int W, int64_t M, int64_t total, int boundary) {
+                  int H, int W, int64_t M, int nchunk, int boundary) {
     const Axis ax = make_axis(H), ay = make_axis(W);
     const int64_t C = (int64_t)H * W;
-    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = gid / M, i = gid - b * M;
-        double* ag = agents + b * 4 * M;
-        const double* ac = action + b * 3 * M;
+    const SlotChunk ch = slot_chunk<kMoveItems>(nchunk);
+    double* ag = agents + ch.b * 4 * M;
+    const double* ac = action + ch.b * 3 * M;
+    int32_t* win = winner + ch.b * C;
+    int32_t* cl = cells + ch.b * M;
+#pragma unroll
+    for (int k = 0; k < kMoveItems; ++k) {
+        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
+        if (i >= M) break;
         double x = ag[i] + ac[i];
         double y = ag[M + i] + ac[M + i];
+        const bool alive = ag[2 * M + i] > 0.0;
         if (boundary == DIE_BOUNDARY_WRAP) {
             x = mod1(x);
             y = mod1(y);
@@ -227,8 +281,8 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
         ag[i] = x;
         ag[M + i] = y;
         const int cell = nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        cells[gid] = cell;
-        if (ag[2 * M + i] > 0.0) atomicMax(winner + b * C + cell, (int32_t)i);
+        cl[i] = cell;
+        if (alive) atomicMax(win + cell, (int32_t)i);
     }
 }
 

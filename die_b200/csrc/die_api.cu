@@ -223,11 +223,11 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
     DIE_REQUIRE(agents != nullptr && action != nullptr);
     DIE_REQUIRE(reward_dev != nullptr && alive_dev != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t total = e->M * e->B;
 
     prof_mark(e, 0, st);
-    move_claim_kernel<<<grid_for(total, kAgentThreads, e->num_sms), kAgentThreads, 0, st>>>(
-        agents, action, e->winner, e->cells, e->H, e->W, e->M, total, e->dyn.boundary);
+    const int mchunk = chunks_for(e->M, kMoveItems);
+    move_claim_kernel<<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
+        agents, action, e->winner, e->cells, e->H, e->W, e->M, mchunk, e->dyn.boundary);
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 1, st);
 
@@ -274,20 +274,15 @@ extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium
 // ------------------------------------------------------------------------------------------
 // Agent.forward
 // ------------------------------------------------------------------------------------------
-static int sm_count() {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-}
-
 extern "C" int die_brownian_forward(const double* agents, double* action, int64_t M, int32_t B,
                                     double move_scale, double deposit_scale,
                                     const double* u, uint64_t seed, uint64_t step, void* stream) {
     DIE_REQUIRE(agents != nullptr && action != nullptr);
     DIE_REQUIRE(M >= 1 && B >= 1);
-    const int64_t total = M * B;
-    brownian_forward_kernel<<<grid_for(total, kAgentThreads, sm_count()), kAgentThreads, 0, (cudaStream_t)stream>>>(
-        agents, action, M, total, move_scale, deposit_scale, u, seed, step);
+    DIE_REQUIRE(M <= 0x7fffffffLL);
+    const int nchunk = chunks_for(M, kBrownItems);
+    brownian_forward_kernel<<<(unsigned)((int64_t)nchunk * B), kAgentThreads, 0, (cudaStream_t)stream>>>(
+        agents, action, M, nchunk, move_scale, deposit_scale, u, seed, step);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -296,9 +291,10 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
                                  double dx, double dy, double deposit, void* stream) {
     DIE_REQUIRE(action != nullptr);
     DIE_REQUIRE(M >= 1 && B >= 1);
-    const int64_t total = M * B;
-    const_forward_kernel<<<grid_for(total, kAgentThreads, sm_count()), kAgentThreads, 0, (cudaStream_t)stream>>>(
-        action, M, total, dx, dy, deposit);
+    DIE_REQUIRE(M <= 0x7fffffffLL);
+    const int nchunk = chunks_for(M, kBrownItems);
+    const_forward_kernel<<<(unsigned)((int64_t)nchunk * B), kAgentThreads, 0, (cudaStream_t)stream>>>(
+        action, M, nchunk, dx, dy, deposit);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -318,15 +314,45 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     GradientArgs a;
     memset(&a, 0, sizeof(a));
     a.p = *p;
-    a.H = H; a.W = W; a.M = M; a.total = M * B;
+    DIE_REQUIRE(M <= 0x7fffffffLL);
+    a.H = H; a.W = W; a.M = M; a.nchunk = chunks_for(M, kFwdItems);
     a.agents = agents; a.medium = medium; a.theta = theta; a.prev_grad = prev_grad;
     a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
     a.seed = seed; a.step = step;
-    const int grid = grid_for(a.total, kAgentThreads, sm_count());
+    const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     if (p->discrete_turn)
         gradient_forward_kernel<true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
     else
         gradient_forward_kernel<false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagnostics: die_math.h on device arrays
+// ------------------------------------------------------------------------------------------
+__global__ void math_sincos_kernel(const double* x, double* s, double* c, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        die_sincos(x[i], s + i, c + i);
+}
+
+__global__ void math_atan2_kernel(const double* y, const double* x, double* out, int64_t n, int fast) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = fast ? die_atan2_fast(y[i], x[i]) : die_atan2(y[i], x[i]);
+}
+
+extern "C" int die_math_sincos(const double* x, double* s, double* c, int64_t n, void* stream) {
+    DIE_REQUIRE(x != nullptr && s != nullptr && c != nullptr && n >= 0);
+    if (n == 0) return DIE_OK;
+    math_sincos_kernel<<<grid_for(n, 256, 148), 256, 0, (cudaStream_t)stream>>>(x, s, c, n);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+extern "C" int die_math_atan2(const double* y, const double* x, double* out, int64_t n, int32_t fast, void* stream) {
+    DIE_REQUIRE(x != nullptr && y != nullptr && out != nullptr && n >= 0);
+    if (n == 0) return DIE_OK;
+    math_atan2_kernel<<<grid_for(n, 256, 148), 256, 0, (cudaStream_t)stream>>>(y, x, out, n, fast);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }

@@ -9,6 +9,8 @@
 #include <cfloat>
 #include <cuda_runtime.h>
 
+#include "die_math.h"
+
 namespace die {
 
 constexpr double kPi    = 3.141592653589793;    // np.pi
@@ -40,13 +42,19 @@ __device__ __forceinline__ double grid_coord(const Axis& a, int i) {
 __device__ __forceinline__ int nearest_cell(double c, const Axis& a) {
     if (!(c > 0.0)) return 0;                 // c <= 0 (and NaN): first cell
     if (c >= 1.0) return a.n - 1;
-    int i = (int)(c * a.nm1);                 // floor estimate, off by at most one
+    int i = (int)(c * a.nm1);                 // floor estimate of L, off by at most one
     if (i > a.n - 2) i = a.n - 2;
-    while (i > 0 && grid_coord(a, i) > c) --i;
-    while (i < a.n - 2 && grid_coord(a, i + 1) <= c) ++i;
-    const double gl = grid_coord(a, i);
+    double gl = grid_coord(a, i), gr = grid_coord(a, i + 1);
+    if (gl > c) {                             // (rare) estimate one too high
+        --i;
+        gr = gl;
+        gl = grid_coord(a, i);
+    } else if (gr <= c) {                     // (rare) estimate one too low
+        ++i;
+        gl = gr;
+        gr = grid_coord(a, i + 1);
+    }
     if (gl == c) return i;
-    const double gr = grid_coord(a, i + 1);
     return (__dsub_rn(c, gl) < __dsub_rn(gr, c)) ? i : i + 1;
 }
 
@@ -81,10 +89,13 @@ __device__ __forceinline__ double renormalize_radians(double r) {
 // np.angle(x + np.multiply(1j, y))  (core/utils.py:158-168).  The complex construction
 // yields re = x + (0*y - 0), im = 0 + y, which is what makes (-0., -0.) -> +pi and every
 // other all-zero pair -> 0.
+// The arctangent is die_math.h's bit-reproducible one: FAST = die_atan2_fast (<= 1.8 ulp) for
+// angles that are only compared against thresholds, else the compensated die_atan2.
+template <bool FAST>
 __device__ __forceinline__ double angle_xy(double x, double y) {
     const double re = __dadd_rn(x, __dsub_rn(__dmul_rn(0.0, y), 0.0));
     const double im = __dadd_rn(0.0, y);
-    return atan2(im, re);
+    return FAST ? die_atan2_fast(im, re) : die_atan2(im, re);
 }
 
 // np.nan_to_num(a / n)  (core/agent/gradient.py:62)
@@ -121,6 +132,9 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
+
+// uniform in [0, 1) with 32 random bits
+__device__ __forceinline__ double u32(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
 
 // ---- block reduction (fixed order => deterministic) ------------------------------------------
 template <typename T>

@@ -143,6 +143,13 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          int32_t* sense_cells_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
+/* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
+ * to device arrays, so tests can check the device results equal the host build of the same
+ * source bit-for-bit.  fast != 0 selects die_atan2_fast. */
+int die_math_sincos(const double* x_dev, double* sin_dev, double* cos_dev, int64_t n, void* stream);
+int die_math_atan2(const double* y_dev, const double* x_dev, double* out_dev, int64_t n,
+                   int32_t fast, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,16 +73,43 @@ def nearest_index(c: np.ndarray, n: int) -> np.ndarray:
     return np.where(take_left, lc, rc).astype(np.int64)
 
 
+# Math backend.  'numpy' (default) evaluates sin / cos / arctan2 exactly as the reference does
+# (numpy -> the host's libm).  'portable' routes ONLY those three functions through the host
+# build of die_b200/csrc/die_math.h (oracle/portable_math.c): bit-reproducible routines, the
+# same ones the CUDA kernels use, so that free-running trajectories can be compared bit-for-bit
+# (the turn rule has exact knife edges, see die_math.h).  Everything else is unchanged.
+_MATH = 'numpy'
+
+
+def set_math_backend(name: str) -> None:
+    global _MATH
+    if name not in ('numpy', 'portable'):
+        raise ValueError(name)
+    _MATH = name
+
+
+def get_math_backend() -> str:
+    return _MATH
+
+
 def polar2xy(r, theta):
-    """core/utils.py:154-164 (via complex exp)."""
+    """core/utils.py:154-164 (via complex exp): (r cos(theta), r sin(theta))."""
+    if _MATH == 'portable':
+        from oracle import portable_math
+        s, c = portable_math.sincos(theta)
+        return r * c, r * s
     z = r * np.exp(np.multiply(1j, theta))
     return np.real(z), np.imag(z)
 
 
-def xy2polar(x, y):
+def xy2polar(x, y, fast_angle=False):
     """core/utils.py:158-168.  NB the complex construction turns a (-0., -0.) pair into
-    angle +pi and every other all-zero pair into 0."""
+    angle +pi and every other all-zero pair into 0.  ``fast_angle`` only selects
+    die_atan2_fast in the portable backend (angles that are merely thresholded)."""
     z = x + np.multiply(1j, y)
+    if _MATH == 'portable':
+        from oracle import portable_math
+        return abs(z), portable_math.atan2(np.imag(z), np.real(z), fast=fast_angle)
     return abs(z), np.angle(z)
 
 
@@ -522,7 +549,7 @@ class PhysarumAgent(GradientAgent):
     def _process_gradient(self, grad, coin=None):
         """_discrete_turn, core/agent/gradient.py:195-208,216-219."""
         dx, dy = grad
-        dr, drads = xy2polar(dx, dy)
+        dr, drads = xy2polar(dx, dy, fast_angle=True)
         turn = self._choose_turn(drads, coin)
         directions = renormalize_radians(self._direction_rads + turn)
         dr = 1. if self._normalized else dr

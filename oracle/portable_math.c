@@ -1,0 +1,17 @@
+/* portable_math.c -- host build of die_b200/csrc/die_math.h for the oracle's "portable" math
+ * backend (TEST INFRASTRUCTURE: lets the numpy oracle evaluate sin/cos/atan2 with the same
+ * bit-reproducible routines the CUDA kernels use, so free-running trajectories can be compared
+ * bit-for-bit).  Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/build_oracle.py). */
+#include "../die_b200/csrc/die_math.h"
+
+void die_sincos_array(const double* x, double* sn, double* cs, long n) {
+    for (long i = 0; i < n; ++i) die_sincos(x[i], sn + i, cs + i);
+}
+
+void die_atan2_array(const double* y, const double* x, double* out, long n) {
+    for (long i = 0; i < n; ++i) out[i] = die_atan2(y[i], x[i]);
+}
+
+void die_atan2_fast_array(const double* y, const double* x, double* out, long n) {
+    for (long i = 0; i < n; ++i) out[i] = die_atan2_fast(y[i], x[i]);
+}

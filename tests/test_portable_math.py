@@ -1,0 +1,98 @@
+"""die_b200/csrc/die_math.h (the kernels' bit-reproducible sin/cos/atan2): accuracy of the host
+build against mpmath, IEEE special cases, and (on the GPU) bit-equality of device and host."""
+import numpy as np
+import pytest
+
+from oracle import portable_math as P
+
+
+def _ulps(vals, exact):
+    import mpmath as mp
+    out = []
+    for v, e in zip(vals, exact):
+        ed = float(e)
+        u = np.spacing(abs(ed)) if ed != 0 else 5e-324
+        out.append(float(abs(mp.mpf(float(v)) - e) / mp.mpf(u)))
+    return np.array(out)
+
+
+def test_sincos_accuracy_vs_mpmath():
+    import mpmath as mp
+    mp.mp.prec = 200
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-np.pi, np.pi, 6000), rng.uniform(-7, 7, 1500),
+                         np.arange(-12, 13) * np.radians(30), np.arange(-8, 9) * np.pi / 2,
+                         rng.uniform(-1e-3, 1e-3, 500)])
+    s, c = P.sincos(xs)
+    es = _ulps(s, [mp.sin(mp.mpf(float(x))) for x in xs])
+    ec = _ulps(c, [mp.cos(mp.mpf(float(x))) for x in xs])
+    assert es.max() < 0.75 and ec.max() < 0.75, (es.max(), ec.max())
+    # within 1 ulp of numpy everywhere, identical almost everywhere
+    assert np.max(np.abs(s - np.sin(xs)) / np.spacing(np.abs(np.sin(xs)))) <= 1.0
+    assert np.mean(s == np.sin(xs)) > 0.97 and np.mean(c == np.cos(xs)) > 0.97
+
+
+def test_atan2_accuracy_vs_mpmath():
+    import mpmath as mp
+    mp.mp.prec = 200
+    rng = np.random.default_rng(1)
+    ang = rng.uniform(-np.pi, np.pi, 8000)
+    rad = np.exp(rng.uniform(-3, 3, 8000))
+    y, x = rad * np.sin(ang), rad * np.cos(ang)
+    ex = [mp.atan2(mp.mpf(float(a)), mp.mpf(float(b))) for a, b in zip(y, x)]
+    assert _ulps(P.atan2(y, x), ex).max() < 0.52            # compensated: ~correctly rounded
+    assert _ulps(P.atan2(y, x, fast=True), ex).max() < 2.0   # thresholds-only variant
+
+
+def test_atan2_ieee_special_cases():
+    y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1, 1, -1, -1, 0.0, 1e-300, 3.0, 0.0, -0.0, 2.0, -2.0])
+    x = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, 1, -1, 1, -1, -2.0, 1e-300, -0.0, 5.0, 5.0, -0.0, 0.0])
+    ref = np.arctan2(y, x)
+    for fast in (False, True):
+        got = P.atan2(y, x, fast=fast)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(np.signbit(got), np.signbit(ref))
+
+
+def test_sincos_special_cases():
+    x = np.array([0.0, -0.0, np.pi / 2, -np.pi / 2, np.pi, -np.pi, np.pi / 6])
+    s, c = P.sincos(x)
+    assert np.array_equal(s, np.sin(x)) and np.array_equal(c, np.cos(x))
+    assert np.signbit(s[1]) and not np.signbit(s[0])
+
+
+def test_round_trip_is_identity_on_the_primary_turn_lattice():
+    """theta' = k * 30 deg: angle(cos theta' + i sin theta') must return theta' exactly, as it does
+    with numpy/glibc -- this is what keeps Physarum headings on the lattice step after step."""
+    tr = np.radians(30)
+    th = np.array([k * tr for k in range(-5, 7)])
+    s, c = P.sincos(th)
+    assert np.array_equal(P.atan2(s, c), th)
+    assert np.array_equal(np.arctan2(np.sin(th), np.cos(th)), th)
+
+
+@pytest.mark.gpu
+def test_device_math_equals_host_build_bit_for_bit():
+    import torch
+    from die_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    xs = np.concatenate([rng.uniform(-2 * np.pi, 2 * np.pi, n), np.arange(-12, 13) * np.radians(30),
+                         [0.0, -0.0, np.pi, -np.pi, np.pi / 2]])
+    xd = torch.from_numpy(xs).cuda()
+    sd, cd = torch.empty_like(xd), torch.empty_like(xd)
+    _lib.check(lib.die_math_sincos(xd.data_ptr(), sd.data_ptr(), cd.data_ptr(), xd.numel(), None))
+    torch.cuda.synchronize()
+    s, c = P.sincos(xs)
+    assert np.array_equal(sd.cpu().numpy(), s) and np.array_equal(cd.cpu().numpy(), c)
+    y = np.concatenate([rng.normal(size=n) * np.exp(rng.uniform(-20, 20, n)), s[:100000], [0.0, -0.0, 0.0, -0.0, 1.0]])
+    x = np.concatenate([rng.normal(size=n) * np.exp(rng.uniform(-20, 20, n)), c[:100000], [0.0, 0.0, -0.0, -0.0, 0.0]])
+    yd, xd2 = torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda()
+    od = torch.empty_like(yd)
+    for fast in (0, 1):
+        _lib.check(lib.die_math_atan2(yd.data_ptr(), xd2.data_ptr(), od.data_ptr(), yd.numel(), fast, None))
+        torch.cuda.synchronize()
+        ref = P.atan2(y, x, fast=bool(fast))
+        got = od.cpu().numpy()
+        assert np.array_equal(got, ref) and np.array_equal(np.signbit(got), np.signbit(ref))
