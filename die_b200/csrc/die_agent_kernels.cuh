@@ -106,6 +106,7 @@ constexpr int kFwdItems = 8;     // one 32-bit Philox word serves a thread's 8 c
 
 struct GradientArgs {
     die_gradient_params_t p;
+    Axis ax, ay;                // axis 0 (H cells, coordinate x) and axis 1 (W cells, coordinate y)
     int H, W;
     int64_t M;
     int nchunk;
@@ -124,31 +125,37 @@ template <bool DISCRETE_TURN>
 __global__ void __launch_bounds__(kAgentThreads)
 gradient_forward_kernel(const GradientArgs a) {
     const die_gradient_params_t& p = a.p;
-    const Axis ax = make_axis(a.H), ay = make_axis(a.W);
+    const Axis ax = a.ax, ay = a.ay;
     const int64_t M = a.M;
     const int64_t C = (int64_t)a.H * a.W;
     const int H = a.H, W = a.W;
     const SlotChunk ch = slot_chunk<kFwdItems>(a.nchunk);
+    const int64_t first = ch.base + threadIdx.x;          // this thread's slots: first + k*256
 
-    const double* ag = a.agents + ch.b * 4 * M;
+    // per-thread base pointers, advanced by kAgentThreads per item
+    const double* ag_x = a.agents + ch.b * 4 * M + first;
     const double* food = a.medium + (ch.b * 3 + 1) * C;
     const double* chem = a.medium + (ch.b * 3 + 2) * C;
-    double* th_p = a.theta + ch.b * M;
-    double* ab = a.action + ch.b * 3 * M;
-    double* pg = (a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M : nullptr;
-    const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M : nullptr;
-    const double* nz = (a.noise != nullptr) ? a.noise + ch.b * 2 * M : nullptr;
-    int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M : nullptr;
+    double* th_p = a.theta + ch.b * M + first;
+    double* ab = a.action + ch.b * 3 * M + first;
+    double* pg = (a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M + first : nullptr;
+    const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
+    const double* nz = (a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
+    int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
 
     uint32_t coin_bits = 0;
     if (DISCRETE_TURN && coin_p == nullptr)      // coin of slot (CTA, t, k) = bit k of this word
         coin_bits = philox_draw(a.seed, a.step, (uint64_t)blockIdx.x * kAgentThreads + threadIdx.x, 2u).x;
     const double atol = p.turn_radians * p.turn_tolerance;
+    const bool safe_div = p.use_grad_clip && p.grad_clip > 0.0;
+    // with an identity momentum step (no inertia, no noise) and a unit-length direction the new
+    // heading angle(cos d + i sin d) comes out of die_sincos_angle together with cos d, sin d
+    const bool fused_heading = DISCRETE_TURN && pg == nullptr && p.normalized_grad;
 
     for (int k = 0; k < kFwdItems; ++k) {
-        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
-        if (i >= M) break;
-        const double x = ag[i], y = ag[M + i];
+        const int i = k * kAgentThreads;                       // offset from this thread's first slot
+        if (first + i >= M) break;
+        const double x = ag_x[i], y = ag_x[M + i];
         const double th = th_p[i];
 
         // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
@@ -158,20 +165,20 @@ gradient_forward_kernel(const GradientArgs a) {
         const double py = y + p.sense_offset * sn;
         // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
-        if (sc_p != nullptr) sc_p[i] = sx * W + sy;
         // food under the agent (:113-115), issued early: independent of the turn arithmetic
         const int ix = nearest_cell(x, ax), iy = nearest_cell(y, ay);
-        const double food_here = food[(int64_t)ix * W + iy];
+        const double food_here = food[ix * W + iy];
 
-        // np.gradient at (sx, sy): central interior, one-sided edges, non-periodic (Q5)
-        const double* row = chem + (int64_t)sx * W;
-        double gx, gy;
-        if (sx == 0)            gx = row[W + sy] - row[sy];
-        else if (sx == H - 1)   gx = row[sy] - row[sy - W];
-        else                    gx = (row[sy + W] - row[sy - W]) / 2.0;
-        if (sy == 0)            gy = row[1] - row[0];
-        else if (sy == W - 1)   gy = row[sy] - row[sy - 1];
-        else                    gy = (row[sy + 1] - row[sy - 1]) / 2.0;
+        // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
+        // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
+        const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
+        if (sc_p != nullptr) sc_p[i] = sc;
+        const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
+        const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
+        double gx = chem[sc + xp] - chem[sc + xm];
+        double gy = chem[sc + yp] - chem[sc + ym];
+        if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
+        if (yp - ym == 2) gy *= 0.5;
 
         // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling);
         // grad = nan_to_num(grad / norm) (:62); grad *= (norm >= clip) (:65) keeps signed zeros
@@ -181,6 +188,9 @@ gradient_forward_kernel(const GradientArgs a) {
             if (clipped) {          // (+-q) * 0.0: only the zero's sign survives; 0/0 -> nan -> +0
                 gx = (norm == 0.0 && gx == 0.0) ? 0.0 : copysign(0.0, gx);
                 gy = (norm == 0.0 && gy == 0.0) ? 0.0 : copysign(0.0, gy);
+            } else if (safe_div) {  // norm >= clip > 0: the quotient is finite
+                gx = __ddiv_rn(gx, norm);
+                gy = __ddiv_rn(gy, norm);
             } else {
                 gx = div_nan_to_num(gx, norm);
                 gy = div_nan_to_num(gy, norm);
@@ -191,6 +201,7 @@ gradient_forward_kernel(const GradientArgs a) {
         }
 
         bool deposit_mask = true;
+        double heading = 0.0;
         if (DISCRETE_TURN) {
             // PhysarumAgent._discrete_turn / _choose_turn (:168-208)
             const double dr = p.normalized_grad ? 1.0 : hypot(gx, gy);
@@ -209,7 +220,8 @@ gradient_forward_kernel(const GradientArgs a) {
             deposit_mask = !(und_grad || und_turn);
             const double dirn = renormalize_radians(th + turn);
             double s2, c2;
-            die_sincos(dirn, &s2, &c2);
+            if (fused_heading) die_sincos_angle(dirn, &s2, &c2, &heading);
+            else die_sincos(dirn, &s2, &c2);
             gx = dr * c2;
             gy = dr * s2;
         }
@@ -222,7 +234,7 @@ gradient_forward_kernel(const GradientArgs a) {
                 gx += p.noise_scale * nz[i];
                 gy += p.noise_scale * nz[M + i];
             } else if (p.noise_scale != 0.0) {
-                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)(ch.b * M + i), 3u);
+                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)(ch.b * M + first + i), 3u);
                 const double u1 = 1.0 - u53(r.x, r.y), u2 = u53(r.z, r.w);
                 const double rad = 0.4 * sqrt(-2.0 * log(u1));
                 double sn3, cs3;
@@ -233,7 +245,7 @@ gradient_forward_kernel(const GradientArgs a) {
             pg[i] = gx;
             pg[M + i] = gy;
         }
-        th_p[i] = angle_xy<false>(gx, gy);                     // :110
+        th_p[i] = fused_heading ? heading : angle_xy<false>(gx, gy);   // :110
 
         // deposit relative to the food under the agent (:113-117, :210-214)
         double dep = p.deposit * food_here;
@@ -256,9 +268,9 @@ constexpr int kMoveItems = 4;
 __global__ void __launch_bounds__(kAgentThreads)
 move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   int32_t* __restrict__ winner, int32_t* __restrict__ cells,
-                  int H, int W, int64_t M, int nchunk, int boundary) {
-    const Axis ax = make_axis(H), ay = make_axis(W);
-    const int64_t C = (int64_t)H * W;
+                  const Axis ax, const Axis ay, int64_t M, int nchunk, int boundary) {
+    const int W = ay.n;
+    const int64_t C = (int64_t)ax.n * ay.n;
     const SlotChunk ch = slot_chunk<kMoveItems>(nchunk);
     double* ag = agents + ch.b * 4 * M;
     const double* ac = action + ch.b * 3 * M;
@@ -294,41 +306,60 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
+// food / chem are the env_food / chem1 channels of the same medium buffer (disjoint ranges), passed
+// as separate restrict pointers so that the chem1 store of one slot does not fence the gathers of
+// the next: all of a thread's loads are issued before its first store.
 __global__ void __launch_bounds__(kAgentThreads)
 deposit_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
-                    double* __restrict__ medium, const int32_t* __restrict__ winner,
-                    const int32_t* __restrict__ cells,
+                    const double* __restrict__ food_all, double* __restrict__ chem_all,
+                    const int32_t* __restrict__ winner, const int32_t* __restrict__ cells,
                     double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
-                    int H, int W, int64_t M, int nblk,
+                    int64_t C, int64_t M, int nblk,
                     double rate_feed, double w_dep, double w_dist) {
-    const int64_t C = (int64_t)H * W;
-    const int64_t b = blockIdx.x / nblk;
+    const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
-    double* ag = agents + b * 4 * M;
-    const double* ac = action + b * 3 * M;
-    const double* food = medium + (b * 3 + 1) * C;
-    double* chem = medium + (b * 3 + 2) * C;
+    const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
+    double* ag_alive = agents + (b * 4 + 2) * M + first;       // alive; agent_food is + M
+    const double* ac = action + b * 3 * M + first;
+    const double* food = food_all + b * 3 * C;
+    double* chem = chem_all + b * 3 * C;
     const int32_t* win = winner + b * C;
-    const int32_t* cl = cells + b * M;
+    const int32_t* cl = cells + b * M + first;
 
-    double gain_sum = 0.0;
-    int alive_cnt = 0;
-    const int64_t base = (int64_t)blk * (kAgentThreads * kFeedItems);
+    int cell[kFeedItems], w[kFeedItems];
+    double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], f[kFeedItems];
+    bool alive[kFeedItems], valid[kFeedItems];
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
-        const int64_t i = base + (int64_t)k * kAgentThreads + threadIdx.x;
-        if (i < M) {
-            const int cell = cl[i];
-            const int w = win[cell];
-            const bool alive = ag[2 * M + i] > 0.0;
-            const double dx = ac[i], dy = ac[M + i], dep = ac[2 * M + i];
-            if (alive && w == (int)i) chem[cell] = chem[cell] + dep;   // winner's deposit lands once
-            const double consumed = (rate_feed * food[cell]) * ((w >= 0) ? 1.0 : 0.0);   // Q1, Q7
-            const double burned = w_dep * fabs(dep) + w_dist * sqrt(dx * dx + dy * dy);
+        const int i = k * kAgentThreads;
+        valid[k] = first + i < M;
+        cell[k] = valid[k] ? cl[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kFeedItems; ++k) {
+        const int i = k * kAgentThreads;
+        w[k] = valid[k] ? win[cell[k]] : -1;
+        f[k] = valid[k] ? food[cell[k]] : 0.0;
+        alive[k] = valid[k] && ag_alive[i] > 0.0;
+        stock[k] = valid[k] ? ag_alive[M + i] : 0.0;
+        dx[k] = valid[k] ? ac[i] : 0.0;
+        dy[k] = valid[k] ? ac[M + i] : 0.0;
+        dep[k] = valid[k] ? ac[2 * M + i] : 0.0;
+    }
+    double gain_sum = 0.0;
+    int alive_cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kFeedItems; ++k) {
+        if (valid[k]) {
+            const int i = k * kAgentThreads;
+            const int64_t slot = first + i;
+            if (alive[k] && w[k] == (int)slot) chem[cell[k]] = chem[cell[k]] + dep[k];   // winner's deposit lands once
+            const double consumed = (rate_feed * f[k]) * ((w[k] >= 0) ? 1.0 : 0.0);      // Q1, Q7
+            const double burned = w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
             const double gained = consumed - burned;
-            ag[3 * M + i] += gained;
+            ag_alive[M + i] = stock[k] + gained;
             gain_sum += gained;
-            alive_cnt += alive ? 1 : 0;
+            alive_cnt += alive[k] ? 1 : 0;
         }
     }
     __shared__ double s_gain[kAgentThreads / 32];

@@ -227,13 +227,14 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
     prof_mark(e, 0, st);
     const int mchunk = chunks_for(e->M, kMoveItems);
     move_claim_kernel<<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, e->winner, e->cells, e->H, e->W, e->M, mchunk, e->dyn.boundary);
+        agents, action, e->winner, e->cells, make_axis(e->H), make_axis(e->W), e->M, mchunk, e->dyn.boundary);
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 1, st);
 
     deposit_feed_kernel<<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, medium_in, e->winner, e->cells, e->part_gain, e->part_alive,
-        e->H, e->W, e->M, e->nblk, e->dyn.rate_feed, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
+        agents, action, medium_in + (size_t)e->H * e->W, medium_in + 2 * (size_t)e->H * e->W,
+        e->winner, e->cells, e->part_gain, e->part_alive,
+        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.rate_feed, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 2, st);
 
@@ -308,6 +309,7 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
                                     uint64_t seed, uint64_t step, void* stream) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
+    DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
     DIE_REQUIRE(agents != nullptr && medium != nullptr && theta != nullptr && action != nullptr);
     // prev_grad may only be omitted when it cannot influence any output
     DIE_REQUIRE(prev_grad != nullptr || (p->inertia == 0.0 && p->noise_scale == 0.0));
@@ -316,6 +318,8 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     a.p = *p;
     DIE_REQUIRE(M <= 0x7fffffffLL);
     a.H = H; a.W = W; a.M = M; a.nchunk = chunks_for(M, kFwdItems);
+    a.ax = make_axis(H);
+    a.ay = make_axis(W);
     a.agents = agents; a.medium = medium; a.theta = theta; a.prev_grad = prev_grad;
     a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
     a.seed = seed; a.step = step;

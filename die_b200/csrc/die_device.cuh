@@ -27,7 +27,7 @@ struct Axis {
     double nm1;      // (double)(n - 1)
 };
 
-__host__ __device__ inline Axis make_axis(int n) {
+inline Axis make_axis(int n) {                 // host side: passed to the kernels by value
     Axis a;
     a.n = n;
     a.nm1 = (double)(n - 1);
@@ -39,51 +39,58 @@ __device__ __forceinline__ double grid_coord(const Axis& a, int i) {
     return (i >= a.n - 1) ? 1.0 : __dmul_rn((double)i, a.step);
 }
 
+// Straight-line form, no conversions and no data-dependent branch on the hot path.
+//   i  = rint(c (n-1) - 0.5) by the add-magic trick: the integer is the low word of the sum, its
+//        double the sum minus the magic.  i estimates L and can be off by one -- but only when c
+//        lies within a few ulp of a grid coordinate, and then that coordinate IS the nearest
+//        one and the comparison below still lands on it (checked exhaustively against pandas in
+//        tests/test_gpu_cells.py), so no correction step is needed.
+//   gl = g(i), gr = g(i+1) with the linspace quirk g(n-1) = 1.0 exactly.
+//   out-of-range c gives i < 0 or i > n-2; the final clamp resolves those to 0 / n-1.
+// gl == c needs no special case (then 0 < gr - c picks i).
 __device__ __forceinline__ int nearest_cell(double c, const Axis& a) {
-    if (!(c > 0.0)) return 0;                 // c <= 0 (and NaN): first cell
-    if (c >= 1.0) return a.n - 1;
-    int i = (int)(c * a.nm1);                 // floor estimate of L, off by at most one
-    if (i > a.n - 2) i = a.n - 2;
-    double gl = grid_coord(a, i), gr = grid_coord(a, i + 1);
-    if (gl > c) {                             // (rare) estimate one too high
-        --i;
-        gr = gl;
-        gl = grid_coord(a, i);
-    } else if (gr <= c) {                     // (rare) estimate one too low
-        ++i;
-        gl = gr;
-        gr = grid_coord(a, i + 1);
-    }
-    if (gl == c) return i;
-    return (__dsub_rn(c, gl) < __dsub_rn(gr, c)) ? i : i + 1;
+    if (!(fabs(c) < 4.0)) return (c >= 4.0) ? a.n - 1 : 0;            // absurd / NaN: clamp (never hot)
+    const double u = __dadd_rn(__dsub_rn(__dmul_rn(c, a.nm1), 0.5), DIE_RINT_MAGIC);
+    const int i = __double2loint(u);
+    const double di = __dsub_rn(u, DIE_RINT_MAGIC);
+    const double gl = __dmul_rn(di, a.step);
+    const double gr = (i == a.n - 2) ? 1.0 : __dmul_rn(__dadd_rn(di, 1.0), a.step);
+    const int r = (__dsub_rn(c, gl) < __dsub_rn(gr, c)) ? i : i + 1;
+    return min(max(r, 0), a.n - 1);
 }
 
 // ---- numpy float remainder ----------------------------------------------------------------
-// exact fmod for |a| < 2|b| (Sterbenz), generic fmod otherwise
-__device__ __forceinline__ double fmod_small(double a, double b) {
-    const double fa = fabs(a), fb = fabs(b);
-    if (fa < fb) return a;
-    if (fa < 2.0 * fb) return copysign(__dsub_rn(fa, fb), a);
-    return fmod(a, b);
-}
-
-// np.remainder(a, b): sign of b; exact zero gets the sign of b.
+// np.remainder(a, b) = fmod(a, b), moved into the sign of b; an exact zero gets the sign of b.
+// fmod is exact; for |a| < 2|b| it is a or |a| - |b| (Sterbenz), which is all the hot path
+// ever sees, so the generic fmod() sits behind an unlikely branch.
 __device__ __forceinline__ double np_remainder(double a, double b) {
-    double m = fmod_small(a, b);
-    if (m != 0.0) {
-        if ((b < 0.0) != (m < 0.0)) m = __dadd_rn(m, b);
-    } else {
-        m = copysign(0.0, b);
-    }
-    return m;
+    const double fa = fabs(a), fb = fabs(b);
+    double m;
+    if (fa < 2.0 * fb) m = (fa < fb) ? a : copysign(__dsub_rn(fa, fb), a);
+    else m = fmod(a, b);
+    if (m == 0.0) return copysign(0.0, b);
+    return ((b < 0.0) != (m < 0.0)) ? __dadd_rn(m, b) : m;
 }
 
 // coords % 1.  (core/env.py:155) -- returns exactly 1.0 for tiny negatives.
 __device__ __forceinline__ double mod1(double a) { return np_remainder(a, 1.0); }
 
 // renormalize_radians (core/utils.py:177-179): (r - pi) % (-2 pi) + pi, in (-pi, pi].
+// np.remainder(a, -2pi) spelled out for |a| < 4 pi (all the hot path ever sees): fmod(a, -2pi) is
+// a, a - 2pi or a + 2pi (exact), and a positive remainder is moved into the divisor's sign by one
+// ROUNDED add of -2pi.  The sign of a zero remainder is irrelevant here (+-0 + pi = pi).
 __device__ __forceinline__ double renormalize_radians(double r) {
-    return __dadd_rn(np_remainder(__dsub_rn(r, kPi), -kTwoPi), kPi);
+    const double a = __dsub_rn(r, kPi);
+    double m;
+    if (fabs(a) < 2.0 * kTwoPi) {
+        double f = a;
+        if (a >= kTwoPi) f = __dsub_rn(a, kTwoPi);
+        else if (a <= -kTwoPi) f = __dadd_rn(a, kTwoPi);
+        m = (f > 0.0) ? __dsub_rn(f, kTwoPi) : f;
+    } else {
+        m = np_remainder(a, -kTwoPi);
+    }
+    return __dadd_rn(m, kPi);
 }
 
 // np.angle(x + np.multiply(1j, y))  (core/utils.py:158-168).  The complex construction
@@ -100,7 +107,7 @@ __device__ __forceinline__ double angle_xy(double x, double y) {
 
 // np.nan_to_num(a / n)  (core/agent/gradient.py:62)
 __device__ __forceinline__ double div_nan_to_num(double a, double n) {
-    double q = a / n;
+    const double q = __ddiv_rn(a, n);
     if (isnan(q)) return 0.0;
     if (isinf(q)) return copysign(DBL_MAX, q);
     return q;

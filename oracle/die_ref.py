@@ -498,9 +498,10 @@ class GradientAgent:
         sx, sy = self._nearest(pos[0], h), self._nearest(pos[1], w)
         self.last_sense_cells = (sx, sy)
         grad = grad_field[:, sx, sy]
+        self._fused_angle = None
         grad = self._process_gradient(grad, coin)
         grad = self._process_momentum(grad, noise)
-        self._direction_rads = get_radians(grad)
+        self._direction_rads = get_radians(grad) if self._fused_angle is None else self._fused_angle
 
         ix, iy = self._nearest(agents[AG_X], h), self._nearest(agents[AG_Y], w)
         deposit = self._process_deposit(agents, medium[CH_FOOD][ix, iy])
@@ -553,6 +554,13 @@ class PhysarumAgent(GradientAgent):
         turn = self._choose_turn(drads, coin)
         directions = renormalize_radians(self._direction_rads + turn)
         dr = 1. if self._normalized else dr
+        self._fused_angle = None
+        if _MATH == 'portable' and self._normalized and self._inertia == 0. and self._noise_scale == 0.:
+            # mirror of the kernel: with an identity momentum step the new heading
+            # angle(cos d + i sin d) comes from die_sincos_angle (sin, cos and their angle in one go)
+            from oracle import portable_math
+            s, c, self._fused_angle = portable_math.sincos_angle(directions)
+            return np.stack([dr * c, dr * s])
         return np.stack(polar2xy(dr, directions))
 
     def _process_deposit(self, agents, sensed_food):

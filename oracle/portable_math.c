@@ -15,3 +15,7 @@ void die_atan2_array(const double* y, const double* x, double* out, long n) {
 void die_atan2_fast_array(const double* y, const double* x, double* out, long n) {
     for (long i = 0; i < n; ++i) out[i] = die_atan2_fast(y[i], x[i]);
 }
+
+void die_sincos_angle_array(const double* x, double* sn, double* cs, double* ang, long n) {
+    for (long i = 0; i < n; ++i) die_sincos_angle(x[i], sn + i, cs + i, ang + i);
+}

@@ -32,3 +32,12 @@ def atan2(y, x, fast=False):
     fn = _load().die_atan2_fast_array if fast else _load().die_atan2_array
     fn(y.ctypes.data_as(_dp), x.ctypes.data_as(_dp), out.ctypes.data_as(_dp), ctypes.c_long(x.size))
     return out
+
+
+def sincos_angle(x):
+    """(sin x, cos x, atan2(sin x, cos x)) for |x| <= pi -- die_sincos_angle."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    s, c, a = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    _load().die_sincos_angle_array(x.ctypes.data_as(_dp), s.ctypes.data_as(_dp), c.ctypes.data_as(_dp),
+                                   a.ctypes.data_as(_dp), ctypes.c_long(x.size))
+    return s, c, a
