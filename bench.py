@@ -3,9 +3,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl die_b200|reference]
 
-N = 1 : PhysarumAgent on a single 4096x4096 field, agent_ratio 0.1  (BASELINE.json configs[2])
-N > 1 : 4096 independent 256x256 Physarum envs sharded over the ranks, no data-path collective
-        (BASELINE.json configs[3]); launched by torchrun, one rank per GPU.
+Every N : 4096 independent 256x256 Physarum envs (README params) sharded over the ranks, no data-path
+          collective (BASELINE.json configs[3], "sharded across 1/2/4/8 B200"); strong scaling.
+          For N > 1 launch with torchrun, one rank per GPU.
+N = 1   : additionally the single 4096x4096 Physarum field (BASELINE.json configs[2]) is measured in the
+          same run and reported under "also" (its own value + roofline).
 Rank 0 prints ONE JSON line.  `value` = cell-updates/s of the whole job with state resident in
 HBM; `e2e` = the same loop through the host-buffer API (numpy obs/action cross PCIe every call);
 `roofline` = the dominant kernel's algorithmic bytes / CUDA-event time against the measured HBM
@@ -142,6 +144,101 @@ def lattice_theta_device(B, M, turn_angle, seed, device):
     return k.to(torch.float64) * tr
 
 
+def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_base):
+    """Seeded synthetic state: up to 16 distinct host-built environments, tiled on the device."""
+    n_distinct = 1 if not batched else min(B_local, 16)
+    med_h, ag_h = build_host_state(field, n_distinct, seed=seed_base + 1000 * rank)
+    med = torch.from_numpy(med_h).to(device)
+    ag = torch.from_numpy(ag_h).to(device)
+    if batched and B_local > n_distinct:
+        reps = (B_local + n_distinct - 1) // n_distinct
+        med = med.repeat(reps, 1, 1, 1)[:B_local]
+        ag = ag.repeat(reps, 1, 1)[:B_local]
+    alive = int((ag[:, 2] > 0).sum().item())
+    env = D.Env(field, D.Dynamics(init_agent_ratio=AGENT_RATIO), batch=(B_local if batched else None),
+                init_state=(med, ag), device=device)
+    del med, ag
+    M = env.max_agents
+    agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
+    agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
+    return env, agent, alive
+
+
+def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks):
+    """Warm-up, the timed region (CUDA events, barrier + synchronize on both sides, max over
+    ranks), then the per-kernel breakdown.  Returns a dict of raw measurements."""
+    env, agent, alive_local = make_env_and_agent(D, torch, field, B_local, batched, device, rank, 0)
+    M, C = env.max_agents, field[0] * field[1]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def loop(n, obs):
+        for _ in range(n):
+            action = agent.forward(obs)
+            obs, _, _ = env.step_async(action)
+        return obs
+
+    obs = loop(args.warmup, env._get_current_obs)
+    sync_all()
+    sampler = ClockSampler(device.index)
+    if want_clocks:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    obs = loop(args.steps, obs)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if want_clocks else None
+    from die_b200.sharding import max_over_ranks
+    ms = max_over_ranks(ms, device)                         # device time, max over ranks
+    ms_per_step = ms / args.steps
+
+    # per-kernel breakdown: CUDA events on the launching stream between the kernels
+    env.set_profiling(True)
+    fwd_events = []
+    n_prof = min(args.steps, 200)
+    for _ in range(n_prof):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        action = agent.forward(obs)
+        e1.record()
+        obs, _, _ = env.step_async(action)
+        fwd_events.append((e0, e1))
+    torch.cuda.synchronize()
+    kms, nprof = env.kernel_times()
+    env.set_profiling(False)
+    kernel_ms = {"physarum_forward": sum(a.elapsed_time(b) for a, b in fwd_events) / n_prof}
+    kernel_ms.update({k: v / max(nprof, 1) for k, v in kms.items()})
+    return dict(env=env, agent=agent, ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
+                alive_local=alive_local, M=M, C=C)
+
+
+def roofline_of(meas, B_local, wl_name):
+    peak, peak_src = measured_hbm_peak()
+    M, C, alive_local = meas["M"], meas["C"], meas["alive_local"]
+    slots_local, cells_local = M * B_local, C * B_local
+    kernels = {}
+    for k, t_ms in meas["kernel_ms"].items():
+        units = cells_local if k == "field_step" else slots_local
+        nbytes = BYTES[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
+        gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        kernels[k] = {"ms": round(t_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1),
+                      "frac": round(gbs / peak, 4)}
+    dominant = max((k for k in kernels if BYTES[k] > 0), key=lambda k: kernels[k]["ms"])
+    step_bytes = sum(v["algorithmic_bytes"] for v in kernels.values())
+    step_gbs = step_bytes / (meas["ms_per_step"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": kernels[dominant]["frac"], "peak_source": peak_src,
+            "traffic": ncu_traffic(wl_name, dominant), "kernels": kernels,
+            "step": {"algorithmic_bytes": step_bytes, "gbs": round(step_gbs, 1),
+                     "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4)}}, step_bytes
+
+
 def run_die_b200(args):
     import torch
     import torch.distributed as dist
@@ -161,135 +258,74 @@ def run_die_b200(args):
 
     import die_b200 as D
 
+    # ---- headline workload: 4096 independent 256x256 Physarum envs sharded over the ranks ----------
     workload = args.workload
     if workload == "auto":
-        workload = "field4096" if n_gpus == 1 else "batch256"
-    if workload == "field4096":
-        field, B_total = (args.field, args.field), 1
-        scaling = "weak"
-    else:
-        field, B_total = (256, 256), args.batch
-        scaling = "strong"
-    if B_total % n_gpus != 0 and workload != "field4096":
-        raise SystemExit(f"batch {B_total} not divisible by {n_gpus} ranks")
-    B_local = B_total // n_gpus if workload != "field4096" else 1
-    batched = workload != "field4096"
-
-    # ---- state ---------------------------------------------------------------------------
+        workload = "batch256"
     t0 = time.time()
-    n_distinct = 1 if not batched else min(B_local, 16)
-    med_h, ag_h = build_host_state(field, n_distinct, seed=1000 * rank)
-    if batched:
-        reps = (B_local + n_distinct - 1) // n_distinct
-        med_h = np.tile(med_h, (reps, 1, 1, 1))[:B_local]
-        ag_h = np.tile(ag_h, (reps, 1, 1))[:B_local]
-    env = D.Env(field, D.Dynamics(init_agent_ratio=AGENT_RATIO), batch=(B_local if batched else None),
-                init_state=(med_h, ag_h), device=device)
-    M = env.max_agents
-    C = field[0] * field[1]
-    alive_local = int((ag_h[:, 2] > 0).sum())
-    del med_h, ag_h
-    agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
-    agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
+    if workload == "field4096":
+        field, B_total, batched, scaling = (args.field, args.field), 1, False, "weak"
+        B_local = 1
+        wl_name = "physarum_single_field_%dx%d" % field
+    else:
+        field, B_total, batched, scaling = (256, 256), args.batch, True, "strong"
+        from die_b200.sharding import shard_range
+        lo, hi = shard_range(B_total, n_gpus, rank)          # block partition, no data-path collective
+        B_local = hi - lo
+        wl_name = f"physarum_batched_{B_total}x256x256"
+    meas = measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks=(rank == 0))
     setup_s = time.time() - t0
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def loop(n, obs):
-        for _ in range(n):
-            action = agent.forward(obs)
-            obs, _, _ = env.step_async(action)
-        return obs
-
-    # ---- warm-up + timed region (device resident) ------------------------------------------------
-    obs = env._get_current_obs
-    obs = loop(args.warmup, obs)
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    obs = loop(args.steps, obs)
-    ev1.record()
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+    M, C = meas["M"], meas["C"]
+    ms_per_step = meas["ms_per_step"]
     cells_per_step = C * B_total
     value = cells_per_step / (ms_per_step * 1e-3)
+    roofline, step_bytes = roofline_of(meas, B_local, wl_name)
+    alive_local = meas["alive_local"]
+    del meas["env"], meas["agent"]
+    torch.cuda.empty_cache()
 
-    # ---- per-kernel breakdown with CUDA events on the launching stream ---------------------------
-    env.set_profiling(True)
-    fwd_events = []
-    n_prof = min(args.steps, 200)
-    for _ in range(n_prof):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        action = agent.forward(obs)
-        e1.record()
-        obs, _, _ = env.step_async(action)
-        fwd_events.append((e0, e1))
-    torch.cuda.synchronize()
-    kms, nprof = env.kernel_times()
-    env.set_profiling(False)
-    kernel_ms = {"physarum_forward": sum(a.elapsed_time(b) for a, b in fwd_events) / n_prof}
-    kernel_ms.update({k: v / max(nprof, 1) for k, v in kms.items()})
-    peak, peak_src = measured_hbm_peak()
-    slots_local, cells_local = M * B_local, C * B_local
-    kernels = {}
-    for k, t_ms in kernel_ms.items():
-        units = cells_local if k == "field_step" else slots_local
-        nbytes = BYTES[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
-        gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
-        kernels[k] = {"ms": round(t_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1),
-                      "frac": round(gbs / peak, 4)}
-    dominant = max((k for k in kernels if BYTES[k] > 0), key=lambda k: kernels[k]["ms"])
-    step_bytes = sum(v["algorithmic_bytes"] for v in kernels.values())
-    wl_name = ("physarum_single_field_%dx%d" % field) if not batched else f"physarum_batched_{B_total}x256x256"
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dominant]["frac"], "peak_source": peak_src,
-                "traffic": ncu_traffic(wl_name, dominant),
-                "kernels": kernels,
-                "step": {"algorithmic_bytes": step_bytes,
-                         "gbs": round(step_bytes / (ms_per_step * 1e-3) / 1e9 * (1 if batched else 1), 1),
-                         "frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
-                         "frac_of_8TBs_nominal": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0, 4)}}
+    # ---- N = 1 only: the single 4096x4096 field (BASELINE.json configs[2]) in the same run ----------
+    also = None
+    if n_gpus == 1 and workload == "batch256" and not args.no_single_field:
+        f2 = (args.field, args.field)
+        m2 = measure(D, torch, dist, args, f2, 1, False, device, rank, world, want_clocks=False)
+        r2, sb2 = roofline_of(m2, 1, "physarum_single_field_%dx%d" % f2)
+        also = {"physarum_single_field_%dx%d" % f2: {
+            "value": f2[0] * f2[1] / (m2["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m2["ms_per_step"],
+            "max_agents": m2["M"], "alive_agents": m2["alive_local"], "roofline": r2}}
+        del m2
+        torch.cuda.empty_cache()
 
-    # ---- e2e: the same loop through the host-buffer API -----------------------------------------
+    # ---- e2e: the same loop through the host-buffer API (numpy obs/action cross PCIe every call) ----
     e2e = None
     if not args.no_e2e:
+        B_e2e = min(B_local, args.e2e_envs) if batched else 1
+        env, agent, _ = make_env_and_agent(D, torch, field, B_e2e, batched, device, rank, 50)
         k_e2e = max(3, min(args.steps, args.e2e_steps))
         hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
         for _ in range(2):                                   # warm the pinned staging buffers
             hact = agent.forward(hobs)
             hobs, *_ = env.step(hact)
-        sync_all()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t_start = time.perf_counter()
         for _ in range(k_e2e):
             hact = agent.forward(hobs)                       # H2D obs, kernel, D2H action
             hobs, hr, _, _, _ = env.step(hact)               # H2D action, kernels, D2H obs + reward
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t_start
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
+        from die_b200.sharding import max_over_ranks
+        t_e2e = max_over_ranks(t_e2e, device)
         h2d_step, d2h_step = env.host_io_bytes_per_step()
-        fwd_h2d = 8 * B_local * (4 * M + 3 * C)
-        fwd_d2h = 8 * B_local * 3 * M
-        e2e = {"value": cells_per_step * k_e2e / t_e2e, "unit": UNIT, "steps": k_e2e,
-               "ms_per_step": t_e2e / k_e2e * 1e3,
+        fwd_h2d = 8 * B_e2e * (4 * M + 3 * C)
+        fwd_d2h = 8 * B_e2e * 3 * M
+        e2e = {"value": C * B_e2e * n_gpus * k_e2e / t_e2e, "unit": UNIT, "steps": k_e2e,
+               "ms_per_step": t_e2e / k_e2e * 1e3, "envs_per_gpu": B_e2e,
                "h2d_bytes_per_step": (h2d_step + fwd_h2d) * n_gpus, "d2h_bytes_per_step": (d2h_step + fwd_d2h) * n_gpus,
-               "api": "numpy obs/action across Agent.forward and Env.step (die_env_step_host)"}
+               "api": "numpy obs/action across Agent.forward and Env.step (die_env_step_host); PCIe-bound, "
+                      "so measured on a bounded number of envs per GPU (pinned host memory)"}
+        del env, agent
 
     # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------
     cpu = None
@@ -308,8 +344,8 @@ def run_die_b200(args):
                              % (step_bytes / 1e9)},
             "agent_steps_per_s": M * B_total / (ms_per_step * 1e-3),
             "alive_agent_steps_per_s": alive_local * n_gpus / (ms_per_step * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps * 5 * 1, "launches_per_step": 5, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "also": also,
+            "gpu_launches": args.steps * 5, "launches_per_step": 5, "clocks": meas["clocks"],
             "setup_s": round(setup_s, 1),
         }
         print(json.dumps(line))
@@ -369,10 +405,10 @@ def run_reference(args):
     sample = (f"each step = one PhysarumAgent.forward + Env.step on a {field_n}x{field_n} field "
               f"(same per-cell work as the GPU arm's workload), numpy/scipy oracle port, 1 thread "
               f"(the reference is single-threaded)")
-    wl = "physarum_single_field_4096x4096" if n_gpus == 1 else "physarum_batched_4096x256x256"
+    wl = "physarum_batched_4096x256x256"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak" if n_gpus == 1 else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": wl, "sample_field": list(field),
                                                             "agent": "PhysarumAgent", **PHYS,
                                                             "agent_ratio": AGENT_RATIO},
@@ -391,7 +427,9 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "field4096", "batch256"])
     ap.add_argument("--field", type=int, default=4096, help="side of the single field (field4096 workload)")
     ap.add_argument("--batch", type=int, default=4096, help="total number of 256x256 envs (batch256 workload)")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU on the host-buffer (e2e) leg")
+    ap.add_argument("--no-single-field", action="store_true")
     ap.add_argument("--cpu-field", type=int, default=512, help="side of the CPU sample field")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-e2e", action="store_true")

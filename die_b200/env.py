@@ -162,16 +162,24 @@ class Env:
                 mediums.append(m)
                 agentss.append(data_init.agents_from_medium(m))
             medium, agents = np.stack(mediums), np.stack(agentss)
+        elif isinstance(init_state[0], torch.Tensor):
+            # device (or host) tensors: no numpy round trip (large batches are assembled on the GPU)
+            medium = init_state[0].to(dtype=torch.float64).reshape(B, 3, h, w)
+            agents = init_state[1].to(dtype=torch.float64).reshape(B, 4, -1)
         else:
             medium, agents = (np.asarray(a, dtype=np.float64) for a in init_state)
             medium = medium.reshape(B, 3, h, w)
             agents = agents.reshape(B, 4, -1)
         self._M = int(agents.shape[-1])
         with torch.cuda.device(self.device):
-            self._medium_buf = [torch.from_numpy(np.ascontiguousarray(medium)).to(self.device),
-                                torch.empty((B, 3, h, w), dtype=torch.float64, device=self.device)]
+            if isinstance(medium, torch.Tensor):
+                first = medium.to(self.device).contiguous().clone()
+                self._agents = agents.to(self.device).contiguous().clone()
+            else:
+                first = torch.from_numpy(np.ascontiguousarray(medium)).to(self.device)
+                self._agents = torch.from_numpy(np.ascontiguousarray(agents)).to(self.device)
+            self._medium_buf = [first, torch.empty((B, 3, h, w), dtype=torch.float64, device=self.device)]
             self._cur = 0
-            self._agents = torch.from_numpy(np.ascontiguousarray(agents)).to(self.device)
             self._reward_dev = torch.zeros(B, dtype=torch.float64, device=self.device)
             self._alive_dev = torch.zeros(B, dtype=torch.int64, device=self.device)
             self._stats_host = torch.zeros(2 * B, dtype=torch.float64).pin_memory()
