@@ -4,17 +4,26 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``die_b200/`` imports this module; only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs do, and only as the checker / the timed CPU baseline.
 
-PARITY UNPINNED: the reference cannot be imported here (xarray, skimage,
-perlin_noise, gymnasium, matplotlib, evotorch are absent and there is no network),
-and the reference's own tests (``test/unit/agent.py``) never touch this path, so
-there are no golden vectors from the reference itself.  What *is* pinned, in
-``tests/test_oracle_*.py``: every third-party primitive this file leans on is checked
-bit-for-bit against the library the reference's arithmetic bottoms out in
-(``scipy.ndimage.gaussian_filter`` for ``skimage.filters.gaussian``,
-``pandas.Index.get_indexer(method='nearest')`` for ``xarray .sel(method='nearest')``,
-numpy for ``%``, ``np.gradient``, ``np.angle``, ``np.isclose``, duplicate fancy-assign).
-A second, independent check runs the reference's *own source files* over minimal
-stand-ins for the missing packages (``oracle/shims``); see ``oracle/README.md``.
+PARITY STATUS: the reference cannot be imported as is (xarray, skimage, perlin_noise, gymnasium,
+matplotlib, evotorch are absent, there is no network) and its own tests (``test/unit/agent.py``)
+never touch this path, so there are no golden vectors shipped by the reference: formally
+"parity unpinned".  What pins this file instead:
+  1. ``tests/test_golden_oracle.py::test_oracle_equals_reference_executed_live`` runs the
+     reference's OWN source files (``/root/reference/core/*.py``, unmodified) over minimal stand-ins
+     for the missing packages (``oracle/shims``: xarray.DataArray on numpy + pandas.get_indexer,
+     skimage.filters.gaussian on scipy.ndimage) side by side with this restatement: actions,
+     rewards, info, medium, agents and headings are IDENTICAL BIT FOR BIT at every step, for
+     Brownian / Const / Physarum agents and default / non-default dynamics.
+  2. ``tests/golden/*.npz`` are vectors recorded from those runs
+     (``oracle/make_golden_from_reference.py``); this oracle and the CUDA path are both checked
+     against them (the reference itself does not travel to the GPU box, the vectors do).
+  3. ``tests/test_oracle_primitives.py`` checks every third-party primitive bit-for-bit against the
+     library the reference's arithmetic bottoms out in (``scipy.ndimage.gaussian_filter`` for
+     ``skimage.filters.gaussian``, ``pandas.Index.get_indexer(method='nearest')`` for
+     ``xarray .sel(method='nearest')``, numpy for ``%``, ``np.gradient``, ``np.angle``,
+     ``np.isclose``, duplicate fancy-assign).
+What remains restated rather than executed: xarray's own semantics (vectorised pointwise
+indexing, get-add-set through ``.loc`` with repeated cells) -- see ``oracle/shims/README.md``.
 
 Everything is float64 and in *index form*: xarray label lookups are replaced by the
 integer cell indices they resolve to.  All citations are ``file:line`` relative to
