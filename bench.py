@@ -36,11 +36,14 @@ UNIT = "cell-updates/s"
 # Algorithmic bytes (float64 fields and agents, s_f = s_a = 8):
 #   physarum_forward  R{x,y,theta} W{theta,dx,dy,dep} + gathers{4 chem, 1 food}        = 96 B / slot
 #   move_claim        R{x,y,alive,dx,dy} W{x,y}                                          = 56 B / slot
-#   deposit_feed      R{agent_food,dep} W{agent_food} + gathers{food,occ} (+16 B/alive)  = 40 B / slot
-#   field_step        chem R+W, food R+W, occupancy R+W                                  = 48 B / cell
-BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "deposit_feed": 40.0, "field_step": 48.0,
+#   agent_feed        R{agent_food,dep} W{agent_food} + gathers{food,occ}                = 40 B / slot
+#   field_step        chem R+W, food R+W, occupancy R+W (+24 B per alive agent:         = 48 B / cell
+#                     its deposit gather, chem add and occupancy write)
+# (the survey's model; implementation extras -- the 4 B/cell claim table, the 4 B/slot cell cache,
+#  the 8 B/cell consumed_field scratch, dx/dy re-read by the feed kernel -- are NOT counted)
+BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "agent_feed": 40.0, "field_step": 48.0,
          "finalize_stats": 0.0}
-ALIVE_EXTRA = {"deposit_feed": 16.0, "field_step": 8.0}        # chem RMW, occupancy write of alive cells
+ALIVE_EXTRA = {"field_step": 24.0}
 
 
 def measured_hbm_peak():

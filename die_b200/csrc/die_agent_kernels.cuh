@@ -299,47 +299,41 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 }
 
 // ---------------------------------------------------------------------------------------------
-// Env._agent_deposit_and_layout (chem part, core/env.py:204-211) + Env._agent_feed per-slot
-// part (core/env.py:220-234, cost :29-35) + the reward / num_agents reduction (:118-121).
-// Block partials are written in a fixed layout and summed in a fixed order by
-// finalize_stats_kernel, so the reward is run-to-run deterministic.
+// Env._agent_feed per-slot part (core/env.py:220-234, cost :29-35) + the reward / num_agents
+// reduction (:118-121).  consumed[M] = consumed_field[cell(slot)] for ALL M slots (Q1, Q7), where
+// consumed_field = rate_feed * food * occ was written per cell by the field pass.  Alive slots also
+// clear their cell's claim for the next step.  Block partials are written in a fixed layout and
+// summed in a fixed order by finalize_stats_kernel, so the reward is run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
-// food / chem are the env_food / chem1 channels of the same medium buffer (disjoint ranges), passed
-// as separate restrict pointers so that the chem1 store of one slot does not fence the gathers of
-// the next: all of a thread's loads are issued before its first store.
 __global__ void __launch_bounds__(kAgentThreads)
-deposit_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
-                    const double* __restrict__ food_all, double* __restrict__ chem_all,
-                    const int32_t* __restrict__ winner, const int32_t* __restrict__ cells,
-                    double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
-                    int64_t C, int64_t M, int nblk,
-                    double rate_feed, double w_dep, double w_dist) {
+agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
+                  const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
+                  const int32_t* __restrict__ cells,
+                  double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
+                  int64_t C, int64_t M, int nblk, double w_dep, double w_dist) {
     const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
     double* ag_alive = agents + (b * 4 + 2) * M + first;       // alive; agent_food is + M
     const double* ac = action + b * 3 * M + first;
-    const double* food = food_all + b * 3 * C;
-    double* chem = chem_all + b * 3 * C;
-    const int32_t* win = winner + b * C;
+    const double* cf = consumed_field + b * C;
+    int32_t* win = winner + b * C;
     const int32_t* cl = cells + b * M + first;
 
-    int cell[kFeedItems], w[kFeedItems];
-    double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], f[kFeedItems];
+    int cell[kFeedItems];
+    double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], eaten[kFeedItems];
     bool alive[kFeedItems], valid[kFeedItems];
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
-        const int i = k * kAgentThreads;
-        valid[k] = first + i < M;
-        cell[k] = valid[k] ? cl[i] : 0;
+        valid[k] = first + k * kAgentThreads < M;
+        cell[k] = valid[k] ? cl[k * kAgentThreads] : 0;
     }
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        w[k] = valid[k] ? win[cell[k]] : -1;
-        f[k] = valid[k] ? food[cell[k]] : 0.0;
+        eaten[k] = valid[k] ? cf[cell[k]] : 0.0;
         alive[k] = valid[k] && ag_alive[i] > 0.0;
         stock[k] = valid[k] ? ag_alive[M + i] : 0.0;
         dx[k] = valid[k] ? ac[i] : 0.0;
@@ -351,15 +345,14 @@ deposit_feed_kernel(double* __restrict__ agents, const double* __restrict__ acti
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         if (valid[k]) {
-            const int i = k * kAgentThreads;
-            const int64_t slot = first + i;
-            if (alive[k] && w[k] == (int)slot) chem[cell[k]] = chem[cell[k]] + dep[k];   // winner's deposit lands once
-            const double consumed = (rate_feed * f[k]) * ((w[k] >= 0) ? 1.0 : 0.0);      // Q1, Q7
             const double burned = w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
-            const double gained = consumed - burned;
-            ag_alive[M + i] = stock[k] + gained;
+            const double gained = eaten[k] - burned;
+            ag_alive[M + k * kAgentThreads] = stock[k] + gained;
             gain_sum += gained;
-            alive_cnt += alive[k] ? 1 : 0;
+            if (alive[k]) {
+                win[cell[k]] = -1;                 // claim table back to empty for the next step
+                ++alive_cnt;
+            }
         }
     }
     __shared__ double s_gain[kAgentThreads / 32];

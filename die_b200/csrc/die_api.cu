@@ -36,6 +36,7 @@ struct die_env {
     die_dynamics_t dyn;
     int32_t* winner;       // [B][H*W]  claim table, -1 = empty
     int32_t* cells;        // [B][M]    linear cell of every slot after the move
+    double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double* part_gain;     // [B][nblk]
     int32_t* part_alive;   // [B][nblk]
     int nblk;
@@ -93,6 +94,7 @@ extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
     const size_t C = (size_t)H * W;
     if (err == cudaSuccess) err = cudaMalloc(&e->winner, sizeof(int32_t) * C * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->cells, sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->consumed, sizeof(double) * C * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double) * B);
@@ -112,6 +114,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     if (e == nullptr) return DIE_OK;
     cudaFree(e->winner);
     cudaFree(e->cells);
+    cudaFree(e->consumed);
     cudaFree(e->part_gain);
     cudaFree(e->part_alive);
     cudaFree(e->action_stage);
@@ -182,12 +185,16 @@ static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static cudaError_t launch_field_any(const die_env* e, const double* min, double* mout, cudaStream_t st) {
+static cudaError_t launch_field_any(const die_env* e, const double* min, double* mout, const double* action,
+                                    cudaStream_t st) {
     FieldArgs a;
     memset(&a, 0, sizeof(a));
     a.medium_in = min;
     a.medium_out = mout;
     a.winner = e->winner;
+    a.action = action;
+    a.consumed = e->consumed;
+    a.M = e->M;
     a.H = e->H;
     a.W = e->W;
     a.rate_feed = e->dyn.rate_feed;
@@ -231,14 +238,13 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 1, st);
 
-    deposit_feed_kernel<<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, medium_in + (size_t)e->H * e->W, medium_in + 2 * (size_t)e->H * e->W,
-        e->winner, e->cells, e->part_gain, e->part_alive,
-        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.rate_feed, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
-    DIE_CUDA(cudaGetLastError());
+    DIE_CUDA(launch_field_any(e, medium_in, medium_out, action, st));
     prof_mark(e, 2, st);
 
-    DIE_CUDA(launch_field_any(e, medium_in, medium_out, st));
+    agent_feed_kernel<<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
+        agents, action, e->consumed, e->winner, e->cells, e->part_gain, e->part_alive,
+        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
+    DIE_CUDA(cudaGetLastError());
     prof_mark(e, 3, st);
 
     finalize_stats_kernel<<<e->B, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, reward_dev, alive_dev);

@@ -1,15 +1,20 @@
 // die_field_kernels.cuh -- the dense half of Env.step: one pass over every cell that fuses
-//   occupancy layout      medium['agents'] = 0; [cells] = 1        core/env.py:214-215
-//   food consumption      food -= rate_feed * food * (occ > 0)     core/env.py:224-228
-//   food flow             identity                                 core/env.py:147-150
-//   diffusion * decay     gaussian(chem, sigma, 'wrap') * (1-d)    core/env.py:136-145
-//   claim-table reset     (winner = -1 for the next step)
-// reading medium_in (+ the claim table) and writing medium_out: 6 doubles of algorithmic
-// traffic per cell (chem R+W, food R+W, occupancy W, + 2x4 B of claim table).
+//   pheromone deposit     chem[cell] = chem[cell] + deposit[winner]   core/env.py:211  (Q2)
+//   occupancy layout      medium['agents'] = 0; [cells] = 1            core/env.py:214-215
+//   food consumption      food -= rate_feed * food * (occ > 0)         core/env.py:224-228
+//   food flow             identity                                     core/env.py:147-150
+//   diffusion * decay     gaussian(chem, sigma, 'wrap') * (1-d)        core/env.py:136-145
+// reading medium_in (never written) and the claim table, writing medium_out and the per-cell
+// consumed_field (rate_feed * food * occ, core/env.py:224) that the agent feed kernel gathers.
+// Algorithmic traffic: chem R+W, food R+W, occupancy W (+ claim table 4 B R, consumed 8 B W).
 //
-// The blur is scipy.ndimage's separable correlate1d in its exact operation order (axis 0
-// then axis 1, each  x0*w0 + (x[-r]+x[+r])*w[-r] + ... + (x[-1]+x[+1])*w[-1], periodic), so
-// the result is bit-identical to skimage.filters.gaussian on the same input.
+// The deposit is applied while the halo tile is staged: every staged cell reads its claim
+// (the winning slot, or -1) and, when claimed, gathers that slot's deposit1 -- so the previous
+// medium buffer stays intact and no scatter into the field is needed.
+//
+// The blur is scipy.ndimage's separable correlate1d in its exact operation order (axis 0 then
+// axis 1, each  x0*w0 + (x[-r]+x[+r])*w[-r] + ... + (x[-1]+x[+1])*w[-1], periodic), so the result
+// is bit-identical to skimage.filters.gaussian on the same input.
 #pragma once
 #include "die_device.cuh"
 #include "../../include/die_b200.h"
@@ -23,13 +28,16 @@ struct BlurWeights {
 struct FieldArgs {
     const double* medium_in;
     double* medium_out;
-    int32_t* winner;
+    const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
+    const double* action;        // [B][3][M]; channel 2 = deposit1
+    double* consumed;            // [B][H*W] consumed_field out
     int H, W;
+    int64_t M;
     int tiles_i, tiles_j;
     double rate_feed;
-    double keep;             // 1. - rate_decay_chem
+    double keep;                 // 1. - rate_decay_chem
     int food_infinite;
-    BlurWeights bw;          // centre at [R]
+    BlurWeights bw;              // centre at [R]
 };
 
 __device__ __forceinline__ int wrap_index(int i, int n) {
@@ -37,13 +45,16 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
     return i < 0 ? i + n : i;
 }
 
-// Tile TH x TW outputs per CTA; (TH+2R) x (TW+2R) chem halo tile staged in shared memory,
-// vertical (axis 0) pass into a second shared tile, horizontal (axis 1) pass to global.
+// Tile TH x TW outputs per CTA; (TH+2R) x (TW+2R) chem halo tile staged in shared memory
+// (deposit applied on the way in), axis-0 pass into a second shared tile, axis-1 pass to global.
+// Staging is done in two sweeps so that all of a thread's (independent) chem + claim loads are
+// in flight before the first dependent deposit gather.
 template <int R, int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
     constexpr int LW = TW + 2 * R;           // staged row length
     constexpr int LH = TH + 2 * R;
+    constexpr int NSTAGE = (LH * LW + NT - 1) / NT;
     extern __shared__ double smem[];
     double* s_in = smem;                     // [LH][LW]
     double* s_v = smem + LH * LW;            // [TH][LW]
@@ -51,7 +62,7 @@ field_step_kernel(const FieldArgs a) {
     const int H = a.H, W = a.W;
     const int64_t C = (int64_t)H * W;
     const int tiles = a.tiles_i * a.tiles_j;
-    const int64_t b = blockIdx.x / tiles;
+    const int64_t b = blockIdx.x / (unsigned)tiles;
     const int t = blockIdx.x - (int)b * tiles;
     const int ti = t / a.tiles_j, tj = t - ti * a.tiles_j;
     const int i0 = ti * TH, j0 = tj * TW;
@@ -61,14 +72,31 @@ field_step_kernel(const FieldArgs a) {
     double* occ_out = a.medium_out + (b * 3 + 0) * C;
     double* food_out = a.medium_out + (b * 3 + 1) * C;
     double* chem_out = a.medium_out + (b * 3 + 2) * C;
-    int32_t* win = a.winner + b * C;
+    const int32_t* win = a.winner + b * C;
+    const double* dep = a.action + (b * 3 + 2) * a.M;
+    double* cons = a.consumed + b * C;
 
-    // ---- stage the periodic halo tile ---------------------------------------------------
-    for (int idx = threadIdx.x; idx < LH * LW; idx += NT) {
-        const int r = idx / LW, c = idx - r * LW;
-        const int gi = wrap_index(i0 - R + r, H);
-        const int gj = wrap_index(j0 - R + c, W);
-        s_in[idx] = chem_in[(int64_t)gi * W + gj];
+    // ---- stage the periodic halo tile, deposit included -------------------------------------
+    double v[NSTAGE];
+    int w[NSTAGE];
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int idx = threadIdx.x + s * NT;
+        v[s] = 0.0;
+        w[s] = -1;
+        if (idx < LH * LW) {
+            const int r = idx / LW, c = idx - r * LW;
+            const int gi = wrap_index(i0 - R + r, H);
+            const int gj = wrap_index(j0 - R + c, W);
+            const int g = gi * W + gj;
+            v[s] = chem_in[g];
+            w[s] = win[g];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+        const int idx = threadIdx.x + s * NT;
+        if (idx < LH * LW) s_in[idx] = (w[s] >= 0) ? v[s] + dep[w[s]] : v[s];
     }
     __syncthreads();
 
@@ -92,16 +120,15 @@ field_step_kernel(const FieldArgs a) {
             double acc = p[0] * a.bw.w[R];
 #pragma unroll
             for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
-            const int64_t g = (int64_t)gi * W + gj;
+            const int g = gi * W + gj;
             chem_out[g] = acc * a.keep;
 
-            const int w = win[g];
-            const double occ = (w >= 0) ? 1.0 : 0.0;
+            const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
-            const double cf = (a.rate_feed * f) * occ;
+            const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
             food_out[g] = a.food_infinite ? f : f - cf;
             occ_out[g] = occ;
-            if (w >= 0) win[g] = -1;
+            cons[g] = cf;
         }
     }
 }
@@ -118,10 +145,13 @@ field_step_noblur_kernel(const FieldArgs a, int64_t total) {
         const int w = a.winner[gid];
         const double occ = (w >= 0) ? 1.0 : 0.0;
         const double f = min[C + g];
+        const double cf = (a.rate_feed * f) * occ;
+        double chem = min[2 * C + g];
+        if (w >= 0) chem = chem + a.action[(b * 3 + 2) * a.M + w];
         mout[g] = occ;
-        mout[C + g] = a.food_infinite ? f : f - (a.rate_feed * f) * occ;
-        mout[2 * C + g] = (min[2 * C + g] * a.bw.w[0]) * a.bw.w[0] * a.keep;
-        if (w >= 0) a.winner[gid] = -1;
+        mout[C + g] = a.food_infinite ? f : f - cf;
+        mout[2 * C + g] = (chem * a.bw.w[0]) * a.bw.w[0] * a.keep;
+        a.consumed[gid] = cf;
     }
 }
 

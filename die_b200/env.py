@@ -3,8 +3,8 @@
 Same class names, constructor, ``step`` signature and return tuple as the reference
 (core/env.py:42-131).  State lives in HBM as float64 torch tensors in the reference's
 channel-major layout and every ``step`` is four kernel launches of ``libdie_sm100a.so``
-through its C ABI (``include/die_b200.h``): move+claim, deposit+feed+reduce, the fused
-field pass, and the stats finalisation.  There is no CPU fallback.
+through its C ABI (``include/die_b200.h``): move+claim, the fused field pass (deposit, occupancy,
+food, diffusion*decay), agent feed+reduce, and the stats finalisation.  There is no CPU fallback.
 
 Differences a caller of the reference can observe (all documented in DESIGN.md):
   * obs / action are ``torch`` CUDA tensors (or pinned ``numpy`` arrays on the host-buffer
@@ -353,7 +353,7 @@ class Env:
         return 8 * B * 3 * M, 8 * B * (4 * M + 3 * h * w) + 16 * B
 
     # -- measurement aid ----------------------------------------------------------------------
-    STEP_KERNELS = ('move_claim', 'deposit_feed', 'field_step', 'finalize_stats')
+    STEP_KERNELS = ('move_claim', 'field_step', 'agent_feed', 'finalize_stats')
 
     def set_profiling(self, on: bool) -> None:
         """Record CUDA events between the step's kernels (bench.py's per-kernel roofline)."""

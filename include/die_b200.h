@@ -89,8 +89,8 @@ int die_env_destroy(die_env_t* env);
 int die_env_set_dynamics(die_env_t* env, const die_dynamics_t* dyn);
 
 /* Env.step, core/env.py:101-131: move -> deposit + layout -> feed -> food flow ->
- * diffuse*decay -> reward / num_agents.  Reads medium_in (its chem1 channel is updated
- * in place by the deposit), writes the next medium into medium_out (a different buffer),
+ * diffuse*decay -> reward / num_agents.  Reads medium_in (never written: the previous
+ * observation stays valid), writes the next medium into medium_out (a different buffer),
  * updates agents in place.  reward_dev[B] = sum over ALL M slots of gained; alive_dev[B] =
  * #(alive > 0).  die_env_cells() exposes the int32 [B][M] linear cell index ix*W+iy of
  * every slot after the move (validation aid). */
@@ -102,7 +102,7 @@ const int32_t* die_env_cells(const die_env_t* env);   /* device ptr, int32 [B][M
 /* Per-kernel timing of Env.step with CUDA events recorded on the launching stream between
  * the step's kernels (measurement aid for bench.py's roofline; off by default).
  * die_env_kernel_times synchronises the recorded events and returns the accumulated
- * milliseconds of {move_claim, deposit_feed, field_step, finalize_stats} and the number of
+ * milliseconds of {move_claim, field_step, agent_feed, finalize_stats} and the number of
  * profiled steps since profiling was (re-)enabled; at most DIE_MAX_PROFILED_STEPS are kept. */
 #define DIE_NUM_STEP_KERNELS     4
 #define DIE_MAX_PROFILED_STEPS   2048
