@@ -55,6 +55,8 @@ SIGNATURES = {
     "die_env_set_dynamics": (C.c_int, [_P, C.POINTER(DieDynamics)]),
     "die_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "die_env_cells": (_P, [_P]),
+    "die_env_publish_gradient": (C.c_int, [_P, C.c_int32]),
+    "die_env_gradient": (_P, [_P]),
     "die_env_set_profiling": (C.c_int, [_P, C.c_int32]),
     "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -62,7 +64,7 @@ SIGNATURES = {
                                        C.c_uint64, C.c_uint64, _P]),
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
-                                       _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "die_math_sincos": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "die_math_atan2": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
 }

@@ -10,6 +10,7 @@ from typing import Optional
 import numpy as np
 import torch
 
+from .. import _hints
 from .. import _lib
 from ..base_types import ActType, ObsType
 from .static import _DeviceAgent, _split_obs
@@ -66,6 +67,8 @@ class GradientAgent(_DeviceAgent):
         self._noise_host = self._noise_dev = None
         self._sense_cells = None
         self.record_sense_cells = False
+        self.use_env_hints = True           # die_b200/_hints.py: cached cells + published gradient
+        self.last_hints = (False, False)
 
     # -- state ------------------------------------------------------------------------------
     def _needs_prev(self) -> bool:
@@ -167,13 +170,17 @@ class GradientAgent(_DeviceAgent):
                 self._sense_cells = torch.empty((B, M), dtype=torch.int32, device=agents.device)
             cells_ptr = self._sense_cells.data_ptr()
 
+        # cached cells / published gradient of the Env that produced this observation, if provably valid
+        grad_hint, cells_hint = _hints.lookup(agents, medium, want_gradient=True) if self.use_env_hints else (None, None)
+        self.last_hints = (grad_hint is not None, cells_hint is not None)
+
         p = self._params_c()
         with torch.cuda.device(agents.device):
             _lib.check(self._lib.die_gradient_forward(
                 _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(),
                 self._theta.data_ptr(),
                 self._prev_grad.data_ptr() if self._prev_grad is not None else None,
-                action.data_ptr(), coin_ptr, noise_ptr, cells_ptr,
+                action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, grad_hint, cells_hint,
                 self._seed, self._step, torch.cuda.current_stream().cuda_stream))
         self._step += 1
         return action

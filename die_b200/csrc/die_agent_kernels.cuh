@@ -118,6 +118,8 @@ struct GradientArgs {
     const uint8_t* coin;        // may be null -> Philox
     const double* noise;        // may be null -> Philox Box-Muller (only if noise_scale != 0)
     int32_t* sense_cells;       // may be null
+    const double2* grad;        // may be null: np.gradient(chem1) per cell, published by Env.step
+    const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
 };
 
@@ -142,6 +144,8 @@ gradient_forward_kernel(const GradientArgs a) {
     const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
     const double* nz = (a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
     int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
+    const double2* grad = (a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
+    const int32_t* cl_p = (a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
 
     uint32_t coin_bits = 0;
     if (DISCRETE_TURN && coin_p == nullptr)      // coin of slot (CTA, t, k) = bit k of this word
@@ -166,19 +170,26 @@ gradient_forward_kernel(const GradientArgs a) {
         // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
         // food under the agent (:113-115), issued early: independent of the turn arithmetic
-        const int ix = nearest_cell(x, ax), iy = nearest_cell(y, ay);
-        const double food_here = food[ix * W + iy];
+        const int here = (cl_p != nullptr) ? cl_p[i] : nearest_cell(x, ax) * W + nearest_cell(y, ay);
+        const double food_here = food[here];
 
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
         const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
         if (sc_p != nullptr) sc_p[i] = sc;
-        const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
-        const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
-        double gx = chem[sc + xp] - chem[sc + xm];
-        double gy = chem[sc + yp] - chem[sc + ym];
-        if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
-        if (yp - ym == 2) gy *= 0.5;
+        double gx, gy;
+        if (grad != nullptr) {                // published by the field pass: one 16-byte gather
+            const double2 g2 = grad[sc];
+            gx = g2.x;
+            gy = g2.y;
+        } else {
+            const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
+            const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
+            gx = chem[sc + xp] - chem[sc + xm];
+            gy = chem[sc + yp] - chem[sc + ym];
+            if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
+            if (yp - ym == 2) gy *= 0.5;
+        }
 
         // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling);
         // grad = nan_to_num(grad / norm) (:62); grad *= (norm >= clip) (:65) keeps signed zeros

@@ -37,6 +37,8 @@ struct die_env {
     int32_t* winner;       // [B][H*W]  claim table, -1 = empty
     int32_t* cells;        // [B][M]    linear cell of every slot after the move
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
+    double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
+    int publish_grad;
     double* part_gain;     // [B][nblk]
     int32_t* part_alive;   // [B][nblk]
     int nblk;
@@ -115,6 +117,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->winner);
     cudaFree(e->cells);
     cudaFree(e->consumed);
+    cudaFree(e->grad);
     cudaFree(e->part_gain);
     cudaFree(e->part_alive);
     cudaFree(e->action_stage);
@@ -137,6 +140,18 @@ extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
 }
 
 extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells : nullptr; }
+
+extern "C" int die_env_publish_gradient(die_env_t* e, int32_t on) {
+    DIE_REQUIRE(e != nullptr);
+    if (on && e->grad == nullptr)
+        DIE_CUDA(cudaMalloc(&e->grad, sizeof(double2) * (size_t)e->H * e->W * e->B));
+    e->publish_grad = on ? 1 : 0;
+    return DIE_OK;
+}
+
+extern "C" const double* die_env_gradient(const die_env_t* e) {
+    return (e && e->publish_grad && e->dyn.blur_radius > 0) ? (const double*)e->grad : nullptr;
+}
 
 extern "C" int die_env_set_profiling(die_env_t* e, int32_t on) {
     DIE_REQUIRE(e != nullptr);
@@ -170,19 +185,25 @@ extern "C" int die_env_kernel_times(die_env_t* e, double* ms_out, int64_t* steps
 // ------------------------------------------------------------------------------------------
 // field pass launch
 // ------------------------------------------------------------------------------------------
-template <int R>
-static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
-    constexpr int TH = 32, TW = 64, NT = 256;
+template <int R, bool GRAD>
+static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
+    constexpr int TH = 32, TW = 64, NT = 256, G = GRAD ? 1 : 0;
     FieldArgs a = fa;
     a.tiles_i = (a.H + TH - 1) / TH;
     a.tiles_j = (a.W + TW - 1) / TW;
-    const size_t smem = sizeof(double) * (size_t)((TH + 2 * R) * (TW + 2 * R) + TH * (TW + 2 * R));
-    auto kern = field_step_kernel<R, TH, TW, NT>;
+    const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
+                                                  (TH + 2 * G) * (TW + 2 * G + 2 * R));
+    auto kern = field_step_kernel<R, TH, TW, NT, GRAD>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     const int64_t grid = (int64_t)a.tiles_i * a.tiles_j * B;
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
+    return fa.grad != nullptr ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
 }
 
 static cudaError_t launch_field_any(const die_env* e, const double* min, double* mout, const double* action,
@@ -194,6 +215,7 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
     a.winner = e->winner;
     a.action = action;
     a.consumed = e->consumed;
+    a.grad = (e->publish_grad && e->dyn.blur_radius > 0) ? e->grad : nullptr;
     a.M = e->M;
     a.H = e->H;
     a.W = e->W;
@@ -312,6 +334,7 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
                                     double* theta, double* prev_grad, double* action,
                                     const uint8_t* coin, const double* noise,
                                     int32_t* sense_cells,
+                                    const double* grad_hint, const int32_t* cells_hint,
                                     uint64_t seed, uint64_t step, void* stream) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
@@ -328,6 +351,7 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     a.ay = make_axis(W);
     a.agents = agents; a.medium = medium; a.theta = theta; a.prev_grad = prev_grad;
     a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
+    a.grad = (const double2*)grad_hint; a.cells = cells_hint;
     a.seed = seed; a.step = step;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     if (p->discrete_turn)

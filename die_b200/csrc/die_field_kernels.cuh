@@ -31,6 +31,7 @@ struct FieldArgs {
     const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
     const double* action;        // [B][3][M]; channel 2 = deposit1
     double* consumed;            // [B][H*W] consumed_field out
+    double2* grad;               // [B][H*W] np.gradient(chem_out) (raw d/dx, d/dy) or null
     int H, W;
     int64_t M;
     int tiles_i, tiles_j;
@@ -45,19 +46,27 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
     return i < 0 ? i + n : i;
 }
 
-// Tile TH x TW outputs per CTA; (TH+2R) x (TW+2R) chem halo tile staged in shared memory
-// (deposit applied on the way in), axis-0 pass into a second shared tile, axis-1 pass to global.
+// Tile TH x TW outputs per CTA.  With GRAD the CTA blurs a one-cell ring more ((TH+2) x (TW+2))
+// so that np.gradient of the NEW chem field can be formed per output cell (central differences
+// inside, one-sided at the global edges, non-periodic -- core/agent/gradient.py:57) and published
+// for GradientAgent / PhysarumAgent.forward, which then needs ONE 16-byte gather per slot instead
+// of four 8-byte ones.  G = ring width (0 or 1).
+//   s_in  [(TH+2G+2R)][(TW+2G+2R)]  staged chem (+deposit), reused for the blurred ring tile
+//   s_v   [(TH+2G)][(TW+2G+2R)]     after the axis-0 pass
 // Staging is done in two sweeps so that all of a thread's (independent) chem + claim loads are
 // in flight before the first dependent deposit gather.
-template <int R, int TH, int TW, int NT>
+template <int R, int TH, int TW, int NT, bool GRAD>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
-    constexpr int LW = TW + 2 * R;           // staged row length
-    constexpr int LH = TH + 2 * R;
+    constexpr int G = GRAD ? 1 : 0;
+    constexpr int OH = TH + 2 * G, OW = TW + 2 * G;     // blurred region
+    constexpr int LW = OW + 2 * R;                      // staged row length
+    constexpr int LH = OH + 2 * R;
     constexpr int NSTAGE = (LH * LW + NT - 1) / NT;
     extern __shared__ double smem[];
     double* s_in = smem;                     // [LH][LW]
-    double* s_v = smem + LH * LW;            // [TH][LW]
+    double* s_v = smem + LH * LW;            // [OH][LW]
+    double* s_out = smem;                    // [OH][OW] blurred * keep (aliases s_in, GRAD only)
 
     const int H = a.H, W = a.W;
     const int64_t C = (int64_t)H * W;
@@ -86,8 +95,8 @@ field_step_kernel(const FieldArgs a) {
         w[s] = -1;
         if (idx < LH * LW) {
             const int r = idx / LW, c = idx - r * LW;
-            const int gi = wrap_index(i0 - R + r, H);
-            const int gj = wrap_index(j0 - R + c, W);
+            const int gi = wrap_index(i0 - G - R + r, H);
+            const int gj = wrap_index(j0 - G - R + c, W);
             const int g = gi * W + gj;
             v[s] = chem_in[g];
             w[s] = win[g];
@@ -101,7 +110,7 @@ field_step_kernel(const FieldArgs a) {
     __syncthreads();
 
     // ---- axis-0 pass --------------------------------------------------------------------
-    for (int idx = threadIdx.x; idx < TH * LW; idx += NT) {
+    for (int idx = threadIdx.x; idx < OH * LW; idx += NT) {
         const int r = idx / LW, c = idx - r * LW;
         const double* p = s_in + (r + R) * LW + c;
         double acc = p[0] * a.bw.w[R];
@@ -111,17 +120,55 @@ field_step_kernel(const FieldArgs a) {
     }
     __syncthreads();
 
-    // ---- axis-1 pass + elementwise channels ------------------------------------------------
+    if constexpr (!GRAD) {
+        // ---- axis-1 pass + elementwise channels ---------------------------------------------
+        for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+            const int r = idx / TW, c = idx - r * TW;
+            const int gi = i0 + r, gj = j0 + c;
+            if (gi < H && gj < W) {
+                const double* p = s_v + r * LW + c + R;
+                double acc = p[0] * a.bw.w[R];
+#pragma unroll
+                for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
+                const int g = gi * W + gj;
+                chem_out[g] = acc * a.keep;
+                const double occ = (win[g] >= 0) ? 1.0 : 0.0;
+                const double f = food_in[g];
+                const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
+                food_out[g] = a.food_infinite ? f : f - cf;
+                occ_out[g] = occ;
+                cons[g] = cf;
+            }
+        }
+    } else {
+    // ---- axis-1 pass over the ring tile into shared memory ------------------------------------
+    for (int idx = threadIdx.x; idx < OH * OW; idx += NT) {
+        const int r = idx / OW, c = idx - r * OW;
+        const double* p = s_v + r * LW + c + R;
+        double acc = p[0] * a.bw.w[R];
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
+        s_out[idx] = acc * a.keep;
+    }
+    __syncthreads();
+
+    // ---- outputs: new chem, its np.gradient, elementwise channels ------------------------------
+    double2* grad = a.grad + b * C;
     for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
         const int r = idx / TW, c = idx - r * TW;
         const int gi = i0 + r, gj = j0 + c;
         if (gi < H && gj < W) {
-            const double* p = s_v + r * LW + c + R;
-            double acc = p[0] * a.bw.w[R];
-#pragma unroll
-            for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
+            const double* q = s_out + (r + 1) * OW + (c + 1);
             const int g = gi * W + gj;
-            chem_out[g] = acc * a.keep;
+            chem_out[g] = q[0];
+            // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
+            const int um = (gi > 0) ? -OW : 0, up = (gi < H - 1) ? OW : 0;
+            const int lm = (gj > 0) ? -1 : 0, lp = (gj < W - 1) ? 1 : 0;
+            double gx = q[up] - q[um];
+            double gy = q[lp] - q[lm];
+            if (up - um == 2 * OW) gx *= 0.5;
+            if (lp - lm == 2) gy *= 0.5;
+            grad[g] = make_double2(gx, gy);
 
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
@@ -131,6 +178,7 @@ field_step_kernel(const FieldArgs a) {
             cons[g] = cf;
         }
     }
+    }   // GRAD
 }
 
 // No diffusion (blur_radius == 0): gaussian with radius 0 is the identity (w = [1]).

@@ -25,6 +25,7 @@ from typing import Callable, Optional, Tuple, Union
 import numpy as np
 import torch
 
+from . import _hints
 from . import _lib
 from . import data_init
 from .base_types import ActType, ObsType
@@ -190,7 +191,8 @@ class Env:
             cdyn = _dynamics_to_c(self.dynamics)
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
-            self._alive_count = (self._agents[:, 2] > 0).sum(dim=1)
+            self._publish_grad = False
+            self._hint_state = None         # (medium ptr, medium version, agents version, grad published)
 
     def __del__(self):
         try:
@@ -283,7 +285,33 @@ class Env:
                 self._agents.data_ptr(), action.data_ptr(),
                 self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), stream))
         self._cur = nxt
+        self._after_step()
         return self._get_current_obs, self._reward_dev, self._alive_dev
+
+    # -- fast-path hints for Agent.forward (see die_b200/_hints.py) ---------------------------------
+    def _after_step(self) -> None:
+        buf = self._medium_buf[self._cur]
+        self._hint_state = (buf.data_ptr(), buf._version, self._agents._version, self._publish_grad)
+        _hints.publish(self, buf)
+
+    def _hints_for(self, agents, medium, want_gradient: bool):
+        if want_gradient and not self._publish_grad:
+            # a gradient agent is acting on this env: publish np.gradient(chem1) from the next step on
+            _lib.check(self._lib.die_env_publish_gradient(self._handle, 1))
+            self._publish_grad = True
+        st = self._hint_state
+        if st is None:
+            return None, None
+        buf = self._medium_buf[self._cur]
+        grad_ptr = cells_ptr = None
+        if (medium.data_ptr() == st[0] == buf.data_ptr() and medium._version == st[1]
+                and medium.shape[-2:] == buf.shape[-2:] and medium.numel() == buf.numel()):
+            if agents.data_ptr() == self._agents.data_ptr() and agents._version == st[2] \
+                    and agents.numel() == self._agents.numel():
+                cells_ptr = self._lib.die_env_cells(self._handle)
+            if want_gradient and st[3]:
+                grad_ptr = self._lib.die_env_gradient(self._handle) or None
+        return grad_ptr, cells_ptr
 
     def step(self, action: ActType):
         """core/env.py:101-131 -> (obs, reward, terminated, truncated, info)."""
@@ -343,6 +371,7 @@ class Env:
                 hb['agents'].data_ptr(), med_t.data_ptr(),
                 hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
         self._cur = nxt
+        self._after_step()
         obs = (self._unbatch(hb['agents'].numpy()), self._unbatch(med_t.numpy()))
         return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))
 

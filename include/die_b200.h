@@ -99,6 +99,16 @@ int die_env_step(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
                  double* reward_dev, int64_t* alive_dev, void* stream);
 const int32_t* die_env_cells(const die_env_t* env);   /* device ptr, int32 [B][M], valid after a step */
 
+/* Derived fields the environment can publish for the agents' forward pass (optional fast path).
+ * die_env_publish_gradient(env, 1): from the next step on, the field pass also writes
+ * np.gradient of the NEW chem1 channel (raw d/dx, d/dy pairs, core/agent/gradient.py:57) into an
+ * internal [B][H*W][2] buffer; die_env_gradient() returns it (NULL when not published).  Passing it
+ * (and die_env_cells()) to die_gradient_forward replaces four 8-byte gathers and two coordinate
+ * look-ups per slot by one 16-byte gather and one 4-byte read.  The hints are valid only for the
+ * medium / agents written by the last die_env_step and until they are modified by the caller. */
+int die_env_publish_gradient(die_env_t* env, int32_t on);
+const double* die_env_gradient(const die_env_t* env);
+
 /* Per-kernel timing of Env.step with CUDA events recorded on the launching stream between
  * the step's kernels (measurement aid for bench.py's roofline; off by default).
  * die_env_kernel_times synchronises the recorded events and returns the accumulated
@@ -134,13 +144,16 @@ int die_const_forward(double* action_dev, int64_t M, int32_t B,
  * reach any output).  coin_dev[B][M] uint8 in {0,1} = np.random.randint(0, 2, M); NULL =
  * Philox.  noise_dev[B][2][M] = rng.normal(0, .4, (2, M)); NULL = Philox Box-Muller
  * (skipped entirely when noise_scale == 0).  sense_cells_dev (optional) int32 [B][M]:
- * linear index of the cell each slot sensed (validation aid). */
+ * linear index of the cell each slot sensed (validation aid).  grad_hint_dev / cells_hint_dev
+ * (optional): die_env_gradient() / die_env_cells() of the environment that produced the
+ * observation -- same results bit for bit, fewer gathers. */
 int die_gradient_forward(const die_gradient_params_t* p,
                          int32_t H, int32_t W, int64_t M, int32_t B,
                          const double* agents_dev, const double* medium_dev,
                          double* theta_dev, double* prev_grad_dev, double* action_dev,
                          const uint8_t* coin_dev, const double* noise_dev,
                          int32_t* sense_cells_dev,
+                         const double* grad_hint_dev, const int32_t* cells_hint_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied

@@ -264,3 +264,41 @@ def test_host_buffer_path_equals_device_path():
         o2, r2, _, _, i2 = g2.step(act2)
         assert r1 == r2 and i1 == i2
         assert np.array_equal(o1[0].cpu().numpy(), o2[0]) and np.array_equal(o1[1].cpu().numpy(), o2[1])
+
+
+def test_env_hints_fast_path_is_bit_identical_and_invalidates():
+    """Agent.forward uses the Env's cached cells + published gradient only when the observation is
+    provably the one the Env wrote; results must be bit-identical to the recompute-everything path,
+    and any in-place edit of the observation must switch the hints off."""
+    import torch
+    import die_b200 as D
+    (_,), env = make_pair((96, 80), seed=12)
+    m = env.max_agents
+    theta0, _ = lattice_theta(m, 30, 12)
+    fast, slow = D.PhysarumAgent(max_agents=m, **PHYS), D.PhysarumAgent(max_agents=m, **PHYS)
+    slow.use_env_hints = False
+    fast.set_state(theta=theta0)
+    rng = np.random.default_rng(0)
+    obs = env._get_current_obs
+    seen_fast = False
+    for it in range(25):
+        coin = rng.integers(0, 2, m)
+        slow.set_state(theta=fast.get_state()[0])
+        a_fast = fast.forward(obs, coin=coin).clone()
+        a_slow = slow.forward(obs, coin=coin)
+        assert torch.equal(a_fast, a_slow), it
+        assert np.array_equal(fast.get_state()[0], slow.get_state()[0])
+        assert slow.last_hints == (False, False)
+        if it >= 2:
+            assert fast.last_hints == (True, True), (it, fast.last_hints)
+            seen_fast = True
+        obs, *_ = env.step(a_fast)
+    assert seen_fast
+    # an in-place edit of the medium invalidates the gradient hint (and, being nested, the cells)
+    env.medium[2] += 0.0
+    fast.forward(env._get_current_obs, coin=rng.integers(0, 2, m))
+    assert fast.last_hints == (False, False)
+    obs, *_ = env.step(fast.forward(env._get_current_obs, coin=rng.integers(0, 2, m)))
+    env.agents[0] += 0.0                                  # in-place edit of the agents: cells hint off
+    fast.forward(env._get_current_obs, coin=rng.integers(0, 2, m))
+    assert fast.last_hints == (True, False)
