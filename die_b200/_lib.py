@@ -65,6 +65,7 @@ SIGNATURES = {
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "die_set_field_impl": (C.c_int, [C.c_int32]),
     "die_math_sincos": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "die_math_atan2": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
 }

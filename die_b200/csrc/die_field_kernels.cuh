@@ -181,6 +181,155 @@ field_step_kernel(const FieldArgs a) {
     }   // GRAD
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-tiled version for small radii (R <= 3): no shared memory, no block barriers.
+// Each WARP owns a strip of 32 staged columns (OWV = 24 or 28 of them are outputs) and marches down
+// RB output rows: every lane keeps the 2R+1 most recent input values of its column in registers
+// (axis-0 pass), takes the axis-1 neighbours from the adjacent lanes with warp shuffles, and (GRAD)
+// keeps the last three blurred rows to form np.gradient of the new field.  Loads run a few rows
+// ahead of the arithmetic in a 4-slot register ring: (A) chem + claim of input row t+4, (B) the
+// deposit gather of the claimed cells of row t+2, (C) consume row t; the food / claim of the output
+// row are prefetched three rows ahead the same way.  Operation order is identical to the tile
+// version, so results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct MarchGeom {
+    int strips;      // ceil(W / OWV)
+    int rblocks;     // ceil(H / RB)
+    int B;
+};
+
+template <int R, bool GRAD, int RB>
+__global__ void __launch_bounds__(256, 3)
+field_march_kernel(const FieldArgs a, const MarchGeom geo) {
+    constexpr int G = GRAD ? 1 : 0;
+    constexpr int HALO = R + G;
+    constexpr int OWV = (32 - 2 * HALO) & ~3;          // outputs per warp row: 32-byte aligned stores
+    constexpr int T = RB + 2 * HALO;                   // input rows consumed per block
+    constexpr int LAG = 2 * R + 2 * G;                 // output row of iteration t = i0 + t - LAG
+    constexpr int CL = HALO;                           // claim of the output row was loaded CL rows ago
+    constexpr unsigned FULL = 0xffffffffu;
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int per_env = geo.strips * geo.rblocks;
+    const int64_t b = warp / per_env;
+    if (b >= geo.B) return;                            // whole warp exits together
+    const int rem = (int)(warp - b * per_env);
+    const int rb = rem / geo.strips, strip = rem - rb * geo.strips;
+    const int H = a.H, W = a.W;
+    const int64_t C = (int64_t)H * W;
+    const int i0 = rb * RB, j0 = strip * OWV;
+    const int oc = j0 - HALO + lane;                   // my column, unwrapped
+    const int gj = wrap_index(oc, W);
+    const bool col_out = lane >= HALO && lane < HALO + OWV && oc < W;
+    const int rows_here = min(RB, H - i0);             // output rows of this block
+    // np.gradient is one-sided on the global border: only the first / last strip and row can touch it
+    const bool left_edge = oc == 0, right_edge = oc == W - 1;
+
+    const double* min_b = a.medium_in + b * 3 * C;     // channels at +0 (occ), +C (food), +2C (chem)
+    double* mout_b = a.medium_out + b * 3 * C;
+    const int32_t* win = a.winner + b * C;
+    const double* dep = a.action + (b * 3 + 2) * a.M;
+    double* cons = a.consumed + b * C;
+    double2* grad = GRAD ? a.grad + b * C : nullptr;
+
+    double wk[R + 1];                                  // wk[k] = weight of taps at distance k
+#pragma unroll
+    for (int k = 0; k <= R; ++k) wk[k] = a.bw.w[R - k];
+
+    // register rings (indices are compile-time after unrolling)
+    double px[4], pd[4], fo[4];
+    int pw[4];
+    int claim_line[CL + 1];                            // claims of the last CL+1 consumed rows
+#pragma unroll
+    for (int k = 0; k <= CL; ++k) claim_line[k] = -1;
+    int gi_a = wrap_index(i0 - HALO, H);               // next input row to fetch (stage A)
+
+    auto stage_a = [&](int slot) {
+        const int g = gi_a * W + gj;
+        px[slot] = min_b[2 * C + g];
+        pw[slot] = win[g];
+        gi_a = (gi_a + 1 == H) ? 0 : gi_a + 1;
+    };
+    auto stage_b = [&](int slot) { pd[slot] = (pw[slot] >= 0) ? dep[pw[slot]] : 0.0; };
+    auto prefetch_food = [&](int slot, int rel) {      // rel = output row relative to i0
+        const bool ok = col_out && rel >= 0 && rel < rows_here;
+        fo[slot] = ok ? min_b[C + (i0 + rel) * W + oc] : 0.0;
+    };
+
+    double win_v[2 * R + 1];                            // vertical window, win_v[2R] = newest
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) win_v[k] = 0.0;
+    double bp = 0.0, bc = 0.0, bn = 0.0;
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < 4; ++s) stage_a(s);
+    stage_b(0);
+    stage_b(1);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) prefetch_food(s, s - LAG);
+
+    int rel = -LAG;                                     // output row of iteration t, relative to i0
+    for (int t0 = 0; t0 < T; t0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // (C) consume input row t
+            const int cw = pw[u];
+            const double x = (cw >= 0) ? px[u] + pd[u] : px[u];
+#pragma unroll
+            for (int k = 0; k < 2 * R; ++k) win_v[k] = win_v[k + 1];
+            win_v[2 * R] = x;
+#pragma unroll
+            for (int k = 0; k < CL; ++k) claim_line[k] = claim_line[k + 1];
+            claim_line[CL] = cw;
+            stage_a(u);                                 // (A) row t+4 into the slot just freed
+            stage_b((u + 2) & 3);                       // (B) deposits of row t+2
+
+            // axis-0 pass for the row at the window centre, then axis-1 via shuffles
+            double v = win_v[R] * wk[0];
+#pragma unroll
+            for (int k = R; k >= 1; --k) v += (win_v[R - k] + win_v[R + k]) * wk[k];
+            double h = v * wk[0];
+#pragma unroll
+            for (int k = R; k >= 1; --k) {
+                const double lft = __shfl_sync(FULL, v, (lane - k) & 31);
+                const double rgt = __shfl_sync(FULL, v, (lane + k) & 31);
+                h += (lft + rgt) * wk[k];
+            }
+            bp = bc;
+            bc = bn;
+            bn = h * a.keep;                            // blurred row i0 + t - 2R - G
+
+            // output row i0 + rel
+            const double centre = GRAD ? bc : bn;
+            double gx = 0.0, gy = 0.0;
+            if (GRAD) {
+                const double lft = __shfl_sync(FULL, bc, (lane - 1) & 31);
+                const double rgt = __shfl_sync(FULL, bc, (lane + 1) & 31);
+                const int ro = i0 + rel;
+                if (ro > 0 && ro < H - 1) gx = (bn - bp) * 0.5;               // warp-uniform branch
+                else gx = (ro < H - 1 ? bn : bc) - (ro > 0 ? bp : bc);
+                gy = (right_edge ? bc : rgt) - (left_edge ? bc : lft);
+                if (!(left_edge || right_edge)) gy *= 0.5;
+            }
+            if (col_out && rel >= 0 && rel < rows_here) {
+                const int g = (i0 + rel) * W + oc;
+                mout_b[2 * C + g] = centre;
+                if (GRAD) grad[g] = make_double2(gx, gy);
+                const double occ = (claim_line[0] >= 0) ? 1.0 : 0.0;    // claim of row t - CL = output row
+                const double f = fo[u];
+                const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
+                mout_b[C + g] = a.food_infinite ? f : f - cf;
+                mout_b[g] = occ;
+                cons[g] = cf;
+            }
+            prefetch_food((u + 3) & 3, rel + 3);        // food of the row output at t+3
+            ++rel;
+        }
+    }
+}
+
 // No diffusion (blur_radius == 0): gaussian with radius 0 is the identity (w = [1]).
 template <int NT>
 __global__ void __launch_bounds__(NT)

@@ -156,6 +156,11 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          const double* grad_hint_dev, const int32_t* cells_hint_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
+/* Field-pass implementation switch (tests / A-B timing): 0 = shared-memory tile kernel (default),
+ * 1 = register-tiled warp-marching kernel (blur radius <= 3; measured slower on B200 so far: 0.29 vs
+ * 0.25 ms at 4096^2).  Both give bit-identical results. */
+int die_set_field_impl(int32_t impl);
+
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
  * to device arrays, so tests can check the device results equal the host build of the same
  * source bit-for-bit.  fast != 0 selects die_atan2_fast. */

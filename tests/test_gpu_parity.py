@@ -302,3 +302,37 @@ def test_env_hints_fast_path_is_bit_identical_and_invalidates():
     env.agents[0] += 0.0                                  # in-place edit of the agents: cells hint off
     fast.forward(env._get_current_obs, coin=rng.integers(0, 2, m))
     assert fast.last_hints == (True, False)
+
+
+@pytest.mark.parametrize("shape,sigma", [((96, 80), 0.5), ((37, 53), 0.5), ((5, 7), 0.5), ((130, 65), 0.3),
+                                         ((64, 200), 0.8), ((256, 256), 0.5), ((40, 40), 1.1)])
+def test_field_kernels_agree_bit_for_bit(shape, sigma):
+    """The register-tiled warp-marching field pass and the shared-memory tile version (and, through
+    the other tests, the oracle) must give identical media and identical published gradients."""
+    import torch
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    results = []
+    for impl in (0, 1):
+        lib.die_set_field_impl(impl)
+        try:
+            (_,), env = make_pair(shape, seed=21, dynamics_kw=dict(diffuse_sigma=sigma))
+            m = env.max_agents
+            theta0, _ = lattice_theta(m, 30, 21)
+            ag = D.PhysarumAgent(max_agents=m, **PHYS)
+            ag.set_state(theta=theta0)
+            rng = np.random.default_rng(3)
+            obs = env._get_current_obs
+            acts = []
+            for it in range(12):
+                act = ag.forward(obs, coin=rng.integers(0, 2, m))
+                acts.append(act.cpu().numpy().copy())
+                obs, r, *_ = env.step(act)
+            med, agn = env.get_state()
+            results.append((med, agn, np.array(acts), r, ag.last_hints))
+        finally:
+            lib.die_set_field_impl(0)
+    (m0, a0, c0, r0, h0), (m1, a1, c1, r1, h1) = results
+    assert np.array_equal(m0, m1) and np.array_equal(a0, a1) and np.array_equal(c0, c1) and r0 == r1
+    assert h0 == h1 == (True, True)
