@@ -41,6 +41,18 @@ class DieGradientParams(C.Structure):
     ]
 
 
+DIE_MAX_RANKS = 8
+
+
+class DieSlabGeom(C.Structure):
+    _fields_ = [
+        ("G", C.c_int32), ("rank", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("M", C.c_int64),
+        ("s0", C.c_int64 * DIE_MAX_RANKS), ("n0", C.c_int64 * DIE_MAX_RANKS),
+        ("s1", C.c_int64 * DIE_MAX_RANKS), ("n1", C.c_int64 * DIE_MAX_RANKS),
+    ]
+
+
 class DieError(RuntimeError):
     pass
 
@@ -65,6 +77,15 @@ SIGNATURES = {
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "die_slab_create": (C.c_int, [C.POINTER(DieSlabGeom), C.POINTER(DieDynamics), C.POINTER(_P)]),
+    "die_slab_destroy": (C.c_int, [_P]),
+    "die_slab_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "die_slab_forward": (C.c_int, [_P, C.POINTER(DieGradientParams), C.c_int32, _P, _P, _P, _P, C.c_int32,
+                                   C.c_uint64, C.c_uint64, _P]),
+    "die_slab_move_claim": (C.c_int, [_P, _P, _P, _P]),
+    "die_slab_field": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "die_slab_feed": (C.c_int, [_P, _P, _P, _P, _P]),
+    "die_slab_cells": (_P, [_P]),
     "die_set_field_impl": (C.c_int, [C.c_int32]),
     "die_math_sincos": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "die_math_atan2": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),

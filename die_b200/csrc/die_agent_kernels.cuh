@@ -7,6 +7,7 @@
 // each).  Citations are file:line under /root/reference.
 #pragma once
 #include "die_device.cuh"
+#include "die_slab.cuh"
 #include "../../include/die_b200.h"
 
 namespace die {
@@ -121,9 +122,11 @@ struct GradientArgs {
     const double2* grad;        // may be null: np.gradient(chem1) per cell, published by Env.step
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
+    SlabGeom sg;                // SLAB instantiation only: H, W above are the GLOBAL field, M the LOCAL slots
+    SlabTables st;
 };
 
-template <bool DISCRETE_TURN>
+template <bool DISCRETE_TURN, bool SLAB>
 __global__ void __launch_bounds__(kAgentThreads)
 gradient_forward_kernel(const GradientArgs a) {
     const die_gradient_params_t& p = a.p;
@@ -171,22 +174,27 @@ gradient_forward_kernel(const GradientArgs a) {
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
         // food under the agent (:113-115), issued early: independent of the turn arithmetic
         const int here = (cl_p != nullptr) ? cl_p[i] : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = food[here];
+        const double food_here = SLAB ? *slab_chan(a.st.medium_in, a.sg, 1, here) : food[here];
 
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
         const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
         if (sc_p != nullptr) sc_p[i] = sc;
         double gx, gy;
-        if (grad != nullptr) {                // published by the field pass: one 16-byte gather
-            const double2 g2 = grad[sc];
+        if (SLAB ? a.st.grad != nullptr : grad != nullptr) {   // published by the field pass: one 16-byte gather
+            const double2 g2 = SLAB ? *slab_cell(a.st.grad, a.sg, sc) : grad[sc];
             gx = g2.x;
             gy = g2.y;
         } else {
             const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
             const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
-            gx = chem[sc + xp] - chem[sc + xm];
-            gy = chem[sc + yp] - chem[sc + ym];
+            if (SLAB) {
+                gx = *slab_chan(a.st.medium_in, a.sg, 2, sc + xp) - *slab_chan(a.st.medium_in, a.sg, 2, sc + xm);
+                gy = *slab_chan(a.st.medium_in, a.sg, 2, sc + yp) - *slab_chan(a.st.medium_in, a.sg, 2, sc + ym);
+            } else {
+                gx = chem[sc + xp] - chem[sc + xm];
+                gy = chem[sc + yp] - chem[sc + ym];
+            }
             if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
             if (yp - ym == 2) gy *= 0.5;
         }
@@ -276,10 +284,12 @@ gradient_forward_kernel(const GradientArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kMoveItems = 4;
 
+template <bool SLAB>
 __global__ void __launch_bounds__(kAgentThreads)
 move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   int32_t* __restrict__ winner, int32_t* __restrict__ cells,
-                  const Axis ax, const Axis ay, int64_t M, int nchunk, int boundary) {
+                  const Axis ax, const Axis ay, int64_t M, int nchunk, int boundary,
+                  const SlabGeom sg, const SlabTables st) {
     const int W = ay.n;
     const int64_t C = (int64_t)ax.n * ay.n;
     const SlotChunk ch = slot_chunk<kMoveItems>(nchunk);
@@ -305,7 +315,10 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
         ag[M + i] = y;
         const int cell = nearest_cell(x, ax) * W + nearest_cell(y, ay);
         cl[i] = cell;
-        if (alive) atomicMax(win + cell, (int32_t)i);
+        if (alive) {
+            if (SLAB) atomicMax(slab_cell(st.claim, sg, cell), (int32_t)slab_slot_global(sg, sg.rank, i));
+            else atomicMax(win + cell, (int32_t)i);
+        }
     }
 }
 
@@ -318,12 +331,14 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
+template <bool SLAB>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
                   const int32_t* __restrict__ cells,
                   double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
-                  int64_t C, int64_t M, int nblk, double w_dep, double w_dist) {
+                  int64_t C, int64_t M, int nblk, double w_dep, double w_dist,
+                  const SlabGeom sg, const SlabTables st) {
     const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
@@ -344,7 +359,7 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? cf[cell[k]] : 0.0;
+        eaten[k] = valid[k] ? (SLAB ? *slab_cell(st.consumed, sg, cell[k]) : cf[cell[k]]) : 0.0;
         alive[k] = valid[k] && ag_alive[i] > 0.0;
         stock[k] = valid[k] ? ag_alive[M + i] : 0.0;
         dx[k] = valid[k] ? ac[i] : 0.0;
@@ -360,8 +375,9 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
             const double gained = eaten[k] - burned;
             ag_alive[M + k * kAgentThreads] = stock[k] + gained;
             gain_sum += gained;
-            if (alive[k]) {
-                win[cell[k]] = -1;                 // claim table back to empty for the next step
+            if (alive[k]) {                        // claim table back to empty for the next step
+                if (SLAB) *slab_cell(st.claim, sg, cell[k]) = -1;
+                else win[cell[k]] = -1;
                 ++alive_cnt;
             }
         }

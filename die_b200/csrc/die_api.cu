@@ -193,7 +193,7 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     a.tiles_j = (a.W + TW - 1) / TW;
     const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
-    auto kern = field_step_kernel<R, TH, TW, NT, GRAD>;
+    auto kern = field_step_kernel<R, TH, TW, NT, GRAD, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     const int64_t grid = (int64_t)a.tiles_i * a.tiles_j * B;
@@ -279,17 +279,19 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
 
     prof_mark(e, 0, st);
     const int mchunk = chunks_for(e->M, kMoveItems);
-    move_claim_kernel<<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, e->winner, e->cells, make_axis(e->H), make_axis(e->W), e->M, mchunk, e->dyn.boundary);
+    move_claim_kernel<false><<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
+        agents, action, e->winner, e->cells, make_axis(e->H), make_axis(e->W), e->M, mchunk, e->dyn.boundary,
+        SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 1, st);
 
     DIE_CUDA(launch_field_any(e, medium_in, medium_out, action, st));
     prof_mark(e, 2, st);
 
-    agent_feed_kernel<<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
+    agent_feed_kernel<false><<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
         agents, action, e->consumed, e->winner, e->cells, e->part_gain, e->part_alive,
-        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist);
+        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+        SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 3, st);
 
@@ -379,9 +381,9 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     a.seed = seed; a.step = step;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     if (p->discrete_turn)
-        gradient_forward_kernel<true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+        gradient_forward_kernel<true, false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
     else
-        gradient_forward_kernel<false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+        gradient_forward_kernel<false, false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -411,6 +413,206 @@ extern "C" int die_math_atan2(const double* y, const double* x, double* out, int
     DIE_REQUIRE(x != nullptr && y != nullptr && out != nullptr && n >= 0);
     if (n == 0) return DIE_OK;
     math_atan2_kernel<<<grid_for(n, 256, 148), 256, 0, (cudaStream_t)stream>>>(y, x, out, n, fast);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one field over G GPUs: row slabs + NVLink peer access (die_slab.cuh)
+// ------------------------------------------------------------------------------------------
+struct die_slab {
+    SlabGeom g;
+    die_dynamics_t dyn;
+    SlabTables tbl[2];         // [cur]: medium_in = medium[cur], medium_out = medium[1-cur]
+    int64_t Ml;                // local slots
+    int32_t* cells;            // [Ml] global linear cell after the move
+    double* part_gain;
+    int32_t* part_alive;
+    double* reward_dev;        // [1]
+    int64_t* alive_dev;        // [1]
+    int nblk;
+};
+
+__global__ void slab_pack_stats_kernel(const double* reward, const int64_t* alive, double* out) {
+    out[0] = reward[0];
+    out[1] = (double)alive[0];
+}
+
+extern "C" int die_slab_create(const die_slab_geom_t* geom, const die_dynamics_t* dyn, die_slab_t** out) {
+    DIE_REQUIRE(out != nullptr && geom != nullptr);
+    *out = nullptr;
+    DIE_REQUIRE(geom->G >= 1 && geom->G <= DIE_MAX_RANKS && geom->rank >= 0 && geom->rank < geom->G);
+    DIE_REQUIRE(geom->H >= 2 && geom->W >= 2 && geom->H % geom->G == 0);
+    DIE_REQUIRE((int64_t)geom->H * geom->W <= 0x7fffffffLL && geom->M >= 1 && geom->M <= 0x7fffffffLL);
+    if (int rc = check_dynamics(dyn)) return rc;
+    DIE_REQUIRE(dyn->blur_radius >= 1);
+    die_slab* e = new (std::nothrow) die_slab();
+    if (e == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
+    memset(e, 0, sizeof(*e));
+    SlabGeom& g = e->g;
+    g.G = geom->G; g.rank = geom->rank; g.H = geom->H; g.W = geom->W;
+    g.rows_per = geom->H / geom->G;
+    g.slab_cells = g.rows_per * g.W;
+    g.slab_shift = -1;
+    for (int sft = 0; sft < 31; ++sft) if ((1 << sft) == g.slab_cells) g.slab_shift = sft;
+    g.M = geom->M;
+    int64_t total = 0;
+    for (int q = 0; q < geom->G; ++q) {
+        g.s0[q] = geom->s0[q]; g.n0[q] = geom->n0[q]; g.s1[q] = geom->s1[q]; g.n1[q] = geom->n1[q];
+        total += g.n0[q] + g.n1[q];
+    }
+    if (total != g.M) { delete e; return fail(DIE_E_INVALID, "slot ranges do not cover M%s%s"); }
+    e->dyn = *dyn;
+    e->Ml = g.n0[g.rank] + g.n1[g.rank];
+    e->nblk = (int)((e->Ml + (int64_t)kAgentThreads * kFeedItems - 1) / ((int64_t)kAgentThreads * kFeedItems));
+    if (e->nblk < 1) e->nblk = 1;
+    cudaError_t err = cudaMalloc(&e->cells, sizeof(int32_t) * (size_t)(e->Ml > 0 ? e->Ml : 1));
+    if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk);
+    if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk);
+    if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double));
+    if (err == cudaSuccess) err = cudaMalloc(&e->alive_dev, sizeof(int64_t));
+    if (err != cudaSuccess) {
+        die_slab_destroy(e);
+        return fail(DIE_E_CUDA, "die_slab_create: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return DIE_OK;
+}
+
+extern "C" int die_slab_destroy(die_slab_t* e) {
+    if (e == nullptr) return DIE_OK;
+    cudaFree(e->cells);
+    cudaFree(e->part_gain);
+    cudaFree(e->part_alive);
+    cudaFree(e->reward_dev);
+    cudaFree(e->alive_dev);
+    delete e;
+    return DIE_OK;
+}
+
+extern "C" int die_slab_bind(die_slab_t* e, const void* med_a, const void* med_b, const void* claim,
+                             const void* consumed, const void* grad, const void* action) {
+    DIE_REQUIRE(e != nullptr && med_a != nullptr && med_b != nullptr && claim != nullptr);
+    DIE_REQUIRE(consumed != nullptr && grad != nullptr && action != nullptr);
+    for (int cur = 0; cur < 2; ++cur) {
+        SlabTables& t = e->tbl[cur];
+        t.medium_in = (double* const*)(cur == 0 ? med_a : med_b);
+        t.medium_out = (double* const*)(cur == 0 ? med_b : med_a);
+        t.claim = (int32_t* const*)claim;
+        t.consumed = (double* const*)consumed;
+        t.grad = (double2* const*)grad;
+        t.action = (double* const*)action;
+    }
+    return DIE_OK;
+}
+
+extern "C" const int32_t* die_slab_cells(const die_slab_t* e) { return e ? e->cells : nullptr; }
+
+extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, int32_t cur,
+                                const double* agents, double* theta, double* action,
+                                const uint8_t* coin, int32_t hints,
+                                uint64_t seed, uint64_t step, void* stream) {
+    DIE_REQUIRE(e != nullptr && p != nullptr && (cur == 0 || cur == 1));
+    DIE_REQUIRE(agents != nullptr && theta != nullptr && action != nullptr);
+    DIE_REQUIRE(p->inertia == 0.0 && p->noise_scale == 0.0);       // no prev_grad in slab mode (Physarum defaults)
+    if (e->Ml == 0) return DIE_OK;
+    GradientArgs a;
+    memset(&a, 0, sizeof(a));
+    a.p = *p;
+    a.H = e->g.H; a.W = e->g.W; a.M = e->Ml; a.nchunk = chunks_for(e->Ml, kFwdItems);
+    a.ax = make_axis(e->g.H);
+    a.ay = make_axis(e->g.W);
+    a.agents = agents; a.theta = theta; a.action = action; a.coin = coin;
+    a.seed = seed; a.step = step;
+    a.sg = e->g;
+    a.st = e->tbl[cur];
+    if (!(hints & 1)) a.st.grad = nullptr;       // bit 0: the gradient published by the last die_slab_field
+    if (hints & 2) a.cells = e->cells;           // bit 1: the cell cache of the last die_slab_move_claim
+    const unsigned grid = (unsigned)a.nchunk;
+    if (p->discrete_turn)
+        gradient_forward_kernel<true, true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    else
+        gradient_forward_kernel<false, true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+extern "C" int die_slab_move_claim(die_slab_t* e, double* agents, const double* action, void* stream) {
+    DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr);
+    if (e->Ml == 0) return DIE_OK;
+    const int mchunk = chunks_for(e->Ml, kMoveItems);
+    move_claim_kernel<true><<<(unsigned)mchunk, kAgentThreads, 0, (cudaStream_t)stream>>>(
+        agents, action, nullptr, e->cells, make_axis(e->g.H), make_axis(e->g.W), e->Ml, mchunk,
+        e->dyn.boundary, e->g, e->tbl[0]);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+template <int R>
+static cudaError_t launch_field_slab(const FieldArgs& fa, bool grad, cudaStream_t st) {
+    constexpr int TH = 32, TW = 64, NT = 256;
+    FieldArgs a = fa;
+    a.tiles_i = (a.sg.rows_per + TH - 1) / TH;
+    a.tiles_j = (a.W + TW - 1) / TW;
+    const int G = grad ? 1 : 0;
+    const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
+                                                  (TH + 2 * G) * (TW + 2 * G + 2 * R));
+    cudaError_t err;
+    const unsigned grid = (unsigned)(a.tiles_i * a.tiles_j);
+    if (grad) {
+        auto kern = field_step_kernel<R, TH, TW, NT, true, true>;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, NT, smem, st>>>(a);
+    } else {
+        auto kern = field_step_kernel<R, TH, TW, NT, false, true>;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, NT, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+extern "C" int die_slab_field(die_slab_t* e, int32_t cur, int32_t publish_grad, void* stream) {
+    DIE_REQUIRE(e != nullptr && (cur == 0 || cur == 1));
+    FieldArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = e->g.H;
+    a.W = e->g.W;
+    a.rate_feed = e->dyn.rate_feed;
+    a.keep = 1.0 - e->dyn.rate_decay_chem;
+    a.food_infinite = e->dyn.food_infinite;
+    for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
+    a.sg = e->g;
+    a.st = e->tbl[cur];
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err = cudaErrorInvalidValue;
+    switch (e->dyn.blur_radius) {
+        case 1: err = launch_field_slab<1>(a, publish_grad != 0, st); break;
+        case 2: err = launch_field_slab<2>(a, publish_grad != 0, st); break;
+        case 3: err = launch_field_slab<3>(a, publish_grad != 0, st); break;
+        case 4: err = launch_field_slab<4>(a, publish_grad != 0, st); break;
+        default: return fail(DIE_E_INVALID, "slab mode supports blur radius 1..4%s%s");
+    }
+    DIE_CUDA(err);
+    return DIE_OK;
+}
+
+extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action, double* stats, void* stream) {
+    DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr && stats != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->Ml > 0) {
+        agent_feed_kernel<true><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
+            agents, action, nullptr, nullptr, e->cells, e->part_gain, e->part_alive,
+            (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist, e->g, e->tbl[0]);
+        DIE_CUDA(cudaGetLastError());
+        finalize_stats_kernel<<<1, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
+    } else {
+        DIE_CUDA(cudaMemsetAsync(e->reward_dev, 0, sizeof(double), st));
+        DIE_CUDA(cudaMemsetAsync(e->alive_dev, 0, sizeof(int64_t), st));
+    }
+    DIE_CUDA(cudaGetLastError());
+    slab_pack_stats_kernel<<<1, 1, 0, st>>>(e->reward_dev, e->alive_dev, stats);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }

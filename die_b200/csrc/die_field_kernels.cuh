@@ -17,6 +17,7 @@
 // is bit-identical to skimage.filters.gaussian on the same input.
 #pragma once
 #include "die_device.cuh"
+#include "die_slab.cuh"
 #include "../../include/die_b200.h"
 
 namespace die {
@@ -39,6 +40,8 @@ struct FieldArgs {
     double keep;                 // 1. - rate_decay_chem
     int food_infinite;
     BlurWeights bw;              // centre at [R]
+    SlabGeom sg;                 // SLAB instantiation only (H, W above are then the GLOBAL field)
+    SlabTables st;
 };
 
 __device__ __forceinline__ int wrap_index(int i, int n) {
@@ -55,7 +58,7 @@ __device__ __forceinline__ int wrap_index(int i, int n) {
 //   s_v   [(TH+2G)][(TW+2G+2R)]     after the axis-0 pass
 // Staging is done in two sweeps so that all of a thread's (independent) chem + claim loads are
 // in flight before the first dependent deposit gather.
-template <int R, int TH, int TW, int NT, bool GRAD>
+template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
     constexpr int G = GRAD ? 1 : 0;
@@ -68,22 +71,26 @@ field_step_kernel(const FieldArgs a) {
     double* s_v = smem + LH * LW;            // [OH][LW]
     double* s_out = smem;                    // [OH][OW] blurred * keep (aliases s_in, GRAD only)
 
-    const int H = a.H, W = a.W;
-    const int64_t C = (int64_t)H * W;
+    const int H = a.H, W = a.W;              // GLOBAL field (== the local one unless SLAB)
+    const int HL = SLAB ? a.sg.rows_per : H; // rows this launch produces
+    const int row0 = SLAB ? a.sg.rank * a.sg.rows_per : 0;
+    const int64_t C = (int64_t)HL * W;
     const int tiles = a.tiles_i * a.tiles_j;
     const int64_t b = blockIdx.x / (unsigned)tiles;
     const int t = blockIdx.x - (int)b * tiles;
     const int ti = t / a.tiles_j, tj = t - ti * a.tiles_j;
-    const int i0 = ti * TH, j0 = tj * TW;
+    const int i0 = ti * TH, j0 = tj * TW;    // LOCAL row / column of the tile
 
-    const double* food_in = a.medium_in + (b * 3 + 1) * C;
-    const double* chem_in = a.medium_in + (b * 3 + 2) * C;
-    double* occ_out = a.medium_out + (b * 3 + 0) * C;
-    double* food_out = a.medium_out + (b * 3 + 1) * C;
-    double* chem_out = a.medium_out + (b * 3 + 2) * C;
-    const int32_t* win = a.winner + b * C;
-    const double* dep = a.action + (b * 3 + 2) * a.M;
-    double* cons = a.consumed + b * C;
+    const double* min_l = SLAB ? a.st.medium_in[a.sg.rank] : a.medium_in + b * 3 * C;
+    double* mout_l = SLAB ? a.st.medium_out[a.sg.rank] : a.medium_out + b * 3 * C;
+    const double* food_in = min_l + C;
+    const double* chem_in = min_l + 2 * C;
+    double* occ_out = mout_l;
+    double* food_out = mout_l + C;
+    double* chem_out = mout_l + 2 * C;
+    const int32_t* win = SLAB ? a.st.claim[a.sg.rank] : a.winner + b * C;
+    const double* dep = SLAB ? nullptr : a.action + (b * 3 + 2) * a.M;
+    double* cons = SLAB ? a.st.consumed[a.sg.rank] : a.consumed + b * C;
 
     // ---- stage the periodic halo tile, deposit included -------------------------------------
     double v[NSTAGE];
@@ -95,17 +102,34 @@ field_step_kernel(const FieldArgs a) {
         w[s] = -1;
         if (idx < LH * LW) {
             const int r = idx / LW, c = idx - r * LW;
-            const int gi = wrap_index(i0 - G - R + r, H);
+            const int gi = wrap_index(row0 + i0 - G - R + r, H);     // global row, periodic over the WHOLE field
             const int gj = wrap_index(j0 - G - R + c, W);
             const int g = gi * W + gj;
-            v[s] = chem_in[g];
-            w[s] = win[g];
+            if (SLAB) {                       // rows outside this rank's slab come from the neighbours over NVLink
+                v[s] = *slab_chan(a.st.medium_in, a.sg, 2, g);
+                w[s] = *slab_cell(a.st.claim, a.sg, g);
+            } else {
+                v[s] = chem_in[g];
+                w[s] = win[g];
+            }
         }
     }
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
         const int idx = threadIdx.x + s * NT;
-        if (idx < LH * LW) s_in[idx] = (w[s] >= 0) ? v[s] + dep[w[s]] : v[s];
+        if (idx < LH * LW) {
+            double x = v[s];
+            if (w[s] >= 0) {
+                if (SLAB) {                   // the winner is a GLOBAL slot id: its deposit lives on its owner
+                    int64_t local;
+                    const int q = slab_slot_owner(a.sg, w[s], local);
+                    x = x + a.st.action[q][2 * slab_slots_of(a.sg, q) + local];
+                } else {
+                    x = x + dep[w[s]];
+                }
+            }
+            s_in[idx] = x;
+        }
     }
     __syncthreads();
 
@@ -124,13 +148,13 @@ field_step_kernel(const FieldArgs a) {
         // ---- axis-1 pass + elementwise channels ---------------------------------------------
         for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
             const int r = idx / TW, c = idx - r * TW;
-            const int gi = i0 + r, gj = j0 + c;
-            if (gi < H && gj < W) {
+            const int li = i0 + r, gj = j0 + c;
+            if (li < HL && gj < W) {
                 const double* p = s_v + r * LW + c + R;
                 double acc = p[0] * a.bw.w[R];
 #pragma unroll
                 for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
-                const int g = gi * W + gj;
+                const int g = li * W + gj;
                 chem_out[g] = acc * a.keep;
                 const double occ = (win[g] >= 0) ? 1.0 : 0.0;
                 const double f = food_in[g];
@@ -153,13 +177,14 @@ field_step_kernel(const FieldArgs a) {
     __syncthreads();
 
     // ---- outputs: new chem, its np.gradient, elementwise channels ------------------------------
-    double2* grad = a.grad + b * C;
+    double2* grad = SLAB ? a.st.grad[a.sg.rank] : a.grad + b * C;
     for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
         const int r = idx / TW, c = idx - r * TW;
-        const int gi = i0 + r, gj = j0 + c;
-        if (gi < H && gj < W) {
+        const int li = i0 + r, gj = j0 + c;
+        const int gi = row0 + li;            // global row: np.gradient is one-sided on the GLOBAL border only
+        if (li < HL && gj < W) {
             const double* q = s_out + (r + 1) * OW + (c + 1);
-            const int g = gi * W + gj;
+            const int g = li * W + gj;
             chem_out[g] = q[0];
             // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
             const int um = (gi > 0) ? -OW : 0, up = (gi < H - 1) ? OW : 0;

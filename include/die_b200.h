@@ -156,6 +156,43 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          const double* grad_hint_dev, const int32_t* cells_hint_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * One field split into row slabs over G GPUs (BASELINE configs[4]; SURVEY section 8e, mode 2).
+ * Rank r owns rows [r*H/G, (r+1)*H/G) of every per-cell array and the agent slots given by two
+ * global ranges (s0/n0: its slab's alive agents in the reference's row-major order; s1/n1: its share of
+ * the ghost slots).  Per-cell arrays and the action array are allocated by the caller as SYMMETRIC
+ * memory (e.g. torch.distributed._symmetric_memory) and passed as device tables of G peer base
+ * pointers; the kernels read / atomically update remote cells directly over NVLink.  The caller
+ * places a cross-rank barrier after die_slab_move_claim, after die_slab_field and after die_slab_feed.
+ * Results are identical to a single-GPU Env on the concatenated state.
+ *   medium tables: each peer buffer [3][H/G][W];  claim [H/G*W] int32 (init -1);  consumed [H/G*W];
+ *   grad [H/G*W][2];  action [3][n0[q]+n1[q]];  agents_local [4][Ml], theta_local [Ml]. */
+#define DIE_MAX_RANKS 8
+typedef struct die_slab_geom {
+    int32_t G, rank, H, W;
+    int64_t M;                                  /* global slot count */
+    int64_t s0[DIE_MAX_RANKS], n0[DIE_MAX_RANKS], s1[DIE_MAX_RANKS], n1[DIE_MAX_RANKS];
+} die_slab_geom_t;
+typedef struct die_slab die_slab_t;
+
+int die_slab_create(const die_slab_geom_t* geom, const die_dynamics_t* dyn, die_slab_t** out);
+int die_slab_destroy(die_slab_t* slab);
+int die_slab_bind(die_slab_t* slab, const void* medium_a_tbl_dev, const void* medium_b_tbl_dev,
+                  const void* claim_tbl_dev, const void* consumed_tbl_dev, const void* grad_tbl_dev,
+                  const void* action_tbl_dev);
+/* GradientAgent/PhysarumAgent.forward for this rank's slots; cur = index (0/1) of the current medium. */
+int die_slab_forward(die_slab_t* slab, const die_gradient_params_t* p, int32_t cur,
+                     const double* agents_local_dev, double* theta_local_dev, double* action_local_dev,
+                     const uint8_t* coin_local_dev, int32_t hints /* bit0: published grad, bit1: cell cache */,
+                     uint64_t seed, uint64_t step, void* stream);
+int die_slab_move_claim(die_slab_t* slab, double* agents_local_dev, const double* action_local_dev, void* stream);
+int die_slab_field(die_slab_t* slab, int32_t cur, int32_t publish_grad, void* stream);
+/* stats_dev[0] = this rank's sum of gained, stats_dev[1] = its alive count (as double); the caller
+ * all-reduces them (the only collective of the step). */
+int die_slab_feed(die_slab_t* slab, double* agents_local_dev, const double* action_local_dev,
+                  double* stats_dev, void* stream);
+const int32_t* die_slab_cells(const die_slab_t* slab);    /* int32 [Ml] GLOBAL linear cell of every local slot */
+
 /* Field-pass implementation switch (tests / A-B timing): 0 = shared-memory tile kernel (default),
  * 1 = register-tiled warp-marching kernel (blur radius <= 3; measured slower on B200 so far: 0.29 vs
  * 0.25 ms at 4096^2).  Both give bit-identical results. */

@@ -1,0 +1,57 @@
+"""One field split into row slabs over G ranks (die_b200/slab.py) must reproduce the single-GPU Env
+bit for bit.  Here the G ranks are emulated in one process on one GPU (the multi-rank kernels never
+wait on each other, so running the phases rank after rank is exact); the real multi-process /
+NVLink path is exercised by tools/slab_check.py under torchrun."""
+import numpy as np
+import pytest
+
+from tests._parity import make_pair, lattice_theta
+
+pytestmark = pytest.mark.gpu
+PHYS = dict(scale=0.02, turn_angle=30, sense_offset=0.08)      # large moves: agents cross slab seams quickly
+
+
+@pytest.mark.parametrize("shape,G", [((64, 64), 2), ((64, 64), 4), ((96, 80), 4), ((48, 36), 3), ((128, 32), 8)])
+def test_slab_world_equals_single_env(shape, G):
+    import die_b200 as D
+    from die_b200.slab import EmulatedSlabWorld
+    (ref,), env = make_pair(shape, seed=31, ratio=0.15)
+    medium0, agents0 = env.get_state()
+    m = env.max_agents
+    theta0, _ = lattice_theta(m, 30, 31)
+    agent = D.PhysarumAgent(max_agents=m, **PHYS)
+    agent.set_state(theta=theta0)
+    world = EmulatedSlabWorld(medium0, agents0, theta0, G, **PHYS)
+    rng = np.random.default_rng(1)
+    obs = env._get_current_obs
+    crossed = 0
+    for it in range(30):
+        coin = rng.integers(0, 2, m)
+        act = agent.forward(obs, coin=coin)
+        world.forward(coin)
+        obs, r, _, _, info = env.step(act)
+        wr, walive, _ = world.step()
+        med, ag = env.get_state()
+        wmed, wag, wth, wact, wcells = world.gather()
+        assert np.array_equal(wact, act.cpu().numpy()), f"action differs at step {it}"
+        assert np.array_equal(wcells, env.last_cells().cpu().numpy()), f"cells differ at step {it}"
+        assert np.array_equal(wmed, med), f"medium differs at step {it}"
+        assert np.array_equal(wag, ag), f"agents differ at step {it}"
+        assert np.array_equal(wth, agent.get_state()[0]), f"theta differs at step {it}"
+        assert walive == info['num_agents']
+        assert abs(wr - r) <= 1e-11 * max(1.0, abs(r))
+        rows = wcells // shape[1]
+        owner_of_cell = rows // (shape[0] // G)
+        slot_owner = np.concatenate([np.full(world.layout.local_slots(q), q) for q in range(G)])
+        ids = np.concatenate([world.layout.global_ids(q) for q in range(G)])
+        crossed = max(crossed, int((owner_of_cell[ids] != slot_owner).sum()))
+    assert crossed > 0, "the test must exercise agents standing on another rank's slab"
+
+
+def test_slab_layout_ranges():
+    from die_b200.slab import make_layout
+    L = make_layout((64, 32), 4, 2048, [50, 60, 40, 55])
+    assert L.s0 == [0, 50, 110, 150] and L.n0 == [50, 60, 40, 55]
+    assert sum(L.n1) == 2048 - 205 and L.s1[0] == 205
+    ids = np.concatenate([L.global_ids(q) for q in range(4)])
+    assert sorted(ids.tolist()) == list(range(2048))
