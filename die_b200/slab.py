@@ -299,3 +299,197 @@ class EmulatedSlabWorld:
             action[:, ids] = r.action.cpu().numpy()[:, :n]
             cells[ids] = r.cells().cpu().numpy()
         return medium, agents, theta, action, cells
+
+
+# --------------------------------------------------------------------------------------------
+# real multi-process environment (one process per GPU, torchrun)
+# --------------------------------------------------------------------------------------------
+def _grid(n: int, lo: int, hi: int, device) -> torch.Tensor:
+    """np.linspace(0, 1, n)[lo:hi] with numpy's arithmetic: i * (1/(n-1)), last element exactly 1."""
+    idx = torch.arange(lo, hi, dtype=torch.float64, device=device)
+    g = idx * (1.0 / (n - 1))
+    if hi == n:
+        g[-1] = 1.0
+    return g
+
+
+def device_gradient_noise(H: int, W: int, row_lo: int, row_hi: int, periods: int, seed: int, device) -> torch.Tensor:
+    """Rows [row_lo, row_hi) of the Perlin-style food texture of die_b200.data_init.gradient_noise,
+    evaluated on the device (same lattice for every rank: it depends on (seed, periods) only)."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(seed)
+    ang = (torch.rand((periods + 2, periods + 2), generator=gen, dtype=torch.float64) * (2 * np.pi)).to(device)
+    gx, gy = torch.cos(ang), torch.sin(ang)
+    xs = _grid(H, row_lo, row_hi, device) * periods
+    ys = _grid(W, 0, W, device) * periods
+    x0, y0 = torch.floor(xs).long(), torch.floor(ys).long()
+    fx, fy = (xs - x0)[:, None], (ys - y0)[None, :]
+    x0, y0 = x0[:, None], y0[None, :]
+
+    def fade(t):
+        return t * t * t * (t * (t * 6. - 15.) + 10.)
+
+    def corner(ix, iy, dx, dy):
+        return gx[ix, iy] * dx + gy[ix, iy] * dy
+
+    n00 = corner(x0, y0, fx, fy)
+    n10 = corner(x0 + 1, y0, fx - 1., fy)
+    n01 = corner(x0, y0 + 1, fx, fy - 1.)
+    n11 = corner(x0 + 1, y0 + 1, fx - 1., fy - 1.)
+    u, v = fade(fx), fade(fy)
+    nx0 = n00 + u * (n10 - n00)
+    nx1 = n01 + u * (n11 - n01)
+    return torch.round((nx0 + v * (nx1 - nx0)) * 1000.0) / 1000.0
+
+
+class SlabEnv:
+    """``Env`` for ONE field split over the ranks of a torch.distributed group (one process per GPU).
+
+        env = SlabEnv((32768, 32768), Dynamics(init_agent_ratio=0.1))        # collective
+        agent = SlabPhysarumAgent(env, scale=..., sense_offset=...)
+        obs = env._get_current_obs
+        for i in range(iters):
+            action = agent.forward(obs)
+            obs, reward, terminated, truncated, info = env.step(action)
+
+    obs = (this rank's agents [4, Ml], this rank's medium slab [3, H/G, W]); reward / info are global
+    (one 2-double all-reduce per step).  ``init_state=(layout, medium_slab, agents_local)`` injects a split
+    of a global state (``split_global_state``); otherwise the state is generated on the device."""
+
+    def __init__(self, field_size: Tuple[int, int], dynamics: Optional[Dynamics] = None, *, group=None,
+                 init_state=None, seed: int = 0, noise_periods: Optional[int] = None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.dynamics = dynamics or Dynamics()
+        self.peers = SymmetricPeers(group)
+        self.rank, self.G, self.device = self.peers.rank, self.peers.G, self.peers.device
+        H, W = int(field_size[0]), int(field_size[1])
+        if H % self.G:
+            raise ValueError(f"H={H} must be divisible by the world size {self.G}")
+        rp = H // self.G
+        M = H * W
+        if init_state is not None:
+            layout, medium_slab, agents_local = init_state
+            medium_slab = torch.as_tensor(medium_slab, dtype=torch.float64).to(self.device)
+            agents_local = torch.as_tensor(agents_local, dtype=torch.float64).to(self.device)
+        else:
+            medium_slab, alive_rc = self._device_init(H, W, rp, seed, noise_periods)
+            counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.G)]
+            dist.all_gather(counts, torch.tensor([alive_rc.shape[0]], dtype=torch.int64, device=self.device),
+                            group=self.peers.group)
+            layout = make_layout((H, W), self.G, M, [int(c.item()) for c in counts])
+            agents_local = self._device_agents(layout, alive_rc, H, W, rp, seed)
+        self.layout = layout
+        Ml = layout.local_slots(self.rank)
+        Ml_max = max(layout.local_slots(q) for q in range(self.G))
+        P = self.peers
+        med_a, tbl_a = P.alloc((3, rp, W), torch.float64)
+        med_b, tbl_b = P.alloc((3, rp, W), torch.float64)
+        claim, tbl_c = P.alloc((rp * W,), torch.int32, fill=-1)
+        cons, tbl_k = P.alloc((rp * W,), torch.float64)
+        grad, tbl_g = P.alloc((rp * W, 2), torch.float64)
+        act_full, tbl_act = P.alloc((3 * max(Ml_max, 1),), torch.float64)
+        med_a.copy_(medium_slab)
+        del medium_slab
+        self._keep = (claim, cons, grad, act_full)
+        action = act_full[:3 * max(Ml, 1)].view(3, max(Ml, 1))
+        tensors = dict(medium=[med_a, med_b], action=action, agents=agents_local.contiguous(),
+                       theta=torch.zeros(max(Ml, 1), dtype=torch.float64, device=self.device))
+        tables = dict(medium_a=tbl_a, medium_b=tbl_b, claim=tbl_c, consumed=tbl_k, grad=tbl_g, action=tbl_act)
+        self.slab = SlabRank(layout, self.rank, self.dynamics, tensors, tables, self.device)
+        self._stats_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize(self.device)
+        P.barrier()
+
+    # -- device-side initial state (core/env.py:74-86 in spirit; init-time only) -----------------------
+    def _device_init(self, H, W, rp, seed, noise_periods):
+        periods = noise_periods or max(8, 8 * H // 256)
+        lo = self.rank * rp
+        food = device_gradient_noise(H, W, lo, lo + rp, periods, seed, self.device)
+        food = food * ((food >= 0.0) & (food <= 1.0))
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed * 1000003 + self.rank)
+        u = torch.round(torch.rand((rp, W), generator=gen, dtype=torch.float64, device=self.device) * 1000.0) / 1000.0
+        occ = ((u > 0.0) & (u <= self.dynamics.init_agent_ratio)).to(torch.float64)
+        medium = torch.zeros((3, rp, W), dtype=torch.float64, device=self.device)
+        medium[0], medium[1] = occ, food
+        self._gen = gen
+        return medium, torch.nonzero(occ)                   # row-major (local row, col)
+
+    def _device_agents(self, layout, alive_rc, H, W, rp, seed):
+        Ml, n0 = layout.local_slots(self.rank), layout.n0[self.rank]
+        agents = torch.zeros((4, max(Ml, 1)), dtype=torch.float64, device=self.device)
+        gx = _grid(H, self.rank * rp, (self.rank + 1) * rp, self.device)
+        gy = _grid(W, 0, W, self.device)
+        agents[0, :n0] = gx[alive_rc[:, 0]]
+        agents[1, :n0] = gy[alive_rc[:, 1]]
+        agents[2, :n0] = 1.0
+        u = torch.round(torch.rand(n0, generator=self._gen, dtype=torch.float64, device=self.device) * 1000.0) / 1000.0
+        agents[3, :n0] = 0.9 * u + 0.1
+        return agents
+
+    # -- the reference protocol ---------------------------------------------------------------------------
+    @property
+    def agents(self):
+        return self.slab.agents
+
+    @property
+    def medium(self):
+        return self.slab.medium[self.slab.cur]
+
+    @property
+    def _get_current_obs(self):
+        return self.agents, self.medium
+
+    def step_async(self, action=None):
+        """All kernels + barriers + the stats all-reduce enqueued; returns the device stats tensor
+        [sum gained, num alive] (global)."""
+        s = self.slab
+        if action is not None and action.data_ptr() != s.action.data_ptr():
+            s.action.copy_(action)
+        s.phase_move()
+        self.peers.barrier()          # every claim is in before any slab is blurred
+        s.phase_field()
+        self.peers.barrier()          # consumed_field / new medium complete before anybody gathers from it
+        s.phase_feed()
+        self.peers.barrier()          # claim table clean before the next step's claims
+        self._dist.all_reduce(s.stats, group=self.peers.group)
+        return self._get_current_obs, s.stats
+
+    def step(self, action=None):
+        obs, stats = self.step_async(action)
+        self._stats_host.copy_(stats, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        reward, n = float(self._stats_host[0]), int(round(float(self._stats_host[1])))
+        mean = reward / n if n > 0 else 0.
+        info = {'num_agents': n, 'reward': np.round(reward, 3), 'mean_reward': np.round(mean, 5)}
+        return obs, reward, n == 0, False, info
+
+
+class SlabPhysarumAgent:
+    """PhysarumAgent (core/agent/gradient.py:138-219, default inertia = noise = 0) for a SlabEnv."""
+
+    def __init__(self, env: SlabEnv, *, seed: int = 0, theta=None, **physarum_kw):
+        self.env = env
+        self.params = _physarum_params(**physarum_kw)
+        self._seed, self._step = seed + 7919 * env.rank, 0
+        Ml = env.layout.local_slots(env.rank)
+        if theta is None:
+            tr = self.params.turn_radians
+            nlat = int(round(2 * np.pi / tr))
+            gen = torch.Generator(device=env.device)
+            gen.manual_seed(self._seed)
+            k = torch.randint(-nlat // 2, nlat - nlat // 2, (max(Ml, 1),), generator=gen, device=env.device)
+            theta = k.to(torch.float64) * tr
+        env.slab.theta.copy_(torch.as_tensor(theta, dtype=torch.float64).to(env.device).reshape(-1)[:max(Ml, 1)])
+        self._coin = None
+
+    def forward(self, obs=None, coin=None):
+        s = self.env.slab
+        coin_t = None
+        if coin is not None:
+            coin_t = torch.as_tensor(np.ascontiguousarray(coin).astype(np.uint8)).to(s.device)
+            self._coin = coin_t
+        s.forward(self.params, coin_t, self._seed, self._step)
+        self._step += 1
+        return s.action
