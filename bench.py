@@ -242,6 +242,62 @@ def roofline_of(meas, B_local, wl_name):
                      "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4)}}, step_bytes
 
 
+def run_slab(args, torch, dist, device, rank, world):
+    """BASELINE configs[4]: ONE field split into row slabs over the ranks, NVLink peer access in-kernel
+    (die_b200/slab.py).  Agent parameters are the README ones expressed in cells: the
+    256^2 geometry (1.785 cells per step, 10.2 cells look-ahead) at any field size."""
+    import die_b200 as D
+    from die_b200.slab import SlabEnv, SlabPhysarumAgent
+    from die_b200.sharding import max_over_ranks
+    N = args.field
+    phys = dict(scale=1.785 / (N - 1), turn_angle=30, sense_offset=10.2 / (N - 1))
+    t0 = time.time()
+    env = SlabEnv((N, N), D.Dynamics(init_agent_ratio=AGENT_RATIO), seed=3)
+    agent = SlabPhysarumAgent(env, seed=11, **phys)
+    torch.cuda.synchronize()
+    setup_s = time.time() - t0
+    obs = env._get_current_obs
+    for _ in range(args.warmup):
+        obs, _ = env.step_async(agent.forward(obs))
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device.index)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        obs, stats = env.step_async(agent.forward(obs))
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    reward, alive = float(stats[0].item()), int(round(float(stats[1].item())))
+    peak, peak_src = measured_hbm_peak()
+    C = N * N
+    step_bytes = 240.0 * C + 24.0 * alive
+    if rank == 0:
+        gbs = step_bytes / (ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": C / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated gradient-noise food, Bernoulli(0.1) agents)",
+                "config": {"workload": f"physarum_single_field_{N}x{N}_slab", "field": [N, N], "agent": "PhysarumAgent",
+                           **phys, "agent_ratio": AGENT_RATIO, "max_agents": C, "alive_agents": alive,
+                           "decomposition": f"{world} row slabs, symmetric memory, in-kernel NVLink peer loads/atomics, "
+                                            "3 barriers + one 2-double all-reduce per step",
+                           "l2": "per-step working set >> 126 MB L2 (no flush)"},
+                "agent_steps_per_s": C / (ms * 1e-3), "alive_agent_steps_per_s": alive / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs / world, 1), "peak": peak,
+                             "unit": "GB/s per GPU", "frac": round(gbs / world / peak, 4), "peak_source": peak_src,
+                             "traffic": None},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * 9, "launches_per_step": 9,
+                "clocks": clocks, "setup_s": round(setup_s, 1), "last_reward": reward}
+        print(json.dumps(line))
+
+
 def run_die_b200(args):
     import torch
     import torch.distributed as dist
@@ -260,6 +316,14 @@ def run_die_b200(args):
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     import die_b200 as D
+
+    if args.workload == "slab":
+        if world < 2:
+            raise SystemExit("--workload slab needs torchrun with >= 2 ranks")
+        run_slab(args, torch, dist, device, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     # ---- headline workload: 4096 independent 256x256 Physarum envs sharded over the ranks ----------
     workload = args.workload
@@ -427,7 +491,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="die_b200", choices=["die_b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "field4096", "batch256"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "field4096", "batch256", "slab"])
     ap.add_argument("--field", type=int, default=4096, help="side of the single field (field4096 workload)")
     ap.add_argument("--batch", type=int, default=4096, help="total number of 256x256 envs (batch256 workload)")
     ap.add_argument("--e2e-steps", type=int, default=10)

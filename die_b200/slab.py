@@ -405,16 +405,19 @@ class SlabEnv:
     def _device_init(self, H, W, rp, seed, noise_periods):
         periods = noise_periods or max(8, 8 * H // 256)
         lo = self.rank * rp
-        food = device_gradient_noise(H, W, lo, lo + rp, periods, seed, self.device)
-        food = food * ((food >= 0.0) & (food <= 1.0))
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed * 1000003 + self.rank)
-        u = torch.round(torch.rand((rp, W), generator=gen, dtype=torch.float64, device=self.device) * 1000.0) / 1000.0
-        occ = ((u > 0.0) & (u <= self.dynamics.init_agent_ratio)).to(torch.float64)
         medium = torch.zeros((3, rp, W), dtype=torch.float64, device=self.device)
-        medium[0], medium[1] = occ, food
+        chunk = max(1, min(rp, (1 << 25) // W))              # bound the temporaries of the noise evaluation
+        for r0 in range(0, rp, chunk):
+            r1 = min(rp, r0 + chunk)
+            food = device_gradient_noise(H, W, lo + r0, lo + r1, periods, seed, self.device)
+            medium[1, r0:r1] = food * ((food >= 0.0) & (food <= 1.0))
+            u = torch.round(torch.rand((r1 - r0, W), generator=gen, dtype=torch.float64, device=self.device) * 1000.0) / 1000.0
+            medium[0, r0:r1] = ((u > 0.0) & (u <= self.dynamics.init_agent_ratio)).to(torch.float64)
+            del food, u
         self._gen = gen
-        return medium, torch.nonzero(occ)                   # row-major (local row, col)
+        return medium, torch.nonzero(medium[0])              # row-major (local row, col)
 
     def _device_agents(self, layout, alive_rc, H, W, rp, seed):
         Ml, n0 = layout.local_slots(self.rank), layout.n0[self.rank]
