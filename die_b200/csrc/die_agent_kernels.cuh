@@ -174,7 +174,7 @@ gradient_forward_kernel(const GradientArgs a) {
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
         // food under the agent (:113-115), issued early: independent of the turn arithmetic
         const int here = (cl_p != nullptr) ? cl_p[i] : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = SLAB ? *slab_chan(a.st.medium_in, a.sg, 1, here) : food[here];
+        const double food_here = SLAB ? __ldg(slab_chan(a.st.medium_in, a.sg, 1, here)) : food[here];
 
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
@@ -182,15 +182,17 @@ gradient_forward_kernel(const GradientArgs a) {
         if (sc_p != nullptr) sc_p[i] = sc;
         double gx, gy;
         if (SLAB ? a.st.grad != nullptr : grad != nullptr) {   // published by the field pass: one 16-byte gather
-            const double2 g2 = SLAB ? *slab_cell(a.st.grad, a.sg, sc) : grad[sc];
+            // read-only for the whole launch: ld.global.nc lets L1 cache lines that live on a peer GPU
+            // (the ghost slots of every rank all look at the same few cells near the corners)
+            const double2 g2 = SLAB ? __ldg(slab_cell(a.st.grad, a.sg, sc)) : grad[sc];
             gx = g2.x;
             gy = g2.y;
         } else {
             const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
             const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
             if (SLAB) {
-                gx = *slab_chan(a.st.medium_in, a.sg, 2, sc + xp) - *slab_chan(a.st.medium_in, a.sg, 2, sc + xm);
-                gy = *slab_chan(a.st.medium_in, a.sg, 2, sc + yp) - *slab_chan(a.st.medium_in, a.sg, 2, sc + ym);
+                gx = __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + xp)) - __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + xm));
+                gy = __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + yp)) - __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + ym));
             } else {
                 gx = chem[sc + xp] - chem[sc + xm];
                 gy = chem[sc + yp] - chem[sc + ym];
@@ -359,7 +361,7 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? (SLAB ? *slab_cell(st.consumed, sg, cell[k]) : cf[cell[k]]) : 0.0;
+        eaten[k] = valid[k] ? (SLAB ? __ldg(slab_cell(st.consumed, sg, cell[k])) : cf[cell[k]]) : 0.0;
         alive[k] = valid[k] && ag_alive[i] > 0.0;
         stock[k] = valid[k] ? ag_alive[M + i] : 0.0;
         dx[k] = valid[k] ? ac[i] : 0.0;

@@ -106,8 +106,8 @@ field_step_kernel(const FieldArgs a) {
             const int gj = wrap_index(j0 - G - R + c, W);
             const int g = gi * W + gj;
             if (SLAB) {                       // rows outside this rank's slab come from the neighbours over NVLink
-                v[s] = *slab_chan(a.st.medium_in, a.sg, 2, g);
-                w[s] = *slab_cell(a.st.claim, a.sg, g);
+                v[s] = __ldg(slab_chan(a.st.medium_in, a.sg, 2, g));
+                w[s] = __ldg(slab_cell(a.st.claim, a.sg, g));
             } else {
                 v[s] = chem_in[g];
                 w[s] = win[g];
@@ -123,7 +123,7 @@ field_step_kernel(const FieldArgs a) {
                 if (SLAB) {                   // the winner is a GLOBAL slot id: its deposit lives on its owner
                     int64_t local;
                     const int q = slab_slot_owner(a.sg, w[s], local);
-                    x = x + a.st.action[q][2 * slab_slots_of(a.sg, q) + local];
+                    x = x + __ldg(a.st.action[q] + 2 * slab_slots_of(a.sg, q) + local);
                 } else {
                     x = x + dep[w[s]];
                 }

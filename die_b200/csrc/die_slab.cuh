@@ -50,14 +50,14 @@ __device__ __forceinline__ int slab_owner(const SlabGeom& g, int cell, int& loca
 __device__ __forceinline__ double* slab_chan(double* const* tab, const SlabGeom& g, int ch, int cell) {
     int local;
     const int o = slab_owner(g, cell, local);
-    return tab[o] + (int64_t)ch * g.slab_cells + local;
+    return (double*)__ldg((const unsigned long long*)(tab + o)) + (int64_t)ch * g.slab_cells + local;
 }
 
 template <typename T>
 __device__ __forceinline__ T* slab_cell(T* const* tab, const SlabGeom& g, int cell) {
     int local;
     const int o = slab_owner(g, cell, local);
-    return tab[o] + local;
+    return (T*)__ldg((const unsigned long long*)(tab + o)) + local;
 }
 
 __device__ __forceinline__ int64_t slab_slots_of(const SlabGeom& g, int q) { return g.n0[q] + g.n1[q]; }
