@@ -267,8 +267,13 @@ def run_slab(args, torch, dist, device, rank, world):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    mode = os.environ.get("DIE_SLAB_MODE", "reduce")          # diagnosis: reduce | noreduce | sync
     for _ in range(args.steps):
-        obs, stats = env.step_async(agent.forward(obs))
+        obs, stats = env.step_async(agent.forward(obs), reduce_stats=(mode != "noreduce"))
+        if mode == "sync":
+            torch.cuda.synchronize()
+    if mode == "noreduce":
+        dist.all_reduce(stats)
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()

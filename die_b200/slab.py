@@ -444,9 +444,9 @@ class SlabEnv:
     def _get_current_obs(self):
         return self.agents, self.medium
 
-    def step_async(self, action=None):
-        """All kernels + barriers + the stats all-reduce enqueued; returns the device stats tensor
-        [sum gained, num alive] (global)."""
+    def step_async(self, action=None, reduce_stats: bool = True):
+        """All kernels + barriers (+ the stats all-reduce unless ``reduce_stats=False``) enqueued; returns
+        the device stats tensor [sum gained, num alive] (global, or this rank's share when not reduced)."""
         s = self.slab
         if action is not None and action.data_ptr() != s.action.data_ptr():
             s.action.copy_(action)
@@ -456,7 +456,8 @@ class SlabEnv:
         self.peers.barrier()          # consumed_field / new medium complete before anybody gathers from it
         s.phase_feed()
         self.peers.barrier()          # claim table clean before the next step's claims
-        self._dist.all_reduce(s.stats, group=self.peers.group)
+        if reduce_stats:
+            self._dist.all_reduce(s.stats, group=self.peers.group)
         return self._get_current_obs, s.stats
 
     def step(self, action=None):

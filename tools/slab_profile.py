@@ -32,7 +32,10 @@ def main():
         ev[7].record(); dist.all_reduce(s.stats)
         ev[8].record()
         torch.cuda.synchronize()
-        acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        cur = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        acc += cur
+        if rank in (0, world // 2) and it % 5 == 0:
+            print(f"rank {rank} step {it + 10}: total {cur.sum():.3f} ms  " + " ".join(f"{n}={v:.2f}" for n, v in zip(names, cur)), flush=True)
     acc /= steps
     out = [None] * world
     dist.all_gather_object(out, (rank, env.layout.local_slots(rank), env.layout.n0[rank], acc.round(3).tolist()))
