@@ -30,6 +30,7 @@ import numpy as np
 
 PHYS = dict(scale=0.007, turn_angle=30, sense_offset=0.04)      # reference README.md:45-48
 AGENT_RATIO = 0.1
+ARGS = None
 METRIC = "env cell-updates/sec (agent.forward + env.step, Physarum)"
 UNIT = "cell-updates/s"
 
@@ -43,6 +44,10 @@ UNIT = "cell-updates/s"
 #  the 8 B/cell consumed_field scratch, dx/dy re-read by the feed kernel -- are NOT counted)
 BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "agent_feed": 40.0, "field_step": 48.0,
          "finalize_stats": 0.0}
+# fused step (default): the forward kernel also does move_claim's reads, cell resolution and claims; the
+# positions (W{x,y}, 16 B) are committed by the feed kernel.  Same 240 B per cell-update in total.
+BYTES_FUSED = {"physarum_forward": 96.0 + 40.0, "move_claim": 0.0, "agent_feed": 40.0 + 16.0, "field_step": 48.0,
+               "finalize_stats": 0.0}
 ALIVE_EXTRA = {"field_step": 24.0}
 
 
@@ -164,6 +169,7 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
     M = env.max_agents
     agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
     agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
+    agent.fuse_move = not ARGS.no_fuse
     return env, agent, alive
 
 
@@ -218,7 +224,7 @@ def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     kernel_ms = {"physarum_forward": sum(a.elapsed_time(b) for a, b in fwd_events) / n_prof}
     kernel_ms.update({k: v / max(nprof, 1) for k, v in kms.items()})
     return dict(env=env, agent=agent, ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
-                alive_local=alive_local, M=M, C=C)
+                alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused))
 
 
 def roofline_of(meas, B_local, wl_name):
@@ -226,13 +232,14 @@ def roofline_of(meas, B_local, wl_name):
     M, C, alive_local = meas["M"], meas["C"], meas["alive_local"]
     slots_local, cells_local = M * B_local, C * B_local
     kernels = {}
+    BY = BYTES_FUSED if meas.get("fused") else BYTES
     for k, t_ms in meas["kernel_ms"].items():
         units = cells_local if k == "field_step" else slots_local
-        nbytes = BYTES[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
+        nbytes = BY[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
         gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         kernels[k] = {"ms": round(t_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1),
                       "frac": round(gbs / peak, 4)}
-    dominant = max((k for k in kernels if BYTES[k] > 0), key=lambda k: kernels[k]["ms"])
+    dominant = max((k for k in kernels if BY[k] > 0), key=lambda k: kernels[k]["ms"])
     step_bytes = sum(v["algorithmic_bytes"] for v in kernels.values())
     step_gbs = step_bytes / (meas["ms_per_step"] * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["gbs"], "peak": peak,
@@ -321,6 +328,10 @@ def run_die_b200(args):
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     import die_b200 as D
+    from die_b200 import _lib as dlib
+    for kv in args.tune:
+        key, val = kv.split("=")
+        dlib.check(dlib.load().die_set_tuning(key.encode(), int(val)))
 
     if args.workload == "slab":
         if world < 2:
@@ -402,7 +413,7 @@ def run_die_b200(args):
     # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
-        cpu = time_oracle(args.cpu_field, args.cpu_steps, warmup=2)
+        cpu = time_oracle(args.cpu_field, args.cpu_steps, warmup=2, procs=args.cpu_procs)
 
     if rank == 0:
         line = {
@@ -417,7 +428,8 @@ def run_die_b200(args):
             "agent_steps_per_s": M * B_total / (ms_per_step * 1e-3),
             "alive_agent_steps_per_s": alive_local * n_gpus / (ms_per_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "also": also,
-            "gpu_launches": args.steps * 5, "launches_per_step": 5, "clocks": meas["clocks"],
+            "gpu_launches": args.steps * (4 if meas["fused"] else 5), "launches_per_step": 4 if meas["fused"] else 5,
+            "fused_move": meas["fused"], "tuning": ARGS.tune, "clocks": meas["clocks"],
             "setup_s": round(setup_s, 1),
         }
         print(json.dumps(line))
@@ -429,62 +441,67 @@ def run_die_b200(args):
 # --------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference)
 # --------------------------------------------------------------------------------------------
-def time_oracle(field_n, steps, warmup):
+def _oracle_worker(job):
+    """One process = one 256x256-style env stepped by the numpy oracle (imports no torch, no CUDA)."""
+    field_n, steps, warmup, seed = job
     from oracle import die_ref as R
     field = (field_n, field_n)
-    np.random.seed(0)
-    env = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=0)
+    np.random.seed(seed)
+    env = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=seed)
     m = env.agents.shape[-1]
     agent = R.PhysarumAgent(max_agents=m, **PHYS)
     obs = env._get_current_obs
     for _ in range(warmup):
         obs, *_ = env.step(agent.forward(obs))
-    times = []
+    t0 = time.time()
     for _ in range(steps):
-        t = time.perf_counter()
         obs, *_ = env.step(agent.forward(obs))
-        times.append(time.perf_counter() - t)
-    per = float(np.mean(times))
-    return {"value": field_n * field_n / per, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{steps} steps of PhysarumAgent on a {field_n}x{field_n} field (numpy/scipy oracle, "
-                      f"single thread like the reference), after {warmup} warm-up steps",
-            "ms_per_step": per * 1e3, "host_cpus": os.cpu_count()}
+    return t0, time.time()
+
+
+def time_oracle(field_n, steps, warmup, procs=None):
+    """The CPU path on this host: `procs` independent envs (one process each, the way the batched workload
+    parallelises on a CPU; the reference itself is single-threaded per env), `steps` steps each.
+    value = all cell-updates / (last finish - first start)."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    jobs = [(field_n, steps, warmup, k) for k in range(procs)]
+    if procs == 1:
+        spans = [_oracle_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            spans = pool.map(_oracle_worker, jobs)
+    wall = max(e for _, e in spans) - min(b for b, _ in spans)
+    per_env_step = float(np.mean([(e - b) / steps for b, e in spans]))
+    return {"value": field_n * field_n * steps * procs / wall, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x 1 env of {field_n}x{field_n} x {steps} steps of PhysarumAgent.forward + "
+                      f"Env.step (numpy/scipy/pandas oracle port of the reference's CPU path; the reference runs one "
+                      f"thread per env), after {warmup} warm-up steps",
+            "ms_per_env_step": per_env_step * 1e3, "single_core_value": field_n * field_n / per_env_step,
+            "host_cpus": os.cpu_count()}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port: the reference
-    itself cannot be imported here) on the host cores; each step is one Physarum iteration on a
-    bounded-size field with the same per-cell work as the GPU arm's workload."""
+    itself cannot be imported here) on all the host cores: one 256x256 env per process, each bench step =
+    one Physarum iteration of every process's env (a bounded sample of the 4096-env workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_gpus = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    from oracle import die_ref as R
     field_n = args.cpu_field
-    field = (field_n, field_n)
-    np.random.seed(0)
-    env = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=0)
-    m = env.agents.shape[-1]
-    agent = R.PhysarumAgent(max_agents=m, **PHYS)
-    obs = env._get_current_obs
-    for _ in range(args.warmup):
-        obs, *_ = env.step(agent.forward(obs))
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        obs, *_ = env.step(agent.forward(obs))
-    dt = time.perf_counter() - t0
-    value = field_n * field_n * args.steps / dt
-    sample = (f"each step = one PhysarumAgent.forward + Env.step on a {field_n}x{field_n} field "
-              f"(same per-cell work as the GPU arm's workload), numpy/scipy oracle port, 1 thread "
-              f"(the reference is single-threaded)")
+    cpu = time_oracle(field_n, args.steps, args.warmup, procs=args.cpu_procs)
+    value = cpu["value"]
     wl = "physarum_batched_4096x256x256"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": field_n * field_n * cpu["cores"] / value * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": wl, "sample_field": list(field),
+            "dtype": "f64", "data": "synthetic", "config": {"workload": wl, "sample_field": [field_n, field_n],
+                                                            "sample_envs": cpu["cores"],
                                                             "agent": "PhysarumAgent", **PHYS,
                                                             "agent_ratio": AGENT_RATIO},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -502,13 +519,19 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU on the host-buffer (e2e) leg")
     ap.add_argument("--no-single-field", action="store_true")
-    ap.add_argument("--cpu-field", type=int, default=512, help="side of the CPU sample field")
-    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-field", type=int, default=256, help="side of each CPU sample env")
+    ap.add_argument("--cpu-steps", type=int, default=100, help="steps per CPU env in the cpu_baseline leg")
+    ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="A-B: agent.forward does not evaluate the move speculatively")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global ARGS
+    ARGS = args
     if args.impl == "reference":
         run_reference(args)
     else:

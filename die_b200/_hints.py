@@ -16,6 +16,20 @@ def publish(env, medium_buf) -> None:
     _REGISTRY[(medium_buf.device.index, medium_buf.data_ptr())] = weakref.ref(env)
 
 
+def find_env(agents, medium):
+    """The live Env one of whose medium buffers `medium` is (same storage, same shape, and an agents tensor
+    of that Env's size), or None.  Which of the Env's caches are valid for this observation is decided by
+    ``Env._forward_flags``."""
+    ref = _REGISTRY.get((medium.device.index, medium.data_ptr()))
+    env = ref() if ref is not None else None
+    if env is None or env._handle is None:
+        return None
+    buf = env._medium_buf[0]
+    if medium.numel() != buf.numel() or medium.shape[-2:] != buf.shape[-2:] or agents.numel() != env._agents.numel():
+        return None
+    return env
+
+
 def lookup(agents, medium, want_gradient: bool):
     """-> (grad_ptr or None, cells_ptr or None) for this observation."""
     ref = _REGISTRY.get((medium.device.index, medium.data_ptr()))

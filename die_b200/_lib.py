@@ -7,6 +7,7 @@ from ._build import LIB_PATH
 
 DIE_MAX_RADIUS = 8
 BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
+FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE = 1, 2, 4
 
 
 class DieDynamics(C.Structure):
@@ -77,6 +78,14 @@ SIGNATURES = {
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "die_env_forward_gradient": (C.c_int, [_P, C.POINTER(DieGradientParams), _P, _P, _P, _P, _P, _P, _P, _P,
+                                           C.c_int32, C.c_uint64, C.c_uint64, _P]),
+    "die_env_step_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_env_discard_move": (C.c_int, [_P, _P]),
+    "die_env_pending_move": (C.c_int, [_P]),
+    "die_env_refresh_alive": (C.c_int, [_P, _P, _P]),
+    "die_set_turn_quick": (C.c_int, [C.c_int32]),
+    "die_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
     "die_slab_create": (C.c_int, [C.POINTER(DieSlabGeom), C.POINTER(DieDynamics), C.POINTER(_P)]),
     "die_slab_destroy": (C.c_int, [_P]),
     "die_slab_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

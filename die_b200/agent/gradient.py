@@ -68,7 +68,9 @@ class GradientAgent(_DeviceAgent):
         self._sense_cells = None
         self.record_sense_cells = False
         self.use_env_hints = True           # die_b200/_hints.py: cached cells + published gradient
+        self.fuse_move = True               # ... and the speculative move + claim for Env.step to adopt
         self.last_hints = (False, False)
+        self.last_speculated = False
 
     # -- state ------------------------------------------------------------------------------
     def _needs_prev(self) -> bool:
@@ -170,18 +172,32 @@ class GradientAgent(_DeviceAgent):
                 self._sense_cells = torch.empty((B, M), dtype=torch.int32, device=agents.device)
             cells_ptr = self._sense_cells.data_ptr()
 
-        # cached cells / published gradient of the Env that produced this observation, if provably valid
-        grad_hint, cells_hint = _hints.lookup(agents, medium, want_gradient=True) if self.use_env_hints else (None, None)
-        self.last_hints = (grad_hint is not None, cells_hint is not None)
-
         p = self._params_c()
+        prev_ptr = self._prev_grad.data_ptr() if self._prev_grad is not None else None
+        # The Env that produced this observation, if it provably did (die_b200/_hints.py): its cached cells and
+        # published gradient replace gathers, and the move of the action is evaluated in the same launch.
+        env = _hints.find_env(agents, medium) if self.use_env_hints else None
         with torch.cuda.device(agents.device):
-            _lib.check(self._lib.die_gradient_forward(
-                _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(),
-                self._theta.data_ptr(),
-                self._prev_grad.data_ptr() if self._prev_grad is not None else None,
-                action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, grad_hint, cells_hint,
-                self._seed, self._step, torch.cuda.current_stream().cuda_stream))
+            stream = torch.cuda.current_stream().cuda_stream
+            if env is not None:
+                flags = env._forward_flags(agents, medium, want_gradient=True, speculate=self.fuse_move)
+                _lib.check(self._lib.die_env_forward_gradient(
+                    env._handle, _lib.C.byref(p), agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
+                    prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, flags,
+                    self._seed, self._step, stream))
+            else:
+                flags = 0
+                _lib.check(self._lib.die_gradient_forward(
+                    _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
+                    prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, None, None,
+                    self._seed, self._step, stream))
+        # the kernel wrote `action` through its raw pointer: make that visible to torch's version counter, so a
+        # stale speculation can never be mistaken for this one (two envs sharing one agent, repeated forwards)
+        torch.autograd.graph.increment_version(action)
+        self.last_hints = (bool(flags & _lib.FWD_USE_GRADIENT), bool(flags & _lib.FWD_USE_CELLS))
+        self.last_speculated = bool(flags & _lib.FWD_SPECULATE_MOVE)
+        if self.last_speculated:
+            env._note_speculation(action)
         self._step += 1
         return action
 

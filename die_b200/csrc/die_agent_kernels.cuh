@@ -104,9 +104,11 @@ const_forward_kernel(double* __restrict__ action, int64_t M, int nchunk,
 // bit-reproducible routines (see that file for why).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFwdItems = 8;     // one 32-bit Philox word serves a thread's 8 coin flips
+// MINB (template): minimum resident CTAs per SM = register cap 65536 / (256 * MINB): 3 -> 80, 4 -> 64, 5 -> 48
 
 struct GradientArgs {
     die_gradient_params_t p;
+    die_turn_plan_t plan;       // guard-banded thresholds of the quick turn decision (die_turn.h)
     Axis ax, ay;                // axis 0 (H cells, coordinate x) and axis 1 (W cells, coordinate y)
     int H, W;
     int64_t M;
@@ -122,12 +124,28 @@ struct GradientArgs {
     const double2* grad;        // may be null: np.gradient(chem1) per cell, published by Env.step
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
+    // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
+    int32_t* winner;            // [B][H*W] claim table
+    int32_t* cells_out;         // [B][M] post-move cell of every slot (the env's OTHER cell buffer)
+    const uint32_t* alive_bits; // [B][Mw] bit i&31 of word i>>5 = (alive[i] > 0)
+    int64_t Mw;
+    int boundary;
     SlabGeom sg;                // SLAB instantiation only: H, W above are the GLOBAL field, M the LOCAL slots
     SlabTables st;
 };
 
-template <bool DISCRETE_TURN, bool SLAB>
-__global__ void __launch_bounds__(kAgentThreads)
+// Env._agent_move_handle_boundary (core/env.py:152-161) for one coordinate
+__device__ __forceinline__ double apply_boundary(double v, int boundary) {
+    if (boundary == DIE_BOUNDARY_WRAP) return mod1(v);
+    if (boundary == DIE_BOUNDARY_LIMIT) return fmin(fmax(v, 0.0), 1.0);          // np.clip(0., 1.)
+    return v;
+}
+
+// Software pipeline: the coalesced loads (x, y, theta, cached cell) of item k+1 are issued before the
+// arithmetic of item k, and the food gather of item k right at its start, so the only exposed memory
+// latency per item is the gradient gather at the sensed cell.
+template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB>
+__global__ void __launch_bounds__(kAgentThreads, MINB)
 gradient_forward_kernel(const GradientArgs a) {
     const die_gradient_params_t& p = a.p;
     const Axis ax = a.ax, ay = a.ay;
@@ -149,21 +167,45 @@ gradient_forward_kernel(const GradientArgs a) {
     int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
     const double2* grad = (a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
     const int32_t* cl_p = (a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
+    int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
+    int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
+    // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
+    const uint32_t* bits_p = MOVE ? a.alive_bits + ch.b * a.Mw + (first >> 5) : nullptr;
 
     uint32_t coin_bits = 0;
     if (DISCRETE_TURN && coin_p == nullptr)      // coin of slot (CTA, t, k) = bit k of this word
         coin_bits = philox_draw(a.seed, a.step, (uint64_t)blockIdx.x * kAgentThreads + threadIdx.x, 2u).x;
     const double atol = p.turn_radians * p.turn_tolerance;
-    const bool safe_div = p.use_grad_clip && p.grad_clip > 0.0;
     // with an identity momentum step (no inertia, no noise) and a unit-length direction the new
     // heading angle(cos d + i sin d) comes out of die_sincos_angle together with cos d, sin d
     const bool fused_heading = DISCRETE_TURN && pg == nullptr && p.normalized_grad;
 
+    bool nvalid = first < M;
+    double nx = 0.0, ny = 0.0, nth = 0.0;
+    int ncell = 0;
+    if (nvalid) {
+        nx = ag_x[0];
+        ny = ag_x[M];
+        nth = th_p[0];
+        if (cl_p != nullptr) ncell = cl_p[0];
+    }
+
     for (int k = 0; k < kFwdItems; ++k) {
+        if (!nvalid) break;
         const int i = k * kAgentThreads;                       // offset from this thread's first slot
-        if (first + i >= M) break;
-        const double x = ag_x[i], y = ag_x[M + i];
-        const double th = th_p[i];
+        const double x = nx, y = ny, th = nth;
+        // food under the agent (:113-115), issued first: independent of the turn arithmetic
+        const int here = (cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
+        const double food_here = SLAB ? __ldg(slab_chan(a.st.medium_in, a.sg, 1, here)) : food[here];
+        uint32_t alive_word = 0;
+        if (MOVE) alive_word = bits_p[i >> 5];
+        nvalid = (k + 1 < kFwdItems) && (first + i + kAgentThreads < M);
+        if (nvalid) {                                          // next item's coalesced loads
+            nx = ag_x[i + kAgentThreads];
+            ny = ag_x[M + i + kAgentThreads];
+            nth = th_p[i + kAgentThreads];
+            if (cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
+        }
 
         // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
         double sn, cs;
@@ -172,9 +214,6 @@ gradient_forward_kernel(const GradientArgs a) {
         const double py = y + p.sense_offset * sn;
         // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
         const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
-        // food under the agent (:113-115), issued early: independent of the turn arithmetic
-        const int here = (cl_p != nullptr) ? cl_p[i] : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = SLAB ? __ldg(slab_chan(a.st.medium_in, a.sg, 1, here)) : food[here];
 
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
@@ -201,50 +240,32 @@ gradient_forward_kernel(const GradientArgs a) {
             if (yp - ym == 2) gy *= 0.5;
         }
 
-        // scipy.linalg.norm(axis=0, ord=2) == sqrt(gx*gx + gy*gy) (no hypot scaling);
-        // grad = nan_to_num(grad / norm) (:62); grad *= (norm >= clip) (:65) keeps signed zeros
-        const double norm = sqrt(gx * gx + gy * gy);
-        const bool clipped = p.use_grad_clip && !(norm >= p.grad_clip);
-        if (p.normalized_grad) {
-            if (clipped) {          // (+-q) * 0.0: only the zero's sign survives; 0/0 -> nan -> +0
-                gx = (norm == 0.0 && gx == 0.0) ? 0.0 : copysign(0.0, gx);
-                gy = (norm == 0.0 && gy == 0.0) ? 0.0 : copysign(0.0, gy);
-            } else if (safe_div) {  // norm >= clip > 0: the quotient is finite
-                gx = __ddiv_rn(gx, norm);
-                gy = __ddiv_rn(gy, norm);
-            } else {
-                gx = div_nan_to_num(gx, norm);
-                gy = div_nan_to_num(gy, norm);
-            }
-        } else if (clipped) {
-            gx *= 0.0;
-            gy *= 0.0;
-        }
-
         bool deposit_mask = true;
         double heading = 0.0;
         if (DISCRETE_TURN) {
-            // PhysarumAgent._discrete_turn / _choose_turn (:168-208)
-            const double dr = p.normalized_grad ? 1.0 : hypot(gx, gy);
-            const double drads = angle_xy<true>(gx, gy);
-            double dd = renormalize_radians(th - drads);
-            const bool und_grad = fabs(0.0 - drads) <= 1e-8 + 1e-5 * fabs(drads);
-            const bool und_turn = fabs(0.0 - dd) <= atol + 1e-2 * fabs(dd);
-            const bool unseen = fabs(dd) > p.sense_radians;
-            const bool und = und_grad || und_turn || unseen;
+            // PhysarumAgent._discrete_turn / _choose_turn (:168-208).  die_turn_quick settles the turn from
+            // the raw gradient and (sin, cos) of the heading whenever no threshold is within its guard band;
+            // the rest (about one warp in 300) runs the reference's own arithmetic, die_turn_exact.
+            die_turn_t tr;
+            double dr = 1.0;
+            if (!(a.plan.enabled && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
+                // _get_gradient (:59-65): scipy.linalg.norm, nan_to_num(grad / norm), grad *= (norm >= clip)
+                die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
+                if (!p.normalized_grad) dr = hypot(gx, gy);
+                tr = die_turn_exact(gx, gy, th, atol, p.sense_radians);
+            }
             const int c = (coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
-            double turn = ((double)c - 0.5) * 2.0;
-            dd *= und ? 0.0 : 1.0;
-            if (dd > atol) turn = -1.0;
-            if (dd < -atol) turn = 1.0;
+            double turn = (tr.turn != 0) ? (double)tr.turn : ((double)c - 0.5) * 2.0;
             turn *= p.turn_radians;
-            deposit_mask = !(und_grad || und_turn);
+            deposit_mask = tr.deposit_mask != 0;
             const double dirn = renormalize_radians(th + turn);
             double s2, c2;
             if (fused_heading) die_sincos_angle(dirn, &s2, &c2, &heading);
             else die_sincos(dirn, &s2, &c2);
             gx = dr * c2;
             gy = dr * s2;
+        } else {
+            die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
         }
 
         // _process_momentum (:82-91)
@@ -272,9 +293,21 @@ gradient_forward_kernel(const GradientArgs a) {
         double dep = p.deposit * food_here;
         if (DISCRETE_TURN) dep = dep * (deposit_mask ? 1.0 : 0.1);
 
-        ab[i] = gx * p.scale;                                  // unmasked (Q8)
-        ab[M + i] = gy * p.scale;
+        const double adx = gx * p.scale, ady = gy * p.scale;  // unmasked (Q8)
+        ab[i] = adx;
+        ab[M + i] = ady;
         ab[2 * M + i] = dep;
+
+        if (MOVE) {
+            // Env._agent_move (core/env.py:152-172) of THIS action + cell resolution + claim: what
+            // move_claim_kernel would compute from (agents, action); the positions themselves are
+            // committed by the feed kernel once Env.step adopts the action (die_env_step_fused)
+            const double mx = apply_boundary(x + adx, a.boundary);
+            const double my = apply_boundary(y + ady, a.boundary);
+            const int cell = nearest_cell(mx, ax) * W + nearest_cell(my, ay);
+            co_p[i] = cell;
+            if ((alive_word >> (threadIdx.x & 31)) & 1u) atomicMax(win + cell, (int32_t)(first + i));
+        }
     }
 }
 
@@ -303,16 +336,9 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
     for (int k = 0; k < kMoveItems; ++k) {
         const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
         if (i >= M) break;
-        double x = ag[i] + ac[i];
-        double y = ag[M + i] + ac[M + i];
+        const double x = apply_boundary(ag[i] + ac[i], boundary);
+        const double y = apply_boundary(ag[M + i] + ac[M + i], boundary);
         const bool alive = ag[2 * M + i] > 0.0;
-        if (boundary == DIE_BOUNDARY_WRAP) {
-            x = mod1(x);
-            y = mod1(y);
-        } else if (boundary == DIE_BOUNDARY_LIMIT) {          // np.clip(0., 1.)
-            x = fmin(fmax(x, 0.0), 1.0);
-            y = fmin(fmax(y, 0.0), 1.0);
-        }
         ag[i] = x;
         ag[M + i] = y;
         const int cell = nearest_cell(x, ax) * W + nearest_cell(y, ay);
@@ -333,25 +359,32 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
-template <bool SLAB>
+// MOVE: the step adopted a move that the forward kernel evaluated speculatively (cells + claims are
+// in place); this kernel then also commits the positions, pos = boundary(pos + action[dx, dy])
+// (core/env.py:152-172, the same two operations as move_claim_kernel), and takes `alive` from the
+// env's bitmask instead of the float64 channel.
+template <bool SLAB, bool MOVE>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
                   const int32_t* __restrict__ cells,
                   double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
                   int64_t C, int64_t M, int nblk, double w_dep, double w_dist,
+                  const uint32_t* __restrict__ alive_bits, int64_t Mw, int boundary,
                   const SlabGeom sg, const SlabTables st) {
     const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
-    double* ag_alive = agents + (b * 4 + 2) * M + first;       // alive; agent_food is + M
+    double* ag_x = agents + b * 4 * M + first;                 // x; y, alive, agent_food are + M, 2M, 3M
     const double* ac = action + b * 3 * M + first;
     const double* cf = consumed_field + b * C;
     int32_t* win = winner + b * C;
     const int32_t* cl = cells + b * M + first;
+    const uint32_t* bits_p = MOVE ? alive_bits + b * Mw + (first >> 5) : nullptr;
 
     int cell[kFeedItems];
     double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], eaten[kFeedItems];
+    double px[kFeedItems], py[kFeedItems];
     bool alive[kFeedItems], valid[kFeedItems];
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
@@ -362,8 +395,14 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
         eaten[k] = valid[k] ? (SLAB ? __ldg(slab_cell(st.consumed, sg, cell[k])) : cf[cell[k]]) : 0.0;
-        alive[k] = valid[k] && ag_alive[i] > 0.0;
-        stock[k] = valid[k] ? ag_alive[M + i] : 0.0;
+        if (MOVE) {
+            alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
+            px[k] = valid[k] ? ag_x[i] : 0.0;
+            py[k] = valid[k] ? ag_x[M + i] : 0.0;
+        } else {
+            alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
+        }
+        stock[k] = valid[k] ? ag_x[3 * M + i] : 0.0;
         dx[k] = valid[k] ? ac[i] : 0.0;
         dy[k] = valid[k] ? ac[M + i] : 0.0;
         dep[k] = valid[k] ? ac[2 * M + i] : 0.0;
@@ -373,9 +412,14 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         if (valid[k]) {
+            const int i = k * kAgentThreads;
+            if (MOVE) {
+                ag_x[i] = apply_boundary(px[k] + dx[k], boundary);
+                ag_x[M + i] = apply_boundary(py[k] + dy[k], boundary);
+            }
             const double burned = w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
             const double gained = eaten[k] - burned;
-            ag_alive[M + k * kAgentThreads] = stock[k] + gained;
+            ag_x[3 * M + i] = stock[k] + gained;
             gain_sum += gained;
             if (alive[k]) {                        // claim table back to empty for the next step
                 if (SLAB) *slab_cell(st.claim, sg, cell[k]) = -1;
@@ -404,6 +448,18 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
         }
         part_gain[blockIdx.x] = g;
         part_alive[blockIdx.x] = n;
+    }
+}
+
+// alive bitmask of the env: bit (i & 31) of word [b][i >> 5] = (agents[b][2][i] > 0)
+__global__ void __launch_bounds__(256)
+alive_bits_kernel(const double* __restrict__ agents, uint32_t* __restrict__ bits, int64_t M, int64_t Mw, int B) {
+    const int64_t total = (int64_t)B * Mw * 32;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int64_t b = t / (Mw * 32), i = t - b * (Mw * 32);
+        const bool alive = i < M && agents[(b * 4 + 2) * M + i] > 0.0;
+        const uint32_t word = __ballot_sync(0xffffffffu, alive);
+        if ((threadIdx.x & 31) == 0) bits[b * Mw + (i >> 5)] = word;
     }
 }
 

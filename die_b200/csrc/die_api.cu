@@ -35,7 +35,12 @@ struct die_env {
     int64_t M;
     die_dynamics_t dyn;
     int32_t* winner;       // [B][H*W]  claim table, -1 = empty
-    int32_t* cells;        // [B][M]    linear cell of every slot after the move
+    int32_t* cells2[2];    // [B][M] x 2 linear cell of every slot after the move; [cur] is the valid one, the
+    int cur;               //            other receives the cells of a speculative move (die_env_forward_gradient)
+    uint32_t* alive_bits;  // [B][Mw]   (alive > 0) per slot, one bit each (die_env_refresh_alive)
+    int64_t Mw;
+    int alive_valid;
+    int pending_move;      // a speculative move (cells2[1-cur] + claims) waits for die_env_step_fused
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     int publish_grad;
@@ -95,14 +100,18 @@ extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t C = (size_t)H * W;
     if (err == cudaSuccess) err = cudaMalloc(&e->winner, sizeof(int32_t) * C * B);
-    if (err == cudaSuccess) err = cudaMalloc(&e->cells, sizeof(int32_t) * (size_t)M * B);
+    e->Mw = (M + 31) / 32;
+    if (err == cudaSuccess) err = cudaMalloc(&e->cells2[0], sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->cells2[1], sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->alive_bits, sizeof(uint32_t) * (size_t)e->Mw * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->consumed, sizeof(double) * C * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double) * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->alive_dev, sizeof(int64_t) * B);
     if (err == cudaSuccess) err = cudaMemset(e->winner, 0xFF, sizeof(int32_t) * C * B);
-    if (err == cudaSuccess) err = cudaMemset(e->cells, 0, sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMemset(e->cells2[0], 0, sizeof(int32_t) * (size_t)M * B);
+    if (err == cudaSuccess) err = cudaMemset(e->cells2[1], 0, sizeof(int32_t) * (size_t)M * B);
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
         die_env_destroy(e);
@@ -115,7 +124,9 @@ extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
 extern "C" int die_env_destroy(die_env_t* e) {
     if (e == nullptr) return DIE_OK;
     cudaFree(e->winner);
-    cudaFree(e->cells);
+    cudaFree(e->cells2[0]);
+    cudaFree(e->cells2[1]);
+    cudaFree(e->alive_bits);
     cudaFree(e->consumed);
     cudaFree(e->grad);
     cudaFree(e->part_gain);
@@ -139,7 +150,7 @@ extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
     return DIE_OK;
 }
 
-extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells : nullptr; }
+extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells2[e->cur] : nullptr; }
 
 extern "C" int die_env_publish_gradient(die_env_t* e, int32_t on) {
     DIE_REQUIRE(e != nullptr);
@@ -268,9 +279,9 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
 // ------------------------------------------------------------------------------------------
 // Env.step
 // ------------------------------------------------------------------------------------------
-extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
-                            double* agents, const double* action,
-                            double* reward_dev, int64_t* alive_dev, void* stream) {
+static int env_step_impl(die_env_t* e, double* medium_in, double* medium_out,
+                         double* agents, const double* action,
+                         double* reward_dev, int64_t* alive_dev, bool fused, void* stream) {
     DIE_REQUIRE(e != nullptr);
     DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out);
     DIE_REQUIRE(agents != nullptr && action != nullptr);
@@ -278,20 +289,37 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
     cudaStream_t st = (cudaStream_t)stream;
 
     prof_mark(e, 0, st);
-    const int mchunk = chunks_for(e->M, kMoveItems);
-    move_claim_kernel<false><<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, e->winner, e->cells, make_axis(e->H), make_axis(e->W), e->M, mchunk, e->dyn.boundary,
-        SlabGeom(), SlabTables());
-    DIE_CUDA(cudaGetLastError());
+    if (fused) {
+        // the forward kernel already resolved cells and claims for exactly this action
+        if (!e->pending_move) return fail(DIE_E_INVALID, "die_env_step_fused: no speculative move is pending%s%s");
+        e->cur ^= 1;
+        e->pending_move = 0;
+    } else {
+        if (e->pending_move) {          // abandoned speculation: its claims must not leak into this step
+            if (int rc = die_env_discard_move(e, stream)) return rc;
+        }
+        const int mchunk = chunks_for(e->M, kMoveItems);
+        move_claim_kernel<false><<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
+            agents, action, e->winner, e->cells2[e->cur], make_axis(e->H), make_axis(e->W), e->M, mchunk,
+            e->dyn.boundary, SlabGeom(), SlabTables());
+        DIE_CUDA(cudaGetLastError());
+    }
     prof_mark(e, 1, st);
 
     DIE_CUDA(launch_field_any(e, medium_in, medium_out, action, st));
     prof_mark(e, 2, st);
 
-    agent_feed_kernel<false><<<(unsigned)((int64_t)e->nblk * e->B), kAgentThreads, 0, st>>>(
-        agents, action, e->consumed, e->winner, e->cells, e->part_gain, e->part_alive,
-        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-        SlabGeom(), SlabTables());
+    const unsigned fgrid = (unsigned)((int64_t)e->nblk * e->B);
+    if (fused)
+        agent_feed_kernel<false, true><<<fgrid, kAgentThreads, 0, st>>>(
+            agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
+            (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+            e->alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
+    else
+        agent_feed_kernel<false, false><<<fgrid, kAgentThreads, 0, st>>>(
+            agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
+            (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+            nullptr, 0, e->dyn.boundary, SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 3, st);
 
@@ -301,6 +329,38 @@ extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
     return DIE_OK;
 }
+
+extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
+                            double* agents, const double* action,
+                            double* reward_dev, int64_t* alive_dev, void* stream) {
+    return env_step_impl(e, medium_in, medium_out, agents, action, reward_dev, alive_dev, false, stream);
+}
+
+extern "C" int die_env_step_fused(die_env_t* e, double* medium_in, double* medium_out,
+                                  double* agents, const double* action,
+                                  double* reward_dev, int64_t* alive_dev, void* stream) {
+    return env_step_impl(e, medium_in, medium_out, agents, action, reward_dev, alive_dev, true, stream);
+}
+
+extern "C" int die_env_discard_move(die_env_t* e, void* stream) {
+    DIE_REQUIRE(e != nullptr);
+    if (!e->pending_move) return DIE_OK;
+    DIE_CUDA(cudaMemsetAsync(e->winner, 0xFF, sizeof(int32_t) * (size_t)e->H * e->W * e->B, (cudaStream_t)stream));
+    e->pending_move = 0;
+    return DIE_OK;
+}
+
+extern "C" int die_env_refresh_alive(die_env_t* e, const double* agents, void* stream) {
+    DIE_REQUIRE(e != nullptr && agents != nullptr);
+    const int64_t total = (int64_t)e->B * e->Mw * 32;
+    alive_bits_kernel<<<grid_for(total, 256, e->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        agents, e->alive_bits, e->M, e->Mw, e->B);
+    DIE_CUDA(cudaGetLastError());
+    e->alive_valid = 1;
+    return DIE_OK;
+}
+
+extern "C" int die_env_pending_move(const die_env_t* e) { return e ? e->pending_move : 0; }
 
 extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
                                  double* agents, const double* action_host,
@@ -354,14 +414,39 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
     return DIE_OK;
 }
 
-extern "C" int die_gradient_forward(const die_gradient_params_t* p,
-                                    int32_t H, int32_t W, int64_t M, int32_t B,
-                                    const double* agents, const double* medium,
-                                    double* theta, double* prev_grad, double* action,
-                                    const uint8_t* coin, const double* noise,
-                                    int32_t* sense_cells,
-                                    const double* grad_hint, const int32_t* cells_hint,
-                                    uint64_t seed, uint64_t step, void* stream) {
+static int g_turn_quick = 1;       // 0: every slot runs die_turn_exact (diagnosis / A-B tests; same results)
+static int g_fwd_min_blocks = 4;   // register cap of the forward kernel (3 / 4 / 5 resident CTAs per SM)
+
+extern "C" int die_set_turn_quick(int32_t on) {
+    g_turn_quick = on ? 1 : 0;
+    return DIE_OK;
+}
+
+extern "C" int die_set_tuning(const char* key, int32_t value) {
+    DIE_REQUIRE(key != nullptr);
+    if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;
+    else if (strcmp(key, "fwd_min_blocks") == 0) { DIE_REQUIRE(value >= 3 && value <= 5); g_fwd_min_blocks = value; }
+    else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
+    else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
+    return DIE_OK;
+}
+
+static die_turn_plan_t plan_for(const die_gradient_params_t* p) {
+    die_turn_plan_t plan;
+    memset(&plan, 0, sizeof(plan));
+    if (g_turn_quick && p->discrete_turn)
+        plan = die_turn_plan(p->normalized_grad, p->use_grad_clip, p->grad_clip,
+                             p->turn_radians * p->turn_tolerance, p->sense_radians);
+    return plan;
+}
+
+static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradient_params_t* p,
+                                 int32_t H, int32_t W, int64_t M, int32_t B,
+                                 const double* agents, const double* medium,
+                                 double* theta, double* prev_grad, double* action,
+                                 const uint8_t* coin, const double* noise, int32_t* sense_cells,
+                                 const double* grad_hint, const int32_t* cells_hint,
+                                 uint64_t seed, uint64_t step, void* stream) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -371,6 +456,7 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     GradientArgs a;
     memset(&a, 0, sizeof(a));
     a.p = *p;
+    a.plan = plan_for(p);
     DIE_REQUIRE(M <= 0x7fffffffLL);
     a.H = H; a.W = W; a.M = M; a.nchunk = chunks_for(M, kFwdItems);
     a.ax = make_axis(H);
@@ -380,12 +466,59 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
     a.grad = (const double2*)grad_hint; a.cells = cells_hint;
     a.seed = seed; a.step = step;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
-    if (p->discrete_turn)
-        gradient_forward_kernel<true, false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
-    else
-        gradient_forward_kernel<false, false><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (speculate) {
+        a.winner = env->winner;
+        a.cells_out = env->cells2[1 - env->cur];
+        a.alive_bits = env->alive_bits;
+        a.Mw = env->Mw;
+        a.boundary = env->dyn.boundary;
+    }
+    void (*kern)(const GradientArgs) = nullptr;
+#define DIE_PICK_FWD(MINB)                                                                               \
+    kern = speculate ? (p->discrete_turn ? gradient_forward_kernel<true, false, true, MINB>              \
+                                         : gradient_forward_kernel<false, false, true, MINB>)            \
+                     : (p->discrete_turn ? gradient_forward_kernel<true, false, false, MINB>             \
+                                         : gradient_forward_kernel<false, false, false, MINB>)
+    if (g_fwd_min_blocks == 3) { DIE_PICK_FWD(3); }
+    else if (g_fwd_min_blocks == 5) { DIE_PICK_FWD(5); }
+    else { DIE_PICK_FWD(4); }
+#undef DIE_PICK_FWD
+    kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
+    if (speculate) env->pending_move = 1;
     return DIE_OK;
+}
+
+extern "C" int die_gradient_forward(const die_gradient_params_t* p,
+                                    int32_t H, int32_t W, int64_t M, int32_t B,
+                                    const double* agents, const double* medium,
+                                    double* theta, double* prev_grad, double* action,
+                                    const uint8_t* coin, const double* noise,
+                                    int32_t* sense_cells,
+                                    const double* grad_hint, const int32_t* cells_hint,
+                                    uint64_t seed, uint64_t step, void* stream) {
+    return gradient_forward_impl(nullptr, false, p, H, W, M, B, agents, medium, theta, prev_grad, action,
+                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
+}
+
+extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_t* p,
+                                        const double* agents, const double* medium,
+                                        double* theta, double* prev_grad, double* action,
+                                        const uint8_t* coin, const double* noise, int32_t* sense_cells,
+                                        int32_t flags, uint64_t seed, uint64_t step, void* stream) {
+    DIE_REQUIRE(e != nullptr);
+    const bool speculate = (flags & DIE_FWD_SPECULATE_MOVE) != 0;
+    if (speculate) {
+        if (!e->alive_valid) return fail(DIE_E_INVALID, "die_env_forward_gradient: call die_env_refresh_alive first%s%s");
+        if (e->pending_move) {          // a previous speculation was never adopted: drop its claims
+            if (int rc = die_env_discard_move(e, stream)) return rc;
+        }
+    }
+    const double* grad_hint = (flags & DIE_FWD_USE_GRADIENT) ? die_env_gradient(e) : nullptr;
+    const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;
+    return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
+                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,6 +655,7 @@ extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, i
     a.H = e->g.H; a.W = e->g.W; a.M = e->Ml; a.nchunk = chunks_for(e->Ml, kFwdItems);
     a.ax = make_axis(e->g.H);
     a.ay = make_axis(e->g.W);
+    a.plan = plan_for(p);
     a.agents = agents; a.theta = theta; a.action = action; a.coin = coin;
     a.seed = seed; a.step = step;
     a.sg = e->g;
@@ -530,9 +664,9 @@ extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, i
     if (hints & 2) a.cells = e->cells;           // bit 1: the cell cache of the last die_slab_move_claim
     const unsigned grid = (unsigned)a.nchunk;
     if (p->discrete_turn)
-        gradient_forward_kernel<true, true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+        gradient_forward_kernel<true, true, false, 4><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
     else
-        gradient_forward_kernel<false, true><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+        gradient_forward_kernel<false, true, false, 4><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -602,9 +736,10 @@ extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action
     DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr && stats != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     if (e->Ml > 0) {
-        agent_feed_kernel<true><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
+        agent_feed_kernel<true, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
             agents, action, nullptr, nullptr, e->cells, e->part_gain, e->part_alive,
-            (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist, e->g, e->tbl[0]);
+            (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+            nullptr, 0, e->dyn.boundary, e->g, e->tbl[0]);
         DIE_CUDA(cudaGetLastError());
         finalize_stats_kernel<<<1, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
     } else {

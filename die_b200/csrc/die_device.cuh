@@ -10,11 +10,12 @@
 #include <cuda_runtime.h>
 
 #include "die_math.h"
+#include "die_turn.h"
 
 namespace die {
 
-constexpr double kPi    = 3.141592653589793;    // np.pi
-constexpr double kTwoPi = 6.283185307179586;    // 2 * np.pi (exact doubling)
+constexpr double kPi    = DIE_PI;        // np.pi
+constexpr double kTwoPi = DIE_TWO_PI;    // 2 * np.pi (exact doubling)
 
 // ---- nearest grid cell ------------------------------------------------------------------
 // xarray .sel(method='nearest') -> pandas.Index.get_indexer(method='nearest') on
@@ -59,59 +60,21 @@ __device__ __forceinline__ int nearest_cell(double c, const Axis& a) {
     return min(max(r, 0), a.n - 1);
 }
 
-// ---- numpy float remainder ----------------------------------------------------------------
-// np.remainder(a, b) = fmod(a, b), moved into the sign of b; an exact zero gets the sign of b.
-// fmod is exact; for |a| < 2|b| it is a or |a| - |b| (Sterbenz), which is all the hot path
-// ever sees, so the generic fmod() sits behind an unlikely branch.
-__device__ __forceinline__ double np_remainder(double a, double b) {
-    const double fa = fabs(a), fb = fabs(b);
-    double m;
-    if (fa < 2.0 * fb) m = (fa < fb) ? a : copysign(__dsub_rn(fa, fb), a);
-    else m = fmod(a, b);
-    if (m == 0.0) return copysign(0.0, b);
-    return ((b < 0.0) != (m < 0.0)) ? __dadd_rn(m, b) : m;
-}
+// ---- numpy float remainder, renormalize_radians, np.angle, nan_to_num ------------------------
+// The turn-rule arithmetic lives in die_turn.h (host + device, so its guard-band logic is testable on
+// the CPU); these are the device-side names the kernels use.
+__device__ __forceinline__ double np_remainder(double a, double b) { return die_np_remainder(a, b); }
 
 // coords % 1.  (core/env.py:155) -- returns exactly 1.0 for tiny negatives.
-__device__ __forceinline__ double mod1(double a) { return np_remainder(a, 1.0); }
+__device__ __forceinline__ double mod1(double a) { return die_np_remainder(a, 1.0); }
 
 // renormalize_radians (core/utils.py:177-179): (r - pi) % (-2 pi) + pi, in (-pi, pi].
-// np.remainder(a, -2pi) spelled out for |a| < 4 pi (all the hot path ever sees): fmod(a, -2pi) is
-// a, a - 2pi or a + 2pi (exact), and a positive remainder is moved into the divisor's sign by one
-// ROUNDED add of -2pi.  The sign of a zero remainder is irrelevant here (+-0 + pi = pi).
-__device__ __forceinline__ double renormalize_radians(double r) {
-    const double a = __dsub_rn(r, kPi);
-    double m;
-    if (fabs(a) < 2.0 * kTwoPi) {
-        double f = a;
-        if (a >= kTwoPi) f = __dsub_rn(a, kTwoPi);
-        else if (a <= -kTwoPi) f = __dadd_rn(a, kTwoPi);
-        m = (f > 0.0) ? __dsub_rn(f, kTwoPi) : f;
-    } else {
-        m = np_remainder(a, -kTwoPi);
-    }
-    return __dadd_rn(m, kPi);
-}
+__device__ __forceinline__ double renormalize_radians(double r) { return die_renormalize_radians(r); }
 
-// np.angle(x + np.multiply(1j, y))  (core/utils.py:158-168).  The complex construction
-// yields re = x + (0*y - 0), im = 0 + y, which is what makes (-0., -0.) -> +pi and every
-// other all-zero pair -> 0.
-// The arctangent is die_math.h's bit-reproducible one: FAST = die_atan2_fast (<= 1.8 ulp) for
+// np.angle(x + np.multiply(1j, y))  (core/utils.py:158-168); FAST = die_atan2_fast (<= 1.8 ulp) for
 // angles that are only compared against thresholds, else the compensated die_atan2.
 template <bool FAST>
-__device__ __forceinline__ double angle_xy(double x, double y) {
-    const double re = __dadd_rn(x, __dsub_rn(__dmul_rn(0.0, y), 0.0));
-    const double im = __dadd_rn(0.0, y);
-    return FAST ? die_atan2_fast(im, re) : die_atan2(im, re);
-}
-
-// np.nan_to_num(a / n)  (core/agent/gradient.py:62)
-__device__ __forceinline__ double div_nan_to_num(double a, double n) {
-    const double q = __ddiv_rn(a, n);
-    if (isnan(q)) return 0.0;
-    if (isinf(q)) return copysign(DBL_MAX, q);
-    return q;
-}
+__device__ __forceinline__ double angle_xy(double x, double y) { return die_angle_xy(x, y, FAST ? 1 : 0); }
 
 // ---- Philox4x32-10 counter RNG (perf mode; validation mode injects the host's draws) -------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {

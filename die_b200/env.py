@@ -193,6 +193,10 @@ class Env:
             self._handle = handle
             self._publish_grad = False
             self._hint_state = None         # (medium ptr, medium version, agents version, grad published)
+            self._speculation = None        # (action ptr, action version, agents version) of a pending fused move
+            self._alive_version = None      # agents._version the library's alive bitmask was built for
+            self.last_step_fused = False
+            _hints.publish(self, first)
 
     def __del__(self):
         try:
@@ -278,12 +282,18 @@ class Env:
         as device tensors, everything enqueued on the current stream."""
         action = self._check_action(action)
         nxt = 1 - self._cur
+        # a gradient agent may have evaluated this very action's move + claims already (see _forward_flags):
+        # adopt them iff the action tensor and the agents are provably untouched since
+        spec, self._speculation = self._speculation, None
+        fused = (spec is not None and spec == (action.data_ptr(), action._version, self._agents._version))
+        step_fn = self._lib.die_env_step_fused if fused else self._lib.die_env_step     # the latter discards
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(self._lib.die_env_step(
+            _lib.check(step_fn(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
                 self._agents.data_ptr(), action.data_ptr(),
                 self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), stream))
+        self.last_step_fused = fused
         self._cur = nxt
         self._after_step()
         return self._get_current_obs, self._reward_dev, self._alive_dev
@@ -312,6 +322,25 @@ class Env:
             if want_gradient and st[3]:
                 grad_ptr = self._lib.die_env_gradient(self._handle) or None
         return grad_ptr, cells_ptr
+
+    def _forward_flags(self, agents, medium, want_gradient: bool, speculate: bool) -> int:
+        """Flags for ``die_env_forward_gradient`` (include/die_b200.h) given the observation an agent
+        received: which of this env's caches are provably valid for it, and whether the agent may
+        evaluate the move of its action speculatively (``obs[0]`` must be this env's own agents tensor;
+        the alive bitmask is rebuilt here whenever the agents tensor was edited)."""
+        grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
+        flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
+        if speculate and agents.data_ptr() == self._agents.data_ptr() and agents.numel() == self._agents.numel():
+            if self._alive_version != self._agents._version:
+                with torch.cuda.device(self.device):
+                    _lib.check(self._lib.die_env_refresh_alive(self._handle, self._agents.data_ptr(),
+                                                               torch.cuda.current_stream().cuda_stream))
+                self._alive_version = self._agents._version
+            flags |= _lib.FWD_SPECULATE_MOVE
+        return flags
+
+    def _note_speculation(self, action: torch.Tensor) -> None:
+        self._speculation = (action.data_ptr(), action._version, self._agents._version)
 
     def step(self, action: ActType):
         """core/env.py:101-131 -> (obs, reward, terminated, truncated, info)."""

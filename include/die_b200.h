@@ -156,6 +156,47 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          const double* grad_hint_dev, const int32_t* cells_hint_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
+/* The same forward pass bound to the environment that produced the observation (what
+ * die_b200.PhysarumAgent.forward calls when `obs` is provably that Env's own, die_b200/_hints.py).
+ * flags:
+ *   DIE_FWD_USE_GRADIENT    the gradient published by the env's last step is valid for `medium_dev`
+ *   DIE_FWD_USE_CELLS       the env's cell cache is valid for `agents_dev`
+ *   DIE_FWD_SPECULATE_MOVE  additionally evaluate Env._agent_move + cell resolution + the claim
+ *                           (core/env.py:152-172, :211) for the action being written: post-move cells go
+ *                           to the env's second cell buffer, claims into its claim table; positions are NOT
+ *                           touched.  If the very next die_env_step_fused receives this action unmodified
+ *                           (the caller's responsibility: die_b200.Env checks the tensor identity and torch's
+ *                           version counters of action and agents), the step skips its move+claim kernel and
+ *                           the feed kernel commits the positions -- same results bit for bit, one launch
+ *                           and ~32 B per slot less.  Any other continuation (die_env_step, another
+ *                           forward) first calls die_env_discard_move, which empties the claim table.
+ * Needs die_env_refresh_alive() after every change of the `alive` channel (the speculative claim and
+ * the fused feed read alive-ness from a bitmask). */
+#define DIE_FWD_USE_GRADIENT    1
+#define DIE_FWD_USE_CELLS       2
+#define DIE_FWD_SPECULATE_MOVE  4
+int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
+                             const double* agents_dev, const double* medium_dev,
+                             double* theta_dev, double* prev_grad_dev, double* action_dev,
+                             const uint8_t* coin_dev, const double* noise_dev, int32_t* sense_cells_dev,
+                             int32_t flags, uint64_t seed, uint64_t step, void* stream);
+/* Env.step (as die_env_step) adopting the pending speculative move; DIE_E_INVALID if none is pending. */
+int die_env_step_fused(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+                       double* agents_dev, const double* action_dev,
+                       double* reward_dev, int64_t* alive_dev, void* stream);
+int die_env_discard_move(die_env_t* env, void* stream);
+int die_env_pending_move(const die_env_t* env);          /* 1 while a speculative move waits for its step */
+int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream);
+
+/* PhysarumAgent._choose_turn has two implementations (die_b200/csrc/die_turn.h): the reference's own
+ * arithmetic, and a guard-banded float32 shortcut that defers to it whenever a threshold is close.
+ * die_set_turn_quick(0) forces the former for every slot (A-B tests; results are identical). */
+int die_set_turn_quick(int32_t on);
+
+/* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
+ * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "field_impl" 0/1. */
+int die_set_tuning(const char* key, int32_t value);
+
 /* ---------------------------------------------------------------------------------------------
  * One field split into row slabs over G GPUs (BASELINE configs[4]; SURVEY section 8e, mode 2).
  * Rank r owns rows [r*H/G, (r+1)*H/G) of every per-cell array and the agent slots given by two
