@@ -169,7 +169,7 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
     M = env.max_agents
     agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
     agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
-    agent.fuse_move = not ARGS.no_fuse
+    agent.fuse_move = bool(ARGS.fuse)
     return env, agent, alive
 
 
@@ -523,7 +523,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=100, help="steps per CPU env in the cpu_baseline leg")
     ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-fuse", action="store_true", help="A-B: agent.forward does not evaluate the move speculatively")
+    ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")
     ap.add_argument("--no-cpu", action="store_true")

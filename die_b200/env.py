@@ -392,6 +392,8 @@ class Env:
         hb['flip'] ^= 1
         med_t = hb['medium'][hb['flip']]
         nxt = 1 - self._cur
+        self._speculation = None          # die_env_step_host runs the plain step (and discards a pending move)
+        self.last_step_fused = False
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(self._lib.die_env_step_host(

@@ -29,6 +29,7 @@ def _agents(m, seed, **kw):
     for _ in range(2):
         ag = D.PhysarumAgent(max_agents=m, **kw)
         ag.set_state(theta=theta0)
+        ag.fuse_move = True
         out.append(ag)
     return out
 
@@ -76,7 +77,7 @@ def test_fused_move_batched_envs():
     ag_f, ag_p = D.PhysarumAgent(max_agents=m, **PHYS), D.PhysarumAgent(max_agents=m, **PHYS)
     ag_f.set_state(theta=th)
     ag_p.set_state(theta=th)
-    ag_p.fuse_move = False
+    ag_f.fuse_move, ag_p.fuse_move = True, False
     rng = np.random.default_rng(6)
     of, op = env_f._get_current_obs, env_p._get_current_obs
     for it in range(25):
@@ -183,6 +184,7 @@ def test_tuning_switches_do_not_change_results(key, values):
             m = env.max_agents
             ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
             ag.set_state(theta=lattice_theta(m, 30, 13)[0])
+            ag.fuse_move = (key == "fwd_min_blocks")          # covers the MOVE instantiations of every register cap
             obs = env._get_current_obs
             total = 0.0
             for _ in range(60):
