@@ -415,6 +415,8 @@ def run_die_b200(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         cpu = time_oracle(args.cpu_field, args.cpu_steps, warmup=2, procs=args.cpu_procs)
 
+    # forward, move_claim, field_step, agent_feed, finalize_stats; the fused path has no move_claim
+    launches = 5 - (1 if meas["fused"] else 0)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
@@ -428,7 +430,7 @@ def run_die_b200(args):
             "agent_steps_per_s": M * B_total / (ms_per_step * 1e-3),
             "alive_agent_steps_per_s": alive_local * n_gpus / (ms_per_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "also": also,
-            "gpu_launches": args.steps * (4 if meas["fused"] else 5), "launches_per_step": 4 if meas["fused"] else 5,
+            "gpu_launches": args.steps * launches, "launches_per_step": launches,
             "fused_move": meas["fused"], "tuning": ARGS.tune, "clocks": meas["clocks"],
             "setup_s": round(setup_s, 1),
         }

@@ -8,6 +8,7 @@ from ._build import LIB_PATH
 DIE_MAX_RADIUS = 8
 BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
 FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE = 1, 2, 4
+STEP_ADOPT_MOVE, STEP_ALIVE_BITS = 1, 2
 
 
 class DieDynamics(C.Structure):
@@ -80,7 +81,7 @@ SIGNATURES = {
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "die_env_forward_gradient": (C.c_int, [_P, C.POINTER(DieGradientParams), _P, _P, _P, _P, _P, _P, _P, _P,
                                            C.c_int32, C.c_uint64, C.c_uint64, _P]),
-    "die_env_step_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_env_step_flags": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "die_env_discard_move": (C.c_int, [_P, _P]),
     "die_env_pending_move": (C.c_int, [_P]),
     "die_env_refresh_alive": (C.c_int, [_P, _P, _P]),

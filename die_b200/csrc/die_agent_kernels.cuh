@@ -301,7 +301,7 @@ gradient_forward_kernel(const GradientArgs a) {
         if (MOVE) {
             // Env._agent_move (core/env.py:152-172) of THIS action + cell resolution + claim: what
             // move_claim_kernel would compute from (agents, action); the positions themselves are
-            // committed by the feed kernel once Env.step adopts the action (die_env_step_fused)
+            // committed by the feed kernel once Env.step adopts the action (die_env_step_flags, DIE_STEP_ADOPT_MOVE)
             const double mx = apply_boundary(x + adx, a.boundary);
             const double my = apply_boundary(y + ady, a.boundary);
             const int cell = nearest_cell(mx, ax) * W + nearest_cell(my, ay);
@@ -319,11 +319,12 @@ gradient_forward_kernel(const GradientArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kMoveItems = 4;
 
-template <bool SLAB>
+template <bool SLAB, bool BITS>
 __global__ void __launch_bounds__(kAgentThreads)
 move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   int32_t* __restrict__ winner, int32_t* __restrict__ cells,
                   const Axis ax, const Axis ay, int64_t M, int nchunk, int boundary,
+                  const uint32_t* __restrict__ alive_bits, int64_t Mw,
                   const SlabGeom sg, const SlabTables st) {
     const int W = ay.n;
     const int64_t C = (int64_t)ax.n * ay.n;
@@ -332,13 +333,15 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
     const double* ac = action + ch.b * 3 * M;
     int32_t* win = winner + ch.b * C;
     int32_t* cl = cells + ch.b * M;
+    // BITS: alive-ness from the env's bitmask (1 bit instead of 8 bytes per slot)
+    const uint32_t* bits_p = BITS ? alive_bits + ch.b * Mw : nullptr;
 #pragma unroll
     for (int k = 0; k < kMoveItems; ++k) {
         const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
         if (i >= M) break;
         const double x = apply_boundary(ag[i] + ac[i], boundary);
         const double y = apply_boundary(ag[M + i] + ac[M + i], boundary);
-        const bool alive = ag[2 * M + i] > 0.0;
+        const bool alive = BITS ? ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u) != 0 : ag[2 * M + i] > 0.0;
         ag[i] = x;
         ag[M + i] = y;
         const int cell = nearest_cell(x, ax) * W + nearest_cell(y, ay);
@@ -361,9 +364,9 @@ constexpr int kFeedItems = 4;      // slots per thread
 
 // MOVE: the step adopted a move that the forward kernel evaluated speculatively (cells + claims are
 // in place); this kernel then also commits the positions, pos = boundary(pos + action[dx, dy])
-// (core/env.py:152-172, the same two operations as move_claim_kernel), and takes `alive` from the
-// env's bitmask instead of the float64 channel.
-template <bool SLAB, bool MOVE>
+// (core/env.py:152-172, the same two operations as move_claim_kernel).
+// BITS: alive-ness comes from the env's bitmask instead of the float64 channel (MOVE implies BITS).
+template <bool SLAB, bool MOVE, bool BITS>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
@@ -380,7 +383,7 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
     const double* cf = consumed_field + b * C;
     int32_t* win = winner + b * C;
     const int32_t* cl = cells + b * M + first;
-    const uint32_t* bits_p = MOVE ? alive_bits + b * Mw + (first >> 5) : nullptr;
+    const uint32_t* bits_p = BITS ? alive_bits + b * Mw + (first >> 5) : nullptr;
 
     int cell[kFeedItems];
     double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], eaten[kFeedItems];
@@ -395,12 +398,11 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
         eaten[k] = valid[k] ? (SLAB ? __ldg(slab_cell(st.consumed, sg, cell[k])) : cf[cell[k]]) : 0.0;
+        if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
+        else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {
-            alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
             px[k] = valid[k] ? ag_x[i] : 0.0;
             py[k] = valid[k] ? ag_x[M + i] : 0.0;
-        } else {
-            alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         }
         stock[k] = valid[k] ? ag_x[3 * M + i] : 0.0;
         dx[k] = valid[k] ? ac[i] : 0.0;
@@ -463,18 +465,34 @@ alive_bits_kernel(const double* __restrict__ agents, uint32_t* __restrict__ bits
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kFinalThreads = 1024;
+
+// Sum of an environment's block partials in a fixed order (thread t takes partials t, t + 1024, ... in four
+// interleaved accumulators, then warp shuffles, then the 32 warp sums in index order): run-to-run deterministic.
+__global__ void __launch_bounds__(kFinalThreads)
 finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __restrict__ part_alive,
                       int nblk, double* __restrict__ reward, int64_t* __restrict__ alive) {
     const int b = blockIdx.x;
-    double g = 0.0;
+    const double* pgn = part_gain + (int64_t)b * nblk;
+    const int32_t* pal = part_alive + (int64_t)b * nblk;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
     long long n = 0;
-    for (int k = threadIdx.x; k < nblk; k += 256) {
-        g += part_gain[(int64_t)b * nblk + k];
-        n += part_alive[(int64_t)b * nblk + k];
+    int k = threadIdx.x;
+    for (; k + 3 * kFinalThreads < nblk; k += 4 * kFinalThreads) {
+        const double a0 = pgn[k], a1 = pgn[k + kFinalThreads], a2 = pgn[k + 2 * kFinalThreads], a3 = pgn[k + 3 * kFinalThreads];
+        n += (long long)pal[k] + pal[k + kFinalThreads] + pal[k + 2 * kFinalThreads] + pal[k + 3 * kFinalThreads];
+        g0 += a0;
+        g1 += a1;
+        g2 += a2;
+        g3 += a3;
     }
-    __shared__ double s_g[8];
-    __shared__ long long s_n[8];
+    for (; k < nblk; k += kFinalThreads) {
+        g0 += pgn[k];
+        n += pal[k];
+    }
+    double g = (g0 + g1) + (g2 + g3);
+    __shared__ double s_g[kFinalThreads / 32];
+    __shared__ long long s_n[kFinalThreads / 32];
     g = warp_sum(g);
     n = warp_sum(n);
     if ((threadIdx.x & 31) == 0) {
@@ -485,9 +503,9 @@ finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __res
     if (threadIdx.x == 0) {
         double gg = 0.0;
         long long nn = 0;
-        for (int k = 0; k < 8; ++k) {
-            gg += s_g[k];
-            nn += s_n[k];
+        for (int w = 0; w < kFinalThreads / 32; ++w) {
+            gg += s_g[w];
+            nn += s_n[w];
         }
         reward[b] = gg;
         alive[b] = nn;

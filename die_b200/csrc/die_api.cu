@@ -40,7 +40,7 @@ struct die_env {
     uint32_t* alive_bits;  // [B][Mw]   (alive > 0) per slot, one bit each (die_env_refresh_alive)
     int64_t Mw;
     int alive_valid;
-    int pending_move;      // a speculative move (cells2[1-cur] + claims) waits for die_env_step_fused
+    int pending_move;      // a speculative move (cells2[1-cur] + claims) waits for a step with DIE_STEP_ADOPT_MOVE
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     int publish_grad;
@@ -225,6 +225,7 @@ static cudaError_t launch_march(const FieldArgs& a, int B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static int g_field_prefetch = 1;   // tile kernel: prefetch the output tile's food lines to L2 while staging
 static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms at 4096^2), 1 = register-tiled march (0.29 ms)
 
 template <int R>
@@ -257,6 +258,7 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
     a.rate_feed = e->dyn.rate_feed;
     a.keep = 1.0 - e->dyn.rate_decay_chem;
     a.food_infinite = e->dyn.food_infinite;
+    a.prefetch_food = g_field_prefetch;
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
     switch (e->dyn.blur_radius) {
         case 0: {
@@ -279,19 +281,26 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
 // ------------------------------------------------------------------------------------------
 // Env.step
 // ------------------------------------------------------------------------------------------
-static int env_step_impl(die_env_t* e, double* medium_in, double* medium_out,
-                         double* agents, const double* action,
-                         double* reward_dev, int64_t* alive_dev, bool fused, void* stream) {
+static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitmask (when valid) instead of the float64 channel
+
+extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* medium_out,
+                                  double* agents, const double* action,
+                                  double* reward_dev, int64_t* alive_dev, int32_t flags, void* stream) {
     DIE_REQUIRE(e != nullptr);
     DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out);
     DIE_REQUIRE(agents != nullptr && action != nullptr);
     DIE_REQUIRE(reward_dev != nullptr && alive_dev != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool fused = (flags & DIE_STEP_ADOPT_MOVE) != 0;
+    const bool bits = (flags & DIE_STEP_ALIVE_BITS) != 0;
+    if ((fused || bits) && !e->alive_valid)
+        return fail(DIE_E_INVALID, "die_env_step_flags: call die_env_refresh_alive first%s%s");
+    const uint32_t* alive_bits = (fused || bits) ? e->alive_bits : nullptr;
 
     prof_mark(e, 0, st);
     if (fused) {
         // the forward kernel already resolved cells and claims for exactly this action
-        if (!e->pending_move) return fail(DIE_E_INVALID, "die_env_step_fused: no speculative move is pending%s%s");
+        if (!e->pending_move) return fail(DIE_E_INVALID, "die_env_step_flags: no speculative move is pending%s%s");
         e->cur ^= 1;
         e->pending_move = 0;
     } else {
@@ -299,9 +308,10 @@ static int env_step_impl(die_env_t* e, double* medium_in, double* medium_out,
             if (int rc = die_env_discard_move(e, stream)) return rc;
         }
         const int mchunk = chunks_for(e->M, kMoveItems);
-        move_claim_kernel<false><<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
+        auto move = (alive_bits != nullptr) ? move_claim_kernel<false, true> : move_claim_kernel<false, false>;
+        move<<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
             agents, action, e->winner, e->cells2[e->cur], make_axis(e->H), make_axis(e->W), e->M, mchunk,
-            e->dyn.boundary, SlabGeom(), SlabTables());
+            e->dyn.boundary, alive_bits, e->Mw, SlabGeom(), SlabTables());
         DIE_CUDA(cudaGetLastError());
     }
     prof_mark(e, 1, st);
@@ -310,20 +320,17 @@ static int env_step_impl(die_env_t* e, double* medium_in, double* medium_out,
     prof_mark(e, 2, st);
 
     const unsigned fgrid = (unsigned)((int64_t)e->nblk * e->B);
-    if (fused)
-        agent_feed_kernel<false, true><<<fgrid, kAgentThreads, 0, st>>>(
-            agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
-            (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-            e->alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
-    else
-        agent_feed_kernel<false, false><<<fgrid, kAgentThreads, 0, st>>>(
-            agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
-            (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-            nullptr, 0, e->dyn.boundary, SlabGeom(), SlabTables());
+    const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
+    auto feed = fused ? agent_feed_kernel<false, true, true>
+                      : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
+    feed<<<fgrid, kAgentThreads, 0, st>>>(
+        agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
+        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+        alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 3, st);
 
-    finalize_stats_kernel<<<e->B, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, reward_dev, alive_dev);
+    finalize_stats_kernel<<<e->B, kFinalThreads, 0, st>>>(e->part_gain, e->part_alive, e->nblk, reward_dev, alive_dev);
     DIE_CUDA(cudaGetLastError());
     prof_mark(e, 4, st);
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
@@ -333,13 +340,7 @@ static int env_step_impl(die_env_t* e, double* medium_in, double* medium_out,
 extern "C" int die_env_step(die_env_t* e, double* medium_in, double* medium_out,
                             double* agents, const double* action,
                             double* reward_dev, int64_t* alive_dev, void* stream) {
-    return env_step_impl(e, medium_in, medium_out, agents, action, reward_dev, alive_dev, false, stream);
-}
-
-extern "C" int die_env_step_fused(die_env_t* e, double* medium_in, double* medium_out,
-                                  double* agents, const double* action,
-                                  double* reward_dev, int64_t* alive_dev, void* stream) {
-    return env_step_impl(e, medium_in, medium_out, agents, action, reward_dev, alive_dev, true, stream);
+    return die_env_step_flags(e, medium_in, medium_out, agents, action, reward_dev, alive_dev, 0, stream);
 }
 
 extern "C" int die_env_discard_move(die_env_t* e, void* stream) {
@@ -426,6 +427,8 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     DIE_REQUIRE(key != nullptr);
     if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;
     else if (strcmp(key, "fwd_min_blocks") == 0) { DIE_REQUIRE(value >= 3 && value <= 5); g_fwd_min_blocks = value; }
+    else if (strcmp(key, "feed_bits") == 0) g_feed_bits = value ? 1 : 0;
+    else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;
@@ -675,9 +678,9 @@ extern "C" int die_slab_move_claim(die_slab_t* e, double* agents, const double* 
     DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr);
     if (e->Ml == 0) return DIE_OK;
     const int mchunk = chunks_for(e->Ml, kMoveItems);
-    move_claim_kernel<true><<<(unsigned)mchunk, kAgentThreads, 0, (cudaStream_t)stream>>>(
+    move_claim_kernel<true, false><<<(unsigned)mchunk, kAgentThreads, 0, (cudaStream_t)stream>>>(
         agents, action, nullptr, e->cells, make_axis(e->g.H), make_axis(e->g.W), e->Ml, mchunk,
-        e->dyn.boundary, e->g, e->tbl[0]);
+        e->dyn.boundary, nullptr, 0, e->g, e->tbl[0]);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -736,12 +739,12 @@ extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action
     DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr && stats != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     if (e->Ml > 0) {
-        agent_feed_kernel<true, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
+        agent_feed_kernel<true, false, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
             agents, action, nullptr, nullptr, e->cells, e->part_gain, e->part_alive,
             (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
             nullptr, 0, e->dyn.boundary, e->g, e->tbl[0]);
         DIE_CUDA(cudaGetLastError());
-        finalize_stats_kernel<<<1, 256, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
+        finalize_stats_kernel<<<1, kFinalThreads, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
     } else {
         DIE_CUDA(cudaMemsetAsync(e->reward_dev, 0, sizeof(double), st));
         DIE_CUDA(cudaMemsetAsync(e->alive_dev, 0, sizeof(int64_t), st));

@@ -39,6 +39,7 @@ struct FieldArgs {
     double rate_feed;
     double keep;                 // 1. - rate_decay_chem
     int food_infinite;
+    int prefetch_food;           // tile kernel: L2 prefetch of the output tile's food lines (tuning switch)
     BlurWeights bw;              // centre at [R]
     SlabGeom sg;                 // SLAB instantiation only (H, W above are then the GLOBAL field)
     SlabTables st;
@@ -91,6 +92,17 @@ field_step_kernel(const FieldArgs a) {
     const int32_t* win = SLAB ? a.st.claim[a.sg.rank] : a.winner + b * C;
     const double* dep = SLAB ? nullptr : a.action + (b * 3 + 2) * a.M;
     double* cons = SLAB ? a.st.consumed[a.sg.rank] : a.consumed + b * C;
+
+    // food of the output tile is only needed by the last phase: pull its lines towards L2 now, so that
+    // those loads do not start a fresh DRAM round trip after the blur (one 128-byte line per thread)
+    if (a.prefetch_food) {
+        constexpr int LINES_PER_ROW = TW * 8 / 128;
+        for (int l = threadIdx.x; l < TH * LINES_PER_ROW; l += NT) {
+            const int r = l / LINES_PER_ROW, c = (l - r * LINES_PER_ROW) * 16;
+            if (i0 + r < HL && j0 + c < W)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(food_in + (int64_t)(i0 + r) * W + j0 + c));
+        }
+    }
 
     // ---- stage the periodic halo tile, deposit included -------------------------------------
     double v[NSTAGE];

@@ -168,8 +168,8 @@ static inline die_turn_plan_t die_turn_plan(int normalized, int use_clip, double
  * A clipped gradient (|g| < grad_clip: every slot far from any trail) is settled exactly instead: its
  * processed value is (+-0, +-0), so phi is 0 (undetermined_grad) or, for two negative zeros, exactly pi
  * -- and delta = renormalize(theta - pi) then sits ON the sense threshold for headings of +-90 degrees. */
-DIE_MATH_FN int die_turn_quick(const die_turn_plan_t* p, double gx, double gy, double sn, double cs,
-                               double theta, double atol, double sense_radians, die_turn_t* out) {
+DIE_MATH_FN int die_turn_quick_f(const die_turn_plan_t* p, double gx, double gy, float sf, float cf,
+                                 double theta, double atol, double sense_radians, die_turn_t* out) {
     const float gxf = (float)gx, gyf = (float)gy;
     const float n2 = gxf * gxf + gyf * gyf;
     if (!(n2 < p->n2_max)) return 0;                        /* huge, inf or nan */
@@ -187,7 +187,6 @@ DIE_MATH_FN int die_turn_quick(const die_turn_plan_t* p, double gx, double gy, d
         return 1;
     }
     if (gxf > 0.0f && fabsf(gyf) <= p->phi0_ratio * gxf) return 0;    /* phi within ~1e-8 of 0: isclose(0, phi) */
-    const float sf = (float)sn, cf = (float)cs;
     const float cd = cf * gxf + sf * gyf;
     const float sd = sf * gxf - cf * gyf;
     const float q = cd * fabsf(cd);
@@ -203,6 +202,11 @@ DIE_MATH_FN int die_turn_quick(const die_turn_plan_t* p, double gx, double gy, d
      * the sign of delta; delta > atol turns by -1, delta < -atol by +1 (:186-187) */
     out->turn = (unseen || und_turn) ? 0 : (sd > 0.0f ? -1 : 1);
     return 1;
+}
+
+DIE_MATH_FN int die_turn_quick(const die_turn_plan_t* p, double gx, double gy, double sn, double cs,
+                               double theta, double atol, double sense_radians, die_turn_t* out) {
+    return die_turn_quick_f(p, gx, gy, (float)sn, (float)cs, theta, atol, sense_radians, out);
 }
 
 #endif /* DIE_TURN_H */

@@ -286,13 +286,14 @@ class Env:
         # adopt them iff the action tensor and the agents are provably untouched since
         spec, self._speculation = self._speculation, None
         fused = (spec is not None and spec == (action.data_ptr(), action._version, self._agents._version))
-        step_fn = self._lib.die_env_step_fused if fused else self._lib.die_env_step     # the latter discards
+        flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | _lib.STEP_ALIVE_BITS
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(step_fn(
+            self._refresh_alive(stream)
+            _lib.check(self._lib.die_env_step_flags(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
                 self._agents.data_ptr(), action.data_ptr(),
-                self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), stream))
+                self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), flags, stream))
         self.last_step_fused = fused
         self._cur = nxt
         self._after_step()
@@ -331,13 +332,17 @@ class Env:
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
         if speculate and agents.data_ptr() == self._agents.data_ptr() and agents.numel() == self._agents.numel():
-            if self._alive_version != self._agents._version:
-                with torch.cuda.device(self.device):
-                    _lib.check(self._lib.die_env_refresh_alive(self._handle, self._agents.data_ptr(),
-                                                               torch.cuda.current_stream().cuda_stream))
-                self._alive_version = self._agents._version
+            with torch.cuda.device(self.device):
+                self._refresh_alive(torch.cuda.current_stream().cuda_stream)
             flags |= _lib.FWD_SPECULATE_MOVE
         return flags
+
+    def _refresh_alive(self, stream) -> None:
+        """(Re)build the library's one-bit-per-slot alive mask iff the agents tensor was edited since it was
+        built (torch's version counter; the step kernels never change the alive channel)."""
+        if self._alive_version != self._agents._version:
+            _lib.check(self._lib.die_env_refresh_alive(self._handle, self._agents.data_ptr(), stream))
+            self._alive_version = self._agents._version
 
     def _note_speculation(self, action: torch.Tensor) -> None:
         self._speculation = (action.data_ptr(), action._version, self._agents._version)

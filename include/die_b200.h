@@ -164,9 +164,10 @@ int die_gradient_forward(const die_gradient_params_t* p,
  *   DIE_FWD_SPECULATE_MOVE  additionally evaluate Env._agent_move + cell resolution + the claim
  *                           (core/env.py:152-172, :211) for the action being written: post-move cells go
  *                           to the env's second cell buffer, claims into its claim table; positions are NOT
- *                           touched.  If the very next die_env_step_fused receives this action unmodified
+ *                           touched.  If the very next step receives this action unmodified
  *                           (the caller's responsibility: die_b200.Env checks the tensor identity and torch's
- *                           version counters of action and agents), the step skips its move+claim kernel and
+ *                           version counters of action and agents), die_env_step_flags(DIE_STEP_ADOPT_MOVE)
+ *                           skips the move+claim kernel and
  *                           the feed kernel commits the positions -- same results bit for bit, one launch
  *                           and ~32 B per slot less.  Any other continuation (die_env_step, another
  *                           forward) first calls die_env_discard_move, which empties the claim table.
@@ -180,10 +181,15 @@ int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
                              double* theta_dev, double* prev_grad_dev, double* action_dev,
                              const uint8_t* coin_dev, const double* noise_dev, int32_t* sense_cells_dev,
                              int32_t flags, uint64_t seed, uint64_t step, void* stream);
-/* Env.step (as die_env_step) adopting the pending speculative move; DIE_E_INVALID if none is pending. */
-int die_env_step_fused(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+/* Env.step (as die_env_step) with result-neutral options:
+ *   DIE_STEP_ADOPT_MOVE  adopt the pending speculative move (DIE_E_INVALID if none is pending);
+ *   DIE_STEP_ALIVE_BITS  the bitmask built by die_env_refresh_alive is valid for `agents_dev`: the move
+ *                        and feed kernels read alive-ness from it (1 bit instead of 8 bytes per slot). */
+#define DIE_STEP_ADOPT_MOVE  1
+#define DIE_STEP_ALIVE_BITS  2
+int die_env_step_flags(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
                        double* agents_dev, const double* action_dev,
-                       double* reward_dev, int64_t* alive_dev, void* stream);
+                       double* reward_dev, int64_t* alive_dev, int32_t flags, void* stream);
 int die_env_discard_move(die_env_t* env, void* stream);
 int die_env_pending_move(const die_env_t* env);          /* 1 while a speculative move waits for its step */
 int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream);
@@ -194,7 +200,8 @@ int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream
 int die_set_turn_quick(int32_t on);
 
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
- * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "field_impl" 0/1. */
+ * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "feed_bits" 0/1 (feed kernel takes
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1. */
 int die_set_tuning(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------------
