@@ -18,12 +18,15 @@ def get_random(size, a=0., b=1.) -> np.ndarray:
     return (b - a) * np.random.random_sample(size).round(3) + a
 
 
-def gradient_noise(field_size: Tuple[int, int], periods: int = 8, seed: Optional[int] = None) -> np.ndarray:
+def gradient_noise(field_size: Tuple[int, int], periods: int = 8, seed: Optional[int] = None,
+                   ang: Optional[np.ndarray] = None) -> np.ndarray:
     """Perlin-style gradient noise on linspace(0,1)^2: `periods` lattice cells per axis,
-    quintic fade, rounded to 3 dp (core/data_init.py:190-196)."""
+    quintic fade, rounded to 3 dp (core/data_init.py:190-196).  `ang` ([periods+2, periods+2]) injects the
+    lattice's gradient directions (default: drawn from default_rng(seed))."""
     h, w = field_size
-    rng = np.random.default_rng(seed)
-    ang = rng.uniform(0., 2. * np.pi, size=(periods + 2, periods + 2))
+    if ang is None:
+        rng = np.random.default_rng(seed)
+        ang = rng.uniform(0., 2. * np.pi, size=(periods + 2, periods + 2))
     gx, gy = np.cos(ang), np.sin(ang)
     xs = np.linspace(0., 1., h) * periods
     ys = np.linspace(0., 1., w) * periods

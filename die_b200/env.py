@@ -134,7 +134,13 @@ class Env:
                  batch: Optional[int] = None,
                  device: Optional[Union[int, str, torch.device]] = None,
                  noise_seed: Optional[int] = None,
-                 init_state: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+                 init_state: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                 init: str = 'host',
+                 seed: Optional[int] = None):
+        """``init='host'`` (default) builds the initial state with numpy in the reference's draw order
+        (``np.random.seed`` reproduces it); ``init='device'`` builds it on the GPU (die_b200/device_init.py:
+        same arithmetic and slot order, torch's device generator seeded by ``seed``) -- the only practical
+        choice for 4096^2 and beyond, where the reference's per-cell Python loop takes minutes."""
         if not torch.cuda.is_available():
             raise RuntimeError("die_b200.Env needs a CUDA device: there is no CPU fallback")
         self._lib = _lib.load()
@@ -146,6 +152,11 @@ class Env:
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self._noise_seed = noise_seed
+        if init not in ('host', 'device'):
+            raise ValueError("init must be 'host' or 'device'")
+        self._init_mode = init
+        self._seed = 0 if seed is None else int(seed)
+        self._resets = 0
         self._handle = None
         self._host = None
         self._init_data(self._field_size, init_state)
@@ -155,6 +166,14 @@ class Env:
         """core/env.py:74-86."""
         h, w = field_size
         B = self._B
+        owned = False
+        if init_state is None and self._init_mode == 'device':
+            from . import device_init
+            owned = True
+            with torch.cuda.device(self.device):
+                init_state = device_init.init_state_device(field_size, self.dynamics.init_agent_ratio,
+                                                           self._seed + 7919 * self._resets, self.device, batch=B)
+            self._resets += 1
         if init_state is None:
             mediums, agentss = [], []
             for b in range(B):
@@ -174,8 +193,12 @@ class Env:
         self._M = int(agents.shape[-1])
         with torch.cuda.device(self.device):
             if isinstance(medium, torch.Tensor):
-                first = medium.to(self.device).contiguous().clone()
-                self._agents = agents.to(self.device).contiguous().clone()
+                first = medium.to(self.device).contiguous()
+                self._agents = agents.to(self.device).contiguous()
+                if not owned:               # never alias the caller's tensors
+                    first = first.clone() if first.data_ptr() == init_state[0].data_ptr() else first
+                    self._agents = self._agents.clone() if self._agents.data_ptr() == init_state[1].data_ptr() \
+                        else self._agents
             else:
                 first = torch.from_numpy(np.ascontiguousarray(medium)).to(self.device)
                 self._agents = torch.from_numpy(np.ascontiguousarray(agents)).to(self.device)

@@ -304,42 +304,7 @@ class EmulatedSlabWorld:
 # --------------------------------------------------------------------------------------------
 # real multi-process environment (one process per GPU, torchrun)
 # --------------------------------------------------------------------------------------------
-def _grid(n: int, lo: int, hi: int, device) -> torch.Tensor:
-    """np.linspace(0, 1, n)[lo:hi] with numpy's arithmetic: i * (1/(n-1)), last element exactly 1."""
-    idx = torch.arange(lo, hi, dtype=torch.float64, device=device)
-    g = idx * (1.0 / (n - 1))
-    if hi == n:
-        g[-1] = 1.0
-    return g
-
-
-def device_gradient_noise(H: int, W: int, row_lo: int, row_hi: int, periods: int, seed: int, device) -> torch.Tensor:
-    """Rows [row_lo, row_hi) of the Perlin-style food texture of die_b200.data_init.gradient_noise,
-    evaluated on the device (same lattice for every rank: it depends on (seed, periods) only)."""
-    gen = torch.Generator(device='cpu')
-    gen.manual_seed(seed)
-    ang = (torch.rand((periods + 2, periods + 2), generator=gen, dtype=torch.float64) * (2 * np.pi)).to(device)
-    gx, gy = torch.cos(ang), torch.sin(ang)
-    xs = _grid(H, row_lo, row_hi, device) * periods
-    ys = _grid(W, 0, W, device) * periods
-    x0, y0 = torch.floor(xs).long(), torch.floor(ys).long()
-    fx, fy = (xs - x0)[:, None], (ys - y0)[None, :]
-    x0, y0 = x0[:, None], y0[None, :]
-
-    def fade(t):
-        return t * t * t * (t * (t * 6. - 15.) + 10.)
-
-    def corner(ix, iy, dx, dy):
-        return gx[ix, iy] * dx + gy[ix, iy] * dy
-
-    n00 = corner(x0, y0, fx, fy)
-    n10 = corner(x0 + 1, y0, fx - 1., fy)
-    n01 = corner(x0, y0 + 1, fx, fy - 1.)
-    n11 = corner(x0 + 1, y0 + 1, fx - 1., fy - 1.)
-    u, v = fade(fx), fade(fy)
-    nx0 = n00 + u * (n10 - n00)
-    nx1 = n01 + u * (n11 - n01)
-    return torch.round((nx0 + v * (nx1 - nx0)) * 1000.0) / 1000.0
+from .device_init import grid_coords as _grid, device_gradient_noise      # noqa: E402  (device-side initial state)
 
 
 class SlabEnv:
