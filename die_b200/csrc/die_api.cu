@@ -41,6 +41,13 @@ struct die_env {
     int64_t Mw;
     int alive_valid;
     int pending_move;      // a speculative move (cells2[1-cur] + claims) waits for a step with DIE_STEP_ADOPT_MOVE
+    // op_food_flow = WaveSequence flow operator (die_env_set_food_flow); borrowed device tables, host copy of ts
+    const double* flow_rwave;
+    const double* flow_col;    // [T][W]
+    const double* flow_row;    // [T][H]
+    double* flow_ts;           // host [T]
+    int64_t flow_T, flow_k;
+    double flow_scale, flow_keep;
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     int publish_grad;
@@ -127,6 +134,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->cells2[0]);
     cudaFree(e->cells2[1]);
     cudaFree(e->alive_bits);
+    delete[] e->flow_ts;
     cudaFree(e->consumed);
     cudaFree(e->grad);
     cudaFree(e->part_gain);
@@ -147,6 +155,27 @@ extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
     DIE_REQUIRE(e != nullptr);
     if (int rc = check_dynamics(dyn)) return rc;
     e->dyn = *dyn;
+    return DIE_OK;
+}
+
+extern "C" int die_env_set_food_flow(die_env_t* e, const double* rwave_dev, const double* col_dev, const double* row_dev,
+                                     const double* ts_host, int64_t T, int64_t k0, double scale, double decay) {
+    DIE_REQUIRE(e != nullptr);
+    delete[] e->flow_ts;
+    e->flow_ts = nullptr;
+    e->flow_rwave = e->flow_col = e->flow_row = nullptr;
+    if (rwave_dev == nullptr) return DIE_OK;                // back to the identity flow
+    DIE_REQUIRE(col_dev != nullptr && row_dev != nullptr && ts_host != nullptr && T >= 1 && k0 >= 0);
+    e->flow_ts = new (std::nothrow) double[(size_t)T];
+    if (e->flow_ts == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
+    memcpy(e->flow_ts, ts_host, sizeof(double) * (size_t)T);
+    e->flow_rwave = rwave_dev;
+    e->flow_col = col_dev;
+    e->flow_row = row_dev;
+    e->flow_T = T;
+    e->flow_k = k0;
+    e->flow_scale = scale;
+    e->flow_keep = 1.0 - decay;
     return DIE_OK;
 }
 
@@ -259,6 +288,15 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
     a.keep = 1.0 - e->dyn.rate_decay_chem;
     a.food_infinite = e->dyn.food_infinite;
     a.prefetch_food = g_field_prefetch;
+    if (e->flow_rwave != nullptr) {
+        const int64_t k = e->flow_k % e->flow_T;           // `for t in cycle(self._ts)`, core/data_init.py:40-42
+        a.flow_rwave = e->flow_rwave;
+        a.flow_col = e->flow_col + k * e->W;
+        a.flow_row = e->flow_row + k * e->H;
+        a.flow_t = e->flow_ts[k];
+        a.flow_scale = e->flow_scale;
+        a.flow_keep = e->flow_keep;
+    }
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
     switch (e->dyn.blur_radius) {
         case 0: {
@@ -317,6 +355,7 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
     prof_mark(e, 1, st);
 
     DIE_CUDA(launch_field_any(e, medium_in, medium_out, action, st));
+    if (e->flow_rwave != nullptr) ++e->flow_k;
     prof_mark(e, 2, st);
 
     const unsigned fgrid = (unsigned)((int64_t)e->nblk * e->B);

@@ -40,10 +40,32 @@ struct FieldArgs {
     double keep;                 // 1. - rate_decay_chem
     int food_infinite;
     int prefetch_food;           // tile kernel: L2 prefetch of the output tile's food lines (tuning switch)
+    // op_food_flow = WaveSequence(...).get_flow_operator(scale, decay), core/data_init.py:29-38, 71-89 (null = identity)
+    const double* flow_rwave;    // [H*W]  r + cos(pi x) + sin(0.4 pi y): the time-independent part of the wave phase
+    const double* flow_col;      // [W]    sin(pi x 3 + t) of the current time step, per column
+    const double* flow_row;      // [H]    cos(pi y 3 + t) of the current time step, per row
+    double flow_t, flow_scale, flow_keep;
     BlurWeights bw;              // centre at [R]
     SlabGeom sg;                 // SLAB instantiation only (H, W above are then the GLOBAL field)
     SlabTables st;
 };
+
+// Env._agent_feed's subtraction (core/env.py:227-228) followed by Env._medium_resource_dynamics (:147-150):
+//   food = op_food_flow(food - consumed_field),  identity or  scale * F_t + (1 - decay) * food  with
+//   F_t = (1 - mix) cos(1 pi (rwave + t)) + mix (sin(pi x 3 + t) + cos(pi y 3 + t)),  mix = 0.25   (WaveSequence)
+// The cosine is die_math.h's (<= 0.7 ulp, bit-identical to the oracle's portable backend); everything
+// time-independent or separable was tabulated by numpy on the host.
+__device__ __forceinline__ double next_food(const FieldArgs& a, double f, double cf, int row, int col, int64_t g) {
+    double food = a.food_infinite ? f : f - cf;
+    if (a.flow_rwave != nullptr) {
+        double sn, cs;
+        die_sincos(kPi * (a.flow_rwave[g] + a.flow_t), &sn, &cs);
+        const double islands = a.flow_col[col] + a.flow_row[row];
+        const double z = 0.75 * cs + 0.25 * islands;
+        food = a.flow_scale * z + a.flow_keep * food;
+    }
+    return food;
+}
 
 __device__ __forceinline__ int wrap_index(int i, int n) {
     i %= n;
@@ -171,7 +193,7 @@ field_step_kernel(const FieldArgs a) {
                 const double occ = (win[g] >= 0) ? 1.0 : 0.0;
                 const double f = food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                food_out[g] = a.food_infinite ? f : f - cf;
+                food_out[g] = next_food(a, f, cf, li, gj, g);
                 occ_out[g] = occ;
                 cons[g] = cf;
             }
@@ -210,7 +232,7 @@ field_step_kernel(const FieldArgs a) {
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
-            food_out[g] = a.food_infinite ? f : f - cf;
+            food_out[g] = next_food(a, f, cf, li, gj, g);
             occ_out[g] = occ;
             cons[g] = cf;
         }
@@ -357,7 +379,7 @@ field_march_kernel(const FieldArgs a, const MarchGeom geo) {
                 const double occ = (claim_line[0] >= 0) ? 1.0 : 0.0;    // claim of row t - CL = output row
                 const double f = fo[u];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                mout_b[C + g] = a.food_infinite ? f : f - cf;
+                mout_b[C + g] = next_food(a, f, cf, i0 + rel, oc, g);
                 mout_b[g] = occ;
                 cons[g] = cf;
             }
@@ -383,7 +405,7 @@ field_step_noblur_kernel(const FieldArgs a, int64_t total) {
         double chem = min[2 * C + g];
         if (w >= 0) chem = chem + a.action[(b * 3 + 2) * a.M + w];
         mout[g] = occ;
-        mout[C + g] = a.food_infinite ? f : f - cf;
+        mout[C + g] = next_food(a, f, cf, (int)(g / a.W), (int)(g % a.W), g);
         mout[2 * C + g] = (chem * a.bw.w[0]) * a.bw.w[0] * a.keep;
         a.consumed[gid] = cf;
     }

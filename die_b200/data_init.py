@@ -82,3 +82,83 @@ def agents_from_medium(medium: np.ndarray, max_agents: Optional[int] = None,
     agents[2, :n_alive] = 1.
     agents[3, :n_alive] = get_random(n_alive, 0.1, food_ratio)
     return agents
+
+
+# --------------------------------------------------------------------------------------------
+# time-dependent food fields (core/data_init.py:16-89)
+# --------------------------------------------------------------------------------------------
+def get_meshgrid(field_size) -> np.ndarray:
+    """core/utils.py:113-118 (dim order reversed, as there)."""
+    xcs = [np.linspace(0., 1., num=size) for size in reversed(field_size)]
+    return np.stack(np.meshgrid(*xcs))
+
+
+class FoodFlowOperator:
+    """What ``FieldSequence.get_flow_operator`` returns (core/data_init.py:29-38):
+    ``food -> scale * F_t + (1 - decay) * food`` with t advancing by one entry of the sequence per call and
+    cycling.  ``Env`` recognises the object and evaluates it inside the field kernel
+    (``die_env_set_food_flow``); calling it on a host array evaluates it with numpy."""
+
+    def __init__(self, sequence: 'FieldSequence', scale: float = 1.0, decay: float = 0.0):
+        self.sequence, self.scale, self.decay = sequence, float(scale), float(decay)
+        self.calls = 0                       # position of the iterator
+
+    def __call__(self, current):
+        t = self.sequence.ts[self.calls % len(self.sequence)]
+        self.calls += 1
+        return self.scale * self.sequence[t] + (1 - self.decay) * np.asarray(current)
+
+
+class FieldSequence:
+    """core/data_init.py:16-51."""
+
+    def __init__(self, field_size, dt: float = 0.01, t_bounds: Tuple[float, float] = (0, 10)):
+        self._size = tuple(int(s) for s in field_size)
+        self._tbounds = t_bounds
+        self._grid = get_meshgrid(self._size)
+        self._ts = np.arange(*t_bounds, dt)
+
+    @property
+    def ts(self) -> np.ndarray:
+        return self._ts
+
+    def get_flow_operator(self, scale: float = 1.0, decay: float = 0.0) -> FoodFlowOperator:
+        return FoodFlowOperator(self, scale, decay)
+
+    def __len__(self):
+        return len(self._ts)
+
+    def __contains__(self, t: float):
+        t0, t_end = self._tbounds
+        return t0 <= t < t_end
+
+    def __getitem__(self, t: float) -> np.ndarray:
+        raise NotImplementedError
+
+
+class WaveSequence(FieldSequence):
+    """core/data_init.py:71-89: running waves + moving islands."""
+
+    def __getitem__(self, t: float) -> np.ndarray:
+        pi = np.pi
+        x, y = (self._grid - 0.5) * 2
+        r = np.linalg.norm((x, y), axis=0)
+        rwave = r + np.cos(pi * x) + np.sin(0.4 * pi * y)
+        z_waves = np.cos(1 * pi * (rwave + t))
+        sx, sy = 3, 3
+        z_islands = (np.sin(pi * x * sx + t) + np.cos(pi * y * sy + t))
+        mix = 0.25
+        return (1 - mix) * z_waves + mix * z_islands
+
+    def device_tables(self):
+        """The parts of ``self[t]`` that do not need a per-cell transcendental at run time, tabulated with the
+        reference's own numpy expressions: rwave [H, W]; sin(pi x 3 + t_k) per column [T, W]; cos(pi y 3 + t_k)
+        per row [T, H]  (x varies along axis 1 and y along axis 0 of the field: np.meshgrid's 'xy' indexing)."""
+        pi = np.pi
+        x, y = (self._grid - 0.5) * 2
+        r = np.linalg.norm((x, y), axis=0)
+        rwave = r + np.cos(pi * x) + np.sin(0.4 * pi * y)
+        ts = self._ts[:, None]
+        col = np.sin(pi * x[0][None, :] * 3 + ts)
+        row = np.cos(pi * y[:, 0][None, :] * 3 + ts)
+        return np.ascontiguousarray(rwave), np.ascontiguousarray(col), np.ascontiguousarray(row)

@@ -89,14 +89,21 @@ def gaussian_kernel1d(sigma: float, truncate: float = 4.0) -> np.ndarray:
     return phi / phi.sum()
 
 
+def _is_wave_flow(op) -> bool:
+    return isinstance(op, data_init.FoodFlowOperator) and isinstance(op.sequence, data_init.WaveSequence)
+
+
 def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
     weights = getattr(d.op_action_cost, '_die_weights', None)
     if weights is None:
         raise NotImplementedError(
             "op_action_cost must be die_b200.env.linear_action_cost or zero_cost: the cost is "
             "evaluated inside the CUDA feed kernel, arbitrary Python operators are not supported")
-    if d.op_food_flow is not identity_food_flow and d.op_food_flow is not None:
-        raise NotImplementedError("op_food_flow other than identity is not on the GPU path yet")
+    if d.op_food_flow is not identity_food_flow and d.op_food_flow is not None \
+            and not _is_wave_flow(d.op_food_flow):
+        raise NotImplementedError("op_food_flow must be the identity or WaveSequence(...).get_flow_operator(...): "
+                                  "the flow is evaluated inside the CUDA field kernel, arbitrary Python operators "
+                                  "(and PerlinNoiseSequence, whose third-party noise is unseeded) are not supported")
     if d.diffuse_mode != 'wrap':
         raise NotImplementedError("only diffuse_mode='wrap' (the reference default) is implemented")
     if d.apply_sense_mask or d.agents_die:
@@ -214,12 +221,29 @@ class Env:
             cdyn = _dynamics_to_c(self.dynamics)
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
+            self._install_food_flow()
             self._publish_grad = False
             self._hint_state = None         # (medium ptr, medium version, agents version, grad published)
             self._speculation = None        # (action ptr, action version, agents version) of a pending fused move
             self._alive_version = None      # agents._version the library's alive bitmask was built for
             self.last_step_fused = False
             _hints.publish(self, first)
+
+    def _install_food_flow(self) -> None:
+        """Dynamics.op_food_flow = WaveSequence flow operator -> device tables for the field kernel."""
+        op = self.dynamics.op_food_flow
+        self._flow_tables = None
+        if not _is_wave_flow(op):
+            return
+        if tuple(op.sequence._size) != tuple(self._field_size):
+            raise ValueError(f"the WaveSequence was built for field {op.sequence._size}, the env is {self._field_size}")
+        rwave, col, row = op.sequence.device_tables()
+        ts = np.ascontiguousarray(op.sequence.ts, dtype=np.float64)
+        tabs = [torch.from_numpy(a).to(self.device) for a in (rwave, col, row)]
+        self._flow_tables = tabs                   # borrowed by the library until the handle dies
+        _lib.check(self._lib.die_env_set_food_flow(
+            self._handle, tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
+            ts.ctypes.data, len(ts), op.calls % len(ts), op.scale, op.decay))
 
     def __del__(self):
         try:
@@ -319,6 +343,8 @@ class Env:
                 self._reward_dev.data_ptr(), self._alive_dev.data_ptr(), flags, stream))
         self.last_step_fused = fused
         self._cur = nxt
+        if self._flow_tables is not None:
+            self.dynamics.op_food_flow.calls += 1      # the operator's iterator advances once per step
         self._after_step()
         return self._get_current_obs, self._reward_dev, self._alive_dev
 
@@ -430,6 +456,8 @@ class Env:
                 hb['agents'].data_ptr(), med_t.data_ptr(),
                 hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
         self._cur = nxt
+        if self._flow_tables is not None:
+            self.dynamics.op_food_flow.calls += 1
         self._after_step()
         obs = (self._unbatch(hb['agents'].numpy()), self._unbatch(med_t.numpy()))
         return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))

@@ -169,6 +169,9 @@ class SlabRank:
         self._handle = _lib.C.c_void_p()
         geom = layout.to_c(rank)
         cdyn = _dynamics_to_c(dynamics)
+        from .env import identity_food_flow
+        if dynamics.op_food_flow is not identity_food_flow and dynamics.op_food_flow is not None:
+            raise NotImplementedError("slab mode runs the identity food flow only")
         with torch.cuda.device(self.device):
             _lib.check(self._lib.die_slab_create(_lib.C.byref(geom), _lib.C.byref(cdyn), _lib.C.byref(self._handle)))
             _lib.check(self._lib.die_slab_bind(self._handle, *[int(tables[k]) for k in

@@ -88,6 +88,17 @@ int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
 int die_env_destroy(die_env_t* env);
 int die_env_set_dynamics(die_env_t* env, const die_dynamics_t* dyn);
 
+/* Dynamics.op_food_flow = WaveSequence(field_size, dt, t_bounds).get_flow_operator(scale, decay)
+ * (core/data_init.py:16-47, 71-89; used by examples/simple_agents.py:95-100): every step
+ *     food = scale * F_t + (1 - decay) * food,   t cycling over np.arange(*t_bounds, dt),
+ *     F_t = 0.75 cos(pi (rwave + t)) + 0.25 (sin(pi x 3 + t) + cos(pi y 3 + t)),  rwave = r + cos(pi x) + sin(0.4 pi y)
+ * evaluated inside the field pass.  The caller tabulates (with numpy, i.e. the reference's own arithmetic)
+ * rwave_dev[H*W], col_dev[T][W] = sin(pi x 3 + t_k), row_dev[T][H] = cos(pi y 3 + t_k) and ts_host[T]; the
+ * device tables are borrowed until the flow is reset or the env destroyed.  The per-cell cosine is
+ * die_math.h's.  k0 = index of the first time step to use.  rwave_dev == NULL restores the identity flow. */
+int die_env_set_food_flow(die_env_t* env, const double* rwave_dev, const double* col_dev, const double* row_dev,
+                          const double* ts_host, int64_t T, int64_t k0, double scale, double decay);
+
 /* Env.step, core/env.py:101-131: move -> deposit + layout -> feed -> food flow ->
  * diffuse*decay -> reward / num_agents.  Reads medium_in (never written: the previous
  * observation stays valid), writes the next medium into medium_out (a different buffer),

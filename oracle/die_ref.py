@@ -286,6 +286,57 @@ def agents_from_medium(medium: np.ndarray, max_agents: Optional[int] = None,
 
 
 # --------------------------------------------------------------------------------------
+# Time-dependent food fields (core/data_init.py:16-89)
+# --------------------------------------------------------------------------------------
+
+def get_meshgrid(field_size) -> np.ndarray:
+    """core/utils.py:113-118: dim order reversed; np.meshgrid's default 'xy' indexing, so for a field
+    (H, W) both outputs have shape (H, W), [0] varying along axis 1 and [1] along axis 0."""
+    xcs = [np.linspace(0., 1., num=size) for size in reversed(field_size)]
+    return np.stack(np.meshgrid(*xcs))
+
+
+class WaveSequence:
+    """core/data_init.py:16-51 (FieldSequence) + :71-89 (WaveSequence)."""
+
+    def __init__(self, field_size, dt: float = 0.01, t_bounds=(0, 10)):
+        self._size = tuple(field_size)
+        self._grid = get_meshgrid(self._size)
+        self._ts = np.arange(*t_bounds, dt)
+
+    def __len__(self):
+        return len(self._ts)
+
+    def __getitem__(self, t: float) -> np.ndarray:
+        pi = np.pi
+        x, y = (self._grid - 0.5) * 2
+        r = np.linalg.norm((x, y), axis=0)
+        rwave = r + np.cos(pi * x) + np.sin(0.4 * pi * y)
+        phase = 1 * pi * (rwave + t)
+        if _MATH == 'portable':         # the one transcendental the CUDA field kernel evaluates per cell
+            from oracle import portable_math
+            z_waves = portable_math.sincos(phase)[1].reshape(phase.shape)
+        else:
+            z_waves = np.cos(phase)
+        sx, sy = 3, 3
+        z_islands = (np.sin(pi * x * sx + t) + np.cos(pi * y * sy + t))
+        mix = 0.25
+        return (1 - mix) * z_waves + mix * z_islands
+
+    def get_flow_operator(self, scale: float = 1.0, decay: float = 0.0, k0: int = 0):
+        """core/data_init.py:29-38: ``it = iter(self)`` cycles over the time steps, one per call
+        (``k0``: position the iterator starts at -- replay aid, 0 in the reference)."""
+        state = {'k': int(k0)}
+
+        def food_flow(current):
+            t = self._ts[state['k'] % len(self._ts)]
+            state['k'] += 1
+            return scale * self[t] + (1 - decay) * current
+
+        return food_flow
+
+
+# --------------------------------------------------------------------------------------
 # Environment (core/env.py)
 # --------------------------------------------------------------------------------------
 

@@ -11,6 +11,8 @@ Fixtures (float64, seeded; legacy np.random streams are frozen across numpy vers
                        agents, theta), the coin flips, the action, the post-step state, reward, info.
   physarum_limit_sigma08_20x20.npz   as above with boundary='limit', diffuse_sigma=0.8 (radius-3 blur),
                        food_infinite, zero_cost, turn_angle=35, sense_angle=120.
+  physarum_waveflow_24x32.npz   as the first with op_food_flow = WaveSequence((24, 32), dt=0.01)
+                       .get_flow_operator(scale=0.5, decay=0.5); step k uses the sequence's k-th time step.
 """
 import os
 import sys
@@ -87,6 +89,10 @@ def main():
              dict(boundary=ref.BoundaryCondition.limit, diffuse_sigma=0.8, food_infinite=True,
                   op_action_cost=ref.zero_cost),
              dict(scale=0.03, turn_angle=35, sense_angle=120, sense_offset=0.06, turn_tolerance=0.05))
+    # Dynamics.op_food_flow = WaveSequence flow (examples/simple_agents.py:95-100, 'dyn-pred')
+    wave = ref.WaveSequence((24, 32), dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
+    physarum(ref, "physarum_waveflow_24x32.npz", (24, 32), 12, 41, dict(op_food_flow=wave),
+             dict(scale=0.007, turn_angle=30, sense_offset=0.04))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 

@@ -27,6 +27,7 @@ def load():
     import core.env as env
     import core.agent.static as static
     import core.agent.gradient as gradient
+    import core.data_init as data_init
 
     class NS:
         pass
@@ -35,4 +36,5 @@ def load():
     ns.Env, ns.Dynamics, ns.BoundaryCondition, ns.zero_cost = env.Env, env.Dynamics, env.BoundaryCondition, env.zero_cost
     ns.BrownianAgent, ns.ConstAgent = static.BrownianAgent, static.ConstAgent
     ns.PhysarumAgent, ns.GradientAgent = gradient.PhysarumAgent, gradient.GradientAgent
+    ns.WaveSequence = data_init.WaveSequence
     return ns

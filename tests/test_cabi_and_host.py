@@ -119,3 +119,26 @@ def test_agent_params_roundtrip(tmp_path):
     b = D.PhysarumAgent.load(str(f))
     assert b.init_params() == a.init_params()
     assert D.BrownianAgent.load.__self__ is D.BrownianAgent
+
+
+def test_wave_sequence_host_mirror_and_device_tables():
+    """die_b200.WaveSequence (host mirror of core/data_init.py:71-89) equals the oracle's restatement, and
+    the tables handed to the field kernel recombine to the same field bit for bit (so the only arithmetic
+    the kernel adds is one cosine per cell)."""
+    from oracle import die_ref as R
+    from die_b200 import data_init as DI
+    for field in ((20, 33), (64, 64), (5, 9)):
+        ws, wd = R.WaveSequence(field), DI.WaveSequence(field)
+        assert len(ws) == len(wd) == 1000 and np.array_equal(wd.ts, np.arange(0, 10, 0.01))
+        rwave, col, row = wd.device_tables()
+        assert rwave.shape == field and col.shape == (1000, field[1]) and row.shape == (1000, field[0])
+        for k in (0, 37, 999):
+            t = wd.ts[k]
+            assert np.array_equal(ws[t], wd[t])
+            z = 0.75 * np.cos(np.pi * (rwave + t)) + 0.25 * (col[k][None, :] + row[k][:, None])
+            assert np.array_equal(z, wd[t])
+    op, oo = DI.WaveSequence((12, 10)).get_flow_operator(0.5, 0.5), R.WaveSequence((12, 10)).get_flow_operator(0.5, 0.5)
+    f = np.random.default_rng(0).random((12, 10))
+    for _ in range(3):
+        assert np.array_equal(op(f), oo(f))
+    assert op.calls == 3

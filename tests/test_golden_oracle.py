@@ -35,7 +35,17 @@ PHYS_CASES = {
     "physarum_limit_sigma08_20x20.npz": (
         dict(boundary='limit', diffuse_sigma=0.8, food_infinite=True, op_action_cost=R.zero_cost),
         dict(scale=0.03, turn_angle=35, sense_angle=120, sense_offset=0.06, turn_tolerance=0.05)),
+    # op_food_flow = WaveSequence flow operator; replayed step k starts the sequence at its k-th time step
+    "physarum_waveflow_24x32.npz": (dict(waveflow=(0.5, 0.5)), dict(scale=0.007, turn_angle=30, sense_offset=0.04)),
 }
+
+
+def _dynamics(dyn_kw, size, k0=0):
+    dyn_kw = dict(dyn_kw)
+    wf = dyn_kw.pop("waveflow", None)
+    if wf is not None:
+        dyn_kw["op_food_flow"] = R.WaveSequence(size, dt=0.01).get_flow_operator(scale=wf[0], decay=wf[1], k0=k0)
+    return R.Dynamics(**dyn_kw)
 
 
 @pytest.mark.parametrize("name", sorted(PHYS_CASES))
@@ -49,7 +59,7 @@ def test_physarum_golden_every_step(name):
     m = g["agents_pre"].shape[-1]
     exact_all = True
     for k in range(len(g["reward"])):
-        env = R.Env(size, R.Dynamics(**dyn_kw), medium=g["medium_pre"][k], agents=g["agents_pre"][k])
+        env = R.Env(size, _dynamics(dyn_kw, size, k0=k), medium=g["medium_pre"][k], agents=g["agents_pre"][k])
         agent = R.PhysarumAgent(max_agents=m, prev_grad=np.ones((2, m)), **agent_kw)
         agent._direction_rads = g["theta_pre"][k].copy()
         act = agent.forward(env._get_current_obs, coin=g["coin"][k].astype(np.int64))
@@ -73,6 +83,8 @@ def test_physarum_golden_every_step(name):
     ("physarum", (36, 36), 30, 5, dict(limit=True, diffuse_sigma=0.8, rate_feed=0.3, rate_decay_chem=0.2),
      dict(scale=0.05, sense_offset=0.1)),
     ("const", (24, 24), 20, 6, {}, dict(delta_xy=(-0.01, 0.005), deposit=0.1)),
+    ("physarum", (32, 48), 30, 7, dict(waveflow=(0.5, 0.5)), dict(scale=0.007, turn_angle=30, sense_offset=0.04)),
+    ("brownian", (28, 20), 30, 8, dict(waveflow=(1.0, 0.1), food_infinite=True), dict(move_scale=0.02)),
 ])
 def test_oracle_equals_reference_executed_live(kind, size, steps, seed, dyn, akw):
     """The reference's own classes (over the stand-in packages) and the index-form restatement, side
@@ -81,10 +93,15 @@ def test_oracle_equals_reference_executed_live(kind, size, steps, seed, dyn, akw
     ref = run_reference.load()
     dyn = dict(dyn)
     limit = dyn.pop("limit", False)
+    wf = dyn.pop("waveflow", None)
+    rdyn, odyn = dict(dyn), dict(dyn)
+    if wf is not None:
+        rdyn["op_food_flow"] = ref.WaveSequence(size, dt=0.01).get_flow_operator(scale=wf[0], decay=wf[1])
+        odyn["op_food_flow"] = R.WaveSequence(size, dt=0.01).get_flow_operator(scale=wf[0], decay=wf[1])
     np.random.seed(seed)
     renv = ref.Env(size, ref.Dynamics(init_agent_ratio=0.1, boundary=ref.BoundaryCondition.limit if limit
-                                      else ref.BoundaryCondition.wrap, **dyn))
-    oenv = R.Env(size, R.Dynamics(boundary='limit' if limit else 'wrap', **dyn),
+                                      else ref.BoundaryCondition.wrap, **rdyn))
+    oenv = R.Env(size, R.Dynamics(boundary='limit' if limit else 'wrap', **odyn),
                  medium=renv.medium.values.copy(), agents=renv.agents.values.copy())
     m = renv.agents.shape[-1]
     if kind == "brownian":

@@ -34,6 +34,9 @@ CASES = {
     "physarum_limit_sigma08_20x20.npz": (
         dict(boundary='limit', diffuse_sigma=0.8, food_infinite=True, op_action_cost='zero'),
         dict(scale=0.03, turn_angle=35, sense_angle=120, sense_offset=0.06, turn_tolerance=0.05)),
+    # op_food_flow = WaveSequence flow (core/data_init.py:29-38, 71-89): the field kernel evaluates one cosine per
+    # cell with die_math.h (<= 0.7 ulp), so the food channel is compared to 1e-15 instead of bit for bit
+    "physarum_waveflow_24x32.npz": (dict(waveflow=(0.5, 0.5)), dict(scale=0.007, turn_angle=30, sense_offset=0.04)),
 }
 
 
@@ -51,11 +54,17 @@ def test_physarum_golden_every_step(name):
         dyn_kw["boundary"] = D.BoundaryCondition.limit
     if dyn_kw.get("op_action_cost") == 'zero':
         dyn_kw["op_action_cost"] = D.zero_cost
-    size = tuple(g["size"])
+    size = tuple(int(v) for v in g["size"])
+    wf = dyn_kw.pop("waveflow", None)
+    flow = D.WaveSequence(size, dt=0.01).get_flow_operator(scale=wf[0], decay=wf[1]) if wf is not None else None
+    if flow is not None:
+        dyn_kw["op_food_flow"] = flow
     m = g["agents_pre"].shape[-1]
     agent = D.PhysarumAgent(max_agents=m, **agent_kw)
     import torch
     for k in range(len(g["reward"])):
+        if flow is not None:
+            flow.calls = k                      # the recorded step k used the sequence's k-th time step
         env = D.Env(size, D.Dynamics(**dyn_kw), init_state=(g["medium_pre"][k], g["agents_pre"][k]))
         agent.set_state(theta=g["theta_pre"][k])
         act = agent.forward(env._get_current_obs, coin=g["coin"][k]).cpu().numpy()
@@ -67,6 +76,10 @@ def test_physarum_golden_every_step(name):
         gold_act = torch.from_numpy(g["action"][k]).cuda()
         _, r, _, _, info = env.step(gold_act)
         med, ag = env.get_state()
+        if flow is not None:
+            np.testing.assert_allclose(med[1], g["medium_post"][k][1], rtol=0, atol=1e-15)
+            assert (med[1] == g["medium_post"][k][1]).mean() > 0.9
+            med[1] = g["medium_post"][k][1]
         assert np.array_equal(med, g["medium_post"][k]) and np.array_equal(ag, g["agents_post"][k]), k
         assert abs(r - g["reward"][k]) <= 1e-12 * max(1.0, abs(g["reward"][k]))
         assert info["num_agents"] == g["num_agents"][k]
