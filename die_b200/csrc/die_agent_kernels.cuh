@@ -196,7 +196,7 @@ gradient_forward_kernel(const GradientArgs a) {
         const double x = nx, y = ny, th = nth;
         // food under the agent (:113-115), issued first: independent of the turn arithmetic
         const int here = (cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = SLAB ? __ldg(slab_chan(a.st.medium_in, a.sg, 1, here)) : food[here];
+        const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : food[here];
         uint32_t alive_word = 0;
         if (MOVE) alive_word = bits_p[i >> 5];
         nvalid = (k + 1 < kFwdItems) && (first + i + kAgentThreads < M);
@@ -223,7 +223,7 @@ gradient_forward_kernel(const GradientArgs a) {
         if (SLAB ? a.st.grad != nullptr : grad != nullptr) {   // published by the field pass: one 16-byte gather
             // read-only for the whole launch: ld.global.nc lets L1 cache lines that live on a peer GPU
             // (the ghost slots of every rank all look at the same few cells near the corners)
-            const double2 g2 = SLAB ? __ldg(slab_cell(a.st.grad, a.sg, sc)) : grad[sc];
+            const double2 g2 = SLAB ? slab_load_grad(a.st, a.sg, sc) : grad[sc];
             gx = g2.x;
             gy = g2.y;
         } else {
@@ -397,7 +397,7 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? (SLAB ? __ldg(slab_cell(st.consumed, sg, cell[k])) : cf[cell[k]]) : 0.0;
+        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : cf[cell[k]]) : 0.0;
         if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
         else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {
@@ -462,6 +462,20 @@ alive_bits_kernel(const double* __restrict__ agents, uint32_t* __restrict__ bits
         const bool alive = i < M && agents[(b * 4 + 2) * M + i] > 0.0;
         const uint32_t word = __ballot_sync(0xffffffffu, alive);
         if ((threadIdx.x & 31) == 0) bits[b * Mw + (i >> 5)] = word;
+    }
+}
+
+// Refresh of the mirrored edge band (die_slab.cuh): rows [0, K) and [H-K, H) of the published gradient, the
+// NEW medium's env_food and consumed_field, pulled from their owners (peer loads over NVLink) into local memory.
+__global__ void __launch_bounds__(256)
+slab_band_copy_kernel(const SlabGeom sg, const SlabTables st, double2* __restrict__ band_grad,
+                      double* __restrict__ band_food, double* __restrict__ band_cons, int with_grad) {
+    const int total = 2 * st.band_cells;
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < total; b += gridDim.x * 256) {
+        const int cell = (b < st.band_cells) ? b : st.band_hi_start + (b - st.band_cells);
+        if (with_grad) band_grad[b] = __ldg(slab_cell(st.grad, sg, cell));
+        band_food[b] = __ldg(slab_chan(st.medium_out, sg, 1, cell));
+        band_cons[b] = __ldg(slab_cell(st.consumed, sg, cell));
     }
 }
 

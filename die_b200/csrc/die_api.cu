@@ -606,7 +606,34 @@ struct die_slab {
     double* reward_dev;        // [1]
     int64_t* alive_dev;        // [1]
     int nblk;
+    // mirrored edge band (die_slab.cuh): local copies of rows [0, K) and [H-K, H)
+    int band_rows;
+    double2* band_grad;
+    double* band_food;
+    double* band_cons;
+    int band_valid;            // food + consumed_field mirrored by a refresh since the last field pass
+    int band_grad_valid;
 };
+
+// the tables a kernel of this rank gets: band pointers only while the mirror is valid
+static SlabTables slab_tables(const die_slab* e, int cur, bool want_band) {
+    SlabTables t = e->tbl[cur];
+    t.band_grad = nullptr;
+    t.band_food = nullptr;
+    t.band_cons = nullptr;
+    t.band_cells = 0;
+    t.band_hi_start = 0x7fffffff;
+    if (e->band_rows > 0) {
+        t.band_cells = e->band_rows * e->g.W;
+        t.band_hi_start = (e->g.H - e->band_rows) * e->g.W;
+        if (want_band && e->band_valid) {
+            t.band_food = e->band_food;
+            t.band_cons = e->band_cons;
+            if (e->band_grad_valid) t.band_grad = e->band_grad;
+        }
+    }
+    return t;
+}
 
 __global__ void slab_pack_stats_kernel(const double* reward, const int64_t* alive, double* out) {
     out[0] = reward[0];
@@ -661,7 +688,41 @@ extern "C" int die_slab_destroy(die_slab_t* e) {
     cudaFree(e->part_alive);
     cudaFree(e->reward_dev);
     cudaFree(e->alive_dev);
+    cudaFree(e->band_grad);
+    cudaFree(e->band_food);
+    cudaFree(e->band_cons);
     delete e;
+    return DIE_OK;
+}
+
+extern "C" int die_slab_set_band(die_slab_t* e, int32_t rows) {
+    DIE_REQUIRE(e != nullptr && rows >= 0 && 2 * rows <= e->g.H);
+    cudaFree(e->band_grad);
+    cudaFree(e->band_food);
+    cudaFree(e->band_cons);
+    e->band_grad = nullptr;
+    e->band_food = e->band_cons = nullptr;
+    e->band_rows = 0;
+    e->band_valid = e->band_grad_valid = 0;
+    if (rows == 0) return DIE_OK;
+    const size_t n = (size_t)2 * rows * e->g.W;
+    DIE_CUDA(cudaMalloc(&e->band_grad, sizeof(double2) * n));
+    DIE_CUDA(cudaMalloc(&e->band_food, sizeof(double) * n));
+    DIE_CUDA(cudaMalloc(&e->band_cons, sizeof(double) * n));
+    e->band_rows = rows;
+    return DIE_OK;
+}
+
+extern "C" int die_slab_band_refresh(die_slab_t* e, int32_t cur, int32_t with_grad, void* stream) {
+    DIE_REQUIRE(e != nullptr && (cur == 0 || cur == 1));
+    if (e->band_rows == 0) return DIE_OK;
+    const SlabTables t = slab_tables(e, cur, false);
+    const int total = 2 * t.band_cells;
+    slab_band_copy_kernel<<<grid_for(total, 256, 148), 256, 0, (cudaStream_t)stream>>>(
+        e->g, t, e->band_grad, e->band_food, e->band_cons, with_grad ? 1 : 0);
+    DIE_CUDA(cudaGetLastError());
+    e->band_valid = 1;
+    e->band_grad_valid = with_grad ? 1 : 0;
     return DIE_OK;
 }
 
@@ -701,8 +762,11 @@ extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, i
     a.agents = agents; a.theta = theta; a.action = action; a.coin = coin;
     a.seed = seed; a.step = step;
     a.sg = e->g;
-    a.st = e->tbl[cur];
-    if (!(hints & 1)) a.st.grad = nullptr;       // bit 0: the gradient published by the last die_slab_field
+    a.st = slab_tables(e, cur, true);
+    if (!(hints & 1)) {                          // bit 0: the gradient published by the last die_slab_field
+        a.st.grad = nullptr;
+        a.st.band_grad = nullptr;
+    }
     if (hints & 2) a.cells = e->cells;           // bit 1: the cell cache of the last die_slab_move_claim
     const unsigned grid = (unsigned)a.nchunk;
     if (p->discrete_turn)
@@ -719,7 +783,7 @@ extern "C" int die_slab_move_claim(die_slab_t* e, double* agents, const double* 
     const int mchunk = chunks_for(e->Ml, kMoveItems);
     move_claim_kernel<true, false><<<(unsigned)mchunk, kAgentThreads, 0, (cudaStream_t)stream>>>(
         agents, action, nullptr, e->cells, make_axis(e->g.H), make_axis(e->g.W), e->Ml, mchunk,
-        e->dyn.boundary, nullptr, 0, e->g, e->tbl[0]);
+        e->dyn.boundary, nullptr, 0, e->g, slab_tables(e, 0, false));
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -760,7 +824,8 @@ extern "C" int die_slab_field(die_slab_t* e, int32_t cur, int32_t publish_grad, 
     a.food_infinite = e->dyn.food_infinite;
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
     a.sg = e->g;
-    a.st = e->tbl[cur];
+    a.st = slab_tables(e, cur, false);
+    e->band_valid = e->band_grad_valid = 0;      // the mirror describes the previous step until die_slab_band_refresh
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t err = cudaErrorInvalidValue;
     switch (e->dyn.blur_radius) {
@@ -781,7 +846,7 @@ extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action
         agent_feed_kernel<true, false, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
             agents, action, nullptr, nullptr, e->cells, e->part_gain, e->part_alive,
             (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-            nullptr, 0, e->dyn.boundary, e->g, e->tbl[0]);
+            nullptr, 0, e->dyn.boundary, e->g, slab_tables(e, 0, true));
         DIE_CUDA(cudaGetLastError());
         finalize_stats_kernel<<<1, kFinalThreads, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
     } else {

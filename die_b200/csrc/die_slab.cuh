@@ -38,7 +38,23 @@ struct SlabTables {            // device arrays [G] of peer base pointers (symme
     double* const* consumed;
     double2* const* grad;
     double* const* action;     // each [3][Ml(q)]
+    // Mirrored edge band (LOCAL memory, may be null): the first and last `band_rows` rows of the field --
+    // where the reference parks its ~0.9 M ghost slots (they start at (0, 0) and positions wrap, so they
+    // live around the four corners) -- copied to every rank after each field pass.  Without it every rank's
+    // ghost gathers cross NVLink into ranks 0 and G-1.  Layout [2 * band_cells]: rows [0, K), then [H-K, H).
+    const double2* band_grad;
+    const double* band_food;   // env_food of the CURRENT medium (medium_in of the next forward)
+    const double* band_cons;
+    int band_cells;            // K * W
+    int band_hi_start;         // (H - K) * W
 };
+
+// index into the band mirror of global cell `cell`, or -1
+__device__ __forceinline__ int slab_band_index(const SlabTables& t, int cell) {
+    if (cell < t.band_cells) return cell;
+    if (cell >= t.band_hi_start) return t.band_cells + (cell - t.band_hi_start);
+    return -1;
+}
 
 __device__ __forceinline__ int slab_owner(const SlabGeom& g, int cell, int& local) {
     const int o = (g.slab_shift >= 0) ? (cell >> g.slab_shift) : (cell / g.slab_cells);
@@ -58,6 +74,31 @@ __device__ __forceinline__ T* slab_cell(T* const* tab, const SlabGeom& g, int ce
     int local;
     const int o = slab_owner(g, cell, local);
     return (T*)__ldg((const unsigned long long*)(tab + o)) + local;
+}
+
+// read-only gathers of the forward / feed kernels: the local band mirror when the cell is in it
+__device__ __forceinline__ double2 slab_load_grad(const SlabTables& t, const SlabGeom& g, int cell) {
+    if (t.band_grad != nullptr) {
+        const int b = slab_band_index(t, cell);
+        if (b >= 0) return __ldg(t.band_grad + b);
+    }
+    return __ldg(slab_cell(t.grad, g, cell));
+}
+
+__device__ __forceinline__ double slab_load_food(const SlabTables& t, const SlabGeom& g, int cell) {
+    if (t.band_food != nullptr) {
+        const int b = slab_band_index(t, cell);
+        if (b >= 0) return __ldg(t.band_food + b);
+    }
+    return __ldg(slab_chan(t.medium_in, g, 1, cell));
+}
+
+__device__ __forceinline__ double slab_load_consumed(const SlabTables& t, const SlabGeom& g, int cell) {
+    if (t.band_cons != nullptr) {
+        const int b = slab_band_index(t, cell);
+        if (b >= 0) return __ldg(t.band_cons + b);
+    }
+    return __ldg(slab_cell(t.consumed, g, cell));
 }
 
 __device__ __forceinline__ int64_t slab_slots_of(const SlabGeom& g, int q) { return g.n0[q] + g.n1[q]; }

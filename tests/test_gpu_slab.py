@@ -11,8 +11,12 @@ pytestmark = pytest.mark.gpu
 PHYS = dict(scale=0.02, turn_angle=30, sense_offset=0.08)      # large moves: agents cross slab seams quickly
 
 
-@pytest.mark.parametrize("shape,G", [((64, 64), 2), ((64, 64), 4), ((96, 80), 4), ((48, 36), 3), ((128, 32), 8)])
-def test_slab_world_equals_single_env(shape, G):
+@pytest.mark.parametrize("shape,G,band", [((64, 64), 2, 0), ((64, 64), 4, 0), ((96, 80), 4, 0), ((48, 36), 3, 0),
+                                          ((128, 32), 8, 0), ((64, 64), 2, 5), ((96, 80), 4, 7), ((128, 32), 8, 64),
+                                          ((48, 36), 3, 2)])
+def test_slab_world_equals_single_env(shape, G, band):
+    """band > 0: the mirrored edge band (first / last `band` rows copied to every rank after the field pass)
+    serves the gathers that fall into it; everything must stay bit-identical."""
     import die_b200 as D
     from die_b200.slab import EmulatedSlabWorld
     (ref,), env = make_pair(shape, seed=31, ratio=0.15)
@@ -21,7 +25,7 @@ def test_slab_world_equals_single_env(shape, G):
     theta0, _ = lattice_theta(m, 30, 31)
     agent = D.PhysarumAgent(max_agents=m, **PHYS)
     agent.set_state(theta=theta0)
-    world = EmulatedSlabWorld(medium0, agents0, theta0, G, **PHYS)
+    world = EmulatedSlabWorld(medium0, agents0, theta0, G, band_rows=band, **PHYS)
     rng = np.random.default_rng(1)
     obs = env._get_current_obs
     crossed = 0
