@@ -259,7 +259,7 @@ def run_slab(args, torch, dist, device, rank, world):
     N = args.field
     phys = dict(scale=1.785 / (N - 1), turn_angle=30, sense_offset=10.2 / (N - 1))
     t0 = time.time()
-    env = SlabEnv((N, N), D.Dynamics(init_agent_ratio=AGENT_RATIO), seed=3)
+    env = SlabEnv((N, N), D.Dynamics(init_agent_ratio=AGENT_RATIO), seed=3, corner_r=args.corner_r)
     agent = SlabPhysarumAgent(env, seed=11, **phys)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
@@ -299,13 +299,14 @@ def run_slab(args, torch, dist, device, rank, world):
                 "config": {"workload": f"physarum_single_field_{N}x{N}_slab", "field": [N, N], "agent": "PhysarumAgent",
                            **phys, "agent_ratio": AGENT_RATIO, "max_agents": C, "alive_agents": alive,
                            "decomposition": f"{world} row slabs, symmetric memory, in-kernel NVLink peer loads/atomics, "
+                                            f"corner mirror of {args.corner_r} cells, "
                                             "3 barriers + one 2-double all-reduce per step",
                            "l2": "per-step working set >> 126 MB L2 (no flush)"},
                 "agent_steps_per_s": C / (ms * 1e-3), "alive_agent_steps_per_s": alive / (ms * 1e-3),
                 "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs / world, 1), "peak": peak,
                              "unit": "GB/s per GPU", "frac": round(gbs / world / peak, 4), "peak_source": peak_src,
                              "traffic": None},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * 9, "launches_per_step": 9,
+                "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (10 if args.corner_r else 9), "launches_per_step": 10 if args.corner_r else 9,
                 "clocks": clocks, "setup_s": round(setup_s, 1), "last_reward": reward}
         print(json.dumps(line))
 
@@ -524,6 +525,7 @@ def main():
     ap.add_argument("--cpu-field", type=int, default=256, help="side of each CPU sample env")
     ap.add_argument("--cpu-steps", type=int, default=100, help="steps per CPU env in the cpu_baseline leg")
     ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")
+    ap.add_argument("--corner-r", type=int, default=512, help="slab workload: side of the mirrored corner patches (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",

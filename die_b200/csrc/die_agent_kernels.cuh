@@ -465,17 +465,22 @@ alive_bits_kernel(const double* __restrict__ agents, uint32_t* __restrict__ bits
     }
 }
 
-// Refresh of the mirrored edge band (die_slab.cuh): rows [0, K) and [H-K, H) of the published gradient, the
-// NEW medium's env_food and consumed_field, pulled from their owners (peer loads over NVLink) into local memory.
+// Refresh of the corner mirror (die_slab.cuh): the four corner_r x corner_r corner patches of the published
+// gradient, the NEW medium's env_food and consumed_field, pulled from their owners (peer loads over NVLink)
+// into local memory.
 __global__ void __launch_bounds__(256)
-slab_band_copy_kernel(const SlabGeom sg, const SlabTables st, double2* __restrict__ band_grad,
-                      double* __restrict__ band_food, double* __restrict__ band_cons, int with_grad) {
-    const int total = 2 * st.band_cells;
+slab_corner_copy_kernel(const SlabGeom sg, const SlabTables st, double2* __restrict__ corner_grad,
+                        double* __restrict__ corner_food, double* __restrict__ corner_cons, int with_grad) {
+    const int R = st.corner_r, P = 2 * R;
+    const int total = P * P;
     for (int b = blockIdx.x * 256 + threadIdx.x; b < total; b += gridDim.x * 256) {
-        const int cell = (b < st.band_cells) ? b : st.band_hi_start + (b - st.band_cells);
-        if (with_grad) band_grad[b] = __ldg(slab_cell(st.grad, sg, cell));
-        band_food[b] = __ldg(slab_chan(st.medium_out, sg, 1, cell));
-        band_cons[b] = __ldg(slab_cell(st.consumed, sg, cell));
+        const int pr = b / P, pc = b - pr * P;
+        const int row = (pr < R) ? pr : pr + (sg.H - P);
+        const int col = (pc < R) ? pc : pc + (sg.W - P);
+        const int cell = row * sg.W + col;
+        if (with_grad) corner_grad[b] = __ldg(slab_cell(st.grad, sg, cell));
+        corner_food[b] = __ldg(slab_chan(st.medium_out, sg, 1, cell));
+        corner_cons[b] = __ldg(slab_cell(st.consumed, sg, cell));
     }
 }
 

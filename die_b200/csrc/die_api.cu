@@ -606,31 +606,26 @@ struct die_slab {
     double* reward_dev;        // [1]
     int64_t* alive_dev;        // [1]
     int nblk;
-    // mirrored edge band (die_slab.cuh): local copies of rows [0, K) and [H-K, H)
-    int band_rows;
-    double2* band_grad;
-    double* band_food;
-    double* band_cons;
-    int band_valid;            // food + consumed_field mirrored by a refresh since the last field pass
-    int band_grad_valid;
+    // corner mirror (die_slab.cuh): local copies of the four corner_r x corner_r corner patches
+    int corner_r;
+    double2* corner_grad;
+    double* corner_food;
+    double* corner_cons;
+    int corner_valid;          // food + consumed_field mirrored by a refresh since the last field pass
+    int corner_grad_valid;
 };
 
-// the tables a kernel of this rank gets: band pointers only while the mirror is valid
-static SlabTables slab_tables(const die_slab* e, int cur, bool want_band) {
+// the tables a kernel of this rank gets: mirror pointers only while the mirror is valid
+static SlabTables slab_tables(const die_slab* e, int cur, bool want_mirror) {
     SlabTables t = e->tbl[cur];
-    t.band_grad = nullptr;
-    t.band_food = nullptr;
-    t.band_cons = nullptr;
-    t.band_cells = 0;
-    t.band_hi_start = 0x7fffffff;
-    if (e->band_rows > 0) {
-        t.band_cells = e->band_rows * e->g.W;
-        t.band_hi_start = (e->g.H - e->band_rows) * e->g.W;
-        if (want_band && e->band_valid) {
-            t.band_food = e->band_food;
-            t.band_cons = e->band_cons;
-            if (e->band_grad_valid) t.band_grad = e->band_grad;
-        }
+    t.corner_grad = nullptr;
+    t.corner_food = nullptr;
+    t.corner_cons = nullptr;
+    t.corner_r = e->corner_r;
+    if (e->corner_r > 0 && want_mirror && e->corner_valid) {
+        t.corner_food = e->corner_food;
+        t.corner_cons = e->corner_cons;
+        if (e->corner_grad_valid) t.corner_grad = e->corner_grad;
     }
     return t;
 }
@@ -688,41 +683,41 @@ extern "C" int die_slab_destroy(die_slab_t* e) {
     cudaFree(e->part_alive);
     cudaFree(e->reward_dev);
     cudaFree(e->alive_dev);
-    cudaFree(e->band_grad);
-    cudaFree(e->band_food);
-    cudaFree(e->band_cons);
+    cudaFree(e->corner_grad);
+    cudaFree(e->corner_food);
+    cudaFree(e->corner_cons);
     delete e;
     return DIE_OK;
 }
 
-extern "C" int die_slab_set_band(die_slab_t* e, int32_t rows) {
-    DIE_REQUIRE(e != nullptr && rows >= 0 && 2 * rows <= e->g.H);
-    cudaFree(e->band_grad);
-    cudaFree(e->band_food);
-    cudaFree(e->band_cons);
-    e->band_grad = nullptr;
-    e->band_food = e->band_cons = nullptr;
-    e->band_rows = 0;
-    e->band_valid = e->band_grad_valid = 0;
-    if (rows == 0) return DIE_OK;
-    const size_t n = (size_t)2 * rows * e->g.W;
-    DIE_CUDA(cudaMalloc(&e->band_grad, sizeof(double2) * n));
-    DIE_CUDA(cudaMalloc(&e->band_food, sizeof(double) * n));
-    DIE_CUDA(cudaMalloc(&e->band_cons, sizeof(double) * n));
-    e->band_rows = rows;
+extern "C" int die_slab_set_corner_mirror(die_slab_t* e, int32_t r) {
+    DIE_REQUIRE(e != nullptr && r >= 0 && 2 * r <= e->g.H && 2 * r <= e->g.W);
+    cudaFree(e->corner_grad);
+    cudaFree(e->corner_food);
+    cudaFree(e->corner_cons);
+    e->corner_grad = nullptr;
+    e->corner_food = e->corner_cons = nullptr;
+    e->corner_r = 0;
+    e->corner_valid = e->corner_grad_valid = 0;
+    if (r == 0) return DIE_OK;
+    const size_t n = (size_t)4 * r * r;
+    DIE_CUDA(cudaMalloc(&e->corner_grad, sizeof(double2) * n));
+    DIE_CUDA(cudaMalloc(&e->corner_food, sizeof(double) * n));
+    DIE_CUDA(cudaMalloc(&e->corner_cons, sizeof(double) * n));
+    e->corner_r = r;
     return DIE_OK;
 }
 
-extern "C" int die_slab_band_refresh(die_slab_t* e, int32_t cur, int32_t with_grad, void* stream) {
+extern "C" int die_slab_corner_refresh(die_slab_t* e, int32_t cur, int32_t with_grad, void* stream) {
     DIE_REQUIRE(e != nullptr && (cur == 0 || cur == 1));
-    if (e->band_rows == 0) return DIE_OK;
+    if (e->corner_r == 0) return DIE_OK;
     const SlabTables t = slab_tables(e, cur, false);
-    const int total = 2 * t.band_cells;
-    slab_band_copy_kernel<<<grid_for(total, 256, 148), 256, 0, (cudaStream_t)stream>>>(
-        e->g, t, e->band_grad, e->band_food, e->band_cons, with_grad ? 1 : 0);
+    const int64_t total = (int64_t)4 * e->corner_r * e->corner_r;
+    slab_corner_copy_kernel<<<grid_for(total, 256, 148), 256, 0, (cudaStream_t)stream>>>(
+        e->g, t, e->corner_grad, e->corner_food, e->corner_cons, with_grad ? 1 : 0);
     DIE_CUDA(cudaGetLastError());
-    e->band_valid = 1;
-    e->band_grad_valid = with_grad ? 1 : 0;
+    e->corner_valid = 1;
+    e->corner_grad_valid = with_grad ? 1 : 0;
     return DIE_OK;
 }
 
@@ -765,7 +760,7 @@ extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, i
     a.st = slab_tables(e, cur, true);
     if (!(hints & 1)) {                          // bit 0: the gradient published by the last die_slab_field
         a.st.grad = nullptr;
-        a.st.band_grad = nullptr;
+        a.st.corner_grad = nullptr;
     }
     if (hints & 2) a.cells = e->cells;           // bit 1: the cell cache of the last die_slab_move_claim
     const unsigned grid = (unsigned)a.nchunk;
@@ -825,7 +820,7 @@ extern "C" int die_slab_field(die_slab_t* e, int32_t cur, int32_t publish_grad, 
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
     a.sg = e->g;
     a.st = slab_tables(e, cur, false);
-    e->band_valid = e->band_grad_valid = 0;      // the mirror describes the previous step until die_slab_band_refresh
+    e->corner_valid = e->corner_grad_valid = 0;  // the mirror describes the previous step until die_slab_corner_refresh
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t err = cudaErrorInvalidValue;
     switch (e->dyn.blur_radius) {

@@ -38,21 +38,25 @@ struct SlabTables {            // device arrays [G] of peer base pointers (symme
     double* const* consumed;
     double2* const* grad;
     double* const* action;     // each [3][Ml(q)]
-    // Mirrored edge band (LOCAL memory, may be null): the first and last `band_rows` rows of the field --
-    // where the reference parks its ~0.9 M ghost slots (they start at (0, 0) and positions wrap, so they
-    // live around the four corners) -- copied to every rank after each field pass.  Without it every rank's
-    // ghost gathers cross NVLink into ranks 0 and G-1.  Layout [2 * band_cells]: rows [0, K), then [H-K, H).
-    const double2* band_grad;
-    const double* band_food;   // env_food of the CURRENT medium (medium_in of the next forward)
-    const double* band_cons;
-    int band_cells;            // K * W
-    int band_hi_start;         // (H - K) * W
+    // Corner mirror (LOCAL memory, may be null).  The reference creates ~90 % of its slots as "ghosts" at
+    // (0, 0) and positions wrap, so for thousands of steps they live within a few hundred cells of the four
+    // corners of the field -- on ranks 0 and G-1 -- and every other rank's ghost gathers would cross NVLink
+    // into those two.  The corner_r x corner_r patches at the four corners of the published gradient, the
+    // current env_food and consumed_field are therefore copied to every rank after each field pass.
+    // Layout [2 corner_r][2 corner_r]: patch row = row (top) or row - (H - 2 corner_r) (bottom), same for columns.
+    const double2* corner_grad;
+    const double* corner_food;   // env_food of the CURRENT medium (medium_in of the next forward)
+    const double* corner_cons;
+    int corner_r;
 };
 
-// index into the band mirror of global cell `cell`, or -1
-__device__ __forceinline__ int slab_band_index(const SlabTables& t, int cell) {
-    if (cell < t.band_cells) return cell;
-    if (cell >= t.band_hi_start) return t.band_cells + (cell - t.band_hi_start);
+// index into the corner mirror of global cell `cell`, or -1
+__device__ __forceinline__ int slab_corner_index(const SlabTables& t, int H, int W, int cell) {
+    const int R = t.corner_r;
+    const int row = cell / W, col = cell - row * W;
+    const bool top = row < R, left = col < R;
+    if ((top || row >= H - R) && (left || col >= W - R))
+        return (top ? row : row - (H - 2 * R)) * (2 * R) + (left ? col : col - (W - 2 * R));
     return -1;
 }
 
@@ -76,27 +80,27 @@ __device__ __forceinline__ T* slab_cell(T* const* tab, const SlabGeom& g, int ce
     return (T*)__ldg((const unsigned long long*)(tab + o)) + local;
 }
 
-// read-only gathers of the forward / feed kernels: the local band mirror when the cell is in it
+// read-only gathers of the forward / feed kernels: the local corner mirror when the cell is in it
 __device__ __forceinline__ double2 slab_load_grad(const SlabTables& t, const SlabGeom& g, int cell) {
-    if (t.band_grad != nullptr) {
-        const int b = slab_band_index(t, cell);
-        if (b >= 0) return __ldg(t.band_grad + b);
+    if (t.corner_grad != nullptr) {
+        const int b = slab_corner_index(t, g.H, g.W, cell);
+        if (b >= 0) return __ldg(t.corner_grad + b);
     }
     return __ldg(slab_cell(t.grad, g, cell));
 }
 
 __device__ __forceinline__ double slab_load_food(const SlabTables& t, const SlabGeom& g, int cell) {
-    if (t.band_food != nullptr) {
-        const int b = slab_band_index(t, cell);
-        if (b >= 0) return __ldg(t.band_food + b);
+    if (t.corner_food != nullptr) {
+        const int b = slab_corner_index(t, g.H, g.W, cell);
+        if (b >= 0) return __ldg(t.corner_food + b);
     }
     return __ldg(slab_chan(t.medium_in, g, 1, cell));
 }
 
 __device__ __forceinline__ double slab_load_consumed(const SlabTables& t, const SlabGeom& g, int cell) {
-    if (t.band_cons != nullptr) {
-        const int b = slab_band_index(t, cell);
-        if (b >= 0) return __ldg(t.band_cons + b);
+    if (t.corner_cons != nullptr) {
+        const int b = slab_corner_index(t, g.H, g.W, cell);
+        if (b >= 0) return __ldg(t.corner_cons + b);
     }
     return __ldg(slab_cell(t.consumed, g, cell));
 }
@@ -109,6 +113,13 @@ __device__ __forceinline__ int64_t slab_slot_global(const SlabGeom& g, int q, in
 
 // owner rank and local index of a global slot id
 __device__ __forceinline__ int slab_slot_owner(const SlabGeom& g, int64_t gid, int64_t& local) {
+    {   // almost always the winner of a cell of this slab is one of this rank's own alive slots
+        const int r = g.rank;
+        if (gid >= g.s0[r] && gid < g.s0[r] + g.n0[r]) {
+            local = gid - g.s0[r];
+            return r;
+        }
+    }
     for (int q = 0; q < g.G; ++q) {
         if (gid >= g.s0[q] && gid < g.s0[q] + g.n0[q]) {
             local = gid - g.s0[q];

@@ -212,17 +212,17 @@ class SlabRank:
         self.cur = 1 - self.cur
         self.grad_valid = True
 
-    def set_band(self, rows: int):
-        """Mirror the first / last `rows` rows (gradient, food, consumed_field) locally, see include/die_b200.h."""
+    def set_corner_mirror(self, r: int):
+        """Mirror the four r x r corner patches (gradient, food, consumed_field) locally, see include/die_b200.h."""
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.die_slab_set_band(self._handle, int(rows)))
-        self.band_rows = int(rows)
+            _lib.check(self._lib.die_slab_set_corner_mirror(self._handle, int(r)))
+        self.corner_r = int(r)
 
-    def phase_band(self):
+    def phase_corners(self):
         """After the barrier that follows phase_field (every slab's new rows are complete), before phase_feed."""
-        if getattr(self, 'band_rows', 0) > 0:
+        if getattr(self, 'corner_r', 0) > 0:
             with torch.cuda.device(self.device):
-                _lib.check(self._lib.die_slab_band_refresh(self._handle, 1 - self.cur, 1, self._stream()))
+                _lib.check(self._lib.die_slab_corner_refresh(self._handle, 1 - self.cur, 1, self._stream()))
 
     def phase_feed(self):
         with torch.cuda.device(self.device):
@@ -252,7 +252,7 @@ class EmulatedSlabWorld:
     without a multi-GPU box.  Built from a GLOBAL state so results can be compared with ``Env``."""
 
     def __init__(self, medium: np.ndarray, agents: np.ndarray, theta: np.ndarray, G: int,
-                 dynamics: Optional[Dynamics] = None, device=None, band_rows: int = 0, **physarum_kw):
+                 dynamics: Optional[Dynamics] = None, device=None, corner_r: int = 0, **physarum_kw):
         device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.dynamics = dynamics or Dynamics()
         self.layout, mediums, locals_ = split_global_state(medium, agents, G)
@@ -276,8 +276,8 @@ class EmulatedSlabWorld:
                            agents=torch.from_numpy(locals_[q]).to(device),
                            theta=torch.from_numpy(np.ascontiguousarray(theta[ids])).to(device))
             self.ranks.append(SlabRank(L, q, self.dynamics, tensors, tables, device))
-            if band_rows:
-                self.ranks[-1].set_band(min(band_rows, L.H // 2))
+            if corner_r:
+                self.ranks[-1].set_corner_mirror(min(corner_r, L.H // 2, L.W // 2))
         self._step = 0
 
     def forward(self, coin_global: Optional[np.ndarray] = None):
@@ -294,7 +294,7 @@ class EmulatedSlabWorld:
         for r in self.ranks:            # (barrier)
             r.phase_field()
         for r in self.ranks:            # (barrier)
-            r.phase_band()
+            r.phase_corners()
         for r in self.ranks:
             r.phase_feed()
         self._step += 1
@@ -341,7 +341,7 @@ class SlabEnv:
     of a global state (``split_global_state``); otherwise the state is generated on the device."""
 
     def __init__(self, field_size: Tuple[int, int], dynamics: Optional[Dynamics] = None, *, group=None,
-                 init_state=None, seed: int = 0, noise_periods: Optional[int] = None, band_rows: int = 64):
+                 init_state=None, seed: int = 0, noise_periods: Optional[int] = None, corner_r: int = 512):
         import torch.distributed as dist
         self._dist = dist
         self.dynamics = dynamics or Dynamics()
@@ -381,8 +381,8 @@ class SlabEnv:
                        theta=torch.zeros(max(Ml, 1), dtype=torch.float64, device=self.device))
         tables = dict(medium_a=tbl_a, medium_b=tbl_b, claim=tbl_c, consumed=tbl_k, grad=tbl_g, action=tbl_act)
         self.slab = SlabRank(layout, self.rank, self.dynamics, tensors, tables, self.device)
-        if band_rows and self.G > 1:
-            self.slab.set_band(min(int(band_rows), H // 2))
+        if corner_r and self.G > 1:
+            self.slab.set_corner_mirror(min(int(corner_r), H // 2, W // 2))
         self._stats_host = torch.zeros(2, dtype=torch.float64).pin_memory()
         torch.cuda.synchronize(self.device)
         P.barrier()
@@ -440,7 +440,7 @@ class SlabEnv:
         self.peers.barrier()          # every claim is in before any slab is blurred
         s.phase_field()
         self.peers.barrier()          # consumed_field / new medium complete before anybody gathers from it
-        s.phase_band()                # pull the edge band (where the ghost slots live) into local memory
+        s.phase_corners()             # pull the corner patches (where the ghost slots live) into local memory
         s.phase_feed()
         self.peers.barrier()          # claim table clean before the next step's claims
         if reduce_stats:

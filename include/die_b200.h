@@ -251,14 +251,15 @@ int die_slab_field(die_slab_t* slab, int32_t cur, int32_t publish_grad, void* st
 int die_slab_feed(die_slab_t* slab, double* agents_local_dev, const double* action_local_dev,
                   double* stats_dev, void* stream);
 const int32_t* die_slab_cells(const die_slab_t* slab);    /* int32 [Ml] GLOBAL linear cell of every local slot */
-/* Mirrored edge band: local copies of the first and last `rows` rows of the published gradient, the current
- * env_food and consumed_field.  The reference creates ~90 % of its slots as ghosts at (0, 0); positions wrap,
- * so they stay around the four corners and every rank's ghost gathers would otherwise cross NVLink into ranks
- * 0 and G-1.  die_slab_band_refresh (same `cur` as the die_slab_field before it) pulls the band from its
- * owners; call it after the barrier that follows die_slab_field and before die_slab_feed.  Gathers outside the
- * band still go to the owner, so `rows` is a performance parameter only; results do not change. */
-int die_slab_set_band(die_slab_t* slab, int32_t rows);
-int die_slab_band_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, void* stream);
+/* Corner mirror: local copies of the four r x r corner patches of the published gradient, the current env_food
+ * and consumed_field.  The reference creates ~90 % of its slots as ghosts at (0, 0); positions wrap, so for
+ * thousands of steps they stay within a few hundred cells of the four corners and every rank's ghost gathers
+ * would otherwise cross NVLink into ranks 0 and G-1.  die_slab_corner_refresh (same `cur` as the die_slab_field
+ * before it) pulls the patches from their owners; call it after the barrier that follows die_slab_field and
+ * before die_slab_feed.  Gathers outside the patches still go to the owner, so `r` is a performance parameter
+ * only; results do not change. */
+int die_slab_set_corner_mirror(die_slab_t* slab, int32_t r);
+int die_slab_corner_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, void* stream);
 
 /* Field-pass implementation switch (tests / A-B timing): 0 = shared-memory tile kernel (default),
  * 1 = register-tiled warp-marching kernel (blur radius <= 3; measured slower on B200 so far: 0.29 vs

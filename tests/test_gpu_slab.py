@@ -15,8 +15,8 @@ PHYS = dict(scale=0.02, turn_angle=30, sense_offset=0.08)      # large moves: ag
                                           ((128, 32), 8, 0), ((64, 64), 2, 5), ((96, 80), 4, 7), ((128, 32), 8, 64),
                                           ((48, 36), 3, 2)])
 def test_slab_world_equals_single_env(shape, G, band):
-    """band > 0: the mirrored edge band (first / last `band` rows copied to every rank after the field pass)
-    serves the gathers that fall into it; everything must stay bit-identical."""
+    """band > 0: the corner mirror (the four band x band corner patches copied to every rank after the field
+    pass) serves the gathers that fall into it; everything must stay bit-identical."""
     import die_b200 as D
     from die_b200.slab import EmulatedSlabWorld
     (ref,), env = make_pair(shape, seed=31, ratio=0.15)
@@ -25,7 +25,7 @@ def test_slab_world_equals_single_env(shape, G, band):
     theta0, _ = lattice_theta(m, 30, 31)
     agent = D.PhysarumAgent(max_agents=m, **PHYS)
     agent.set_state(theta=theta0)
-    world = EmulatedSlabWorld(medium0, agents0, theta0, G, band_rows=band, **PHYS)
+    world = EmulatedSlabWorld(medium0, agents0, theta0, G, corner_r=band, **PHYS)
     rng = np.random.default_rng(1)
     obs = env._get_current_obs
     crossed = 0

@@ -18,7 +18,7 @@ def main():
     for _ in range(10):
         env.step_async(agent.forward())
     torch.cuda.synchronize(); dist.barrier()
-    names = ["forward", "move", "bar1", "field", "bar2", "feed", "bar3", "allreduce"]
+    names = ["forward", "move", "bar1", "field", "bar2", "corners", "feed", "bar3", "allreduce"]
     acc = np.zeros(len(names))
     for it in range(steps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
@@ -27,10 +27,11 @@ def main():
         ev[2].record(); env.peers.barrier()
         ev[3].record(); s.phase_field()
         ev[4].record(); env.peers.barrier()
-        ev[5].record(); s.phase_feed()
-        ev[6].record(); env.peers.barrier()
-        ev[7].record(); dist.all_reduce(s.stats)
-        ev[8].record()
+        ev[5].record(); s.phase_corners()
+        ev[6].record(); s.phase_feed()
+        ev[7].record(); env.peers.barrier()
+        ev[8].record(); dist.all_reduce(s.stats)
+        ev[9].record()
         torch.cuda.synchronize()
         cur = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
         acc += cur
