@@ -438,11 +438,9 @@ class Env:
     def _step_host(self, action: np.ndarray):
         hb = self.host_buffers()
         B, M = self._B, self._M
-        act_t = hb['action']
-        act_np = act_t.numpy()
-        src = np.asarray(action, dtype=np.float64).reshape(B, 3, M)
-        if not np.shares_memory(src, act_np):
-            np.copyto(act_np, src)
+        # the library copies straight from the caller's array (cudaMemcpyAsync: full speed if it is pinned --
+        # e.g. the array an Agent's host path returned -- staged by the driver if it is pageable); no host memcpy
+        src = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(B, 3, M))
         hb['flip'] ^= 1
         med_t = hb['medium'][hb['flip']]
         nxt = 1 - self._cur
@@ -452,7 +450,7 @@ class Env:
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(self._lib.die_env_step_host(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
-                self._agents.data_ptr(), act_t.data_ptr(),
+                self._agents.data_ptr(), src.ctypes.data,
                 hb['agents'].data_ptr(), med_t.data_ptr(),
                 hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
         self._cur = nxt
