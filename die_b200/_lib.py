@@ -7,6 +7,7 @@ from ._build import LIB_PATH
 
 DIE_MAX_RADIUS = 8
 BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
+DIFFUSE_MODES = {'wrap': 0, 'reflect': 1, 'nearest': 2, 'mirror': 3, 'constant': 4}
 FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE = 1, 2, 4
 STEP_ADOPT_MOVE, STEP_ALIVE_BITS = 1, 2
 
@@ -21,7 +22,7 @@ class DieDynamics(C.Structure):
         ("blur_radius", C.c_int32),
         ("boundary", C.c_int32),
         ("food_infinite", C.c_int32),
-        ("reserved", C.c_int32),
+        ("diffuse_mode", C.c_int32),
     ]
 
 

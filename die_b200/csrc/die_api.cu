@@ -75,6 +75,7 @@ static int check_dynamics(const die_dynamics_t* d) {
     DIE_REQUIRE(d != nullptr);
     DIE_REQUIRE(d->blur_radius >= 0 && d->blur_radius <= DIE_MAX_RADIUS);
     DIE_REQUIRE(d->boundary >= DIE_BOUNDARY_WRAP && d->boundary <= DIE_BOUNDARY_NONE);
+    DIE_REQUIRE(d->diffuse_mode >= DIE_DIFFUSE_WRAP && d->diffuse_mode <= DIE_DIFFUSE_CONSTANT);
     return DIE_OK;
 }
 
@@ -260,7 +261,7 @@ static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms 
 template <int R>
 static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
     if constexpr (R <= 3) {
-        if (g_field_impl == 1)
+        if (g_field_impl == 1 && fa.diffuse_mode == DIE_DIFFUSE_WRAP)
             return fa.grad != nullptr ? launch_march<R, true>(fa, B, st) : launch_march<R, false>(fa, B, st);
     }
     return fa.grad != nullptr ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
@@ -288,6 +289,7 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
     a.keep = 1.0 - e->dyn.rate_decay_chem;
     a.food_infinite = e->dyn.food_infinite;
     a.prefetch_food = g_field_prefetch;
+    a.diffuse_mode = e->dyn.diffuse_mode;
     if (e->flow_rwave != nullptr) {
         const int64_t k = e->flow_k % e->flow_T;           // `for t in cycle(self._ts)`, core/data_init.py:40-42
         a.flow_rwave = e->flow_rwave;
@@ -643,6 +645,7 @@ extern "C" int die_slab_create(const die_slab_geom_t* geom, const die_dynamics_t
     DIE_REQUIRE((int64_t)geom->H * geom->W <= 0x7fffffffLL && geom->M >= 1 && geom->M <= 0x7fffffffLL);
     if (int rc = check_dynamics(dyn)) return rc;
     DIE_REQUIRE(dyn->blur_radius >= 1);
+    DIE_REQUIRE(dyn->diffuse_mode == DIE_DIFFUSE_WRAP);
     die_slab* e = new (std::nothrow) die_slab();
     if (e == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
     memset(e, 0, sizeof(*e));

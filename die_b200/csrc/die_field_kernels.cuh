@@ -39,6 +39,7 @@ struct FieldArgs {
     double rate_feed;
     double keep;                 // 1. - rate_decay_chem
     int food_infinite;
+    int diffuse_mode;            // DIE_DIFFUSE_* (tile kernel; the march and slab kernels are wrap only)
     int prefetch_food;           // tile kernel: L2 prefetch of the output tile's food lines (tuning switch)
     // op_food_flow = WaveSequence(...).get_flow_operator(scale, decay), core/data_init.py:29-38, 71-89 (null = identity)
     const double* flow_rwave;    // [H*W]  r + cos(pi x) + sin(0.4 pi y): the time-independent part of the wave phase
@@ -70,6 +71,28 @@ __device__ __forceinline__ double next_food(const FieldArgs& a, double f, double
 __device__ __forceinline__ int wrap_index(int i, int n) {
     i %= n;
     return i < 0 ? i + n : i;
+}
+
+// scipy.ndimage boundary extension (skimage.filters.gaussian(mode=...), core/env.py:140-143): the source index an
+// out-of-range index i stands for, or -1 for 'constant' (cval = 0).
+//   wrap      a b c d | a b c d | a b c d        nearest   a a a a | a b c d | d d d d
+//   reflect   d c b a | a b c d | d c b a        mirror    d c b | a b c d | c b a
+__device__ __forceinline__ int extend_index(int i, int n, int mode) {
+    if (mode == DIE_DIFFUSE_WRAP) return wrap_index(i, n);
+    if (i >= 0 && i < n) return i;
+    if (mode == DIE_DIFFUSE_NEAREST) return i < 0 ? 0 : n - 1;
+    if (mode == DIE_DIFFUSE_REFLECT) {
+        const int p = 2 * n;
+        i = wrap_index(i, p);
+        return i < n ? i : p - 1 - i;
+    }
+    if (mode == DIE_DIFFUSE_MIRROR) {
+        if (n == 1) return 0;
+        const int p = 2 * n - 2;
+        i = wrap_index(i, p);
+        return i < n ? i : p - i;
+    }
+    return -1;                                     // DIE_DIFFUSE_CONSTANT
 }
 
 // Tile TH x TW outputs per CTA.  With GRAD the CTA blurs a one-cell ring more ((TH+2) x (TW+2))
@@ -136,13 +159,14 @@ field_step_kernel(const FieldArgs a) {
         w[s] = -1;
         if (idx < LH * LW) {
             const int r = idx / LW, c = idx - r * LW;
-            const int gi = wrap_index(row0 + i0 - G - R + r, H);     // global row, periodic over the WHOLE field
-            const int gj = wrap_index(j0 - G - R + c, W);
+            // global row / column this staged cell stands for (periodic over the WHOLE field by default)
+            const int gi = SLAB ? wrap_index(row0 + i0 - G - R + r, H) : extend_index(i0 - G - R + r, H, a.diffuse_mode);
+            const int gj = SLAB ? wrap_index(j0 - G - R + c, W) : extend_index(j0 - G - R + c, W, a.diffuse_mode);
             const int g = gi * W + gj;
             if (SLAB) {                       // rows outside this rank's slab come from the neighbours over NVLink
                 v[s] = __ldg(slab_chan(a.st.medium_in, a.sg, 2, g));
                 w[s] = __ldg(slab_cell(a.st.claim, a.sg, g));
-            } else {
+            } else if (gi >= 0 && gj >= 0) {  // ('constant' extension: 0, no deposit)
                 v[s] = chem_in[g];
                 w[s] = win[g];
             }

@@ -104,8 +104,8 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
         raise NotImplementedError("op_food_flow must be the identity or WaveSequence(...).get_flow_operator(...): "
                                   "the flow is evaluated inside the CUDA field kernel, arbitrary Python operators "
                                   "(and PerlinNoiseSequence, whose third-party noise is unseeded) are not supported")
-    if d.diffuse_mode != 'wrap':
-        raise NotImplementedError("only diffuse_mode='wrap' (the reference default) is implemented")
+    if d.diffuse_mode not in _lib.DIFFUSE_MODES:
+        raise ValueError(f"diffuse_mode must be one of {sorted(_lib.DIFFUSE_MODES)} (scipy.ndimage's modes)")
     if d.apply_sense_mask or d.agents_die:
         raise NotImplementedError("apply_sense_mask / agents_die are off by default in the reference and "
                                   "not implemented on the GPU path")
@@ -128,6 +128,7 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
         logging.warning(f'Unfamiliar boundary condition: {d.boundary}! Doing nothing with boundary...')
         c.boundary = _lib.BOUNDARY_NONE
     c.food_infinite = int(bool(d.food_infinite))
+    c.diffuse_mode = _lib.DIFFUSE_MODES[d.diffuse_mode]
     return c
 
 

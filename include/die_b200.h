@@ -38,6 +38,13 @@ extern "C" {
 
 #define DIE_MAX_RADIUS  8   /* blur radius int(4*sigma+.5) <= 8  <=>  sigma <= 2.1 */
 
+/* Dynamics.diffuse_mode: the `mode` skimage.filters.gaussian hands to scipy.ndimage (core/env.py:140-143) */
+#define DIE_DIFFUSE_WRAP      0   /* the reference's default */
+#define DIE_DIFFUSE_REFLECT   1
+#define DIE_DIFFUSE_NEAREST   2
+#define DIE_DIFFUSE_MIRROR    3
+#define DIE_DIFFUSE_CONSTANT  4   /* cval = 0 */
+
 #define DIE_BOUNDARY_WRAP   0   /* BoundaryCondition.wrap  core/env.py:154-155 */
 #define DIE_BOUNDARY_LIMIT  1   /* BoundaryCondition.limit core/env.py:156-157 */
 #define DIE_BOUNDARY_NONE   2   /* unknown enum: warn + leave as is, core/env.py:158-161 */
@@ -46,7 +53,7 @@ extern "C" {
  * two operators: linear_action_cost (weights 0.02, 0.01; core/env.py:29-35) and zero_cost
  * (both weights 0; core/env.py:38-39).  op_food_flow is identity (core/env.py:45).
  * blur_w holds the 2*blur_radius+1 weights scipy.ndimage.gaussian_filter1d builds for
- * diffuse_sigma (w[k] = exp(-.5/sigma^2 k^2)/sum, k=-r..r); diffuse_mode is 'wrap'. */
+ * diffuse_sigma (w[k] = exp(-.5/sigma^2 k^2)/sum, k=-r..r). */
 typedef struct die_dynamics {
     double  rate_feed;
     double  rate_decay_chem;
@@ -56,7 +63,7 @@ typedef struct die_dynamics {
     int32_t blur_radius;
     int32_t boundary;
     int32_t food_infinite;
-    int32_t reserved;
+    int32_t diffuse_mode;     /* DIE_DIFFUSE_*; 0 = 'wrap' */
 } die_dynamics_t;
 
 /* GradientAgent / PhysarumAgent constructor state, core/agent/gradient.py:19-45,139-163. */

@@ -74,8 +74,10 @@ def test_dynamics_rejects_what_is_not_on_the_gpu_path():
     from die_b200 import env as E
     with pytest.raises(NotImplementedError):
         E._dynamics_to_c(E.Dynamics(op_action_cost=lambda a: 0))
-    with pytest.raises(NotImplementedError):
-        E._dynamics_to_c(E.Dynamics(diffuse_mode='reflect'))
+    with pytest.raises(ValueError):
+        E._dynamics_to_c(E.Dynamics(diffuse_mode='periodic'))
+    assert [E._dynamics_to_c(E.Dynamics(diffuse_mode=m)).diffuse_mode
+            for m in ('wrap', 'reflect', 'nearest', 'mirror', 'constant')] == [0, 1, 2, 3, 4]
     with pytest.raises(NotImplementedError):
         E._dynamics_to_c(E.Dynamics(diffuse_sigma=5.0))
     assert E._dynamics_to_c(E.Dynamics(op_action_cost=E.zero_cost)).cost_w_dist == 0.0

@@ -113,3 +113,43 @@ def test_unsupported_flows_are_refused():
     seq = D.WaveSequence((8, 8))
     with pytest.raises(ValueError):
         D.Env((16, 16), D.Dynamics(op_food_flow=seq.get_flow_operator()))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Dynamics.diffuse_mode: every boundary extension skimage.filters.gaussian / scipy.ndimage offers
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ['reflect', 'nearest', 'mirror', 'constant', 'wrap'])
+@pytest.mark.parametrize("field,sigma", [((40, 56), 0.5), ((33, 70), 0.8), ((5, 7), 0.5), ((64, 64), 1.6), ((5, 7), 1.6)])
+def test_diffuse_modes_bit_exact(mode, field, sigma):
+    """Brownian free run (only +,-,*,/ on the path): every field must equal scipy's blur with that mode bit for bit;
+    a Physarum agent is then run for a few steps so that the published gradient is exercised under the mode too."""
+    import die_b200 as D
+    (ref,), gpu = make_pair(field, seed=6, ratio=0.3, dynamics_kw=dict(diffuse_mode=mode, diffuse_sigma=sigma))
+    ra, ga = R.BrownianAgent(0.05, 1.0), D.BrownianAgent(move_scale=0.05, deposit_scale=1.0)
+    m = ref.agents.shape[-1]
+    rng = np.random.default_rng(4)
+    robs, gobs = ref._get_current_obs, gpu._get_current_obs
+    for it in range(15):
+        u = rng.random((3, m))
+        ract, gact = ra.forward(robs, u=u), ga.forward(gobs, u=u)
+        robs, rr, *_ = ref.step(ract)
+        gobs, gr, *_ = gpu.step(gact)
+        assert_state_equal(ref, *gpu.get_state(), float_exact=True)
+    R.set_math_backend('portable')
+    try:
+        kw = dict(scale=0.02, turn_angle=30, sense_offset=0.06)
+        from tests._parity import lattice_theta
+        theta0, prev = lattice_theta(m, 30, 6)
+        rp, gp = R.PhysarumAgent(max_agents=m, prev_grad=prev, **kw), D.PhysarumAgent(max_agents=m, **kw)
+        gp.set_state(theta=theta0)
+        for it in range(8):
+            coin = rng.integers(0, 2, m)
+            ract = rp.forward(robs, coin=coin.copy())
+            gact = gp.forward(gobs, coin=coin)
+            assert np.array_equal(ract, gact.cpu().numpy()), (mode, it)
+            robs, *_ = ref.step(ract)
+            gobs, *_ = gpu.step(gact)
+            assert_state_equal(ref, *gpu.get_state(), float_exact=True)
+        assert gp.last_hints == (True, True)
+    finally:
+        R.set_math_backend('numpy')
