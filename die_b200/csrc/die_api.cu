@@ -429,6 +429,46 @@ extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium
 }
 
 // ------------------------------------------------------------------------------------------
+// Env._get_sensed_medium with Dynamics.apply_sense_mask (core/env.py:275-294)
+// ------------------------------------------------------------------------------------------
+template <int R>
+static cudaError_t launch_sense_mask(const double* medium, double* obs, int H, int W, int B,
+                                     const BlurWeights& bw, cudaStream_t st) {
+    constexpr int TH = 32, TW = 64, NT = 256;
+    const int tiles_i = (H + TH - 1) / TH, tiles_j = (W + TW - 1) / TW;
+    const size_t smem = sizeof(double) * (size_t)((TH + 2 * R) * (TW + 2 * R) + TH * (TW + 2 * R));
+    auto kern = sense_mask_kernel<R, TH, TW, NT>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<(unsigned)((int64_t)tiles_i * tiles_j * B), NT, smem, st>>>(medium, obs, H, W, tiles_i, tiles_j, bw);
+    return cudaGetLastError();
+}
+
+extern "C" int die_sense_mask(int32_t H, int32_t W, int32_t B, const double* weights, int32_t radius,
+                              const double* medium, double* obs, void* stream) {
+    DIE_REQUIRE(H >= 1 && W >= 1 && B >= 1 && (int64_t)H * W <= 0x7fffffffLL);
+    DIE_REQUIRE(weights != nullptr && medium != nullptr && obs != nullptr && medium != obs);
+    DIE_REQUIRE(radius >= 1 && radius <= DIE_MAX_RADIUS);
+    BlurWeights bw;
+    memset(&bw, 0, sizeof(bw));
+    for (int k = 0; k < 2 * radius + 1; ++k) bw.w[k] = weights[k];
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err = cudaErrorInvalidValue;
+    switch (radius) {
+        case 1: err = launch_sense_mask<1>(medium, obs, H, W, B, bw, st); break;
+        case 2: err = launch_sense_mask<2>(medium, obs, H, W, B, bw, st); break;
+        case 3: err = launch_sense_mask<3>(medium, obs, H, W, B, bw, st); break;
+        case 4: err = launch_sense_mask<4>(medium, obs, H, W, B, bw, st); break;
+        case 5: err = launch_sense_mask<5>(medium, obs, H, W, B, bw, st); break;
+        case 6: err = launch_sense_mask<6>(medium, obs, H, W, B, bw, st); break;
+        case 7: err = launch_sense_mask<7>(medium, obs, H, W, B, bw, st); break;
+        case 8: err = launch_sense_mask<8>(medium, obs, H, W, B, bw, st); break;
+    }
+    DIE_CUDA(err);
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Agent.forward
 // ------------------------------------------------------------------------------------------
 extern "C" int die_brownian_forward(const double* agents, double* action, int64_t M, int32_t B,

@@ -413,6 +413,62 @@ field_march_kernel(const FieldArgs a, const MarchGeom geo) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Env._get_sensed_medium / _get_sense_mask (core/env.py:275-294), Dynamics.apply_sense_mask:
+//   mask = ceil(round(gaussian(occupancy, sigma=2.0), 3));   obs_medium = medium.where(mask, other=0.)
+// skimage's default mode is 'nearest' and truncate 4.0, i.e. a radius-8 blur with clamped borders, in
+// scipy's operation order (as the diffusion pass above); round(v, 3) = rint(v * 1000) / 1000.
+// One CTA per TH x TW tile: stage the clamped halo tile of the occupancy channel, two 1-D passes,
+// then the three channels of the tile are copied or zeroed.
+// ---------------------------------------------------------------------------------------------
+template <int R, int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT)
+sense_mask_kernel(const double* __restrict__ medium, double* __restrict__ obs, int H, int W,
+                  int tiles_i, int tiles_j, const BlurWeights bw) {
+    constexpr int LW = TW + 2 * R, LH = TH + 2 * R;
+    extern __shared__ double smem[];
+    double* s_in = smem;                     // [LH][LW]
+    double* s_v = smem + LH * LW;            // [TH][LW]
+    const int64_t C = (int64_t)H * W;
+    const int tiles = tiles_i * tiles_j;
+    const int64_t b = blockIdx.x / (unsigned)tiles;
+    const int t = blockIdx.x - (int)b * tiles;
+    const int ti = t / tiles_j, tj = t - ti * tiles_j;
+    const int i0 = ti * TH, j0 = tj * TW;
+    const double* med = medium + b * 3 * C;
+    double* out = obs + b * 3 * C;
+
+    for (int idx = threadIdx.x; idx < LH * LW; idx += NT) {
+        const int r = idx / LW, c = idx - r * LW;
+        const int gi = min(max(i0 - R + r, 0), H - 1), gj = min(max(j0 - R + c, 0), W - 1);     // 'nearest'
+        s_in[idx] = med[(int64_t)gi * W + gj];                                                 // channel 0: occupancy
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * LW; idx += NT) {
+        const int r = idx / LW, c = idx - r * LW;
+        const double* p = s_in + (r + R) * LW + c;
+        double acc = p[0] * bw.w[R];
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc += (p[-k * LW] + p[k * LW]) * bw.w[R - k];
+        s_v[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+        const int r = idx / TW, c = idx - r * TW;
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi < H && gj < W) {
+            const double* p = s_v + r * LW + c + R;
+            double acc = p[0] * bw.w[R];
+#pragma unroll
+            for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * bw.w[R - k];
+            const bool seen = ceil(rint(acc * 1000.0) / 1000.0) != 0.0;
+            const int64_t g = (int64_t)gi * W + gj;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) out[ch * C + g] = seen ? med[ch * C + g] : 0.0;
+        }
+    }
+}
+
 // No diffusion (blur_radius == 0): gaussian with radius 0 is the identity (w = [1]).
 template <int NT>
 __global__ void __launch_bounds__(NT)

@@ -106,9 +106,9 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
                                   "(and PerlinNoiseSequence, whose third-party noise is unseeded) are not supported")
     if d.diffuse_mode not in _lib.DIFFUSE_MODES:
         raise ValueError(f"diffuse_mode must be one of {sorted(_lib.DIFFUSE_MODES)} (scipy.ndimage's modes)")
-    if d.apply_sense_mask or d.agents_die:
-        raise NotImplementedError("apply_sense_mask / agents_die are off by default in the reference and "
-                                  "not implemented on the GPU path")
+    if d.agents_die:
+        raise NotImplementedError("agents_die is off by default in the reference (and broken there: core/env.py:250 "
+                                  "rebinds self.agents while AgentIndexer keeps the old array) -- not on the GPU path")
     c = _lib.DieDynamics()
     c.rate_feed = d.rate_feed
     c.rate_decay_chem = d.rate_decay_chem
@@ -223,6 +223,12 @@ class Env:
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
             self._install_food_flow()
+            # Dynamics.apply_sense_mask: the observation is a masked COPY of the medium (core/env.py:275-294)
+            self._obs_buf = None
+            if self.dynamics.apply_sense_mask:
+                self._obs_buf = [torch.empty_like(first), torch.empty_like(first)]
+                self._sense_w = np.ascontiguousarray(gaussian_kernel1d(2.0), dtype=np.float64)
+                self._refresh_sensed_medium()
             self._publish_grad = False
             self._hint_state = None         # (medium ptr, medium version, agents version, grad published)
             self._speculation = None        # (action ptr, action version, agents version) of a pending fused move
@@ -245,6 +251,16 @@ class Env:
         _lib.check(self._lib.die_env_set_food_flow(
             self._handle, tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
             ts.ctypes.data, len(ts), op.calls % len(ts), op.scale, op.decay))
+
+    def _refresh_sensed_medium(self) -> None:
+        """obs medium = medium.where(sense_mask, 0.) for the current medium (die_sense_mask)."""
+        w = self._sense_w
+        h, wd = self._field_size
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.die_sense_mask(h, wd, self._B, w.ctypes.data, (len(w) - 1) // 2,
+                                                self._medium_buf[self._cur].data_ptr(),
+                                                self._obs_buf[self._cur].data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
 
     def __del__(self):
         try:
@@ -291,7 +307,9 @@ class Env:
 
     @property
     def _get_current_obs(self) -> ObsType:
-        """core/env.py:296-298."""
+        """core/env.py:296-298: (the live agents, the sensed medium)."""
+        if self._obs_buf is not None:
+            return self.agents, self._unbatch(self._obs_buf[self._cur])
         return self.agents, self.medium
 
     def get_state(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -302,6 +320,8 @@ class Env:
         if medium is not None:
             src = torch.as_tensor(np.asarray(medium, dtype=np.float64)).reshape(self._medium_buf[0].shape)
             self._medium_buf[self._cur].copy_(src)
+            if self._obs_buf is not None:
+                self._refresh_sensed_medium()
         if agents is not None:
             src = torch.as_tensor(np.asarray(agents, dtype=np.float64)).reshape(self._agents.shape)
             self._agents.copy_(src)
@@ -351,6 +371,8 @@ class Env:
 
     # -- fast-path hints for Agent.forward (see die_b200/_hints.py) ---------------------------------
     def _after_step(self) -> None:
+        if self._obs_buf is not None:
+            self._refresh_sensed_medium()
         buf = self._medium_buf[self._cur]
         self._hint_state = (buf.data_ptr(), buf._version, self._agents._version, self._publish_grad)
         _hints.publish(self, buf)
@@ -452,12 +474,16 @@ class Env:
             _lib.check(self._lib.die_env_step_host(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
                 self._agents.data_ptr(), src.ctypes.data,
-                hb['agents'].data_ptr(), med_t.data_ptr(),
+                hb['agents'].data_ptr(), med_t.data_ptr() if self._obs_buf is None else None,
                 hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
         self._cur = nxt
         if self._flow_tables is not None:
             self.dynamics.op_food_flow.calls += 1
         self._after_step()
+        if self._obs_buf is not None:              # the host observation is the masked medium, too
+            with torch.cuda.device(self.device):
+                med_t.copy_(self._obs_buf[self._cur], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         obs = (self._unbatch(hb['agents'].numpy()), self._unbatch(med_t.numpy()))
         return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))
 

@@ -145,6 +145,14 @@ int die_env_step_host(die_env_t* env, double* medium_in_dev, double* medium_out_
                       double* agents_host, double* medium_host,
                       double* reward_host, int64_t* alive_host, void* stream);
 
+/* Env._get_sensed_medium with Dynamics.apply_sense_mask (core/env.py:275-294): the observation's medium is
+ *     medium.where(ceil(round(gaussian(medium['agents'], sigma=2.0), 3)), other=0.)
+ * i.e. every channel zeroed outside the blurred neighbourhood of the agents.  weights_host[2*radius+1] = the
+ * scipy.ndimage weights of that gaussian (sigma 2 -> radius 8); borders are clamped (skimage's default
+ * mode='nearest').  medium_dev [B][3][H][W] -> obs_dev [B][3][H][W] (a different buffer). */
+int die_sense_mask(int32_t H, int32_t W, int32_t B, const double* weights_host, int32_t radius,
+                   const double* medium_dev, double* obs_dev, void* stream);
+
 /* BrownianAgent.forward, core/agent/static.py:40-50 (+ core/data_init.py:159-169,218-220,
  * 248-253).  u_dev[B][3][M] = the three uniform draws in the reference's order
  * (dx, dy, deposit1); NULL = draw in-kernel (Philox4x32-10 keyed on seed, step, slot). */
