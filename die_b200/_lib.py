@@ -77,6 +77,7 @@ SIGNATURES = {
     "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_sense_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P]),
+    "die_render_frames": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, C.c_double, _P, _P, _P, _P]),
     "die_brownian_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P,
                                        C.c_uint64, C.c_uint64, _P]),
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),

@@ -469,6 +469,29 @@ extern "C" int die_sense_mask(int32_t H, int32_t W, int32_t B, const double* wei
 }
 
 // ------------------------------------------------------------------------------------------
+// EnvRenderer.render (core/render.py:76-132)
+// ------------------------------------------------------------------------------------------
+extern "C" int die_render_frames(int32_t H, int32_t W, int64_t M, int32_t B,
+                                 const double* medium, const double* agents, double* trace, double decay,
+                                 const double* color_host, double* img_medium, double* img_agents, void* stream) {
+    DIE_REQUIRE(H >= 1 && W >= 1 && B >= 1 && (int64_t)H * W <= 0x7fffffffLL);
+    DIE_REQUIRE(medium != nullptr && trace != nullptr && img_medium != nullptr);
+    DIE_REQUIRE(img_agents == nullptr || (agents != nullptr && M == (int64_t)H * W));
+    RenderArgs a;
+    memset(&a, 0, sizeof(a));
+    a.medium = medium; a.agents = agents; a.trace = trace; a.img_medium = img_medium; a.img_agents = img_agents;
+    a.H = H; a.W = W; a.M = M; a.decay = decay;
+    if (color_host != nullptr) {
+        a.use_color = 1;
+        for (int k = 0; k < 3; ++k) a.color[k] = color_host[k];
+    }
+    const int64_t total = (int64_t)H * W * B;
+    render_frames_kernel<<<grid_for(total, 256, 148), 256, 0, (cudaStream_t)stream>>>(a, total);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Agent.forward
 // ------------------------------------------------------------------------------------------
 extern "C" int die_brownian_forward(const double* agents, double* action, int64_t M, int32_t B,

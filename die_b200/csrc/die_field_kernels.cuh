@@ -469,6 +469,58 @@ sense_mask_kernel(const double* __restrict__ medium, double* __restrict__ obs, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// EnvRenderer.render (core/render.py:76-132) + FieldTrace.update (:9-29): the three frames of one step in
+// one pass, for plotting / GIF export (the step either side of the hot path).
+//   medium frame  [H][W][3]   (agents, env_food, chem1) interleaved; optional colour rotation
+//                             rgb -> cross(color, rgb) (RendererBase._set_colors, :47-58)
+//   trace         [H][W]      trace = trace * decay + occupancy  (in place; the caller colour-maps it)
+//   agents frame  [Wd][Ht][4] (0, agent_food, 0, alive != 0) with the reference's reshape
+//                             (2, height, -1) -> transpose(1, 2, 0), where width, height = field_size
+// One thread per cell (and per agent slot: the agents frame needs M == H*W, as in the reference).
+// ---------------------------------------------------------------------------------------------
+struct RenderArgs {
+    const double* medium;     // [B][3][H][W]
+    const double* agents;     // [B][4][M]
+    double* trace;            // [B][H][W] in/out
+    double* img_medium;       // [B][H][W][3]
+    double* img_agents;       // [B][M][4] == [B][height = W][M / W][4], or null
+    int H, W;
+    int64_t M;
+    double decay;
+    int use_color;
+    double color[3];          // normalised
+};
+
+__global__ void __launch_bounds__(256)
+render_frames_kernel(const RenderArgs a, int64_t total) {
+    const int64_t C = (int64_t)a.H * a.W;
+    for (int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * 256) {
+        const int64_t b = gid / C, g = gid - b * C;
+        const double* med = a.medium + b * 3 * C;
+        const double r = med[g], gr = med[C + g], bl = med[2 * C + g];
+        double* px = a.img_medium + (b * C + g) * 3;
+        if (a.use_color) {            // np.cross(color, rgb): (c1 b2 - c2 b1, c2 b0 - c0 b2, c0 b1 - c1 b0)
+            px[0] = a.color[1] * bl - a.color[2] * gr;
+            px[1] = a.color[2] * r - a.color[0] * bl;
+            px[2] = a.color[0] * gr - a.color[1] * r;
+        } else {
+            px[0] = r;
+            px[1] = gr;
+            px[2] = bl;
+        }
+        a.trace[gid] = a.trace[gid] * a.decay + r;
+        if (a.img_agents != nullptr) {          // slot g of the (2, M) block -> pixel g of the [W][M/W] image
+            const double* ag = a.agents + b * 4 * a.M;
+            double* q = a.img_agents + (b * a.M + g) * 4;
+            q[0] = 0.0;
+            q[1] = ag[3 * a.M + g];
+            q[2] = 0.0;
+            q[3] = (ag[2 * a.M + g] != 0.0) ? 1.0 : 0.0;
+        }
+    }
+}
+
 // No diffusion (blur_radius == 0): gaussian with radius 0 is the identity (w = [1]).
 template <int NT>
 __global__ void __launch_bounds__(NT)

@@ -507,9 +507,15 @@ class Env:
         _lib.check(self._lib.die_env_kernel_times(self._handle, ms, _lib.C.byref(n)))
         return dict(zip(self.STEP_KERNELS, list(ms))), int(n.value)
 
-    def render(self):
-        """core/env.py:133-134 -- visualisation is out of scope of the hot path."""
-        raise NotImplementedError("rendering is not part of the B200 hot path; read env.medium / env.agents")
+    def render(self, host: bool = False):
+        """core/env.py:133-134: the frames of EnvRenderer.render(medium, agents) (die_b200/render.py), device tensors
+        by default, numpy arrays in pinned memory with ``host=True``."""
+        if getattr(self, '_renderer', None) is None or self._renderer._B != self._B:
+            from .render import EnvRenderer
+            self._renderer = EnvRenderer(self._field_size, field_colors_id='rgb', batch=self._B, device=self.device)
+        med, ag = self._medium_buf[self._cur], self._agents
+        frames = self._renderer.render_host(med, ag) if host else self._renderer.render(med, ag)
+        return frames if self._batched else [f[0] if f is not None else None for f in frames]
 
 
 class _DevicePtrView:

@@ -153,6 +153,17 @@ int die_env_step_host(die_env_t* env, double* medium_in_dev, double* medium_out_
 int die_sense_mask(int32_t H, int32_t W, int32_t B, const double* weights_host, int32_t radius,
                    const double* medium_dev, double* obs_dev, void* stream);
 
+/* EnvRenderer.render + FieldTrace.update (core/render.py:9-29, 76-132): the frames of one step, on the device.
+ *   img_medium_dev [B][H][W][3] = (agents, env_food, chem1) per pixel, or cross(color, rgb) when color_host[3]
+ *                                 (normalised) is given (RendererBase._set_colors);
+ *   trace_dev      [B][H][W]    = trace * decay + occupancy, in place (decay = 1 - 1/trace_steps); the caller
+ *                                 colour-maps it (matplotlib's LUT is not part of this library);
+ *   img_agents_dev [B][M][4]    = (0, agent_food, 0, alive != 0) per slot -- with M == H*W this IS the reference's
+ *                                 (2, height, -1) -> transpose(1, 2, 0) image [W][H][4]; NULL to skip. */
+int die_render_frames(int32_t H, int32_t W, int64_t M, int32_t B,
+                      const double* medium_dev, const double* agents_dev, double* trace_dev, double decay,
+                      const double* color_host, double* img_medium_dev, double* img_agents_dev, void* stream);
+
 /* BrownianAgent.forward, core/agent/static.py:40-50 (+ core/data_init.py:159-169,218-220,
  * 248-253).  u_dev[B][3][M] = the three uniform draws in the reference's order
  * (dx, dy, deposit1); NULL = draw in-kernel (Philox4x32-10 keyed on seed, step, slot). */

@@ -629,6 +629,40 @@ class PhysarumAgent(GradientAgent):
         return self._deposit * sensed_food * mask
 
 
+# --------------------------------------------------------------------------------------
+# Rendering (core/render.py) -- the frames before any matplotlib colour map
+# --------------------------------------------------------------------------------------
+
+class EnvRenderer:
+    """core/render.py:76-132 + FieldTrace (:9-29) + RendererBase._set_colors (:47-58)."""
+
+    field_colors = {'rgb': None, 'one': [0.19, -0.3, 0.74], 'two': [-0.45, 0.65, 0.83]}
+
+    def __init__(self, field_size, field_colors_id: str = 'rgb', trace_steps: int = 8):
+        self.field_size = tuple(field_size)
+        self._decay = 1 - 1 / trace_steps
+        self._trace = np.zeros(self.field_size)
+        color = self.field_colors.get(field_colors_id)
+        self._color = None
+        if color is not None:
+            color = np.array(color, dtype=np.float64)
+            color /= np.linalg.norm(color)
+            self._color = color
+
+    def render(self, medium: np.ndarray, agents: np.ndarray):
+        """-> [medium frame (H, W, 3), trace (H, W) (the reference colour-maps it), agents frame (W, M/W, 4)]."""
+        rgb = np.stack([medium[CH_OCC], medium[CH_FOOD], medium[CH_CHEM]], axis=-1)
+        if self._color is not None:
+            rgb = np.cross(self._color, rgb, axisb=-1)
+        self._trace = self._trace * self._decay + medium[CH_OCC]            # FieldTrace.update
+        width, height = self.field_size
+        data = agents[[AG_ALIVE, AG_FOOD]].reshape((2, height, -1)).transpose((1, 2, 0))
+        alive_mask = data[:, :, 0].astype(bool)
+        zero = np.zeros(alive_mask.shape)
+        img_agents = np.stack([zero, data[:, :, 1], zero, alive_mask], axis=-1)
+        return [rgb, self._trace, img_agents]
+
+
 def run(env: Env, agent, iters: int):
     """The canonical caller, examples/minimal_run.py:14-29 without plotting."""
     total = 0.

@@ -126,3 +126,26 @@ def test_oracle_equals_reference_executed_live(kind, size, steps, seed, dyn, akw
         assert np.array_equal(robs[1].values, oobs[1])
         if kind == "physarum":
             assert np.array_equal(ra._direction_rads, oa._direction_rads)
+
+
+@pytest.mark.skipif(not run_reference.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("colors", ['rgb', 'one', 'two'])
+def test_oracle_renderer_equals_reference_executed_live(colors):
+    """core/render.py's EnvRenderer (own source, over the stand-in packages; its matplotlib colour map aside) vs the
+    oracle's restatement: medium frame, agent trace and agents frame over several steps, non-square field."""
+    ref = run_reference.load()
+    import core.render as render
+    size = (24, 40)
+    np.random.seed(9)
+    renv = ref.Env(size, ref.Dynamics(init_agent_ratio=0.2))
+    rr = render.EnvRenderer(size, field_colors_id=colors)
+    orr = R.EnvRenderer(size, field_colors_id=colors)
+    agent = ref.BrownianAgent(move_scale=0.02)
+    obs = renv._get_current_obs
+    for it in range(6):
+        frames = orr.render(renv.medium.values, renv.agents.values)
+        assert np.array_equal(rr._upd_img_medium(renv.medium), frames[0])
+        rr._agent_trace.update(renv.medium.sel(channel='agents'))
+        assert np.array_equal(np.asarray(rr._agent_trace.as_mask()), frames[1])
+        assert np.array_equal(rr._upd_img_agents(renv.agents), frames[2])
+        obs, *_ = renv.step(agent.forward(obs))
