@@ -104,6 +104,8 @@ __device__ __forceinline__ int extend_index(int i, int n, int mode) {
 //   s_v   [(TH+2G)][(TW+2G+2R)]     after the axis-0 pass
 // Staging is done in two sweeps so that all of a thread's (independent) chem + claim loads are
 // in flight before the first dependent deposit gather.
+// (register caps were tried: 40 / 48 / 56 / 72 registers give 299 / 279 / 250 / 273 us at 4096^2; the compiler's own
+//  choice without a minimum-blocks hint, 60 registers = 4 CTAs per SM, is the best at 241 us)
 template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
