@@ -144,7 +144,10 @@ __device__ __forceinline__ double apply_boundary(double v, int boundary) {
 // Software pipeline: the coalesced loads (x, y, theta, cached cell) of item k+1 are issued before the
 // arithmetic of item k, and the food gather of item k right at its start, so the only exposed memory
 // latency per item is the gradient gather at the sensed cell.
-template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB>
+// LEAN: the steady-state configuration of the Physarum loop is known at compile time -- in-kernel Philox coins, no
+// momentum state, no recorded sense cells, the env's published gradient and cell cache valid -- so the per-item null
+// checks and parameter reloads of the general kernel fold away.  Same arithmetic, same results.
+template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false>
 __global__ void __launch_bounds__(kAgentThreads, MINB)
 gradient_forward_kernel(const GradientArgs a) {
     const die_gradient_params_t& p = a.p;
@@ -161,24 +164,24 @@ gradient_forward_kernel(const GradientArgs a) {
     const double* chem = a.medium + (ch.b * 3 + 2) * C;
     double* th_p = a.theta + ch.b * M + first;
     double* ab = a.action + ch.b * 3 * M + first;
-    double* pg = (a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M + first : nullptr;
-    const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
-    const double* nz = (a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
-    int32_t* sc_p = (a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
-    const double2* grad = (a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
-    const int32_t* cl_p = (a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
+    double* pg = (!LEAN && a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M + first : nullptr;
+    const uint8_t* coin_p = (!LEAN && a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
+    const double* nz = (!LEAN && a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
+    int32_t* sc_p = (!LEAN && a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
+    const double2* grad = (LEAN || a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
+    const int32_t* cl_p = (LEAN || a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
     int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
     int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
     // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
     const uint32_t* bits_p = MOVE ? a.alive_bits + ch.b * a.Mw + (first >> 5) : nullptr;
 
     uint32_t coin_bits = 0;
-    if (DISCRETE_TURN && coin_p == nullptr)      // coin of slot (CTA, t, k) = bit k of this word
+    if (DISCRETE_TURN && (LEAN || coin_p == nullptr))      // coin of slot (CTA, t, k) = bit k of this word
         coin_bits = philox_draw(a.seed, a.step, (uint64_t)blockIdx.x * kAgentThreads + threadIdx.x, 2u).x;
     const double atol = p.turn_radians * p.turn_tolerance;
     // with an identity momentum step (no inertia, no noise) and a unit-length direction the new
     // heading angle(cos d + i sin d) comes out of die_sincos_angle together with cos d, sin d
-    const bool fused_heading = DISCRETE_TURN && pg == nullptr && p.normalized_grad;
+    const bool fused_heading = LEAN || (DISCRETE_TURN && pg == nullptr && p.normalized_grad);
 
     bool nvalid = first < M;
     double nx = 0.0, ny = 0.0, nth = 0.0;
@@ -187,7 +190,7 @@ gradient_forward_kernel(const GradientArgs a) {
         nx = ag_x[0];
         ny = ag_x[M];
         nth = th_p[0];
-        if (cl_p != nullptr) ncell = cl_p[0];
+        if (LEAN || cl_p != nullptr) ncell = cl_p[0];
     }
 
     for (int k = 0; k < kFwdItems; ++k) {
@@ -195,7 +198,7 @@ gradient_forward_kernel(const GradientArgs a) {
         const int i = k * kAgentThreads;                       // offset from this thread's first slot
         const double x = nx, y = ny, th = nth;
         // food under the agent (:113-115), issued first: independent of the turn arithmetic
-        const int here = (cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
+        const int here = (LEAN || cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
         const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : food[here];
         uint32_t alive_word = 0;
         if (MOVE) alive_word = bits_p[i >> 5];
@@ -204,7 +207,7 @@ gradient_forward_kernel(const GradientArgs a) {
             nx = ag_x[i + kAgentThreads];
             ny = ag_x[M + i + kAgentThreads];
             nth = th_p[i + kAgentThreads];
-            if (cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
+            if (LEAN || cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
         }
 
         // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
@@ -218,9 +221,9 @@ gradient_forward_kernel(const GradientArgs a) {
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
         const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
-        if (sc_p != nullptr) sc_p[i] = sc;
+        if (!LEAN && sc_p != nullptr) sc_p[i] = sc;
         double gx, gy;
-        if (SLAB ? a.st.grad != nullptr : grad != nullptr) {   // published by the field pass: one 16-byte gather
+        if (LEAN || (SLAB ? a.st.grad != nullptr : grad != nullptr)) {   // published by the field pass: one 16-byte gather
             // read-only for the whole launch: ld.global.nc lets L1 cache lines that live on a peer GPU
             // (the ghost slots of every rank all look at the same few cells near the corners)
             const double2 g2 = SLAB ? slab_load_grad(a.st, a.sg, sc) : grad[sc];
@@ -248,13 +251,13 @@ gradient_forward_kernel(const GradientArgs a) {
             // the rest (about one warp in 300) runs the reference's own arithmetic, die_turn_exact.
             die_turn_t tr;
             double dr = 1.0;
-            if (!(a.plan.enabled && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
+            if (!((LEAN || a.plan.enabled) && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
                 // _get_gradient (:59-65): scipy.linalg.norm, nan_to_num(grad / norm), grad *= (norm >= clip)
                 die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
                 if (!p.normalized_grad) dr = hypot(gx, gy);
                 tr = die_turn_exact(gx, gy, th, atol, p.sense_radians);
             }
-            const int c = (coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
+            const int c = (!LEAN && coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
             double turn = (tr.turn != 0) ? (double)tr.turn : ((double)c - 0.5) * 2.0;
             turn *= p.turn_radians;
             deposit_mask = tr.deposit_mask != 0;
@@ -269,7 +272,7 @@ gradient_forward_kernel(const GradientArgs a) {
         }
 
         // _process_momentum (:82-91)
-        if (pg != nullptr) {
+        if (!LEAN && pg != nullptr) {
             gx = (1.0 - p.inertia) * gx + p.inertia * pg[i];
             gy = (1.0 - p.inertia) * gy + p.inertia * pg[M + i];
             if (nz != nullptr) {

@@ -234,7 +234,8 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     a.tiles_j = (a.W + TW - 1) / TW;
     const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
-    auto kern = field_step_kernel<R, TH, TW, NT, GRAD, false>;
+    const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr;
+    auto kern = plain ? field_step_kernel<R, TH, TW, NT, GRAD, false, true> : field_step_kernel<R, TH, TW, NT, GRAD, false, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     const int64_t grid = (int64_t)a.tiles_i * a.tiles_j * B;
@@ -520,6 +521,7 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
 }
 
 static int g_turn_quick = 1;       // 0: every slot runs die_turn_exact (diagnosis / A-B tests; same results)
+static int g_fwd_lean = 1;         // use the LEAN instantiation of the forward kernel when its preconditions hold
 static int g_fwd_min_blocks = 4;   // register cap of the forward kernel (3 / 4 / 5 resident CTAs per SM)
 
 extern "C" int die_set_turn_quick(int32_t on) {
@@ -532,6 +534,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;
     else if (strcmp(key, "fwd_min_blocks") == 0) { DIE_REQUIRE(value >= 3 && value <= 5); g_fwd_min_blocks = value; }
     else if (strcmp(key, "feed_bits") == 0) g_feed_bits = value ? 1 : 0;
+    else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value ? 1 : 0;
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
@@ -591,6 +594,11 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     else if (g_fwd_min_blocks == 5) { DIE_PICK_FWD(5); }
     else { DIE_PICK_FWD(4); }
 #undef DIE_PICK_FWD
+    // the steady-state Physarum configuration has its own instantiation (see LEAN in die_agent_kernels.cuh)
+    const bool lean = g_fwd_lean && !speculate && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
+                      prev_grad == nullptr && coin == nullptr && noise == nullptr && sense_cells == nullptr &&
+                      a.grad != nullptr && a.cells != nullptr && g_fwd_min_blocks == 4;
+    if (lean) kern = gradient_forward_kernel<true, false, false, 4, true>;
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
     if (speculate) env->pending_move = 1;

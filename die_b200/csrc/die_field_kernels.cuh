@@ -56,9 +56,10 @@ struct FieldArgs {
 //   F_t = (1 - mix) cos(1 pi (rwave + t)) + mix (sin(pi x 3 + t) + cos(pi y 3 + t)),  mix = 0.25   (WaveSequence)
 // The cosine is die_math.h's (<= 0.7 ulp, bit-identical to the oracle's portable backend); everything
 // time-independent or separable was tabulated by numpy on the host.
+template <bool PLAIN = false>
 __device__ __forceinline__ double next_food(const FieldArgs& a, double f, double cf, int row, int col, int64_t g) {
     double food = a.food_infinite ? f : f - cf;
-    if (a.flow_rwave != nullptr) {
+    if (!PLAIN && a.flow_rwave != nullptr) {
         double sn, cs;
         die_sincos(kPi * (a.flow_rwave[g] + a.flow_t), &sn, &cs);
         const double islands = a.flow_col[col] + a.flow_row[row];
@@ -106,7 +107,8 @@ __device__ __forceinline__ int extend_index(int i, int n, int mode) {
 // in flight before the first dependent deposit gather.
 // (register caps were tried: 40 / 48 / 56 / 72 registers give 299 / 279 / 250 / 273 us at 4096^2; the compiler's own
 //  choice without a minimum-blocks hint, 60 registers = 4 CTAs per SM, is the best at 241 us)
-template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB>
+// PLAIN: the reference's default dynamics (periodic diffusion, identity food flow) known at compile time.
+template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB, bool PLAIN = false>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
     constexpr int G = GRAD ? 1 : 0;
@@ -162,13 +164,13 @@ field_step_kernel(const FieldArgs a) {
         if (idx < LH * LW) {
             const int r = idx / LW, c = idx - r * LW;
             // global row / column this staged cell stands for (periodic over the WHOLE field by default)
-            const int gi = SLAB ? wrap_index(row0 + i0 - G - R + r, H) : extend_index(i0 - G - R + r, H, a.diffuse_mode);
-            const int gj = SLAB ? wrap_index(j0 - G - R + c, W) : extend_index(j0 - G - R + c, W, a.diffuse_mode);
+            const int gi = (SLAB || PLAIN) ? wrap_index(row0 + i0 - G - R + r, H) : extend_index(i0 - G - R + r, H, a.diffuse_mode);
+            const int gj = (SLAB || PLAIN) ? wrap_index(j0 - G - R + c, W) : extend_index(j0 - G - R + c, W, a.diffuse_mode);
             const int g = gi * W + gj;
             if (SLAB) {                       // rows outside this rank's slab come from the neighbours over NVLink
                 v[s] = __ldg(slab_chan(a.st.medium_in, a.sg, 2, g));
                 w[s] = __ldg(slab_cell(a.st.claim, a.sg, g));
-            } else if (gi >= 0 && gj >= 0) {  // ('constant' extension: 0, no deposit)
+            } else if (PLAIN || (gi >= 0 && gj >= 0)) {  // ('constant' extension: 0, no deposit)
                 v[s] = chem_in[g];
                 w[s] = win[g];
             }
@@ -219,7 +221,7 @@ field_step_kernel(const FieldArgs a) {
                 const double occ = (win[g] >= 0) ? 1.0 : 0.0;
                 const double f = food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                food_out[g] = next_food(a, f, cf, li, gj, g);
+                food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
                 occ_out[g] = occ;
                 cons[g] = cf;
             }
@@ -258,7 +260,7 @@ field_step_kernel(const FieldArgs a) {
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
-            food_out[g] = next_food(a, f, cf, li, gj, g);
+            food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
             occ_out[g] = occ;
             cons[g] = cf;
         }

@@ -237,7 +237,8 @@ int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream
 int die_set_turn_quick(int32_t on);
 
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
- * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "feed_bits" 0/1 (feed kernel takes
+ * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
+ * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
  * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1. */
 int die_set_tuning(const char* key, int32_t value);
 

@@ -170,7 +170,7 @@ def test_one_agent_two_envs_never_adopts_the_wrong_speculation():
     _same(env_b, ref_b, ag, ag_ref)
 
 
-@pytest.mark.parametrize("key,values", [("turn_quick", (1, 0)), ("fwd_min_blocks", (4, 3, 5)), ("feed_bits", (1, 0)), ("field_prefetch", (1, 0))])
+@pytest.mark.parametrize("key,values", [("turn_quick", (1, 0)), ("fwd_min_blocks", (4, 3, 5)), ("feed_bits", (1, 0)), ("field_prefetch", (1, 0)), ("fwd_lean", (1, 0))])
 def test_tuning_switches_do_not_change_results(key, values):
     """Free-running 60 steps (in-kernel Philox coins, identical seeds) under every setting of a switch."""
     import die_b200 as D
@@ -184,7 +184,7 @@ def test_tuning_switches_do_not_change_results(key, values):
             m = env.max_agents
             ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
             ag.set_state(theta=lattice_theta(m, 30, 13)[0])
-            ag.fuse_move = (key != "turn_quick")          # covers the MOVE instantiations of every register cap
+            ag.fuse_move = key in ("fwd_min_blocks", "feed_bits", "field_prefetch")   # also covers the MOVE instantiations
             obs = env._get_current_obs
             total = 0.0
             for _ in range(60):
