@@ -144,6 +144,15 @@ __device__ __forceinline__ double apply_boundary(double v, int boundary) {
 // Software pipeline: the coalesced loads (x, y, theta, cached cell) of item k+1 are issued before the
 // arithmetic of item k, and the food gather of item k right at its start, so the only exposed memory
 // latency per item is the gradient gather at the sensed cell.
+// The reference arithmetic of the turn decision as an out-of-line call: it runs for about one warp in 300
+// (die_turn_quick defers to it), and kept out of line its registers (atan2, sqrt, two divisions) do not count
+// against the hot path of the LEAN kernel.
+__device__ __noinline__ die_turn_t turn_exact_call(double gx, double gy, double th, double atol, double sense_radians,
+                                                   int normalized, int use_clip, double clip) {
+    die_normalize_gradient(&gx, &gy, normalized, use_clip, clip);
+    return die_turn_exact(gx, gy, th, atol, sense_radians);
+}
+
 // LEAN: the steady-state configuration of the Physarum loop is known at compile time -- in-kernel Philox coins, no
 // momentum state, no recorded sense cells, the env's published gradient and cell cache valid -- so the per-item null
 // checks and parameter reloads of the general kernel fold away.  Same arithmetic, same results.
@@ -252,10 +261,14 @@ gradient_forward_kernel(const GradientArgs a) {
             die_turn_t tr;
             double dr = 1.0;
             if (!((LEAN || a.plan.enabled) && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
-                // _get_gradient (:59-65): scipy.linalg.norm, nan_to_num(grad / norm), grad *= (norm >= clip)
-                die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
-                if (!p.normalized_grad) dr = hypot(gx, gy);
-                tr = die_turn_exact(gx, gy, th, atol, p.sense_radians);
+                if (LEAN) {           // (normalised gradient: dr = 1)
+                    tr = turn_exact_call(gx, gy, th, atol, p.sense_radians, 1, p.use_grad_clip, p.grad_clip);
+                } else {
+                    // _get_gradient (:59-65): scipy.linalg.norm, nan_to_num(grad / norm), grad *= (norm >= clip)
+                    die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
+                    if (!p.normalized_grad) dr = hypot(gx, gy);
+                    tr = die_turn_exact(gx, gy, th, atol, p.sense_radians);
+                }
             }
             const int c = (!LEAN && coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
             double turn = (tr.turn != 0) ? (double)tr.turn : ((double)c - 0.5) * 2.0;
