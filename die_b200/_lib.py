@@ -75,6 +75,7 @@ SIGNATURES = {
     "die_env_gradient": (_P, [_P]),
     "die_env_set_profiling": (C.c_int, [_P, C.c_int32]),
     "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "die_env_read_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_sense_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "die_render_frames": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, C.c_double, _P, _P, _P, _P]),
@@ -125,6 +126,26 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` only when `device` is not already current (the context manager costs a few
+    microseconds per call, which is most of the host time of a step on a small environment)."""
+    import torch
+    if torch.cuda.current_device() == device.index:
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def check(rc: int) -> None:

@@ -133,6 +133,14 @@ class GradientAgent(_DeviceAgent):
         p.discrete_turn = int(self._discrete_turn)
         return p
 
+    def _params_cached(self) -> _lib.DieGradientParams:
+        """The C struct is rebuilt only when one of the (private) constructor parameters was changed."""
+        key = (self._scale, self._deposit, self._inertia, self._sense_offset_scale, self._noise_scale, self._grad_clip,
+               self._turn_radians, self._sense_radians, self._rtol, self._normalized, self._discrete_turn)
+        if getattr(self, '_params_key', None) != key:
+            self._params_key, self._params_struct = key, self._params_c()
+        return self._params_struct
+
     # -- forward ------------------------------------------------------------------------------
     def _upload(self, name: str, arr: np.ndarray, shape, dtype, device):
         host, dev = getattr(self, f'_{name}_host'), getattr(self, f'_{name}_dev')
@@ -175,12 +183,12 @@ class GradientAgent(_DeviceAgent):
                 self._sense_cells = torch.empty((B, M), dtype=torch.int32, device=agents.device)
             cells_ptr = self._sense_cells.data_ptr()
 
-        p = self._params_c()
+        p = self._params_cached()
         prev_ptr = self._prev_grad.data_ptr() if self._prev_grad is not None else None
         # The Env that produced this observation, if it provably did (die_b200/_hints.py): its cached cells and
         # published gradient replace gathers, and the move of the action is evaluated in the same launch.
         env = _hints.find_env(agents, medium) if self.use_env_hints else None
-        with torch.cuda.device(agents.device):
+        with _lib.on_device(agents.device):
             stream = torch.cuda.current_stream().cuda_stream
             if env is not None:
                 flags = env._forward_flags(agents, medium, want_gradient=True, speculate=self.fuse_move)

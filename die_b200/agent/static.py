@@ -77,7 +77,7 @@ class ConstAgent(_DeviceAgent):
         agents, _, _, B, M = _split_obs(obs)
         self._check(agents)
         action = self._action_for(agents)
-        with torch.cuda.device(agents.device):
+        with _lib.on_device(agents.device):
             _lib.check(self._lib.die_const_forward(action.data_ptr(), M, B, *self._data,
                                                    torch.cuda.current_stream().cuda_stream))
         return action
@@ -123,7 +123,7 @@ class BrownianAgent(_DeviceAgent):
             self._u_host.numpy()[...] = np.asarray(u, dtype=np.float64).reshape(B, 3, M)
             self._u_dev.copy_(self._u_host, non_blocking=True)
             u_ptr = self._u_dev.data_ptr()
-        with torch.cuda.device(agents.device):
+        with _lib.on_device(agents.device):
             _lib.check(self._lib.die_brownian_forward(
                 agents.data_ptr(), action.data_ptr(), M, B, self._scale, self._dep_scale,
                 u_ptr, self._seed, self._step, torch.cuda.current_stream().cuda_stream))

@@ -405,6 +405,17 @@ extern "C" int die_env_refresh_alive(die_env_t* e, const double* agents, void* s
 
 extern "C" int die_env_pending_move(const die_env_t* e) { return e ? e->pending_move : 0; }
 
+extern "C" int die_env_read_stats(die_env_t* e, const double* reward_dev, const int64_t* alive_dev,
+                                  double* reward_host, int64_t* alive_host, void* stream) {
+    DIE_REQUIRE(e != nullptr && reward_dev != nullptr && alive_dev != nullptr);
+    DIE_REQUIRE(reward_host != nullptr && alive_host != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    DIE_CUDA(cudaMemcpyAsync(reward_host, reward_dev, sizeof(double) * e->B, cudaMemcpyDeviceToHost, st));
+    DIE_CUDA(cudaMemcpyAsync(alive_host, alive_dev, sizeof(int64_t) * e->B, cudaMemcpyDeviceToHost, st));
+    DIE_CUDA(cudaStreamSynchronize(st));
+    return DIE_OK;
+}
+
 extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
                                  double* agents, const double* action_host,
                                  double* agents_host, double* medium_host,

@@ -214,7 +214,9 @@ class Env:
             self._cur = 0
             self._reward_dev = torch.zeros(B, dtype=torch.float64, device=self.device)
             self._alive_dev = torch.zeros(B, dtype=torch.int64, device=self.device)
-            self._stats_host = torch.zeros(2 * B, dtype=torch.float64).pin_memory()
+            self._reward_host = torch.zeros(B, dtype=torch.float64).pin_memory()
+            self._alive_host = torch.zeros(B, dtype=torch.int64).pin_memory()
+            self._reward_np, self._alive_np = self._reward_host.numpy(), self._alive_host.numpy()
             if self._handle is not None:
                 _lib.check(self._lib.die_env_destroy(self._handle))
                 self._handle = None
@@ -355,7 +357,7 @@ class Env:
         spec, self._speculation = self._speculation, None
         fused = (spec is not None and spec == (action.data_ptr(), action._version, self._agents._version))
         flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | _lib.STEP_ALIVE_BITS
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             self._refresh_alive(stream)
             _lib.check(self._lib.die_env_step_flags(
@@ -404,7 +406,7 @@ class Env:
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
         if speculate and agents.data_ptr() == self._agents.data_ptr() and agents.numel() == self._agents.numel():
-            with torch.cuda.device(self.device):
+            with _lib.on_device(self.device):
                 self._refresh_alive(torch.cuda.current_stream().cuda_stream)
             flags |= _lib.FWD_SPECULATE_MOVE
         return flags
@@ -424,13 +426,11 @@ class Env:
         if isinstance(action, np.ndarray):
             return self._step_host(action)
         obs, _, _ = self.step_async(action)
-        B = self._B
-        with torch.cuda.device(self.device):
-            self._stats_host[:B].copy_(self._reward_dev, non_blocking=True)
-            self._stats_host[B:].copy_(self._alive_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return (obs, *self._summarise(self._stats_host[:B].numpy().copy(),
-                                      self._stats_host[B:].numpy().astype(np.int64)))
+        with _lib.on_device(self.device):
+            _lib.check(self._lib.die_env_read_stats(
+                self._handle, self._reward_dev.data_ptr(), self._alive_dev.data_ptr(),
+                self._reward_host.data_ptr(), self._alive_host.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return (obs, *self._summarise(self._reward_np.copy(), self._alive_np.copy()))
 
     def _summarise(self, reward: np.ndarray, alive: np.ndarray):
         """core/env.py:117-131."""

@@ -137,6 +137,11 @@ const double* die_env_gradient(const die_env_t* env);
 int die_env_set_profiling(die_env_t* env, int32_t on);
 int die_env_kernel_times(die_env_t* env, double* ms_out /*[DIE_NUM_STEP_KERNELS]*/, int64_t* steps_out);
 
+/* The read-back that makes Env.step's return value (core/env.py:117-131): reward_dev[B] / alive_dev[B] of the last
+ * die_env_step -> host (pinned for full speed), then synchronises `stream`.  16 bytes per environment. */
+int die_env_read_stats(die_env_t* env, const double* reward_dev, const int64_t* alive_dev,
+                       double* reward_host, int64_t* alive_host, void* stream);
+
 /* Env.step through HOST buffers: H2D of action_host[B][3][M], the step, D2H of the new
  * observation (agents_host[B][4][M], medium_host[B][3][H][W]; either may be NULL to skip)
  * and of reward_host[B] / alive_host[B]; synchronises `stream` before returning. */
