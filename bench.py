@@ -407,8 +407,9 @@ def run_die_b200(args):
         e2e = {"value": C * B_e2e * n_gpus * k_e2e / t_e2e, "unit": UNIT, "steps": k_e2e,
                "ms_per_step": t_e2e / k_e2e * 1e3, "envs_per_gpu": B_e2e,
                "h2d_bytes_per_step": (h2d_step + fwd_h2d) * n_gpus, "d2h_bytes_per_step": (d2h_step + fwd_d2h) * n_gpus,
-               "api": "numpy obs/action across Agent.forward and Env.step (die_env_step_host); PCIe-bound, "
-                      "so measured on a bounded number of envs per GPU (pinned host memory)"}
+               "api": "numpy obs/action across Agent.forward (die_gradient_forward_host) and Env.step (die_env_step_host), "
+                      "batch cut into chunks on two streams so both PCIe directions stay busy; PCIe-bound, so measured "
+                      "on a bounded number of envs per GPU (pinned host memory)"}
         del env, agent
 
     # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------

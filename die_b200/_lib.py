@@ -84,6 +84,10 @@ SIGNATURES = {
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "die_host_ctx_create": (C.c_int, [C.POINTER(_P)]),
+    "die_host_ctx_destroy": (C.c_int, [_P]),
+    "die_gradient_forward_host": (C.c_int, [_P, C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "die_env_forward_gradient": (C.c_int, [_P, C.POINTER(DieGradientParams), _P, _P, _P, _P, _P, _P, _P, _P,
                                            C.c_int32, C.c_uint64, C.c_uint64, _P]),
     "die_env_step_flags": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),

@@ -133,6 +133,30 @@ class GradientAgent(_DeviceAgent):
         p.discrete_turn = int(self._discrete_turn)
         return p
 
+    def _host_staging(self, agents_np: np.ndarray, medium_np: np.ndarray):
+        """Device staging tensors + pinned action buffer + stream context of the host-buffer path."""
+        dev = torch.device('cuda', torch.cuda.current_device())
+        hb = self._host
+        if hb is None or hb['agents'].shape != agents_np.shape or hb['medium'].shape != medium_np.shape:
+            hb = self._host = {
+                'agents': torch.empty(agents_np.shape, dtype=torch.float64, device=dev),
+                'medium': torch.empty(medium_np.shape, dtype=torch.float64, device=dev),
+                'action': torch.empty((*agents_np.shape[:-2], 3, agents_np.shape[-1]), dtype=torch.float64).pin_memory(),
+            }
+        if getattr(self, '_host_ctx', None) is None:
+            ctx = _lib.C.c_void_p()
+            _lib.check(self._lib.die_host_ctx_create(_lib.C.byref(ctx)))
+            self._host_ctx = ctx
+        return hb['agents'], hb['medium']
+
+    def __del__(self):
+        try:
+            if getattr(self, '_host_ctx', None) is not None:
+                self._lib.die_host_ctx_destroy(self._host_ctx)
+                self._host_ctx = None
+        except Exception:
+            pass
+
     def _params_cached(self) -> _lib.DieGradientParams:
         """The C struct is rebuilt only when one of the (private) constructor parameters was changed."""
         key = (self._scale, self._deposit, self._inertia, self._sense_offset_scale, self._noise_scale, self._grad_clip,
@@ -157,9 +181,15 @@ class GradientAgent(_DeviceAgent):
                 noise: Optional[np.ndarray] = None) -> ActType:
         """core/agent/gradient.py:96-124.  ``coin`` ([B,] M in {0,1}) / ``noise`` ([B,] 2, M):
         explicitly injected draws (override ``rng``)."""
-        if isinstance(obs[0], np.ndarray):
-            return self._forward_host(obs)
-        agents, medium, _, B, M = _split_obs(obs)
+        host = isinstance(obs[0], np.ndarray)
+        if host:
+            # host-buffer path: the observation is uploaded into device staging tensors, chunk by chunk, inside
+            # die_gradient_forward_host; everything else (state, injected draws) is handled as on the device path
+            agents_np, medium_np = (np.ascontiguousarray(a, dtype=np.float64) for a in obs)
+            agents, medium = self._host_staging(agents_np, medium_np)
+        else:
+            agents, medium = obs
+        _, _, _, B, M = _split_obs((agents, medium))
         self._check(agents)
         self._check(medium)
         H, W = medium.shape[-2:]
@@ -185,6 +215,17 @@ class GradientAgent(_DeviceAgent):
 
         p = self._params_cached()
         prev_ptr = self._prev_grad.data_ptr() if self._prev_grad is not None else None
+        if host:
+            hb = self._host
+            with _lib.on_device(agents.device):
+                _lib.check(self._lib.die_gradient_forward_host(
+                    self._host_ctx, _lib.C.byref(p), H, W, M, B, agents_np.ctypes.data, medium_np.ctypes.data,
+                    agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(), prev_ptr, action.data_ptr(),
+                    hb['action'].data_ptr(), coin_ptr, noise_ptr, cells_ptr, self._seed, self._step,
+                    torch.cuda.current_stream().cuda_stream))
+            self.last_hints, self.last_speculated = (False, False), False
+            self._step += 1
+            return hb['action'].numpy()
         # The Env that produced this observation, if it provably did (die_b200/_hints.py): its cached cells and
         # published gradient replace gathers, and the move of the action is evaluated in the same launch.
         env = _hints.find_env(agents, medium) if self.use_env_hints else None

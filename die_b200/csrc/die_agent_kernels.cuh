@@ -124,6 +124,8 @@ struct GradientArgs {
     const double2* grad;        // may be null: np.gradient(chem1) per cell, published by Env.step
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
+    int b0;                     // the launch covers environments [b0, b0 + B') of a larger batch (pointers already offset):
+                                // only the in-kernel RNG needs to know, so that chunked launches draw the same numbers
     // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
     int32_t* winner;            // [B][H*W] claim table
     int32_t* cells_out;         // [B][M] post-move cell of every slot (the env's OTHER cell buffer)
@@ -186,7 +188,8 @@ gradient_forward_kernel(const GradientArgs a) {
 
     uint32_t coin_bits = 0;
     if (DISCRETE_TURN && (LEAN || coin_p == nullptr))      // coin of slot (CTA, t, k) = bit k of this word
-        coin_bits = philox_draw(a.seed, a.step, (uint64_t)blockIdx.x * kAgentThreads + threadIdx.x, 2u).x;
+        coin_bits = philox_draw(a.seed, a.step,
+                                ((uint64_t)blockIdx.x + (uint64_t)a.b0 * a.nchunk) * kAgentThreads + threadIdx.x, 2u).x;
     const double atol = p.turn_radians * p.turn_tolerance;
     // with an identity momentum step (no inertia, no noise) and a unit-length direction the new
     // heading angle(cos d + i sin d) comes out of die_sincos_angle together with cos d, sin d
@@ -292,7 +295,7 @@ gradient_forward_kernel(const GradientArgs a) {
                 gx += p.noise_scale * nz[i];
                 gy += p.noise_scale * nz[M + i];
             } else if (p.noise_scale != 0.0) {
-                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)(ch.b * M + first + i), 3u);
+                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)((ch.b + a.b0) * M + first + i), 3u);
                 const double u1 = 1.0 - u53(r.x, r.y), u2 = u53(r.z, r.w);
                 const double rad = 0.4 * sqrt(-2.0 * log(u1));
                 double sn3, cs3;

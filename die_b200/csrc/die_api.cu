@@ -55,6 +55,8 @@ struct die_env {
     int32_t* part_alive;   // [B][nblk]
     int nblk;
     double* action_stage;  // [B][3][M] device staging for die_env_step_host (lazy)
+    cudaStream_t host_streams[2];      // die_env_step_host: chunks of the batch alternate between two streams (lazy)
+    cudaEvent_t host_events[3];
     double* reward_dev;    // [B] (host path)
     int64_t* alive_dev;    // [B] (host path)
     int num_sms;
@@ -141,6 +143,8 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->part_gain);
     cudaFree(e->part_alive);
     cudaFree(e->action_stage);
+    for (int k = 0; k < 2; ++k) if (e->host_streams[k]) cudaStreamDestroy(e->host_streams[k]);
+    for (int k = 0; k < 3; ++k) if (e->host_events[k]) cudaEventDestroy(e->host_events[k]);
     cudaFree(e->reward_dev);
     cudaFree(e->alive_dev);
     if (e->prof_events != nullptr) {
@@ -273,16 +277,18 @@ extern "C" int die_set_field_impl(int32_t impl) {
     return DIE_OK;
 }
 
-static cudaError_t launch_field_any(const die_env* e, const double* min, double* mout, const double* action,
-                                    cudaStream_t st) {
+// Field pass over environments [b0, b0 + nb) of the batch; min / mout / action already point at environment b0.
+static cudaError_t launch_field_any(const die_env* e, int b0, int nb, const double* min, double* mout,
+                                    const double* action, cudaStream_t st) {
+    const size_t C = (size_t)e->H * e->W;
     FieldArgs a;
     memset(&a, 0, sizeof(a));
     a.medium_in = min;
     a.medium_out = mout;
-    a.winner = e->winner;
+    a.winner = e->winner + b0 * C;
     a.action = action;
-    a.consumed = e->consumed;
-    a.grad = (e->publish_grad && e->dyn.blur_radius > 0) ? e->grad : nullptr;
+    a.consumed = e->consumed + b0 * C;
+    a.grad = (e->publish_grad && e->dyn.blur_radius > 0) ? e->grad + b0 * C : nullptr;
     a.M = e->M;
     a.H = e->H;
     a.W = e->W;
@@ -303,18 +309,18 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
     switch (e->dyn.blur_radius) {
         case 0: {
-            const int64_t total = (int64_t)e->H * e->W * e->B;
+            const int64_t total = (int64_t)e->H * e->W * nb;
             field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
             return cudaGetLastError();
         }
-        case 1: return launch_field<1>(a, e->B, st);
-        case 2: return launch_field<2>(a, e->B, st);
-        case 3: return launch_field<3>(a, e->B, st);
-        case 4: return launch_field<4>(a, e->B, st);
-        case 5: return launch_field<5>(a, e->B, st);
-        case 6: return launch_field<6>(a, e->B, st);
-        case 7: return launch_field<7>(a, e->B, st);
-        case 8: return launch_field<8>(a, e->B, st);
+        case 1: return launch_field<1>(a, nb, st);
+        case 2: return launch_field<2>(a, nb, st);
+        case 3: return launch_field<3>(a, nb, st);
+        case 4: return launch_field<4>(a, nb, st);
+        case 5: return launch_field<5>(a, nb, st);
+        case 6: return launch_field<6>(a, nb, st);
+        case 7: return launch_field<7>(a, nb, st);
+        case 8: return launch_field<8>(a, nb, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -323,6 +329,53 @@ static cudaError_t launch_field_any(const die_env* e, const double* min, double*
 // Env.step
 // ------------------------------------------------------------------------------------------
 static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitmask (when valid) instead of the float64 channel
+
+// The four launches of Env.step for environments [b0, b0 + nb) of the batch, on stream `st`.  Every pointer argument
+// refers to the WHOLE batch; the range is resolved here (all per-env arrays are contiguous per environment).
+static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, double* medium_out,
+                          double* agents, const double* action, double* reward_dev, int64_t* alive_dev,
+                          bool fused, const uint32_t* alive_bits, bool profile, cudaStream_t st) {
+    const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
+    medium_in += (size_t)b0 * 3 * C;
+    medium_out += (size_t)b0 * 3 * C;
+    agents += (size_t)b0 * 4 * M;
+    action += (size_t)b0 * 3 * M;
+    int32_t* winner = e->winner + (size_t)b0 * C;
+    int32_t* cells = e->cells2[e->cur] + (size_t)b0 * M;
+    double* part_gain = e->part_gain + (size_t)b0 * e->nblk;
+    int32_t* part_alive = e->part_alive + (size_t)b0 * e->nblk;
+    if (alive_bits != nullptr) alive_bits += (size_t)b0 * e->Mw;
+
+    if (profile) prof_mark(e, 0, st);
+    if (!fused) {
+        const int mchunk = chunks_for(e->M, kMoveItems);
+        auto move = (alive_bits != nullptr) ? move_claim_kernel<false, true> : move_claim_kernel<false, false>;
+        move<<<(unsigned)((int64_t)mchunk * nb), kAgentThreads, 0, st>>>(
+            agents, action, winner, cells, make_axis(e->H), make_axis(e->W), e->M, mchunk,
+            e->dyn.boundary, alive_bits, e->Mw, SlabGeom(), SlabTables());
+        DIE_CUDA(cudaGetLastError());
+    }
+    if (profile) prof_mark(e, 1, st);
+
+    DIE_CUDA(launch_field_any(e, b0, nb, medium_in, medium_out, action, st));
+    if (profile) prof_mark(e, 2, st);
+
+    const unsigned fgrid = (unsigned)((int64_t)e->nblk * nb);
+    const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
+    auto feed = fused ? agent_feed_kernel<false, true, true>
+                      : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
+    feed<<<fgrid, kAgentThreads, 0, st>>>(
+        agents, action, e->consumed + (size_t)b0 * C, winner, cells, part_gain, part_alive,
+        (int64_t)C, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
+        alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
+    DIE_CUDA(cudaGetLastError());
+    if (profile) prof_mark(e, 3, st);
+
+    finalize_stats_kernel<<<nb, kFinalThreads, 0, st>>>(part_gain, part_alive, e->nblk, reward_dev + b0, alive_dev + b0);
+    DIE_CUDA(cudaGetLastError());
+    if (profile) prof_mark(e, 4, st);
+    return DIE_OK;
+}
 
 extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* medium_out,
                                   double* agents, const double* action,
@@ -337,44 +390,18 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
     if ((fused || bits) && !e->alive_valid)
         return fail(DIE_E_INVALID, "die_env_step_flags: call die_env_refresh_alive first%s%s");
     const uint32_t* alive_bits = (fused || bits) ? e->alive_bits : nullptr;
-
-    prof_mark(e, 0, st);
     if (fused) {
         // the forward kernel already resolved cells and claims for exactly this action
         if (!e->pending_move) return fail(DIE_E_INVALID, "die_env_step_flags: no speculative move is pending%s%s");
         e->cur ^= 1;
         e->pending_move = 0;
-    } else {
-        if (e->pending_move) {          // abandoned speculation: its claims must not leak into this step
-            if (int rc = die_env_discard_move(e, stream)) return rc;
-        }
-        const int mchunk = chunks_for(e->M, kMoveItems);
-        auto move = (alive_bits != nullptr) ? move_claim_kernel<false, true> : move_claim_kernel<false, false>;
-        move<<<(unsigned)((int64_t)mchunk * e->B), kAgentThreads, 0, st>>>(
-            agents, action, e->winner, e->cells2[e->cur], make_axis(e->H), make_axis(e->W), e->M, mchunk,
-            e->dyn.boundary, alive_bits, e->Mw, SlabGeom(), SlabTables());
-        DIE_CUDA(cudaGetLastError());
+    } else if (e->pending_move) {       // abandoned speculation: its claims must not leak into this step
+        if (int rc = die_env_discard_move(e, stream)) return rc;
     }
-    prof_mark(e, 1, st);
-
-    DIE_CUDA(launch_field_any(e, medium_in, medium_out, action, st));
+    if (int rc = env_step_range(e, 0, e->B, medium_in, medium_out, agents, action, reward_dev, alive_dev,
+                                fused, alive_bits, true, st))
+        return rc;
     if (e->flow_rwave != nullptr) ++e->flow_k;
-    prof_mark(e, 2, st);
-
-    const unsigned fgrid = (unsigned)((int64_t)e->nblk * e->B);
-    const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
-    auto feed = fused ? agent_feed_kernel<false, true, true>
-                      : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
-    feed<<<fgrid, kAgentThreads, 0, st>>>(
-        agents, action, e->consumed, e->winner, e->cells2[e->cur], e->part_gain, e->part_alive,
-        (int64_t)e->H * e->W, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-        alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
-    DIE_CUDA(cudaGetLastError());
-    prof_mark(e, 3, st);
-
-    finalize_stats_kernel<<<e->B, kFinalThreads, 0, st>>>(e->part_gain, e->part_alive, e->nblk, reward_dev, alive_dev);
-    DIE_CUDA(cudaGetLastError());
-    prof_mark(e, 4, st);
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
     return DIE_OK;
 }
@@ -416,26 +443,62 @@ extern "C" int die_env_read_stats(die_env_t* e, const double* reward_dev, const 
     return DIE_OK;
 }
 
+// Env.step through host buffers.  The environments of a batch are independent, so the batch is cut into chunks that
+// run on two internal streams: while chunk k's observation travels device -> host, chunk k+1's action travels host ->
+// device and its kernels run -- both PCIe directions stay busy instead of taking turns.
+static int g_host_chunks = 4;
+static size_t g_host_chunk_min_bytes = (size_t)32 << 20;   // below this a call is not worth chunking
+
 extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
                                  double* agents, const double* action_host,
                                  double* agents_host, double* medium_host,
                                  double* reward_host, int64_t* alive_host, void* stream) {
     DIE_REQUIRE(e != nullptr && action_host != nullptr);
+    DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out && agents != nullptr);
     DIE_REQUIRE(reward_host != nullptr && alive_host != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t act_bytes = sizeof(double) * 3 * (size_t)e->M * e->B;
-    if (e->action_stage == nullptr) DIE_CUDA(cudaMalloc(&e->action_stage, act_bytes));
-    DIE_CUDA(cudaMemcpyAsync(e->action_stage, action_host, act_bytes, cudaMemcpyHostToDevice, st));
-    if (int rc = die_env_step(e, medium_in, medium_out, agents, e->action_stage, e->reward_dev, e->alive_dev, stream))
-        return rc;
-    if (agents_host != nullptr)
-        DIE_CUDA(cudaMemcpyAsync(agents_host, agents, sizeof(double) * 4 * (size_t)e->M * e->B,
-                                 cudaMemcpyDeviceToHost, st));
-    if (medium_host != nullptr)
-        DIE_CUDA(cudaMemcpyAsync(medium_host, medium_out, sizeof(double) * 3 * (size_t)e->H * e->W * e->B,
-                                 cudaMemcpyDeviceToHost, st));
-    DIE_CUDA(cudaMemcpyAsync(reward_host, e->reward_dev, sizeof(double) * e->B, cudaMemcpyDeviceToHost, st));
-    DIE_CUDA(cudaMemcpyAsync(alive_host, e->alive_dev, sizeof(int64_t) * e->B, cudaMemcpyDeviceToHost, st));
+    const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
+    if (e->action_stage == nullptr) DIE_CUDA(cudaMalloc(&e->action_stage, sizeof(double) * 3 * M * e->B));
+    if (e->pending_move) {
+        if (int rc = die_env_discard_move(e, stream)) return rc;
+    }
+    // chunking pays once a chunk's copies are a few MB; small batches take the single-stream path
+    int nchunks = (g_host_chunks > 1 && e->B >= 2 * g_host_chunks && sizeof(double) * 3 * M * e->B >= g_host_chunk_min_bytes)
+                      ? g_host_chunks : 1;
+    if (nchunks > 1 && e->host_streams[0] == nullptr) {
+        for (int k = 0; k < 2; ++k) {
+            DIE_CUDA(cudaStreamCreateWithFlags(&e->host_streams[k], cudaStreamNonBlocking));
+            DIE_CUDA(cudaEventCreateWithFlags(&e->host_events[k], cudaEventDisableTiming));
+        }
+        DIE_CUDA(cudaEventCreateWithFlags(&e->host_events[2], cudaEventDisableTiming));
+    }
+    if (nchunks > 1) DIE_CUDA(cudaEventRecord(e->host_events[2], st));       // the chunks start after the caller's work
+    for (int k = 0; k < nchunks; ++k) {
+        const int b0 = (int)((int64_t)e->B * k / nchunks), b1 = (int)((int64_t)e->B * (k + 1) / nchunks);
+        const int nb = b1 - b0;
+        cudaStream_t s = (nchunks > 1) ? e->host_streams[k & 1] : st;
+        if (nchunks > 1 && k < 2) DIE_CUDA(cudaStreamWaitEvent(s, e->host_events[2], 0));
+        DIE_CUDA(cudaMemcpyAsync(e->action_stage + (size_t)b0 * 3 * M, action_host + (size_t)b0 * 3 * M,
+                                 sizeof(double) * 3 * M * nb, cudaMemcpyHostToDevice, s));
+        if (int rc = env_step_range(e, b0, nb, medium_in, medium_out, agents, e->action_stage, e->reward_dev, e->alive_dev,
+                                    false, nullptr, false, s))
+            return rc;
+        if (agents_host != nullptr)
+            DIE_CUDA(cudaMemcpyAsync(agents_host + (size_t)b0 * 4 * M, agents + (size_t)b0 * 4 * M,
+                                     sizeof(double) * 4 * M * nb, cudaMemcpyDeviceToHost, s));
+        if (medium_host != nullptr)
+            DIE_CUDA(cudaMemcpyAsync(medium_host + (size_t)b0 * 3 * C, medium_out + (size_t)b0 * 3 * C,
+                                     sizeof(double) * 3 * C * nb, cudaMemcpyDeviceToHost, s));
+        DIE_CUDA(cudaMemcpyAsync(reward_host + b0, e->reward_dev + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
+        DIE_CUDA(cudaMemcpyAsync(alive_host + b0, e->alive_dev + b0, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, s));
+    }
+    if (nchunks > 1) {
+        for (int k = 0; k < 2; ++k) {                                         // the caller's stream continues after both
+            DIE_CUDA(cudaEventRecord(e->host_events[k], e->host_streams[k]));
+            DIE_CUDA(cudaStreamWaitEvent(st, e->host_events[k], 0));
+        }
+    }
+    if (e->flow_rwave != nullptr) ++e->flow_k;
     DIE_CUDA(cudaStreamSynchronize(st));
     return DIE_OK;
 }
@@ -545,6 +608,8 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;
     else if (strcmp(key, "fwd_min_blocks") == 0) { DIE_REQUIRE(value >= 3 && value <= 5); g_fwd_min_blocks = value; }
     else if (strcmp(key, "feed_bits") == 0) g_feed_bits = value ? 1 : 0;
+    else if (strcmp(key, "host_chunks") == 0) { DIE_REQUIRE(value >= 1 && value <= 64); g_host_chunks = value; }
+    else if (strcmp(key, "host_chunk_min_kb") == 0) { DIE_REQUIRE(value >= 0); g_host_chunk_min_bytes = (size_t)value << 10; }
     else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value;      // 0 off, 1 on (4 CTAs/SM), 5 on with a 48-register cap
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
@@ -567,7 +632,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
                                  double* theta, double* prev_grad, double* action,
                                  const uint8_t* coin, const double* noise, int32_t* sense_cells,
                                  const double* grad_hint, const int32_t* cells_hint,
-                                 uint64_t seed, uint64_t step, void* stream) {
+                                 uint64_t seed, uint64_t step, void* stream, int b0 = 0) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -586,6 +651,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
     a.grad = (const double2*)grad_hint; a.cells = cells_hint;
     a.seed = seed; a.step = step;
+    a.b0 = b0;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     cudaStream_t st = (cudaStream_t)stream;
     if (speculate) {
@@ -646,6 +712,82 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
     const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;
     return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Agent.forward through host buffers, chunked over the environments of the batch
+// ------------------------------------------------------------------------------------------
+struct die_host_ctx {
+    cudaStream_t streams[2];
+    cudaEvent_t events[3];
+};
+
+extern "C" int die_host_ctx_create(die_host_ctx_t** out) {
+    DIE_REQUIRE(out != nullptr);
+    *out = nullptr;
+    die_host_ctx* c = new (std::nothrow) die_host_ctx();
+    if (c == nullptr) return fail(DIE_E_NOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) err = cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking);
+    for (int k = 0; k < 3 && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&c->events[k], cudaEventDisableTiming);
+    if (err != cudaSuccess) {
+        die_host_ctx_destroy(c);
+        return fail(DIE_E_CUDA, "die_host_ctx_create: %s", cudaGetErrorString(err));
+    }
+    *out = c;
+    return DIE_OK;
+}
+
+extern "C" int die_host_ctx_destroy(die_host_ctx_t* c) {
+    if (c == nullptr) return DIE_OK;
+    for (int k = 0; k < 2; ++k) if (c->streams[k]) cudaStreamDestroy(c->streams[k]);
+    for (int k = 0; k < 3; ++k) if (c->events[k]) cudaEventDestroy(c->events[k]);
+    delete c;
+    return DIE_OK;
+}
+
+extern "C" int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient_params_t* p,
+                                         int32_t H, int32_t W, int64_t M, int32_t B,
+                                         const double* agents_host, const double* medium_host,
+                                         double* agents_stage, double* medium_stage,
+                                         double* theta, double* prev_grad, double* action, double* action_host,
+                                         const uint8_t* coin, const double* noise, int32_t* sense_cells,
+                                         uint64_t seed, uint64_t step, void* stream) {
+    DIE_REQUIRE(ctx != nullptr && p != nullptr && B >= 1 && M >= 1 && H >= 2 && W >= 2);
+    DIE_REQUIRE(agents_host != nullptr && medium_host != nullptr && agents_stage != nullptr && medium_stage != nullptr);
+    DIE_REQUIRE(theta != nullptr && action != nullptr && action_host != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t C = (size_t)H * W, Ms = (size_t)M;
+    const size_t obs_bytes = sizeof(double) * (4 * Ms + 3 * C) * B;
+    const int nchunks = (g_host_chunks > 1 && B >= 2 * g_host_chunks && obs_bytes >= g_host_chunk_min_bytes) ? g_host_chunks : 1;
+    if (nchunks > 1) DIE_CUDA(cudaEventRecord(ctx->events[2], st));
+    for (int k = 0; k < nchunks; ++k) {
+        const int b0 = (int)((int64_t)B * k / nchunks), b1 = (int)((int64_t)B * (k + 1) / nchunks);
+        const int nb = b1 - b0;
+        cudaStream_t s = (nchunks > 1) ? ctx->streams[k & 1] : st;
+        if (nchunks > 1 && k < 2) DIE_CUDA(cudaStreamWaitEvent(s, ctx->events[2], 0));
+        DIE_CUDA(cudaMemcpyAsync(agents_stage + b0 * 4 * Ms, agents_host + b0 * 4 * Ms, sizeof(double) * 4 * Ms * nb,
+                                 cudaMemcpyHostToDevice, s));
+        DIE_CUDA(cudaMemcpyAsync(medium_stage + b0 * 3 * C, medium_host + b0 * 3 * C, sizeof(double) * 3 * C * nb,
+                                 cudaMemcpyHostToDevice, s));
+        if (int rc = gradient_forward_impl(nullptr, false, p, H, W, M, nb, agents_stage + b0 * 4 * Ms, medium_stage + b0 * 3 * C,
+                                           theta + b0 * Ms, prev_grad ? prev_grad + b0 * 2 * Ms : nullptr, action + b0 * 3 * Ms,
+                                           coin ? coin + b0 * Ms : nullptr, noise ? noise + b0 * 2 * Ms : nullptr,
+                                           sense_cells ? sense_cells + b0 * Ms : nullptr, nullptr, nullptr,
+                                           seed, step, (void*)s, b0))
+            return rc;
+        DIE_CUDA(cudaMemcpyAsync(action_host + b0 * 3 * Ms, action + b0 * 3 * Ms, sizeof(double) * 3 * Ms * nb,
+                                 cudaMemcpyDeviceToHost, s));
+    }
+    if (nchunks > 1) {
+        for (int k = 0; k < 2; ++k) {
+            DIE_CUDA(cudaEventRecord(ctx->events[k], ctx->streams[k]));
+            DIE_CUDA(cudaStreamWaitEvent(st, ctx->events[k], 0));
+        }
+    }
+    DIE_CUDA(cudaStreamSynchronize(st));
+    return DIE_OK;
 }
 
 // ------------------------------------------------------------------------------------------

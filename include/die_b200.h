@@ -144,7 +144,9 @@ int die_env_read_stats(die_env_t* env, const double* reward_dev, const int64_t* 
 
 /* Env.step through HOST buffers: H2D of action_host[B][3][M], the step, D2H of the new
  * observation (agents_host[B][4][M], medium_host[B][3][H][W]; either may be NULL to skip)
- * and of reward_host[B] / alive_host[B]; synchronises `stream` before returning. */
+ * and of reward_host[B] / alive_host[B]; synchronises `stream` before returning.  Large batches are
+ * processed in chunks of environments on two internal streams, so that one chunk's D2H overlaps the next
+ * chunk's H2D and kernels (die_set_tuning("host_chunks", n); 1 = one stream). */
 int die_env_step_host(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
                       double* agents_dev, const double* action_host,
                       double* agents_host, double* medium_host,
@@ -198,6 +200,22 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          const double* grad_hint_dev, const int32_t* cells_hint_dev,
                          uint64_t seed, uint64_t step, void* stream);
 
+/* GradientAgent.forward / PhysarumAgent.forward through HOST buffers: H2D of the observation (agents_host[B][4][M],
+ * medium_host[B][3][H][W]) into the caller's device staging buffers, the forward kernel, D2H of the action into
+ * action_host[B][3][M]; synchronises `stream` before returning.  Large batches are cut into chunks of environments that
+ * alternate between the two streams of a die_host_ctx_t, so one chunk's action download overlaps the next chunk's
+ * observation upload (both PCIe directions busy).  In-kernel random draws do not depend on the chunking. */
+typedef struct die_host_ctx die_host_ctx_t;
+int die_host_ctx_create(die_host_ctx_t** out);
+int die_host_ctx_destroy(die_host_ctx_t* ctx);
+int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient_params_t* p,
+                              int32_t H, int32_t W, int64_t M, int32_t B,
+                              const double* agents_host, const double* medium_host,
+                              double* agents_stage_dev, double* medium_stage_dev,
+                              double* theta_dev, double* prev_grad_dev, double* action_dev, double* action_host,
+                              const uint8_t* coin_dev, const double* noise_dev, int32_t* sense_cells_dev,
+                              uint64_t seed, uint64_t step, void* stream);
+
 /* The same forward pass bound to the environment that produced the observation (what
  * die_b200.PhysarumAgent.forward calls when `obs` is provably that Env's own, die_b200/_hints.py).
  * flags:
@@ -242,7 +260,7 @@ int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream
 int die_set_turn_quick(int32_t on);
 
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
- * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
+ * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
  * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1. */
 int die_set_tuning(const char* key, int32_t value);

@@ -63,3 +63,44 @@ def test_minimal_run_example(argv):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ms per iteration" in out.stdout and "frames:" in out.stdout
+
+
+@pytest.mark.parametrize("agent_kind", ["physarum", "gradient"])
+def test_chunked_host_path_equals_device_path(agent_kind):
+    """die_env_step_host / die_gradient_forward_host cut a batch into chunks of environments on two internal streams
+    (PCIe both ways at once).  With the chunk threshold lowered to zero, a batched run through numpy buffers -- in-kernel
+    Philox draws included -- must reproduce the device-tensor run bit for bit."""
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 0))
+    _lib.check(lib.die_set_tuning(b"host_chunks", 3))
+    try:
+        B, field = 8, (48, 40)
+        refs, dev_env = make_pair(field, seed=50, batch=B)
+        _, host_env = make_pair(field, seed=50, batch=B)
+        m = dev_env.max_agents
+        th = np.stack([lattice_theta(m, 30, 60 + b)[0] for b in range(B)])
+        if agent_kind == "physarum":
+            mk = lambda: D.PhysarumAgent(max_agents=m, seed=9, **PHYS)
+        else:
+            mk = lambda: D.GradientAgent(max_agents=m, seed=9, scale=0.01, inertia=0.9, noise_scale=0.025, sense_offset=0.03)
+        a_dev, a_host = mk(), mk()
+        prev = np.random.default_rng(5).normal(0, 0.4, (B, 2, m))
+        for a in (a_dev, a_host):
+            a.use_env_hints = False            # the host path cannot use the env's caches: compare like with like
+            a._lazy_init(B, m, dev_env.device)
+            a.set_state(theta=th, prev_grad=prev)
+        dobs = dev_env._get_current_obs
+        hobs = tuple(t.cpu().numpy() for t in host_env._get_current_obs)
+        for it in range(8):
+            dact = a_dev.forward(dobs)
+            hact = a_host.forward(hobs)
+            assert isinstance(hact, np.ndarray) and np.array_equal(dact.cpu().numpy(), hact), it
+            dobs, dr, _, _, di = dev_env.step(dact)
+            hobs, hr, _, _, hi = host_env.step(hact)
+            assert np.array_equal(dr, hr) and np.array_equal(di['num_agents'], hi['num_agents'])
+            assert np.array_equal(dobs[0].cpu().numpy(), hobs[0]) and np.array_equal(dobs[1].cpu().numpy(), hobs[1])
+    finally:
+        _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
+        _lib.check(lib.die_set_tuning(b"host_chunks", 4))
