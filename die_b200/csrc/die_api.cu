@@ -610,7 +610,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "feed_bits") == 0) g_feed_bits = value ? 1 : 0;
     else if (strcmp(key, "host_chunks") == 0) { DIE_REQUIRE(value >= 1 && value <= 64); g_host_chunks = value; }
     else if (strcmp(key, "host_chunk_min_kb") == 0) { DIE_REQUIRE(value >= 0); g_host_chunk_min_bytes = (size_t)value << 10; }
-    else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value;      // 0 off, 1 on (4 CTAs/SM), 5 on with a 48-register cap
+    else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value;      // 0 off, 1 on (4 CTAs/SM), 5: 48-register cap
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
@@ -675,8 +675,10 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     const bool lean = g_fwd_lean && !speculate && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
                       prev_grad == nullptr && coin == nullptr && noise == nullptr && sense_cells == nullptr &&
                       a.grad != nullptr && a.cells != nullptr && g_fwd_min_blocks == 4;
-    if (lean) kern = (g_fwd_lean == 5) ? gradient_forward_kernel<true, false, false, 5, true>
-                                       : gradient_forward_kernel<true, false, false, 4, true>;
+    if (lean) {
+        if (g_fwd_lean == 5) kern = gradient_forward_kernel<true, false, false, 5, true>;
+        else kern = gradient_forward_kernel<true, false, false, 4, true>;
+    }
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
     if (speculate) env->pending_move = 1;
