@@ -2,8 +2,9 @@
 
 ``Env.step`` caches, per slot, the linear cell index of every agent, and -- once a gradient agent has
 asked for it -- publishes np.gradient of the new chem1 channel per cell.  ``Agent.forward(obs)`` only
-receives ``obs``; it finds the producing Env here, keyed by the medium tensor's device address, and
-uses the cached arrays ONLY IF the observation is provably the one the Env wrote in its last step:
+receives ``obs``; it finds the producing Env here (``find_env``), keyed by the medium tensor's device address,
+and ``Env._forward_flags`` lets it use the cached arrays ONLY IF the observation is provably the one the Env
+wrote in its last step:
 same storage, and torch's in-place version counters of the medium / agents tensors unchanged (our
 kernels write through raw pointers and do not bump them; any ``tensor[...] = ...`` by the caller
 does).  Otherwise the kernel recomputes everything from ``obs`` -- same results bit for bit."""
@@ -13,6 +14,9 @@ _REGISTRY = {}          # medium data_ptr -> weakref(Env)
 
 
 def publish(env, medium_buf) -> None:
+    if len(_REGISTRY) > 4096:               # entries of collected Envs are dead weakrefs: drop them now and then
+        for key in [k for k, r in _REGISTRY.items() if r() is None]:
+            del _REGISTRY[key]
     _REGISTRY[(medium_buf.device.index, medium_buf.data_ptr())] = weakref.ref(env)
 
 
@@ -28,12 +32,3 @@ def find_env(agents, medium):
     if medium.numel() != buf.numel() or medium.shape[-2:] != buf.shape[-2:] or agents.numel() != env._agents.numel():
         return None
     return env
-
-
-def lookup(agents, medium, want_gradient: bool):
-    """-> (grad_ptr or None, cells_ptr or None) for this observation."""
-    ref = _REGISTRY.get((medium.device.index, medium.data_ptr()))
-    env = ref() if ref is not None else None
-    if env is None or env._handle is None:
-        return None, None
-    return env._hints_for(agents, medium, want_gradient)

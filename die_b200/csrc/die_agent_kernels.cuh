@@ -1,10 +1,10 @@
 // die_agent_kernels.cuh -- per-slot kernels: policies (Brownian / Const / Gradient / Physarum)
-// and the agent half of Env.step (move + claim, deposit + feed + reduce).
+// and the agent half of Env.step (move + claim, feed + reward partials, final reduction).
 //
-// One thread per agent slot, grid-stride over all B*M slots; every per-slot array is
-// channel-major ([B][ch][M]) so consecutive threads read consecutive doubles (coalesced,
-// 256 B per warp per channel).  Field accesses are data-dependent gathers (one 32 B sector
-// each).  Citations are file:line under /root/reference.
+// One thread handles a few slots of one environment (a CTA owns a chunk of consecutive slots, see
+// slot_chunk); every per-slot array is channel-major ([B][ch][M]) so consecutive threads read
+// consecutive doubles (coalesced, 256 B per warp per channel).  Field accesses are data-dependent
+// gathers (one 32 B sector each).  Citations are file:line under /root/reference.
 #pragma once
 #include "die_device.cuh"
 #include "die_slab.cuh"
