@@ -50,12 +50,3 @@ def test_slab_world_equals_single_env(shape, G, band):
         ids = np.concatenate([world.layout.global_ids(q) for q in range(G)])
         crossed = max(crossed, int((owner_of_cell[ids] != slot_owner).sum()))
     assert crossed > 0, "the test must exercise agents standing on another rank's slab"
-
-
-def test_slab_layout_ranges():
-    from die_b200.slab import make_layout
-    L = make_layout((64, 32), 4, 2048, [50, 60, 40, 55])
-    assert L.s0 == [0, 50, 110, 150] and L.n0 == [50, 60, 40, 55]
-    assert sum(L.n1) == 2048 - 205 and L.s1[0] == 205
-    ids = np.concatenate([L.global_ids(q) for q in range(4)])
-    assert sorted(ids.tolist()) == list(range(2048))
