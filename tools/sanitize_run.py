@@ -1,0 +1,46 @@
+"""A short tour of every kernel and option combination on small inputs (device init, batches, every agent, food flow +
+sense mask + 'constant' diffusion, fused move, render, chunked host path, the march field kernel).  Written to be run under
+`compute-sanitizer --tool memcheck` (closed on this pool, so it only serves as a crash / sticky-error check here)."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import die_b200 as D
+from die_b200 import _lib
+from die_b200.render import EnvRenderer
+
+lib = _lib.load()
+field = (37, 53)
+for mode, flow, mask in (("wrap", False, False), ("constant", True, True), ("reflect", False, False)):
+    dyn = D.Dynamics(init_agent_ratio=0.2, diffuse_mode=mode, apply_sense_mask=mask)
+    if flow:
+        dyn.op_food_flow = D.WaveSequence(field, dt=0.5, t_bounds=(0, 2)).get_flow_operator(0.5, 0.5)
+    env = D.Env(field, dyn, init='device', seed=1, batch=3)
+    m = env.max_agents
+    for agent in (D.PhysarumAgent(max_agents=m, scale=0.02, sense_offset=0.06), D.BrownianAgent(0.03),
+                  D.GradientAgent(max_agents=m, scale=0.02, sense_offset=0.05), D.ConstAgent((0.01, -0.02), 0.3)):
+        if hasattr(agent, "fuse_move"):
+            agent.fuse_move = (mode == "reflect")
+        obs = env._get_current_obs
+        for _ in range(4):
+            obs, r, *_ = env.step(agent.forward(obs))
+    env.render(host=True)
+    hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
+    _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 0))
+    _lib.check(lib.die_set_tuning(b"host_chunks", 2))
+    big = D.Env(field, D.Dynamics(init_agent_ratio=0.2), init='device', seed=2, batch=5)
+    ag = D.PhysarumAgent(max_agents=m, scale=0.02, sense_offset=0.06)
+    hobs = tuple(t.cpu().numpy() for t in big._get_current_obs)
+    for _ in range(3):
+        hobs, *_ = big.step(ag.forward(hobs))
+    _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
+    _lib.check(lib.die_set_tuning(b"host_chunks", 4))
+lib.die_set_field_impl(1)
+env = D.Env((64, 40), D.Dynamics(), init='device', seed=3)
+ag = D.PhysarumAgent(max_agents=env.max_agents, scale=0.02, sense_offset=0.06)
+obs = env._get_current_obs
+for _ in range(4):
+    obs, *_ = env.step(ag.forward(obs))
+lib.die_set_field_impl(0)
+torch.cuda.synchronize()
+print("sanitize tour done")
