@@ -7,7 +7,7 @@ import os
 from abc import ABC, abstractmethod
 from typing import Any, Dict, Union
 
-from ..base_types import ActType, ObsType
+from ..base_types import ActType, AgtType, ObsType
 
 
 class Agent(ABC):
@@ -38,3 +38,19 @@ class Agent(ABC):
         else:
             params = json.load(file)
         return cls(**params)
+
+    # -- action post-processing helpers (core/agent/base.py:45-62); not used by the built-in policies there either -----
+    @staticmethod
+    def postprocess_action(agents: AgtType, action: ActType) -> ActType:
+        return Agent._rescale_outputs(Agent._masked_alive(agents, action))
+
+    @staticmethod
+    def _rescale_outputs(action: ActType) -> ActType:
+        """core/agent/base.py:52-55: identity."""
+        return action
+
+    @staticmethod
+    def _masked_alive(agents: AgtType, action: ActType) -> ActType:
+        """core/agent/base.py:58-62: action * (alive > 0), broadcast over the action channels."""
+        alive = agents[..., 2, :] > 0
+        return action * alive.unsqueeze(-2).to(action.dtype)

@@ -144,3 +144,16 @@ def test_wave_sequence_host_mirror_and_device_tables():
     for _ in range(3):
         assert np.array_equal(op(f), oo(f))
     assert op.calls == 3
+
+
+def test_agent_postprocess_action_helpers():
+    """core/agent/base.py:45-62: mask the action by alive-ness, rescale = identity."""
+    import torch
+    from die_b200 import Agent
+    agents = torch.tensor([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6], [1.0, 0.0, 1.0], [0.5, 0.5, 0.5]], dtype=torch.float64)
+    action = torch.arange(9, dtype=torch.float64).reshape(3, 3) + 1
+    out = Agent.postprocess_action(agents, action)
+    assert torch.equal(out, action * torch.tensor([1.0, 0.0, 1.0], dtype=torch.float64))
+    batched = Agent._masked_alive(agents.expand(2, 4, 3), action.expand(2, 3, 3))
+    assert batched.shape == (2, 3, 3) and torch.equal(batched[1], out)
+    assert Agent._rescale_outputs(action) is action
