@@ -11,9 +11,14 @@ Differences a caller of the reference can observe (all documented in DESIGN.md):
     path) instead of ``xarray.DataArray``; ``die_b200.base_types.channel`` replaces
     ``.sel(channel=...)``.
   * ``obs[1]`` (the medium) is a zero-copy view of the env's current buffer, valid until the
-    next ``step`` (the reference makes a fresh copy, core/env.py:290-294); ``obs[0]`` is the
-    env's live ``agents`` tensor exactly as in the reference (core/env.py:298).
+    next-but-one ``step`` (two buffers ping-pong; the reference makes a fresh copy,
+    core/env.py:290-294); with ``apply_sense_mask`` it is the masked copy the reference hands out.
+    ``obs[0]`` is the env's live ``agents`` tensor exactly as in the reference (core/env.py:298).
   * ``batch=B`` runs B independent environments in one set of launches (leading axis B).
+  * ``init='device'`` builds the initial state on the GPU; ``render()`` returns device tensors
+    (``render(host=True)``: numpy arrays) instead of drawing with matplotlib.
+Also on the path: ``Dynamics.op_food_flow = WaveSequence(...).get_flow_operator(...)`` (evaluated in
+the field kernel), every ``diffuse_mode`` of scipy.ndimage, ``boundary=limit``, ``food_infinite``.
 """
 from __future__ import annotations
 
