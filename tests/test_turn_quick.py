@@ -140,3 +140,36 @@ def test_other_enabled_parameter_sets(lib, kw):
     enabled, out = run(lib, mag * np.cos(ang), mag * np.sin(ang), th, **kw)
     assert enabled == 1
     assert assert_consistent(out) > 0.98
+
+
+def test_dense_sweep_across_the_guard_band_edges(lib):
+    """delta swept densely (2000 points per threshold and side) from well inside to well outside every guard band,
+    for gradient magnitudes from just above the clip threshold to O(1): whatever the quick path decides must be the
+    exact path's answer, and it must start deciding again right outside the bands."""
+    rng = np.random.default_rng(7)
+    atol = np.radians(30.) * 0.1
+    marks = np.array([atol / 0.99, -atol / 0.99, np.pi / 2, -np.pi / 2, atol, -atol])
+    offs = np.concatenate([np.linspace(-3e-3, 3e-3, 2001), np.geomspace(1e-9, 3e-3, 400), -np.geomspace(1e-9, 3e-3, 400)])
+    for mag in (1.0002e-5, 1.5e-5, 3e-4, 0.02, 0.9, 7.0):
+        phi = rng.uniform(-np.pi, np.pi, 12)
+        P, Mk, O = np.meshgrid(phi, marks, offs, indexing='ij')
+        th = (P + Mk + O + np.pi) % (2 * np.pi) - np.pi
+        enabled, out = run(lib, mag * np.cos(P), mag * np.sin(P), th)
+        assert enabled == 1
+        assert_consistent(out)
+        far = np.abs(O.ravel()) > 2.5e-3                    # beyond the widest band (3.8e-4 rad) with margin
+        banded = np.isin(Mk.ravel(), marks[:4])             # +-atol itself is no threshold of the quick path
+        near = (np.abs(O.ravel()) < 1e-6) & banded
+        assert out[far, 0].mean() > 0.99 and out[near, 0].mean() < 0.01
+
+
+def test_magnitudes_around_the_clip_threshold(lib):
+    rng = np.random.default_rng(8)
+    n = 200_000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    mag = 1e-5 * (1 + rng.uniform(-3e-4, 3e-4, n))          # |g| within 0.03 % of grad_clip, both sides
+    mag[:64] = 1e-5 * (1 + np.linspace(-1e-15, 1e-15, 64))  # ... and within a few ulp of it
+    th = np.where(rng.random(n) < 0.5, lattice(n, rng), rng.uniform(-np.pi, np.pi, n))
+    enabled, out = run(lib, mag * np.cos(ang), mag * np.sin(ang), th)
+    frac = assert_consistent(out)
+    assert 0.2 < frac < 0.95                                 # the band around the threshold defers, the rest decides
