@@ -445,8 +445,17 @@ def run_die_b200(args):
 # --------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference)
 # --------------------------------------------------------------------------------------------
+_ORACLE_BARRIER = None
+
+
+def _oracle_init(barrier):
+    global _ORACLE_BARRIER
+    _ORACLE_BARRIER = barrier
+
+
 def _oracle_worker(job):
-    """One process = one 256x256-style env stepped by the numpy oracle (imports no torch, no CUDA)."""
+    """One process = one 256x256-style env stepped by the numpy oracle (imports no torch, no CUDA).  All workers
+    finish their warm-up, meet at a barrier and only then start their timed loops."""
     field_n, steps, warmup, seed = job
     from oracle import die_ref as R
     field = (field_n, field_n)
@@ -457,6 +466,8 @@ def _oracle_worker(job):
     obs = env._get_current_obs
     for _ in range(warmup):
         obs, *_ = env.step(agent.forward(obs))
+    if _ORACLE_BARRIER is not None:
+        _ORACLE_BARRIER.wait()
     t0 = time.time()
     for _ in range(steps):
         obs, *_ = env.step(agent.forward(obs))
@@ -473,8 +484,9 @@ def time_oracle(field_n, steps, warmup, procs=None):
     if procs == 1:
         spans = [_oracle_worker(jobs[0])]
     else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            spans = pool.map(_oracle_worker, jobs)
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(procs, initializer=_oracle_init, initargs=(ctx.Barrier(procs),)) as pool:
+            spans = pool.map(_oracle_worker, jobs, chunksize=1)
     wall = max(e for _, e in spans) - min(b for b, _ in spans)
     per_env_step = float(np.mean([(e - b) / steps for b, e in spans]))
     return {"value": field_n * field_n * steps * procs / wall, "unit": UNIT, "cores": procs, "kind": "port",
