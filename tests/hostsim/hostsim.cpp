@@ -1,0 +1,184 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE: the scheduler behind tests/hostsim/cuda_runtime.h.
+//
+// A launch runs its blocks one after the other; the threads of a block are cooperative fibers (ucontext) that
+// run until they finish or reach a barrier (__syncthreads, or the exchange step of a warp shuffle / ballot).
+// A barrier releases once every thread of the block (warp) that has not yet exited has arrived, as on the
+// hardware.  If no fiber can run and some have not finished, the launch reports an error instead of hanging.
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <cstdio>
+#include <vector>
+
+#include "cuda_runtime.h"
+
+namespace hostsim {
+
+ThreadCtx* cur = nullptr;
+int last_error = 0;
+
+namespace {
+
+constexpr size_t kStackBytes = 256 << 10;
+
+struct Warp {
+    int alive = 0;
+    int count = 0;
+    unsigned gen = 0;
+    uint64_t slot[32];
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    ThreadCtx tc;
+    bool done = false;
+    const unsigned* wait_ptr = nullptr;     // blocked while *wait_ptr == wait_val
+    unsigned wait_val = 0;
+    int warp = 0, lane = 0;
+};
+
+struct Block {
+    int alive = 0;
+    int bar_count = 0;
+    unsigned bar_gen = 0;
+    std::vector<Warp> warps;
+};
+
+ucontext_t g_sched;
+std::vector<Fiber> g_fibers;
+std::vector<char*> g_stacks;
+Fiber* g_self = nullptr;
+Block g_blk;
+const std::function<void()>* g_body = nullptr;
+std::vector<char> g_smem;
+
+char* stack_for(size_t i) {
+    while (g_stacks.size() <= i) {
+        void* p = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p == MAP_FAILED) { perror("hostsim: mmap"); abort(); }
+        g_stacks.push_back((char*)p);
+    }
+    return g_stacks[i];
+}
+
+void yield() { swapcontext(&g_self->ctx, &g_sched); }
+
+void block_wait(unsigned* gen, int* count, int alive) {
+    Fiber* f = g_self;
+    const unsigned g = *gen;
+    if (++*count >= alive) {
+        *count = 0;
+        ++*gen;
+        return;
+    }
+    f->wait_ptr = gen;
+    f->wait_val = g;
+    yield();
+}
+
+void thread_exit(Fiber* f) {
+    f->done = true;
+    // a thread that leaves no longer counts towards the barriers of its block / warp
+    --g_blk.alive;
+    if (g_blk.bar_count > 0 && g_blk.bar_count >= g_blk.alive) {
+        g_blk.bar_count = 0;
+        ++g_blk.bar_gen;
+    }
+    Warp& w = g_blk.warps[f->warp];
+    --w.alive;
+    if (w.count > 0 && w.count >= w.alive) {
+        w.count = 0;
+        ++w.gen;
+    }
+}
+
+void trampoline() {
+    (*g_body)();
+    thread_exit(g_self);
+    swapcontext(&g_self->ctx, &g_sched);
+}
+
+}  // namespace
+
+void* dyn_smem() { return g_smem.data(); }
+unsigned lane_id() { return (unsigned)g_self->lane; }
+
+void syncthreads() { block_wait(&g_blk.bar_gen, &g_blk.bar_count, g_blk.alive); }
+
+void warp_exchange(uint64_t mine, uint64_t* all32) {
+    Warp& w = g_blk.warps[g_self->warp];
+    w.slot[g_self->lane] = mine;
+    block_wait(&w.gen, &w.count, w.alive);
+    memcpy(all32, w.slot, sizeof(w.slot));
+    block_wait(&w.gen, &w.count, w.alive);      // nobody deposits the next value before everybody has read
+}
+
+void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    const size_t nthreads = (size_t)block.x * block.y * block.z;
+    if (nthreads == 0 || nthreads > 1024 || grid.x == 0) {
+        last_error = cudaErrorInvalidValue;
+        return;
+    }
+    g_body = &body;
+    if (g_fibers.size() < nthreads) g_fibers.resize(nthreads);
+    g_smem.assign(smem + 16, (char)0xFF);      // NaN-poisoned: a read of unwritten shared memory shows up in the results
+    const int nwarps = (int)((nthreads + 31) / 32);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_blk.alive = (int)nthreads;
+        g_blk.bar_count = 0;
+        g_blk.warps.assign(nwarps, Warp());
+        for (size_t t = 0; t < nthreads; ++t) {
+            Fiber& f = g_fibers[t];
+            f.done = false;
+            f.wait_ptr = nullptr;
+            f.warp = (int)(t / 32);
+            f.lane = (int)(t % 32);
+            ++g_blk.warps[f.warp].alive;
+            f.tc.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((size_t)block.x * block.y))};
+            f.tc.bid = uint3{bx, by, bz};
+            f.tc.bdim = block;
+            f.tc.gdim = grid;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = stack_for(t);
+            f.ctx.uc_stack.ss_size = kStackBytes;
+            f.ctx.uc_link = &g_sched;
+            makecontext(&f.ctx, trampoline, 0);
+        }
+        size_t remaining = nthreads;
+        while (remaining > 0) {
+            bool progressed = false;
+            for (size_t t = 0; t < nthreads; ++t) {
+                Fiber& f = g_fibers[t];
+                if (f.done) continue;
+                if (f.wait_ptr != nullptr && *f.wait_ptr == f.wait_val) continue;
+                f.wait_ptr = nullptr;
+                g_self = &f;
+                cur = &f.tc;
+                swapcontext(&g_sched, &f.ctx);
+                progressed = true;
+                if (f.done) --remaining;
+            }
+            if (!progressed) {                  // every live thread waits at a barrier that cannot complete
+                last_error = cudaErrorLaunchFailure;
+                g_self = nullptr;
+                cur = nullptr;
+                return;
+            }
+        }
+    }
+    g_self = nullptr;
+    cur = nullptr;
+}
+
+void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
+    memset(p, 0xCD, bytes);                     // cudaMalloc does not zero either
+    return p;
+}
+
+void dev_free(void* p) { free(p); }
+
+}  // namespace hostsim

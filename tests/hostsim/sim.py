@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE: a numpy driver over the C ABI of libdie_hostsim.so (the kernel sources of die_b200/csrc
+executed thread by thread on the CPU, tests/hostsim/cuda_runtime.h).  "Device pointers" are numpy arrays.
+
+It mirrors what die_b200/env.py and die_b200/agent/*.py do with torch CUDA tensors -- the same C entry points in the
+same order with the same flags -- so the `-m "not gpu"` suite can check the kernels' logic against the oracle
+without a GPU.  The product never imports this module.
+"""
+import ctypes as C
+
+import numpy as np
+
+from die_b200 import _lib as L          # the prototypes (SIGNATURES) and the C structs only
+from die_b200.env import Dynamics, _dynamics_to_c
+
+from . import build as _build
+
+_sim = None
+
+
+def lib() -> C.CDLL:
+    global _sim
+    if _sim is None:
+        so = C.CDLL(_build.build())
+        for name, (res, args) in L.SIGNATURES.items():
+            fn = getattr(so, name)
+            fn.restype = res
+            fn.argtypes = args
+        _sim = so
+    return _sim
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libdie_hostsim error {rc}: {lib().die_last_error().decode()}")
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(lib().die_set_tuning(key.encode(), int(value)))
+
+
+def gradient_params(scale=0.005, deposit=4.0, inertia=0.0, sense_offset=0.03, noise_scale=0.0, normalized_grad=True,
+                    grad_clip=1e-5, turn_angle=30, sense_angle=90, turn_tolerance=0.1, discrete_turn=True):
+    """PhysarumAgent's constructor defaults (core/agent/gradient.py:139-151) -> die_gradient_params_t."""
+    p = L.DieGradientParams()
+    p.scale, p.deposit, p.inertia, p.sense_offset, p.noise_scale = scale, deposit, inertia, sense_offset, noise_scale
+    p.grad_clip = 0.0 if grad_clip is None else float(grad_clip)
+    p.turn_radians = float(np.radians(turn_angle)) if discrete_turn else 0.0
+    p.sense_radians = float(np.radians(sense_angle)) if discrete_turn else 0.0
+    p.turn_tolerance = float(turn_tolerance) if discrete_turn else 0.0
+    p.normalized_grad = int(normalized_grad)
+    p.use_grad_clip = int(grad_clip is not None)
+    p.discrete_turn = int(discrete_turn)
+    return p
+
+
+class SimEnv:
+    """die_b200.Env's call sequence on numpy arrays."""
+
+    def __init__(self, field_size, medium, agents, dynamics: Dynamics = None, batch=None):
+        self.lib = lib()
+        self.h, self.w = int(field_size[0]), int(field_size[1])
+        self.B = int(batch) if batch is not None else 1
+        self.dynamics = dynamics or Dynamics()
+        self.agents = np.ascontiguousarray(np.asarray(agents, dtype=np.float64).reshape(self.B, 4, -1)).copy()
+        self.M = self.agents.shape[-1]
+        first = np.ascontiguousarray(np.asarray(medium, dtype=np.float64).reshape(self.B, 3, self.h, self.w)).copy()
+        self.medium_buf = [first, np.full_like(first, np.nan)]
+        self.cur = 0
+        self.reward = np.zeros(self.B)
+        self.alive = np.zeros(self.B, dtype=np.int64)
+        self.handle = C.c_void_p()
+        cdyn = _dynamics_to_c(self.dynamics)
+        check(self.lib.die_env_create(self.h, self.w, self.M, self.B, C.byref(cdyn), C.byref(self.handle)))
+        self.publish_grad = False
+        self.hints_valid = False
+        self._flow = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.die_env_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def medium(self):
+        return self.medium_buf[self.cur]
+
+    def set_food_flow(self, op):
+        """Dynamics.op_food_flow = WaveSequence flow operator (die_b200/env.py:_install_food_flow)."""
+        rwave, col, row = (np.ascontiguousarray(a) for a in op.sequence.device_tables())
+        ts = np.ascontiguousarray(op.sequence.ts, dtype=np.float64)
+        self._flow = (rwave, col, row, ts)
+        check(self.lib.die_env_set_food_flow(self.handle, ptr(rwave), ptr(col), ptr(row), ptr(ts), len(ts),
+                                             op.calls % len(ts), op.scale, op.decay))
+
+    def want_gradient(self):
+        if not self.publish_grad:
+            check(self.lib.die_env_publish_gradient(self.handle, 1))
+            self.publish_grad = True
+
+    def step(self, action, flags=L.STEP_ALIVE_BITS):
+        action = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(self.B, 3, self.M))
+        nxt = 1 - self.cur
+        check(self.lib.die_env_refresh_alive(self.handle, ptr(self.agents), None))
+        check(self.lib.die_env_step_flags(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
+                                          ptr(self.agents), ptr(action), ptr(self.reward), ptr(self.alive), flags, None))
+        self.cur = nxt
+        self.hints_valid = True
+        self.grad_valid = self.publish_grad
+        return self.reward.copy(), self.alive.copy()
+
+    def step_host(self, action):
+        """die_env_step_host: action / observation through "host" buffers, chunked over the batch."""
+        action = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(self.B, 3, self.M))
+        nxt = 1 - self.cur
+        agents_h = np.empty_like(self.agents)
+        medium_h = np.empty_like(self.medium_buf[0])
+        check(self.lib.die_env_step_host(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
+                                         ptr(self.agents), ptr(action), ptr(agents_h), ptr(medium_h),
+                                         ptr(self.reward), ptr(self.alive), None))
+        self.cur = nxt
+        self.hints_valid = True
+        self.grad_valid = self.publish_grad
+        return (agents_h, medium_h), self.reward.copy(), self.alive.copy()
+
+    def cells(self):
+        p = self.lib.die_env_cells(self.handle)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(self.B, self.M)).copy()
+
+    def gradient(self):
+        p = self.lib.die_env_gradient(self.handle)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.B, self.h, self.w, 2)).copy()
+
+
+class SimGradientAgent:
+    """die_b200.GradientAgent / PhysarumAgent's call sequence on numpy arrays."""
+
+    def __init__(self, M, B=1, seed=0, **params):
+        self.lib = lib()
+        self.p = gradient_params(**params)
+        self.M, self.B = M, B
+        self.theta = np.zeros((B, M))
+        needs_prev = self.p.inertia != 0.0 or self.p.noise_scale != 0.0
+        self.prev_grad = np.zeros((B, 2, M)) if needs_prev else None
+        self.action = np.full((B, 3, M), np.nan)
+        self.sense_cells = np.zeros((B, M), dtype=np.int32)
+        self.record_sense_cells = False
+        self.seed, self.step_no = seed, 0
+        self.fuse_move = False
+
+    def forward(self, env: SimEnv, coin=None, noise=None, use_hints=True, obs=None):
+        """obs = (agents, medium) arrays other than the env's own disable the hints, as die_b200/_hints.py does."""
+        agents, medium = (env.agents, env.medium) if obs is None else obs
+        coin_a = None if coin is None else np.ascontiguousarray(np.asarray(coin).astype(np.uint8).reshape(self.B, self.M))
+        noise_a = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(self.B, 2, self.M))
+        sc = self.sense_cells if self.record_sense_cells else None
+        own = obs is None
+        if own and use_hints:
+            env.want_gradient()
+            flags = 0
+            if env.hints_valid:
+                flags |= L.FWD_USE_CELLS
+                if getattr(env, 'grad_valid', False):
+                    flags |= L.FWD_USE_GRADIENT
+            if self.fuse_move:
+                check(self.lib.die_env_refresh_alive(env.handle, ptr(env.agents), None))
+                flags |= L.FWD_SPECULATE_MOVE
+            check(self.lib.die_env_forward_gradient(env.handle, C.byref(self.p), ptr(agents), ptr(medium), ptr(self.theta),
+                                                    ptr(self.prev_grad), ptr(self.action), ptr(coin_a), ptr(noise_a),
+                                                    ptr(sc), flags, self.seed, self.step_no, None))
+            self.last_flags = flags
+        else:
+            check(self.lib.die_gradient_forward(C.byref(self.p), env.h, env.w, self.M, self.B, ptr(agents), ptr(medium),
+                                                ptr(self.theta), ptr(self.prev_grad), ptr(self.action), ptr(coin_a),
+                                                ptr(noise_a), ptr(sc), None, None, self.seed, self.step_no, None))
+            self.last_flags = 0
+        self.step_no += 1
+        return self.action
+
+
+def brownian_forward(agents, move_scale=0.01, deposit_scale=0.5, u=None, seed=0, step=0):
+    agents = np.ascontiguousarray(agents, dtype=np.float64)
+    B = 1 if agents.ndim == 2 else agents.shape[0]
+    M = agents.shape[-1]
+    action = np.full((B, 3, M), np.nan)
+    u_a = None if u is None else np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(B, 3, M))
+    check(lib().die_brownian_forward(ptr(agents), ptr(action), M, B, move_scale, deposit_scale, ptr(u_a), seed, step, None))
+    return action if agents.ndim == 3 else action[0]

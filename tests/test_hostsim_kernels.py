@@ -1,0 +1,423 @@
+"""The kernel SOURCES of die_b200/csrc, executed thread by thread on the CPU (tests/hostsim: one fiber per CUDA
+thread, __syncthreads / shuffles / ballots as fiber barriers), through the same C ABI and in the same call order
+as die_b200.Env / die_b200.PhysarumAgent, against the numpy oracle.
+
+What this buys: the logic of every kernel (indexing, tiling, halos, the claim protocol, the reductions, every
+template instantiation the dispatcher can pick) is checked on every CPU run, bit for bit -- the arithmetic is the
+same IEEE float64 sequence on both machines (-fmad=false / -ffp-contract=off, die_math.h for sin / cos / atan2).
+What it does not: speed, and races between CTAs (blocks run one after the other).  The `-m gpu` tests stay the
+parity tests proper; the product never loads the emulated library.
+"""
+import numpy as np
+import pytest
+
+import die_b200 as D
+from die_b200 import _lib as L
+from oracle import die_ref as R
+from tests._parity import lattice_theta, ref_cells_linear, assert_state_equal
+from tests.hostsim import sim as S
+
+PHYS = dict(scale=0.007, turn_angle=30, sense_offset=0.04)     # README.md:45-48
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(a), abs(b), 1e-300)
+
+
+def make_pair(field, seed=1, ratio=0.1, dynamics_kw=None, ref_dynamics_kw=None, batch=None):
+    dynamics_kw = dynamics_kw or {}
+    ref_dynamics_kw = ref_dynamics_kw if ref_dynamics_kw is not None else dict(dynamics_kw)
+    refs = []
+    for b in range(batch or 1):
+        np.random.seed(seed + b)
+        refs.append(R.Env(field, R.Dynamics(init_agent_ratio=ratio, **ref_dynamics_kw), noise_seed=seed + b))
+    env = S.SimEnv(field, np.stack([r.medium for r in refs]), np.stack([r.agents for r in refs]),
+                   D.Dynamics(init_agent_ratio=ratio, **dynamics_kw), batch=batch)
+    return refs, env
+
+
+@pytest.fixture
+def portable_math():
+    R.set_math_backend('portable')
+    yield
+    R.set_math_backend('numpy')
+
+
+@pytest.fixture
+def tuning():
+    """set_tuning(key, value) with every switch restored afterwards."""
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0)
+    yield S.set_tuning
+    for k, v in defaults.items():
+        S.set_tuning(k, v)
+
+
+# ------------------------------------------------------------------------------------------
+# config 1: BrownianAgent free running, bit-exact (brownian_forward, move_claim, field_step, agent_feed, finalize)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field,iters,flags", [((37, 53), 25, L.STEP_ALIVE_BITS), ((64, 64), 10, 0), ((24, 200), 10, L.STEP_ALIVE_BITS)])
+def test_brownian_free_run_bit_exact(field, iters, flags):
+    (ref,), env = make_pair(field, seed=1)
+    ra = R.BrownianAgent(0.01)
+    m = ref.agents.shape[-1]
+    rng = np.random.default_rng(7)
+    robs = ref._get_current_obs
+    for it in range(iters):
+        u = rng.random((3, m))
+        ract = ra.forward(robs, u=u)
+        gact = S.brownian_forward(env.agents[0], u=u)
+        assert np.array_equal(ract, gact), f"action differs at step {it}"
+        robs, rr, rterm, _, rinfo = ref.step(ract)
+        r, alive = env.step(gact, flags=flags)
+        assert np.array_equal(ref_cells_linear(ref), env.cells()[0]), f"cells differ at step {it}"
+        assert rinfo['num_agents'] == alive[0]
+        assert _rel(rr, r[0]) < 1e-11
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+
+
+def test_brownian_philox_is_launch_invariant_and_masked():
+    """In-kernel Philox draws: ghosts get exactly zero (Q8), values lie on the 3-decimal lattice (Q9), and a batch
+    of two environments draws different numbers per environment."""
+    (ref,), _ = make_pair((32, 32), seed=3)
+    ag = np.stack([ref.agents, ref.agents])
+    act = S.brownian_forward(ag, move_scale=0.01, seed=5, step=9)
+    ghosts = ag[0, 2] == 0
+    assert (act[:, :, ghosts] == 0).all()
+    q = (act[0, 0, ~ghosts] + 0.01) / 0.02 * 1000
+    assert np.allclose(q, np.rint(q), atol=1e-9)
+    assert not np.array_equal(act[0], act[1])
+    assert np.array_equal(act, S.brownian_forward(ag, move_scale=0.01, seed=5, step=9))
+
+
+# ------------------------------------------------------------------------------------------
+# config 2: PhysarumAgent, oracle in its portable math backend -> everything bit-exact, free running
+# ------------------------------------------------------------------------------------------
+def _physarum_free_run(field, iters, agent_kw, seed=2, dynamics_kw=None, ref_dynamics_kw=None, use_hints=True,
+                       record=True, fuse=False):
+    (ref,), env = make_pair(field, seed=seed, dynamics_kw=dynamics_kw, ref_dynamics_kw=ref_dynamics_kw)
+    m = ref.agents.shape[-1]
+    theta0, prev = lattice_theta(m, agent_kw.get('turn_angle', 30), seed)
+    ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **agent_kw)
+    ga = S.SimGradientAgent(m, **agent_kw)
+    ga.theta[0] = theta0
+    ga.record_sense_cells = record
+    ga.fuse_move = fuse
+    rng = np.random.default_rng(seed)
+    robs = ref._get_current_obs
+    w = field[1]
+    seen_flags = set()
+    for it in range(iters):
+        coin = rng.integers(0, 2, m)
+        ract = ra.forward(robs, coin=coin.copy())
+        gact = ga.forward(env, coin=coin, use_hints=use_hints)[0]
+        seen_flags.add(ga.last_flags)
+        if record:
+            sx, sy = ra.last_sense_cells
+            assert np.array_equal((sx * w + sy).astype(np.int32), ga.sense_cells[0]), f"sense cells, step {it}"
+        assert np.array_equal(ga.theta[0], ra._direction_rads), f"theta differs at step {it}"
+        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        robs, rr, _, _, rinfo = ref.step(ract)
+        flags = L.STEP_ALIVE_BITS | (L.STEP_ADOPT_MOVE if fuse else 0)
+        r, alive = env.step(gact, flags=flags)
+        assert np.array_equal(ref_cells_linear(ref), env.cells()[0]), f"cells differ at step {it}"
+        assert rinfo['num_agents'] == alive[0]
+        assert _rel(rr, r[0]) < 1e-11
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+    return env, ga, seen_flags
+
+
+def test_physarum_free_run_with_env_hints(portable_math):
+    """Published gradient + cell cache (the steady-state path of the drop-in loop)."""
+    _, _, flags = _physarum_free_run((48, 80), 30, PHYS)
+    assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
+
+
+def test_physarum_free_run_without_hints(portable_math):
+    """die_gradient_forward: cells resolved and np.gradient evaluated per sample (4 chem gathers)."""
+    _physarum_free_run((45, 131), 20, dict(scale=0.02, turn_angle=35, sense_angle=120, sense_offset=0.06,
+                                           turn_tolerance=0.05), seed=5, use_hints=False)
+
+
+def test_physarum_free_run_fused_move(portable_math):
+    """The forward kernel evaluates the move + claims speculatively, the step adopts them (feed commits positions)."""
+    _physarum_free_run((40, 72), 20, dict(scale=0.02, turn_angle=30, sense_offset=0.06), seed=8, fuse=True)
+
+
+def test_physarum_limit_boundary_sigma08_infinite_food_zero_cost(portable_math):
+    _physarum_free_run((33, 70), 15, PHYS, seed=4,
+                       dynamics_kw=dict(boundary=D.BoundaryCondition.limit, diffuse_sigma=0.8, food_infinite=True,
+                                        op_action_cost=D.zero_cost),
+                       ref_dynamics_kw=dict(boundary='limit', diffuse_sigma=0.8, food_infinite=True,
+                                            op_action_cost=R.zero_cost))
+
+
+@pytest.mark.parametrize("mode", ['reflect', 'nearest', 'mirror', 'constant'])
+def test_diffuse_modes(portable_math, mode):
+    _physarum_free_run((20, 37), 8, PHYS, seed=6, dynamics_kw=dict(diffuse_mode=mode, diffuse_sigma=0.8))
+
+
+def test_no_diffusion(portable_math):
+    """blur radius 0 (sigma 0.1): the no-blur field kernel; no gradient is published then."""
+    _physarum_free_run((20, 37), 8, PHYS, seed=6, dynamics_kw=dict(diffuse_sigma=0.1))
+
+
+# ------------------------------------------------------------------------------------------
+# A-B: every instantiation the dispatcher can pick gives the same bits
+# ------------------------------------------------------------------------------------------
+def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
+    """Free run with in-kernel Philox coins (the LEAN forward's precondition) -> final state."""
+    refs, env = make_pair(field, seed=seed, batch=batch)
+    m = env.M
+    ga = S.SimGradientAgent(m, B=env.B, seed=3, **agent_kw)
+    for b in range(env.B):
+        ga.theta[b] = lattice_theta(m, 30, seed + b)[0]
+    ga.record_sense_cells = record
+    rewards = []
+    for it in range(iters):
+        act = ga.forward(env)
+        r, _ = env.step(act)
+        rewards.append(r)
+    return env.medium.copy(), env.agents.copy(), ga.theta.copy(), np.array(rewards)
+
+
+@pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
+                                        ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0])])
+def test_tuning_switches_do_not_change_results(tuning, key, values):
+    base = _philox_run((40, 72), 12)
+    for v in values:
+        tuning(key, v)
+        out = _philox_run((40, 72), 12)
+        for a, b, what in zip(base, out, ("medium", "agents", "theta", "reward")):
+            assert np.array_equal(a, b), f"{key}={v}: {what} differs"
+
+
+@pytest.mark.parametrize("sigma", [0.3, 0.5, 0.8])
+def test_march_field_kernel_equals_tile_kernel(tuning, sigma):
+    """field_impl = 1: the register-tiled warp-marching kernel (radii 1..3), ragged widths included."""
+    outs = []
+    for impl in (0, 1):
+        tuning("field_impl", impl)
+        (ref,), env = make_pair((67, 45), seed=13, dynamics_kw=dict(diffuse_sigma=sigma))
+        ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
+        ga.theta[0] = lattice_theta(env.M, 30, 13)[0]
+        for it in range(6):
+            env.step(ga.forward(env))
+        outs.append((env.medium.copy(), env.agents.copy(), env.gradient()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_batched_envs_match_single_envs():
+    """B = 3 environments in one set of launches == three single environments (same Philox coins: the in-kernel
+    RNG is keyed on (environment, slot), not on the launch geometry)."""
+    med, ag, th, rw = _philox_run((32, 48), 8, batch=3)
+    # single environments see the same coins only through injected draws, so compare against the oracle instead
+    refs, env = make_pair((32, 48), seed=11, batch=3)
+    m = env.M
+    ga = S.SimGradientAgent(m, B=3, seed=3, **PHYS)
+    singles = []
+    for b in range(3):
+        ga.theta[b] = lattice_theta(m, 30, 11 + b)[0]
+        e1 = S.SimEnv((32, 48), refs[b].medium, refs[b].agents)
+        a1 = S.SimGradientAgent(m, seed=3, **PHYS)
+        a1.theta[0] = ga.theta[b]
+        singles.append((e1, a1))
+    rng = np.random.default_rng(0)
+    for it in range(8):
+        coin = rng.integers(0, 2, (3, m))
+        env.step(ga.forward(env, coin=coin))
+        for b, (e1, a1) in enumerate(singles):
+            e1.step(a1.forward(e1, coin=coin[b]))
+    for b, (e1, a1) in enumerate(singles):
+        assert np.array_equal(env.medium[b], e1.medium[0])
+        assert np.array_equal(env.agents[b], e1.agents[0])
+        assert np.array_equal(ga.theta[b], a1.theta[0])
+        assert env.reward[b] == e1.reward[0] and env.alive[b] == e1.alive[0]
+
+
+def test_gradient_agent_inertia_noise(portable_math):
+    """GradientAgent (no discrete turn): momentum with injected noise, prev_grad state."""
+    (ref,), env = make_pair((40, 56), seed=21)
+    m = env.M
+    kw = dict(scale=0.01, deposit=4.0, inertia=0.9, sense_offset=0.02, noise_scale=0.025)
+    rng = np.random.default_rng(21)
+    prev = rng.normal(0., 0.4, size=(2, m))
+    ra = R.GradientAgent(max_agents=m, prev_grad=prev.copy(), **kw)
+    ga = S.SimGradientAgent(m, discrete_turn=False, **kw)
+    ga.theta[0] = R.get_radians(prev)
+    ga.prev_grad[0] = prev
+    robs = ref._get_current_obs
+    for it in range(10):
+        noise = rng.normal(0., 0.4, size=(2, m))
+        ract = ra.forward(robs, noise=noise.copy())
+        gact = ga.forward(env, noise=noise)[0]
+        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        assert np.array_equal(ga.theta[0], ra._direction_rads)
+        robs, rr, *_ = ref.step(ract)
+        r, _ = env.step(gact)
+        assert _rel(rr, r[0]) < 1e-11
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+
+
+def test_host_buffer_step_is_chunked_and_identical(tuning):
+    """die_env_step_host cuts the batch into chunks on two streams; same results as the device-pointer step."""
+    tuning("host_chunk_min_kb", 0)
+    try:
+        outs = []
+        for host in (False, True):
+            refs, env = make_pair((24, 32), seed=17, batch=9)
+            ga = S.SimGradientAgent(env.M, B=9, seed=2, **PHYS)
+            for b in range(9):
+                ga.theta[b] = lattice_theta(env.M, 30, b)[0]
+            for it in range(4):
+                act = ga.forward(env, use_hints=False)
+                if host:
+                    (ag_h, med_h), _, _ = env.step_host(act)
+                    assert np.array_equal(ag_h, env.agents) and np.array_equal(med_h, env.medium)
+                else:
+                    env.step(act)
+            outs.append((env.medium.copy(), env.agents.copy(), env.reward.copy(), env.alive.copy()))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+    finally:
+        tuning("host_chunk_min_kb", 32 << 10)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases of the reference's semantics, on the emulated kernels
+# ------------------------------------------------------------------------------------------
+def test_everybody_on_one_cell_and_full_occupancy():
+    h, w = 8, 8
+    m = h * w
+    medium = np.zeros((3, h, w))
+    medium[1] = 0.5
+    agents = np.zeros((4, m))
+    agents[2] = 1.0                     # all alive, all at (0, 0)
+    agents[3] = 0.3
+    env = S.SimEnv((h, w), medium, agents)
+    action = np.zeros((3, m))
+    action[2] = np.arange(m) + 1.0      # deposit of slot i = i + 1: the LAST slot's deposit must land (Q2)
+    env.step(action)
+    # chem before blur had one cell = m (last writer); blur * decay conserves mass * 0.9
+    assert abs(env.medium[0, 2].sum() - 0.9 * m) < 1e-9
+    assert env.medium[0, 0].sum() == 1.0 and env.medium[0, 0, 0, 0] == 1.0
+    # every slot eats the full rate_feed * food of the cell (Q7), the cell loses it once
+    assert np.allclose(env.agents[0, 3], 0.3 + 0.1 * 0.5 - 0.02 * (np.arange(m) + 1.0))
+    assert env.medium[0, 1, 0, 0] == 0.5 - 0.1 * 0.5
+    assert env.alive[0] == m
+
+
+def test_fewer_and_more_slots_than_cells(portable_math):
+    for m in (50, 700):
+        h, w = 16, 24
+        rng = np.random.default_rng(m)
+        medium = np.zeros((3, h, w))
+        medium[1] = rng.random((h, w)).round(3)
+        agents = np.zeros((4, m))
+        n = m // 3
+        agents[0, :n] = rng.integers(0, h, n) / (h - 1)
+        agents[1, :n] = rng.integers(0, w, n) / (w - 1)
+        agents[2, :n] = 1.0
+        agents[3, :n] = 0.5
+        env = S.SimEnv((h, w), medium, agents)
+        ga = S.SimGradientAgent(m, seed=1, **PHYS)
+        for it in range(5):
+            env.step(ga.forward(env))
+        assert env.alive[0] == n
+        assert np.isfinite(env.medium).all() and np.isfinite(env.agents).all()
+        assert env.medium[0, 0].sum() <= n
+
+
+def test_smallest_field():
+    """2 x 2: coordinate 1.0 wraps to 0.0 on the move (Q3), so both agents end on cell (0, 0); the oracle agrees."""
+    medium = np.zeros((3, 2, 2))
+    medium[1] = [[0.2, 0.4], [0.6, 0.8]]
+    agents = np.array([[0., 1., 0., 0.], [1., 0., 0., 0.], [1., 1., 0., 0.], [.5, .5, 0., 0.]])
+    ref = R.Env((2, 2), R.Dynamics(), medium=medium, agents=agents)
+    env = S.SimEnv((2, 2), medium, agents)
+    act = np.zeros((3, 4))
+    act[2, :2] = [1.0, 2.0]
+    for it in range(3):
+        _, rr, _, _, info = ref.step(act)
+        r, alive = env.step(act)
+        assert alive[0] == 2 == info['num_agents']
+        assert _rel(rr, r[0]) < 1e-12
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+    assert env.medium[0, 0].tolist() == [[1., 0.], [0., 0.]]
+
+
+# ------------------------------------------------------------------------------------------
+# the library's other kernels
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field,ratio", [((24, 32), 0.1), ((37, 70), 0.02)])
+def test_sense_mask_kernel(field, ratio):
+    from die_b200.env import gaussian_kernel1d
+    (ref,), env = make_pair(field, seed=9, ratio=ratio, ref_dynamics_kw=dict(apply_sense_mask=True))
+    w = np.ascontiguousarray(gaussian_kernel1d(2.0))
+    obs = np.full_like(env.medium, np.nan)
+    S.check(S.lib().die_sense_mask(field[0], field[1], 1, S.ptr(w), (len(w) - 1) // 2, S.ptr(env.medium), S.ptr(obs), None))
+    assert np.array_equal(obs[0], ref._get_current_obs[1])
+
+
+@pytest.mark.parametrize("field,colors", [((24, 32), 'rgb'), ((37, 53), 'one')])
+def test_render_kernel(field, colors):
+    (ref,), env = make_pair(field, seed=9, ratio=0.2)
+    rr = R.EnvRenderer(field, field_colors_id=colors)
+    h, w = field
+    trace = np.zeros((1, h, w))
+    img_m = np.full((1, h, w, 3), np.nan)
+    img_a = np.full((1, env.M, 4), np.nan)
+    color = None if rr._color is None else np.ascontiguousarray(rr._color)
+    ra = R.BrownianAgent(0.02)
+    rng = np.random.default_rng(1)
+    for it in range(3):
+        frames = rr.render(ref.medium, ref.agents)
+        S.check(S.lib().die_render_frames(h, w, env.M, 1, S.ptr(env.medium), S.ptr(env.agents), S.ptr(trace), rr._decay,
+                                          S.ptr(color), S.ptr(img_m), S.ptr(img_a), None))
+        assert np.array_equal(img_m[0], frames[0])
+        assert np.array_equal(trace[0], frames[1])
+        assert np.array_equal(img_a[0].reshape(frames[2].shape), frames[2])
+        act = ra.forward(ref._get_current_obs, u=rng.random((3, env.M)))
+        ref.step(act)
+        env.step(act)
+
+
+def test_math_kernels_equal_the_host_build():
+    from oracle import portable_math
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 5000), [0.0, -0.0, np.pi, -np.pi, 1e-300, 1e6]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    S.check(S.lib().die_math_sincos(S.ptr(x), S.ptr(s), S.ptr(c), len(x), None))
+    ps, pc = portable_math.sincos(x)
+    assert np.array_equal(s, ps) and np.array_equal(c, pc)
+    y = rng.normal(size=len(x))
+    for fast in (0, 1):
+        out = np.empty_like(x)
+        S.check(S.lib().die_math_atan2(S.ptr(y), S.ptr(x), S.ptr(out), len(x), fast, None))
+        assert np.array_equal(out, portable_math.atan2(y, x, fast=bool(fast)))
+
+
+def test_emulator_reports_a_deadlock_instead_of_hanging(tmp_path):
+    """The scheduler's own safety net: a barrier that part of a block never reaches is an error, not a hang."""
+    import ctypes, subprocess, textwrap
+    from tests.hostsim import build as B
+    src = tmp_path / "dead.cpp"
+    src.write_text(textwrap.dedent('''
+        #include "cuda_runtime.h"
+        static void bad_kernel(int* out) { if (threadIdx.x < 16) __syncthreads(); else { for (;;) { __syncthreads(); } } out[0] = 1; }
+        static void good_kernel(int* out) { __shared__ int s[64]; s[threadIdx.x] = threadIdx.x; __syncthreads();
+                                            int v = __shfl_sync(0xffffffffu, s[63 - threadIdx.x], (threadIdx.x + 1) & 31);
+                                            out[blockIdx.x * 64 + threadIdx.x] = v + (int)__ballot_sync(0xffffffffu, threadIdx.x & 1); }
+        extern "C" int run_bad(int* out) { hostsim::launch(dim3(1), dim3(64), 0, nullptr, bad_kernel, out); return cudaGetLastError(); }
+        extern "C" int run_good(int* out) { hostsim::launch(dim3(2), dim3(64), 0, nullptr, good_kernel, out); return cudaGetLastError(); }
+    '''))
+    so = tmp_path / "dead.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", B.HERE, "-o", str(so), str(src),
+                    B.os.path.join(B.HERE, "hostsim.cpp")], check=True)
+    lib = ctypes.CDLL(str(so))
+    out = np.zeros(128, dtype=np.int32)
+    assert lib.run_good(out.ctypes.data_as(ctypes.c_void_p)) == 0
+    t = np.arange(64)
+    src_lane = (t & ~31) | ((t + 1) & 31)
+    assert np.array_equal(out[:64], (63 - src_lane) + 0xAAAAAAAA - (1 << 32))
+    assert np.array_equal(out[64:], out[:64])
