@@ -194,3 +194,98 @@ def brownian_forward(agents, move_scale=0.01, deposit_scale=0.5, u=None, seed=0,
     u_a = None if u is None else np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(B, 3, M))
     check(lib().die_brownian_forward(ptr(agents), ptr(action), M, B, move_scale, deposit_scale, ptr(u_a), seed, step, None))
     return action if agents.ndim == 3 else action[0]
+
+
+class SimSlabWorld:
+    """die_b200.slab.EmulatedSlabWorld's call sequence on numpy arrays: one field split into row slabs over G
+    "ranks", all in this process; the peer tables are arrays of numpy base addresses."""
+
+    def __init__(self, medium, agents, theta, G, dynamics: Dynamics = None, corner_r=0, **physarum_kw):
+        from die_b200.slab import split_global_state, _physarum_params
+        self.lib = lib()
+        self.dynamics = dynamics or Dynamics()
+        self.layout, mediums, locals_ = split_global_state(medium, agents, G)
+        Lo, rp, W = self.layout, self.layout.rows_per, self.layout.W
+        self.G = G
+
+        def alloc(shapes, dtype, fill):
+            arrs = [np.full(s, fill, dtype=dtype) for s in shapes]
+            return arrs, np.array([a.ctypes.data for a in arrs], dtype=np.int64)
+
+        self.med_a, self.tbl_a = alloc([(3, rp, W)] * G, np.float64, np.nan)
+        self.med_b, self.tbl_b = alloc([(3, rp, W)] * G, np.float64, np.nan)
+        self.claim, self.tbl_c = alloc([(rp * W,)] * G, np.int32, -1)
+        self.cons, self.tbl_k = alloc([(rp * W,)] * G, np.float64, 0.0)
+        self.grad, self.tbl_g = alloc([(rp * W, 2)] * G, np.float64, 0.0)
+        self.act, self.tbl_act = alloc([(3, max(Lo.local_slots(q), 1)) for q in range(G)], np.float64, 0.0)
+        self.params = _physarum_params(**physarum_kw)
+        self.handles, self.agents, self.theta, self.stats = [], [], [], []
+        self.cur = 0
+        self.grad_valid = self.cells_valid = False
+        self.corner_r = 0
+        cdyn = _dynamics_to_c(self.dynamics)
+        for q in range(G):
+            self.med_a[q][...] = mediums[q]
+            self.agents.append(np.ascontiguousarray(locals_[q]).copy())
+            self.theta.append(np.ascontiguousarray(theta[Lo.global_ids(q)]).copy())
+            self.stats.append(np.zeros(2))
+            h = C.c_void_p()
+            geom = Lo.to_c(q)
+            check(self.lib.die_slab_create(C.byref(geom), C.byref(cdyn), C.byref(h)))
+            check(self.lib.die_slab_bind(h, ptr(self.tbl_a), ptr(self.tbl_b), ptr(self.tbl_c), ptr(self.tbl_k),
+                                         ptr(self.tbl_g), ptr(self.tbl_act)))
+            if corner_r:
+                self.corner_r = min(corner_r, Lo.H // 2, Lo.W // 2)
+                check(self.lib.die_slab_set_corner_mirror(h, self.corner_r))
+            self.handles.append(h)
+        self._step = 0
+
+    def __del__(self):
+        try:
+            for h in self.handles:
+                self.lib.die_slab_destroy(h)
+            self.handles = []
+        except Exception:
+            pass
+
+    def forward(self, coin_global=None):
+        hints = (1 if self.grad_valid else 0) | (2 if self.cells_valid else 0)
+        for q, h in enumerate(self.handles):
+            coin = None
+            if coin_global is not None:
+                coin = np.ascontiguousarray(coin_global[self.layout.global_ids(q)]).astype(np.uint8)
+            check(self.lib.die_slab_forward(h, C.byref(self.params), self.cur, ptr(self.agents[q]), ptr(self.theta[q]),
+                                            ptr(self.act[q]), ptr(coin), hints, q, self._step, None))
+
+    def step(self):
+        for q, h in enumerate(self.handles):
+            check(self.lib.die_slab_move_claim(h, ptr(self.agents[q]), ptr(self.act[q]), None))
+        self.cells_valid = True
+        for h in self.handles:                      # (barrier)
+            check(self.lib.die_slab_field(h, self.cur, 1, None))
+        self.cur = 1 - self.cur
+        self.grad_valid = True
+        if self.corner_r > 0:
+            for h in self.handles:                  # (barrier)
+                check(self.lib.die_slab_corner_refresh(h, 1 - self.cur, 1, None))
+        for q, h in enumerate(self.handles):
+            check(self.lib.die_slab_feed(h, ptr(self.agents[q]), ptr(self.act[q]), ptr(self.stats[q]), None))
+        self._step += 1
+        stats = np.stack(self.stats)
+        return float(stats[:, 0].sum()), int(round(stats[:, 1].sum()))
+
+    def gather(self):
+        Lo = self.layout
+        med = self.med_a if self.cur == 0 else self.med_b
+        medium = np.concatenate(med, axis=1)
+        agents, theta = np.zeros((4, Lo.M)), np.zeros(Lo.M)
+        action, cells = np.zeros((3, Lo.M)), np.zeros(Lo.M, dtype=np.int32)
+        for q, h in enumerate(self.handles):
+            ids = Lo.global_ids(q)
+            n = len(ids)
+            agents[:, ids] = self.agents[q]
+            theta[ids] = self.theta[q]
+            action[:, ids] = self.act[q][:, :n]
+            p = self.lib.die_slab_cells(h)
+            cells[ids] = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n]
+        return medium, agents, theta, action, cells

@@ -421,3 +421,125 @@ def test_emulator_reports_a_deadlock_instead_of_hanging(tmp_path):
     src_lane = (t & ~31) | ((t + 1) & 31)
     assert np.array_equal(out[:64], (63 - src_lane) + 0xAAAAAAAA - (1 << 32))
     assert np.array_equal(out[64:], out[:64])
+
+
+# ------------------------------------------------------------------------------------------
+# one field over G ranks (row slabs, peer-pointer kernels): the emulated multi-rank world == the single env
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,G,band", [((32, 40), 2, 0), ((48, 36), 3, 0), ((64, 32), 8, 0), ((32, 40), 2, 5),
+                                          ((48, 36), 3, 2), ((64, 32), 4, 16)])
+def test_slab_world_equals_single_env(shape, G, band):
+    phys = dict(scale=0.02, turn_angle=30, sense_offset=0.08)      # large moves: agents cross slab seams quickly
+    (ref,), env = make_pair(shape, seed=31, ratio=0.15)
+    m = env.M
+    theta0, _ = lattice_theta(m, 30, 31)
+    ga = S.SimGradientAgent(m, **phys)
+    ga.theta[0] = theta0
+    world = S.SimSlabWorld(env.medium[0], env.agents[0], theta0, G, corner_r=band, **phys)
+    rng = np.random.default_rng(1)
+    crossed = 0
+    for it in range(12):
+        coin = rng.integers(0, 2, m)
+        act = ga.forward(env, coin=coin)[0]
+        world.forward(coin)
+        r, alive = env.step(act)
+        wr, walive = world.step()
+        wmed, wag, wth, wact, wcells = world.gather()
+        assert np.array_equal(wact, act), f"action differs at step {it}"
+        assert np.array_equal(wcells, env.cells()[0]), f"cells differ at step {it}"
+        assert np.array_equal(wmed, env.medium[0]), f"medium differs at step {it}"
+        assert np.array_equal(wag, env.agents[0]), f"agents differ at step {it}"
+        assert np.array_equal(wth, ga.theta[0]), f"theta differs at step {it}"
+        assert walive == alive[0]
+        assert abs(wr - r[0]) <= 1e-11 * max(1.0, abs(r[0]))
+        owner_of_cell = (wcells // shape[1]) // (shape[0] // G)
+        slot_owner = np.concatenate([np.full(world.layout.local_slots(q), q) for q in range(G)])
+        ids = np.concatenate([world.layout.global_ids(q) for q in range(G)])
+        crossed = max(crossed, int((owner_of_cell[ids] != slot_owner).sum()))
+    assert crossed > 0, "the test must exercise agents standing on another rank's slab"
+
+
+# ------------------------------------------------------------------------------------------
+# the committed golden vectors (tests/golden: recorded by executing the reference's own source,
+# oracle/make_golden_from_reference.py) replayed through the emulated kernels
+# ------------------------------------------------------------------------------------------
+import os      # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_brownian_golden_bit_exact():
+    g = np.load(os.path.join(GOLD, "brownian_24x32.npz"))
+    size = tuple(int(v) for v in g["size"])
+    env = S.SimEnv(size, g["medium0"], g["agents0"])
+    np.random.seed(int(g["loop_seed"]))
+    m = env.M
+    for k in range(len(g["rewards"])):
+        u = np.stack([np.random.random_sample(m) for _ in range(3)])      # the reference's draw order: dx, dy, deposit1
+        act = S.brownian_forward(env.agents[0], float(g["move_scale"]), float(g["deposit_scale"]), u=u)
+        assert np.array_equal(act, g["actions"][k]), k
+        r, alive = env.step(act)
+        assert abs(r[0] - g["rewards"][k]) <= 1e-12 * max(1.0, abs(g["rewards"][k]))
+        assert alive[0] == g["num_agents"][k]
+    assert np.array_equal(env.medium[0], g["medium_final"]) and np.array_equal(env.agents[0], g["agents_final"])
+
+
+GOLDEN_CASES = {
+    "physarum_24x32.npz": (dict(), dict(scale=0.007, turn_angle=30, sense_offset=0.04)),
+    "physarum_limit_sigma08_20x20.npz": (
+        dict(boundary=D.BoundaryCondition.limit, diffuse_sigma=0.8, food_infinite=True, op_action_cost=D.zero_cost),
+        dict(scale=0.03, turn_angle=35, sense_angle=120, sense_offset=0.06, turn_tolerance=0.05)),
+    "physarum_waveflow_24x32.npz": (dict(waveflow=(0.5, 0.5)), dict(scale=0.007, turn_angle=30, sense_offset=0.04)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_physarum_golden_every_step(name):
+    """Same bar as tests/test_gpu_golden.py: every recorded step from its recorded pre-state; decisions, cells,
+    occupancy and the deposit channel exact; headings / moves to 1e-13 (die_math.h vs the recording host's libm);
+    Env.step on the recorded action bit-exact in every field (the wave flow's per-cell cosine: 1e-15)."""
+    g = np.load(os.path.join(GOLD, name))
+    dyn_kw, agent_kw = GOLDEN_CASES[name]
+    dyn_kw = dict(dyn_kw)
+    size = tuple(int(v) for v in g["size"])
+    wf = dyn_kw.pop("waveflow", None)
+    flow = D.WaveSequence(size, dt=0.01).get_flow_operator(scale=wf[0], decay=wf[1]) if wf is not None else None
+    m = g["agents_pre"].shape[-1]
+    for k in range(len(g["reward"])):
+        env = S.SimEnv(size, g["medium_pre"][k], g["agents_pre"][k], D.Dynamics(**dyn_kw))
+        if flow is not None:
+            flow.calls = k
+            env.set_food_flow(flow)
+        agent = S.SimGradientAgent(m, **agent_kw)
+        agent.theta[0] = g["theta_pre"][k]
+        act = agent.forward(env, coin=g["coin"][k])[0]
+        assert np.array_equal(act[2], g["action"][k][2]), f"deposit differs at step {k}"
+        np.testing.assert_allclose(act[:2], g["action"][k][:2], rtol=0, atol=1e-15)
+        d = np.abs((agent.theta[0] - g["theta_post"][k] + np.pi) % (2 * np.pi) - np.pi)
+        assert d.max() < 1e-13, f"heading differs at step {k}"
+        r, alive = env.step(g["action"][k])
+        med, ag = env.medium[0].copy(), env.agents[0]
+        if flow is not None:
+            np.testing.assert_allclose(med[1], g["medium_post"][k][1], rtol=0, atol=1e-15)
+            med[1] = g["medium_post"][k][1]
+        assert np.array_equal(med, g["medium_post"][k]) and np.array_equal(ag, g["agents_post"][k]), k
+        assert abs(r[0] - g["reward"][k]) <= 1e-12 * max(1.0, abs(g["reward"][k]))
+        assert alive[0] == g["num_agents"][k]
+
+
+@pytest.mark.parametrize("field,impl,sigma", [((24, 40), 0, 0.5), ((37, 53), 1, 0.5), ((20, 20), 0, 0.1)])
+def test_wave_flow_bit_exact_with_portable_math(portable_math, tuning, field, impl, sigma):
+    tuning("field_impl", impl)
+    rflow = R.WaveSequence(field, dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
+    gflow = D.WaveSequence(field, dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
+    (ref,), env = make_pair(field, seed=5, dynamics_kw=dict(diffuse_sigma=sigma),
+                            ref_dynamics_kw=dict(op_food_flow=rflow, diffuse_sigma=sigma))
+    env.set_food_flow(gflow)
+    ra = R.BrownianAgent(0.01)
+    rng = np.random.default_rng(3)
+    for it in range(10):
+        act = ra.forward(ref._get_current_obs, u=rng.random((3, env.M)))
+        _, rr, *_ = ref.step(act)
+        r, _ = env.step(act)
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+        assert abs(rr - r[0]) <= 1e-10 * max(1.0, abs(rr))
