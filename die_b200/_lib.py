@@ -73,6 +73,7 @@ SIGNATURES = {
     "die_env_cells": (_P, [_P]),
     "die_env_publish_gradient": (C.c_int, [_P, C.c_int32]),
     "die_env_gradient": (_P, [_P]),
+    "die_env_gradient_kind": (C.c_int, [_P]),
     "die_env_set_profiling": (C.c_int, [_P, C.c_int32]),
     "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "die_env_read_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -122,6 +122,8 @@ struct GradientArgs {
     const double* noise;        // may be null -> Philox Box-Muller (only if noise_scale != 0)
     int32_t* sense_cells;       // may be null
     const double2* grad;        // may be null: np.gradient(chem1) per cell, published by Env.step
+    const float2* grad32;       // may be null: the same, rounded to float32 (only offered when the gradient is used for
+                                // the guard-banded turn DECISION alone: discrete turn, plan enabled, normalised)
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
     int b0;                     // the launch covers environments [b0, b0 + B') of a larger batch (pointers already offset):
@@ -155,10 +157,25 @@ __device__ __noinline__ die_turn_t turn_exact_call(double gx, double gy, double 
     return die_turn_exact(gx, gy, th, atol, sense_radians);
 }
 
+// np.gradient of chem at cell (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
+// f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
+__device__ __forceinline__ void sample_gradient(const double* __restrict__ chem, int sx, int sy, int H, int W,
+                                                double& gx, double& gy) {
+    const int sc = sx * W + sy;
+    const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
+    const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
+    gx = chem[sc + xp] - chem[sc + xm];
+    gy = chem[sc + yp] - chem[sc + ym];
+    if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
+    if (yp - ym == 2) gy *= 0.5;
+}
+
 // LEAN: the steady-state configuration of the Physarum loop is known at compile time -- in-kernel Philox coins, no
 // momentum state, no recorded sense cells, the env's published gradient and cell cache valid -- so the per-item null
 // checks and parameter reloads of the general kernel fold away.  Same arithmetic, same results.
-template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false>
+// G32 (LEAN only): the published gradient is the float32 one.  die_turn_quick rounds the gradient to float32 first
+// thing, so every decision it settles is the same; a slot it defers re-samples the float64 gradient from chem1.
+template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false, bool G32 = false>
 __global__ void __launch_bounds__(kAgentThreads, MINB)
 gradient_forward_kernel(const GradientArgs a) {
     const die_gradient_params_t& p = a.p;
@@ -179,7 +196,8 @@ gradient_forward_kernel(const GradientArgs a) {
     const uint8_t* coin_p = (!LEAN && a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
     const double* nz = (!LEAN && a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
     int32_t* sc_p = (!LEAN && a.sense_cells != nullptr) ? a.sense_cells + ch.b * M + first : nullptr;
-    const double2* grad = (LEAN || a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
+    const double2* grad = ((LEAN && !G32) || a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
+    const float2* grad32 = (G32 || (!LEAN && !SLAB && a.grad32 != nullptr)) ? a.grad32 + ch.b * C : nullptr;
     const int32_t* cl_p = (LEAN || a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
     int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
     int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
@@ -235,7 +253,12 @@ gradient_forward_kernel(const GradientArgs a) {
         const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
         if (!LEAN && sc_p != nullptr) sc_p[i] = sc;
         double gx, gy;
-        if (LEAN || (SLAB ? a.st.grad != nullptr : grad != nullptr)) {   // published by the field pass: one 16-byte gather
+        const bool from32 = G32 || (!LEAN && grad32 != nullptr);
+        if (from32) {                                                    // published as float32: one 8-byte gather
+            const float2 g2 = grad32[sc];
+            gx = (double)g2.x;
+            gy = (double)g2.y;
+        } else if (LEAN || (SLAB ? a.st.grad != nullptr : grad != nullptr)) {   // published by the field pass: one 16-byte gather
             // read-only for the whole launch: ld.global.nc lets L1 cache lines that live on a peer GPU
             // (the ghost slots of every rank all look at the same few cells near the corners)
             const double2 g2 = SLAB ? slab_load_grad(a.st, a.sg, sc) : grad[sc];
@@ -251,7 +274,7 @@ gradient_forward_kernel(const GradientArgs a) {
                 gx = chem[sc + xp] - chem[sc + xm];
                 gy = chem[sc + yp] - chem[sc + ym];
             }
-            if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
+            if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly (as sample_gradient)
             if (yp - ym == 2) gy *= 0.5;
         }
 
@@ -264,6 +287,7 @@ gradient_forward_kernel(const GradientArgs a) {
             die_turn_t tr;
             double dr = 1.0;
             if (!((LEAN || a.plan.enabled) && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
+                if (from32) sample_gradient(chem, sx, sy, H, W, gx, gy);     // the exact path wants all 53 bits
                 if (LEAN) {           // (normalised gradient: dr = 1)
                     tr = turn_exact_call(gx, gy, th, atol, p.sense_radians, 1, p.use_grad_clip, p.grad_clip);
                 } else {
@@ -385,8 +409,9 @@ constexpr int kFeedItems = 4;      // slots per thread
 // in place); this kernel then also commits the positions, pos = boundary(pos + action[dx, dy])
 // (core/env.py:152-172, the same two operations as move_claim_kernel).
 // BITS: alive-ness comes from the env's bitmask instead of the float64 channel (MOVE implies BITS).
-template <bool SLAB, bool MOVE, bool BITS>
-__global__ void __launch_bounds__(kAgentThreads)
+// MINB: minimum resident CTAs per SM (register cap 65536 / (256 MINB)); 0 = the compiler's own choice (74 registers, 3 CTAs)
+template <bool SLAB, bool MOVE, bool BITS, int MINB = 0>
+__global__ void __launch_bounds__(kAgentThreads, MINB)
 agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
                   const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
                   const int32_t* __restrict__ cells,

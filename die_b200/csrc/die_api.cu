@@ -50,6 +50,8 @@ struct die_env {
     double flow_scale, flow_keep;
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
+    float2* grad32;        // [B][H*W]  the same rounded to float32 (lazy; tuning "grad_f32")
+    int grad_kind;         // which of the two the LAST field pass wrote: 0 none, 1 grad, 2 grad32
     int publish_grad;
     double* part_gain;     // [B][nblk]
     int32_t* part_alive;   // [B][nblk]
@@ -140,6 +142,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     delete[] e->flow_ts;
     cudaFree(e->consumed);
     cudaFree(e->grad);
+    cudaFree(e->grad32);
     cudaFree(e->part_gain);
     cudaFree(e->part_alive);
     cudaFree(e->action_stage);
@@ -186,16 +189,36 @@ extern "C" int die_env_set_food_flow(die_env_t* e, const double* rwave_dev, cons
 
 extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells2[e->cur] : nullptr; }
 
+static int g_grad_f32 = 0;         // the field pass publishes np.gradient(chem1) as float32 pairs instead of float64 ones
+
+// the buffer the next field pass publishes into (allocated on first use)
+static int ensure_gradient_buffer(die_env* e) {
+    const size_t n = (size_t)e->H * e->W * e->B;
+    if (g_grad_f32) {
+        if (e->grad32 == nullptr) DIE_CUDA(cudaMalloc(&e->grad32, sizeof(float2) * n));
+    } else if (e->grad == nullptr) {
+        DIE_CUDA(cudaMalloc(&e->grad, sizeof(double2) * n));
+    }
+    return DIE_OK;
+}
+
 extern "C" int die_env_publish_gradient(die_env_t* e, int32_t on) {
     DIE_REQUIRE(e != nullptr);
-    if (on && e->grad == nullptr)
-        DIE_CUDA(cudaMalloc(&e->grad, sizeof(double2) * (size_t)e->H * e->W * e->B));
+    if (on) {
+        if (int rc = ensure_gradient_buffer(e)) return rc;
+    } else {
+        e->grad_kind = 0;
+    }
     e->publish_grad = on ? 1 : 0;
     return DIE_OK;
 }
 
 extern "C" const double* die_env_gradient(const die_env_t* e) {
-    return (e && e->publish_grad && e->dyn.blur_radius > 0) ? (const double*)e->grad : nullptr;
+    return (e && e->publish_grad && e->dyn.blur_radius > 0 && e->grad_kind != 2) ? (const double*)e->grad : nullptr;
+}
+
+extern "C" int die_env_gradient_kind(const die_env_t* e) {
+    return (e && e->publish_grad && e->dyn.blur_radius > 0) ? e->grad_kind : 0;
 }
 
 extern "C" int die_env_set_profiling(die_env_t* e, int32_t on) {
@@ -265,11 +288,12 @@ static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms 
 
 template <int R>
 static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
+    const bool want_grad = fa.grad != nullptr || fa.grad32 != nullptr;
     if constexpr (R <= 3) {
         if (g_field_impl == 1 && fa.diffuse_mode == DIE_DIFFUSE_WRAP)
-            return fa.grad != nullptr ? launch_march<R, true>(fa, B, st) : launch_march<R, false>(fa, B, st);
+            return want_grad ? launch_march<R, true>(fa, B, st) : launch_march<R, false>(fa, B, st);
     }
-    return fa.grad != nullptr ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
+    return want_grad ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
 }
 
 extern "C" int die_set_field_impl(int32_t impl) {
@@ -278,7 +302,7 @@ extern "C" int die_set_field_impl(int32_t impl) {
 }
 
 // Field pass over environments [b0, b0 + nb) of the batch; min / mout / action already point at environment b0.
-static cudaError_t launch_field_any(const die_env* e, int b0, int nb, const double* min, double* mout,
+static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* min, double* mout,
                                     const double* action, cudaStream_t st) {
     const size_t C = (size_t)e->H * e->W;
     FieldArgs a;
@@ -288,7 +312,14 @@ static cudaError_t launch_field_any(const die_env* e, int b0, int nb, const doub
     a.winner = e->winner + b0 * C;
     a.action = action;
     a.consumed = e->consumed + b0 * C;
-    a.grad = (e->publish_grad && e->dyn.blur_radius > 0) ? e->grad + b0 * C : nullptr;
+    if (e->publish_grad && e->dyn.blur_radius > 0) {
+        if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
+        if (g_grad_f32) a.grad32 = e->grad32 + b0 * C;
+        else a.grad = e->grad + b0 * C;
+        e->grad_kind = g_grad_f32 ? 2 : 1;
+    } else {
+        e->grad_kind = 0;
+    }
     a.M = e->M;
     a.H = e->H;
     a.W = e->W;
@@ -329,6 +360,7 @@ static cudaError_t launch_field_any(const die_env* e, int b0, int nb, const doub
 // Env.step
 // ------------------------------------------------------------------------------------------
 static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitmask (when valid) instead of the float64 channel
+static int g_feed_min_blocks = 1;  // register cap of the (plain, bitmask) feed kernel: 1 = unhinted (74 registers), 4 -> 64, 5 -> 48
 
 // The four launches of Env.step for environments [b0, b0 + nb) of the batch, on stream `st`.  Every pointer argument
 // refers to the WHOLE batch; the range is resolved here (all per-env arrays are contiguous per environment).
@@ -364,6 +396,8 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
     auto feed = fused ? agent_feed_kernel<false, true, true>
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
+    if (!fused && feed_bits && g_feed_min_blocks == 4) feed = agent_feed_kernel<false, false, true, 4>;
+    if (!fused && feed_bits && g_feed_min_blocks == 5) feed = agent_feed_kernel<false, false, true, 5>;
     feed<<<fgrid, kAgentThreads, 0, st>>>(
         agents, action, e->consumed + (size_t)b0 * C, winner, cells, part_gain, part_alive,
         (int64_t)C, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
@@ -613,6 +647,8 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value;      // 0 off, 1 on (4 CTAs/SM), 5: 48-register cap
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
+    else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
+    else if (strcmp(key, "feed_min_blocks") == 0) { DIE_REQUIRE(value == 1 || value == 4 || value == 5); g_feed_min_blocks = value; }
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;
 }
@@ -632,7 +668,8 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
                                  double* theta, double* prev_grad, double* action,
                                  const uint8_t* coin, const double* noise, int32_t* sense_cells,
                                  const double* grad_hint, const int32_t* cells_hint,
-                                 uint64_t seed, uint64_t step, void* stream, int b0 = 0) {
+                                 uint64_t seed, uint64_t step, void* stream, int b0 = 0,
+                                 const float2* grad32_hint = nullptr) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -650,6 +687,10 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     a.agents = agents; a.medium = medium; a.theta = theta; a.prev_grad = prev_grad;
     a.action = action; a.coin = coin; a.noise = noise; a.sense_cells = sense_cells;
     a.grad = (const double2*)grad_hint; a.cells = cells_hint;
+    // the float32 gradient serves the guard-banded turn decision only (die_turn.h); anything that needs the VALUE of
+    // the gradient (GradientAgent, unnormalised gradients, the exact turn path for every slot) samples chem1 instead
+    if (grad_hint == nullptr && grad32_hint != nullptr && p->discrete_turn && a.plan.enabled && p->normalized_grad)
+        a.grad32 = grad32_hint;
     a.seed = seed; a.step = step;
     a.b0 = b0;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
@@ -674,10 +715,15 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     // the steady-state Physarum configuration has its own instantiation (see LEAN in die_agent_kernels.cuh)
     const bool lean = g_fwd_lean && !speculate && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
                       prev_grad == nullptr && coin == nullptr && noise == nullptr && sense_cells == nullptr &&
-                      a.grad != nullptr && a.cells != nullptr && g_fwd_min_blocks == 4;
+                      (a.grad != nullptr || a.grad32 != nullptr) && a.cells != nullptr && g_fwd_min_blocks == 4;
     if (lean) {
-        if (g_fwd_lean == 5) kern = gradient_forward_kernel<true, false, false, 5, true>;
-        else kern = gradient_forward_kernel<true, false, false, 4, true>;
+        if (a.grad32 != nullptr) {
+            if (g_fwd_lean == 5) kern = gradient_forward_kernel<true, false, false, 5, true, true>;
+            else kern = gradient_forward_kernel<true, false, false, 4, true, true>;
+        } else {
+            if (g_fwd_lean == 5) kern = gradient_forward_kernel<true, false, false, 5, true>;
+            else kern = gradient_forward_kernel<true, false, false, 4, true>;
+        }
     }
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
@@ -711,9 +757,10 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
         }
     }
     const double* grad_hint = (flags & DIE_FWD_USE_GRADIENT) ? die_env_gradient(e) : nullptr;
+    const float2* grad32_hint = ((flags & DIE_FWD_USE_GRADIENT) && die_env_gradient_kind(e) == 2) ? e->grad32 : nullptr;
     const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;
     return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
-                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
+                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream, 0, grad32_hint);
 }
 
 // ------------------------------------------------------------------------------------------

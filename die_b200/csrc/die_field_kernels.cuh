@@ -33,6 +33,8 @@ struct FieldArgs {
     const double* action;        // [B][3][M]; channel 2 = deposit1
     double* consumed;            // [B][H*W] consumed_field out
     double2* grad;               // [B][H*W] np.gradient(chem_out) (raw d/dx, d/dy) or null
+    float2* grad32;              // the same pairs rounded to float32 (tuning "grad_f32"): what the guard-banded quick turn
+                                 // decision reads anyway (die_turn.h); at most one of grad / grad32 is set
     int H, W;
     int64_t M;
     int tiles_i, tiles_j;
@@ -239,7 +241,8 @@ field_step_kernel(const FieldArgs a) {
     __syncthreads();
 
     // ---- outputs: new chem, its np.gradient, elementwise channels ------------------------------
-    double2* grad = SLAB ? a.st.grad[a.sg.rank] : a.grad + b * C;
+    double2* grad = SLAB ? a.st.grad[a.sg.rank] : (a.grad != nullptr ? a.grad + b * C : nullptr);
+    float2* grad32 = (!SLAB && a.grad32 != nullptr) ? a.grad32 + b * C : nullptr;
     for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
         const int r = idx / TW, c = idx - r * TW;
         const int li = i0 + r, gj = j0 + c;
@@ -255,7 +258,8 @@ field_step_kernel(const FieldArgs a) {
             double gy = q[lp] - q[lm];
             if (up - um == 2 * OW) gx *= 0.5;
             if (lp - lm == 2) gy *= 0.5;
-            grad[g] = make_double2(gx, gy);
+            if (grad32 != nullptr) grad32[g] = make_float2((float)gx, (float)gy);
+            else grad[g] = make_double2(gx, gy);
 
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
@@ -318,7 +322,8 @@ field_march_kernel(const FieldArgs a, const MarchGeom geo) {
     const int32_t* win = a.winner + b * C;
     const double* dep = a.action + (b * 3 + 2) * a.M;
     double* cons = a.consumed + b * C;
-    double2* grad = GRAD ? a.grad + b * C : nullptr;
+    double2* grad = (GRAD && a.grad != nullptr) ? a.grad + b * C : nullptr;
+    float2* grad32 = (GRAD && a.grad32 != nullptr) ? a.grad32 + b * C : nullptr;
 
     double wk[R + 1];                                  // wk[k] = weight of taps at distance k
 #pragma unroll
@@ -403,7 +408,10 @@ field_march_kernel(const FieldArgs a, const MarchGeom geo) {
             if (col_out && rel >= 0 && rel < rows_here) {
                 const int g = (i0 + rel) * W + oc;
                 mout_b[2 * C + g] = centre;
-                if (GRAD) grad[g] = make_double2(gx, gy);
+                if (GRAD) {
+                    if (grad32 != nullptr) grad32[g] = make_float2((float)gx, (float)gy);
+                    else grad[g] = make_double2(gx, gy);
+                }
                 const double occ = (claim_line[0] >= 0) ? 1.0 : 0.0;    // claim of row t - CL = output row
                 const double f = fo[u];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224

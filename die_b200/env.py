@@ -400,7 +400,7 @@ class Env:
                     and agents.numel() == self._agents.numel():
                 cells_ptr = self._lib.die_env_cells(self._handle)
             if want_gradient and st[3]:
-                grad_ptr = self._lib.die_env_gradient(self._handle) or None
+                grad_ptr = self._lib.die_env_gradient_kind(self._handle) or None      # 1 float64, 2 float32 cache
         return grad_ptr, cells_ptr
 
     def _forward_flags(self, agents, medium, want_gradient: bool, speculate: bool) -> int:

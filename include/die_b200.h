@@ -126,6 +126,13 @@ const int32_t* die_env_cells(const die_env_t* env);   /* device ptr, int32 [B][M
  * medium / agents written by the last die_env_step and until they are modified by the caller. */
 int die_env_publish_gradient(die_env_t* env, int32_t on);
 const double* die_env_gradient(const die_env_t* env);
+/* With die_set_tuning("grad_f32", 1) the pairs are published rounded to float32 instead (8 bytes per cell written
+ * and gathered): the guard-banded turn decision of PhysarumAgent rounds the gradient to float32 anyway and re-samples
+ * chem1 in float64 whenever it defers to the reference arithmetic (die_b200/csrc/die_turn.h), so results do not
+ * change; a policy that uses the gradient's VALUE (GradientAgent) ignores the float32 cache.
+ * die_env_gradient_kind: what the last step published -- 0 nothing, 1 float64 (die_env_gradient()), 2 float32
+ * (internal; reached through die_env_forward_gradient's DIE_FWD_USE_GRADIENT). */
+int die_env_gradient_kind(const die_env_t* env);
 
 /* Per-kernel timing of Env.step with CUDA events recorded on the launching stream between
  * the step's kernels (measurement aid for bench.py's roofline; off by default).
@@ -262,7 +269,8 @@ int die_set_turn_quick(int32_t on);
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
  * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
- * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1. */
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1, "grad_f32" 0/1 (see die_env_gradient_kind),
+ * "feed_min_blocks" 1/4/5 (register cap of the feed kernel; 1 = the compiler's choice). */
 int die_set_tuning(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------------

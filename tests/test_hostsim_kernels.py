@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0, grad_f32=0, feed_min_blocks=1)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -151,6 +151,21 @@ def test_physarum_limit_boundary_sigma08_infinite_food_zero_cost(portable_math):
                                             op_action_cost=R.zero_cost))
 
 
+@pytest.mark.parametrize("impl,lean", [(0, 1), (1, 1), (0, 0)])
+def test_physarum_free_run_float32_gradient_cache(portable_math, tuning, impl, lean):
+    """grad_f32: the field pass (tile or march kernel) publishes np.gradient(chem1) as float32 pairs; the quick turn
+    decision reads those, deferred slots re-sample chem1 in float64.  Against the oracle, and with the structured
+    fields of a long run where gradients underflow float32 / sit on the clip threshold."""
+    tuning("grad_f32", 1)
+    tuning("field_impl", impl)
+    tuning("fwd_lean", lean)
+    env, ga, flags = _physarum_free_run((48, 80), 30, PHYS)
+    assert S.lib().die_env_gradient_kind(env.handle) == 2 and not S.lib().die_env_gradient(env.handle)
+    assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
+    # GradientAgent needs the gradient's value: the float32 cache must be ignored, results still exact
+    test_gradient_agent_inertia_noise(None)
+
+
 @pytest.mark.parametrize("mode", ['reflect', 'nearest', 'mirror', 'constant'])
 def test_diffuse_modes(portable_math, mode):
     _physarum_free_run((20, 37), 8, PHYS, seed=6, dynamics_kw=dict(diffuse_mode=mode, diffuse_sigma=0.8))
@@ -181,7 +196,8 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0])])
+                                        ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0]),
+                                        ("grad_f32", [1]), ("feed_min_blocks", [4, 5])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     base = _philox_run((40, 72), 12)
     for v in values:
@@ -543,3 +559,43 @@ def test_wave_flow_bit_exact_with_portable_math(portable_math, tuning, field, im
         r, _ = env.step(act)
         assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
         assert abs(rr - r[0]) <= 1e-10 * max(1.0, abs(rr))
+
+
+def test_float32_gradient_cache_on_adversarial_fields(tuning):
+    """Gradients that underflow / overflow float32, sit on the clip threshold, are exactly symmetric or exactly zero:
+    with the float32 cache every such slot must be deferred (and re-sampled in float64) exactly when it matters.
+    The state after each of 6 steps must equal the float64-cache run bit for bit, LEAN and general kernel."""
+    shape = (64, 64)
+    yy, xx = np.meshgrid(np.arange(64), np.arange(64))
+    blobs = np.zeros(shape)
+    for cx, cy in [(16, 16), (48, 16), (16, 48), (48, 48), (32, 32)]:
+        blobs += np.maximum(0, 6 - np.maximum(abs(xx - cx), abs(yy - cy))) * 0.25
+    rng = np.random.default_rng(5)
+    noise = rng.random(shape)
+    scales = [1e-300, 1e-50, 1e-46, 1e-44, 1e-40, 1e-10, 3e-6, 1e-5, 1.0, 1e20, 1e37, 1e39, 1e200, 0.0, 1e-5, 2e-5]
+    chem = blobs.copy()
+    for k, sc in enumerate(scales):                       # 4-row bands of noise at wildly different magnitudes
+        chem[4 * k:4 * k + 4, 32:] = noise[4 * k:4 * k + 4, 32:] * sc
+    chem[40:, :8] = 3e-6
+    outs = {}
+    for f32 in (0, 1):
+        for lean in (0, 1):
+            tuning("grad_f32", f32)
+            tuning("fwd_lean", lean)
+            (ref,), env = make_pair(shape, seed=3)
+            env.medium[0, 2] = chem
+            m = env.M
+            ga = S.SimGradientAgent(m, seed=2, **PHYS)
+            ga.theta[0] = np.random.default_rng(0).integers(-6, 7, m) * np.radians(30)
+            trace = []
+            for it in range(6):
+                act = ga.forward(env).copy()
+                env.step(act)
+                trace.append((act, ga.theta.copy(), env.medium.copy(), env.agents.copy()))
+            outs[(f32, lean)] = trace
+            assert S.lib().die_env_gradient_kind(env.handle) == (2 if f32 else 1)
+    base = outs[(0, 0)]
+    for key, trace in outs.items():
+        for it, (a, b) in enumerate(zip(base, trace)):
+            for x, y, what in zip(a, b, ("action", "theta", "medium", "agents")):
+                assert np.array_equal(x, y, equal_nan=True), f"grad_f32, fwd_lean = {key}: {what} differs at step {it}"
