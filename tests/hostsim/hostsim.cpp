@@ -8,6 +8,7 @@
 #include <ucontext.h>
 
 #include <cstdio>
+#include <unordered_map>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -172,13 +173,42 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     cur = nullptr;
 }
 
+// "Device" allocations are electric-fence style: the buffer ENDS at a page boundary followed by an inaccessible page,
+// and an inaccessible page precedes its first page, so a kernel that reads or writes past the end of an array (or
+// before its first page) faults on the spot -- the emulator's stand-in for compute-sanitizer's memcheck.
+namespace {
+constexpr size_t kPage = 4096;
+struct Mapping { void* base; size_t bytes; };
+std::unordered_map<void*, Mapping>& mappings() {
+    static std::unordered_map<void*, Mapping> m;
+    return m;
+}
+}  // namespace
+
 void* dev_alloc(size_t bytes) {
-    void* p = nullptr;
-    if (posix_memalign(&p, 256, bytes ? bytes : 1) != 0) return nullptr;
-    memset(p, 0xCD, bytes);                     // cudaMalloc does not zero either
+    const size_t need = ((bytes ? bytes : 1) + 15) & ~(size_t)15;          // keep 16-byte alignment of the start
+    const size_t body = (need + kPage - 1) / kPage * kPage;
+    const size_t total = body + 2 * kPage;
+    char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return nullptr;
+    mprotect(base, kPage, PROT_NONE);
+    mprotect(base + kPage + body, kPage, PROT_NONE);
+    memset(base + kPage, 0xCD, body);           // cudaMalloc does not zero either
+    char* p = base + kPage + body - need;
+    mappings()[p] = Mapping{base, total};
     return p;
 }
 
-void dev_free(void* p) { free(p); }
+void dev_free(void* p) {
+    if (p == nullptr) return;
+    auto it = mappings().find(p);
+    if (it == mappings().end()) { fprintf(stderr, "hostsim: free of a pointer that was never allocated\n"); abort(); }
+    munmap(it->second.base, it->second.bytes);
+    mappings().erase(it);
+}
 
 }  // namespace hostsim
+
+// numpy-side arrays (medium, agents, action ...) can live in fenced memory too: tests/hostsim/sim.py
+extern "C" void* hostsim_alloc(size_t bytes) { return hostsim::dev_alloc(bytes); }
+extern "C" void hostsim_free(void* p) { hostsim::dev_free(p); }

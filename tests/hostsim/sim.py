@@ -34,6 +34,49 @@ def check(rc: int) -> None:
         raise RuntimeError(f"libdie_hostsim error {rc}: {lib().die_last_error().decode()}")
 
 
+class _Fenced:
+    """Keeps a fenced allocation alive as long as the numpy array built on it."""
+
+    def __init__(self, nbytes):
+        so = lib()
+        so.hostsim_alloc.restype, so.hostsim_alloc.argtypes = C.c_void_p, [C.c_size_t]
+        so.hostsim_free.restype, so.hostsim_free.argtypes = None, [C.c_void_p]
+        self._so, self.nbytes = so, nbytes
+        self.addr = so.hostsim_alloc(nbytes)
+        if not self.addr:
+            raise MemoryError(nbytes)
+
+    def __del__(self):
+        try:
+            self._so.hostsim_free(self.addr)
+        except Exception:
+            pass
+
+
+def fenced(shape, dtype=np.float64, fill=None):
+    """A numpy array in "device" memory of the emulator: it ends at a page boundary followed by an inaccessible page
+    (and an inaccessible page precedes it), so a kernel that runs off either end faults instead of corrupting a
+    neighbour -- what compute-sanitizer's memcheck does on the GPU."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    nbytes = max(n * dtype.itemsize, 1)
+    pad = (-nbytes) % 16                                   # hostsim_alloc rounds up to 16 bytes: keep OUR end on the fence
+    blk = _Fenced(nbytes + pad)
+    buf = (C.c_char * (nbytes + pad)).from_address(blk.addr)
+    buf._fence = blk
+    arr = np.frombuffer(buf, dtype=dtype, count=n, offset=pad).reshape(shape)
+    if fill is not None:
+        arr[...] = fill
+    return arr
+
+
+def fenced_copy(a, dtype=None):
+    a = np.asarray(a, dtype=dtype)
+    out = fenced(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 def ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -65,13 +108,13 @@ class SimEnv:
         self.h, self.w = int(field_size[0]), int(field_size[1])
         self.B = int(batch) if batch is not None else 1
         self.dynamics = dynamics or Dynamics()
-        self.agents = np.ascontiguousarray(np.asarray(agents, dtype=np.float64).reshape(self.B, 4, -1)).copy()
+        self.agents = fenced_copy(np.asarray(agents, dtype=np.float64).reshape(self.B, 4, -1))
         self.M = self.agents.shape[-1]
-        first = np.ascontiguousarray(np.asarray(medium, dtype=np.float64).reshape(self.B, 3, self.h, self.w)).copy()
-        self.medium_buf = [first, np.full_like(first, np.nan)]
+        first = fenced_copy(np.asarray(medium, dtype=np.float64).reshape(self.B, 3, self.h, self.w))
+        self.medium_buf = [first, fenced(first.shape, fill=np.nan)]
         self.cur = 0
-        self.reward = np.zeros(self.B)
-        self.alive = np.zeros(self.B, dtype=np.int64)
+        self.reward = fenced((self.B,), fill=0.0)
+        self.alive = fenced((self.B,), np.int64, fill=0)
         self.handle = C.c_void_p()
         cdyn = _dynamics_to_c(self.dynamics)
         check(self.lib.die_env_create(self.h, self.w, self.M, self.B, C.byref(cdyn), C.byref(self.handle)))
@@ -105,7 +148,7 @@ class SimEnv:
             self.publish_grad = True
 
     def step(self, action, flags=L.STEP_ALIVE_BITS):
-        action = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(self.B, 3, self.M))
+        action = fenced_copy(np.asarray(action, dtype=np.float64).reshape(self.B, 3, self.M))
         nxt = 1 - self.cur
         check(self.lib.die_env_refresh_alive(self.handle, ptr(self.agents), None))
         check(self.lib.die_env_step_flags(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
@@ -147,11 +190,11 @@ class SimGradientAgent:
         self.lib = lib()
         self.p = gradient_params(**params)
         self.M, self.B = M, B
-        self.theta = np.zeros((B, M))
+        self.theta = fenced((B, M), fill=0.0)
         needs_prev = self.p.inertia != 0.0 or self.p.noise_scale != 0.0
-        self.prev_grad = np.zeros((B, 2, M)) if needs_prev else None
-        self.action = np.full((B, 3, M), np.nan)
-        self.sense_cells = np.zeros((B, M), dtype=np.int32)
+        self.prev_grad = fenced((B, 2, M), fill=0.0) if needs_prev else None
+        self.action = fenced((B, 3, M), fill=np.nan)
+        self.sense_cells = fenced((B, M), np.int32, fill=0)
         self.record_sense_cells = False
         self.seed, self.step_no = seed, 0
         self.fuse_move = False
@@ -159,8 +202,8 @@ class SimGradientAgent:
     def forward(self, env: SimEnv, coin=None, noise=None, use_hints=True, obs=None):
         """obs = (agents, medium) arrays other than the env's own disable the hints, as die_b200/_hints.py does."""
         agents, medium = (env.agents, env.medium) if obs is None else obs
-        coin_a = None if coin is None else np.ascontiguousarray(np.asarray(coin).astype(np.uint8).reshape(self.B, self.M))
-        noise_a = None if noise is None else np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(self.B, 2, self.M))
+        coin_a = None if coin is None else fenced_copy(np.asarray(coin).astype(np.uint8).reshape(self.B, self.M))
+        noise_a = None if noise is None else fenced_copy(np.asarray(noise, dtype=np.float64).reshape(self.B, 2, self.M))
         sc = self.sense_cells if self.record_sense_cells else None
         own = obs is None
         if own and use_hints:
@@ -190,8 +233,9 @@ def brownian_forward(agents, move_scale=0.01, deposit_scale=0.5, u=None, seed=0,
     agents = np.ascontiguousarray(agents, dtype=np.float64)
     B = 1 if agents.ndim == 2 else agents.shape[0]
     M = agents.shape[-1]
-    action = np.full((B, 3, M), np.nan)
-    u_a = None if u is None else np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(B, 3, M))
+    agents = fenced_copy(agents)
+    action = fenced((B, 3, M), fill=np.nan)
+    u_a = None if u is None else fenced_copy(np.asarray(u, dtype=np.float64).reshape(B, 3, M))
     check(lib().die_brownian_forward(ptr(agents), ptr(action), M, B, move_scale, deposit_scale, ptr(u_a), seed, step, None))
     return action if agents.ndim == 3 else action[0]
 
@@ -209,7 +253,7 @@ class SimSlabWorld:
         self.G = G
 
         def alloc(shapes, dtype, fill):
-            arrs = [np.full(s, fill, dtype=dtype) for s in shapes]
+            arrs = [fenced(s, dtype, fill=fill) for s in shapes]
             return arrs, np.array([a.ctypes.data for a in arrs], dtype=np.int64)
 
         self.med_a, self.tbl_a = alloc([(3, rp, W)] * G, np.float64, np.nan)
@@ -226,8 +270,8 @@ class SimSlabWorld:
         cdyn = _dynamics_to_c(self.dynamics)
         for q in range(G):
             self.med_a[q][...] = mediums[q]
-            self.agents.append(np.ascontiguousarray(locals_[q]).copy())
-            self.theta.append(np.ascontiguousarray(theta[Lo.global_ids(q)]).copy())
+            self.agents.append(fenced_copy(locals_[q]))
+            self.theta.append(fenced_copy(theta[Lo.global_ids(q)]))
             self.stats.append(np.zeros(2))
             h = C.c_void_p()
             geom = Lo.to_c(q)
@@ -253,7 +297,7 @@ class SimSlabWorld:
         for q, h in enumerate(self.handles):
             coin = None
             if coin_global is not None:
-                coin = np.ascontiguousarray(coin_global[self.layout.global_ids(q)]).astype(np.uint8)
+                coin = fenced_copy(coin_global[self.layout.global_ids(q)].astype(np.uint8))
             check(self.lib.die_slab_forward(h, C.byref(self.params), self.cur, ptr(self.agents[q]), ptr(self.theta[q]),
                                             ptr(self.act[q]), ptr(coin), hints, q, self._step, None))
 

@@ -599,3 +599,23 @@ def test_float32_gradient_cache_on_adversarial_fields(tuning):
         for it, (a, b) in enumerate(zip(base, trace)):
             for x, y, what in zip(a, b, ("action", "theta", "medium", "agents")):
                 assert np.array_equal(x, y, equal_nan=True), f"grad_f32, fwd_lean = {key}: {what} differs at step {it}"
+
+
+def test_fenced_memory_faults_on_an_overrun():
+    """The emulator's memcheck: arrays end at an inaccessible page, so a kernel told to process one element more
+    than the array holds dies with SIGSEGV (in a child process) instead of silently reading a neighbour."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys
+        import numpy as np
+        from tests.hostsim import sim as S
+        n = int(sys.argv[1])
+        x = S.fenced((512,), fill=0.5); s = S.fenced((512,)); c = S.fenced((512,))
+        S.check(S.lib().die_math_sincos(S.ptr(x), S.ptr(s), S.ptr(c), n, None))
+        print("ok", float(s[0]))
+    ''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ok = subprocess.run([sys.executable, "-c", code, "512"], cwd=root, capture_output=True, text=True)
+    assert ok.returncode == 0 and ok.stdout.startswith("ok"), ok.stderr
+    bad = subprocess.run([sys.executable, "-c", code, "513"], cwd=root, capture_output=True, text=True)
+    assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr[-300:])
