@@ -77,7 +77,13 @@ class GradientAgent(_DeviceAgent):
 
     # -- state ------------------------------------------------------------------------------
     def _needs_prev(self) -> bool:
-        return self._inertia != 0.0 or self._noise_scale != 0.0
+        """Whether ``_process_momentum`` (core/agent/gradient.py:82-91) can change anything.  With inertia = noise_scale
+        = 0 it computes 1.0 * g' + 0.0 * prev + 0.0 * noise, which is g' -- except for a component of g' that is
+        exactly -0.0: (-0.0) + (+0.0) = +0.0, and the new heading angle(gx + 1j gy) is pi only for (-0.0, -0.0)
+        (SURVEY Q6).  A Physarum turn on a NORMALISED gradient yields (cos d, sin d), never a zero; every other
+        configuration (unnormalised: 0 * cos d; GradientAgent: the clipped gradient's signed zeros) can, so there the
+        momentum arithmetic is carried out with its real operands."""
+        return self._inertia != 0.0 or self._noise_scale != 0.0 or not (self._discrete_turn and self._normalized)
 
     def _initial_theta(self, prev_grad: np.ndarray) -> np.ndarray:
         """get_radians(prev_grad), core/agent/gradient.py:42-43."""

@@ -191,7 +191,8 @@ class SimGradientAgent:
         self.p = gradient_params(**params)
         self.M, self.B = M, B
         self.theta = fenced((B, M), fill=0.0)
-        needs_prev = self.p.inertia != 0.0 or self.p.noise_scale != 0.0
+        needs_prev = (self.p.inertia != 0.0 or self.p.noise_scale != 0.0 or
+                      not (self.p.discrete_turn and self.p.normalized_grad))       # die_b200/agent/gradient.py:_needs_prev
         self.prev_grad = fenced((B, 2, M), fill=0.0) if needs_prev else None
         self.action = fenced((B, 3, M), fill=np.nan)
         self.sense_cells = fenced((B, M), np.int32, fill=0)

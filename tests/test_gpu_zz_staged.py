@@ -59,3 +59,26 @@ def test_feed_register_caps_do_not_change_results(cap):
     base, _ = _run("feed_min_blocks", 1)
     out, _ = _run("feed_min_blocks", cap)
     assert all(np.array_equal(a, b) for a, b in zip(base[:3], out[:3])) and base[3] == out[3]
+
+
+def test_unnormalised_physarum_keeps_the_momentum_operands():
+    """Found on the CPU emulator: with normalized_grad=False a zero gradient gives g' = (0 * cos d, 0 * sin d), signed
+    zeros, and the reference's identity momentum step 1.0 * g' + 0.0 * prev + 0.0 * noise turns (-0.0) + (+0.0) into
+    +0.0 -- so the new heading (pi only for (-0., -0.)) depends on the signs of prev_grad and of the noise
+    draw.  GradientAgent._needs_prev now keeps those operands for every configuration whose g' can hold a zero."""
+    import die_b200 as D
+    from oracle import die_ref as R
+    (ref,), env = make_pair((32, 48), seed=12)
+    m = env.max_agents
+    theta0, prev = lattice_theta(m, 30, 12)
+    kw = dict(PHYS, normalized_grad=False)
+    ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **kw)
+    ga = D.PhysarumAgent(max_agents=m, **kw)
+    ga.set_state(theta=theta0, prev_grad=prev)
+    rng = np.random.default_rng(0)
+    coin, noise = rng.integers(0, 2, m), rng.normal(0., 0.4, size=(2, m))
+    ract = ra.forward(ref._get_current_obs, coin=coin.copy(), noise=noise.copy())      # chem1 == 0: every gradient is zero
+    gact = ga.forward(env._get_current_obs, coin=coin, noise=noise).cpu().numpy()
+    assert set(np.unique(ra._direction_rads)) <= {0.0, np.pi}
+    assert np.array_equal(ga.get_state()[0], ra._direction_rads)
+    assert np.array_equal(gact, ract)

@@ -93,13 +93,17 @@ def test_brownian_philox_is_launch_invariant_and_masked():
 # config 2: PhysarumAgent, oracle in its portable math backend -> everything bit-exact, free running
 # ------------------------------------------------------------------------------------------
 def _physarum_free_run(field, iters, agent_kw, seed=2, dynamics_kw=None, ref_dynamics_kw=None, use_hints=True,
-                       record=True, fuse=False):
+                       record=True, fuse=False, exact=True):
+    """exact=False: the policy involves a libm function die_math.h does not replace (hypot of an unnormalised
+    gradient), so headings / moves are compared to 1e-13 and the oracle continues from the kernel's values."""
     (ref,), env = make_pair(field, seed=seed, dynamics_kw=dynamics_kw, ref_dynamics_kw=ref_dynamics_kw)
     m = ref.agents.shape[-1]
     theta0, prev = lattice_theta(m, agent_kw.get('turn_angle', 30), seed)
     ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **agent_kw)
     ga = S.SimGradientAgent(m, **agent_kw)
     ga.theta[0] = theta0
+    if ga.prev_grad is not None:
+        ga.prev_grad[0] = prev
     ga.record_sense_cells = record
     ga.fuse_move = fuse
     rng = np.random.default_rng(seed)
@@ -108,14 +112,22 @@ def _physarum_free_run(field, iters, agent_kw, seed=2, dynamics_kw=None, ref_dyn
     seen_flags = set()
     for it in range(iters):
         coin = rng.integers(0, 2, m)
-        ract = ra.forward(robs, coin=coin.copy())
-        gact = ga.forward(env, coin=coin, use_hints=use_hints)[0]
+        # the momentum step's noise draws matter even at noise_scale = 0 wherever g' can hold a -0.0 (see _needs_prev)
+        noise = rng.normal(0., 0.4, size=(2, m)) if ga.prev_grad is not None else None
+        ract = ra.forward(robs, coin=coin.copy(), noise=None if noise is None else noise.copy())
+        gact = ga.forward(env, coin=coin, noise=noise, use_hints=use_hints)[0]
         seen_flags.add(ga.last_flags)
         if record:
             sx, sy = ra.last_sense_cells
             assert np.array_equal((sx * w + sy).astype(np.int32), ga.sense_cells[0]), f"sense cells, step {it}"
-        assert np.array_equal(ga.theta[0], ra._direction_rads), f"theta differs at step {it}"
-        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        if exact:
+            assert np.array_equal(ga.theta[0], ra._direction_rads), f"theta differs at step {it}"
+            assert np.array_equal(gact, ract), f"action differs at step {it}"
+        else:
+            d = np.abs(R.renormalize_radians(ga.theta[0] - ra._direction_rads))
+            assert np.minimum(d, 2 * np.pi - d).max() < 1e-13, f"theta differs at step {it}"
+            np.testing.assert_allclose(gact, ract, rtol=1e-13, atol=1e-17)
+            ra._direction_rads, ra._prev_grad, ract = ga.theta[0].copy(), ga.prev_grad[0].copy(), gact.copy()
         robs, rr, _, _, rinfo = ref.step(ract)
         flags = L.STEP_ALIVE_BITS | (L.STEP_ADOPT_MOVE if fuse else 0)
         r, alive = env.step(gact, flags=flags)
@@ -619,3 +631,45 @@ def test_fenced_memory_faults_on_an_overrun():
     assert ok.returncode == 0 and ok.stdout.startswith("ok"), ok.stderr
     bad = subprocess.run([sys.executable, "-c", code, "513"], cwd=root, capture_output=True, text=True)
     assert bad.returncode == -11, (bad.returncode, bad.stdout, bad.stderr[-300:])
+
+
+# ------------------------------------------------------------------------------------------
+# the remaining branches (line coverage of the kernel sources under the emulator: tools/REPRODUCE.md)
+# ------------------------------------------------------------------------------------------
+def test_const_agent_and_moves_longer_than_the_field():
+    """ConstAgent.forward (core/agent/static.py:19-28) with a step of 2.3 field lengths: `% 1.` goes through the
+    generic fmod path of die_np_remainder; the oracle agrees bit for bit."""
+    (ref,), env = make_pair((24, 32), seed=4)
+    m = env.M
+    action = S.fenced((1, 3, m), fill=np.nan)
+    S.check(S.lib().die_const_forward(S.ptr(action), m, 1, 2.3, -3.7, 0.25, None))
+    ra = R.ConstAgent((2.3, -3.7), 0.25)
+    ract = ra.forward(ref._get_current_obs)
+    assert np.array_equal(ract, action[0])
+    for it in range(4):
+        _, rr, *_ = ref.step(ract)
+        r, _ = env.step(action)
+        assert np.array_equal(ref_cells_linear(ref), env.cells()[0])
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+        assert _rel(rr, r[0]) < 1e-11
+
+
+@pytest.mark.parametrize("kw", [dict(grad_clip=None), dict(normalized_grad=False), dict(normalized_grad=False, grad_clip=None)])
+def test_gradient_processing_variants(portable_math, kw):
+    """grad_clip=None (nan_to_num of 0/0) and unnormalised gradients: the quick turn decision is not offered there,
+    every slot takes the reference arithmetic."""
+    _physarum_free_run((28, 44), 8, dict(PHYS, **kw), seed=12, exact=kw.get('normalized_grad', True))
+
+
+def test_gradient_agent_in_kernel_noise_is_reproducible():
+    """GradientAgent with rng='philox': Box-Muller noise drawn in the kernel, keyed on (seed, step, env, slot)."""
+    outs = []
+    for rep in range(2):
+        (ref,), env = make_pair((24, 32), seed=6)
+        ga = S.SimGradientAgent(env.M, seed=9, discrete_turn=False, scale=0.01, inertia=0.9, sense_offset=0.02, noise_scale=0.025)
+        ga.prev_grad[...] = np.random.default_rng(1).normal(0, 0.4, ga.prev_grad.shape)
+        for it in range(4):
+            env.step(ga.forward(env))
+        outs.append((ga.prev_grad.copy(), ga.theta.copy(), env.agents.copy()))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    assert np.isfinite(outs[0][0]).all() and np.std(outs[0][0]) > 0.01
