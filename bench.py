@@ -227,6 +227,54 @@ def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, 
                 alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused))
 
 
+def e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus):
+    """Experimental (--e2e-workers W, off by default, NOT yet measured on a GPU): the host-buffer loop driven by W host
+    threads, each with its own Env / Agent over B_e2e / W environments and its own CUDA stream.  One thread's
+    Agent.forward (upload-heavy: the observation) then overlaps another's Env.step (download-heavy), so both PCIe
+    directions carry data all the time instead of taking turns.  Same public calls, same bytes per environment."""
+    import threading
+    W = args.e2e_workers
+    per = B_e2e // W
+    pairs = [make_env_and_agent(D, torch, field, per, True, device, rank, 60 + w)[:2] for w in range(W)]
+    streams = [torch.cuda.Stream(device=device) for _ in range(W)]
+    start = threading.Barrier(W + 1)
+    errors = []
+
+    def worker(w):
+        env, agent = pairs[w]
+        try:
+            torch.cuda.set_device(device)
+            with torch.cuda.stream(streams[w]):
+                hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
+                for _ in range(2):
+                    hobs, *_ = env.step(agent.forward(hobs))
+                start.wait()
+                for _ in range(k_e2e):
+                    hobs, *_ = env.step(agent.forward(hobs))
+                streams[w].synchronize()
+        except Exception as exc:                # report, never hang the barrier
+            errors.append(repr(exc))
+            start.abort()
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(W)]
+    for t in threads:
+        t.start()
+    try:
+        start.wait()
+    except threading.BrokenBarrierError:
+        pass
+    t0 = time.perf_counter()
+    for t in threads:
+        t.join()
+    dt = time.perf_counter() - t0
+    if errors:
+        return {"error": errors[0]}
+    from die_b200.sharding import max_over_ranks
+    dt = max_over_ranks(dt, device)
+    return {"workers": W, "envs_per_worker": per, "value": C * per * W * n_gpus * k_e2e / dt, "unit": UNIT,
+            "ms_per_step": dt / k_e2e * 1e3}
+
+
 def roofline_of(meas, B_local, wl_name):
     peak, peak_src = measured_hbm_peak()
     M, C, alive_local = meas["M"], meas["C"], meas["alive_local"]
@@ -411,6 +459,8 @@ def run_die_b200(args):
                       "batch cut into chunks on two streams so both PCIe directions stay busy; PCIe-bound, so measured "
                       "on a bounded number of envs per GPU (pinned host memory)"}
         del env, agent
+        if args.e2e_workers > 1 and batched:
+            e2e["workers"] = e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus)
 
     # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------
     cpu = None
@@ -540,6 +590,8 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")
     ap.add_argument("--corner-r", type=int, default=512, help="slab workload: side of the mirrored corner patches (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=1,
+                    help="experimental: also time the host-buffer loop driven by this many host threads (see e2e_workers_leg)")
     ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")
