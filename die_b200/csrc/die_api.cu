@@ -6,6 +6,7 @@
 
 #include "die_agent_kernels.cuh"
 #include "die_field_kernels.cuh"
+#include "die_field_bulk.cuh"
 
 using namespace die;
 
@@ -284,11 +285,43 @@ static cudaError_t launch_march(const FieldArgs& a, int B, cudaStream_t st) {
 }
 
 static int g_field_prefetch = 1;   // tile kernel: prefetch the output tile's food lines to L2 while staging
-static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms at 4096^2), 1 = register-tiled march (0.29 ms)
+static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms at 4096^2), 1 = register-tiled march (0.29 ms),
+                                   // 2 = persistent, bulk-async double-buffered tiles (die_field_bulk.cuh; staged, untimed)
+
+template <int R, bool GRAD>
+static cudaError_t launch_field_bulk(const FieldArgs& fa, int B, int num_sms, cudaStream_t st) {
+    constexpr int TH = 32, TW = 64, NT = 256;
+    using GEO = BulkGeom<R, TH, TW, GRAD>;
+    FieldArgs a = fa;
+    a.tiles_i = (a.H + TH - 1) / TH;
+    a.tiles_j = (a.W + TW - 1) / TW;
+    const int64_t total = (int64_t)a.tiles_i * a.tiles_j * B;
+    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const bool plain = a.flow_rwave == nullptr;
+    auto kern = plain ? field_step_bulk_kernel<R, TH, TW, NT, GRAD, true> : field_step_bulk_kernel<R, TH, TW, NT, GRAD, false>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::kSmemBytes);
+    if (err != cudaSuccess) return err;
+    const int64_t cap = (int64_t)(num_sms > 0 ? num_sms : 148) * 2;          // two resident CTAs per SM, one wave
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    kern<<<grid, NT, GEO::kSmemBytes, st>>>(a, (int)total);
+    return cudaGetLastError();
+}
+
+// what the bulk kernel needs: periodic diffusion, rows that are 16-byte aligned for the int32 claims and wrap at most once
+template <int R, bool GRAD>
+static bool bulk_field_ok(const FieldArgs& fa) {
+    return fa.diffuse_mode == DIE_DIFFUSE_WRAP && fa.W % 4 == 0 && fa.W >= BulkGeom<R, 32, 64, GRAD>::LWA;
+}
 
 template <int R>
-static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
+static cudaError_t launch_field(const FieldArgs& fa, int B, int num_sms, cudaStream_t st) {
     const bool want_grad = fa.grad != nullptr || fa.grad32 != nullptr;
+    if constexpr (R <= 4) {
+        if (g_field_impl == 2) {
+            if (want_grad && bulk_field_ok<R, true>(fa)) return launch_field_bulk<R, true>(fa, B, num_sms, st);
+            if (!want_grad && bulk_field_ok<R, false>(fa)) return launch_field_bulk<R, false>(fa, B, num_sms, st);
+        }
+    }
     if constexpr (R <= 3) {
         if (g_field_impl == 1 && fa.diffuse_mode == DIE_DIFFUSE_WRAP)
             return want_grad ? launch_march<R, true>(fa, B, st) : launch_march<R, false>(fa, B, st);
@@ -297,7 +330,8 @@ static cudaError_t launch_field(const FieldArgs& fa, int B, cudaStream_t st) {
 }
 
 extern "C" int die_set_field_impl(int32_t impl) {
-    g_field_impl = impl ? 1 : 0;
+    DIE_REQUIRE(impl >= 0 && impl <= 2);
+    g_field_impl = impl;
     return DIE_OK;
 }
 
@@ -344,14 +378,14 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
             field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
             return cudaGetLastError();
         }
-        case 1: return launch_field<1>(a, nb, st);
-        case 2: return launch_field<2>(a, nb, st);
-        case 3: return launch_field<3>(a, nb, st);
-        case 4: return launch_field<4>(a, nb, st);
-        case 5: return launch_field<5>(a, nb, st);
-        case 6: return launch_field<6>(a, nb, st);
-        case 7: return launch_field<7>(a, nb, st);
-        case 8: return launch_field<8>(a, nb, st);
+        case 1: return launch_field<1>(a, nb, e->num_sms, st);
+        case 2: return launch_field<2>(a, nb, e->num_sms, st);
+        case 3: return launch_field<3>(a, nb, e->num_sms, st);
+        case 4: return launch_field<4>(a, nb, e->num_sms, st);
+        case 5: return launch_field<5>(a, nb, e->num_sms, st);
+        case 6: return launch_field<6>(a, nb, e->num_sms, st);
+        case 7: return launch_field<7>(a, nb, e->num_sms, st);
+        case 8: return launch_field<8>(a, nb, e->num_sms, st);
     }
     return cudaErrorInvalidValue;
 }

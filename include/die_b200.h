@@ -269,7 +269,7 @@ int die_set_turn_quick(int32_t on);
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
  * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
- * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1, "grad_f32" 0/1 (see die_env_gradient_kind),
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1/2 (tile / register-march / persistent bulk-async tiles, the last one staged and untimed), "grad_f32" 0/1 (see die_env_gradient_kind),
  * "feed_min_blocks" 1/4/5 (register cap of the feed kernel; 1 = the compiler's choice). */
 int die_set_tuning(const char* key, int32_t value);
 

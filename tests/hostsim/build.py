@@ -85,7 +85,8 @@ def _strip_asm(src: str) -> str:
 
 
 def translate(src: str) -> str:
-    src = _strip_asm(src)
+    if "DIE_HOSTSIM" not in src:            # (a file that names the macro keeps its PTX behind #if !defined(DIE_HOSTSIM))
+        src = _strip_asm(src)
     src = _DYN_SMEM.sub(lambda m: f"{m.group(1)}* {m.group(2)} = ({m.group(1)}*)hostsim::dyn_smem();", src)
     src = _rewrite_launches(src)
     src = src.replace('#include "../../include/die_b200.h"', f'#include "{os.path.join(INCLUDE, "die_b200.h")}"')
@@ -109,7 +110,7 @@ def build(force: bool = False, csrc: str = CSRC, out_dir: str = OUT_DIR, extra_f
         with open(os.path.join(out_dir, target), "w") as f:
             f.write(text)
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
-           "-shared", "-fPIC", "-I", HERE, "-I", out_dir, *extra_flags, "-o", lib,
+           "-shared", "-fPIC", "-DDIE_HOSTSIM", "-I", HERE, "-I", out_dir, *extra_flags, "-o", lib,
            os.path.join(out_dir, "die_api.cpp"), os.path.join(HERE, "hostsim.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

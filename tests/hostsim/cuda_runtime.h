@@ -109,6 +109,27 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return w;
 }
 static inline void __syncthreads() { hostsim::syncthreads(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { uint64_t all[32]; hostsim::warp_exchange(0, all); }
+static inline void __trap() { abort(); }
+
+// ---- die_async.cuh under the emulator: mbarrier + 1-D bulk copies (see hostsim.cpp) ----------------
+namespace hostsim {
+void mbar_init(void* bar, int count);
+void mbar_arrive_expect_tx(void* bar, uint32_t bytes);
+void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar);
+void mbar_wait(void* bar, uint32_t parity);
+}  // namespace hostsim
+#if defined(DIE_HOSTSIM)
+namespace die {
+typedef unsigned long long mbar_t;
+static inline void mbar_init(mbar_t* bar, int count) { hostsim::mbar_init(bar, count); }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(mbar_t* bar, uint32_t bytes) { hostsim::mbar_arrive_expect_tx(bar, bytes); }
+static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t* bar) { hostsim::bulk_g2s(dst, src, bytes, bar); }
+static inline void mbar_wait(mbar_t* bar, uint32_t parity) { hostsim::mbar_wait(bar, parity); }
+static inline void proxy_fence_async() {}
+}  // namespace die
+#endif
 
 // ---- runtime API -------------------------------------------------------------------------------
 typedef int cudaError_t;

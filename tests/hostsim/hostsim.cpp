@@ -114,6 +114,92 @@ void warp_exchange(uint64_t mine, uint64_t* all32) {
     block_wait(&w.gen, &w.count, w.alive);      // nobody deposits the next value before everybody has read
 }
 
+// ---- mbarrier + bulk copies (die_b200/csrc/die_async.cuh) ------------------------------------------------------
+// A bulk copy is QUEUED on its barrier and its destination poisoned; the bytes move when somebody first waits on the
+// barrier -- as late as the protocol allows -- so a consumer that reads without waiting sees NaNs, and a phase whose
+// announced byte count does not match the copies never completes (reported as a deadlock).
+namespace {
+struct PendingCopy { void* dst; const void* src; uint32_t bytes; };
+struct MbarState {
+    int init = 0, pending = 0;
+    long tx = 0;
+    unsigned phase = 0;
+    int waiters = 0;
+    std::vector<PendingCopy> queue;
+};
+std::unordered_map<void*, MbarState> g_mbars;
+
+void mbar_maybe_complete(MbarState& st) {
+    if (st.pending == 0 && st.tx == 0) {
+        ++st.phase;
+        st.pending = st.init;
+    }
+}
+
+MbarState& mbar_of(void* bar) {
+    auto it = g_mbars.find(bar);
+    if (it == g_mbars.end()) { fprintf(stderr, "hostsim: mbarrier used before mbarrier.init\n"); abort(); }
+    return it->second;
+}
+}  // namespace
+
+void mbar_init(void* bar, int count) {
+    MbarState st;
+    st.init = st.pending = count;
+    g_mbars[bar] = st;
+}
+
+void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+    MbarState& st = mbar_of(bar);
+    if (st.pending <= 0) { fprintf(stderr, "hostsim: more arrivals than the mbarrier was initialised for\n"); abort(); }
+    st.tx += bytes;
+    --st.pending;
+    mbar_maybe_complete(st);
+}
+
+void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    if (bytes == 0 || bytes % 16 != 0 || ((uintptr_t)dst & 15) != 0 || ((uintptr_t)src & 15) != 0) {
+        fprintf(stderr, "hostsim: cp.async.bulk needs a size that is a multiple of 16 and 16-byte aligned addresses "
+                        "(dst %p, src %p, %u bytes)\n", dst, src, bytes);
+        abort();
+    }
+    char* lo = g_smem.data();
+    if ((char*)dst < lo || (char*)dst + bytes > lo + g_smem.size()) {
+        fprintf(stderr, "hostsim: bulk copy destination outside the dynamic shared memory of the block\n");
+        abort();
+    }
+    MbarState& st = mbar_of(bar);
+    if (st.waiters > 0) {                               // somebody already waits for this phase: the bytes land now
+        memcpy(dst, src, bytes);
+        st.tx -= bytes;
+        mbar_maybe_complete(st);
+        return;
+    }
+    memset(dst, 0xFF, bytes);
+    st.queue.push_back(PendingCopy{dst, src, bytes});
+}
+
+void mbar_wait(void* bar, uint32_t parity) {
+    for (;;) {
+        MbarState& st = mbar_of(bar);
+        if ((st.phase & 1u) != parity) return;          // the phase with this parity has completed
+        if (!st.queue.empty()) {
+            for (const PendingCopy& c : st.queue) {
+                memcpy(c.dst, c.src, c.bytes);
+                st.tx -= c.bytes;
+            }
+            st.queue.clear();
+            mbar_maybe_complete(st);
+            continue;
+        }
+        ++st.waiters;
+        g_self->wait_ptr = &st.phase;
+        g_self->wait_val = st.phase;
+        yield();
+        --mbar_of(bar).waiters;
+    }
+}
+
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     if (nthreads == 0 || nthreads > 1024 || grid.x == 0) {
@@ -128,6 +214,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_blk.alive = (int)nthreads;
+        g_mbars.clear();
         g_blk.bar_count = 0;
         g_blk.warps.assign(nwarps, Warp());
         for (size_t t = 0; t < nthreads; ++t) {

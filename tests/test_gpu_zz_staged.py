@@ -7,7 +7,11 @@ marker from whatever it adopts.
   grad_f32          the field pass publishes np.gradient(chem1) as float32 pairs (8 B/cell less written, half the
                     gather footprint); the guard-banded turn decision reads those, deferred slots re-sample chem1
   feed_min_blocks   register caps of the feed kernel (64 / 48 registers: 4 / 5 resident CTAs per SM instead of 3)
+  field_impl = 2    persistent field pass, halo tiles by cp.async.bulk + mbarrier into a two-stage ring
+                    (die_field_bulk.cuh); its test runs only with DIE_B200_STAGED_BULK=1
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -82,3 +86,31 @@ def test_unnormalised_physarum_keeps_the_momentum_operands():
     assert set(np.unique(ra._direction_rads)) <= {0.0, np.pi}
     assert np.array_equal(ga.get_state()[0], ra._direction_rads)
     assert np.array_equal(gact, ract)
+
+
+@pytest.mark.skipif(os.environ.get("DIE_B200_STAGED_BULK") != "1",
+                    reason="first run of an mbarrier / cp.async.bulk kernel on hardware: only on request "
+                           "(DIE_B200_STAGED_BULK=1, under `timeout`), never in the default suite")
+@pytest.mark.parametrize("shape,sigma,batch", [((256, 256), 0.5, 6), ((40, 72), 0.5, None), ((70, 200), 0.8, None),
+                                               ((128, 96), 0.5, 700)])
+def test_bulk_field_kernel_does_not_change_results(shape, sigma, batch):
+    """field_impl = 2 (die_field_bulk.cuh): the persistent, bulk-async double-buffered field pass.  A protocol error
+    traps after two seconds instead of hanging (die_async.cuh), but a trap poisons the CUDA context: this test is
+    last in the last file."""
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    outs = []
+    try:
+        for impl in (0, 2):
+            _lib.check(lib.die_set_tuning(b"field_impl", impl))
+            _, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch and min(batch, 700))
+            m = env.max_agents
+            ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
+            obs = env._get_current_obs
+            for _ in range(12):
+                obs, r, *_ = env.step(ag.forward(obs))
+            outs.append((*env.get_state(), ag.get_state()[0]))
+    finally:
+        _lib.check(lib.die_set_tuning(b"field_impl", 0))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))

@@ -235,6 +235,55 @@ def test_march_field_kernel_equals_tile_kernel(tuning, sigma):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("shape,sigma,batch", [((64, 128), 0.5, None), ((40, 72), 0.5, None), ((6, 76), 0.5, None),
+                                               ((70, 200), 0.8, None), ((33, 132), 0.3, 3), ((48, 96), 1.0, 2),
+                                               ((96, 80), 0.5, 5)])
+@pytest.mark.parametrize("grad", [True, False])
+def test_bulk_field_kernel_equals_tile_kernel(tuning, shape, sigma, batch, grad):
+    """field_impl = 2: the persistent kernel whose halo tiles arrive by cp.async.bulk + mbarrier into a two-stage ring
+    (die_field_bulk.cuh).  Under the emulator the copies are deferred and their destination poisoned until somebody
+    waits, byte counts and alignment are checked.  Widths that wrap inside a staged row, fields lower than a tile,
+    radii 1..4, batches (several tiles per persistent CTA), with (Physarum) and without (Brownian) the gradient cache,
+    float64 and float32 gradient."""
+    outs = []
+    for impl, f32 in ((0, 0), (2, 0), (2, 1)):
+        tuning("field_impl", impl)
+        tuning("grad_f32", f32)
+        refs, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 13 + b)[0]
+        for it in range(5):
+            if grad:
+                act = ga.forward(env)
+            else:
+                act = S.brownian_forward(env.agents, move_scale=0.02, seed=4, step=it)
+            env.step(act)
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.reward.copy(),
+                     None if f32 else env.gradient()))
+    for k in (1, 2):
+        for a, b, what in zip(outs[0], outs[k], ("medium", "agents", "theta", "reward", "gradient")):
+            if a is None or b is None:
+                continue
+            assert np.array_equal(a, b), f"variant {k}: {what} differs"
+
+
+def test_bulk_field_kernel_falls_back_where_it_does_not_apply(tuning):
+    """Widths that are not a multiple of 4 (claim rows would not be 16-byte aligned), narrower than a staged row, or a
+    non-periodic diffuse_mode: field_impl = 2 silently runs the tile kernel."""
+    for shape, kw in (((40, 70), {}), ((40, 64), {}), ((40, 80), dict(diffuse_mode='reflect'))):
+        outs = []
+        for impl in (0, 2):
+            tuning("field_impl", impl)
+            refs, env = make_pair(shape, seed=3, dynamics_kw=kw)
+            ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
+            for it in range(3):
+                env.step(ga.forward(env))
+            outs.append(env.medium.copy())
+        assert np.array_equal(*outs)
+
+
 def test_batched_envs_match_single_envs():
     """B = 3 environments in one set of launches == three single environments (same Philox coins: the in-kernel
     RNG is keyed on (environment, slot), not on the launch geometry)."""
