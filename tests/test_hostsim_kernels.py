@@ -722,3 +722,122 @@ def test_gradient_agent_in_kernel_noise_is_reproducible():
         outs.append((ga.prev_grad.copy(), ga.theta.copy(), env.agents.copy()))
     assert all(np.array_equal(a, b) for a, b in zip(*outs))
     assert np.isfinite(outs[0][0]).all() and np.std(outs[0][0]) > 0.01
+
+
+def test_abandoned_speculation_leaves_no_trace():
+    """The forward kernel evaluated move + claims speculatively (DIE_FWD_SPECULATE_MOVE) but the step does not adopt
+    them (another action arrives): die_env_step_flags must drop the pending claims and run the plain step; a second
+    speculation replaces the first; die_env_pending_move tracks the state."""
+    phys = dict(scale=0.02, turn_angle=30, sense_offset=0.06)
+    outs = []
+    for abandon in (False, True):
+        (ref,), env = make_pair((40, 72), seed=8)
+        ga = S.SimGradientAgent(env.M, seed=3, **phys)
+        ga.theta[0] = lattice_theta(env.M, 30, 8)[0]
+        other = S.SimGradientAgent(env.M, seed=3, **phys)
+        other.theta[0] = ga.theta[0]
+        for it in range(6):
+            if abandon:
+                ga.fuse_move = True
+                spec = ga.forward(env).copy()                       # speculation pending ...
+                assert S.lib().die_env_pending_move(env.handle) == 1
+                if it % 2 == 0:
+                    ga.theta[...] = other.theta                     # ... repeated forward: the first speculation is replaced
+                    ga.step_no -= 1
+                    spec2 = ga.forward(env).copy()
+                    assert np.array_equal(spec, spec2)
+                other.theta[...] = ga.theta
+                env.step(spec, flags=L.STEP_ALIVE_BITS)             # ... and abandoned: plain step on a copy of the action
+                assert S.lib().die_env_pending_move(env.handle) == 0
+            else:
+                ga.fuse_move = False
+                act = ga.forward(env).copy()
+                other.theta[...] = ga.theta
+                env.step(act)
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.cells()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_forward_through_host_buffers_is_chunked_and_identical(tuning):
+    """die_gradient_forward_host: observation uploaded / action downloaded chunk by chunk on two streams; the in-kernel
+    random draws are keyed on the GLOBAL environment index, so chunking does not change them."""
+    tuning("host_chunk_min_kb", 0)
+    try:
+        refs, env = make_pair((24, 32), seed=17, batch=9)
+        B, M = 9, env.M
+        p = S.gradient_params(**PHYS)
+        theta0 = np.stack([lattice_theta(M, 30, b)[0] for b in range(B)])
+        so = S.lib()
+        ctx = S.C.c_void_p()
+        S.check(so.die_host_ctx_create(S.C.byref(ctx)))
+        res = []
+        for host in (False, True):
+            theta, action = S.fenced_copy(theta0), S.fenced((B, 3, M), fill=np.nan)
+            if host:
+                ag_stage, med_stage = S.fenced(env.agents.shape, fill=np.nan), S.fenced(env.medium.shape, fill=np.nan)
+                action_host = S.fenced((B, 3, M), fill=np.nan)
+                S.check(so.die_gradient_forward_host(ctx, S.C.byref(p), 24, 32, M, B, S.ptr(env.agents), S.ptr(env.medium),
+                                                     S.ptr(ag_stage), S.ptr(med_stage), S.ptr(theta), None, S.ptr(action),
+                                                     S.ptr(action_host), None, None, None, 7, 3, None))
+                assert np.array_equal(action_host, action)
+            else:
+                S.check(so.die_gradient_forward(S.C.byref(p), 24, 32, M, B, S.ptr(env.agents), S.ptr(env.medium), S.ptr(theta),
+                                                None, S.ptr(action), None, None, None, None, None, 7, 3, None))
+            res.append((action.copy(), theta.copy()))
+        S.check(so.die_host_ctx_destroy(ctx))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    finally:
+        tuning("host_chunk_min_kb", 32 << 10)
+
+
+# ------------------------------------------------------------------------------------------
+# seeded random sweep over configurations: emulated kernels vs the oracle, bit for bit
+# ------------------------------------------------------------------------------------------
+def _random_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    h = int(rng.choice([2, 3, 5, 8, 17, 31, 32, 33, 40, 64, 65, 70]))
+    w = int(rng.choice([2, 3, 7, 16, 63, 64, 65, 72, 76, 100, 129, 200]))
+    sigma = float(rng.choice([0.1, 0.3, 0.5, 0.5, 0.8, 1.0, 1.3]))
+    mode = str(rng.choice(['wrap', 'wrap', 'wrap', 'reflect', 'nearest', 'mirror', 'constant']))
+    limit = bool(rng.random() < 0.3)
+    dyn = dict(diffuse_sigma=sigma, diffuse_mode=mode, food_infinite=bool(rng.random() < 0.2),
+               rate_feed=float(rng.choice([0.1, 0.25])), rate_decay_chem=float(rng.choice([0.1, 0.02])))
+    rdyn = dict(dyn)
+    if limit:
+        dyn['boundary'], rdyn['boundary'] = D.BoundaryCondition.limit, 'limit'
+    agent = dict(scale=float(rng.choice([0.007, 0.03, 0.2, 1.7])), sense_offset=float(rng.choice([0.0, 0.04, 0.3, 1.5])),
+                 turn_angle=float(rng.choice([30, 35, 45, 90])), sense_angle=float(rng.choice([60, 90, 120, 170])),
+                 turn_tolerance=float(rng.choice([0.05, 0.1, 0.3])), deposit=float(rng.choice([4.0, 0.5])))
+    tune = dict(field_impl=int(rng.choice([0, 0, 1, 2])), grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
+                feed_bits=int(rng.random() < 0.7))
+    return (h, w), float(rng.choice([0.05, 0.1, 0.5, 1.0])), dyn, rdyn, agent, tune, bool(rng.random() < 0.5)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DIE_SWEEP_SEEDS", "80"))))
+def test_random_configurations_against_the_oracle(portable_math, tuning, seed):
+    field, ratio, dyn, rdyn, agent_kw, tune, hints = _random_case(seed)
+    if agent_kw['sense_angle'] <= agent_kw['turn_angle'] * agent_kw['turn_tolerance'] / 0.99 + 1:
+        agent_kw['sense_angle'] = 170.0
+    for k, v in tune.items():
+        tuning(k, v)
+    (ref,), env = make_pair(field, seed=seed, ratio=ratio, dynamics_kw=dyn, ref_dynamics_kw=rdyn)
+    m = env.M
+    theta0, prev = lattice_theta(m, agent_kw['turn_angle'], seed)
+    ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **agent_kw)
+    ga = S.SimGradientAgent(m, **agent_kw)
+    ga.theta[0] = theta0
+    rng = np.random.default_rng(seed)
+    robs = ref._get_current_obs
+    for it in range(4):
+        coin = rng.integers(0, 2, m)
+        ract = ra.forward(robs, coin=coin.copy())
+        gact = ga.forward(env, coin=coin, use_hints=hints)[0]
+        assert np.array_equal(ga.theta[0], ra._direction_rads), f"theta differs at step {it}"
+        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        robs, rr, _, _, rinfo = ref.step(ract)
+        r, alive = env.step(gact, flags=L.STEP_ALIVE_BITS if tune['feed_bits'] else 0)
+        assert np.array_equal(ref_cells_linear(ref), env.cells()[0]), f"cells differ at step {it}"
+        assert rinfo['num_agents'] == alive[0]
+        assert _rel(rr, r[0]) < 1e-10 or abs(rr - r[0]) < 1e-9
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
