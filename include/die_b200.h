@@ -321,7 +321,9 @@ int die_slab_corner_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, vo
 
 /* Field-pass implementation switch (tests / A-B timing): 0 = shared-memory tile kernel (default),
  * 1 = register-tiled warp-marching kernel (blur radius <= 3; measured slower on B200 so far: 0.29 vs
- * 0.25 ms at 4096^2).  Both give bit-identical results. */
+ * 0.25 ms at 4096^2), 2 = persistent kernel whose halo tiles arrive by cp.async.bulk + mbarrier into a
+ * two-stage ring (blur radius <= 4, periodic diffusion, W % 4 == 0 and W >= one staged row, else the tile
+ * kernel runs; staged, not yet timed).  All give bit-identical results. */
 int die_set_field_impl(int32_t impl);
 
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
