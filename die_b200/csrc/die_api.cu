@@ -310,7 +310,8 @@ static cudaError_t launch_field_bulk(const FieldArgs& fa, int B, int num_sms, cu
 // what the bulk kernel needs: periodic diffusion, rows that are 16-byte aligned for the int32 claims and wrap at most once
 template <int R, bool GRAD>
 static bool bulk_field_ok(const FieldArgs& fa) {
-    return fa.diffuse_mode == DIE_DIFFUSE_WRAP && fa.W % 4 == 0 && fa.W >= BulkGeom<R, 32, 64, GRAD>::LWA;
+    return fa.diffuse_mode == DIE_DIFFUSE_WRAP && fa.W % 4 == 0 && fa.W >= BulkGeom<R, 32, 64, GRAD>::LWA &&
+           ((uintptr_t)fa.medium_in & 15) == 0 && ((uintptr_t)fa.winner & 15) == 0;     // (a caller's odd view of a tensor)
 }
 
 template <int R>
