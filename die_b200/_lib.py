@@ -97,6 +97,7 @@ SIGNATURES = {
     "die_env_refresh_alive": (C.c_int, [_P, _P, _P]),
     "die_set_turn_quick": (C.c_int, [C.c_int32]),
     "die_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
+    "die_get_counter": (C.c_int64, [C.c_char_p]),
     "die_slab_create": (C.c_int, [C.POINTER(DieSlabGeom), C.POINTER(DieDynamics), C.POINTER(_P)]),
     "die_slab_destroy": (C.c_int, [_P]),
     "die_slab_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -74,6 +74,21 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 }
 
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
+
+// launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
+static int64_t g_count_field_tile = 0, g_count_field_march = 0, g_count_field_bulk = 0, g_count_fwd_lean = 0,
+               g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+
+extern "C" int64_t die_get_counter(const char* key) {
+    if (key == nullptr) return -1;
+    if (strcmp(key, "field_tile") == 0) return g_count_field_tile;
+    if (strcmp(key, "field_march") == 0) return g_count_field_march;
+    if (strcmp(key, "field_bulk") == 0) return g_count_field_bulk;
+    if (strcmp(key, "forward_lean") == 0) return g_count_fwd_lean;
+    if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
+    if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
+    return -1;
+}
 extern "C" const char* die_last_error(void) { return g_err; }
 
 static int check_dynamics(const die_dynamics_t* d) {
@@ -268,6 +283,7 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     if (err != cudaSuccess) return err;
     const int64_t grid = (int64_t)a.tiles_i * a.tiles_j * B;
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    ++g_count_field_tile;
     return cudaGetLastError();
 }
 
@@ -281,6 +297,7 @@ static cudaError_t launch_march(const FieldArgs& a, int B, cudaStream_t st) {
     const int64_t warps = (int64_t)geo.strips * geo.rblocks * B;
     const int64_t grid = (warps + 7) / 8;
     field_march_kernel<R, GRAD, RB><<<(unsigned)grid, 256, 0, st>>>(a, geo);
+    ++g_count_field_march;
     return cudaGetLastError();
 }
 
@@ -304,6 +321,7 @@ static cudaError_t launch_field_bulk(const FieldArgs& fa, int B, int num_sms, cu
     const int64_t cap = (int64_t)(num_sms > 0 ? num_sms : 148) * 2;          // two resident CTAs per SM, one wave
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     kern<<<grid, NT, GEO::kSmemBytes, st>>>(a, (int)total);
+    ++g_count_field_bulk;
     return cudaGetLastError();
 }
 
@@ -762,6 +780,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     }
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
+    ++(lean ? (a.grad32 != nullptr ? g_count_fwd_lean_f32 : g_count_fwd_lean) : g_count_fwd_general);
     if (speculate) env->pending_move = 1;
     return DIE_OK;
 }

@@ -272,6 +272,10 @@ int die_set_turn_quick(int32_t on);
  * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1/2 (tile / register-march / persistent bulk-async tiles, the last one staged and untimed), "grad_f32" 0/1 (see die_env_gradient_kind),
  * "feed_min_blocks" 1/4/5 (register cap of the feed kernel; 1 = the compiler's choice). */
 int die_set_tuning(const char* key, int32_t value);
+/* How often a kernel variant has been launched by this process (diagnostics for tests: "the variant I selected is the
+ * one that ran"): "field_tile", "field_march", "field_bulk", "forward_lean", "forward_lean_f32", "forward_general";
+ * -1 for an unknown key. */
+int64_t die_get_counter(const char* key);
 
 /* ---------------------------------------------------------------------------------------------
  * One field split into row slabs over G GPUs (BASELINE configs[4]; SURVEY section 8e, mode 2).

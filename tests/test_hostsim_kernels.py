@@ -171,7 +171,9 @@ def test_physarum_free_run_float32_gradient_cache(portable_math, tuning, impl, l
     tuning("grad_f32", 1)
     tuning("field_impl", impl)
     tuning("fwd_lean", lean)
+    march0 = S.lib().die_get_counter(b"field_march")
     env, ga, flags = _physarum_free_run((48, 80), 30, PHYS)
+    assert (S.lib().die_get_counter(b"field_march") - march0 == 30) == (impl == 1)
     assert S.lib().die_env_gradient_kind(env.handle) == 2 and not S.lib().die_env_gradient(env.handle)
     assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
     # GradientAgent needs the gradient's value: the float32 cache must be ignored, results still exact
@@ -211,7 +213,10 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
                                         ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0]),
                                         ("grad_f32", [1]), ("feed_min_blocks", [4, 5])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
+    lean0 = S.lib().die_get_counter(b"forward_lean")
     base = _philox_run((40, 72), 12)
+    # the default configuration's steady state IS the LEAN forward (every step but the first, which has no hints yet)
+    assert S.lib().die_get_counter(b"forward_lean") == lean0 + 11
     for v in values:
         tuning(key, v)
         out = _philox_run((40, 72), 12)
@@ -246,6 +251,7 @@ def test_bulk_field_kernel_equals_tile_kernel(tuning, shape, sigma, batch, grad)
     radii 1..4, batches (several tiles per persistent CTA), with (Physarum) and without (Brownian) the gradient cache,
     float64 and float32 gradient."""
     outs = []
+    bulk0 = S.lib().die_get_counter(b"field_bulk")
     for impl, f32 in ((0, 0), (2, 0), (2, 1)):
         tuning("field_impl", impl)
         tuning("grad_f32", f32)
@@ -262,6 +268,7 @@ def test_bulk_field_kernel_equals_tile_kernel(tuning, shape, sigma, batch, grad)
             env.step(act)
         outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.reward.copy(),
                      None if f32 else env.gradient()))
+    assert S.lib().die_get_counter(b"field_bulk") == bulk0 + 10, "the bulk kernel must be the one that ran"
     for k in (1, 2):
         for a, b, what in zip(outs[0], outs[k], ("medium", "agents", "theta", "reward", "gradient")):
             if a is None or b is None:
@@ -272,6 +279,7 @@ def test_bulk_field_kernel_equals_tile_kernel(tuning, shape, sigma, batch, grad)
 def test_bulk_field_kernel_falls_back_where_it_does_not_apply(tuning):
     """Widths that are not a multiple of 4 (claim rows would not be 16-byte aligned), narrower than a staged row, or a
     non-periodic diffuse_mode: field_impl = 2 silently runs the tile kernel."""
+    bulk0 = S.lib().die_get_counter(b"field_bulk")
     for shape, kw in (((40, 70), {}), ((40, 64), {}), ((40, 80), dict(diffuse_mode='reflect'))):
         outs = []
         for impl in (0, 2):
@@ -282,6 +290,7 @@ def test_bulk_field_kernel_falls_back_where_it_does_not_apply(tuning):
                 env.step(ga.forward(env))
             outs.append(env.medium.copy())
         assert np.array_equal(*outs)
+    assert S.lib().die_get_counter(b"field_bulk") == bulk0
 
 
 def test_batched_envs_match_single_envs():
@@ -638,7 +647,8 @@ def test_float32_gradient_cache_on_adversarial_fields(tuning):
     for k, sc in enumerate(scales):                       # 4-row bands of noise at wildly different magnitudes
         chem[4 * k:4 * k + 4, 32:] = noise[4 * k:4 * k + 4, 32:] * sc
     chem[40:, :8] = 3e-6
-    outs = {}
+    outs, counts = {}, {}
+    f32_0 = S.lib().die_get_counter(b"forward_lean_f32")
     for f32 in (0, 1):
         for lean in (0, 1):
             tuning("grad_f32", f32)
@@ -655,6 +665,8 @@ def test_float32_gradient_cache_on_adversarial_fields(tuning):
                 trace.append((act, ga.theta.copy(), env.medium.copy(), env.agents.copy()))
             outs[(f32, lean)] = trace
             assert S.lib().die_env_gradient_kind(env.handle) == (2 if f32 else 1)
+            counts[(f32, lean)] = S.lib().die_get_counter(b"forward_lean_f32")
+    assert counts[(1, 0)] == f32_0 and counts[(1, 1)] == f32_0 + 5       # LEAN + float32 cache: steps 2..6
     base = outs[(0, 0)]
     for key, trace in outs.items():
         for it, (a, b) in enumerate(zip(base, trace)):
