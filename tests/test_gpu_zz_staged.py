@@ -52,9 +52,12 @@ def _run(key, value, shape=(128, 96), steps=40, adversarial=False):
 
 @pytest.mark.parametrize("adversarial", [False, True])
 def test_float32_gradient_cache_does_not_change_results(adversarial):
+    from die_b200 import _lib
     base, hints0 = _run("grad_f32", 0, adversarial=adversarial)
+    n0 = _lib.load().die_get_counter(b"forward_lean_f32")
     out, hints1 = _run("grad_f32", 1, adversarial=adversarial)
     assert hints0 == hints1 == (True, True)
+    assert _lib.load().die_get_counter(b"forward_lean_f32") > n0, "the float32 LEAN forward must be the one that ran"
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(base[:3], out[:3])) and base[3] == out[3]
 
 
@@ -101,6 +104,7 @@ def test_bulk_field_kernel_does_not_change_results(shape, sigma, batch):
     from die_b200 import _lib
     lib = _lib.load()
     outs = []
+    n0 = lib.die_get_counter(b"field_bulk")
     try:
         for impl in (0, 2):
             _lib.check(lib.die_set_tuning(b"field_impl", impl))
@@ -113,4 +117,5 @@ def test_bulk_field_kernel_does_not_change_results(shape, sigma, batch):
             outs.append((*env.get_state(), ag.get_state()[0]))
     finally:
         _lib.check(lib.die_set_tuning(b"field_impl", 0))
+    assert lib.die_get_counter(b"field_bulk") == n0 + 12, "the bulk kernel must be the one that ran"
     assert all(np.array_equal(a, b) for a, b in zip(*outs))
