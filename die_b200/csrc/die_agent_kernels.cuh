@@ -305,8 +305,17 @@ gradient_forward_kernel(const GradientArgs a) {
             double s2, c2;
             if (fused_heading) die_sincos_angle(dirn, &s2, &c2, &heading);
             else die_sincos(dirn, &s2, &c2);
-            gx = dr * c2;
-            gy = dr * s2;
+            if (LEAN || p.normalized_grad) {      // dr = 1: 1 * c2 - 0 * s2 = c2 exactly (neither is ever zero)
+                gx = c2;
+                gy = s2;
+            } else {
+                // polar2xy(dr, d) = dr * exp(1j d) with a REAL array dr (core/utils.py:154-164): numpy promotes it to
+                // dr + 0j and multiplies complex numbers, (dr c - 0 s) + 1j (dr s + 0 c).  The same numbers as
+                // (dr c, dr s) unless dr == 0 (a zero gradient), where only the zeros' signs differ -- and those decide
+                // whether the next heading angle(gx + 1j gy) is 0 or pi.
+                gx = __dsub_rn(__dmul_rn(dr, c2), __dmul_rn(0.0, s2));
+                gy = __dadd_rn(__dmul_rn(dr, s2), __dmul_rn(0.0, c2));
+            }
         } else {
             die_normalize_gradient(&gx, &gy, p.normalized_grad, p.use_grad_clip, p.grad_clip);
         }

@@ -53,6 +53,8 @@ struct die_env {
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     float2* grad32;        // [B][H*W]  the same rounded to float32 (lazy; tuning "grad_f32")
     int grad_kind;         // which of the two the LAST field pass wrote: 0 none, 1 grad, 2 grad32
+    int grad_f32_ok;       // the last agent that acted through this env only needs the gradient for the guard-banded
+                           // turn decision (normalised Physarum, die_turn_plan enabled): float32 is enough for it
     int publish_grad;
     double* part_gain;     // [B][nblk]
     int32_t* part_alive;   // [B][nblk]
@@ -205,12 +207,15 @@ extern "C" int die_env_set_food_flow(die_env_t* e, const double* rwave_dev, cons
 
 extern "C" const int32_t* die_env_cells(const die_env_t* e) { return e ? e->cells2[e->cur] : nullptr; }
 
-static int g_grad_f32 = 0;         // the field pass publishes np.gradient(chem1) as float32 pairs instead of float64 ones
+static int g_grad_f32 = 1;         // the field pass may publish np.gradient(chem1) as float32 pairs (see die_env_gradient_kind)
+
+// float32 pairs iff the switch is on AND the env's current consumer only thresholds the gradient
+static inline bool publish_as_f32(const die_env* e) { return g_grad_f32 && e->grad_f32_ok; }
 
 // the buffer the next field pass publishes into (allocated on first use)
 static int ensure_gradient_buffer(die_env* e) {
     const size_t n = (size_t)e->H * e->W * e->B;
-    if (g_grad_f32) {
+    if (publish_as_f32(e)) {
         if (e->grad32 == nullptr) DIE_CUDA(cudaMalloc(&e->grad32, sizeof(float2) * n));
     } else if (e->grad == nullptr) {
         DIE_CUDA(cudaMalloc(&e->grad, sizeof(double2) * n));
@@ -220,12 +225,8 @@ static int ensure_gradient_buffer(die_env* e) {
 
 extern "C" int die_env_publish_gradient(die_env_t* e, int32_t on) {
     DIE_REQUIRE(e != nullptr);
-    if (on) {
-        if (int rc = ensure_gradient_buffer(e)) return rc;
-    } else {
-        e->grad_kind = 0;
-    }
-    e->publish_grad = on ? 1 : 0;
+    if (!on) e->grad_kind = 0;
+    e->publish_grad = on ? 1 : 0;        // (the buffer is allocated by the first field pass that publishes)
     return DIE_OK;
 }
 
@@ -367,9 +368,9 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     a.consumed = e->consumed + b0 * C;
     if (e->publish_grad && e->dyn.blur_radius > 0) {
         if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
-        if (g_grad_f32) a.grad32 = e->grad32 + b0 * C;
+        if (publish_as_f32(e)) a.grad32 = e->grad32 + b0 * C;
         else a.grad = e->grad + b0 * C;
-        e->grad_kind = g_grad_f32 ? 2 : 1;
+        e->grad_kind = publish_as_f32(e) ? 2 : 1;
     } else {
         e->grad_kind = 0;
     }
@@ -810,6 +811,8 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
             if (int rc = die_env_discard_move(e, stream)) return rc;
         }
     }
+    // what the NEXT field pass publishes follows this consumer: float32 pairs serve the guard-banded turn decision only
+    e->grad_f32_ok = (p != nullptr && p->discrete_turn && p->normalized_grad && plan_for(p).enabled) ? 1 : 0;
     const double* grad_hint = (flags & DIE_FWD_USE_GRADIENT) ? die_env_gradient(e) : nullptr;
     const float2* grad32_hint = ((flags & DIE_FWD_USE_GRADIENT) && die_env_gradient_kind(e) == 2) ? e->grad32 : nullptr;
     const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;

@@ -126,10 +126,12 @@ const int32_t* die_env_cells(const die_env_t* env);   /* device ptr, int32 [B][M
  * medium / agents written by the last die_env_step and until they are modified by the caller. */
 int die_env_publish_gradient(die_env_t* env, int32_t on);
 const double* die_env_gradient(const die_env_t* env);
-/* With die_set_tuning("grad_f32", 1) the pairs are published rounded to float32 instead (8 bytes per cell written
- * and gathered): the guard-banded turn decision of PhysarumAgent rounds the gradient to float32 anyway and re-samples
- * chem1 in float64 whenever it defers to the reference arithmetic (die_b200/csrc/die_turn.h), so results do not
- * change; a policy that uses the gradient's VALUE (GradientAgent) ignores the float32 cache.
+/* When the agent that last acted through this env (die_env_forward_gradient) only thresholds the gradient -- a
+ * PhysarumAgent on normalised gradients whose turn rule admits the guard-banded float32 decision -- the pairs are
+ * published rounded to float32 instead (8 bytes per cell written and gathered; die_set_tuning("grad_f32", 0) turns
+ * this off): that decision rounds the gradient to float32 as its first operation anyway and re-samples chem1 in
+ * float64 whenever it defers to the reference arithmetic (die_b200/csrc/die_turn.h), so results do not change.  A
+ * policy that uses the gradient's VALUE (GradientAgent, unnormalised gradients) gets float64 pairs.
  * die_env_gradient_kind: what the last step published -- 0 nothing, 1 float64 (die_env_gradient()), 2 float32
  * (internal; reached through die_env_forward_gradient's DIE_FWD_USE_GRADIENT). */
 int die_env_gradient_kind(const die_env_t* env);

@@ -106,7 +106,9 @@ def polar2xy(r, theta):
     if _MATH == 'portable':
         from oracle import portable_math
         s, c = portable_math.sincos(theta)
-        return r * c, r * s
+        # numpy promotes a real r to r + 0j and multiplies complex numbers: (r c - 0 s) + 1j (r s + 0 c).  Only the
+        # signs of exact zeros (r == 0) differ from (r c, r s), but those decide angle() = 0 or pi
+        return r * c - 0.0 * s, r * s + 0.0 * c
     z = r * np.exp(np.multiply(1j, theta))
     return np.real(z), np.imag(z)
 

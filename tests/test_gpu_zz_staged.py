@@ -47,7 +47,7 @@ def _run(key, value, shape=(128, 96), steps=40, adversarial=False):
             total += r
         return (*env.get_state(), ag.get_state()[0], total), ag.last_hints
     finally:
-        _lib.check(lib.die_set_tuning(key.encode(), 0 if key == "grad_f32" else 1))
+        _lib.check(lib.die_set_tuning(key.encode(), 1))          # the default of both switches
 
 
 @pytest.mark.parametrize("adversarial", [False, True])

@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0, grad_f32=0, feed_min_blocks=1)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0, grad_f32=1, feed_min_blocks=1)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -140,8 +140,9 @@ def _physarum_free_run(field, iters, agent_kw, seed=2, dynamics_kw=None, ref_dyn
 
 def test_physarum_free_run_with_env_hints(portable_math):
     """Published gradient + cell cache (the steady-state path of the drop-in loop)."""
-    _, _, flags = _physarum_free_run((48, 80), 30, PHYS)
+    env, _, flags = _physarum_free_run((48, 80), 30, PHYS)
     assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
+    assert S.lib().die_env_gradient_kind(env.handle) == 2        # a decision-only consumer: float32 pairs by default
 
 
 def test_physarum_free_run_without_hints(portable_math):
@@ -177,7 +178,7 @@ def test_physarum_free_run_float32_gradient_cache(portable_math, tuning, impl, l
     assert S.lib().die_env_gradient_kind(env.handle) == 2 and not S.lib().die_env_gradient(env.handle)
     assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
     # GradientAgent needs the gradient's value: the float32 cache must be ignored, results still exact
-    test_gradient_agent_inertia_noise(None)
+    test_gradient_agent_inertia_noise(None, 0.9, 0.025)
 
 
 @pytest.mark.parametrize("mode", ['reflect', 'nearest', 'mirror', 'constant'])
@@ -211,12 +212,13 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
                                         ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0]),
-                                        ("grad_f32", [1]), ("feed_min_blocks", [4, 5])])
+                                        ("grad_f32", [0]), ("feed_min_blocks", [4, 5])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
-    lean0 = S.lib().die_get_counter(b"forward_lean")
+    lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
-    # the default configuration's steady state IS the LEAN forward (every step but the first, which has no hints yet)
-    assert S.lib().die_get_counter(b"forward_lean") == lean0 + 11
+    # the default configuration's steady state IS the LEAN forward on the float32 gradient cache (every step but the
+    # first, which has no hints yet)
+    assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + 11
     for v in values:
         tuning(key, v)
         out = _philox_run((40, 72), 12)
@@ -321,11 +323,13 @@ def test_batched_envs_match_single_envs():
         assert env.reward[b] == e1.reward[0] and env.alive[b] == e1.alive[0]
 
 
-def test_gradient_agent_inertia_noise(portable_math):
-    """GradientAgent (no discrete turn): momentum with injected noise, prev_grad state."""
+@pytest.mark.parametrize("inertia,noise_scale", [(0.9, 0.025), (0.0, 0.0), (0.0, 0.025)])
+def test_gradient_agent_inertia_noise(portable_math, inertia, noise_scale):
+    """GradientAgent (no discrete turn): momentum with injected noise, prev_grad state.  With inertia = noise_scale = 0
+    the momentum step only matters for the signs of zeros (clipped gradients) -- which decide heading 0 vs pi."""
     (ref,), env = make_pair((40, 56), seed=21)
     m = env.M
-    kw = dict(scale=0.01, deposit=4.0, inertia=0.9, sense_offset=0.02, noise_scale=0.025)
+    kw = dict(scale=0.01, deposit=4.0, inertia=inertia, sense_offset=0.02, noise_scale=noise_scale)
     rng = np.random.default_rng(21)
     prev = rng.normal(0., 0.4, size=(2, m))
     ra = R.GradientAgent(max_agents=m, prev_grad=prev.copy(), **kw)
@@ -343,6 +347,41 @@ def test_gradient_agent_inertia_noise(portable_math):
         r, _ = env.step(gact)
         assert _rel(rr, r[0]) < 1e-11
         assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+    assert S.lib().die_env_gradient_kind(env.handle) == 1        # GradientAgent uses the gradient's value: float64 pairs
+
+
+def test_gradient_cache_follows_its_consumer(portable_math):
+    """One env, a PhysarumAgent and a GradientAgent taking turns: the field pass publishes float32 pairs after a
+    decision-only forward and float64 pairs after a value-using one; a forward that finds the wrong kind samples chem1
+    itself.  Everything stays bit-exact against the oracle."""
+    (ref,), env = make_pair((40, 56), seed=23)
+    m = env.M
+    theta0, prev = lattice_theta(m, 30, 23)
+    rp = R.PhysarumAgent(max_agents=m, prev_grad=prev, **PHYS)
+    gp = S.SimGradientAgent(m, **PHYS)
+    gp.theta[0] = theta0
+    kw = dict(scale=0.01, deposit=4.0, inertia=0.9, sense_offset=0.02, noise_scale=0.025)
+    rg = R.GradientAgent(max_agents=m, prev_grad=prev.copy(), **kw)
+    gg = S.SimGradientAgent(m, discrete_turn=False, **kw)
+    gg.theta[0], gg.prev_grad[0] = R.get_radians(prev), prev
+    rng = np.random.default_rng(3)
+    kinds = []
+    for it in range(12):
+        physarum = (it // 2) % 2 == 0
+        if physarum:
+            coin = rng.integers(0, 2, m)
+            ract = rp.forward(ref._get_current_obs, coin=coin.copy())
+            gact = gp.forward(env, coin=coin)[0]
+        else:
+            noise = rng.normal(0., 0.4, size=(2, m))
+            ract = rg.forward(ref._get_current_obs, noise=noise.copy())
+            gact = gg.forward(env, noise=noise)[0]
+        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        ref.step(ract)
+        env.step(gact)
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+        kinds.append(S.lib().die_env_gradient_kind(env.handle))
+    assert kinds == [2, 2, 1, 1] * 3
 
 
 def test_host_buffer_step_is_chunked_and_identical(tuning):
@@ -720,6 +759,33 @@ def test_gradient_processing_variants(portable_math, kw):
     """grad_clip=None (nan_to_num of 0/0) and unnormalised gradients: the quick turn decision is not offered there,
     every slot takes the reference arithmetic."""
     _physarum_free_run((28, 44), 8, dict(PHYS, **kw), seed=12, exact=kw.get('normalized_grad', True))
+
+
+def test_unnormalised_zero_gradient_headings_match_numpy_itself():
+    """The oracle in its DEFAULT math backend (numpy's own complex arithmetic, as the reference): a zero gradient with
+    normalized_grad=False gives g' = 0 * exp(1j d) = (0 c - 0 s) + 1j (0 s + 0 c) -- numpy promotes the real radius to a
+    complex number -- and the signs of those zeros, of 0 * prev_grad and of 0 * noise decide whether the next heading
+    is 0 or pi.  No libm function is involved at step 0 (chem1 == 0), so the comparison is exact, signs included."""
+    (ref,), env = make_pair((32, 48), seed=12)
+    m = env.M
+    theta0, prev = lattice_theta(m, 30, 12)
+    kw = dict(PHYS, normalized_grad=False)
+    ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **kw)
+    ga = S.SimGradientAgent(m, **kw)
+    ga.theta[0], ga.prev_grad[0] = theta0, prev
+    rng = np.random.default_rng(0)
+    for variant in range(4):                               # all sign patterns of prev / noise
+        coin = rng.integers(0, 2, m)
+        noise = rng.normal(0., 0.4, size=(2, m)) * (1 if variant % 2 == 0 else -1)
+        ra._prev_grad = np.abs(ra._prev_grad) * (1 if variant < 2 else -1) * np.where(rng.random((2, m)) < 0.5, 1, -1)
+        ga.prev_grad[0] = ra._prev_grad
+        ra._direction_rads = theta0.copy()
+        ga.theta[0] = theta0
+        ract = ra.forward(ref._get_current_obs, coin=coin.copy(), noise=noise.copy())
+        gact = ga.forward(env, coin=coin, noise=noise, use_hints=False)[0]
+        assert np.array_equal(ga.theta[0], ra._direction_rads)
+        assert np.array_equal(gact, ract) and np.array_equal(np.signbit(gact), np.signbit(ract))
+        assert np.array_equal(np.signbit(ga.prev_grad[0]), np.signbit(ra._prev_grad))
 
 
 def test_gradient_agent_in_kernel_noise_is_reproducible():
