@@ -9,7 +9,7 @@ mkdir -p $out
 B="python bench.py --no-cpu --no-e2e"
 
 echo "== 1. staged GPU tests (grad_f32, feed caps, unnormalised momentum): XPASS = holds on hardware" | tee $out/${tag}_summary.txt
-timeout 600 python -m pytest tests/test_gpu_zz_staged.py -q -rxX 2>&1 | tail -15 | tee -a $out/${tag}_summary.txt
+timeout 600 python -m pytest tests/test_gpu_zz_staged.py -q -rxXs 2>&1 | tail -15 | tee -a $out/${tag}_summary.txt
 
 echo "== 2. A-B, batched 4096 x 256^2 and single 4096^2 (one JSON line each; compare ms_per_step and roofline.kernels)" | tee -a $out/${tag}_summary.txt
 for variant in "" "--tune grad_f32=1" "--tune feed_min_blocks=4" "--tune feed_min_blocks=5" \
