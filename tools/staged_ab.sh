@@ -8,12 +8,11 @@ out=gpurun_out
 mkdir -p $out
 B="python bench.py --no-cpu --no-e2e"
 
-echo "== 1. staged GPU tests (grad_f32, feed caps, unnormalised momentum): XPASS = holds on hardware" | tee $out/${tag}_summary.txt
+echo "== 1. the late-round-1 GPU tests (float32 vs float64 gradient cache, feed caps, unnormalised momentum)" | tee $out/${tag}_summary.txt
 timeout 600 python -m pytest tests/test_gpu_zz_staged.py -q -rxXs 2>&1 | tail -15 | tee -a $out/${tag}_summary.txt
 
 echo "== 2. A-B, batched 4096 x 256^2 and single 4096^2 (one JSON line each; compare ms_per_step and roofline.kernels)" | tee -a $out/${tag}_summary.txt
-for variant in "" "--tune grad_f32=1" "--tune feed_min_blocks=4" "--tune feed_min_blocks=5" \
-               "--tune grad_f32=1 --tune feed_min_blocks=4"; do
+for variant in "" "--tune grad_f32=0" "--tune feed_min_blocks=4" "--tune feed_min_blocks=5"; do
     name=$(echo "base $variant" | tr -d '-' | tr ' =' '__')
     timeout 300 $B --steps 60 --warmup 20 $variant > $out/${tag}_ab_${name}.json 2> $out/${tag}_ab_${name}.err
     python - "$out/${tag}_ab_${name}.json" "$variant" <<'EOF' | tee -a $out/${tag}_summary.txt
@@ -45,7 +44,7 @@ done
 echo "== 4. bulk-async field pass (field_impl=2): correctness first, in its own process, then timing" | tee -a $out/${tag}_summary.txt
 DIE_B200_STAGED_BULK=1 timeout 300 python -m pytest tests/test_gpu_zz_staged.py -q -rxX -k bulk 2>&1 | tail -8 | tee -a $out/${tag}_summary.txt
 if nvidia-smi > /dev/null 2>&1; then
-    for variant in "--tune field_impl=2" "--tune field_impl=2 --tune grad_f32=1"; do
+    for variant in "--tune field_impl=2" "--tune field_impl=2 --tune grad_f32=0"; do
         name=$(echo "$variant" | tr -d '-' | tr ' =' '__')
         timeout 300 $B --steps 60 --warmup 20 $variant > $out/${tag}_ab_${name}.json 2> $out/${tag}_ab_${name}.err
         python - "$out/${tag}_ab_${name}.json" "$variant" <<'EOF' | tee -a $out/${tag}_summary.txt
