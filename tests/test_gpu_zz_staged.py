@@ -91,6 +91,20 @@ def test_unnormalised_physarum_keeps_the_momentum_operands():
     assert np.array_equal(gact, ract)
 
 
+@pytest.mark.xfail(strict=False, reason="example written after the round's GPU budget was spent: not yet run on a GPU")
+@pytest.mark.parametrize("argv", [["--agent", "const"], ["--agent", "rand"], ["--agent", "grad", "--dynamics", "dyn-pred"],
+                                  ["--agent", "physarum", "--dynamics", "dyn-pred", "--frames-every", "10"]])
+def test_simple_agents_example(argv):
+    """examples/simple_agents.py: the reference's four hand-written policies on its two dynamics (callers)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "simple_agents.py"), "--field", "96",
+                          "--iters", "30", *argv], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ms per iteration" in out.stdout and "frames:" in out.stdout
+
+
 @pytest.mark.xfail(strict=False, reason="staged in round 1 without GPU budget; CPU-emulator verified only")
 @pytest.mark.skipif(os.environ.get("DIE_B200_STAGED_BULK") != "1",
                     reason="first run of an mbarrier / cp.async.bulk kernel on hardware: only on request "
