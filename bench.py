@@ -69,6 +69,15 @@ def ncu_traffic(workload, kernel):
         return None
 
 
+def ncu_traffic_note():
+    """Provenance remark of that capture (e.g. "taken before change X"), if the file carries one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get("_note")
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # --------------------------------------------------------------------------------------------
@@ -292,7 +301,7 @@ def roofline_of(meas, B_local, wl_name):
     step_gbs = step_bytes / (meas["ms_per_step"] * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["gbs"], "peak": peak,
             "unit": "GB/s", "frac": kernels[dominant]["frac"], "peak_source": peak_src,
-            "traffic": ncu_traffic(wl_name, dominant), "kernels": kernels,
+            "traffic": ncu_traffic(wl_name, dominant), "traffic_note": ncu_traffic_note(), "kernels": kernels,
             "step": {"algorithmic_bytes": step_bytes, "gbs": round(step_gbs, 1),
                      "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4)}}, step_bytes
 
