@@ -919,3 +919,55 @@ def test_random_configurations_against_the_oracle(portable_math, tuning, seed):
         assert rinfo['num_agents'] == alive[0]
         assert _rel(rr, r[0]) < 1e-10 or abs(rr - r[0]) < 1e-9
         assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DIE_SWEEP_SEEDS", "40"))))
+def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
+    """Second sweep: batches of environments, slot counts below / above the cell count (M != H*W), Brownian and
+    Physarum steps interleaved on the same environments, every kernel variant -- against one oracle per environment."""
+    rng = np.random.default_rng(5000 + seed)
+    h, w = int(rng.choice([3, 8, 20, 33, 40])), int(rng.choice([4, 16, 65, 72, 100]))
+    B = int(rng.choice([1, 2, 3, 5]))
+    C = h * w
+    m = int(rng.choice([max(C // 3, 1), C, C, 2 * C + 7]))
+    sigma = float(rng.choice([0.3, 0.5, 0.8]))
+    for k, v in dict(field_impl=int(rng.choice([0, 1, 2])), grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
+                     feed_bits=int(rng.random() < 0.7), feed_min_blocks=int(rng.choice([1, 4, 5]))).items():
+        tuning(k, v)
+    refs, mediums, agentss = [], [], []
+    for b in range(B):
+        np.random.seed(seed * 10 + b)
+        r0 = R.Env((h, w), R.Dynamics(init_agent_ratio=0.2, diffuse_sigma=sigma), noise_seed=seed * 10 + b)
+        ag = np.zeros((4, m))
+        n = min(m, C)
+        ag[:, :n] = r0.agents[:, :n]
+        refs.append(R.Env((h, w), R.Dynamics(init_agent_ratio=0.2, diffuse_sigma=sigma), medium=r0.medium, agents=ag))
+        mediums.append(r0.medium)
+        agentss.append(ag)
+    env = S.SimEnv((h, w), np.stack(mediums), np.stack(agentss), D.Dynamics(init_agent_ratio=0.2, diffuse_sigma=sigma), batch=B)
+    th = [lattice_theta(m, 30, seed + b) for b in range(B)]
+    ras = [R.PhysarumAgent(max_agents=m, prev_grad=th[b][1], **PHYS) for b in range(B)]
+    rb = R.BrownianAgent(0.03)
+    ga = S.SimGradientAgent(m, B=B, **PHYS)
+    for b in range(B):
+        ga.theta[b] = th[b][0]
+    for it in range(5):
+        if rng.random() < 0.6:
+            coin = rng.integers(0, 2, (B, m))
+            racts = [ras[b].forward(refs[b]._get_current_obs, coin=coin[b].copy()) for b in range(B)]
+            gact = ga.forward(env, coin=coin).copy()
+            for b in range(B):
+                assert np.array_equal(ga.theta[b], ras[b]._direction_rads), f"theta, env {b}, step {it}"
+        else:
+            u = rng.random((B, 3, m))
+            racts = [rb.forward(refs[b]._get_current_obs, u=u[b]) for b in range(B)]
+            gact = S.brownian_forward(env.agents, move_scale=0.03, u=u)
+        for b in range(B):
+            assert np.array_equal(gact[b], racts[b]), f"action, env {b}, step {it}"
+        outs = [refs[b].step(racts[b]) for b in range(B)]
+        r, alive = env.step(gact, flags=L.STEP_ALIVE_BITS if rng.random() < 0.7 else 0)
+        for b in range(B):
+            assert np.array_equal(ref_cells_linear(refs[b]), env.cells()[b]), f"cells, env {b}, step {it}"
+            assert outs[b][4]['num_agents'] == alive[b]
+            assert _rel(outs[b][1], r[b]) < 1e-10 or abs(outs[b][1] - r[b]) < 1e-9
+            assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
