@@ -8,12 +8,12 @@ there is no CPU or PyTorch fallback."""
 from . import _lib
 from .base_types import DataChannels, channel
 from .env import Env, Dynamics, BoundaryCondition, linear_action_cost, zero_cost
-from .data_init import WaveSequence, FieldSequence
+from .data_init import WaveSequence, FieldSequence, TabulatedSequence, PerlinNoiseSequence
 from .agent import Agent, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent
 
 _lib.load()     # fail loudly at import time if the CUDA library is missing
 
 __all__ = ['Env', 'Dynamics', 'BoundaryCondition', 'linear_action_cost', 'zero_cost',
            'Agent', 'ConstAgent', 'BrownianAgent', 'GradientAgent', 'PhysarumAgent',
-           'DataChannels', 'channel', 'WaveSequence', 'FieldSequence']
+           'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
 __version__ = '0.1.0'

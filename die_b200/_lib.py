@@ -69,6 +69,7 @@ SIGNATURES = {
     "die_env_destroy": (C.c_int, [_P]),
     "die_env_set_dynamics": (C.c_int, [_P, C.POINTER(DieDynamics)]),
     "die_env_set_food_flow": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double]),
+    "die_env_set_food_frames": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, C.c_double]),
     "die_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "die_env_cells": (_P, [_P]),
     "die_env_publish_gradient": (C.c_int, [_P, C.c_int32]),

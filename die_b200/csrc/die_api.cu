@@ -47,6 +47,7 @@ struct die_env {
     const double* flow_col;    // [T][W]
     const double* flow_row;    // [T][H]
     double* flow_ts;           // host [T]
+    const double* flow_frames; // [T][H*W] tabulated sequence (die_env_set_food_frames); borrowed device memory
     int64_t flow_T, flow_k;
     double flow_scale, flow_keep;
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
@@ -190,6 +191,7 @@ extern "C" int die_env_set_food_flow(die_env_t* e, const double* rwave_dev, cons
     delete[] e->flow_ts;
     e->flow_ts = nullptr;
     e->flow_rwave = e->flow_col = e->flow_row = nullptr;
+    e->flow_frames = nullptr;
     if (rwave_dev == nullptr) return DIE_OK;                // back to the identity flow
     DIE_REQUIRE(col_dev != nullptr && row_dev != nullptr && ts_host != nullptr && T >= 1 && k0 >= 0);
     e->flow_ts = new (std::nothrow) double[(size_t)T];
@@ -198,6 +200,19 @@ extern "C" int die_env_set_food_flow(die_env_t* e, const double* rwave_dev, cons
     e->flow_rwave = rwave_dev;
     e->flow_col = col_dev;
     e->flow_row = row_dev;
+    e->flow_T = T;
+    e->flow_k = k0;
+    e->flow_scale = scale;
+    e->flow_keep = 1.0 - decay;
+    return DIE_OK;
+}
+
+extern "C" int die_env_set_food_frames(die_env_t* e, const double* frames_dev, int64_t T, int64_t k0, double scale, double decay) {
+    DIE_REQUIRE(e != nullptr);
+    if (int rc = die_env_set_food_flow(e, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.0, 0.0)) return rc;   // drop any flow
+    if (frames_dev == nullptr) return DIE_OK;
+    DIE_REQUIRE(T >= 1 && k0 >= 0);
+    e->flow_frames = frames_dev;
     e->flow_T = T;
     e->flow_k = k0;
     e->flow_scale = scale;
@@ -278,7 +293,7 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     a.tiles_j = (a.W + TW - 1) / TW;
     const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
-    const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr;
+    const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr && a.flow_frame == nullptr;
     auto kern = plain ? field_step_kernel<R, TH, TW, NT, GRAD, false, true> : field_step_kernel<R, TH, TW, NT, GRAD, false, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -315,7 +330,7 @@ static cudaError_t launch_field_bulk(const FieldArgs& fa, int B, int num_sms, cu
     a.tiles_j = (a.W + TW - 1) / TW;
     const int64_t total = (int64_t)a.tiles_i * a.tiles_j * B;
     if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const bool plain = a.flow_rwave == nullptr;
+    const bool plain = a.flow_rwave == nullptr && a.flow_frame == nullptr;
     auto kern = plain ? field_step_bulk_kernel<R, TH, TW, NT, GRAD, true> : field_step_bulk_kernel<R, TH, TW, NT, GRAD, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::kSmemBytes);
     if (err != cudaSuccess) return err;
@@ -388,6 +403,10 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
         a.flow_col = e->flow_col + k * e->W;
         a.flow_row = e->flow_row + k * e->H;
         a.flow_t = e->flow_ts[k];
+        a.flow_scale = e->flow_scale;
+        a.flow_keep = e->flow_keep;
+    } else if (e->flow_frames != nullptr) {
+        a.flow_frame = e->flow_frames + (e->flow_k % e->flow_T) * (int64_t)C;
         a.flow_scale = e->flow_scale;
         a.flow_keep = e->flow_keep;
     }
@@ -489,7 +508,7 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
     if (int rc = env_step_range(e, 0, e->B, medium_in, medium_out, agents, action, reward_dev, alive_dev,
                                 fused, alive_bits, true, st))
         return rc;
-    if (e->flow_rwave != nullptr) ++e->flow_k;
+    if (e->flow_rwave != nullptr || e->flow_frames != nullptr) ++e->flow_k;
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
     return DIE_OK;
 }
@@ -586,7 +605,7 @@ extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium
             DIE_CUDA(cudaStreamWaitEvent(st, e->host_events[k], 0));
         }
     }
-    if (e->flow_rwave != nullptr) ++e->flow_k;
+    if (e->flow_rwave != nullptr || e->flow_frames != nullptr) ++e->flow_k;
     DIE_CUDA(cudaStreamSynchronize(st));
     return DIE_OK;
 }

@@ -48,6 +48,8 @@ struct FieldArgs {
     const double* flow_col;      // [W]    sin(pi x 3 + t) of the current time step, per column
     const double* flow_row;      // [H]    cos(pi y 3 + t) of the current time step, per row
     double flow_t, flow_scale, flow_keep;
+    const double* flow_frame;    // [H*W]  F_t of the current time step, tabulated by the host (any FieldSequence: the
+                                 //        reference's PerlinNoiseSequence, a user's own); null = wave closed form / identity
     BlurWeights bw;              // centre at [R]
     SlabGeom sg;                 // SLAB instantiation only (H, W above are then the GLOBAL field)
     SlabTables st;
@@ -61,7 +63,9 @@ struct FieldArgs {
 template <bool PLAIN = false>
 __device__ __forceinline__ double next_food(const FieldArgs& a, double f, double cf, int row, int col, int64_t g) {
     double food = a.food_infinite ? f : f - cf;
-    if (!PLAIN && a.flow_rwave != nullptr) {
+    if (!PLAIN && a.flow_frame != nullptr) {           // scale * next(it) + (1 - decay) * current, core/data_init.py:35
+        food = a.flow_scale * a.flow_frame[g] + a.flow_keep * food;
+    } else if (!PLAIN && a.flow_rwave != nullptr) {
         double sn, cs;
         die_sincos(kPi * (a.flow_rwave[g] + a.flow_t), &sn, &cs);
         const double islands = a.flow_col[col] + a.flow_row[row];

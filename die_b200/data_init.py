@@ -135,6 +135,47 @@ class FieldSequence:
     def __getitem__(self, t: float) -> np.ndarray:
         raise NotImplementedError
 
+    def frames(self) -> np.ndarray:
+        """``self[t]`` for every time step, float64 [T, H, W] (cached): what the field kernel reads when the sequence
+        has no closed form on the device (``die_env_set_food_frames``)."""
+        if getattr(self, '_frames', None) is None:
+            self._frames = np.ascontiguousarray(np.stack([np.asarray(self[t], dtype=np.float64) for t in self._ts]))
+        return self._frames
+
+
+class TabulatedSequence(FieldSequence):
+    """A FieldSequence given by its frames [T, H, W] (time step k <-> ``ts[k]``)."""
+
+    def __init__(self, frames: np.ndarray, dt: float = 0.01):
+        frames = np.ascontiguousarray(frames, dtype=np.float64)
+        super().__init__(frames.shape[1:], dt, (0, dt * frames.shape[0]))
+        self._ts = self._ts[:frames.shape[0]]
+        self._frames = frames
+
+    def __getitem__(self, t: float) -> np.ndarray:
+        return self._frames[int(np.argmin(np.abs(self._ts - t)))]
+
+
+class PerlinNoiseSequence(FieldSequence):
+    """core/data_init.py:54-68: 3-D Perlin noise sampled on the grid at every time step, rounded to 3 decimals.
+    ``noise``: a callable ``noise((x, y, t)) -> float``; default ``perlin_noise.PerlinNoise(octaves)`` as in the
+    reference (a third-party, unseeded, pure-Python package -- slow, and absent from this image)."""
+
+    def __init__(self, field_size, dt: float = 0.01, t_bounds: Tuple[float, float] = (0, 1), octaves: int = 8, noise=None):
+        super().__init__(field_size, dt, t_bounds)
+        if noise is None:
+            try:
+                from perlin_noise import PerlinNoise
+            except ImportError as exc:
+                raise ImportError("PerlinNoiseSequence needs the `perlin_noise` package (or pass noise=callable)") from exc
+            noise = PerlinNoise(octaves=octaves)
+        self._noise = noise
+        self._xs = np.linspace(0, 1, self._size[0])
+        self._ys = np.linspace(0, 1, self._size[1])
+
+    def __getitem__(self, t: float) -> np.ndarray:
+        return np.array([[self._noise((x, y, t)) for y in self._ys] for x in self._xs]).round(3)
+
 
 class WaveSequence(FieldSequence):
     """core/data_init.py:71-89: running waves + moving islands."""

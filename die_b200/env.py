@@ -98,6 +98,12 @@ def _is_wave_flow(op) -> bool:
     return isinstance(op, data_init.FoodFlowOperator) and isinstance(op.sequence, data_init.WaveSequence)
 
 
+def _is_sequence_flow(op) -> bool:
+    """Any ``FieldSequence.get_flow_operator(...)``: the wave sequence has a closed form in the kernel, every other
+    sequence is tabulated by the host (``FieldSequence.frames``) and read per cell."""
+    return isinstance(op, data_init.FoodFlowOperator) and isinstance(op.sequence, data_init.FieldSequence)
+
+
 def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
     weights = getattr(d.op_action_cost, '_die_weights', None)
     if weights is None:
@@ -105,10 +111,10 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
             "op_action_cost must be die_b200.env.linear_action_cost or zero_cost: the cost is "
             "evaluated inside the CUDA feed kernel, arbitrary Python operators are not supported")
     if d.op_food_flow is not identity_food_flow and d.op_food_flow is not None \
-            and not _is_wave_flow(d.op_food_flow):
-        raise NotImplementedError("op_food_flow must be the identity or WaveSequence(...).get_flow_operator(...): "
-                                  "the flow is evaluated inside the CUDA field kernel, arbitrary Python operators "
-                                  "(and PerlinNoiseSequence, whose third-party noise is unseeded) are not supported")
+            and not _is_sequence_flow(d.op_food_flow):
+        raise NotImplementedError("op_food_flow must be the identity or <FieldSequence>.get_flow_operator(...) "
+                                  "(WaveSequence, PerlinNoiseSequence, TabulatedSequence, a subclass): the flow is "
+                                  "evaluated inside the CUDA field kernel, arbitrary Python operators are not supported")
     if d.diffuse_mode not in _lib.DIFFUSE_MODES:
         raise ValueError(f"diffuse_mode must be one of {sorted(_lib.DIFFUSE_MODES)} (scipy.ndimage's modes)")
     if d.agents_die:
@@ -247,10 +253,17 @@ class Env:
         """Dynamics.op_food_flow = WaveSequence flow operator -> device tables for the field kernel."""
         op = self.dynamics.op_food_flow
         self._flow_tables = None
-        if not _is_wave_flow(op):
+        if not _is_sequence_flow(op):
             return
         if tuple(op.sequence._size) != tuple(self._field_size):
-            raise ValueError(f"the WaveSequence was built for field {op.sequence._size}, the env is {self._field_size}")
+            raise ValueError(f"the {type(op.sequence).__name__} was built for field {op.sequence._size}, the env is {self._field_size}")
+        if not _is_wave_flow(op):
+            # no closed form on the device: the frames of every time step, tabulated by the sequence's own code
+            frames = torch.from_numpy(op.sequence.frames()).to(self.device)
+            self._flow_tables = [frames]               # borrowed by the library until the handle dies
+            _lib.check(self._lib.die_env_set_food_frames(
+                self._handle, frames.data_ptr(), frames.shape[0], op.calls % frames.shape[0], op.scale, op.decay))
+            return
         rwave, col, row = op.sequence.device_tables()
         ts = np.ascontiguousarray(op.sequence.ts, dtype=np.float64)
         tabs = [torch.from_numpy(a).to(self.device) for a in (rwave, col, row)]

@@ -105,6 +105,12 @@ int die_env_set_dynamics(die_env_t* env, const die_dynamics_t* dyn);
  * die_math.h's.  k0 = index of the first time step to use.  rwave_dev == NULL restores the identity flow. */
 int die_env_set_food_flow(die_env_t* env, const double* rwave_dev, const double* col_dev, const double* row_dev,
                           const double* ts_host, int64_t T, int64_t k0, double scale, double decay);
+/* The same operator for ANY FieldSequence (core/data_init.py:16-51: the reference's PerlinNoiseSequence :54-68, a
+ * user's own subclass): frames_dev [T][H*W] holds sequence[t_k] for every time step, tabulated by the host with the
+ * sequence's own code; the field pass reads one value per cell,  food = scale * F_k[cell] + (1 - decay) * food,  k
+ * advancing by one per step and cycling, starting at k0.  Shared by all environments of a batch; borrowed until
+ * replaced (either setter with a null table restores the identity flow). */
+int die_env_set_food_frames(die_env_t* env, const double* frames_dev, int64_t T, int64_t k0, double scale, double decay);
 
 /* Env.step, core/env.py:101-131: move -> deposit + layout -> feed -> food flow ->
  * diffuse*decay -> reward / num_agents.  Reads medium_in (never written: the previous

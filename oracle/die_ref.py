@@ -338,6 +338,28 @@ class WaveSequence:
         return food_flow
 
 
+class FrameSequence:
+    """core/data_init.py:16-51 (FieldSequence) for a sequence given by its frames [T, H, W] -- what any subclass
+    (PerlinNoiseSequence :54-68, a user's own) amounts to once ``self[t]`` has been evaluated for every time step."""
+
+    def __init__(self, frames: np.ndarray):
+        self._frames = np.asarray(frames, dtype=np.float64)
+
+    def __len__(self):
+        return self._frames.shape[0]
+
+    def get_flow_operator(self, scale: float = 1.0, decay: float = 0.0, k0: int = 0):
+        """core/data_init.py:29-38: scale * next(it) + (1 - decay) * current, the iterator cycling."""
+        state = {'k': int(k0)}
+
+        def food_flow(current):
+            frame = self._frames[state['k'] % len(self)]
+            state['k'] += 1
+            return scale * frame + (1 - decay) * current
+
+        return food_flow
+
+
 # --------------------------------------------------------------------------------------
 # Environment (core/env.py)
 # --------------------------------------------------------------------------------------

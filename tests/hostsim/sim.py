@@ -134,6 +134,13 @@ class SimEnv:
     def medium(self):
         return self.medium_buf[self.cur]
 
+    def set_food_frames(self, op):
+        """Dynamics.op_food_flow = any other FieldSequence's flow operator: tabulated frames."""
+        frames = fenced_copy(op.sequence.frames())
+        self._flow = (frames,)
+        check(self.lib.die_env_set_food_frames(self.handle, ptr(frames), frames.shape[0], op.calls % frames.shape[0],
+                                               op.scale, op.decay))
+
     def set_food_flow(self, op):
         """Dynamics.op_food_flow = WaveSequence flow operator (die_b200/env.py:_install_food_flow)."""
         rwave, col, row = (np.ascontiguousarray(a) for a in op.sequence.device_tables())

@@ -146,6 +146,32 @@ def test_wave_sequence_host_mirror_and_device_tables():
     assert op.calls == 3
 
 
+def test_generic_field_sequences_on_the_host():
+    """TabulatedSequence / PerlinNoiseSequence (core/data_init.py:16-68): frames, the flow operator evaluated on the
+    host equals the oracle's, the iterator cycles; an arbitrary Python operator is still refused by the env."""
+    from oracle import die_ref as R
+    import die_b200 as D
+    from die_b200.env import _dynamics_to_c
+    rng = np.random.default_rng(0)
+    frames = rng.normal(size=(3, 6, 7)).round(3)
+    seq = D.TabulatedSequence(frames)
+    assert len(seq) == 3 and seq.frames().shape == (3, 6, 7) and np.array_equal(seq[seq.ts[2]], frames[2])
+    op, oo = seq.get_flow_operator(0.5, 0.25), R.FrameSequence(frames).get_flow_operator(0.5, 0.25)
+    f = rng.random((6, 7))
+    for _ in range(7):
+        assert np.array_equal(op(f), oo(f))
+    assert op.calls == 7
+    _dynamics_to_c(D.Dynamics(op_food_flow=op))                       # accepted
+    with pytest.raises(NotImplementedError):
+        _dynamics_to_c(D.Dynamics(op_food_flow=lambda food: food * 0.5))
+    # the reference's PerlinNoiseSequence with an injected noise callable (its default needs the perlin_noise package)
+    pn = D.PerlinNoiseSequence((4, 5), dt=0.25, t_bounds=(0, 1), noise=lambda p: p[0] - 2 * p[1] + 0.1234567 * p[2])
+    fr = pn.frames()
+    assert fr.shape == (4, 4, 5)
+    xs, ys = np.linspace(0, 1, 4), np.linspace(0, 1, 5)
+    assert np.array_equal(fr[2], (xs[:, None] - 2 * ys[None, :] + 0.1234567 * 0.5).round(3))
+
+
 def test_agent_postprocess_action_helpers():
     """core/agent/base.py:45-62: mask the action by alive-ness, rescale = identity."""
     import torch

@@ -91,6 +91,41 @@ def test_unnormalised_physarum_keeps_the_momentum_operands():
     assert np.array_equal(gact, ract)
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: emulator-verified, not yet run on a GPU")
+@pytest.mark.parametrize("field,sigma,batch", [((48, 64), 0.5, None), ((37, 53), 0.8, 3)])
+def test_tabulated_food_flow(field, sigma, batch):
+    """Dynamics.op_food_flow of any FieldSequence through its tabulated frames (die_env_set_food_frames): bit-exact
+    against the oracle, the iterator cycling (T = 4 over 10 steps) and surviving the env's own bookkeeping."""
+    import die_b200 as D
+    from oracle import die_ref as R
+    from tests._parity import assert_state_equal
+    rng = np.random.default_rng(9)
+    frames = rng.normal(0.0, 0.3, size=(4, *field)).round(3)
+    gflow = D.TabulatedSequence(frames).get_flow_operator(scale=0.5, decay=0.25)
+    B = batch or 1
+    refs = []
+    for b in range(B):
+        np.random.seed(5 + b)
+        rflow = R.FrameSequence(frames).get_flow_operator(scale=0.5, decay=0.25)
+        refs.append(R.Env(field, R.Dynamics(init_agent_ratio=0.1, op_food_flow=rflow, diffuse_sigma=sigma), noise_seed=5 + b))
+    env = D.Env(field, D.Dynamics(init_agent_ratio=0.1, op_food_flow=gflow, diffuse_sigma=sigma), batch=batch,
+                init_state=(np.stack([r.medium for r in refs]), np.stack([r.agents for r in refs])))
+    ra, ga = R.BrownianAgent(0.01), D.BrownianAgent(move_scale=0.01)
+    m = env.max_agents
+    obs = env._get_current_obs
+    for it in range(10):
+        u = rng.random((B, 3, m))
+        gact = ga.forward(obs, u=u if batch else u[0])
+        for b in range(B):
+            refs[b].step(ra.forward(refs[b]._get_current_obs, u=u[b]))
+        obs, *_ = env.step(gact)
+        med, ag = env.get_state()
+        med, ag = (med, ag) if batch else (med[None], ag[None])
+        for b in range(B):
+            assert_state_equal(refs[b], med[b], ag[b], float_exact=True)
+    assert gflow.calls == 10
+
+
 @pytest.mark.xfail(strict=False, reason="example written after the round's GPU budget was spent: not yet run on a GPU")
 @pytest.mark.parametrize("argv", [["--agent", "const"], ["--agent", "rand"], ["--agent", "grad", "--dynamics", "dyn-pred"],
                                   ["--agent", "physarum", "--dynamics", "dyn-pred", "--frames-every", "10"]])

@@ -971,3 +971,39 @@ def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
             assert outs[b][4]['num_agents'] == alive[b]
             assert _rel(outs[b][1], r[b]) < 1e-10 or abs(outs[b][1] - r[b]) < 1e-9
             assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
+
+
+@pytest.mark.parametrize("field,impl,sigma,batch", [((24, 40), 0, 0.5, None), ((37, 53), 1, 0.5, None), ((20, 20), 0, 0.1, None),
+                                                    ((40, 72), 2, 0.5, 3), ((33, 70), 0, 0.8, 2)])
+def test_tabulated_food_flow(tuning, field, impl, sigma, batch):
+    """op_food_flow of ANY FieldSequence (the reference's PerlinNoiseSequence, a user's own): the host tabulates
+    sequence[t] for every time step, the field pass reads one value per cell: scale * F_k + (1 - decay) * food, k cycling
+    (die_env_set_food_frames).  T = 4 frames over 10 steps: the iterator wraps twice; a batch shares the sequence."""
+    tuning("field_impl", impl)
+    rng = np.random.default_rng(9)
+    frames = rng.normal(0.0, 0.3, size=(4, *field)).round(3)
+    gflow = D.TabulatedSequence(frames).get_flow_operator(scale=0.5, decay=0.25)
+    gflow.calls = 2                                       # start in the middle of the sequence
+    refs = []
+    for b in range(batch or 1):
+        np.random.seed(5 + b)
+        rflow = R.FrameSequence(frames).get_flow_operator(scale=0.5, decay=0.25, k0=2)
+        refs.append(R.Env(field, R.Dynamics(init_agent_ratio=0.1, op_food_flow=rflow, diffuse_sigma=sigma), noise_seed=5 + b))
+    env = S.SimEnv(field, np.stack([r.medium for r in refs]), np.stack([r.agents for r in refs]),
+                   D.Dynamics(init_agent_ratio=0.1, diffuse_sigma=sigma), batch=batch)
+    env.set_food_frames(gflow)
+    ra = R.BrownianAgent(0.01)
+    for it in range(10):
+        u = rng.random((env.B, 3, env.M))
+        acts = np.stack([ra.forward(refs[b]._get_current_obs, u=u[b]) for b in range(env.B)])
+        rr = [refs[b].step(acts[b])[1] for b in range(env.B)]
+        r, _ = env.step(acts)
+        for b in range(env.B):
+            assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
+            assert abs(rr[b] - r[b]) <= 1e-10 * max(1.0, abs(rr[b]))
+    # back to the identity flow
+    S.check(S.lib().die_env_set_food_frames(env.handle, None, 0, 0, 0.0, 0.0))
+    food = env.medium[:, 1].copy()
+    env.step(np.zeros((env.B, 3, env.M)))
+    occ = env.medium[:, 0]
+    assert np.array_equal(env.medium[:, 1], food - (0.1 * food) * occ)
