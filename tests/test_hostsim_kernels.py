@@ -1007,3 +1007,46 @@ def test_tabulated_food_flow(tuning, field, impl, sigma, batch):
     env.step(np.zeros((env.B, 3, env.M)))
     occ = env.medium[:, 0]
     assert np.array_equal(env.medium[:, 1], food - (0.1 * food) * occ)
+
+
+def test_api_argument_checks_profiling_and_set_dynamics():
+    """Host logic of the C ABI, the same C++ the CUDA build compiles: invalid arguments come back as DIE_E_INVALID with
+    a message naming the violated condition (nothing is launched), the per-kernel profiling counts steps, and
+    die_env_set_dynamics changes the dynamics of a live handle."""
+    so = S.lib()
+    (ref,), env = make_pair((24, 32), seed=2)
+    m = env.M
+    act = S.fenced((1, 3, m), fill=0.0)
+    # same buffer as input and output medium
+    rc = so.die_env_step(env.handle, S.ptr(env.medium), S.ptr(env.medium), S.ptr(env.agents), S.ptr(act),
+                         S.ptr(env.reward), S.ptr(env.alive), None)
+    assert rc != 0 and b"medium_in != medium_out" in so.die_last_error()
+    # adopting a move nobody speculated
+    S.check(so.die_env_refresh_alive(env.handle, S.ptr(env.agents), None))
+    rc = so.die_env_step_flags(env.handle, S.ptr(env.medium_buf[0]), S.ptr(env.medium_buf[1]), S.ptr(env.agents), S.ptr(act),
+                               S.ptr(env.reward), S.ptr(env.alive), L.STEP_ADOPT_MOVE, None)
+    assert rc != 0 and b"no speculative move" in so.die_last_error()
+    h = S.C.c_void_p()
+    bad = _dyn = D.env._dynamics_to_c(D.Dynamics())
+    assert so.die_env_create(1, 32, 10, 1, S.C.byref(bad), S.C.byref(h)) != 0 and not h.value      # H >= 2
+    bad.blur_radius = 99
+    assert so.die_env_create(8, 8, 10, 1, S.C.byref(bad), S.C.byref(h)) != 0 and b"blur_radius" in so.die_last_error()
+    assert so.die_set_tuning(b"no_such_switch", 1) != 0 and b"unknown key" in so.die_last_error()
+    assert so.die_get_counter(b"no_such_counter") == -1
+    assert so.die_env_destroy(None) == 0
+    # profiling: events are recorded between the step's kernels; the emulator's events carry no time
+    S.check(so.die_env_set_profiling(env.handle, 1))
+    for _ in range(3):
+        env.step(act)
+    ms = (S.C.c_double * 4)()
+    n = S.C.c_int64()
+    S.check(so.die_env_kernel_times(env.handle, ms, S.C.byref(n)))
+    assert n.value == 3 and list(ms) == [0.0] * 4
+    S.check(so.die_env_set_profiling(env.handle, 0))
+    # set_dynamics on a live handle: no decay, no feeding -> food untouched, chem mass conserved by the blur
+    dyn = D.env._dynamics_to_c(D.Dynamics(rate_feed=0.0, rate_decay_chem=0.0))
+    S.check(so.die_env_set_dynamics(env.handle, S.C.byref(dyn)))
+    env.medium[0, 2] = np.random.default_rng(0).random((24, 32))
+    food, mass = env.medium[0, 1].copy(), env.medium[0, 2].sum()
+    env.step(act)
+    assert np.array_equal(env.medium[0, 1], food) and abs(env.medium[0, 2].sum() - mass) < 1e-9
