@@ -213,7 +213,10 @@ gradient_forward_kernel(const GradientArgs a) {
     // heading angle(cos d + i sin d) comes out of die_sincos_angle together with cos d, sin d
     const bool fused_heading = LEAN || (DISCRETE_TURN && pg == nullptr && p.normalized_grad);
 
-    bool nvalid = first < M;
+    // slots left from this thread's first one (32 bits: one register carried through the loop instead of the 64-bit
+    // `first`, which the compiler otherwise rebuilds from blockIdx for every item's bounds check)
+    const int left = (int)((M - first < (int64_t)kFwdItems * kAgentThreads) ? (M - first) : (int64_t)kFwdItems * kAgentThreads);
+    bool nvalid = left > 0;
     double nx = 0.0, ny = 0.0, nth = 0.0;
     int ncell = 0;
     if (nvalid) {
@@ -232,7 +235,7 @@ gradient_forward_kernel(const GradientArgs a) {
         const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : food[here];
         uint32_t alive_word = 0;
         if (MOVE) alive_word = bits_p[i >> 5];
-        nvalid = (k + 1 < kFwdItems) && (first + i + kAgentThreads < M);
+        nvalid = (k + 1 < kFwdItems) && (i + kAgentThreads < left);
         if (nvalid) {                                          // next item's coalesced loads
             nx = ag_x[i + kAgentThreads];
             ny = ag_x[M + i + kAgentThreads];
