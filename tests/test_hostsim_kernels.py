@@ -1050,3 +1050,37 @@ def test_api_argument_checks_profiling_and_set_dynamics():
     food, mass = env.medium[0, 1].copy(), env.medium[0, 2].sum()
     env.step(act)
     assert np.array_equal(env.medium[0, 1], food) and abs(env.medium[0, 2].sum() - mass) < 1e-9
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("DIE_SWEEP_SEEDS", "24")) // 2))
+def test_random_slab_worlds(seed):
+    """Third sweep: the multi-rank slab world (peer-pointer kernels, owner look-ups, corner mirror) against the single
+    env for random rank counts, field shapes, mirror sizes, agent geometry and blur radii."""
+    rng = np.random.default_rng(9000 + seed)
+    G = int(rng.choice([2, 3, 4, 8]))
+    rows_per = int(rng.choice([4, 5, 8, 16]))
+    shape = (G * rows_per, int(rng.choice([16, 24, 37, 64])))
+    band = int(rng.choice([0, 0, 2, 5, 100]))
+    sigma = float(rng.choice([0.3, 0.5, 0.8, 1.0]))
+    phys = dict(scale=float(rng.choice([0.007, 0.02, 0.1])), turn_angle=float(rng.choice([30, 45])),
+                sense_offset=float(rng.choice([0.0, 0.04, 0.2])))
+    dyn = dict(diffuse_sigma=sigma)
+    (ref,), env = make_pair(shape, seed=seed, ratio=float(rng.choice([0.05, 0.15, 0.5])), dynamics_kw=dyn)
+    m = env.M
+    theta0, _ = lattice_theta(m, phys['turn_angle'], seed)
+    ga = S.SimGradientAgent(m, **phys)
+    ga.theta[0] = theta0
+    world = S.SimSlabWorld(env.medium[0], env.agents[0], theta0, G, dynamics=D.Dynamics(**dyn), corner_r=band, **phys)
+    for it in range(8):
+        coin = rng.integers(0, 2, m)
+        act = ga.forward(env, coin=coin)[0]
+        world.forward(coin)
+        r, alive = env.step(act)
+        wr, walive = world.step()
+        wmed, wag, wth, wact, wcells = world.gather()
+        assert np.array_equal(wact, act), f"action differs at step {it}"
+        assert np.array_equal(wcells, env.cells()[0]), f"cells differ at step {it}"
+        assert np.array_equal(wmed, env.medium[0]), f"medium differs at step {it}"
+        assert np.array_equal(wag, env.agents[0]), f"agents differ at step {it}"
+        assert np.array_equal(wth, ga.theta[0]), f"theta differs at step {it}"
+        assert walive == alive[0] and abs(wr - r[0]) <= 1e-10 * max(1.0, abs(r[0]))
