@@ -1084,3 +1084,59 @@ def test_random_slab_worlds(seed):
         assert np.array_equal(wag, env.agents[0]), f"agents differ at step {it}"
         assert np.array_equal(wth, ga.theta[0]), f"theta differs at step {it}"
         assert walive == alive[0] and abs(wr - r[0]) <= 1e-10 * max(1.0, abs(r[0]))
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (5, 7), (1031, 33), (1000, 3)])
+def test_cells_match_pandas_on_adversarial_coordinates(shape):
+    """nearest_cell (die_device.cuh: the add-magic rounding trick, no correction step) against
+    pandas.Index.get_indexer(method='nearest') -- what xarray's .sel(method='nearest') runs -- on every grid
+    coordinate, every midpoint, their +-3 ulp neighbours and random points, through move_claim."""
+    h, w = shape
+    rng = np.random.default_rng(h * 131 + w)
+
+    def adversarial(n):
+        g = R.grid_coords(n)
+        mids = (g[:-1] + g[1:]) / 2
+        pts = [g, mids]
+        for base in (g, mids):
+            up, dn = base.copy(), base.copy()
+            for _ in range(3):
+                up, dn = np.nextafter(up, 2), np.nextafter(dn, -2)
+                pts += [up.copy(), dn.copy()]
+        pts.append(rng.uniform(0, 1, 5000))
+        return np.clip(np.concatenate(pts), 0.0, 1.0)
+
+    xs, ys = adversarial(h), adversarial(w)
+    m = max(len(xs), len(ys))
+    xs = np.resize(xs, m)
+    ys = np.resize(rng.permutation(ys), m)
+    agents = np.zeros((4, m))
+    agents[0], agents[1] = xs, ys
+    agents[2, ::3] = 1.0
+    env = S.SimEnv(shape, np.zeros((3, h, w)), agents, D.Dynamics(boundary=D.BoundaryCondition.limit))
+    env.step(np.zeros((3, m)))            # 'limit' boundary + zero action: positions unchanged
+    ref = R.nearest_index_pandas(xs, h) * w + R.nearest_index_pandas(ys, w)
+    assert np.array_equal(env.cells()[0], ref.astype(np.int32))
+
+
+def test_sense_cells_clamp_out_of_range():
+    """pos + offset outside [0, 1] clamps to the edge cells (Q4), through the forward kernel."""
+    from oracle import portable_math as P
+    h, w = 64, 48
+    rng = np.random.default_rng(0)
+    m = 4096
+    agents = np.zeros((4, m))
+    agents[0], agents[1] = rng.uniform(0, 1, m), rng.uniform(0, 1, m)
+    agents[0, :64] = np.linspace(0, 0.02, 64)
+    agents[1, 64:128] = np.linspace(0.98, 1.0, 64)
+    env = S.SimEnv((h, w), np.zeros((3, h, w)), agents)
+    theta = rng.uniform(-np.pi, np.pi, m)
+    ga = S.SimGradientAgent(m, sense_offset=0.3, scale=0.01)
+    ga.theta[0] = theta
+    ga.record_sense_cells = True
+    ga.forward(env, coin=np.zeros(m, dtype=np.uint8))
+    s, c = P.sincos(theta)
+    px, py = agents[0] + 0.3 * c, agents[1] + 0.3 * s
+    ref = R.nearest_index_pandas(px, h) * w + R.nearest_index_pandas(py, w)
+    assert np.array_equal(ga.sense_cells[0], ref.astype(np.int32))
+    assert (px < 0).any() and (px > 1).any() and (py < 0).any() and (py > 1).any()
