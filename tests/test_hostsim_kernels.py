@@ -1140,3 +1140,64 @@ def test_sense_cells_clamp_out_of_range():
     ref = R.nearest_index_pandas(px, h) * w + R.nearest_index_pandas(py, w)
     assert np.array_equal(ga.sense_cells[0], ref.astype(np.int32))
     assert (px < 0).any() and (px > 1).any() and (py < 0).any() and (py > 1).any()
+
+
+@pytest.mark.parametrize("sigma,shape", [(1.2, (20, 37)), (1.4, (40, 40)), (1.6, (5, 7)), (1.9, (33, 70)), (2.0, (64, 64))])
+def test_large_blur_radii(portable_math, sigma, shape):
+    """Radii 5..8 of the tile kernel (the bulk and march kernels stop at 4 / 3), incl. a radius larger than the field."""
+    _physarum_free_run(shape, 4, PHYS, seed=16, dynamics_kw=dict(diffuse_sigma=sigma))
+
+
+def test_reward_reduction_with_thousands_of_partials():
+    """finalize_stats_kernel's four-accumulator loop only runs with more than 3072 block partials per environment
+    (M > 3.1 M slots: the 4096^2 field): here 3.3 M slots on a tiny field, against numpy's sum of the same terms."""
+    h, w, m = 8, 8, 3_300_000
+    rng = np.random.default_rng(0)
+    medium = np.zeros((3, h, w))
+    medium[1] = rng.random((h, w)).round(3)
+    agents = np.zeros((4, m))
+    n = 40_000
+    agents[0, :n], agents[1, :n] = rng.integers(0, h, n) / (h - 1), rng.integers(0, w, n) / (w - 1)
+    agents[2, :n], agents[3, :n] = 1.0, 0.5
+    env = S.SimEnv((h, w), medium, agents)
+    action = np.zeros((3, m))
+    action[2] = rng.random(m).round(3)
+    action[0] = rng.normal(0, 0.01, m)
+    stock0 = env.agents[0, 3].copy()
+    r, alive = env.step(action)
+    assert alive[0] == n
+    gained = env.agents[0, 3] - stock0
+    assert abs(r[0] - gained.sum()) <= 1e-9 * abs(gained).sum()
+    # die_env_read_stats: the two D2H copies + sync of the synchronous Env.step
+    rh, ah = S.fenced((1,), fill=np.nan), S.fenced((1,), np.int64, fill=-1)
+    S.check(S.lib().die_env_read_stats(env.handle, S.ptr(env.reward), S.ptr(env.alive), S.ptr(rh), S.ptr(ah), None))
+    assert rh[0] == r[0] and ah[0] == n
+
+
+def test_unknown_boundary_moves_without_wrapping_or_clipping():
+    """core/env.py:158-161: an unfamiliar boundary condition logs a warning and does nothing -- positions leave [0, 1]
+    and their cells clamp to the edge."""
+    (ref,), env = make_pair((16, 16), seed=1)
+    dyn = D.env._dynamics_to_c(D.Dynamics())
+    dyn.boundary = L.BOUNDARY_NONE
+    S.check(S.lib().die_env_set_dynamics(env.handle, S.C.byref(dyn)))
+    pos0 = env.agents[0, :2].copy()
+    action = np.zeros((3, env.M))
+    action[0], action[1] = 0.7, -0.6
+    env.step(action)
+    assert np.array_equal(env.agents[0, :2], pos0 + np.array([[0.7], [-0.6]]))
+    cells = env.cells()[0]
+    assert ((cells // 16)[pos0[0] + 0.7 > 1.0] == 15).all() and ((cells % 16)[pos0[1] - 0.6 < 0.0] == 0).all()
+
+
+@pytest.mark.parametrize("sigma", [0.3, 0.7, 1.0, 1.5])
+def test_sense_mask_other_radii(sigma):
+    """die_sense_mask is templated on the radius; the reference only uses sigma = 2 (radius 8)."""
+    from die_b200.env import gaussian_kernel1d
+    import scipy.ndimage as ndi
+    (ref,), env = make_pair((30, 44), seed=9, ratio=0.05)
+    wts = np.ascontiguousarray(gaussian_kernel1d(sigma))
+    obs = S.fenced(env.medium.shape, fill=np.nan)
+    S.check(S.lib().die_sense_mask(30, 44, 1, S.ptr(wts), (len(wts) - 1) // 2, S.ptr(env.medium), S.ptr(obs), None))
+    mask = np.ceil(ndi.gaussian_filter(env.medium[0, 0], sigma, mode='nearest').round(3)) != 0
+    assert np.array_equal(obs[0], np.where(mask[None], env.medium[0], 0.0))
