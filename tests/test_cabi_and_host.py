@@ -183,3 +183,30 @@ def test_agent_postprocess_action_helpers():
     batched = Agent._masked_alive(agents.expand(2, 4, 3), action.expand(2, 3, 3))
     assert batched.shape == (2, 3, 3) and torch.equal(batched[1], out)
     assert Agent._rescale_outputs(action) is action
+
+
+def test_import_fails_loudly_without_the_cuda_library(tmp_path):
+    """No CPU / PyTorch fallback: with libdie_sm100a.so missing, `import die_b200` itself raises (in a child process,
+    with the library path pointed at a file that does not exist)."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f'''
+        import importlib.util, sys
+        sys.path.insert(0, {root!r})
+        spec = importlib.util.spec_from_file_location("die_b200._build", {os.path.join(root, "die_b200", "_build.py")!r})
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.LIB_PATH = {str(tmp_path / "libdie_sm100a.so")!r}
+        sys.modules["die_b200._build"] = mod
+        try:
+            import die_b200
+        except ImportError as exc:
+            print("ImportError:", exc)
+            sys.exit(0)
+        sys.exit(1)
+    ''')
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "no CPU / PyTorch fallback" in out.stdout
