@@ -210,9 +210,24 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     if (g_fibers.size() < nthreads) g_fibers.resize(nthreads);
     g_smem.assign(smem + 16, (char)0xFF);      // NaN-poisoned: a read of unwritten shared memory shows up in the results
     const int nwarps = (int)((nthreads + 31) / 32);
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
+    // Blocks run one after the other.  HOSTSIM_BLOCK_ORDER = reverse | shuffle runs them in another order: results that
+    // change with it mean a kernel depends on the order in which its CTAs execute, which the hardware does not promise.
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    std::vector<size_t> order(nblocks);
+    for (size_t i = 0; i < nblocks; ++i) order[i] = i;
+    static const char* mode = getenv("HOSTSIM_BLOCK_ORDER");
+    if (mode != nullptr && strcmp(mode, "reverse") == 0) {
+        for (size_t i = 0; i < nblocks; ++i) order[i] = nblocks - 1 - i;
+    } else if (mode != nullptr && strcmp(mode, "shuffle") == 0) {
+        static uint64_t state = 0x9E3779B97F4A7C15ull;
+        for (size_t i = nblocks; i > 1; --i) {              // Fisher-Yates with a fixed-seed xorshift
+            state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+            std::swap(order[i - 1], order[state % i]);
+        }
+    }
+    for (size_t ob = 0; ob < nblocks; ++ob) {
+        const unsigned bx = (unsigned)(order[ob] % grid.x), by = (unsigned)((order[ob] / grid.x) % grid.y),
+                       bz = (unsigned)(order[ob] / ((size_t)grid.x * grid.y));
         g_blk.alive = (int)nthreads;
         g_mbars.clear();
         g_blk.bar_count = 0;
@@ -234,10 +249,15 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
             f.ctx.uc_link = &g_sched;
             makecontext(&f.ctx, trampoline, 0);
         }
+        // HOSTSIM_THREAD_ORDER = reverse: the fibers of a block are scheduled from the last thread down.  A missing
+        // __syncthreads between a producer and a consumer phase can go unnoticed when producers happen to run first.
+        static const char* torder = getenv("HOSTSIM_THREAD_ORDER");
+        const bool treverse = torder != nullptr && strcmp(torder, "reverse") == 0;
         size_t remaining = nthreads;
         while (remaining > 0) {
             bool progressed = false;
-            for (size_t t = 0; t < nthreads; ++t) {
+            for (size_t tt = 0; tt < nthreads; ++tt) {
+                const size_t t = treverse ? nthreads - 1 - tt : tt;
                 Fiber& f = g_fibers[t];
                 if (f.done) continue;
                 if (f.wait_ptr != nullptr && *f.wait_ptr == f.wait_val) continue;

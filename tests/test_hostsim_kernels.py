@@ -1201,3 +1201,21 @@ def test_sense_mask_other_radii(sigma):
     S.check(S.lib().die_sense_mask(30, 44, 1, S.ptr(wts), (len(wts) - 1) // 2, S.ptr(env.medium), S.ptr(obs), None))
     mask = np.ceil(ndi.gaussian_filter(env.medium[0, 0], sigma, mode='nearest').round(3)) != 0
     assert np.array_equal(obs[0], np.where(mask[None], env.medium[0], 0.0))
+
+
+def test_results_do_not_depend_on_block_or_thread_order():
+    """The emulator runs blocks in ascending order and a block's threads from 0 up; the hardware promises neither.
+    A subset of this file again, in a child process, with the blocks shuffled and the threads scheduled from the last
+    one down (HOSTSIM_BLOCK_ORDER / HOSTSIM_THREAD_ORDER): claims by atomicMax, the persistent bulk kernel's tile
+    assignment, the slab world's peer accesses and every producer / consumer phase must give the same bits."""
+    import subprocess
+    import sys
+    if os.environ.get("HOSTSIM_BLOCK_ORDER") or os.environ.get("HOSTSIM_THREAD_ORDER"):
+        pytest.skip("already running under an alternative order")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HOSTSIM_BLOCK_ORDER="shuffle", HOSTSIM_THREAD_ORDER="reverse", DIE_SWEEP_SEEDS="12")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "tests/test_hostsim_kernels.py",
+                          "-k", "brownian_free_run or with_env_hints or fused_move or bulk_field_kernel_equals or "
+                                "slab_world_equals or golden or random_configurations or tuning_switches"],
+                         cwd=root, env=env, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
