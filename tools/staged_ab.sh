@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: does everything that was staged without a GPU hold on hardware, and what is it worth?
-#   gpurun --timeout 1500 -- 'bash tools/staged_ab.sh r02a'
+#   gpurun --timeout 1500 -- 'bash tools/staged_ab.sh r02a'          (append `ncu` for the traffic table + full capture)
 # Writes gpurun_out/<tag>_*.  Every step runs under its own `timeout`; the mbarrier / cp.async.bulk kernel goes last
 # (a protocol error traps after 2 s and poisons only its own process).
 tag=${1:-staged}
@@ -59,5 +59,15 @@ except Exception as exc:
     print(f"{sys.argv[2]:45s} FAILED: {exc!r}")
 EOF
     done
+fi
+if [ "$2" = "ncu" ]; then
+    echo "== 5. ncu: DRAM traffic of the step kernels (batched), full capture at steady state (single field)" | tee -a $out/${tag}_summary.txt
+    timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        --kernel-name regex:"gradient_forward_kernel|move_claim_kernel|field_step_kernel|agent_feed_kernel" \
+        --launch-skip 164 --launch-count 4 --csv --log-file $out/${tag}_ncu_traffic_batch4096.csv \
+        python bench.py --workload batch256 --no-single-field --steps 3 --warmup 40 --no-e2e --no-cpu > $out/${tag}_ncu_traffic.log 2>&1
+    timeout 900 bash tools/ncu_forward.sh ${tag}
+    python tools/ncu_summary.py $out/prof_${tag}.ncu-rep > $out/${tag}_ncu_full_steady_state.txt 2>&1
+    tail -5 $out/${tag}_ncu_traffic_batch4096.csv | cut -c1-300 | tee -a $out/${tag}_summary.txt
 fi
 echo "done" | tee -a $out/${tag}_summary.txt
