@@ -110,7 +110,7 @@ SIGNATURES = {
     "die_slab_cells": (_P, [_P]),
     "die_slab_set_corner_mirror": (C.c_int, [_P, C.c_int32]),
     "die_slab_corner_refresh": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
-    "die_set_field_impl": (C.c_int, [C.c_int32]),
+    "die_set_step_impl": (C.c_int, [C.c_int32]),
     "die_math_sincos": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "die_math_atan2": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
 }

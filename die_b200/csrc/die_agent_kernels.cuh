@@ -410,10 +410,14 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 
 // ---------------------------------------------------------------------------------------------
 // Env._agent_feed per-slot part (core/env.py:220-234, cost :29-35) + the reward / num_agents
-// reduction (:118-121).  consumed[M] = consumed_field[cell(slot)] for ALL M slots (Q1, Q7), where
-// consumed_field = rate_feed * food * occ was written per cell by the field pass.  Alive slots also
-// clear their cell's claim for the next step.  Block partials are written in a fixed layout and
-// summed in a fixed order by finalize_stats_kernel, so the reward is run-to-run deterministic.
+// reduction (:118-121).  consumed[M] = consumed_field[cell(slot)] for ALL M slots (Q1, Q7) with
+// consumed_field = rate_feed * food * occ (:224): the food is medium_in's (the buffer the field pass
+// read and never writes), occ the cell's bit in the occupancy bitmap the field pass wrote -- the same
+// two factors, multiplied in the same order, as the field pass used for food -= consumed_field.
+// (The slab instantiation gathers the per-cell consumed_field its field pass still writes: the cell may
+// live on another GPU.)  Alive slots also clear their cell's claim for the next step.  Block partials are
+// written in a fixed layout and summed in a fixed order by finalize_stats_kernel, so the reward is
+// run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
@@ -421,25 +425,44 @@ constexpr int kFeedItems = 4;      // slots per thread
 // in place); this kernel then also commits the positions, pos = boundary(pos + action[dx, dy])
 // (core/env.py:152-172, the same two operations as move_claim_kernel).
 // BITS: alive-ness comes from the env's bitmask instead of the float64 channel (MOVE implies BITS).
-// MINB: minimum resident CTAs per SM (register cap 65536 / (256 MINB)); 0 = the compiler's own choice (74 registers, 3 CTAs)
-template <bool SLAB, bool MOVE, bool BITS, int MINB = 0>
-__global__ void __launch_bounds__(kAgentThreads, MINB)
-agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action,
-                  const double* __restrict__ consumed_field, int32_t* __restrict__ winner,
-                  const int32_t* __restrict__ cells,
-                  double* __restrict__ part_gain, int32_t* __restrict__ part_alive,
-                  int64_t C, int64_t M, int nblk, double w_dep, double w_dist,
-                  const uint32_t* __restrict__ alive_bits, int64_t Mw, int boundary,
-                  const SlabGeom sg, const SlabTables st) {
+// (register caps were tried in round 2 on a B200: 64 / 48 registers = 4 / 5 CTAs per SM run 10 % / 20 % SLOWER than
+//  the compiler's own 74 registers, profiles/r02a_staged_ab_summary.txt -- removed)
+struct FeedArgs {
+    double* agents;
+    const double* action;
+    const double* medium_in;         // [B][3][C]: channel 1 = the food the field pass consumed from
+    const uint32_t* occ_bits;        // [B][Cw]
+    int32_t* winner;
+    const int32_t* cells;
+    double* part_gain;
+    int32_t* part_alive;
+    int64_t C, Cw, M;
+    int nblk;
+    double rate_feed, w_dep, w_dist;
+    const uint32_t* alive_bits;
+    int64_t Mw;
+    int boundary;
+};
+
+template <bool SLAB, bool MOVE, bool BITS>
+__global__ void __launch_bounds__(kAgentThreads)
+agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
+    const int64_t M = a.M;
+    const int nblk = a.nblk;
     const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
-    double* ag_x = agents + b * 4 * M + first;                 // x; y, alive, agent_food are + M, 2M, 3M
-    const double* ac = action + b * 3 * M + first;
-    const double* cf = consumed_field + b * C;
-    int32_t* win = winner + b * C;
-    const int32_t* cl = cells + b * M + first;
-    const uint32_t* bits_p = BITS ? alive_bits + b * Mw + (first >> 5) : nullptr;
+    double* ag_x = a.agents + b * 4 * M + first;               // x; y, alive, agent_food are + M, 2M, 3M
+    const double* ac = a.action + b * 3 * M + first;
+    const double* food = SLAB ? nullptr : a.medium_in + (b * 3 + 1) * a.C;
+    const uint32_t* occ = SLAB ? nullptr : a.occ_bits + b * a.Cw;
+    int32_t* win = a.winner + b * a.C;
+    const int32_t* cl = a.cells + b * M + first;
+    const uint32_t* bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
+    const double w_dep = a.w_dep, w_dist = a.w_dist;
+    const int boundary = a.boundary;
+    double* const part_gain = a.part_gain;
+    int32_t* const part_alive = a.part_alive;
 
     int cell[kFeedItems];
     double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], eaten[kFeedItems];
@@ -453,7 +476,14 @@ agent_feed_kernel(double* __restrict__ agents, const double* __restrict__ action
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : cf[cell[k]]) : 0.0;
+        if (SLAB) {
+            eaten[k] = valid[k] ? slab_load_consumed(st, sg, cell[k]) : 0.0;
+        } else {
+            // (rate_feed * food) * occ, occ in {0., 1.}: the field pass's own expression for consumed_field
+            const double f = valid[k] ? food[cell[k]] : 0.0;
+            const uint32_t word = valid[k] ? occ[cell[k] >> 5] : 0u;
+            eaten[k] = (a.rate_feed * f) * (((word >> (cell[k] & 31)) & 1u) ? 1.0 : 0.0);
+        }
         if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
         else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {

@@ -6,7 +6,6 @@
 
 #include "die_agent_kernels.cuh"
 #include "die_field_kernels.cuh"
-#include "die_field_bulk.cuh"
 
 using namespace die;
 
@@ -50,7 +49,8 @@ struct die_env {
     const double* flow_frames; // [T][H*W] tabulated sequence (die_env_set_food_frames); borrowed device memory
     int64_t flow_T, flow_k;
     double flow_scale, flow_keep;
-    double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
+    uint32_t* occ_bits;    // [B][Cw]   one bit per cell: occupied in the current step (written by the field pass, read
+    int64_t Cw;            //           by the feed kernel, which forms consumed_field = rate_feed * food * occ from it)
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     float2* grad32;        // [B][H*W]  the same rounded to float32 (lazy; tuning "grad_f32")
     int grad_kind;         // which of the two the LAST field pass wrote: 0 none, 1 grad, 2 grad32
@@ -79,14 +79,11 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_field_tile = 0, g_count_field_march = 0, g_count_field_bulk = 0, g_count_fwd_lean = 0,
-               g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_field_tile = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
     if (strcmp(key, "field_tile") == 0) return g_count_field_tile;
-    if (strcmp(key, "field_march") == 0) return g_count_field_march;
-    if (strcmp(key, "field_bulk") == 0) return g_count_field_bulk;
     if (strcmp(key, "forward_lean") == 0) return g_count_fwd_lean;
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
     if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
@@ -135,7 +132,8 @@ extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
     if (err == cudaSuccess) err = cudaMalloc(&e->cells2[0], sizeof(int32_t) * (size_t)M * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->cells2[1], sizeof(int32_t) * (size_t)M * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->alive_bits, sizeof(uint32_t) * (size_t)e->Mw * B);
-    if (err == cudaSuccess) err = cudaMalloc(&e->consumed, sizeof(double) * C * B);
+    e->Cw = ((int64_t)C + 31) / 32;
+    if (err == cudaSuccess) err = cudaMalloc(&e->occ_bits, sizeof(uint32_t) * (size_t)e->Cw * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double) * B);
@@ -159,7 +157,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->cells2[1]);
     cudaFree(e->alive_bits);
     delete[] e->flow_ts;
-    cudaFree(e->consumed);
+    cudaFree(e->occ_bits);
     cudaFree(e->grad);
     cudaFree(e->grad32);
     cudaFree(e->part_gain);
@@ -303,70 +301,20 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int R, bool GRAD>
-static cudaError_t launch_march(const FieldArgs& a, int B, cudaStream_t st) {
-    constexpr int HALO = R + (GRAD ? 1 : 0), OWV = (32 - 2 * HALO) & ~3, RB = 64;
-    MarchGeom geo;
-    geo.strips = (a.W + OWV - 1) / OWV;
-    geo.rblocks = (a.H + RB - 1) / RB;
-    geo.B = B;
-    const int64_t warps = (int64_t)geo.strips * geo.rblocks * B;
-    const int64_t grid = (warps + 7) / 8;
-    field_march_kernel<R, GRAD, RB><<<(unsigned)grid, 256, 0, st>>>(a, geo);
-    ++g_count_field_march;
-    return cudaGetLastError();
-}
-
 static int g_field_prefetch = 1;   // tile kernel: prefetch the output tile's food lines to L2 while staging
-static int g_field_impl = 0;       // 0 = shared-memory tiles (default: 0.25 ms at 4096^2), 1 = register-tiled march (0.29 ms),
-                                   // 2 = persistent, bulk-async double-buffered tiles (die_field_bulk.cuh; staged, untimed)
-
-template <int R, bool GRAD>
-static cudaError_t launch_field_bulk(const FieldArgs& fa, int B, int num_sms, cudaStream_t st) {
-    constexpr int TH = 32, TW = 64, NT = 256;
-    using GEO = BulkGeom<R, TH, TW, GRAD>;
-    FieldArgs a = fa;
-    a.tiles_i = (a.H + TH - 1) / TH;
-    a.tiles_j = (a.W + TW - 1) / TW;
-    const int64_t total = (int64_t)a.tiles_i * a.tiles_j * B;
-    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const bool plain = a.flow_rwave == nullptr && a.flow_frame == nullptr;
-    auto kern = plain ? field_step_bulk_kernel<R, TH, TW, NT, GRAD, true> : field_step_bulk_kernel<R, TH, TW, NT, GRAD, false>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::kSmemBytes);
-    if (err != cudaSuccess) return err;
-    const int64_t cap = (int64_t)(num_sms > 0 ? num_sms : 148) * 2;          // two resident CTAs per SM, one wave
-    const unsigned grid = (unsigned)(total < cap ? total : cap);
-    kern<<<grid, NT, GEO::kSmemBytes, st>>>(a, (int)total);
-    ++g_count_field_bulk;
-    return cudaGetLastError();
-}
-
-// what the bulk kernel needs: periodic diffusion, rows that are 16-byte aligned for the int32 claims and wrap at most once
-template <int R, bool GRAD>
-static bool bulk_field_ok(const FieldArgs& fa) {
-    return fa.diffuse_mode == DIE_DIFFUSE_WRAP && fa.W % 4 == 0 && fa.W >= BulkGeom<R, 32, 64, GRAD>::LWA &&
-           ((uintptr_t)fa.medium_in & 15) == 0 && ((uintptr_t)fa.winner & 15) == 0;     // (a caller's odd view of a tensor)
-}
 
 template <int R>
 static cudaError_t launch_field(const FieldArgs& fa, int B, int num_sms, cudaStream_t st) {
     const bool want_grad = fa.grad != nullptr || fa.grad32 != nullptr;
-    if constexpr (R <= 4) {
-        if (g_field_impl == 2) {
-            if (want_grad && bulk_field_ok<R, true>(fa)) return launch_field_bulk<R, true>(fa, B, num_sms, st);
-            if (!want_grad && bulk_field_ok<R, false>(fa)) return launch_field_bulk<R, false>(fa, B, num_sms, st);
-        }
-    }
-    if constexpr (R <= 3) {
-        if (g_field_impl == 1 && fa.diffuse_mode == DIE_DIFFUSE_WRAP)
-            return want_grad ? launch_march<R, true>(fa, B, st) : launch_march<R, false>(fa, B, st);
-    }
     return want_grad ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
 }
 
-extern "C" int die_set_field_impl(int32_t impl) {
-    DIE_REQUIRE(impl >= 0 && impl <= 2);
-    g_field_impl = impl;
+static int g_step_impl = 1;        // 0 = always the three kernels move_claim / field_step / agent_feed;
+                                   // 1 = the cluster-fused environment step wherever it applies (die_env_fused.cuh)
+
+extern "C" int die_set_step_impl(int32_t impl) {
+    DIE_REQUIRE(impl == 0 || impl == 1);
+    g_step_impl = impl;
     return DIE_OK;
 }
 
@@ -380,7 +328,10 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     a.medium_out = mout;
     a.winner = e->winner + b0 * C;
     a.action = action;
-    a.consumed = e->consumed + b0 * C;
+    // the tile kernel writes the occupancy bits itself when a warp's 32 cells are one aligned word
+    const bool bits_in_kernel = e->dyn.blur_radius > 0 && e->W % 32 == 0;
+    a.occ_bits = bits_in_kernel ? e->occ_bits + (size_t)b0 * e->Cw : nullptr;
+    a.Cw = e->Cw;
     if (e->publish_grad && e->dyn.blur_radius > 0) {
         if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
         if (publish_as_f32(e)) a.grad32 = e->grad32 + b0 * C;
@@ -411,29 +362,36 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
         a.flow_keep = e->flow_keep;
     }
     for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
+    cudaError_t err = cudaErrorInvalidValue;
     switch (e->dyn.blur_radius) {
         case 0: {
             const int64_t total = (int64_t)e->H * e->W * nb;
             field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
-            return cudaGetLastError();
+            err = cudaGetLastError();
+            break;
         }
-        case 1: return launch_field<1>(a, nb, e->num_sms, st);
-        case 2: return launch_field<2>(a, nb, e->num_sms, st);
-        case 3: return launch_field<3>(a, nb, e->num_sms, st);
-        case 4: return launch_field<4>(a, nb, e->num_sms, st);
-        case 5: return launch_field<5>(a, nb, e->num_sms, st);
-        case 6: return launch_field<6>(a, nb, e->num_sms, st);
-        case 7: return launch_field<7>(a, nb, e->num_sms, st);
-        case 8: return launch_field<8>(a, nb, e->num_sms, st);
+        case 1: err = launch_field<1>(a, nb, e->num_sms, st); break;
+        case 2: err = launch_field<2>(a, nb, e->num_sms, st); break;
+        case 3: err = launch_field<3>(a, nb, e->num_sms, st); break;
+        case 4: err = launch_field<4>(a, nb, e->num_sms, st); break;
+        case 5: err = launch_field<5>(a, nb, e->num_sms, st); break;
+        case 6: err = launch_field<6>(a, nb, e->num_sms, st); break;
+        case 7: err = launch_field<7>(a, nb, e->num_sms, st); break;
+        case 8: err = launch_field<8>(a, nb, e->num_sms, st); break;
     }
-    return cudaErrorInvalidValue;
+    if (err == cudaSuccess && !bits_in_kernel) {           // ragged rows / no diffusion: bits from the claim table
+        const int64_t total = (int64_t)nb * e->Cw * 32;
+        occ_bits_kernel<<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(
+            e->winner + (size_t)b0 * C, e->occ_bits + (size_t)b0 * e->Cw, (int64_t)C, e->Cw, nb);
+        err = cudaGetLastError();
+    }
+    return err;
 }
 
 // ------------------------------------------------------------------------------------------
 // Env.step
 // ------------------------------------------------------------------------------------------
 static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitmask (when valid) instead of the float64 channel
-static int g_feed_min_blocks = 1;  // register cap of the (plain, bitmask) feed kernel: 1 = unhinted (74 registers), 4 -> 64, 5 -> 48
 
 // The four launches of Env.step for environments [b0, b0 + nb) of the batch, on stream `st`.  Every pointer argument
 // refers to the WHOLE batch; the range is resolved here (all per-env arrays are contiguous per environment).
@@ -469,12 +427,15 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
     auto feed = fused ? agent_feed_kernel<false, true, true>
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
-    if (!fused && feed_bits && g_feed_min_blocks == 4) feed = agent_feed_kernel<false, false, true, 4>;
-    if (!fused && feed_bits && g_feed_min_blocks == 5) feed = agent_feed_kernel<false, false, true, 5>;
-    feed<<<fgrid, kAgentThreads, 0, st>>>(
-        agents, action, e->consumed + (size_t)b0 * C, winner, cells, part_gain, part_alive,
-        (int64_t)C, e->M, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-        alive_bits, e->Mw, e->dyn.boundary, SlabGeom(), SlabTables());
+    FeedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.agents = agents; fa.action = action; fa.medium_in = medium_in;
+    fa.occ_bits = e->occ_bits + (size_t)b0 * e->Cw;
+    fa.winner = winner; fa.cells = cells; fa.part_gain = part_gain; fa.part_alive = part_alive;
+    fa.C = (int64_t)C; fa.Cw = e->Cw; fa.M = e->M; fa.nblk = e->nblk;
+    fa.rate_feed = e->dyn.rate_feed; fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
+    fa.alive_bits = alive_bits; fa.Mw = e->Mw; fa.boundary = e->dyn.boundary;
+    feed<<<fgrid, kAgentThreads, 0, st>>>(fa, SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     if (profile) prof_mark(e, 3, st);
 
@@ -719,9 +680,8 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "host_chunk_min_kb") == 0) { DIE_REQUIRE(value >= 0); g_host_chunk_min_bytes = (size_t)value << 10; }
     else if (strcmp(key, "fwd_lean") == 0) g_fwd_lean = value;      // 0 off, 1 on (4 CTAs/SM), 5: 48-register cap
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
-    else if (strcmp(key, "field_impl") == 0) return die_set_field_impl(value);
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
-    else if (strcmp(key, "feed_min_blocks") == 0) { DIE_REQUIRE(value == 1 || value == 4 || value == 5); g_feed_min_blocks = value; }
+    else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;
 }
@@ -1191,10 +1151,14 @@ extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action
     DIE_REQUIRE(e != nullptr && agents != nullptr && action != nullptr && stats != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     if (e->Ml > 0) {
-        agent_feed_kernel<true, false, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(
-            agents, action, nullptr, nullptr, e->cells, e->part_gain, e->part_alive,
-            (int64_t)e->g.slab_cells, e->Ml, e->nblk, e->dyn.cost_w_deposit, e->dyn.cost_w_dist,
-            nullptr, 0, e->dyn.boundary, e->g, slab_tables(e, 0, true));
+        FeedArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.agents = agents; fa.action = action; fa.cells = e->cells;
+        fa.part_gain = e->part_gain; fa.part_alive = e->part_alive;
+        fa.C = (int64_t)e->g.slab_cells; fa.M = e->Ml; fa.nblk = e->nblk;
+        fa.rate_feed = e->dyn.rate_feed; fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
+        fa.boundary = e->dyn.boundary;
+        agent_feed_kernel<true, false, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(fa, e->g, slab_tables(e, 0, true));
         DIE_CUDA(cudaGetLastError());
         finalize_stats_kernel<<<1, kFinalThreads, 0, st>>>(e->part_gain, e->part_alive, e->nblk, e->reward_dev, e->alive_dev);
     } else {

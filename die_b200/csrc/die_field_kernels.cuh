@@ -4,9 +4,11 @@
 //   food consumption      food -= rate_feed * food * (occ > 0)         core/env.py:224-228
 //   food flow             identity                                     core/env.py:147-150
 //   diffusion * decay     gaussian(chem, sigma, 'wrap') * (1-d)        core/env.py:136-145
-// reading medium_in (never written) and the claim table, writing medium_out and the per-cell
-// consumed_field (rate_feed * food * occ, core/env.py:224) that the agent feed kernel gathers.
-// Algorithmic traffic: chem R+W, food R+W, occupancy W (+ claim table 4 B R, consumed 8 B W).
+// reading medium_in (never written) and the claim table, writing medium_out and one occupancy BIT per
+// cell (occ_bits): the agent feed kernel forms consumed_field = rate_feed * food * occ (core/env.py:224)
+// for a slot's cell from medium_in's food and that bit, so the 8 B/cell consumed_field scratch of round 1
+// is gone (the slab instantiation, whose feed kernel gathers across GPUs, still writes it).
+// Algorithmic traffic: chem R+W, food R+W, occupancy W (+ claim table 4 B R, 1 bit W).
 //
 // The deposit is applied while the halo tile is staged: every staged cell reads its claim
 // (the winning slot, or -1) and, when claimed, gathers that slot's deposit1 -- so the previous
@@ -31,7 +33,10 @@ struct FieldArgs {
     double* medium_out;
     const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
     const double* action;        // [B][3][M]; channel 2 = deposit1
-    double* consumed;            // [B][H*W] consumed_field out
+    double* consumed;            // [B][H*W] consumed_field out (SLAB instantiation only; null otherwise)
+    uint32_t* occ_bits;          // [B][Cw] bit (g & 31) of word (g >> 5) = (claim[g] >= 0); written by the tile kernel when
+                                 // W % 32 == 0 (a warp's 32 output cells are then one aligned word), else by occ_bits_kernel
+    int64_t Cw;                  // words per environment = ceil(H*W / 32)
     double2* grad;               // [B][H*W] np.gradient(chem_out) (raw d/dx, d/dy) or null
     float2* grad32;              // the same pairs rounded to float32 (tuning "grad_f32"): what the guard-banded quick turn
                                  // decision reads anyway (die_turn.h); at most one of grad / grad32 is set
@@ -41,7 +46,7 @@ struct FieldArgs {
     double rate_feed;
     double keep;                 // 1. - rate_decay_chem
     int food_infinite;
-    int diffuse_mode;            // DIE_DIFFUSE_* (tile kernel; the march and slab kernels are wrap only)
+    int diffuse_mode;            // DIE_DIFFUSE_* (the slab instantiation is wrap only)
     int prefetch_food;           // tile kernel: L2 prefetch of the output tile's food lines (tuning switch)
     // op_food_flow = WaveSequence(...).get_flow_operator(scale, decay), core/data_init.py:29-38, 71-89 (null = identity)
     const double* flow_rwave;    // [H*W]  r + cos(pi x) + sin(0.4 pi y): the time-independent part of the wave phase
@@ -146,7 +151,11 @@ field_step_kernel(const FieldArgs a) {
     double* chem_out = mout_l + 2 * C;
     const int32_t* win = SLAB ? a.st.claim[a.sg.rank] : a.winner + b * C;
     const double* dep = SLAB ? nullptr : a.action + (b * 3 + 2) * a.M;
-    double* cons = SLAB ? a.st.consumed[a.sg.rank] : a.consumed + b * C;
+    double* cons = SLAB ? a.st.consumed[a.sg.rank] : nullptr;
+    // one occupancy bit per output cell for the feed kernel: lanes 0..31 of a warp hold 32 consecutive cells of one
+    // row starting at a multiple of 32 columns, i.e. exactly one word when W % 32 == 0 (checked by the launcher)
+    static_assert((TH * TW) % NT == 0 && TW % 32 == 0 && NT % 32 == 0, "the occupancy ballot needs whole warps per row piece");
+    uint32_t* obits = (!SLAB && a.occ_bits != nullptr) ? a.occ_bits + b * a.Cw : nullptr;
 
     // food of the output tile is only needed by the last phase: pull its lines towards L2 now, so that
     // those loads do not start a fresh DRAM round trip after the blur (one 128-byte line per thread)
@@ -217,19 +226,26 @@ field_step_kernel(const FieldArgs a) {
         for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
             const int r = idx / TW, c = idx - r * TW;
             const int li = i0 + r, gj = j0 + c;
-            if (li < HL && gj < W) {
+            const int g = li * W + gj;
+            const bool inside = li < HL && gj < W;
+            bool occupied = false;
+            if (inside) {
                 const double* p = s_v + r * LW + c + R;
                 double acc = p[0] * a.bw.w[R];
 #pragma unroll
                 for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
-                const int g = li * W + gj;
                 chem_out[g] = acc * a.keep;
-                const double occ = (win[g] >= 0) ? 1.0 : 0.0;
+                occupied = win[g] >= 0;
+                const double occ = occupied ? 1.0 : 0.0;
                 const double f = food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
                 food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
                 occ_out[g] = occ;
-                cons[g] = cf;
+                if (SLAB) cons[g] = cf;
+            }
+            if (!SLAB && obits != nullptr) {                    // (uniform branch: every lane votes)
+                const uint32_t word = __ballot_sync(0xffffffffu, occupied);
+                if ((threadIdx.x & 31) == 0 && inside) obits[g >> 5] = word;
             }
         }
     } else {
@@ -251,9 +267,11 @@ field_step_kernel(const FieldArgs a) {
         const int r = idx / TW, c = idx - r * TW;
         const int li = i0 + r, gj = j0 + c;
         const int gi = row0 + li;            // global row: np.gradient is one-sided on the GLOBAL border only
-        if (li < HL && gj < W) {
+        const int g = li * W + gj;
+        const bool inside = li < HL && gj < W;
+        bool occupied = false;
+        if (inside) {
             const double* q = s_out + (r + 1) * OW + (c + 1);
-            const int g = li * W + gj;
             chem_out[g] = q[0];
             // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
             const int um = (gi > 0) ? -OW : 0, up = (gi < H - 1) ? OW : 0;
@@ -265,167 +283,32 @@ field_step_kernel(const FieldArgs a) {
             if (grad32 != nullptr) grad32[g] = make_float2((float)gx, (float)gy);
             else grad[g] = make_double2(gx, gy);
 
-            const double occ = (win[g] >= 0) ? 1.0 : 0.0;
+            occupied = win[g] >= 0;
+            const double occ = occupied ? 1.0 : 0.0;
             const double f = food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
             food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
             occ_out[g] = occ;
-            cons[g] = cf;
+            if (SLAB) cons[g] = cf;
+        }
+        if (!SLAB && obits != nullptr) {                        // (uniform branch: every lane votes)
+            const uint32_t word = __ballot_sync(0xffffffffu, occupied);
+            if ((threadIdx.x & 31) == 0 && inside) obits[g >> 5] = word;
         }
     }
     }   // GRAD
 }
 
-// ---------------------------------------------------------------------------------------------
-// Register-tiled version for small radii (R <= 3): no shared memory, no block barriers.
-// Each WARP owns a strip of 32 staged columns (OWV = 24 or 28 of them are outputs) and marches down
-// RB output rows: every lane keeps the 2R+1 most recent input values of its column in registers
-// (axis-0 pass), takes the axis-1 neighbours from the adjacent lanes with warp shuffles, and (GRAD)
-// keeps the last three blurred rows to form np.gradient of the new field.  Loads run a few rows
-// ahead of the arithmetic in a 4-slot register ring: (A) chem + claim of input row t+4, (B) the
-// deposit gather of the claimed cells of row t+2, (C) consume row t; the food / claim of the output
-// row are prefetched three rows ahead the same way.  Operation order is identical to the tile
-// version, so results are bit-identical.
-// ---------------------------------------------------------------------------------------------
-struct MarchGeom {
-    int strips;      // ceil(W / OWV)
-    int rblocks;     // ceil(H / RB)
-    int B;
-};
-
-template <int R, bool GRAD, int RB>
-__global__ void __launch_bounds__(256, 3)
-field_march_kernel(const FieldArgs a, const MarchGeom geo) {
-    constexpr int G = GRAD ? 1 : 0;
-    constexpr int HALO = R + G;
-    constexpr int OWV = (32 - 2 * HALO) & ~3;          // outputs per warp row: 32-byte aligned stores
-    constexpr int T = RB + 2 * HALO;                   // input rows consumed per block
-    constexpr int LAG = 2 * R + 2 * G;                 // output row of iteration t = i0 + t - LAG
-    constexpr int CL = HALO;                           // claim of the output row was loaded CL rows ago
-    constexpr unsigned FULL = 0xffffffffu;
-
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int per_env = geo.strips * geo.rblocks;
-    const int64_t b = warp / per_env;
-    if (b >= geo.B) return;                            // whole warp exits together
-    const int rem = (int)(warp - b * per_env);
-    const int rb = rem / geo.strips, strip = rem - rb * geo.strips;
-    const int H = a.H, W = a.W;
-    const int64_t C = (int64_t)H * W;
-    const int i0 = rb * RB, j0 = strip * OWV;
-    const int oc = j0 - HALO + lane;                   // my column, unwrapped
-    const int gj = wrap_index(oc, W);
-    const bool col_out = lane >= HALO && lane < HALO + OWV && oc < W;
-    const int rows_here = min(RB, H - i0);             // output rows of this block
-    // np.gradient is one-sided on the global border: only the first / last strip and row can touch it
-    const bool left_edge = oc == 0, right_edge = oc == W - 1;
-
-    const double* min_b = a.medium_in + b * 3 * C;     // channels at +0 (occ), +C (food), +2C (chem)
-    double* mout_b = a.medium_out + b * 3 * C;
-    const int32_t* win = a.winner + b * C;
-    const double* dep = a.action + (b * 3 + 2) * a.M;
-    double* cons = a.consumed + b * C;
-    double2* grad = (GRAD && a.grad != nullptr) ? a.grad + b * C : nullptr;
-    float2* grad32 = (GRAD && a.grad32 != nullptr) ? a.grad32 + b * C : nullptr;
-
-    double wk[R + 1];                                  // wk[k] = weight of taps at distance k
-#pragma unroll
-    for (int k = 0; k <= R; ++k) wk[k] = a.bw.w[R - k];
-
-    // register rings (indices are compile-time after unrolling)
-    double px[4], pd[4], fo[4];
-    int pw[4];
-    int claim_line[CL + 1];                            // claims of the last CL+1 consumed rows
-#pragma unroll
-    for (int k = 0; k <= CL; ++k) claim_line[k] = -1;
-    int gi_a = wrap_index(i0 - HALO, H);               // next input row to fetch (stage A)
-
-    auto stage_a = [&](int slot) {
-        const int g = gi_a * W + gj;
-        px[slot] = min_b[2 * C + g];
-        pw[slot] = win[g];
-        gi_a = (gi_a + 1 == H) ? 0 : gi_a + 1;
-    };
-    auto stage_b = [&](int slot) { pd[slot] = (pw[slot] >= 0) ? dep[pw[slot]] : 0.0; };
-    auto prefetch_food = [&](int slot, int rel) {      // rel = output row relative to i0
-        const bool ok = col_out && rel >= 0 && rel < rows_here;
-        fo[slot] = ok ? min_b[C + (i0 + rel) * W + oc] : 0.0;
-    };
-
-    double win_v[2 * R + 1];                            // vertical window, win_v[2R] = newest
-#pragma unroll
-    for (int k = 0; k < 2 * R + 1; ++k) win_v[k] = 0.0;
-    double bp = 0.0, bc = 0.0, bn = 0.0;
-
-    // prologue
-#pragma unroll
-    for (int s = 0; s < 4; ++s) stage_a(s);
-    stage_b(0);
-    stage_b(1);
-#pragma unroll
-    for (int s = 0; s < 3; ++s) prefetch_food(s, s - LAG);
-
-    int rel = -LAG;                                     // output row of iteration t, relative to i0
-    for (int t0 = 0; t0 < T; t0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            // (C) consume input row t
-            const int cw = pw[u];
-            const double x = (cw >= 0) ? px[u] + pd[u] : px[u];
-#pragma unroll
-            for (int k = 0; k < 2 * R; ++k) win_v[k] = win_v[k + 1];
-            win_v[2 * R] = x;
-#pragma unroll
-            for (int k = 0; k < CL; ++k) claim_line[k] = claim_line[k + 1];
-            claim_line[CL] = cw;
-            stage_a(u);                                 // (A) row t+4 into the slot just freed
-            stage_b((u + 2) & 3);                       // (B) deposits of row t+2
-
-            // axis-0 pass for the row at the window centre, then axis-1 via shuffles
-            double v = win_v[R] * wk[0];
-#pragma unroll
-            for (int k = R; k >= 1; --k) v += (win_v[R - k] + win_v[R + k]) * wk[k];
-            double h = v * wk[0];
-#pragma unroll
-            for (int k = R; k >= 1; --k) {
-                const double lft = __shfl_sync(FULL, v, (lane - k) & 31);
-                const double rgt = __shfl_sync(FULL, v, (lane + k) & 31);
-                h += (lft + rgt) * wk[k];
-            }
-            bp = bc;
-            bc = bn;
-            bn = h * a.keep;                            // blurred row i0 + t - 2R - G
-
-            // output row i0 + rel
-            const double centre = GRAD ? bc : bn;
-            double gx = 0.0, gy = 0.0;
-            if (GRAD) {
-                const double lft = __shfl_sync(FULL, bc, (lane - 1) & 31);
-                const double rgt = __shfl_sync(FULL, bc, (lane + 1) & 31);
-                const int ro = i0 + rel;
-                if (ro > 0 && ro < H - 1) gx = (bn - bp) * 0.5;               // warp-uniform branch
-                else gx = (ro < H - 1 ? bn : bc) - (ro > 0 ? bp : bc);
-                gy = (right_edge ? bc : rgt) - (left_edge ? bc : lft);
-                if (!(left_edge || right_edge)) gy *= 0.5;
-            }
-            if (col_out && rel >= 0 && rel < rows_here) {
-                const int g = (i0 + rel) * W + oc;
-                mout_b[2 * C + g] = centre;
-                if (GRAD) {
-                    if (grad32 != nullptr) grad32[g] = make_float2((float)gx, (float)gy);
-                    else grad[g] = make_double2(gx, gy);
-                }
-                const double occ = (claim_line[0] >= 0) ? 1.0 : 0.0;    // claim of row t - CL = output row
-                const double f = fo[u];
-                const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                mout_b[C + g] = next_food(a, f, cf, i0 + rel, oc, g);
-                mout_b[g] = occ;
-                cons[g] = cf;
-            }
-            prefetch_food((u + 3) & 3, rel + 3);        // food of the row output at t+3
-            ++rel;
-        }
+// The occupancy bits of fields whose rows are not a multiple of 32 cells (the tile kernel's warps then straddle
+// words), and of the no-diffusion pass: one ballot per 32 consecutive cells of the claim table.
+__global__ void __launch_bounds__(256)
+occ_bits_kernel(const int32_t* __restrict__ winner, uint32_t* __restrict__ bits, int64_t C, int64_t Cw, int B) {
+    const int64_t total = (int64_t)B * Cw * 32;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int64_t b = t / (Cw * 32), g = t - b * (Cw * 32);
+        const bool occupied = g < C && winner[b * C + g] >= 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, occupied);
+        if ((threadIdx.x & 31) == 0) bits[b * Cw + (g >> 5)] = word;
     }
 }
 
@@ -555,7 +438,6 @@ field_step_noblur_kernel(const FieldArgs a, int64_t total) {
         mout[g] = occ;
         mout[C + g] = next_food(a, f, cf, (int)(g / a.W), (int)(g % a.W), g);
         mout[2 * C + g] = (chem * a.bw.w[0]) * a.bw.w[0] * a.keep;
-        a.consumed[gid] = cf;
     }
 }
 

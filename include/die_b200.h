@@ -277,11 +277,10 @@ int die_set_turn_quick(int32_t on);
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
  * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
- * alive-ness from the bitmask), "field_prefetch" 0/1, "field_impl" 0/1/2 (tile / register-march / persistent bulk-async tiles, the last one staged and untimed), "grad_f32" 0/1 (see die_env_gradient_kind),
- * "feed_min_blocks" 1/4/5 (register cap of the feed kernel; 1 = the compiler's choice). */
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "step_impl" 0/1 (see die_set_step_impl), "grad_f32" 0/1 (see die_env_gradient_kind). */
 int die_set_tuning(const char* key, int32_t value);
 /* How often a kernel variant has been launched by this process (diagnostics for tests: "the variant I selected is the
- * one that ran"): "field_tile", "field_march", "field_bulk", "forward_lean", "forward_lean_f32", "forward_general";
+ * one that ran"): "field_tile", "step_fused", "forward_lean", "forward_lean_f32", "forward_general";
  * -1 for an unknown key. */
 int64_t die_get_counter(const char* key);
 
@@ -331,12 +330,11 @@ const int32_t* die_slab_cells(const die_slab_t* slab);    /* int32 [Ml] GLOBAL l
 int die_slab_set_corner_mirror(die_slab_t* slab, int32_t r);
 int die_slab_corner_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, void* stream);
 
-/* Field-pass implementation switch (tests / A-B timing): 0 = shared-memory tile kernel (default),
- * 1 = register-tiled warp-marching kernel (blur radius <= 3; measured slower on B200 so far: 0.29 vs
- * 0.25 ms at 4096^2), 2 = persistent kernel whose halo tiles arrive by cp.async.bulk + mbarrier into a
- * two-stage ring (blur radius <= 4, periodic diffusion, W % 4 == 0 and W >= one staged row, else the tile
- * kernel runs; staged, not yet timed).  All give bit-identical results. */
-int die_set_field_impl(int32_t impl);
+/* Env.step implementation switch (tests / A-B timing): 1 (default) = the cluster-fused environment step wherever it
+ * applies (small periodic environments: one thread-block cluster per environment, claim table in distributed shared
+ * memory, field rows by TMA bulk copies; die_b200/csrc/die_env_fused.cuh), 0 = always the three kernels
+ * move_claim / field_step / agent_feed.  Both give bit-identical results. */
+int die_set_step_impl(int32_t impl);
 
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
  * to device arrays, so tests can check the device results equal the host build of the same

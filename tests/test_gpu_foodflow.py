@@ -16,7 +16,7 @@ def _run(field, steps, math, scale, decay, dyn_extra=None, impl=0, sigma=0.5):
     lib = _lib.load()
     dyn_extra = dyn_extra or {}
     R.set_math_backend(math)
-    lib.die_set_field_impl(impl)
+    lib.die_set_step_impl(impl)
     try:
         rflow = R.WaveSequence(field, dt=0.01).get_flow_operator(scale=scale, decay=decay)
         gflow = D.WaveSequence(field, dt=0.01).get_flow_operator(scale=scale, decay=decay)
@@ -47,7 +47,7 @@ def _run(field, steps, math, scale, decay, dyn_extra=None, impl=0, sigma=0.5):
         return worst
     finally:
         R.set_math_backend('numpy')
-        lib.die_set_field_impl(0)
+        lib.die_set_step_impl(0)
 
 
 @pytest.mark.parametrize("field,impl,sigma", [((48, 64), 0, 0.5), ((37, 53), 0, 0.5), ((64, 40), 1, 0.5),

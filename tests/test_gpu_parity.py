@@ -315,7 +315,7 @@ def test_field_kernels_agree_bit_for_bit(shape, sigma):
     lib = _lib.load()
     results = []
     for impl in (0, 1):
-        lib.die_set_field_impl(impl)
+        lib.die_set_step_impl(impl)
         try:
             (_,), env = make_pair(shape, seed=21, dynamics_kw=dict(diffuse_sigma=sigma))
             m = env.max_agents
@@ -332,7 +332,7 @@ def test_field_kernels_agree_bit_for_bit(shape, sigma):
             med, agn = env.get_state()
             results.append((med, agn, np.array(acts), r, ag.last_hints))
         finally:
-            lib.die_set_field_impl(0)
+            lib.die_set_step_impl(0)
     (m0, a0, c0, r0, h0), (m1, a1, c1, r1, h1) = results
     assert np.array_equal(m0, m1) and np.array_equal(a0, a1) and np.array_equal(c0, c1) and r0 == r1
     assert h0 == h1 == (True, True)

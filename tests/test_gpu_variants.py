@@ -1,15 +1,14 @@
-"""Variants written at the end of round 1 after the round's GPU budget was (almost) spent: compiled for sm_100a and
-verified bit-exact on the CPU emulator first (tests/test_hostsim_kernels.py), then -- with the last 100 GPU seconds --
-run on a B200: all of them passed (profiles/r01s3_staged_tests_gpu.txt), so they are ordinary tests now.  The file stays
-last in the suite because of its final test.
+"""Variants staged at the end of round 1 without GPU budget, run on a B200 in the first GPU call of round 2
+(profiles/r02a_staged_ab_summary.txt): everything here passed there and is an ordinary test now.
 
-  grad_f32          the field pass publishes np.gradient(chem1) as float32 pairs for decision-only consumers (adopted as
-                    the default: DESIGN.md 3.10); the A-B here is float64 vs float32 pairs
-  feed_min_blocks   register caps of the feed kernel (64 / 48 registers: 4 / 5 resident CTAs per SM instead of 3)
+  grad_f32          the field pass publishes np.gradient(chem1) as float32 pairs for decision-only consumers (the
+                    default: DESIGN.md 3.10); the A-B here is float64 vs float32 pairs
   unnormalised      the signed zeros of PhysarumAgent(normalized_grad=False) on a zero gradient
-  field_impl = 2    persistent field pass, halo tiles by cp.async.bulk + mbarrier into a two-stage ring
-                    (die_field_bulk.cuh): NOT yet run on hardware; its test runs only with DIE_B200_STAGED_BULK=1 and
-                    is a non-strict xfail until it has
+  tabulated flow    Dynamics.op_food_flow of any FieldSequence through tabulated frames
+  simple_agents     examples/simple_agents.py (the reference's four hand-written policies on its two dynamics)
+Removed after that call, on the numbers: the feed kernel's register caps (10-20 % slower) and the persistent
+cp.async.bulk field pass of round 1 (correct on hardware, 2.3x slower than the tile kernel: one small bulk copy per tile
+row); the TMA path of round 2 is the cluster-fused environment step (die_env_fused.cuh, tests/test_gpu_fused_step.py).
 """
 import os
 
@@ -61,13 +60,6 @@ def test_float32_gradient_cache_does_not_change_results(adversarial):
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(base[:3], out[:3])) and base[3] == out[3]
 
 
-@pytest.mark.parametrize("cap", [4, 5])
-def test_feed_register_caps_do_not_change_results(cap):
-    base, _ = _run("feed_min_blocks", 1)
-    out, _ = _run("feed_min_blocks", cap)
-    assert all(np.array_equal(a, b) for a, b in zip(base[:3], out[:3])) and base[3] == out[3]
-
-
 def test_unnormalised_physarum_keeps_the_momentum_operands():
     """Found on the CPU emulator: with normalized_grad=False a zero gradient gives g' = (0 * cos d, 0 * sin d), signed
     zeros, and the reference's identity momentum step 1.0 * g' + 0.0 * prev + 0.0 * noise turns (-0.0) + (+0.0) into
@@ -91,7 +83,6 @@ def test_unnormalised_physarum_keeps_the_momentum_operands():
     assert np.array_equal(gact, ract)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: emulator-verified, not yet run on a GPU")
 @pytest.mark.parametrize("field,sigma,batch", [((48, 64), 0.5, None), ((37, 53), 0.8, 3)])
 def test_tabulated_food_flow(field, sigma, batch):
     """Dynamics.op_food_flow of any FieldSequence through its tabulated frames (die_env_set_food_frames): bit-exact
@@ -126,7 +117,6 @@ def test_tabulated_food_flow(field, sigma, batch):
     assert gflow.calls == 10
 
 
-@pytest.mark.xfail(strict=False, reason="example written after the round's GPU budget was spent: not yet run on a GPU")
 @pytest.mark.parametrize("argv", [["--agent", "const"], ["--agent", "rand"], ["--agent", "grad", "--dynamics", "dyn-pred"],
                                   ["--agent", "physarum", "--dynamics", "dyn-pred", "--frames-every", "10"]])
 def test_simple_agents_example(argv):
@@ -138,34 +128,3 @@ def test_simple_agents_example(argv):
                           "--iters", "30", *argv], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ms per iteration" in out.stdout and "frames:" in out.stdout
-
-
-@pytest.mark.xfail(strict=False, reason="staged in round 1 without GPU budget; CPU-emulator verified only")
-@pytest.mark.skipif(os.environ.get("DIE_B200_STAGED_BULK") != "1",
-                    reason="first run of an mbarrier / cp.async.bulk kernel on hardware: only on request "
-                           "(DIE_B200_STAGED_BULK=1, under `timeout`), never in the default suite")
-@pytest.mark.parametrize("shape,sigma,batch", [((256, 256), 0.5, 6), ((40, 72), 0.5, None), ((70, 200), 0.8, None),
-                                               ((128, 96), 0.5, 700)])
-def test_bulk_field_kernel_does_not_change_results(shape, sigma, batch):
-    """field_impl = 2 (die_field_bulk.cuh): the persistent, bulk-async double-buffered field pass.  A protocol error
-    traps after two seconds instead of hanging (die_async.cuh), but a trap poisons the CUDA context: this test is
-    last in the last file."""
-    import die_b200 as D
-    from die_b200 import _lib
-    lib = _lib.load()
-    outs = []
-    n0 = lib.die_get_counter(b"field_bulk")
-    try:
-        for impl in (0, 2):
-            _lib.check(lib.die_set_tuning(b"field_impl", impl))
-            _, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch and min(batch, 700))
-            m = env.max_agents
-            ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
-            obs = env._get_current_obs
-            for _ in range(12):
-                obs, r, *_ = env.step(ag.forward(obs))
-            outs.append((*env.get_state(), ag.get_state()[0]))
-    finally:
-        _lib.check(lib.die_set_tuning(b"field_impl", 0))
-    assert lib.die_get_counter(b"field_bulk") == n0 + 12, "the bulk kernel must be the one that ran"
-    assert all(np.array_equal(a, b) for a, b in zip(*outs))

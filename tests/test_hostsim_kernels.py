@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, field_impl=0, grad_f32=1, feed_min_blocks=1)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -164,17 +164,14 @@ def test_physarum_limit_boundary_sigma08_infinite_food_zero_cost(portable_math):
                                             op_action_cost=R.zero_cost))
 
 
-@pytest.mark.parametrize("impl,lean", [(0, 1), (1, 1), (0, 0)])
-def test_physarum_free_run_float32_gradient_cache(portable_math, tuning, impl, lean):
-    """grad_f32: the field pass (tile or march kernel) publishes np.gradient(chem1) as float32 pairs; the quick turn
+@pytest.mark.parametrize("lean", [1, 0])
+def test_physarum_free_run_float32_gradient_cache(portable_math, tuning, lean):
+    """grad_f32: the field pass publishes np.gradient(chem1) as float32 pairs; the quick turn
     decision reads those, deferred slots re-sample chem1 in float64.  Against the oracle, and with the structured
     fields of a long run where gradients underflow float32 / sit on the clip threshold."""
     tuning("grad_f32", 1)
-    tuning("field_impl", impl)
     tuning("fwd_lean", lean)
-    march0 = S.lib().die_get_counter(b"field_march")
     env, ga, flags = _physarum_free_run((48, 80), 30, PHYS)
-    assert (S.lib().die_get_counter(b"field_march") - march0 == 30) == (impl == 1)
     assert S.lib().die_env_gradient_kind(env.handle) == 2 and not S.lib().die_env_gradient(env.handle)
     assert L.FWD_USE_GRADIENT | L.FWD_USE_CELLS in flags
     # GradientAgent needs the gradient's value: the float32 cache must be ignored, results still exact
@@ -211,8 +208,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_impl", [1]), ("field_prefetch", [0]),
-                                        ("grad_f32", [0]), ("feed_min_blocks", [4, 5])])
+                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
@@ -224,75 +220,6 @@ def test_tuning_switches_do_not_change_results(tuning, key, values):
         out = _philox_run((40, 72), 12)
         for a, b, what in zip(base, out, ("medium", "agents", "theta", "reward")):
             assert np.array_equal(a, b), f"{key}={v}: {what} differs"
-
-
-@pytest.mark.parametrize("sigma", [0.3, 0.5, 0.8])
-def test_march_field_kernel_equals_tile_kernel(tuning, sigma):
-    """field_impl = 1: the register-tiled warp-marching kernel (radii 1..3), ragged widths included."""
-    outs = []
-    for impl in (0, 1):
-        tuning("field_impl", impl)
-        (ref,), env = make_pair((67, 45), seed=13, dynamics_kw=dict(diffuse_sigma=sigma))
-        ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
-        ga.theta[0] = lattice_theta(env.M, 30, 13)[0]
-        for it in range(6):
-            env.step(ga.forward(env))
-        outs.append((env.medium.copy(), env.agents.copy(), env.gradient()))
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
-
-
-@pytest.mark.parametrize("shape,sigma,batch", [((64, 128), 0.5, None), ((40, 72), 0.5, None), ((6, 76), 0.5, None),
-                                               ((70, 200), 0.8, None), ((33, 132), 0.3, 3), ((48, 96), 1.0, 2),
-                                               ((96, 80), 0.5, 5)])
-@pytest.mark.parametrize("grad", [True, False])
-def test_bulk_field_kernel_equals_tile_kernel(tuning, shape, sigma, batch, grad):
-    """field_impl = 2: the persistent kernel whose halo tiles arrive by cp.async.bulk + mbarrier into a two-stage ring
-    (die_field_bulk.cuh).  Under the emulator the copies are deferred and their destination poisoned until somebody
-    waits, byte counts and alignment are checked.  Widths that wrap inside a staged row, fields lower than a tile,
-    radii 1..4, batches (several tiles per persistent CTA), with (Physarum) and without (Brownian) the gradient cache,
-    float64 and float32 gradient."""
-    outs = []
-    bulk0 = S.lib().die_get_counter(b"field_bulk")
-    for impl, f32 in ((0, 0), (2, 0), (2, 1)):
-        tuning("field_impl", impl)
-        tuning("grad_f32", f32)
-        refs, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch)
-        B = env.B
-        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
-        for b in range(B):
-            ga.theta[b] = lattice_theta(env.M, 30, 13 + b)[0]
-        for it in range(5):
-            if grad:
-                act = ga.forward(env)
-            else:
-                act = S.brownian_forward(env.agents, move_scale=0.02, seed=4, step=it)
-            env.step(act)
-        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.reward.copy(),
-                     None if f32 else env.gradient()))
-    assert S.lib().die_get_counter(b"field_bulk") == bulk0 + 10, "the bulk kernel must be the one that ran"
-    for k in (1, 2):
-        for a, b, what in zip(outs[0], outs[k], ("medium", "agents", "theta", "reward", "gradient")):
-            if a is None or b is None:
-                continue
-            assert np.array_equal(a, b), f"variant {k}: {what} differs"
-
-
-def test_bulk_field_kernel_falls_back_where_it_does_not_apply(tuning):
-    """Widths that are not a multiple of 4 (claim rows would not be 16-byte aligned), narrower than a staged row, or a
-    non-periodic diffuse_mode: field_impl = 2 silently runs the tile kernel."""
-    bulk0 = S.lib().die_get_counter(b"field_bulk")
-    for shape, kw in (((40, 70), {}), ((40, 64), {}), ((40, 80), dict(diffuse_mode='reflect'))):
-        outs = []
-        for impl in (0, 2):
-            tuning("field_impl", impl)
-            refs, env = make_pair(shape, seed=3, dynamics_kw=kw)
-            ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
-            for it in range(3):
-                env.step(ga.forward(env))
-            outs.append(env.medium.copy())
-        assert np.array_equal(*outs)
-    assert S.lib().die_get_counter(b"field_bulk") == bulk0
 
 
 def test_batched_envs_match_single_envs():
@@ -652,9 +579,8 @@ def test_physarum_golden_every_step(name):
         assert alive[0] == g["num_agents"][k]
 
 
-@pytest.mark.parametrize("field,impl,sigma", [((24, 40), 0, 0.5), ((37, 53), 1, 0.5), ((20, 20), 0, 0.1)])
-def test_wave_flow_bit_exact_with_portable_math(portable_math, tuning, field, impl, sigma):
-    tuning("field_impl", impl)
+@pytest.mark.parametrize("field,sigma", [((24, 40), 0.5), ((37, 53), 0.5), ((20, 20), 0.1), ((24, 64), 0.5)])
+def test_wave_flow_bit_exact_with_portable_math(portable_math, tuning, field, sigma):
     rflow = R.WaveSequence(field, dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
     gflow = D.WaveSequence(field, dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
     (ref,), env = make_pair(field, seed=5, dynamics_kw=dict(diffuse_sigma=sigma),
@@ -887,7 +813,7 @@ def _random_case(seed):
     agent = dict(scale=float(rng.choice([0.007, 0.03, 0.2, 1.7])), sense_offset=float(rng.choice([0.0, 0.04, 0.3, 1.5])),
                  turn_angle=float(rng.choice([30, 35, 45, 90])), sense_angle=float(rng.choice([60, 90, 120, 170])),
                  turn_tolerance=float(rng.choice([0.05, 0.1, 0.3])), deposit=float(rng.choice([4.0, 0.5])))
-    tune = dict(field_impl=int(rng.choice([0, 0, 1, 2])), grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
+    tune = dict(grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
                 feed_bits=int(rng.random() < 0.7))
     return (h, w), float(rng.choice([0.05, 0.1, 0.5, 1.0])), dyn, rdyn, agent, tune, bool(rng.random() < 0.5)
 
@@ -931,8 +857,8 @@ def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
     C = h * w
     m = int(rng.choice([max(C // 3, 1), C, C, 2 * C + 7]))
     sigma = float(rng.choice([0.3, 0.5, 0.8]))
-    for k, v in dict(field_impl=int(rng.choice([0, 1, 2])), grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
-                     feed_bits=int(rng.random() < 0.7), feed_min_blocks=int(rng.choice([1, 4, 5]))).items():
+    for k, v in dict(grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
+                     feed_bits=int(rng.random() < 0.7)).items():
         tuning(k, v)
     refs, mediums, agentss = [], [], []
     for b in range(B):
@@ -973,13 +899,12 @@ def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
             assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
 
 
-@pytest.mark.parametrize("field,impl,sigma,batch", [((24, 40), 0, 0.5, None), ((37, 53), 1, 0.5, None), ((20, 20), 0, 0.1, None),
-                                                    ((40, 72), 2, 0.5, 3), ((33, 70), 0, 0.8, 2)])
-def test_tabulated_food_flow(tuning, field, impl, sigma, batch):
+@pytest.mark.parametrize("field,sigma,batch", [((24, 40), 0.5, None), ((37, 53), 0.5, None), ((20, 20), 0.1, None),
+                                               ((40, 64), 0.5, 3), ((33, 70), 0.8, 2)])
+def test_tabulated_food_flow(tuning, field, sigma, batch):
     """op_food_flow of ANY FieldSequence (the reference's PerlinNoiseSequence, a user's own): the host tabulates
     sequence[t] for every time step, the field pass reads one value per cell: scale * F_k + (1 - decay) * food, k cycling
     (die_env_set_food_frames).  T = 4 frames over 10 steps: the iterator wraps twice; a batch shares the sequence."""
-    tuning("field_impl", impl)
     rng = np.random.default_rng(9)
     frames = rng.normal(0.0, 0.3, size=(4, *field)).round(3)
     gflow = D.TabulatedSequence(frames).get_flow_operator(scale=0.5, decay=0.25)

@@ -35,12 +35,12 @@ for mode, flow, mask in (("wrap", False, False), ("constant", True, True), ("ref
         hobs, *_ = big.step(ag.forward(hobs))
     _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
     _lib.check(lib.die_set_tuning(b"host_chunks", 4))
-lib.die_set_field_impl(1)
+lib.die_set_step_impl(1)
 env = D.Env((64, 40), D.Dynamics(), init='device', seed=3)
 ag = D.PhysarumAgent(max_agents=env.max_agents, scale=0.02, sense_offset=0.06)
 obs = env._get_current_obs
 for _ in range(4):
     obs, *_ = env.step(ag.forward(obs))
-lib.die_set_field_impl(0)
+lib.die_set_step_impl(0)
 torch.cuda.synchronize()
 print("sanitize tour done")
