@@ -410,14 +410,10 @@ move_claim_kernel(double* __restrict__ agents, const double* __restrict__ action
 
 // ---------------------------------------------------------------------------------------------
 // Env._agent_feed per-slot part (core/env.py:220-234, cost :29-35) + the reward / num_agents
-// reduction (:118-121).  consumed[M] = consumed_field[cell(slot)] for ALL M slots (Q1, Q7) with
-// consumed_field = rate_feed * food * occ (:224): the food is medium_in's (the buffer the field pass
-// read and never writes), occ the cell's bit in the occupancy bitmap the field pass wrote -- the same
-// two factors, multiplied in the same order, as the field pass used for food -= consumed_field.
-// (The slab instantiation gathers the per-cell consumed_field its field pass still writes: the cell may
-// live on another GPU.)  Alive slots also clear their cell's claim for the next step.  Block partials are
-// written in a fixed layout and summed in a fixed order by finalize_stats_kernel, so the reward is
-// run-to-run deterministic.
+// reduction (:118-121).  consumed[M] = consumed_field[cell(slot)] for ALL M slots (Q1, Q7), where
+// consumed_field = rate_feed * food * occ was written per cell by the field pass.  Alive slots also
+// clear their cell's claim for the next step.  Block partials are written in a fixed layout and
+// summed in a fixed order by finalize_stats_kernel, so the reward is run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFeedItems = 4;      // slots per thread
 
@@ -430,15 +426,14 @@ constexpr int kFeedItems = 4;      // slots per thread
 struct FeedArgs {
     double* agents;
     const double* action;
-    const double* medium_in;         // [B][3][C]: channel 1 = the food the field pass consumed from
-    const uint32_t* occ_bits;        // [B][Cw]
+    const double* consumed_field;    // [B][C] rate_feed * food * occ of this step (the field pass wrote it)
     int32_t* winner;
     const int32_t* cells;
     double* part_gain;
     int32_t* part_alive;
-    int64_t C, Cw, M;
+    int64_t C, M;
     int nblk;
-    double rate_feed, w_dep, w_dist;
+    double w_dep, w_dist;
     const uint32_t* alive_bits;
     int64_t Mw;
     int boundary;
@@ -452,13 +447,12 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const int64_t b = blockIdx.x / (unsigned)nblk;
     const int blk = blockIdx.x - (int)b * nblk;
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
-    double* ag_x = a.agents + b * 4 * M + first;               // x; y, alive, agent_food are + M, 2M, 3M
-    const double* ac = a.action + b * 3 * M + first;
-    const double* food = SLAB ? nullptr : a.medium_in + (b * 3 + 1) * a.C;
-    const uint32_t* occ = SLAB ? nullptr : a.occ_bits + b * a.Cw;
-    int32_t* win = a.winner + b * a.C;
-    const int32_t* cl = a.cells + b * M + first;
-    const uint32_t* bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
+    double* __restrict__ ag_x = a.agents + b * 4 * M + first;  // x; y, alive, agent_food are + M, 2M, 3M
+    const double* __restrict__ ac = a.action + b * 3 * M + first;
+    const double* __restrict__ cf = SLAB ? nullptr : a.consumed_field + b * a.C;
+    int32_t* __restrict__ win = a.winner + b * a.C;
+    const int32_t* __restrict__ cl = a.cells + b * M + first;
+    const uint32_t* __restrict__ bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
     const double w_dep = a.w_dep, w_dist = a.w_dist;
     const int boundary = a.boundary;
     double* const part_gain = a.part_gain;
@@ -476,14 +470,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        if (SLAB) {
-            eaten[k] = valid[k] ? slab_load_consumed(st, sg, cell[k]) : 0.0;
-        } else {
-            // (rate_feed * food) * occ, occ in {0., 1.}: the field pass's own expression for consumed_field
-            const double f = valid[k] ? food[cell[k]] : 0.0;
-            const uint32_t word = valid[k] ? occ[cell[k] >> 5] : 0u;
-            eaten[k] = (a.rate_feed * f) * (((word >> (cell[k] & 31)) & 1u) ? 1.0 : 0.0);
-        }
+        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : cf[cell[k]]) : 0.0;
         if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
         else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {
@@ -574,35 +561,42 @@ constexpr int kFinalThreads = 1024;
 
 // Sum of an environment's block partials in a fixed order (thread t takes partials t, t + 1024, ... in four
 // interleaved accumulators, then warp shuffles, then the 32 warp sums in index order): run-to-run deterministic.
-__global__ void __launch_bounds__(kFinalThreads)
-finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __restrict__ part_alive,
-                      int nblk, double* __restrict__ reward, int64_t* __restrict__ alive) {
-    const int b = blockIdx.x;
-    const double* pgn = part_gain + (int64_t)b * nblk;
-    const int32_t* pal = part_alive + (int64_t)b * nblk;
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-    long long n = 0;
-    int k = threadIdx.x;
-    for (; k + 3 * kFinalThreads < nblk; k += 4 * kFinalThreads) {
-        const double a0 = pgn[k], a1 = pgn[k + kFinalThreads], a2 = pgn[k + 2 * kFinalThreads], a3 = pgn[k + 3 * kFinalThreads];
-        n += (long long)pal[k] + pal[k + kFinalThreads] + pal[k + 2 * kFinalThreads] + pal[k + 3 * kFinalThreads];
-        g0 += a0;
-        g1 += a1;
-        g2 += a2;
-        g3 += a3;
-    }
-    for (; k < nblk; k += kFinalThreads) {
-        g0 += pgn[k];
-        n += pal[k];
-    }
-    double g = (g0 + g1) + (g2 + g3);
-    __shared__ double s_g[kFinalThreads / 32];
-    __shared__ long long s_n[kFinalThreads / 32];
-    g = warp_sum(g);
-    n = warp_sum(n);
-    if ((threadIdx.x & 31) == 0) {
-        s_g[threadIdx.x >> 5] = g;
-        s_n[threadIdx.x >> 5] = n;
+// NT physical threads execute the 1024 logical ones in passes, so the cluster-fused step (die_env_fused.cuh), whose
+// CTAs are smaller, produces the same bits.  CG: read the partials with ld.global.cg (they were written by other CTAs
+// of the running kernel).  s_g / s_n: 32 entries of shared memory each.
+template <int NT, bool CG>
+__device__ __forceinline__ void finalize_sum(const double* __restrict__ pgn, const int32_t* __restrict__ pal, int nblk,
+                                             double* s_g, long long* s_n, double* reward, int64_t* alive) {
+    static_assert(kFinalThreads % NT == 0 && NT % 32 == 0, "logical threads are emulated in whole passes");
+    for (int pass = 0; pass < kFinalThreads / NT; ++pass) {
+        const int t = pass * NT + threadIdx.x;                 // the logical thread
+        double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+        long long n = 0;
+        int k = t;
+        for (; k + 3 * kFinalThreads < nblk; k += 4 * kFinalThreads) {
+            const double a0 = CG ? __ldcg(pgn + k) : pgn[k];
+            const double a1 = CG ? __ldcg(pgn + k + kFinalThreads) : pgn[k + kFinalThreads];
+            const double a2 = CG ? __ldcg(pgn + k + 2 * kFinalThreads) : pgn[k + 2 * kFinalThreads];
+            const double a3 = CG ? __ldcg(pgn + k + 3 * kFinalThreads) : pgn[k + 3 * kFinalThreads];
+            if (CG) n += (long long)__ldcg(pal + k) + __ldcg(pal + k + kFinalThreads) + __ldcg(pal + k + 2 * kFinalThreads) +
+                         __ldcg(pal + k + 3 * kFinalThreads);
+            else n += (long long)pal[k] + pal[k + kFinalThreads] + pal[k + 2 * kFinalThreads] + pal[k + 3 * kFinalThreads];
+            g0 += a0;
+            g1 += a1;
+            g2 += a2;
+            g3 += a3;
+        }
+        for (; k < nblk; k += kFinalThreads) {
+            g0 += CG ? __ldcg(pgn + k) : pgn[k];
+            n += CG ? __ldcg(pal + k) : pal[k];
+        }
+        double g = (g0 + g1) + (g2 + g3);
+        g = warp_sum(g);
+        n = warp_sum(n);
+        if ((threadIdx.x & 31) == 0) {
+            s_g[t >> 5] = g;
+            s_n[t >> 5] = n;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -612,9 +606,19 @@ finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __res
             gg += s_g[w];
             nn += s_n[w];
         }
-        reward[b] = gg;
-        alive[b] = nn;
+        *reward = gg;
+        *alive = nn;
     }
+}
+
+__global__ void __launch_bounds__(kFinalThreads)
+finalize_stats_kernel(const double* __restrict__ part_gain, const int32_t* __restrict__ part_alive,
+                      int nblk, double* __restrict__ reward, int64_t* __restrict__ alive) {
+    __shared__ double s_g[kFinalThreads / 32];
+    __shared__ long long s_n[kFinalThreads / 32];
+    const int b = blockIdx.x;
+    finalize_sum<kFinalThreads, false>(part_gain + (int64_t)b * nblk, part_alive + (int64_t)b * nblk, nblk, s_g, s_n,
+                                       reward + b, alive + b);
 }
 
 }  // namespace die

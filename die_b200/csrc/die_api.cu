@@ -6,6 +6,7 @@
 
 #include "die_agent_kernels.cuh"
 #include "die_field_kernels.cuh"
+#include "die_env_fused.cuh"
 
 using namespace die;
 
@@ -49,8 +50,7 @@ struct die_env {
     const double* flow_frames; // [T][H*W] tabulated sequence (die_env_set_food_frames); borrowed device memory
     int64_t flow_T, flow_k;
     double flow_scale, flow_keep;
-    uint32_t* occ_bits;    // [B][Cw]   one bit per cell: occupied in the current step (written by the field pass, read
-    int64_t Cw;            //           by the feed kernel, which forms consumed_field = rate_feed * food * occ from it)
+    double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     float2* grad32;        // [B][H*W]  the same rounded to float32 (lazy; tuning "grad_f32")
     int grad_kind;         // which of the two the LAST field pass wrote: 0 none, 1 grad, 2 grad32
@@ -79,11 +79,12 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_field_tile = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_field_tile = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
     if (strcmp(key, "field_tile") == 0) return g_count_field_tile;
+    if (strcmp(key, "step_fused") == 0) return g_count_step_fused;
     if (strcmp(key, "forward_lean") == 0) return g_count_fwd_lean;
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
     if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
@@ -132,8 +133,7 @@ extern "C" int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
     if (err == cudaSuccess) err = cudaMalloc(&e->cells2[0], sizeof(int32_t) * (size_t)M * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->cells2[1], sizeof(int32_t) * (size_t)M * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->alive_bits, sizeof(uint32_t) * (size_t)e->Mw * B);
-    e->Cw = ((int64_t)C + 31) / 32;
-    if (err == cudaSuccess) err = cudaMalloc(&e->occ_bits, sizeof(uint32_t) * (size_t)e->Cw * B);
+    if (err == cudaSuccess) err = cudaMalloc(&e->consumed, sizeof(double) * C * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_gain, sizeof(double) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->part_alive, sizeof(int32_t) * (size_t)e->nblk * B);
     if (err == cudaSuccess) err = cudaMalloc(&e->reward_dev, sizeof(double) * B);
@@ -157,7 +157,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->cells2[1]);
     cudaFree(e->alive_bits);
     delete[] e->flow_ts;
-    cudaFree(e->occ_bits);
+    cudaFree(e->consumed);
     cudaFree(e->grad);
     cudaFree(e->grad32);
     cudaFree(e->part_gain);
@@ -309,8 +309,10 @@ static cudaError_t launch_field(const FieldArgs& fa, int B, int num_sms, cudaStr
     return want_grad ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
 }
 
-static int g_step_impl = 1;        // 0 = always the three kernels move_claim / field_step / agent_feed;
-                                   // 1 = the cluster-fused environment step wherever it applies (die_env_fused.cuh)
+static int g_step_impl = 0;        // 0 (default) = the three kernels move_claim / field_step / agent_feed;
+                                   // 1 = the cluster-fused environment step wherever it applies (die_env_fused.cuh):
+                                   //     bit-identical, 26 % less DRAM traffic, but 2.2x SLOWER on a B200 (19.0 vs 8.7 ms
+                                   //     for 4096 x 256^2: latency / issue bound at two CTAs per SM) -- kept as an opt-in
 
 extern "C" int die_set_step_impl(int32_t impl) {
     DIE_REQUIRE(impl == 0 || impl == 1);
@@ -328,10 +330,7 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     a.medium_out = mout;
     a.winner = e->winner + b0 * C;
     a.action = action;
-    // the tile kernel writes the occupancy bits itself when a warp's 32 cells are one aligned word
-    const bool bits_in_kernel = e->dyn.blur_radius > 0 && e->W % 32 == 0;
-    a.occ_bits = bits_in_kernel ? e->occ_bits + (size_t)b0 * e->Cw : nullptr;
-    a.Cw = e->Cw;
+    a.consumed = e->consumed + b0 * C;
     if (e->publish_grad && e->dyn.blur_radius > 0) {
         if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
         if (publish_as_f32(e)) a.grad32 = e->grad32 + b0 * C;
@@ -379,13 +378,135 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
         case 7: err = launch_field<7>(a, nb, e->num_sms, st); break;
         case 8: err = launch_field<8>(a, nb, e->num_sms, st); break;
     }
-    if (err == cudaSuccess && !bits_in_kernel) {           // ragged rows / no diffusion: bits from the claim table
-        const int64_t total = (int64_t)nb * e->Cw * 32;
-        occ_bits_kernel<<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(
-            e->winner + (size_t)b0 * C, e->occ_bits + (size_t)b0 * e->Cw, (int64_t)C, e->Cw, nb);
-        err = cudaGetLastError();
-    }
     return err;
+}
+
+// ------------------------------------------------------------------------------------------
+// the cluster-fused environment step (die_env_fused.cuh)
+// ------------------------------------------------------------------------------------------
+constexpr size_t kFusedSmemMax = 227u << 10;
+
+typedef void (*fused_kernel_t)(const FusedArgs);
+
+static int g_fused_threads = 512;  // CTA size of the fused step (256 threads / 128 registers measured 45 % slower: removed)
+
+template <int R, int NT>
+static fused_kernel_t pick_fused_nt(bool grad, bool plain) {
+    if (grad) return plain ? env_step_fused_kernel<R, NT, true, true> : env_step_fused_kernel<R, NT, true, false>;
+    return plain ? env_step_fused_kernel<R, NT, false, true> : env_step_fused_kernel<R, NT, false, false>;
+}
+
+template <int R>
+static fused_kernel_t pick_fused(bool grad, bool plain, int nt) {
+    (void)nt;
+    return pick_fused_nt<R, 512>(grad, plain);
+}
+
+// Per kernel instantiation and cluster size: has the shared-memory limit been raised, can the shape be scheduled?
+struct FusedShape { fused_kernel_t kern; int S; size_t smem; int ok; int nt; };
+static FusedShape g_fused_shapes[64];
+static int g_fused_nshapes = 0;
+
+static bool fused_shape_ok(fused_kernel_t kern, int S, size_t smem, int nt) {
+    size_t kernel_max = 0;          // the dynamic shared-memory limit this kernel has been given so far: only ever raised
+    for (int k = 0; k < g_fused_nshapes; ++k) {
+        if (g_fused_shapes[k].kern != kern) continue;
+        if (g_fused_shapes[k].smem > kernel_max) kernel_max = g_fused_shapes[k].smem;
+        if (g_fused_shapes[k].S == S && g_fused_shapes[k].smem >= smem) return g_fused_shapes[k].ok != 0;
+    }
+    int ok = 1;
+#if !defined(DIE_HOSTSIM)
+    if (smem > kernel_max &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) ok = 0;
+    if (ok && S > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = 0;
+    if (ok && max_active_clusters(kern, (unsigned)nt, (unsigned)S, smem) < 1) ok = 0;
+    if (!ok) cudaGetLastError();
+#endif
+    if (g_fused_nshapes < 64) g_fused_shapes[g_fused_nshapes++] = FusedShape{kern, S, smem, ok, nt};
+    else return false;               // (table full: take the three kernels rather than launch an unchecked shape)
+    return ok != 0;
+}
+
+// Runs Env.step for environments [b0, b0 + nb) as one cluster-fused launch if the configuration allows it.
+// *done = 0: not applicable, the caller takes the three kernels.  Pointers already refer to environment b0.
+static int try_fused_step(die_env* e, int b0, int nb, const double* medium_in, double* medium_out, double* agents,
+                          const double* action, double* reward_dev, int64_t* alive_dev, const uint32_t* alive_bits,
+                          cudaStream_t st, int* done) {
+    *done = 0;
+    const int R = e->dyn.blur_radius;
+    if (e->dyn.diffuse_mode != DIE_DIFFUSE_WRAP || R < 1 || R > 4 || (e->W & 1) != 0 || e->W < R) return DIE_OK;
+    if (((uintptr_t)medium_in & 15) != 0 || alive_bits == nullptr) return DIE_OK;   // (a caller's odd view of a tensor)
+    const int nt = g_fused_threads;
+    const bool want_grad = e->publish_grad != 0;
+    const bool plain = e->flow_rwave == nullptr && e->flow_frames == nullptr;
+    fused_kernel_t kern = nullptr;
+    switch (R) {
+        case 1: kern = pick_fused<1>(want_grad, plain, nt); break;
+        case 2: kern = pick_fused<2>(want_grad, plain, nt); break;
+        case 3: kern = pick_fused<3>(want_grad, plain, nt); break;
+        case 4: kern = pick_fused<4>(want_grad, plain, nt); break;
+    }
+    // the largest cluster whose CTAs get whole rows and whose shared memory fits (two CTAs per SM if possible)
+    int S = 0;
+    size_t smem = 0;
+    for (int pass = 0; pass < 2 && S == 0; ++pass) {
+        const size_t limit = pass == 0 ? (size_t)(113u << 10) : kFusedSmemMax;
+        for (int cand = 16; cand >= 1 && S == 0; cand >>= 1) {
+            if (e->H % cand != 0) continue;
+            // a thread group works through at most kFusedMaxRounds feed blocks (their cells stay in registers)
+            if ((e->nblk + cand - 1) / cand > kFusedMaxRounds * (nt / kAgentThreads)) continue;
+            const size_t need = fused_smem_bytes(e->H / cand, e->W, R, want_grad, nt);
+            if (need <= limit && fused_shape_ok(kern, cand, need, nt)) { S = cand; smem = need; }
+        }
+    }
+    if (S == 0) return DIE_OK;
+
+    const size_t C = (size_t)e->H * e->W;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.agents = agents; a.action = action;
+    a.cells = e->cells2[e->cur] + (size_t)b0 * e->M;
+    a.part_gain = e->part_gain + (size_t)b0 * e->nblk;
+    a.part_alive = e->part_alive + (size_t)b0 * e->nblk;
+    a.reward = reward_dev + b0; a.alive_out = alive_dev + b0;
+    a.alive_bits = alive_bits; a.Mw = e->Mw;
+    a.ax = make_axis(e->H); a.ay = make_axis(e->W);
+    a.boundary = e->dyn.boundary;
+    a.w_dep = e->dyn.cost_w_deposit; a.w_dist = e->dyn.cost_w_dist;
+    a.M = e->M; a.nblk = e->nblk; a.bpc = (e->nblk + S - 1) / S;
+    a.medium_in = medium_in; a.medium_out = medium_out;
+    if (want_grad) {
+        if (int rc = ensure_gradient_buffer(e)) return rc;
+        if (publish_as_f32(e)) a.grad32 = e->grad32 + (size_t)b0 * C;
+        else a.grad = e->grad + (size_t)b0 * C;
+        e->grad_kind = publish_as_f32(e) ? 2 : 1;
+    } else {
+        e->grad_kind = 0;
+    }
+    a.H = e->H; a.W = e->W; a.S = S; a.rows_per = e->H / S;
+    a.slab_shift = -1;
+    for (int sft = 0; sft < 31; ++sft) if ((1 << sft) == a.rows_per * e->W) a.slab_shift = sft;
+    a.rate_feed = e->dyn.rate_feed;
+    a.keep = 1.0 - e->dyn.rate_decay_chem;
+    a.food_infinite = e->dyn.food_infinite;
+    if (e->flow_rwave != nullptr) {
+        const int64_t k = e->flow_k % e->flow_T;
+        a.flow_rwave = e->flow_rwave;
+        a.flow_col = e->flow_col + k * e->W;
+        a.flow_row = e->flow_row + k * e->H;
+        a.flow_t = e->flow_ts[k];
+        a.flow_scale = e->flow_scale;
+        a.flow_keep = e->flow_keep;
+    } else if (e->flow_frames != nullptr) {
+        a.flow_frame = e->flow_frames + (e->flow_k % e->flow_T) * (int64_t)C;
+        a.flow_scale = e->flow_scale;
+        a.flow_keep = e->flow_keep;
+    }
+    for (int k = 0; k < 2 * DIE_MAX_RADIUS + 1; ++k) a.bw.w[k] = e->dyn.blur_w[k];
+    DIE_CUDA(launch_cluster(kern, (unsigned)((int64_t)nb * S), (unsigned)nt, (unsigned)S, smem, st, a));
+    ++g_count_step_fused;
+    *done = 1;
+    return DIE_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,6 +531,15 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     if (alive_bits != nullptr) alive_bits += (size_t)b0 * e->Mw;
 
     if (profile) prof_mark(e, 0, st);
+    if (!fused && g_step_impl == 1) {
+        int done = 0;
+        if (int rc = try_fused_step(e, b0, nb, medium_in, medium_out, agents, action, reward_dev, alive_dev, alive_bits, st, &done))
+            return rc;
+        if (done) {                  // (the whole step is the first interval of the per-kernel breakdown)
+            if (profile) for (int k = 1; k <= DIE_NUM_STEP_KERNELS; ++k) prof_mark(e, k, st);
+            return DIE_OK;
+        }
+    }
     if (!fused) {
         const int mchunk = chunks_for(e->M, kMoveItems);
         auto move = (alive_bits != nullptr) ? move_claim_kernel<false, true> : move_claim_kernel<false, false>;
@@ -429,11 +559,11 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
     FeedArgs fa;
     memset(&fa, 0, sizeof(fa));
-    fa.agents = agents; fa.action = action; fa.medium_in = medium_in;
-    fa.occ_bits = e->occ_bits + (size_t)b0 * e->Cw;
+    fa.agents = agents; fa.action = action;
+    fa.consumed_field = e->consumed + (size_t)b0 * C;
     fa.winner = winner; fa.cells = cells; fa.part_gain = part_gain; fa.part_alive = part_alive;
-    fa.C = (int64_t)C; fa.Cw = e->Cw; fa.M = e->M; fa.nblk = e->nblk;
-    fa.rate_feed = e->dyn.rate_feed; fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
+    fa.C = (int64_t)C; fa.M = e->M; fa.nblk = e->nblk;
+    fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
     fa.alive_bits = alive_bits; fa.Mw = e->Mw; fa.boundary = e->dyn.boundary;
     feed<<<fgrid, kAgentThreads, 0, st>>>(fa, SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
@@ -682,6 +812,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
+    else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;
 }
@@ -1156,7 +1287,7 @@ extern "C" int die_slab_feed(die_slab_t* e, double* agents, const double* action
         fa.agents = agents; fa.action = action; fa.cells = e->cells;
         fa.part_gain = e->part_gain; fa.part_alive = e->part_alive;
         fa.C = (int64_t)e->g.slab_cells; fa.M = e->Ml; fa.nblk = e->nblk;
-        fa.rate_feed = e->dyn.rate_feed; fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
+        fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
         fa.boundary = e->dyn.boundary;
         agent_feed_kernel<true, false, false><<<(unsigned)e->nblk, kAgentThreads, 0, st>>>(fa, e->g, slab_tables(e, 0, true));
         DIE_CUDA(cudaGetLastError());

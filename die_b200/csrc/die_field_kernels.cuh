@@ -4,11 +4,14 @@
 //   food consumption      food -= rate_feed * food * (occ > 0)         core/env.py:224-228
 //   food flow             identity                                     core/env.py:147-150
 //   diffusion * decay     gaussian(chem, sigma, 'wrap') * (1-d)        core/env.py:136-145
-// reading medium_in (never written) and the claim table, writing medium_out and one occupancy BIT per
-// cell (occ_bits): the agent feed kernel forms consumed_field = rate_feed * food * occ (core/env.py:224)
-// for a slot's cell from medium_in's food and that bit, so the 8 B/cell consumed_field scratch of round 1
-// is gone (the slab instantiation, whose feed kernel gathers across GPUs, still writes it).
-// Algorithmic traffic: chem R+W, food R+W, occupancy W (+ claim table 4 B R, 1 bit W).
+// reading medium_in (never written) and the claim table, writing medium_out and the per-cell
+// consumed_field (rate_feed * food * occ, core/env.py:224) that the agent feed kernel gathers.
+// Algorithmic traffic: chem R+W, food R+W, occupancy W (+ claim table 4 B R, consumed 8 B W).
+// (Round 2 tried to drop the consumed_field scratch: the field pass wrote one occupancy bit per cell and the feed
+//  kernel formed rate_feed * food * occ from medium_in's food and that bit.  8 B/cell less written, bit-identical -- and
+//  slower on a B200: the feed kernel is bound by its gathers, and two of them per slot (food + bit word) cost more than
+//  the coalesced 8-byte store saved: feed 2.61 -> 2.99 ms, field 3.26 -> 3.26 ms batched; 0.224 -> 0.261 / 0.225 -> 0.212 ms
+//  at 4096^2, profiles/r02e_bench_after_consumed_removal.txt.  Reverted.)
 //
 // The deposit is applied while the halo tile is staged: every staged cell reads its claim
 // (the winning slot, or -1) and, when claimed, gathers that slot's deposit1 -- so the previous
@@ -33,10 +36,7 @@ struct FieldArgs {
     double* medium_out;
     const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
     const double* action;        // [B][3][M]; channel 2 = deposit1
-    double* consumed;            // [B][H*W] consumed_field out (SLAB instantiation only; null otherwise)
-    uint32_t* occ_bits;          // [B][Cw] bit (g & 31) of word (g >> 5) = (claim[g] >= 0); written by the tile kernel when
-                                 // W % 32 == 0 (a warp's 32 output cells are then one aligned word), else by occ_bits_kernel
-    int64_t Cw;                  // words per environment = ceil(H*W / 32)
+    double* consumed;            // [B][H*W] consumed_field out
     double2* grad;               // [B][H*W] np.gradient(chem_out) (raw d/dx, d/dy) or null
     float2* grad32;              // the same pairs rounded to float32 (tuning "grad_f32"): what the guard-banded quick turn
                                  // decision reads anyway (die_turn.h); at most one of grad / grad32 is set
@@ -65,8 +65,8 @@ struct FieldArgs {
 //   F_t = (1 - mix) cos(1 pi (rwave + t)) + mix (sin(pi x 3 + t) + cos(pi y 3 + t)),  mix = 0.25   (WaveSequence)
 // The cosine is die_math.h's (<= 0.7 ulp, bit-identical to the oracle's portable backend); everything
 // time-independent or separable was tabulated by numpy on the host.
-template <bool PLAIN = false>
-__device__ __forceinline__ double next_food(const FieldArgs& a, double f, double cf, int row, int col, int64_t g) {
+template <bool PLAIN = false, typename ARGS = FieldArgs>
+__device__ __forceinline__ double next_food(const ARGS& a, double f, double cf, int row, int col, int64_t g) {
     double food = a.food_infinite ? f : f - cf;
     if (!PLAIN && a.flow_frame != nullptr) {           // scale * next(it) + (1 - decay) * current, core/data_init.py:35
         food = a.flow_scale * a.flow_frame[g] + a.flow_keep * food;
@@ -151,11 +151,7 @@ field_step_kernel(const FieldArgs a) {
     double* chem_out = mout_l + 2 * C;
     const int32_t* win = SLAB ? a.st.claim[a.sg.rank] : a.winner + b * C;
     const double* dep = SLAB ? nullptr : a.action + (b * 3 + 2) * a.M;
-    double* cons = SLAB ? a.st.consumed[a.sg.rank] : nullptr;
-    // one occupancy bit per output cell for the feed kernel: lanes 0..31 of a warp hold 32 consecutive cells of one
-    // row starting at a multiple of 32 columns, i.e. exactly one word when W % 32 == 0 (checked by the launcher)
-    static_assert((TH * TW) % NT == 0 && TW % 32 == 0 && NT % 32 == 0, "the occupancy ballot needs whole warps per row piece");
-    uint32_t* obits = (!SLAB && a.occ_bits != nullptr) ? a.occ_bits + b * a.Cw : nullptr;
+    double* cons = SLAB ? a.st.consumed[a.sg.rank] : a.consumed + b * C;
 
     // food of the output tile is only needed by the last phase: pull its lines towards L2 now, so that
     // those loads do not start a fresh DRAM round trip after the blur (one 128-byte line per thread)
@@ -227,25 +223,18 @@ field_step_kernel(const FieldArgs a) {
             const int r = idx / TW, c = idx - r * TW;
             const int li = i0 + r, gj = j0 + c;
             const int g = li * W + gj;
-            const bool inside = li < HL && gj < W;
-            bool occupied = false;
-            if (inside) {
+            if (li < HL && gj < W) {
                 const double* p = s_v + r * LW + c + R;
                 double acc = p[0] * a.bw.w[R];
 #pragma unroll
                 for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
                 chem_out[g] = acc * a.keep;
-                occupied = win[g] >= 0;
-                const double occ = occupied ? 1.0 : 0.0;
+                const double occ = (win[g] >= 0) ? 1.0 : 0.0;
                 const double f = food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
                 food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
                 occ_out[g] = occ;
-                if (SLAB) cons[g] = cf;
-            }
-            if (!SLAB && obits != nullptr) {                    // (uniform branch: every lane votes)
-                const uint32_t word = __ballot_sync(0xffffffffu, occupied);
-                if ((threadIdx.x & 31) == 0 && inside) obits[g >> 5] = word;
+                cons[g] = cf;
             }
         }
     } else {
@@ -268,9 +257,7 @@ field_step_kernel(const FieldArgs a) {
         const int li = i0 + r, gj = j0 + c;
         const int gi = row0 + li;            // global row: np.gradient is one-sided on the GLOBAL border only
         const int g = li * W + gj;
-        const bool inside = li < HL && gj < W;
-        bool occupied = false;
-        if (inside) {
+        if (li < HL && gj < W) {
             const double* q = s_out + (r + 1) * OW + (c + 1);
             chem_out[g] = q[0];
             // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
@@ -283,33 +270,15 @@ field_step_kernel(const FieldArgs a) {
             if (grad32 != nullptr) grad32[g] = make_float2((float)gx, (float)gy);
             else grad[g] = make_double2(gx, gy);
 
-            occupied = win[g] >= 0;
-            const double occ = occupied ? 1.0 : 0.0;
+            const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
             food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
             occ_out[g] = occ;
-            if (SLAB) cons[g] = cf;
-        }
-        if (!SLAB && obits != nullptr) {                        // (uniform branch: every lane votes)
-            const uint32_t word = __ballot_sync(0xffffffffu, occupied);
-            if ((threadIdx.x & 31) == 0 && inside) obits[g >> 5] = word;
+            cons[g] = cf;
         }
     }
     }   // GRAD
-}
-
-// The occupancy bits of fields whose rows are not a multiple of 32 cells (the tile kernel's warps then straddle
-// words), and of the no-diffusion pass: one ballot per 32 consecutive cells of the claim table.
-__global__ void __launch_bounds__(256)
-occ_bits_kernel(const int32_t* __restrict__ winner, uint32_t* __restrict__ bits, int64_t C, int64_t Cw, int B) {
-    const int64_t total = (int64_t)B * Cw * 32;
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
-        const int64_t b = t / (Cw * 32), g = t - b * (Cw * 32);
-        const bool occupied = g < C && winner[b * C + g] >= 0;
-        const uint32_t word = __ballot_sync(0xffffffffu, occupied);
-        if ((threadIdx.x & 31) == 0) bits[b * Cw + (g >> 5)] = word;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,6 +407,7 @@ field_step_noblur_kernel(const FieldArgs a, int64_t total) {
         mout[g] = occ;
         mout[C + g] = next_food(a, f, cf, (int)(g / a.W), (int)(g % a.W), g);
         mout[2 * C + g] = (chem * a.bw.w[0]) * a.bw.w[0] * a.keep;
+        a.consumed[gid] = cf;
     }
 }
 

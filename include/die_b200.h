@@ -330,10 +330,12 @@ const int32_t* die_slab_cells(const die_slab_t* slab);    /* int32 [Ml] GLOBAL l
 int die_slab_set_corner_mirror(die_slab_t* slab, int32_t r);
 int die_slab_corner_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, void* stream);
 
-/* Env.step implementation switch (tests / A-B timing): 1 (default) = the cluster-fused environment step wherever it
- * applies (small periodic environments: one thread-block cluster per environment, claim table in distributed shared
- * memory, field rows by TMA bulk copies; die_b200/csrc/die_env_fused.cuh), 0 = always the three kernels
- * move_claim / field_step / agent_feed.  Both give bit-identical results. */
+/* Env.step implementation switch (tests / A-B timing): 0 (default) = the three kernels move_claim / field_step /
+ * agent_feed; 1 = the cluster-fused environment step wherever it applies (small periodic environments: one thread-block
+ * cluster per environment, claim table in distributed shared memory, field rows by TMA bulk copies;
+ * die_b200/csrc/die_env_fused.cuh).  Both give bit-identical results.  Measured on a B200 (round 2): the fused step
+ * moves 26 % fewer DRAM bytes but is 2.2x slower (latency / issue bound), so it is an opt-in.
+ * (CTAs of 512 threads; 256 threads with twice the registers measured 45 % slower.) */
 int die_set_step_impl(int32_t impl);
 
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied

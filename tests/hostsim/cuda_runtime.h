@@ -56,6 +56,10 @@ void syncthreads();
 void warp_exchange(uint64_t mine, uint64_t* all32);      // all32[l] = value deposited by lane l (stale if it exited)
 unsigned lane_id();
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void run_grid(dim3 grid, dim3 block, unsigned cluster, size_t smem, const std::function<void()>& body);   // thread-block clusters
+unsigned cluster_rank();
+void cluster_sync();
+void* cluster_map(void* p, unsigned rank);
 void* dev_alloc(size_t bytes);
 void dev_free(void* p);
 extern int last_error;
@@ -82,6 +86,7 @@ static inline double __hiloint2double(int hi, int lo) {
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline int atomicMax(int* p, int v) { const int old = *p; if (v > old) *p = v; return old; }
 
 // ---- warp collectives -------------------------------------------------------------------------
@@ -128,6 +133,10 @@ static inline void mbar_arrive_expect_tx(mbar_t* bar, uint32_t bytes) { hostsim:
 static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t* bar) { hostsim::bulk_g2s(dst, src, bytes, bar); }
 static inline void mbar_wait(mbar_t* bar, uint32_t parity) { hostsim::mbar_wait(bar, parity); }
 static inline void proxy_fence_async() {}
+// die_cluster.cuh under the emulator: the CTAs of a cluster run concurrently, each with its own shared memory
+static inline unsigned cluster_rank() { return hostsim::cluster_rank(); }
+static inline void cluster_sync() { hostsim::cluster_sync(); }
+template <typename T> static inline T* cluster_map(T* p, unsigned rank) { return (T*)hostsim::cluster_map((void*)p, rank); }
 }  // namespace die
 #endif
 
@@ -187,3 +196,13 @@ static inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, K ke
     run_grid(grid, block, smem, [&]() { kern(args...); });
 }
 }  // namespace hostsim
+#if defined(DIE_HOSTSIM)
+namespace die {
+template <typename A>
+static inline cudaError_t launch_cluster(void (*kern)(const A), unsigned grid, unsigned block, unsigned cluster_x,
+                                         size_t smem, cudaStream_t, const A& arg) {
+    hostsim::run_grid(dim3(grid), dim3(block), cluster_x, smem, [&]() { kern(arg); });
+    return cudaGetLastError();
+}
+}  // namespace die
+#endif

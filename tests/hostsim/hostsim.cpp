@@ -36,6 +36,7 @@ struct Fiber {
     const unsigned* wait_ptr = nullptr;     // blocked while *wait_ptr == wait_val
     unsigned wait_val = 0;
     int warp = 0, lane = 0;
+    int blk = 0;                            // index of this thread's CTA within the running cluster
 };
 
 struct Block {
@@ -43,15 +44,27 @@ struct Block {
     int bar_count = 0;
     unsigned bar_gen = 0;
     std::vector<Warp> warps;
+    std::vector<char> store;                // backing store of this CTA's dynamic shared memory
+    char* smem = nullptr;                   // 128-byte aligned in every CTA: the CTAs of a cluster lay it out identically,
+    size_t smem_size = 0;                   // as on the hardware (cluster_map is "same offset in another CTA's window")
+};
+
+// The CTAs of a thread-block cluster run CONCURRENTLY (all their threads are fibers of one scheduling loop), each with
+// its own barriers, warps and shared memory; a plain launch is a cluster of one.
+struct Cluster {
+    int alive = 0;
+    int bar_count = 0;
+    unsigned bar_gen = 0;
 };
 
 ucontext_t g_sched;
 std::vector<Fiber> g_fibers;
 std::vector<char*> g_stacks;
 Fiber* g_self = nullptr;
-Block g_blk;
+std::vector<Block> g_blocks;
+Cluster g_cluster;
 const std::function<void()>* g_body = nullptr;
-std::vector<char> g_smem;
+#define g_blk (g_blocks[g_self->blk])
 
 char* stack_for(size_t i) {
     while (g_stacks.size() <= i) {
@@ -85,6 +98,11 @@ void thread_exit(Fiber* f) {
         g_blk.bar_count = 0;
         ++g_blk.bar_gen;
     }
+    --g_cluster.alive;
+    if (g_cluster.bar_count > 0 && g_cluster.bar_count >= g_cluster.alive) {
+        g_cluster.bar_count = 0;
+        ++g_cluster.bar_gen;
+    }
     Warp& w = g_blk.warps[f->warp];
     --w.alive;
     if (w.count > 0 && w.count >= w.alive) {
@@ -101,8 +119,20 @@ void trampoline() {
 
 }  // namespace
 
-void* dyn_smem() { return g_smem.data(); }
+void* dyn_smem() { return g_blk.smem; }
 unsigned lane_id() { return (unsigned)g_self->lane; }
+
+// ---- thread-block clusters (die_b200/csrc/die_cluster.cuh) ------------------------------------------------------
+unsigned cluster_rank() { return (unsigned)g_self->blk; }
+void cluster_sync() { block_wait(&g_cluster.bar_gen, &g_cluster.bar_count, g_cluster.alive); }
+void* cluster_map(void* p, unsigned rank) {
+    char* lo = g_blk.smem;
+    if ((char*)p < lo || (char*)p >= lo + g_blk.smem_size || rank >= g_blocks.size()) {
+        fprintf(stderr, "hostsim: cluster_map of a pointer outside this CTA's dynamic shared memory, or of a rank outside the cluster\n");
+        abort();
+    }
+    return g_blocks[rank].smem + ((char*)p - lo);
+}
 
 void syncthreads() { block_wait(&g_blk.bar_gen, &g_blk.bar_count, g_blk.alive); }
 
@@ -163,8 +193,8 @@ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
                         "(dst %p, src %p, %u bytes)\n", dst, src, bytes);
         abort();
     }
-    char* lo = g_smem.data();
-    if ((char*)dst < lo || (char*)dst + bytes > lo + g_smem.size()) {
+    char* lo = g_blk.smem;
+    if ((char*)dst < lo || (char*)dst + bytes > lo + g_blk.smem_size) {
         fprintf(stderr, "hostsim: bulk copy destination outside the dynamic shared memory of the block\n");
         abort();
     }
@@ -200,64 +230,80 @@ void mbar_wait(void* bar, uint32_t parity) {
     }
 }
 
-void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) { run_grid(grid, block, 1, smem, body); }
+
+void run_grid(dim3 grid, dim3 block, unsigned cluster, size_t smem, const std::function<void()>& body) {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
-    if (nthreads == 0 || nthreads > 1024 || grid.x == 0) {
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || cluster == 0 || cluster > 16 || nblocks % cluster != 0 ||
+        (cluster > 1 && (grid.y != 1 || grid.z != 1))) {
         last_error = cudaErrorInvalidValue;
         return;
     }
     g_body = &body;
-    if (g_fibers.size() < nthreads) g_fibers.resize(nthreads);
-    g_smem.assign(smem + 16, (char)0xFF);      // NaN-poisoned: a read of unwritten shared memory shows up in the results
+    const size_t nfibers = nthreads * cluster;
+    if (g_fibers.size() < nfibers) g_fibers.resize(nfibers);
     const int nwarps = (int)((nthreads + 31) / 32);
-    // Blocks run one after the other.  HOSTSIM_BLOCK_ORDER = reverse | shuffle runs them in another order: results that
-    // change with it mean a kernel depends on the order in which its CTAs execute, which the hardware does not promise.
-    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
-    std::vector<size_t> order(nblocks);
-    for (size_t i = 0; i < nblocks; ++i) order[i] = i;
+    // Clusters (plain launches: blocks) run one after the other.  HOSTSIM_BLOCK_ORDER = reverse | shuffle runs them in
+    // another order: results that change with it mean a kernel depends on the order in which its CTAs execute, which
+    // the hardware does not promise.
+    const size_t nclusters = nblocks / cluster;
+    std::vector<size_t> order(nclusters);
+    for (size_t i = 0; i < nclusters; ++i) order[i] = i;
     static const char* mode = getenv("HOSTSIM_BLOCK_ORDER");
     if (mode != nullptr && strcmp(mode, "reverse") == 0) {
-        for (size_t i = 0; i < nblocks; ++i) order[i] = nblocks - 1 - i;
+        for (size_t i = 0; i < nclusters; ++i) order[i] = nclusters - 1 - i;
     } else if (mode != nullptr && strcmp(mode, "shuffle") == 0) {
         static uint64_t state = 0x9E3779B97F4A7C15ull;
-        for (size_t i = nblocks; i > 1; --i) {              // Fisher-Yates with a fixed-seed xorshift
+        for (size_t i = nclusters; i > 1; --i) {              // Fisher-Yates with a fixed-seed xorshift
             state ^= state << 13; state ^= state >> 7; state ^= state << 17;
             std::swap(order[i - 1], order[state % i]);
         }
     }
-    for (size_t ob = 0; ob < nblocks; ++ob) {
-        const unsigned bx = (unsigned)(order[ob] % grid.x), by = (unsigned)((order[ob] / grid.x) % grid.y),
-                       bz = (unsigned)(order[ob] / ((size_t)grid.x * grid.y));
-        g_blk.alive = (int)nthreads;
+    g_blocks.resize(cluster);
+    for (size_t oc = 0; oc < nclusters; ++oc) {
         g_mbars.clear();
-        g_blk.bar_count = 0;
-        g_blk.warps.assign(nwarps, Warp());
-        for (size_t t = 0; t < nthreads; ++t) {
-            Fiber& f = g_fibers[t];
-            f.done = false;
-            f.wait_ptr = nullptr;
-            f.warp = (int)(t / 32);
-            f.lane = (int)(t % 32);
-            ++g_blk.warps[f.warp].alive;
-            f.tc.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((size_t)block.x * block.y))};
-            f.tc.bid = uint3{bx, by, bz};
-            f.tc.bdim = block;
-            f.tc.gdim = grid;
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = stack_for(t);
-            f.ctx.uc_stack.ss_size = kStackBytes;
-            f.ctx.uc_link = &g_sched;
-            makecontext(&f.ctx, trampoline, 0);
+        g_cluster = Cluster();
+        g_cluster.alive = (int)nfibers;
+        for (unsigned q = 0; q < cluster; ++q) {
+            Block& blk = g_blocks[q];
+            blk.alive = (int)nthreads;
+            blk.bar_count = 0;
+            blk.warps.assign(nwarps, Warp());
+            blk.store.assign(smem + 16 + 128, (char)0xFF);   // NaN-poisoned: a read of unwritten shared memory shows up in the results
+            blk.smem = (char*)(((uintptr_t)blk.store.data() + 127) & ~(uintptr_t)127);
+            blk.smem_size = smem + 16;
+            const size_t bid = order[oc] * cluster + q;
+            const unsigned bx = (unsigned)(bid % grid.x), by = (unsigned)((bid / grid.x) % grid.y),
+                           bz = (unsigned)(bid / ((size_t)grid.x * grid.y));
+            for (size_t t = 0; t < nthreads; ++t) {
+                Fiber& f = g_fibers[q * nthreads + t];
+                f.done = false;
+                f.wait_ptr = nullptr;
+                f.blk = (int)q;
+                f.warp = (int)(t / 32);
+                f.lane = (int)(t % 32);
+                ++blk.warps[f.warp].alive;
+                f.tc.tid = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((size_t)block.x * block.y))};
+                f.tc.bid = uint3{bx, by, bz};
+                f.tc.bdim = block;
+                f.tc.gdim = grid;
+                getcontext(&f.ctx);
+                f.ctx.uc_stack.ss_sp = stack_for(q * nthreads + t);
+                f.ctx.uc_stack.ss_size = kStackBytes;
+                f.ctx.uc_link = &g_sched;
+                makecontext(&f.ctx, trampoline, 0);
+            }
         }
-        // HOSTSIM_THREAD_ORDER = reverse: the fibers of a block are scheduled from the last thread down.  A missing
-        // __syncthreads between a producer and a consumer phase can go unnoticed when producers happen to run first.
+        // HOSTSIM_THREAD_ORDER = reverse: the fibers are scheduled from the last thread down.  A missing barrier
+        // between a producer and a consumer phase can go unnoticed when producers happen to run first.
         static const char* torder = getenv("HOSTSIM_THREAD_ORDER");
         const bool treverse = torder != nullptr && strcmp(torder, "reverse") == 0;
-        size_t remaining = nthreads;
+        size_t remaining = nfibers;
         while (remaining > 0) {
             bool progressed = false;
-            for (size_t tt = 0; tt < nthreads; ++tt) {
-                const size_t t = treverse ? nthreads - 1 - tt : tt;
+            for (size_t tt = 0; tt < nfibers; ++tt) {
+                const size_t t = treverse ? nfibers - 1 - tt : tt;
                 Fiber& f = g_fibers[t];
                 if (f.done) continue;
                 if (f.wait_ptr != nullptr && *f.wait_ptr == f.wait_val) continue;

@@ -30,14 +30,22 @@ def test_roofline_arithmetic():
     ms = {"physarum_forward": 5.0, "move_claim": 2.5, "field_step": 3.6, "agent_feed": 2.6, "finalize_stats": 0.03}
     meas = dict(M=M, C=C, alive_local=alive, kernel_ms=dict(ms), ms_per_step=13.75)
     r, step_bytes = b.roofline_of(meas, B, "physarum_batched_4096x256x256")
-    # 96 + 56 + 40 B per slot, 48 B per cell (+ 24 B per alive agent): 240 B per cell-update with M = C
-    assert step_bytes == (96 + 56 + 40) * M * B + 48 * C * B + 24 * alive
+    # three-kernel path: 72 (forward with the float32 gradient pair) + 56 + 40 B per slot, 48 B per cell (+ 24 B per alive
+    # agent); the survey's model counts 96 B for the forward kernel: 240 B per cell-update with M = C
+    assert step_bytes == (72 + 56 + 40) * M * B + 48 * C * B + 24 * alive
+    assert r["step"]["survey_bytes"] == (96 + 56 + 40) * M * B + 48 * C * B + 24 * alive
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"] == "physarum_forward"
     k = r["kernels"]["physarum_forward"]
-    assert abs(k["gbs"] - 96 * M * B / 5.0e-3 / 1e9) < 0.1 and abs(r["achieved"] - k["gbs"]) < 1e-9
+    assert abs(k["gbs"] - 72 * M * B / 5.0e-3 / 1e9) < 0.1 and abs(r["achieved"] - k["gbs"]) < 1e-9
     assert abs(r["frac"] - k["gbs"] / r["peak"]) < 1e-3
     assert abs(r["step"]["gbs"] - step_bytes / 13.75e-3 / 1e9) < 0.1
     assert r["traffic"] is None or r["traffic"] > 0
+    # the cluster-fused step: one kernel, 112 B per cell-update (144 B in the survey's model)
+    meas = dict(M=M, C=C, alive_local=alive, kernel_ms={"physarum_forward": 4.0, "env_step_fused": 6.0}, ms_per_step=10.0,
+                grad_kind=1)
+    r, step_bytes = b.roofline_of(meas, B, "physarum_batched_4096x256x256")
+    assert step_bytes == (80 + 112) * M * B + 24 * alive and r["kernel"] == "env_step_fused"
+    assert r["step"]["survey_bytes"] == 240 * M * B + 24 * alive
 
 
 def test_peak_and_traffic_lookups():

@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -208,7 +208,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0])])
+                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
@@ -220,6 +220,54 @@ def test_tuning_switches_do_not_change_results(tuning, key, values):
         out = _philox_run((40, 72), 12)
         for a, b, what in zip(base, out, ("medium", "agents", "theta", "reward")):
             assert np.array_equal(a, b), f"{key}={v}: {what} differs"
+
+
+@pytest.mark.parametrize("shape,sigma,batch", [((64, 64), 0.5, None), ((40, 72), 0.5, 3), ((6, 76), 0.5, None),
+                                               ((48, 96), 1.0, 2), ((33, 132), 0.3, 2), ((16, 34), 0.8, 5)])
+@pytest.mark.parametrize("grad,threads", [(True, 512), (False, 512)])
+def test_fused_step_equals_three_kernels(tuning, shape, sigma, batch, grad, threads):
+    """step_impl = 1 (die_env_fused.cuh): one thread-block cluster per environment -- claims by atomicMax into the
+    distributed shared memory of the CTA that owns the row, chem rows by bulk copies on an mbarrier, the feed phase
+    reading remote claims, block partials and the final sum in the order of the three-kernel path.  Under the emulator
+    the CTAs of a cluster run concurrently as fibers with separate shared memories.  Cluster sizes 16 / 8 / 2 / 1 (by the
+    divisors of H), CTAs without slots (few feed blocks), radii 1..4, batches, with (Physarum) and without (Brownian)
+    the published gradient: medium, agents, headings, rewards and the cell cache must not differ in a bit."""
+    outs = []
+    fused0 = S.lib().die_get_counter(b"step_fused")
+    tuning("fused_threads", threads)
+    for impl in (0, 1):
+        tuning("step_impl", impl)
+        refs, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 13 + b)[0]
+        for it in range(5):
+            if grad:
+                act = ga.forward(env)
+            else:
+                act = S.brownian_forward(env.agents, move_scale=0.02, seed=4, step=it)
+            env.step(act)
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.reward.copy(), env.cells().copy(),
+                     env.gradient() if grad else None))
+    # (33 rows only admit a cluster of one CTA: five rounds of feed blocks for 256 threads, one more than the kernel holds)
+    expect = 0 if (threads == 256 and shape == (33, 132)) else 5
+    assert S.lib().die_get_counter(b"step_fused") == fused0 + expect, "the fused step must be the one that ran"
+    for a, b, what in zip(outs[0], outs[1], ("medium", "agents", "theta", "reward", "cells", "gradient")):
+        if a is None:
+            continue
+        assert np.array_equal(a, b), f"{what} differs"
+
+
+def test_fused_step_falls_back_where_it_does_not_apply(tuning):
+    """Odd row lengths (the bulk copies need 16-byte rows), non-periodic diffusion, no diffusion: the three kernels run."""
+    fused0 = S.lib().die_get_counter(b"step_fused")
+    for shape, kw in (((40, 71), {}), ((40, 64), dict(diffuse_mode='reflect')), ((40, 64), dict(diffuse_sigma=0.1))):
+        refs, env = make_pair(shape, seed=3, dynamics_kw=kw)
+        ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
+        for it in range(2):
+            env.step(ga.forward(env))
+    assert S.lib().die_get_counter(b"step_fused") == fused0
 
 
 def test_batched_envs_match_single_envs():
@@ -813,7 +861,7 @@ def _random_case(seed):
     agent = dict(scale=float(rng.choice([0.007, 0.03, 0.2, 1.7])), sense_offset=float(rng.choice([0.0, 0.04, 0.3, 1.5])),
                  turn_angle=float(rng.choice([30, 35, 45, 90])), sense_angle=float(rng.choice([60, 90, 120, 170])),
                  turn_tolerance=float(rng.choice([0.05, 0.1, 0.3])), deposit=float(rng.choice([4.0, 0.5])))
-    tune = dict(grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
+    tune = dict(step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
                 feed_bits=int(rng.random() < 0.7))
     return (h, w), float(rng.choice([0.05, 0.1, 0.5, 1.0])), dyn, rdyn, agent, tune, bool(rng.random() < 0.5)
 
@@ -857,7 +905,7 @@ def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
     C = h * w
     m = int(rng.choice([max(C // 3, 1), C, C, 2 * C + 7]))
     sigma = float(rng.choice([0.3, 0.5, 0.8]))
-    for k, v in dict(grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
+    for k, v in dict(step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
                      feed_bits=int(rng.random() < 0.7)).items():
         tuning(k, v)
     refs, mediums, agentss = [], [], []
