@@ -65,6 +65,7 @@ class GradientAgent(_DeviceAgent):
         self._prev_grad = None      # [B, 2, M] device (only when it can matter)
         self._coin_host = self._coin_dev = None
         self._noise_host = self._noise_dev = None
+        self._upload_events = {}        # name -> CUDA event recorded after the last copy out of that pinned buffer
         self._sense_cells = None
         self.record_sense_cells = False
         self.use_env_hints = True           # die_b200/_hints.py: cached cells + published gradient
@@ -179,8 +180,16 @@ class GradientAgent(_DeviceAgent):
             dev = torch.empty(shape, dtype=dtype, device=device)
             setattr(self, f'_{name}_host', host)
             setattr(self, f'_{name}_dev', dev)
+        # the previous call's asynchronous copy out of this pinned buffer may still be queued (step_async loops never
+        # synchronise): wait for it before overwriting the buffer, or the GPU could read the NEXT call's draws
+        ev = self._upload_events.get(name)
+        if ev is not None:
+            ev.synchronize()
         host.numpy()[...] = np.asarray(arr).reshape(shape)
         dev.copy_(host, non_blocking=True)
+        if ev is None:
+            ev = self._upload_events[name] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
         return dev.data_ptr()
 
     def forward(self, obs: ObsType, coin: Optional[np.ndarray] = None,

@@ -105,6 +105,7 @@ class BrownianAgent(_DeviceAgent):
         self._seed = int(seed)
         self._u_host = None
         self._u_dev = None
+        self._u_event = None
 
     def forward(self, obs: ObsType, u: Optional[np.ndarray] = None) -> ActType:
         """``u`` ([B,] 3, M): explicitly injected uniforms (overrides ``rng``)."""
@@ -120,8 +121,14 @@ class BrownianAgent(_DeviceAgent):
             if self._u_host is None or self._u_host.shape != (B, 3, M):
                 self._u_host = torch.empty((B, 3, M), dtype=torch.float64).pin_memory()
                 self._u_dev = torch.empty((B, 3, M), dtype=torch.float64, device=agents.device)
+            # the previous call's asynchronous copy out of the pinned buffer may still be queued: wait for it first
+            if self._u_event is not None:
+                self._u_event.synchronize()
             self._u_host.numpy()[...] = np.asarray(u, dtype=np.float64).reshape(B, 3, M)
             self._u_dev.copy_(self._u_host, non_blocking=True)
+            if self._u_event is None:
+                self._u_event = torch.cuda.Event()
+            self._u_event.record(torch.cuda.current_stream(agents.device))
             u_ptr = self._u_dev.data_ptr()
         with _lib.on_device(agents.device):
             _lib.check(self._lib.die_brownian_forward(
