@@ -249,8 +249,91 @@ def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     else:
         kernel_ms.update({k: v / max(nprof, 1) for k, v in kms.items()})
     grad_kind = dlib.load().die_env_gradient_kind(env._handle)
-    return dict(env=env, agent=agent, ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
+    return dict(env=env, agent=agent, obs=obs, steps_done=args.warmup + args.steps + n_prof,
+                ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
                 alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused), grad_kind=int(grad_kind))
+
+
+def steady_state_leg(torch, meas, checkpoints, window=40):
+    """ms per step in a `window`-step window ending at each of `checkpoints` total steps (the ~90 % ghost slots start at
+    (0, 0) and random-walk outwards: the gathers of the first few hundred steps hit L1 / L2 more often than later)."""
+    env, agent, obs, done = meas["env"], meas["agent"], meas["obs"], meas["steps_done"]
+    out = {}
+    for cp in checkpoints:
+        if cp < done + window:
+            continue
+        for _ in range(cp - window - done):
+            obs, _, _ = env.step_async(agent.forward(obs))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(window):
+            obs, _, _ = env.step_async(agent.forward(obs))
+        e1.record()
+        torch.cuda.synchronize()
+        done = cp
+        out[str(cp)] = round(e0.elapsed_time(e1) / window, 5)
+    meas["obs"], meas["steps_done"] = obs, done
+    return out
+
+
+def small_env_leg(D, torch, device, agent_name, iters=300, warmup=20, cpu_iters=20):
+    """BASELINE configs[0] / [1]: ONE 256x256 environment, the reference's own loop (examples/minimal_run.py:21-25,
+    README.md:23-48) -- action = agent.forward(obs); obs, reward, _, _, info = env.step(action) with the reward read back
+    every iteration -- timed by the wall clock around `iters` iterations; next to the oracle on one host core."""
+    import die_b200 as Dm
+    field = (256, 256)
+    med_h, ag_h = build_host_state(field, 1, seed=4242)
+    def make_agent(mod):
+        if agent_name == "brownian":
+            return mod.BrownianAgent(move_scale=0.01)
+        return mod.PhysarumAgent(max_agents=field[0] * field[1], **PHYS)
+    env = D.Env(field, D.Dynamics(init_agent_ratio=AGENT_RATIO), init_state=(med_h[0], ag_h[0]), device=device)
+    agent = make_agent(D)
+    obs = env._get_current_obs
+    for _ in range(warmup):
+        obs, reward, _, _, info = env.step(agent.forward(obs))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        obs, reward, _, _, info = env.step(agent.forward(obs))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"field": list(field), "agent": agent_name, "iters": iters, "ms_per_iter": dt / iters * 1e3,
+           "value": field[0] * field[1] * iters / dt, "unit": UNIT, "num_agents": int(info["num_agents"]),
+           "api": "agent.forward(obs) + env.step(action) -> (obs, reward: float, terminated, truncated, info), one "
+                  "host synchronisation per iteration (the reward read-back)"}
+    graph = getattr(Dm, "GraphedLoop", None)
+    if graph is not None:
+        # the same iteration captured in a CUDA graph (die_b200.GraphedLoop): forward + step_async, reward kept on device
+        try:
+            loop = graph(env, agent)
+            loop.run(warmup)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loop.run(iters)
+            torch.cuda.synchronize()
+            dg = time.perf_counter() - t0
+            out["cuda_graph"] = {"ms_per_iter": dg / iters * 1e3, "value": field[0] * field[1] * iters / dg, "unit": UNIT,
+                                 "api": "die_b200.GraphedLoop(env, agent).run(n): forward + step_async replayed from one "
+                                        "captured graph, rewards accumulated on the device"}
+        except Exception as exc:                     # never lose the whole bench line to the optional leg
+            out["cuda_graph"] = {"error": repr(exc)}
+    if cpu_iters > 0:
+        from oracle import die_ref as R
+        np.random.seed(1)
+        renv = R.Env(field, R.Dynamics(init_agent_ratio=AGENT_RATIO), noise_seed=1)
+        ragent = R.BrownianAgent(0.01) if agent_name == "brownian" else R.PhysarumAgent(max_agents=field[0] * field[1], **PHYS)
+        robs = renv._get_current_obs
+        for _ in range(2):
+            robs, *_ = renv.step(ragent.forward(robs))
+        t0 = time.perf_counter()
+        for _ in range(cpu_iters):
+            robs, *_ = renv.step(ragent.forward(robs))
+        dc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": field[0] * field[1] * cpu_iters / dc, "unit": UNIT, "cores": 1, "kind": "port",
+                               "ms_per_iter": dc / cpu_iters * 1e3,
+                               "sample": f"{cpu_iters} iterations of the same loop by the numpy oracle on one host core"}
+    return out
 
 
 def e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus):
@@ -331,14 +414,13 @@ def roofline_of(meas, B_local, wl_name):
                      "survey_frac_of_8TBs_nominal": round(survey_gbs / 8000.0, 4)}}, step_bytes
 
 
-def run_slab(args, torch, dist, device, rank, world):
+def measure_slab(args, torch, dist, device, rank, world, N, steps, warmup):
     """BASELINE configs[4]: ONE field split into row slabs over the ranks, NVLink peer access in-kernel
     (die_b200/slab.py).  Agent parameters are the README ones expressed in cells: the
-    256^2 geometry (1.785 cells per step, 10.2 cells look-ahead) at any field size."""
+    256^2 geometry (1.785 cells per step, 10.2 cells look-ahead) at any field size.  -> the JSON line (rank 0) or None."""
     import die_b200 as D
     from die_b200.slab import SlabEnv, SlabPhysarumAgent
     from die_b200.sharding import max_over_ranks
-    N = args.field
     phys = dict(scale=1.785 / (N - 1), turn_angle=30, sense_offset=10.2 / (N - 1))
     t0 = time.time()
     env = SlabEnv((N, N), D.Dynamics(init_agent_ratio=AGENT_RATIO), seed=3, corner_r=args.corner_r)
@@ -346,7 +428,7 @@ def run_slab(args, torch, dist, device, rank, world):
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     obs = env._get_current_obs
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         obs, _ = env.step_async(agent.forward(obs))
     torch.cuda.synchronize()
     dist.barrier()
@@ -357,7 +439,7 @@ def run_slab(args, torch, dist, device, rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     mode = os.environ.get("DIE_SLAB_MODE", "reduce")          # diagnosis: reduce | noreduce | sync
-    for _ in range(args.steps):
+    for _ in range(steps):
         obs, stats = env.step_async(agent.forward(obs), reduce_stats=(mode != "noreduce"))
         if mode == "sync":
             torch.cuda.synchronize()
@@ -367,16 +449,18 @@ def run_slab(args, torch, dist, device, rank, world):
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    ms = max_over_ranks(ev0.elapsed_time(ev1), device) / args.steps
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device) / steps
     clocks = sampler.stop() if rank == 0 else None
     reward, alive = float(stats[0].item()), int(round(float(stats[1].item())))
     peak, peak_src = measured_hbm_peak()
     C = N * N
     step_bytes = 240.0 * C + 24.0 * alive
+    del env, agent, obs
+    torch.cuda.empty_cache()
     if rank == 0:
         gbs = step_bytes / (ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": C / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        line = {"metric": METRIC, "value": C / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated gradient-noise food, Bernoulli(0.1) agents)",
                 "config": {"workload": f"physarum_single_field_{N}x{N}_slab", "field": [N, N], "agent": "PhysarumAgent",
                            **phys, "agent_ratio": AGENT_RATIO, "max_agents": C, "alive_agents": alive,
@@ -388,8 +472,15 @@ def run_slab(args, torch, dist, device, rank, world):
                 "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs / world, 1), "peak": peak,
                              "unit": "GB/s per GPU", "frac": round(gbs / world / peak, 4), "peak_source": peak_src,
                              "traffic": None},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (10 if args.corner_r else 9), "launches_per_step": 10 if args.corner_r else 9,
+                "cpu_baseline": None, "e2e": None, "gpu_launches": steps * (10 if args.corner_r else 9), "launches_per_step": 10 if args.corner_r else 9,
                 "clocks": clocks, "setup_s": round(setup_s, 1), "last_reward": reward}
+        return line
+    return None
+
+
+def run_slab(args, torch, dist, device, rank, world):
+    line = measure_slab(args, torch, dist, device, rank, world, args.field, args.steps, args.warmup)
+    if rank == 0:
         print(json.dumps(line))
 
 
@@ -447,20 +538,49 @@ def run_die_b200(args):
     value = cells_per_step / (ms_per_step * 1e-3)
     roofline, step_bytes = roofline_of(meas, B_local, wl_name)
     alive_local = meas["alive_local"]
-    del meas["env"], meas["agent"]
+    del meas["env"], meas["agent"], meas["obs"]
     torch.cuda.empty_cache()
 
-    # ---- N = 1 only: the single 4096x4096 field (BASELINE.json configs[2]) in the same run ----------
+    # ---- N = 1 only: the single 4096x4096 field (BASELINE.json configs[2]) in the same run, followed to its steady
+    #      state, and the reference's own configurations (configs[0], [1]: ONE 256x256 environment, 300 iterations) ----
     also = None
     if n_gpus == 1 and workload == "batch256" and not args.no_single_field:
         f2 = (args.field, args.field)
         m2 = measure(D, torch, dist, args, f2, 1, False, device, rank, world, want_clocks=False)
         r2, sb2 = roofline_of(m2, 1, "physarum_single_field_%dx%d" % f2)
-        also = {"physarum_single_field_%dx%d" % f2: {
-            "value": f2[0] * f2[1] / (m2["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m2["ms_per_step"],
-            "max_agents": m2["M"], "alive_agents": m2["alive_local"], "roofline": r2}}
+        steady = steady_state_leg(torch, m2, [int(c) for c in args.steady.split(",") if c]) if args.steady else {}
+        C2 = f2[0] * f2[1]
+        entry = {"value": C2 / (m2["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m2["ms_per_step"],
+                 "measured_at_steps": [args.warmup, args.warmup + args.steps],
+                 "max_agents": m2["M"], "alive_agents": m2["alive_local"], "roofline": r2}
+        if steady:
+            last = steady[max(steady, key=int)]
+            step_b = r2["step"]["algorithmic_bytes"]
+            entry["steady_state"] = {
+                "ms_per_step_in_the_40_steps_before_step": steady,
+                "value_at_last": C2 / (last * 1e-3), "unit": UNIT,
+                "frac_at_last": round(step_b / (last * 1e-3) / 1e9 / r2["peak"], 4),
+                "frac_of_8TBs_nominal_at_last": round(step_b / (last * 1e-3) / 1e9 / 8000.0, 4),
+                "survey_frac_of_8TBs_nominal_at_last": round(r2["step"]["survey_bytes"] / (last * 1e-3) / 1e9 / 8000.0, 4)}
+        also = {"physarum_single_field_%dx%d" % f2: entry}
         del m2
         torch.cuda.empty_cache()
+        if not args.no_small_env:
+            also["brownian_single_env_256x256_300_iters"] = small_env_leg(D, torch, device, "brownian",
+                                                                         cpu_iters=0 if args.no_cpu else 20)
+            also["physarum_single_env_256x256_300_iters"] = small_env_leg(D, torch, device, "physarum",
+                                                                         cpu_iters=0 if args.no_cpu else 20)
+
+    # ---- N > 1: the single 32768x32768 field split into row slabs over the ranks (BASELINE.json configs[4]) ----------
+    if n_gpus > 1 and workload == "batch256" and not args.no_slab:
+        try:
+            sl = measure_slab(args, torch, dist, device, rank, world, args.slab_field, args.slab_steps, 10)
+        except Exception as exc:                     # (an unsupported peer topology must not lose the headline line)
+            sl = {"error": repr(exc)}
+        if rank == 0 and sl is not None:
+            keep = ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "roofline", "setup_s", "error")
+            also = dict(also or {})
+            also["physarum_single_field_%dx%d_slab" % (args.slab_field, args.slab_field)] = {k: sl[k] for k in keep if k in sl}
 
     # ---- e2e: the same loop through the host-buffer API (numpy obs/action cross PCIe every call) ----
     e2e = None
@@ -620,6 +740,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU on the host-buffer (e2e) leg")
     ap.add_argument("--no-single-field", action="store_true")
+    ap.add_argument("--no-small-env", action="store_true", help="skip the configs[0] / configs[1] legs (one 256x256 env)")
+    ap.add_argument("--steady", default="300,3000", help="single field: also report ms/step in the 40 steps before these "
+                                                          "total step counts ('' = off)")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the configs[4] leg (one field over all ranks)")
+    ap.add_argument("--slab-field", type=int, default=32768, help="side of the slab-decomposed field of the N > 1 run")
+    ap.add_argument("--slab-steps", type=int, default=25)
     ap.add_argument("--cpu-field", type=int, default=256, help="side of each CPU sample env")
     ap.add_argument("--cpu-steps", type=int, default=100, help="steps per CPU env in the cpu_baseline leg")
     ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")

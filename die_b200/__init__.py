@@ -10,10 +10,11 @@ from .base_types import DataChannels, channel
 from .env import Env, Dynamics, BoundaryCondition, linear_action_cost, zero_cost
 from .data_init import WaveSequence, FieldSequence, TabulatedSequence, PerlinNoiseSequence
 from .agent import Agent, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent
+from .graph import GraphedLoop
 
 _lib.load()     # fail loudly at import time if the CUDA library is missing
 
 __all__ = ['Env', 'Dynamics', 'BoundaryCondition', 'linear_action_cost', 'zero_cost',
            'Agent', 'ConstAgent', 'BrownianAgent', 'GradientAgent', 'PhysarumAgent',
-           'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
+           'GraphedLoop', 'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
 __version__ = '0.1.0'

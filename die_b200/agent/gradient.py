@@ -65,6 +65,7 @@ class GradientAgent(_DeviceAgent):
         self._prev_grad = None      # [B, 2, M] device (only when it can matter)
         self._coin_host = self._coin_dev = None
         self._noise_host = self._noise_dev = None
+        self._step_dev = None           # device-resident call counter (set by die_b200.graph.GraphedLoop)
         self._upload_events = {}        # name -> CUDA event recorded after the last copy out of that pinned buffer
         self._sense_cells = None
         self.record_sense_cells = False
@@ -248,12 +249,19 @@ class GradientAgent(_DeviceAgent):
             stream = torch.cuda.current_stream().cuda_stream
             if env is not None:
                 flags = env._forward_flags(agents, medium, want_gradient=True, speculate=self.fuse_move)
+                step_arg = self._step
+                if self._step_dev is not None:       # (die_b200/graph.py) the call counter lives on the device
+                    flags |= _lib.FWD_STEP_ON_DEVICE
+                    step_arg = self._step_dev.data_ptr()
                 _lib.check(self._lib.die_env_forward_gradient(
                     env._handle, _lib.C.byref(p), agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
                     prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, flags,
-                    self._seed, self._step, stream))
+                    self._seed, step_arg, stream))
             else:
                 flags = 0
+                if self._step_dev is not None:
+                    raise RuntimeError("the device-resident call counter (die_b200.GraphedLoop) needs the producing Env: "
+                                       "pass the observation that Env.step returned and keep use_env_hints on")
                 _lib.check(self._lib.die_gradient_forward(
                     _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
                     prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, None, None,

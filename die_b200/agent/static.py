@@ -106,6 +106,7 @@ class BrownianAgent(_DeviceAgent):
         self._u_host = None
         self._u_dev = None
         self._u_event = None
+        self._step_dev = None           # device-resident call counter (set by die_b200.graph.GraphedLoop)
 
     def forward(self, obs: ObsType, u: Optional[np.ndarray] = None) -> ActType:
         """``u`` ([B,] 3, M): explicitly injected uniforms (overrides ``rng``)."""
@@ -131,8 +132,14 @@ class BrownianAgent(_DeviceAgent):
             self._u_event.record(torch.cuda.current_stream(agents.device))
             u_ptr = self._u_dev.data_ptr()
         with _lib.on_device(agents.device):
-            _lib.check(self._lib.die_brownian_forward(
-                agents.data_ptr(), action.data_ptr(), M, B, self._scale, self._dep_scale,
-                u_ptr, self._seed, self._step, torch.cuda.current_stream().cuda_stream))
+            if self._step_dev is not None and u_ptr is None:
+                # (die_b200/graph.py) the call counter lives on the device, so a captured launch can be replayed
+                _lib.check(self._lib.die_brownian_forward_dev(
+                    agents.data_ptr(), action.data_ptr(), M, B, self._scale, self._dep_scale,
+                    self._seed, self._step_dev.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            else:
+                _lib.check(self._lib.die_brownian_forward(
+                    agents.data_ptr(), action.data_ptr(), M, B, self._scale, self._dep_scale,
+                    u_ptr, self._seed, self._step, torch.cuda.current_stream().cuda_stream))
         self._step += 1
         return action

@@ -46,7 +46,10 @@ constexpr int kBrownItems = 4;
 __global__ void __launch_bounds__(kAgentThreads)
 brownian_forward_kernel(const double* __restrict__ agents, double* __restrict__ action,
                         int64_t M, int nchunk, double s, double dep_scale,
-                        const double* __restrict__ u, uint64_t seed, uint64_t step) {
+                        const double* __restrict__ u, uint64_t seed, uint64_t step,
+                        const uint64_t* __restrict__ step_dev) {
+    // step_dev: the call counter lives in device memory (a CUDA-graph replay cannot change a kernel argument)
+    if (step_dev != nullptr) step = *step_dev;
     const SlotChunk ch = slot_chunk<kBrownItems>(nchunk);
     const double* alive_p = agents + (ch.b * 4 + 2) * M;
     const double* ub = (u != nullptr) ? u + ch.b * 3 * M : nullptr;
@@ -126,6 +129,7 @@ struct GradientArgs {
                                 // the guard-banded turn DECISION alone: discrete turn, plan enabled, normalised)
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
+    const uint64_t* step_dev;   // may be null; else the call counter is read from device memory (CUDA-graph replays)
     int b0;                     // the launch covers environments [b0, b0 + B') of a larger batch (pointers already offset):
                                 // only the in-kernel RNG needs to know, so that chunked launches draw the same numbers
     // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
@@ -204,9 +208,10 @@ gradient_forward_kernel(const GradientArgs a) {
     // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
     const uint32_t* bits_p = MOVE ? a.alive_bits + ch.b * a.Mw + (first >> 5) : nullptr;
 
+    const uint64_t step = (a.step_dev != nullptr) ? *a.step_dev : a.step;
     uint32_t coin_bits = 0;
     if (DISCRETE_TURN && (LEAN || coin_p == nullptr))      // coin of slot (CTA, t, k) = bit k of this word
-        coin_bits = philox_draw(a.seed, a.step,
+        coin_bits = philox_draw(a.seed, step,
                                 ((uint64_t)blockIdx.x + (uint64_t)a.b0 * a.nchunk) * kAgentThreads + threadIdx.x, 2u).x;
     const double atol = p.turn_radians * p.turn_tolerance;
     // with an identity momentum step (no inertia, no noise) and a unit-length direction the new
@@ -331,7 +336,7 @@ gradient_forward_kernel(const GradientArgs a) {
                 gx += p.noise_scale * nz[i];
                 gy += p.noise_scale * nz[M + i];
             } else if (p.noise_scale != 0.0) {
-                const uint4 r = philox_draw(a.seed, a.step, (uint64_t)((ch.b + a.b0) * M + first + i), 3u);
+                const uint4 r = philox_draw(a.seed, step, (uint64_t)((ch.b + a.b0) * M + first + i), 3u);
                 const double u1 = 1.0 - u53(r.x, r.y), u2 = u53(r.z, r.w);
                 const double rad = 0.4 * sqrt(-2.0 * log(u1));
                 double sn3, cs3;

@@ -775,7 +775,20 @@ extern "C" int die_brownian_forward(const double* agents, double* action, int64_
     DIE_REQUIRE(M <= 0x7fffffffLL);
     const int nchunk = chunks_for(M, kBrownItems);
     brownian_forward_kernel<<<(unsigned)((int64_t)nchunk * B), kAgentThreads, 0, (cudaStream_t)stream>>>(
-        agents, action, M, nchunk, move_scale, deposit_scale, u, seed, step);
+        agents, action, M, nchunk, move_scale, deposit_scale, u, seed, step, nullptr);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
+extern "C" int die_brownian_forward_dev(const double* agents, double* action, int64_t M, int32_t B,
+                                        double move_scale, double deposit_scale,
+                                        uint64_t seed, const uint64_t* step_dev, void* stream) {
+    DIE_REQUIRE(agents != nullptr && action != nullptr && step_dev != nullptr);
+    DIE_REQUIRE(M >= 1 && B >= 1);
+    DIE_REQUIRE(M <= 0x7fffffffLL);
+    const int nchunk = chunks_for(M, kBrownItems);
+    brownian_forward_kernel<<<(unsigned)((int64_t)nchunk * B), kAgentThreads, 0, (cudaStream_t)stream>>>(
+        agents, action, M, nchunk, move_scale, deposit_scale, nullptr, seed, 0, step_dev);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
@@ -833,7 +846,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
                                  const uint8_t* coin, const double* noise, int32_t* sense_cells,
                                  const double* grad_hint, const int32_t* cells_hint,
                                  uint64_t seed, uint64_t step, void* stream, int b0 = 0,
-                                 const float2* grad32_hint = nullptr) {
+                                 const float2* grad32_hint = nullptr, const uint64_t* step_dev = nullptr) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -856,6 +869,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     if (grad_hint == nullptr && grad32_hint != nullptr && p->discrete_turn && a.plan.enabled && p->normalized_grad)
         a.grad32 = grad32_hint;
     a.seed = seed; a.step = step;
+    a.step_dev = step_dev;
     a.b0 = b0;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     cudaStream_t st = (cudaStream_t)stream;
@@ -926,8 +940,11 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
     const double* grad_hint = (flags & DIE_FWD_USE_GRADIENT) ? die_env_gradient(e) : nullptr;
     const float2* grad32_hint = ((flags & DIE_FWD_USE_GRADIENT) && die_env_gradient_kind(e) == 2) ? e->grad32 : nullptr;
     const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;
+    // DIE_FWD_STEP_ON_DEVICE: `step` is the device address of a uint64 call counter (CUDA-graph replays)
+    const uint64_t* step_dev = (flags & DIE_FWD_STEP_ON_DEVICE) ? (const uint64_t*)(uintptr_t)step : nullptr;
     return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
-                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream, 0, grad32_hint);
+                                 coin, noise, sense_cells, grad_hint, cells_hint, seed, step_dev ? 0 : step, stream, 0,
+                                 grad32_hint, step_dev);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -192,6 +192,10 @@ int die_render_frames(int32_t H, int32_t W, int64_t M, int32_t B,
 int die_brownian_forward(const double* agents_dev, double* action_dev, int64_t M, int32_t B,
                          double move_scale, double deposit_scale,
                          const double* u_dev, uint64_t seed, uint64_t step, void* stream);
+/* The same with in-kernel draws only and the call counter read from device memory (see DIE_FWD_STEP_ON_DEVICE). */
+int die_brownian_forward_dev(const double* agents_dev, double* action_dev, int64_t M, int32_t B,
+                             double move_scale, double deposit_scale, uint64_t seed,
+                             const uint64_t* step_dev, void* stream);
 
 /* ConstAgent.forward, core/agent/static.py:19-28 (not alive-masked). */
 int die_const_forward(double* action_dev, int64_t M, int32_t B,
@@ -251,6 +255,10 @@ int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient_params_t* 
 #define DIE_FWD_USE_GRADIENT    1
 #define DIE_FWD_USE_CELLS       2
 #define DIE_FWD_SPECULATE_MOVE  4
+/*   DIE_FWD_STEP_ON_DEVICE  `step` is not the call counter but the DEVICE ADDRESS of a uint64 holding it: a CUDA graph
+ *                           that captured this call can be replayed while something else (a captured increment) advances
+ *                           the counter, so every replay draws fresh in-kernel random numbers (die_b200/graph.py) */
+#define DIE_FWD_STEP_ON_DEVICE  8
 int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
                              const double* agents_dev, const double* medium_dev,
                              double* theta_dev, double* prev_grad_dev, double* action_dev,

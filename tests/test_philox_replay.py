@@ -72,3 +72,37 @@ def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, bat
             assert np.array_equal(ref_cells_linear(refs[b]), env.cells()[b])
             assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
     assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + iters - 1, "the benchmarked instantiation must be the one compared"
+
+
+def test_call_counter_in_device_memory_draws_the_same_numbers():
+    """DIE_FWD_STEP_ON_DEVICE / die_brownian_forward_dev (die_b200/graph.py: a CUDA-graph replay cannot change a kernel
+    argument, so the call counter is read from memory): identical draws to the counter passed by value."""
+    import ctypes as C
+    from die_b200 import _lib as L
+    lib = S.lib()
+    (ref,), env = make_pair((24, 64), seed=2)
+    counter = S.fenced((1,), np.uint64, fill=0)
+    for step in (0, 5):
+        counter[0] = step
+        a = S.brownian_forward(env.agents, move_scale=0.02, seed=11, step=step)
+        agents = S.fenced_copy(env.agents)
+        action = S.fenced((1, 3, env.M), fill=np.nan)
+        S.check(lib.die_brownian_forward_dev(S.ptr(agents), S.ptr(action), env.M, 1, 0.02, 0.5, 11, S.ptr(counter), None))
+        assert np.array_equal(a, action)
+    outs = []
+    for on_device in (False, True):
+        (ref,), env = make_pair((24, 64), seed=2)
+        ga = S.SimGradientAgent(env.M, seed=3, **PHYS)
+        ga.theta[0] = lattice_theta(env.M, 30, 2)[0]
+        for it in range(4):
+            env.want_gradient()
+            flags = (L.FWD_USE_CELLS | L.FWD_USE_GRADIENT) if it > 0 else 0
+            counter[0] = it
+            step_arg = S.ptr(counter) if on_device else it
+            S.check(lib.die_env_forward_gradient(env.handle, C.byref(ga.p), S.ptr(env.agents), S.ptr(env.medium), S.ptr(ga.theta),
+                                                 None, S.ptr(ga.action), None, None, None,
+                                                 flags | (L.FWD_STEP_ON_DEVICE if on_device else 0), 3, step_arg, None))
+            env.step(ga.action)
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
