@@ -272,8 +272,25 @@ def steady_state_leg(torch, meas, checkpoints, window=40):
         torch.cuda.synchronize()
         done = cp
         out[str(cp)] = round(e0.elapsed_time(e1) / window, 5)
+    kernels = None
+    if out:                                              # which kernel pays: the per-kernel breakdown at the last checkpoint
+        env.set_profiling(True)
+        fwd = []
+        for _ in range(window):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            action = agent.forward(obs)
+            a1.record()
+            obs, _, _ = env.step_async(action)
+            fwd.append((a0, a1))
+        torch.cuda.synchronize()
+        kms, nprof = env.kernel_times()
+        env.set_profiling(False)
+        done += window
+        kernels = {"physarum_forward": round(sum(a.elapsed_time(b) for a, b in fwd) / window, 5)}
+        kernels.update({k: round(v / max(nprof, 1), 5) for k, v in kms.items()})
     meas["obs"], meas["steps_done"] = obs, done
-    return out
+    return out, kernels
 
 
 def small_env_leg(D, torch, device, agent_name, iters=300, warmup=20, cpu_iters=20):
@@ -336,13 +353,87 @@ def small_env_leg(D, torch, device, agent_name, iters=300, warmup=20, cpu_iters=
     return out
 
 
-def e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus):
-    """Experimental (--e2e-workers W, off by default, NOT yet measured on a GPU): the host-buffer loop driven by W host
-    threads, each with its own Env / Agent over B_e2e / W environments and its own CUDA stream.  One thread's
-    Agent.forward (upload-heavy: the observation) then overlaps another's Env.step (download-heavy), so both PCIe
-    directions carry data all the time instead of taking turns.  Same public calls, same bytes per environment."""
+def host_pinned_budget_envs(field, M, frac=0.35):
+    """How many environments' host buffers (pinned: obs x2 + action + agents) fit in `frac` of the available host memory."""
+    C = field[0] * field[1]
+    per_env = 8 * (2 * 3 * C + 4 * M + 3 * M) + 8 * (4 * M + 3 * C)      # env + agent pinned buffers, first host copy of obs
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    return max(1, int(avail * frac // per_env))
+
+
+def e2e_leg(D, torch, dist, args, field, B_local, batched, device, rank, world, M, C, n_gpus):
+    """The metric measured end to end through the public API with HOST buffers: numpy observation in, numpy action out of
+    Agent.forward; numpy action in, numpy observation + reward out of Env.step; every byte crosses PCIe inside the timed
+    region.  On the FULL per-GPU batch (bounded only by pinned host memory; `envs_per_gpu` says what ran).
+    The two calls are synchronous, so one caller thread keeps only one PCIe direction busy at a time (forward uploads
+    7 doubles per slot and downloads 3, step the reverse): `value` is therefore measured with `workers` caller threads,
+    each stepping its own share of the environments through the same two calls; the single-thread figure is reported
+    beside it."""
+    from die_b200.sharding import max_over_ranks
+    B_e2e = B_local if batched else 1
+    if args.e2e_envs > 0:
+        B_e2e = min(B_e2e, args.e2e_envs)
+    B_e2e = max(1, min(B_e2e, host_pinned_budget_envs(field, M)))
+    k_e2e = max(3, min(args.steps, args.e2e_steps))
+    W = max(1, min(args.e2e_workers, B_e2e))
+    out = {"unit": UNIT, "steps": k_e2e, "envs_per_gpu": B_e2e,
+           "api": "numpy obs/action across Agent.forward (die_gradient_forward_host) and Env.step (die_env_step_host / "
+                  "die_env_step_host_dev: the action is not uploaded again when it is the array forward just returned), "
+                  "each call cut into chunks on two streams; pinned host memory"}
+    # -- one caller thread
+    env, agent, _ = make_env_and_agent(D, torch, field, B_e2e, batched, device, rank, 50)
+    hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
+    for _ in range(2):                                   # warm the pinned staging buffers
+        hobs, *_ = env.step(agent.forward(hobs))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start = time.perf_counter()
+    for _ in range(k_e2e):
+        hact = agent.forward(hobs)                       # H2D obs, kernel, D2H action
+        hobs, hr, _, _, _ = env.step(hact)               # (H2D action,) kernels, D2H obs + reward
+    torch.cuda.synchronize()
+    t_one = max_over_ranks(time.perf_counter() - t_start, device)
+    h2d_step, d2h_step = env.host_io_bytes_per_step()
+    fwd_h2d = 8 * B_e2e * (4 * M + 3 * C)
+    fwd_d2h = 8 * B_e2e * 3 * M
+    h2d, d2h = (h2d_step + fwd_h2d) * n_gpus, (d2h_step + fwd_d2h) * n_gpus
+    one = {"value": C * B_e2e * n_gpus * k_e2e / t_one, "ms_per_step": t_one / k_e2e * 1e3,
+           "h2d_gbs_per_gpu": round(h2d / n_gpus / (t_one / k_e2e) / 1e9, 1),
+           "d2h_gbs_per_gpu": round(d2h / n_gpus / (t_one / k_e2e) / 1e9, 1),
+           "action_reupload_skipped": bool(getattr(env, "last_step_reused_device_action", False))}
+    out.update({"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h})
+    del env, agent, hobs, hact
+    torch.cuda.empty_cache()
+    if W > 1 and batched:
+        wk = e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus, W)
+        if "error" not in wk:
+            t_w = wk["ms_per_step"] * 1e-3
+            out.update({"value": wk["value"], "ms_per_step": wk["ms_per_step"], "workers": W,
+                        "envs_per_gpu": wk["envs_per_worker"] * W,
+                        "h2d_bytes_per_step": h2d * wk["envs_per_worker"] * W // B_e2e,
+                        "d2h_bytes_per_step": d2h * wk["envs_per_worker"] * W // B_e2e,
+                        "h2d_gbs_per_gpu": round(h2d / n_gpus * wk["envs_per_worker"] * W / B_e2e / t_w / 1e9, 1),
+                        "d2h_gbs_per_gpu": round(d2h / n_gpus * wk["envs_per_worker"] * W / B_e2e / t_w / 1e9, 1),
+                        "one_caller_thread": one})
+            return out
+        out["workers_error"] = wk["error"]
+    out.update({"value": one["value"], "ms_per_step": one["ms_per_step"], "workers": 1,
+                "h2d_gbs_per_gpu": one["h2d_gbs_per_gpu"], "d2h_gbs_per_gpu": one["d2h_gbs_per_gpu"],
+                "action_reupload_skipped": one["action_reupload_skipped"]})
+    return out
+
+
+def e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus, W):
+    """The host-buffer loop driven by W host threads, each with its own Env / Agent over B_e2e / W environments and its
+    own CUDA stream.  One thread's Agent.forward (upload-heavy: the observation) then overlaps another's Env.step
+    (download-heavy), so both PCIe directions carry data all the time instead of taking turns.  Same public calls,
+    same bytes per environment (the library calls release the GIL)."""
     import threading
-    W = args.e2e_workers
     per = B_e2e // W
     pairs = [make_env_and_agent(D, torch, field, per, True, device, rank, 60 + w)[:2] for w in range(W)]
     streams = [torch.cuda.Stream(device=device) for _ in range(W)]
@@ -495,7 +586,11 @@ def run_die_b200(args):
                          "use --impl reference for the CPU path")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bound_cpus = None
     if world > 1:
+        from die_b200.sharding import bind_rank_to_gpu_cores
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        bound_cpus = bind_rank_to_gpu_cores(local_rank, local_world)     # cores (and first-touch memory) next to this GPU
         dist.init_process_group("nccl", device_id=device)
     n_gpus = world
     if args.gpus != n_gpus and rank == 0:
@@ -548,7 +643,8 @@ def run_die_b200(args):
         f2 = (args.field, args.field)
         m2 = measure(D, torch, dist, args, f2, 1, False, device, rank, world, want_clocks=False)
         r2, sb2 = roofline_of(m2, 1, "physarum_single_field_%dx%d" % f2)
-        steady = steady_state_leg(torch, m2, [int(c) for c in args.steady.split(",") if c]) if args.steady else {}
+        steady, steady_kernels = steady_state_leg(torch, m2, [int(c) for c in args.steady.split(",") if c]) \
+            if args.steady else ({}, None)
         C2 = f2[0] * f2[1]
         entry = {"value": C2 / (m2["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m2["ms_per_step"],
                  "measured_at_steps": [args.warmup, args.warmup + args.steps],
@@ -557,7 +653,7 @@ def run_die_b200(args):
             last = steady[max(steady, key=int)]
             step_b = r2["step"]["algorithmic_bytes"]
             entry["steady_state"] = {
-                "ms_per_step_in_the_40_steps_before_step": steady,
+                "ms_per_step_in_the_40_steps_before_step": steady, "kernel_ms_after_last": steady_kernels,
                 "value_at_last": C2 / (last * 1e-3), "unit": UNIT,
                 "frac_at_last": round(step_b / (last * 1e-3) / 1e9 / r2["peak"], 4),
                 "frac_of_8TBs_nominal_at_last": round(step_b / (last * 1e-3) / 1e9 / 8000.0, 4),
@@ -585,36 +681,7 @@ def run_die_b200(args):
     # ---- e2e: the same loop through the host-buffer API (numpy obs/action cross PCIe every call) ----
     e2e = None
     if not args.no_e2e:
-        B_e2e = min(B_local, args.e2e_envs) if batched else 1
-        env, agent, _ = make_env_and_agent(D, torch, field, B_e2e, batched, device, rank, 50)
-        k_e2e = max(3, min(args.steps, args.e2e_steps))
-        hobs = tuple(t.cpu().numpy() for t in env._get_current_obs)
-        for _ in range(2):                                   # warm the pinned staging buffers
-            hact = agent.forward(hobs)
-            hobs, *_ = env.step(hact)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t_start = time.perf_counter()
-        for _ in range(k_e2e):
-            hact = agent.forward(hobs)                       # H2D obs, kernel, D2H action
-            hobs, hr, _, _, _ = env.step(hact)               # H2D action, kernels, D2H obs + reward
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t_start
-        from die_b200.sharding import max_over_ranks
-        t_e2e = max_over_ranks(t_e2e, device)
-        h2d_step, d2h_step = env.host_io_bytes_per_step()
-        fwd_h2d = 8 * B_e2e * (4 * M + 3 * C)
-        fwd_d2h = 8 * B_e2e * 3 * M
-        e2e = {"value": C * B_e2e * n_gpus * k_e2e / t_e2e, "unit": UNIT, "steps": k_e2e,
-               "ms_per_step": t_e2e / k_e2e * 1e3, "envs_per_gpu": B_e2e,
-               "h2d_bytes_per_step": (h2d_step + fwd_h2d) * n_gpus, "d2h_bytes_per_step": (d2h_step + fwd_d2h) * n_gpus,
-               "api": "numpy obs/action across Agent.forward (die_gradient_forward_host) and Env.step (die_env_step_host), "
-                      "batch cut into chunks on two streams so both PCIe directions stay busy; PCIe-bound, so measured "
-                      "on a bounded number of envs per GPU (pinned host memory)"}
-        del env, agent
-        if args.e2e_workers > 1 and batched:
-            e2e["workers"] = e2e_workers_leg(D, torch, dist, args, field, B_e2e, device, rank, world, k_e2e, C, n_gpus)
+        e2e = e2e_leg(D, torch, dist, args, field, B_local, batched, device, rank, world, M, C, n_gpus)
 
     # ---- CPU baseline: the oracle on this host, rank 0, N = 1 only ------------------------------------
     cpu = None
@@ -639,6 +706,7 @@ def run_die_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "also": also,
             "gpu_launches": args.steps * launches, "launches_per_step": launches,
             "fused_move": meas["fused"], "tuning": ARGS.tune, "clocks": meas["clocks"],
+            "host": {"cpus": os.cpu_count(), "rank0_bound_to_cpus": bound_cpus},
             "setup_s": round(setup_s, 1),
         }
         print(json.dumps(line))
@@ -737,8 +805,10 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "field4096", "batch256", "slab"])
     ap.add_argument("--field", type=int, default=4096, help="side of the single field (field4096 workload)")
     ap.add_argument("--batch", type=int, default=4096, help="total number of 256x256 envs (batch256 workload)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-envs", type=int, default=128, help="envs per GPU on the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-envs", type=int, default=0,
+                    help="cap on the envs per GPU of the host-buffer (e2e) leg (0 = the full per-GPU batch, bounded by "
+                         "35 %% of the available host memory for pinned buffers)")
     ap.add_argument("--no-single-field", action="store_true")
     ap.add_argument("--no-small-env", action="store_true", help="skip the configs[0] / configs[1] legs (one 256x256 env)")
     ap.add_argument("--steady", default="300,3000", help="single field: also report ms/step in the 40 steps before these "
@@ -751,8 +821,8 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=None, help="CPU processes (default: all host cores)")
     ap.add_argument("--corner-r", type=int, default=512, help="slab workload: side of the mirrored corner patches (0 = off)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=1,
-                    help="experimental: also time the host-buffer loop driven by this many host threads (see e2e_workers_leg)")
+    ap.add_argument("--e2e-workers", type=int, default=4,
+                    help="caller threads of the host-buffer (e2e) leg, each stepping its own share of the envs (1 = one thread)")
     ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")

@@ -32,3 +32,32 @@ def find_env(agents, medium):
     if medium.numel() != buf.numel() or medium.shape[-2:] != buf.shape[-2:] or agents.numel() != env._agents.numel():
         return None
     return env
+
+
+# ---- host-buffer path: the action array Agent.forward returned, and its device copy -------------------------------
+# Agent.forward(host obs) returns a READ-ONLY numpy view of a pinned buffer whose content was just downloaded from the
+# agent's device action tensor.  If Env.step receives that very array (same address, still read-only) and the device
+# tensor has not been written since (torch version counter), the step reads the device copy: no H2D of the action.
+# A caller who wants to edit the action has to copy it (the array is read-only) -- and a copy takes the upload path.
+_HOST_ACTIONS = {}      # host address -> (weakref(device tensor), version, nbytes)
+
+
+def register_host_action(host_array, device_tensor) -> None:
+    if len(_HOST_ACTIONS) > 256:
+        for key in [k for k, (r, _, _) in _HOST_ACTIONS.items() if r() is None]:
+            del _HOST_ACTIONS[key]
+    _HOST_ACTIONS[host_array.ctypes.data] = (weakref.ref(device_tensor), device_tensor._version, host_array.nbytes)
+
+
+def device_copy_of(host_array, device):
+    """The device tensor `host_array` was downloaded from, if that is provably still its content; else None."""
+    if host_array.flags.writeable:
+        return None
+    entry = _HOST_ACTIONS.get(host_array.ctypes.data)
+    if entry is None:
+        return None
+    ref, version, nbytes = entry
+    t = ref()
+    if t is None or t._version != version or nbytes != host_array.nbytes or t.device != device:
+        return None
+    return t

@@ -79,6 +79,7 @@ SIGNATURES = {
     "die_env_kernel_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "die_env_read_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_env_step_host_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_sense_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "die_render_frames": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, C.c_double, _P, _P, _P, _P]),
     "die_brownian_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P,

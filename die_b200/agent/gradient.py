@@ -149,7 +149,7 @@ class GradientAgent(_DeviceAgent):
             hb = self._host = {
                 'agents': torch.empty(agents_np.shape, dtype=torch.float64, device=dev),
                 'medium': torch.empty(medium_np.shape, dtype=torch.float64, device=dev),
-                'action': torch.empty((*agents_np.shape[:-2], 3, agents_np.shape[-1]), dtype=torch.float64).pin_memory(),
+                'action': torch.empty((*agents_np.shape[:-2], 3, agents_np.shape[-1]), dtype=torch.float64, pin_memory=True),
             }
         if getattr(self, '_host_ctx', None) is None:
             ctx = _lib.C.c_void_p()
@@ -241,7 +241,11 @@ class GradientAgent(_DeviceAgent):
                     torch.cuda.current_stream().cuda_stream))
             self.last_hints, self.last_speculated = (False, False), False
             self._step += 1
-            return hb['action'].numpy()
+            torch.autograd.graph.increment_version(action)     # the kernel wrote it through its raw pointer
+            out = hb['action'].numpy()
+            out.flags.writeable = False        # Env.step may then use the device copy instead of uploading it again
+            _hints.register_host_action(out, action)
+            return out
         # The Env that produced this observation, if it provably did (die_b200/_hints.py): its cached cells and
         # published gradient replace gathers, and the move of the action is evaluated in the same launch.
         env = _hints.find_env(agents, medium) if self.use_env_hints else None

@@ -4,6 +4,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
+from .. import _hints
 from .. import _lib
 from ..base_types import ActType, ObsType
 from .base import Agent
@@ -52,7 +53,7 @@ class _DeviceAgent(Agent):
                 'agents': torch.empty(agents_np.shape, dtype=torch.float64, device=dev),
                 'medium': torch.empty(medium_np.shape, dtype=torch.float64, device=dev),
                 'action': torch.empty((*agents_np.shape[:-2], 3, agents_np.shape[-1]),
-                                      dtype=torch.float64).pin_memory(),
+                                      dtype=torch.float64, pin_memory=True),
             }
         hb = self._host
         hb['agents'].copy_(torch.from_numpy(agents_np), non_blocking=True)
@@ -60,7 +61,10 @@ class _DeviceAgent(Agent):
         action = self.forward((hb['agents'], hb['medium']))
         hb['action'].copy_(action, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return hb['action'].numpy()
+        out = hb['action'].numpy()
+        out.flags.writeable = False            # Env.step may then use the device copy instead of uploading it again
+        _hints.register_host_action(out, action)
+        return out
 
 
 class ConstAgent(_DeviceAgent):
@@ -80,6 +84,7 @@ class ConstAgent(_DeviceAgent):
         with _lib.on_device(agents.device):
             _lib.check(self._lib.die_const_forward(action.data_ptr(), M, B, *self._data,
                                                    torch.cuda.current_stream().cuda_stream))
+        torch.autograd.graph.increment_version(action)      # written through its raw pointer: tell torch's version counter
         return action
 
 
@@ -142,4 +147,5 @@ class BrownianAgent(_DeviceAgent):
                     agents.data_ptr(), action.data_ptr(), M, B, self._scale, self._dep_scale,
                     u_ptr, self._seed, self._step, torch.cuda.current_stream().cuda_stream))
         self._step += 1
+        torch.autograd.graph.increment_version(action)      # written through its raw pointer: tell torch's version counter
         return action

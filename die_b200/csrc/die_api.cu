@@ -647,16 +647,18 @@ extern "C" int die_env_read_stats(die_env_t* e, const double* reward_dev, const 
 static int g_host_chunks = 4;
 static size_t g_host_chunk_min_bytes = (size_t)32 << 20;   // below this a call is not worth chunking
 
-extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
-                                 double* agents, const double* action_host,
-                                 double* agents_host, double* medium_host,
-                                 double* reward_host, int64_t* alive_host, void* stream) {
-    DIE_REQUIRE(e != nullptr && action_host != nullptr);
+static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_out,
+                              double* agents, const double* action_host, const double* action_dev,
+                              double* agents_host, double* medium_host,
+                              double* reward_host, int64_t* alive_host, void* stream) {
+    DIE_REQUIRE(e != nullptr && (action_host != nullptr) != (action_dev != nullptr));
     DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out && agents != nullptr);
     DIE_REQUIRE(reward_host != nullptr && alive_host != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
-    if (e->action_stage == nullptr) DIE_CUDA(cudaMalloc(&e->action_stage, sizeof(double) * 3 * M * e->B));
+    if (action_dev == nullptr && e->action_stage == nullptr)
+        DIE_CUDA(cudaMalloc(&e->action_stage, sizeof(double) * 3 * M * e->B));
+    const double* action = action_dev != nullptr ? action_dev : e->action_stage;
     if (e->pending_move) {
         if (int rc = die_env_discard_move(e, stream)) return rc;
     }
@@ -676,9 +678,10 @@ extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium
         const int nb = b1 - b0;
         cudaStream_t s = (nchunks > 1) ? e->host_streams[k & 1] : st;
         if (nchunks > 1 && k < 2) DIE_CUDA(cudaStreamWaitEvent(s, e->host_events[2], 0));
-        DIE_CUDA(cudaMemcpyAsync(e->action_stage + (size_t)b0 * 3 * M, action_host + (size_t)b0 * 3 * M,
-                                 sizeof(double) * 3 * M * nb, cudaMemcpyHostToDevice, s));
-        if (int rc = env_step_range(e, b0, nb, medium_in, medium_out, agents, e->action_stage, e->reward_dev, e->alive_dev,
+        if (action_dev == nullptr)
+            DIE_CUDA(cudaMemcpyAsync(e->action_stage + (size_t)b0 * 3 * M, action_host + (size_t)b0 * 3 * M,
+                                     sizeof(double) * 3 * M * nb, cudaMemcpyHostToDevice, s));
+        if (int rc = env_step_range(e, b0, nb, medium_in, medium_out, agents, action, e->reward_dev, e->alive_dev,
                                     false, nullptr, false, s))
             return rc;
         if (agents_host != nullptr)
@@ -699,6 +702,22 @@ extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium
     if (e->flow_rwave != nullptr || e->flow_frames != nullptr) ++e->flow_k;
     DIE_CUDA(cudaStreamSynchronize(st));
     return DIE_OK;
+}
+
+extern "C" int die_env_step_host(die_env_t* e, double* medium_in, double* medium_out,
+                                 double* agents, const double* action_host,
+                                 double* agents_host, double* medium_host,
+                                 double* reward_host, int64_t* alive_host, void* stream) {
+    return env_step_host_impl(e, medium_in, medium_out, agents, action_host, nullptr, agents_host, medium_host,
+                              reward_host, alive_host, stream);
+}
+
+extern "C" int die_env_step_host_dev(die_env_t* e, double* medium_in, double* medium_out,
+                                     double* agents, const double* action_dev,
+                                     double* agents_host, double* medium_host,
+                                     double* reward_host, int64_t* alive_host, void* stream) {
+    return env_step_host_impl(e, medium_in, medium_out, agents, nullptr, action_dev, agents_host, medium_host,
+                              reward_host, alive_host, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -468,11 +468,11 @@ class Env:
         if self._host is None:
             B, M = self._B, self._M
             h, w = self._field_size
-            mk = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
+            mk = lambda *s: torch.empty(s, dtype=torch.float64, pin_memory=True)
             self._host = {
                 'action': mk(B, 3, M), 'agents': mk(B, 4, M),
                 'medium': [mk(B, 3, h, w), mk(B, 3, h, w)], 'flip': 0,
-                'reward': mk(B), 'alive': torch.empty(B, dtype=torch.int64).pin_memory(),
+                'reward': mk(B), 'alive': torch.empty(B, dtype=torch.int64, pin_memory=True),
             }
         return self._host
 
@@ -482,6 +482,11 @@ class Env:
         # the library copies straight from the caller's array (cudaMemcpyAsync: full speed if it is pinned --
         # e.g. the array an Agent's host path returned -- staged by the driver if it is pageable); no host memcpy
         src = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(B, 3, M))
+        # the very (read-only) array an Agent's host path just returned, its device copy untouched since: no re-upload
+        dev_action = _hints.device_copy_of(action, self.device) if isinstance(action, np.ndarray) else None
+        if dev_action is not None and dev_action.numel() != 3 * B * M:
+            dev_action = None
+        self.last_step_reused_device_action = dev_action is not None
         hb['flip'] ^= 1
         med_t = hb['medium'][hb['flip']]
         nxt = 1 - self._cur
@@ -489,9 +494,10 @@ class Env:
         self.last_step_fused = False
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(self._lib.die_env_step_host(
+            fn = self._lib.die_env_step_host if dev_action is None else self._lib.die_env_step_host_dev
+            _lib.check(fn(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
-                self._agents.data_ptr(), src.ctypes.data,
+                self._agents.data_ptr(), src.ctypes.data if dev_action is None else dev_action.data_ptr(),
                 hb['agents'].data_ptr(), med_t.data_ptr() if self._obs_buf is None else None,
                 hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
         self._cur = nxt
@@ -506,10 +512,11 @@ class Env:
         return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))
 
     def host_io_bytes_per_step(self) -> Tuple[int, int]:
-        """(H2D, D2H) bytes one host-path ``step`` moves."""
+        """(H2D, D2H) bytes the last host-path ``step`` moved (no H2D when it re-used the agent's device action)."""
         B, M = self._B, self._M
         h, w = self._field_size
-        return 8 * B * 3 * M, 8 * B * (4 * M + 3 * h * w) + 16 * B
+        h2d = 0 if getattr(self, 'last_step_reused_device_action', False) else 8 * B * 3 * M
+        return h2d, 8 * B * (4 * M + 3 * h * w) + 16 * B
 
     # -- measurement aid ----------------------------------------------------------------------
     STEP_KERNELS = ('move_claim', 'field_step', 'agent_feed', 'finalize_stats')

@@ -166,6 +166,12 @@ int die_env_step_host(die_env_t* env, double* medium_in_dev, double* medium_out_
                       double* agents_dev, const double* action_host,
                       double* agents_host, double* medium_host,
                       double* reward_host, int64_t* alive_host, void* stream);
+/* The same step when the action is ALREADY on the device -- the host array handed to Env.step is the very (read-only)
+ * array Agent.forward's host path returned and its device copy is still valid: no H2D of the action. */
+int die_env_step_host_dev(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+                          double* agents_dev, const double* action_dev,
+                          double* agents_host, double* medium_host,
+                          double* reward_host, int64_t* alive_host, void* stream);
 
 /* Env._get_sensed_medium with Dynamics.apply_sense_mask (core/env.py:275-294): the observation's medium is
  *     medium.where(ceil(round(gaussian(medium['agents'], sigma=2.0), 3)), other=0.)
