@@ -23,6 +23,7 @@ class DieDynamics(C.Structure):
         ("boundary", C.c_int32),
         ("food_infinite", C.c_int32),
         ("diffuse_mode", C.c_int32),
+        ("agents_die", C.c_int32),
     ]
 
 

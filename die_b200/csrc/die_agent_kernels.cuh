@@ -433,7 +433,7 @@ struct FeedArgs {
     const double* action;
     const double* consumed_field;    // [B][C] rate_feed * food * occ of this step (the field pass wrote it)
     int32_t* winner;
-    const int32_t* cells;
+    int32_t* cells;                  // read; DIE also resets the cached cell of a slot it puts back at (0, 0)
     double* part_gain;
     int32_t* part_alive;
     int64_t C, M;
@@ -444,7 +444,10 @@ struct FeedArgs {
     int boundary;
 };
 
-template <bool SLAB, bool MOVE, bool BITS>
+// DIE: Dynamics.agents_die -- Env._agent_lifecycle (core/env.py:245-250) folded in: a slot whose stock after feeding is
+// not above 1e-4 has ALL its channels zeroed (agents.where(agent_food > 1e-4, 0): dead, back at (0, 0), no stock), which
+// holds for every ghost slot every step; num_agents counts the survivors (core/env.py:118, after the lifecycle).
+template <bool SLAB, bool MOVE, bool BITS, bool DIE = false>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const int64_t M = a.M;
@@ -456,7 +459,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const double* __restrict__ ac = a.action + b * 3 * M + first;
     const double* __restrict__ cf = SLAB ? nullptr : a.consumed_field + b * a.C;
     int32_t* __restrict__ win = a.winner + b * a.C;
-    const int32_t* __restrict__ cl = a.cells + b * M + first;
+    int32_t* __restrict__ cl = a.cells + b * M + first;
     const uint32_t* __restrict__ bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
     const double w_dep = a.w_dep, w_dist = a.w_dist;
     const int boundary = a.boundary;
@@ -499,12 +502,23 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
             }
             const double burned = w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
             const double gained = eaten[k] - burned;
-            ag_x[3 * M + i] = stock[k] + gained;
+            const double stock_new = stock[k] + gained;
             gain_sum += gained;
+            bool survives = true;
+            if (DIE) {
+                survives = stock_new > 1e-4;
+                if (!survives) {                   // every channel of the slot <- 0 (core/env.py:249-250)
+                    ag_x[i] = 0.0;
+                    ag_x[M + i] = 0.0;
+                    ag_x[2 * M + i] = 0.0;
+                    cl[i] = 0;                     // the cell of (0, 0): the next forward's cached "cell under the agent"
+                }
+            }
+            ag_x[3 * M + i] = survives ? stock_new : 0.0;
             if (alive[k]) {                        // claim table back to empty for the next step
                 if (SLAB) *slab_cell(st.claim, sg, cell[k]) = -1;
                 else win[cell[k]] = -1;
-                ++alive_cnt;
+                if (survives) ++alive_cnt;
             }
         }
     }

@@ -530,6 +530,13 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     int32_t* part_alive = e->part_alive + (size_t)b0 * e->nblk;
     if (alive_bits != nullptr) alive_bits += (size_t)b0 * e->Mw;
 
+    if (e->dyn.agents_die) {
+        // the lifecycle changes the alive channel every step: the cached bitmask is never valid, and a move evaluated
+        // speculatively by the forward kernel used the bitmask
+        if (fused) return fail(DIE_E_INVALID, "agents_die and a speculative move do not combine%s%s");
+        alive_bits = nullptr;
+        e->alive_valid = 0;
+    }
     if (profile) prof_mark(e, 0, st);
     if (!fused && g_step_impl == 1) {
         int done = 0;
@@ -557,6 +564,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
     auto feed = fused ? agent_feed_kernel<false, true, true>
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
+    if (e->dyn.agents_die) feed = agent_feed_kernel<false, false, false, true>;
     FeedArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.agents = agents; fa.action = action;

@@ -117,9 +117,6 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
                                   "evaluated inside the CUDA field kernel, arbitrary Python operators are not supported")
     if d.diffuse_mode not in _lib.DIFFUSE_MODES:
         raise ValueError(f"diffuse_mode must be one of {sorted(_lib.DIFFUSE_MODES)} (scipy.ndimage's modes)")
-    if d.agents_die:
-        raise NotImplementedError("agents_die is off by default in the reference (and broken there: core/env.py:250 "
-                                  "rebinds self.agents while AgentIndexer keeps the old array) -- not on the GPU path")
     c = _lib.DieDynamics()
     c.rate_feed = d.rate_feed
     c.rate_decay_chem = d.rate_decay_chem
@@ -140,6 +137,9 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
         c.boundary = _lib.BOUNDARY_NONE
     c.food_infinite = int(bool(d.food_infinite))
     c.diffuse_mode = _lib.DIFFUSE_MODES[d.diffuse_mode]
+    # core/env.py:245-250 with the AgentIndexer following the rebound array (the reference's own version does not):
+    # semantics pinned in oracle/die_ref.py:_agent_lifecycle and tests/test_golden_oracle.py
+    c.agents_die = int(bool(d.agents_die))
     return c
 
 
@@ -235,6 +235,7 @@ class Env:
             cdyn = _dynamics_to_c(self.dynamics)
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
+            self._dynamics_key = self._dynamics_snapshot()
             self._install_food_flow()
             # Dynamics.apply_sense_mask: the observation is a masked COPY of the medium (core/env.py:275-294)
             self._obs_buf = None
@@ -258,8 +259,22 @@ class Env:
         if tuple(op.sequence._size) != tuple(self._field_size):
             raise ValueError(f"the {type(op.sequence).__name__} was built for field {op.sequence._size}, the env is {self._field_size}")
         if not _is_wave_flow(op):
-            # no closed form on the device: the frames of every time step, tabulated by the sequence's own code
-            frames = torch.from_numpy(op.sequence.frames()).to(self.device)
+            # no closed form on the device: the frames of every time step, tabulated by the sequence's own code.
+            # T x H x W float64 on the host AND the device: refuse by name what cannot fit (the base-class defaults,
+            # t_bounds = (0, 10) and dt = 0.01, mean T = 1000: 0.5 GB at 256^2, 134 GB at 4096^2), and keep the device
+            # copy across reset() (the frames do not change)
+            seq = op.sequence
+            nbytes = 8 * len(seq._ts) * self._field_size[0] * self._field_size[1]
+            cached = getattr(seq, '_die_device_frames', None)
+            if cached is None or cached.device != self.device:
+                free, _total = torch.cuda.mem_get_info(self.device)
+                if nbytes > 0.5 * free or nbytes > (32 << 30):
+                    raise MemoryError(
+                        f"{type(seq).__name__}: tabulating {len(seq._ts)} frames of {self._field_size[0]}x{self._field_size[1]} "
+                        f"needs {nbytes / 2**30:.1f} GiB on the host and on the device ({free / 2**30:.1f} GiB free); use a "
+                        f"larger dt / shorter t_bounds, a TabulatedSequence of fewer frames, or the WaveSequence (closed form)")
+                seq._die_device_frames = torch.from_numpy(seq.frames()).to(self.device)
+            frames = seq._die_device_frames
             self._flow_tables = [frames]               # borrowed by the library until the handle dies
             _lib.check(self._lib.die_env_set_food_frames(
                 self._handle, frames.data_ptr(), frames.shape[0], op.calls % frames.shape[0], op.scale, op.decay))
@@ -271,6 +286,44 @@ class Env:
         _lib.check(self._lib.die_env_set_food_flow(
             self._handle, tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
             ts.ctypes.data, len(ts), op.calls % len(ts), op.scale, op.decay))
+
+    def _dynamics_snapshot(self):
+        d = self.dynamics
+        return (d.op_action_cost, d.op_food_flow, d.rate_feed, d.rate_decay_chem, d.boundary, d.diffuse_mode,
+                d.diffuse_sigma, d.apply_sense_mask, d.food_infinite, d.agents_die)
+
+    def _sync_dynamics(self) -> None:
+        """The reference reads ``self.dynamics`` on every step (core/env.py:136-150, 220-250), so a caller may change a
+        field between steps (or assign a new Dynamics).  The library holds a snapshot: compare, and on a change hand it the
+        new parameters (die_env_set_dynamics), re-install the food flow tables and (de)allocate the masked observation."""
+        key = self._dynamics_snapshot()
+        if key == self._dynamics_key:
+            return
+        cdyn = _dynamics_to_c(self.dynamics)            # raises for what the kernels do not implement
+        _lib.check(self._lib.die_env_set_dynamics(self._handle, _lib.C.byref(cdyn)))
+        if key[1] is not self._dynamics_key[1]:
+            self._install_food_flow()
+        if key[7] != self._dynamics_key[7]:
+            if key[7]:
+                first = self._medium_buf[0]
+                self._obs_buf = [torch.empty_like(first), torch.empty_like(first)]
+                self._sense_w = np.ascontiguousarray(gaussian_kernel1d(2.0), dtype=np.float64)
+                self._refresh_sensed_medium()
+            else:
+                self._obs_buf = None
+        self._dynamics_key = key
+        self.invalidate_caches()
+
+    def invalidate_caches(self) -> None:
+        """Forget everything the Env caches about its own tensors: the alive bitmask, the per-slot cell cache / published
+        gradient offered to agents as hints, and a pending speculative move.  The caches are validated by torch's version
+        counters, which in-place torch operations bump -- but a write through ``tensor.data``, a DLPack / CuPy / Numba
+        view or a user kernel does NOT.  Call this after such a write (the reference re-reads its arrays every step)."""
+        self._alive_version = None
+        self._hint_state = None
+        self._speculation = None
+        with _lib.on_device(self.device):
+            _lib.check(self._lib.die_env_discard_move(self._handle, torch.cuda.current_stream().cuda_stream))
 
     def _refresh_sensed_medium(self) -> None:
         """obs medium = medium.where(sense_mask, 0.) for the current medium (die_sense_mask)."""
@@ -369,15 +422,19 @@ class Env:
         """``step`` without the host synchronisation: returns (obs, reward_dev[B], alive_dev[B])
         as device tensors, everything enqueued on the current stream."""
         action = self._check_action(action)
+        self._sync_dynamics()
         nxt = 1 - self._cur
         # a gradient agent may have evaluated this very action's move + claims already (see _forward_flags):
         # adopt them iff the action tensor and the agents are provably untouched since
         spec, self._speculation = self._speculation, None
         fused = (spec is not None and spec == (action.data_ptr(), action._version, self._agents._version))
-        flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | _lib.STEP_ALIVE_BITS
+        if self.dynamics.agents_die:
+            fused = False                  # (the library refuses the combination; a pending speculation is discarded)
+        flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | (0 if self.dynamics.agents_die else _lib.STEP_ALIVE_BITS)
         with _lib.on_device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            self._refresh_alive(stream)
+            if not self.dynamics.agents_die:
+                self._refresh_alive(stream)
             _lib.check(self._lib.die_env_step_flags(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
                 self._agents.data_ptr(), action.data_ptr(),
@@ -423,7 +480,8 @@ class Env:
         the alive bitmask is rebuilt here whenever the agents tensor was edited)."""
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
-        if speculate and agents.data_ptr() == self._agents.data_ptr() and agents.numel() == self._agents.numel():
+        if speculate and not self.dynamics.agents_die and agents.data_ptr() == self._agents.data_ptr() \
+                and agents.numel() == self._agents.numel():
             with _lib.on_device(self.device):
                 self._refresh_alive(torch.cuda.current_stream().cuda_stream)
             flags |= _lib.FWD_SPECULATE_MOVE
@@ -479,6 +537,7 @@ class Env:
     def _step_host(self, action: np.ndarray):
         hb = self.host_buffers()
         B, M = self._B, self._M
+        self._sync_dynamics()
         # the library copies straight from the caller's array (cudaMemcpyAsync: full speed if it is pinned --
         # e.g. the array an Agent's host path returned -- staged by the driver if it is pageable); no host memcpy
         src = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(B, 3, M))

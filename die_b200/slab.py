@@ -28,6 +28,25 @@ from . import _lib
 from .env import Dynamics, _dynamics_to_c
 
 
+def validate_slab_dynamics(dynamics: Dynamics, cdyn=None) -> None:
+    """Everything the slab kernels do NOT implement is refused here, up front and by name (the SLAB instantiations
+    hard-code periodic diffusion and the identity food flow; nothing falls back silently)."""
+    from .env import identity_food_flow
+    cdyn = cdyn if cdyn is not None else _dynamics_to_c(dynamics)
+    if dynamics.op_food_flow is not identity_food_flow and dynamics.op_food_flow is not None:
+        raise NotImplementedError("slab mode runs the identity food flow only (Dynamics.op_food_flow)")
+    if dynamics.apply_sense_mask:
+        raise NotImplementedError("slab mode does not implement Dynamics.apply_sense_mask (the observation would be the "
+                                  "unmasked slab)")
+    if dynamics.diffuse_mode != 'wrap':
+        raise NotImplementedError(f"slab mode diffuses periodically only (Dynamics.diffuse_mode={dynamics.diffuse_mode!r})")
+    if not 1 <= cdyn.blur_radius <= 4:
+        raise NotImplementedError(f"slab mode supports blur radius 1..4 (diffuse_sigma={dynamics.diffuse_sigma} gives "
+                                  f"radius {cdyn.blur_radius})")
+    if dynamics.agents_die:
+        raise NotImplementedError("slab mode does not implement Dynamics.agents_die")
+
+
 # --------------------------------------------------------------------------------------------
 # layout
 # --------------------------------------------------------------------------------------------
@@ -169,9 +188,7 @@ class SlabRank:
         self._handle = _lib.C.c_void_p()
         geom = layout.to_c(rank)
         cdyn = _dynamics_to_c(dynamics)
-        from .env import identity_food_flow
-        if dynamics.op_food_flow is not identity_food_flow and dynamics.op_food_flow is not None:
-            raise NotImplementedError("slab mode runs the identity food flow only")
+        validate_slab_dynamics(dynamics, cdyn)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.die_slab_create(_lib.C.byref(geom), _lib.C.byref(cdyn), _lib.C.byref(self._handle)))
             _lib.check(self._lib.die_slab_bind(self._handle, *[int(tables[k]) for k in
@@ -255,6 +272,7 @@ class EmulatedSlabWorld:
                  dynamics: Optional[Dynamics] = None, device=None, corner_r: int = 0, **physarum_kw):
         device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.dynamics = dynamics or Dynamics()
+        validate_slab_dynamics(self.dynamics)
         self.layout, mediums, locals_ = split_global_state(medium, agents, G)
         L, rp, W = self.layout, self.layout.rows_per, self.layout.W
         peers = EmulatedPeers(G, device)
@@ -345,6 +363,7 @@ class SlabEnv:
         import torch.distributed as dist
         self._dist = dist
         self.dynamics = dynamics or Dynamics()
+        validate_slab_dynamics(self.dynamics)          # before any allocation or collective
         self.peers = SymmetricPeers(group)
         self.rank, self.G, self.device = self.peers.rank, self.peers.G, self.peers.device
         H, W = int(field_size[0]), int(field_size[1])

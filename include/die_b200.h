@@ -64,6 +64,9 @@ typedef struct die_dynamics {
     int32_t boundary;
     int32_t food_infinite;
     int32_t diffuse_mode;     /* DIE_DIFFUSE_*; 0 = 'wrap' */
+    int32_t agents_die;       /* Dynamics.agents_die, core/env.py:245-250: after feeding, every channel of a slot whose
+                               * agent_food is not above 1e-4 becomes 0 (the lifecycle the reference intends: its own
+                               * version loses track of the array it rebinds, core/utils.py:22) */
 } die_dynamics_t;
 
 /* GradientAgent / PhysarumAgent constructor state, core/agent/gradient.py:19-45,139-163. */

@@ -429,7 +429,7 @@ class Env:
         self._agent_move(action)
         self._agent_deposit_and_layout(action)
         gained = self._agent_feed(action)
-        # _agent_lifecycle: no-op at defaults (core/env.py:245-261)
+        self._agent_lifecycle()
         self._medium_resource_dynamics()
         self._medium_diffuse_decay()
 
@@ -440,6 +440,18 @@ class Env:
                 'reward': np.round(reward, 3),
                 'mean_reward': np.round(mean_gain, 5)}
         return self._get_current_obs, reward, num_agents == 0, False, info
+
+    def _agent_lifecycle(self):
+        """core/env.py:245-261.  agents_die: ``agents = agents.where(agent_food > 1e-4, 0)`` -- EVERY channel (x, y, alive,
+        agent_food) of a slot without stock becomes 0, for all M slots: an agent that starved dies and is put back at
+        (0, 0), and so is every ghost slot, every step (their stock is never above 0).  NaN stock fails the comparison too.
+        The reference's own version rebinds ``self.agents`` to the new array while its AgentIndexer keeps the old one
+        (core/utils.py:22), so from the next step on it moves one array and looks cells up in another; the semantics
+        restated here are those of that code with the indexer following ``self.agents`` -- pinned by running the
+        reference with exactly that one-line re-binding (tests/test_golden_oracle.py).  agents_born is unimplemented there."""
+        if self.dynamics.agents_die:
+            have_food = self.agents[AG_FOOD] > 1e-4
+            self.agents[:, ~have_food] = 0.
 
     def _agent_move(self, action):
         """core/env.py:152-172 -- ALL M slots, no alive mask."""

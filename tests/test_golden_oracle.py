@@ -129,6 +129,44 @@ def test_oracle_equals_reference_executed_live(kind, size, steps, seed, dyn, akw
 
 
 @pytest.mark.skipif(not run_reference.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("kind,rate_feed,steps", [("brownian", 0.1, 40), ("physarum", 0.02, 40), ("brownian", 0.0, 25)])
+def test_agents_die_equals_reference_with_its_indexer_rebound(kind, rate_feed, steps):
+    """Dynamics(agents_die=True), core/env.py:245-261: the reference's lifecycle rebinds ``self.agents`` to a NEW array
+    (``agents.where(have_food, 0)``) while the AgentIndexer it built in __init__ keeps the old one (core/utils.py:22), so
+    from then on it moves one array and resolves cells from another.  The semantics of a WORKING agents_die are pinned
+    here as: the reference's own code, with the indexer re-pointed at ``self.agents`` after every step (one assignment,
+    nothing else touched).  Agents starve (low rate_feed), ghosts are put back at (0, 0) every step."""
+    ref = run_reference.load()
+    size = (28, 36)
+    np.random.seed(31)
+    renv = ref.Env(size, ref.Dynamics(init_agent_ratio=0.3, agents_die=True, rate_feed=rate_feed))
+    oenv = R.Env(size, R.Dynamics(agents_die=True, rate_feed=rate_feed),
+                 medium=renv.medium.values.copy(), agents=renv.agents.values.copy())
+    m = renv.agents.shape[-1]
+    if kind == "brownian":
+        ra, oa = ref.BrownianAgent(move_scale=0.03, deposit_scale=2.0), R.BrownianAgent(move_scale=0.03, deposit_scale=2.0)
+    else:
+        akw = dict(scale=0.05, turn_angle=30, sense_offset=0.04, deposit=8.0)
+        ra = ref.PhysarumAgent(max_agents=m, **akw)
+        oa = R.PhysarumAgent(max_agents=m, prev_grad=ra._prev_grad.copy(), **akw)
+    robs, oobs = renv._get_current_obs, oenv._get_current_obs
+    alive0 = int((renv.agents.values[2] > 0).sum())
+    for it in range(steps):
+        state = np.random.get_state()
+        ract = ra.forward(robs)
+        np.random.set_state(state)
+        oact = oa.forward(oobs)
+        assert np.array_equal(ract.values, oact), it
+        robs, rr, rt, rtr, rinfo = renv.step(ract)
+        renv._agent_idx._AgentIndexer__agents = renv.agents          # THE fix: the indexer follows the rebound array
+        rinfo = dict(rinfo, num_agents=int((renv.agents.values[2] > 0).sum()))
+        oobs, orr, ot, otr, oinfo = oenv.step(oact)
+        assert rr == orr and oinfo["num_agents"] == rinfo["num_agents"] and oinfo["reward"] == rinfo["reward"], it
+        assert np.array_equal(renv.medium.values, oenv.medium) and np.array_equal(renv.agents.values, oenv.agents), it
+    assert oinfo["num_agents"] < alive0, "the scenario must actually starve agents"
+
+
+@pytest.mark.skipif(not run_reference.available(), reason="/root/reference not present on this box")
 @pytest.mark.parametrize("colors", ['rgb', 'one', 'two'])
 def test_oracle_renderer_equals_reference_executed_live(colors):
     """core/render.py's EnvRenderer (own source, over the stand-in packages; its matplotlib colour map aside) vs the

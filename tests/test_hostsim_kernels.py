@@ -75,6 +75,38 @@ def test_brownian_free_run_bit_exact(field, iters, flags):
         assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
 
 
+@pytest.mark.parametrize("field,rate_feed", [((28, 36), 0.1), ((24, 64), 0.0)])
+def test_agents_die_brownian(field, rate_feed):
+    """Dynamics(agents_die=True): Env._agent_lifecycle (core/env.py:245-250) folded into the feed kernel -- slots whose
+    stock is not above 1e-4 after feeding lose every channel (dead, back at (0, 0)); agents starve over the run, ghosts
+    are reset every step; num_agents counts the survivors.  Semantics pinned against the reference in
+    tests/test_golden_oracle.py::test_agents_die_equals_reference_with_its_indexer_rebound."""
+    dyn = dict(agents_die=True, rate_feed=rate_feed)
+    (ref,), env = make_pair(field, seed=31, ratio=0.3, dynamics_kw=dyn)
+    ra = R.BrownianAgent(0.03, 2.0)
+    m = ref.agents.shape[-1]
+    rng = np.random.default_rng(7)
+    robs = ref._get_current_obs
+    alive0 = ref.num_alive
+    for it in range(30):
+        u = rng.random((3, m))
+        ract = ra.forward(robs, u=u)
+        gact = S.brownian_forward(env.agents[0], move_scale=0.03, deposit_scale=2.0, u=u)
+        assert np.array_equal(ract, gact), f"action differs at step {it}"
+        robs, rr, rterm, _, rinfo = ref.step(ract)
+        r, alive = env.step(gact)
+        assert rinfo['num_agents'] == alive[0]
+        assert _rel(rr, r[0]) < 1e-11
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+    assert ref.num_alive < alive0
+
+
+def test_agents_die_physarum(portable_math):
+    """The same with PhysarumAgent acting through the env's hints: the cell cache of a slot put back at (0, 0) is reset."""
+    dyn = dict(agents_die=True, rate_feed=0.02)
+    _physarum_free_run((28, 40), 25, dict(PHYS, scale=0.05, deposit=8.0), seed=5, dynamics_kw=dyn, ref_dynamics_kw=dyn)
+
+
 def test_brownian_philox_is_launch_invariant_and_masked():
     """In-kernel Philox draws: ghosts get exactly zero (Q8), values lie on the 3-decimal lattice (Q9), and a batch
     of two environments draws different numbers per environment."""
@@ -131,7 +163,10 @@ def _physarum_free_run(field, iters, agent_kw, seed=2, dynamics_kw=None, ref_dyn
         robs, rr, _, _, rinfo = ref.step(ract)
         flags = L.STEP_ALIVE_BITS | (L.STEP_ADOPT_MOVE if fuse else 0)
         r, alive = env.step(gact, flags=flags)
-        assert np.array_equal(ref_cells_linear(ref), env.cells()[0]), f"cells differ at step {it}"
+        expect_cells = ref_cells_linear(ref)
+        if ref.dynamics.agents_die:           # the cache serves the NEXT forward: a slot put back at (0, 0) is in cell 0
+            expect_cells = np.where((ref.agents == 0).all(axis=0), 0, expect_cells)
+        assert np.array_equal(expect_cells, env.cells()[0]), f"cells differ at step {it}"
         assert rinfo['num_agents'] == alive[0]
         assert _rel(rr, r[0]) < 1e-11
         assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)

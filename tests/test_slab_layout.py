@@ -50,3 +50,19 @@ def test_split_requires_the_reference_slot_order():
     agents[2, 5] = 1            # an alive agent that is not in slots [0, A)
     with pytest.raises(ValueError):
         split_global_state(medium, agents, 2)
+
+
+def test_slab_dynamics_are_validated_up_front():
+    """Everything the slab kernels do not implement is refused by name before anything is allocated (advisor finding of
+    round 1: apply_sense_mask was silently ignored, other options failed late inside the first kernel call)."""
+    import pytest
+    from die_b200.env import Dynamics
+    from die_b200.slab import validate_slab_dynamics
+    from die_b200.data_init import WaveSequence
+    validate_slab_dynamics(Dynamics())
+    validate_slab_dynamics(Dynamics(diffuse_sigma=0.8, food_infinite=True))
+    flow = WaveSequence((16, 16), dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
+    for bad in (dict(apply_sense_mask=True), dict(diffuse_mode='reflect'), dict(diffuse_sigma=0.1), dict(diffuse_sigma=1.5),
+                dict(agents_die=True), dict(op_food_flow=flow)):
+        with pytest.raises(NotImplementedError):
+            validate_slab_dynamics(Dynamics(**bad))
