@@ -79,11 +79,12 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_field_tile = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
     if (strcmp(key, "field_tile") == 0) return g_count_field_tile;
+    if (strcmp(key, "field_vec") == 0) return g_count_field_vec;
     if (strcmp(key, "step_fused") == 0) return g_count_step_fused;
     if (strcmp(key, "forward_lean") == 0) return g_count_fwd_lean;
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
@@ -283,6 +284,11 @@ extern "C" int die_env_kernel_times(die_env_t* e, double* ms_out, int64_t* steps
 // ------------------------------------------------------------------------------------------
 // field pass launch
 // ------------------------------------------------------------------------------------------
+static int g_field_vec = 0;        // 1: the 128-bit field pass wherever it applies.  Measured on a B200 (round 2,
+                                   // profiles/r02l_field_vec_ab.txt): half the memory instructions, 52 instead of 60 registers, and
+                                   // NO faster (3.445 vs 3.409 ms batched, 0.230 vs 0.224 ms at 4096^2) -- the pass is bound by DRAM
+                                   // (a 65 % write mix at 80 % of the copy bandwidth), not by its LSU instructions.  Opt-in.
+
 template <int R, bool GRAD>
 static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     constexpr int TH = 32, TW = 64, NT = 256, G = GRAD ? 1 : 0;
@@ -292,6 +298,18 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
     const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr && a.flow_frame == nullptr;
+    if (plain && g_field_vec && (a.W & 1) == 0 && ((uintptr_t)a.medium_in & 15) == 0 && ((uintptr_t)a.medium_out & 15) == 0 &&
+        ((uintptr_t)a.consumed & 15) == 0 && ((uintptr_t)a.winner & 7) == 0 && ((uintptr_t)a.grad32 & 15) == 0) {
+        // the default dynamics on an even row length: the 128-bit version (same tile, same arithmetic, same results)
+        constexpr int PADL = (R + G) & 1, SW = (PADL + TW + 2 * G + 2 * R + 1) & ~1;
+        const size_t vsmem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * SW + (TH + 2 * G) * (TW + 2 * G + 2 * R));
+        auto vkern = field_step_vec_kernel<R, TH, TW, NT, GRAD>;
+        cudaError_t verr = cudaFuncSetAttribute(vkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
+        if (verr != cudaSuccess) return verr;
+        vkern<<<(unsigned)((int64_t)a.tiles_i * a.tiles_j * B), NT, vsmem, st>>>(a);
+        ++g_count_field_vec;
+        return cudaGetLastError();
+    }
     auto kern = plain ? field_step_kernel<R, TH, TW, NT, GRAD, false, true> : field_step_kernel<R, TH, TW, NT, GRAD, false, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -852,6 +870,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "field_prefetch") == 0) g_field_prefetch = value ? 1 : 0;
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
+    else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
     else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;

@@ -282,6 +282,171 @@ field_step_kernel(const FieldArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same pass with 128-bit global accesses, for the reference's default dynamics (periodic diffusion, identity food
+// flow: PLAIN) on fields with an even row length.  Same tile, same shared-memory arithmetic, same results; what changes
+// is how the tile gets in and out:
+//   staging   the halo tile starts at an EVEN column (one pad column when the halo width is odd), so every staged row
+//             is a run of aligned cell pairs: one LDG.E.128 per two chem1 values and one LDG.E.64 per two claims
+//             (a pair never straddles the periodic wrap: W is even);
+//   outputs   a thread owns two adjacent cells: LDG.E.128 for the food, one STG.E.128 each for chem1, food, occupancy
+//             and consumed_field, and one for the two float32 gradient pairs.
+// Half as many memory instructions per cell as field_step_kernel -- and, measured on a B200, no faster (the pass is
+// DRAM-bound: profiles/r02l_field_vec_ab.txt), so this is an opt-in (die_set_tuning("field_vec", 1)) and the scalar
+// version stays the default.
+// ---------------------------------------------------------------------------------------------
+template <int R, int TH, int TW, int NT, bool GRAD>
+__global__ void __launch_bounds__(NT)
+field_step_vec_kernel(const FieldArgs a) {
+    constexpr int G = GRAD ? 1 : 0;
+    constexpr int HALO = R + G;
+    constexpr int PADL = HALO & 1;                      // staged column 0 = field column j0 - HALO - PADL (even)
+    constexpr int OH = TH + 2 * G, OW = TW + 2 * G;     // blurred region
+    constexpr int LW = OW + 2 * R;                      // columns the blur reads
+    constexpr int LH = OH + 2 * R;
+    constexpr int SW = (PADL + LW + 1) & ~1;            // staged row length (even)
+    constexpr int PW = SW / 2;                          // pairs per staged row
+    constexpr int NPAIR = (LH * PW + NT - 1) / NT;
+    static_assert(TW % 2 == 0 && (TH * TW / 2) % NT == 0, "whole pairs, whole passes");
+    extern __shared__ double smem[];
+    double* s_in = smem;                     // [LH][SW]
+    double* s_v = smem + LH * SW;            // [OH][LW]
+    double* s_out = smem;                    // [OH][OW] blurred * keep (aliases s_in, GRAD only)
+
+    const int H = a.H, W = a.W;
+    const int64_t C = (int64_t)H * W;
+    const int tiles = a.tiles_i * a.tiles_j;
+    const int64_t b = blockIdx.x / (unsigned)tiles;
+    const int t = blockIdx.x - (int)b * tiles;
+    const int ti = t / a.tiles_j, tj = t - ti * a.tiles_j;
+    const int i0 = ti * TH, j0 = tj * TW;
+
+    const double* __restrict__ min_l = a.medium_in + b * 3 * C;
+    double* __restrict__ mout_l = a.medium_out + b * 3 * C;
+    const double* __restrict__ food_in = min_l + C;
+    const double* __restrict__ chem_in = min_l + 2 * C;
+    double* __restrict__ occ_out = mout_l;
+    double* __restrict__ food_out = mout_l + C;
+    double* __restrict__ chem_out = mout_l + 2 * C;
+    const int32_t* __restrict__ win = a.winner + b * C;
+    const double* __restrict__ dep = a.action + (b * 3 + 2) * a.M;
+    double* __restrict__ cons = a.consumed + b * C;
+
+    if (a.prefetch_food) {
+        constexpr int LINES_PER_ROW = TW * 8 / 128;
+        for (int l = threadIdx.x; l < TH * LINES_PER_ROW; l += NT) {
+            const int r = l / LINES_PER_ROW, c = (l - r * LINES_PER_ROW) * 16;
+            if (i0 + r < H && j0 + c < W)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(food_in + (int64_t)(i0 + r) * W + j0 + c));
+        }
+    }
+
+    // ---- stage the periodic halo tile pair by pair, deposit included --------------------------------
+    double2 v[NPAIR];
+    int2 w[NPAIR];
+#pragma unroll
+    for (int s = 0; s < NPAIR; ++s) {
+        const int idx = threadIdx.x + s * NT;
+        v[s] = make_double2(0.0, 0.0);
+        w[s] = make_int2(-1, -1);
+        if (idx < LH * PW) {
+            const int r = idx / PW, c = (idx - r * PW) * 2;
+            const int gi = wrap_index(i0 - HALO + r, H);
+            const int gj = wrap_index(j0 - HALO - PADL + c, W);          // even; gj + 1 < W
+            const int g = gi * W + gj;
+            v[s] = *reinterpret_cast<const double2*>(chem_in + g);
+            w[s] = *reinterpret_cast<const int2*>(win + g);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NPAIR; ++s) {
+        const int idx = threadIdx.x + s * NT;
+        if (idx < LH * PW) {
+            double2 x = v[s];
+            if (w[s].x >= 0) x.x = x.x + dep[w[s].x];
+            if (w[s].y >= 0) x.y = x.y + dep[w[s].y];
+            *reinterpret_cast<double2*>(s_in + 2 * idx) = x;             // [r][c], c even: idx * 2 = r * SW + c
+        }
+    }
+    __syncthreads();
+
+    // ---- axis-0 pass (columns PADL .. PADL + LW of the staged rows) -----------------------------------
+    for (int idx = threadIdx.x; idx < OH * LW; idx += NT) {
+        const int r = idx / LW, c = idx - r * LW;
+        const double* p = s_in + (r + R) * SW + PADL + c;
+        double acc = p[0] * a.bw.w[R];
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc += (p[-k * SW] + p[k * SW]) * a.bw.w[R - k];
+        s_v[idx] = acc;
+    }
+    __syncthreads();
+
+    if constexpr (GRAD) {
+        // ---- axis-1 pass over the ring tile into shared memory ---------------------------------------
+        for (int idx = threadIdx.x; idx < OH * OW; idx += NT) {
+            const int r = idx / OW, c = idx - r * OW;
+            const double* p = s_v + r * LW + c + R;
+            double acc = p[0] * a.bw.w[R];
+#pragma unroll
+            for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
+            s_out[idx] = acc * a.keep;
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs, two adjacent cells per thread -------------------------------------------------------
+    float2* grad32 = (GRAD && a.grad32 != nullptr) ? a.grad32 + b * C : nullptr;
+    double2* grad = (GRAD && a.grad != nullptr) ? a.grad + b * C : nullptr;
+    for (int idx = threadIdx.x; idx < TH * TW / 2; idx += NT) {
+        const int r = idx / (TW / 2), c = (idx - r * (TW / 2)) * 2;
+        const int li = i0 + r, gj = j0 + c;
+        if (li < H && gj < W) {                          // (gj even and W even: gj + 1 < W as well)
+            const int g = li * W + gj;
+            double o0, o1;
+            if constexpr (GRAD) {
+                const double* q = s_out + (r + 1) * OW + (c + 1);
+                o0 = q[0];
+                o1 = q[1];
+                // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
+                const int um = (li > 0) ? -OW : 0, up = (li < H - 1) ? OW : 0;
+                double gx0 = q[up] - q[um], gx1 = q[1 + up] - q[1 + um];
+                if (up - um == 2 * OW) { gx0 *= 0.5; gx1 *= 0.5; }
+                const int lm0 = (gj > 0) ? -1 : 0;                       // cell gj: right neighbour gj + 1 always exists
+                double gy0 = q[1] - q[lm0];
+                if (lm0 != 0) gy0 *= 0.5;
+                const int lp1 = (gj + 1 < W - 1) ? 1 : 0;                // cell gj + 1: left neighbour gj always exists
+                double gy1 = q[1 + lp1] - q[0];
+                if (lp1 != 0) gy1 *= 0.5;
+                if (grad32 != nullptr) {
+                    *reinterpret_cast<float4*>(grad32 + g) = make_float4((float)gx0, (float)gy0, (float)gx1, (float)gy1);
+                } else {
+                    grad[g] = make_double2(gx0, gy0);
+                    grad[g + 1] = make_double2(gx1, gy1);
+                }
+            } else {
+                const double* p = s_v + r * LW + c + R;
+                double acc0 = p[0] * a.bw.w[R], acc1 = p[1] * a.bw.w[R];
+#pragma unroll
+                for (int k = R; k >= 1; --k) {
+                    acc0 += (p[-k] + p[k]) * a.bw.w[R - k];
+                    acc1 += (p[1 - k] + p[1 + k]) * a.bw.w[R - k];
+                }
+                o0 = acc0 * a.keep;
+                o1 = acc1 * a.keep;
+            }
+            *reinterpret_cast<double2*>(chem_out + g) = make_double2(o0, o1);
+            const int2 wn = *reinterpret_cast<const int2*>(win + g);
+            const double2 f = *reinterpret_cast<const double2*>(food_in + g);
+            const double occ0 = (wn.x >= 0) ? 1.0 : 0.0, occ1 = (wn.y >= 0) ? 1.0 : 0.0;
+            const double cf0 = (a.rate_feed * f.x) * occ0, cf1 = (a.rate_feed * f.y) * occ1;   // consumed_field, core/env.py:224
+            *reinterpret_cast<double2*>(food_out + g) = make_double2(next_food<true>(a, f.x, cf0, li, gj, g),
+                                                                     next_food<true>(a, f.y, cf1, li, gj + 1, g + 1));
+            *reinterpret_cast<double2*>(occ_out + g) = make_double2(occ0, occ1);
+            *reinterpret_cast<double2*>(cons + g) = make_double2(cf0, cf1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Env._get_sensed_medium / _get_sense_mask (core/env.py:275-294), Dynamics.apply_sense_mask:
 //   mask = ceil(round(gaussian(occupancy, sigma=2.0), 3));   obs_medium = medium.where(mask, other=0.)
 // skimage's default mode is 'nearest' and truncate 4.0, i.e. a radius-8 blur with clamped borders, in

@@ -294,10 +294,10 @@ int die_set_turn_quick(int32_t on);
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
  * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
- * alive-ness from the bitmask), "field_prefetch" 0/1, "step_impl" 0/1 (see die_set_step_impl), "grad_f32" 0/1 (see die_env_gradient_kind). */
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "field_vec" 0/1 (the 128-bit field pass where it applies), "step_impl" 0/1 (see die_set_step_impl), "grad_f32" 0/1 (see die_env_gradient_kind). */
 int die_set_tuning(const char* key, int32_t value);
 /* How often a kernel variant has been launched by this process (diagnostics for tests: "the variant I selected is the
- * one that ran"): "field_tile", "step_fused", "forward_lean", "forward_lean_f32", "forward_general";
+ * one that ran"): "field_tile", "field_vec", "step_fused", "forward_lean", "forward_lean_f32", "forward_general";
  * -1 for an unknown key. */
 int64_t die_get_counter(const char* key);
 

@@ -35,6 +35,8 @@ struct uint3 { unsigned x, y, z; };
 struct uint4 { unsigned x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -43,6 +45,8 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 
 // ---- the running thread ------------------------------------------------------------------------
 namespace hostsim {

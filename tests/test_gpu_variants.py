@@ -128,3 +128,29 @@ def test_simple_agents_example(argv):
                           "--iters", "30", *argv], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ms per iteration" in out.stdout and "frames:" in out.stdout
+
+
+@pytest.mark.parametrize("shape,sigma,batch", [((256, 256), 0.5, 6), ((40, 72), 0.5, None), ((70, 200), 0.8, None),
+                                               ((128, 96), 1.0, 5), ((96, 130), 0.3, 2)])
+def test_vectorised_field_pass_does_not_change_results(shape, sigma, batch):
+    """field_vec = 1 (field_step_vec_kernel, opt-in: no faster than the scalar tile kernel on a B200): 128-bit staging
+    loads and output stores."""
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    outs = []
+    n0 = lib.die_get_counter(b"field_vec")
+    try:
+        for vec in (0, 1):
+            _lib.check(lib.die_set_tuning(b"field_vec", vec))
+            _, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch)
+            m = env.max_agents
+            ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
+            obs = env._get_current_obs
+            for _ in range(12):
+                obs, r, *_ = env.step(ag.forward(obs))
+            outs.append((*env.get_state(), ag.get_state()[0], np.asarray(r)))
+    finally:
+        _lib.check(lib.die_set_tuning(b"field_vec", 0))
+    assert lib.die_get_counter(b"field_vec") == n0 + 12, "the 128-bit kernel must be the one that ran"
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))

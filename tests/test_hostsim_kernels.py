@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -243,7 +243,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1])])
+                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
@@ -292,6 +292,53 @@ def test_fused_step_equals_three_kernels(tuning, shape, sigma, batch, grad, thre
         if a is None:
             continue
         assert np.array_equal(a, b), f"{what} differs"
+
+
+@pytest.mark.parametrize("shape,sigma,batch", [((64, 128), 0.5, None), ((40, 72), 0.5, None), ((6, 76), 0.5, None),
+                                               ((70, 200), 0.8, None), ((33, 132), 0.3, 3), ((48, 96), 1.0, 2),
+                                               ((96, 80), 0.5, 5), ((37, 2), 0.5, None)])
+@pytest.mark.parametrize("grad", [True, False])
+def test_vectorised_field_pass_equals_the_scalar_one(tuning, shape, sigma, batch, grad):
+    """field_vec = 1 (field_step_vec_kernel): the field pass with 128-bit global accesses -- halo tile staged in aligned
+    cell pairs from an even column, two adjacent output cells per thread.  Even widths that are not multiples of the
+    tile (the pair at the right edge), fields lower than a tile, radii 1..4 (odd and even halo widths: with / without
+    the pad column), batches, with (Physarum, float64 and float32 gradient cache) and without (Brownian) the gradient."""
+    outs = []
+    vec0 = S.lib().die_get_counter(b"field_vec")
+    for vec, f32 in ((0, 0), (1, 0), (1, 1)):
+        tuning("field_vec", vec)
+        tuning("grad_f32", f32)
+        refs, env = make_pair(shape, seed=13, dynamics_kw=dict(diffuse_sigma=sigma), batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 13 + b)[0]
+        for it in range(5):
+            if grad:
+                act = ga.forward(env)
+            else:
+                act = S.brownian_forward(env.agents, move_scale=0.02, seed=4, step=it)
+            env.step(act)
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), env.reward.copy(),
+                     None if f32 or not grad else env.gradient()))
+    assert S.lib().die_get_counter(b"field_vec") == vec0 + 10, "the 128-bit kernel must be the one that ran"
+    for k in (1, 2):
+        for a, b, what in zip(outs[0], outs[k], ("medium", "agents", "theta", "reward", "gradient")):
+            if a is None or b is None:
+                continue
+            assert np.array_equal(a, b), f"variant {k}: {what} differs"
+
+
+def test_vectorised_field_pass_falls_back_where_it_does_not_apply(tuning):
+    """Odd widths (a pair would straddle the row end) and the other scipy boundary modes (time-varying food flows: the
+    wave / tabulated flow tests run with field_vec = 1 and stay bit-exact against the oracle)."""
+    vec0 = S.lib().die_get_counter(b"field_vec")
+    for shape, kw in (((40, 71), {}), ((40, 64), dict(diffuse_mode='reflect'))):
+        refs, env = make_pair(shape, seed=3, dynamics_kw=kw)
+        ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
+        for it in range(2):
+            env.step(ga.forward(env))
+    assert S.lib().die_get_counter(b"field_vec") == vec0
 
 
 def test_fused_step_falls_back_where_it_does_not_apply(tuning):
@@ -896,7 +943,7 @@ def _random_case(seed):
     agent = dict(scale=float(rng.choice([0.007, 0.03, 0.2, 1.7])), sense_offset=float(rng.choice([0.0, 0.04, 0.3, 1.5])),
                  turn_angle=float(rng.choice([30, 35, 45, 90])), sense_angle=float(rng.choice([60, 90, 120, 170])),
                  turn_tolerance=float(rng.choice([0.05, 0.1, 0.3])), deposit=float(rng.choice([4.0, 0.5])))
-    tune = dict(step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
+    tune = dict(field_vec=int(rng.random() < 0.7), step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.5), fwd_lean=int(rng.random() < 0.7),
                 feed_bits=int(rng.random() < 0.7))
     return (h, w), float(rng.choice([0.05, 0.1, 0.5, 1.0])), dyn, rdyn, agent, tune, bool(rng.random() < 0.5)
 
@@ -940,7 +987,7 @@ def test_random_batches_slot_counts_and_policies(portable_math, tuning, seed):
     C = h * w
     m = int(rng.choice([max(C // 3, 1), C, C, 2 * C + 7]))
     sigma = float(rng.choice([0.3, 0.5, 0.8]))
-    for k, v in dict(step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
+    for k, v in dict(field_vec=int(rng.random() < 0.7), step_impl=int(rng.random() < 0.3), grad_f32=int(rng.random() < 0.7), fwd_lean=int(rng.random() < 0.5),
                      feed_bits=int(rng.random() < 0.7)).items():
         tuning(k, v)
     refs, mediums, agentss = [], [], []
