@@ -59,6 +59,16 @@ SURVEY_BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "agent_feed": 40.0
 BYTES_FUSED = {"physarum_forward": 72.0 + 40.0, "move_claim": 0.0, "agent_feed": 40.0 + 16.0, "field_step": 48.0,
                "finalize_stats": 0.0}
 ALIVE_EXTRA = {"field_step": 24.0, "env_step_fused": 24.0}
+# float32 FIELD mode (Env(field_dtype=torch.float32): medium + consumed_field in float32, agents / actions float64), bytes
+# counted per dtype (SURVEY 8d with s_f = 4, s_a = 8: 189 B per cell-update):
+#   physarum_forward  R{x,y,theta} W{theta,dx,dy,dep} = 56 + gathers{gradient pair 8 (float32 x 2), food 4}   = 68 B / slot
+#                     (survey: 56 + 5 gathers x 4 = 76)
+#   move_claim        56 B / slot (no field access)
+#   agent_feed        R{agent_food,dep} W{agent_food} = 24 + gathers{food, occ} 2 x 4                        = 32 B / slot
+#   field_step        chem R+W, food R+W, occupancy R+W = 6 x 4                                             = 24 B / cell
+BYTES_F32 = {"physarum_forward": 68.0, "move_claim": 56.0, "agent_feed": 32.0, "field_step": 24.0, "finalize_stats": 0.0}
+SURVEY_BYTES_F32 = {"physarum_forward": 76.0, "move_claim": 56.0, "agent_feed": 32.0, "field_step": 24.0, "finalize_stats": 0.0}
+ALIVE_EXTRA_F32 = {"field_step": 12.0}
 
 
 def measured_hbm_peak():
@@ -171,7 +181,7 @@ def lattice_theta_device(B, M, turn_angle, seed, device):
     return k.to(torch.float64) * tr
 
 
-def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_base):
+def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_base, field_dtype=None):
     """Seeded synthetic state: up to 16 distinct host-built environments, tiled on the device."""
     n_distinct = 1 if not batched else min(B_local, 16)
     med_h, ag_h = build_host_state(field, n_distinct, seed=seed_base + 1000 * rank)
@@ -183,7 +193,7 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
         ag = ag.repeat(reps, 1, 1)[:B_local]
     alive = int((ag[:, 2] > 0).sum().item())
     env = D.Env(field, D.Dynamics(init_agent_ratio=AGENT_RATIO), batch=(B_local if batched else None),
-                init_state=(med, ag), device=device)
+                init_state=(med, ag), device=device, field_dtype=field_dtype or torch.float64)
     del med, ag
     M = env.max_agents
     agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
@@ -192,10 +202,10 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
     return env, agent, alive
 
 
-def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks):
+def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks, field_dtype=None):
     """Warm-up, the timed region (CUDA events, barrier + synchronize on both sides, max over
     ranks), then the per-kernel breakdown.  Returns a dict of raw measurements."""
-    env, agent, alive_local = make_env_and_agent(D, torch, field, B_local, batched, device, rank, 0)
+    env, agent, alive_local = make_env_and_agent(D, torch, field, B_local, batched, device, rank, 0, field_dtype)
     M, C = env.max_agents, field[0] * field[1]
 
     def sync_all():
@@ -251,7 +261,8 @@ def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     grad_kind = dlib.load().die_env_gradient_kind(env._handle)
     return dict(env=env, agent=agent, obs=obs, steps_done=args.warmup + args.steps + n_prof,
                 ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
-                alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused), grad_kind=int(grad_kind))
+                alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused), grad_kind=int(grad_kind),
+                f32=(field_dtype is not None and field_dtype == torch.float32))
 
 
 def steady_state_leg(torch, meas, checkpoints, window=40):
@@ -481,15 +492,18 @@ def roofline_of(meas, B_local, wl_name):
     slots_local, cells_local = M * B_local, C * B_local
     kernels = {}
     BY = dict(BYTES_FUSED if meas.get("fused") else BYTES)
+    SV, AX = SURVEY_BYTES, ALIVE_EXTRA
+    if meas.get("f32"):
+        BY, SV, AX = dict(BYTES_F32), SURVEY_BYTES_F32, ALIVE_EXTRA_F32
     if meas.get("grad_kind") == 1:                 # float64 gradient cache: a 16-byte pair per slot
         BY["physarum_forward"] += 8.0
     for k, t_ms in meas["kernel_ms"].items():
         units = cells_local if k in ("field_step", "env_step_fused") else slots_local
-        nbytes = BY[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local
+        nbytes = BY[k] * units + AX.get(k, 0.0) * alive_local
         gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         kernels[k] = {"ms": round(t_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(gbs, 1),
                       "frac": round(gbs / peak, 4),
-                      "survey_bytes": SURVEY_BYTES[k] * units + ALIVE_EXTRA.get(k, 0.0) * alive_local}
+                      "survey_bytes": SV[k] * units + AX.get(k, 0.0) * alive_local}
     dominant = max((k for k in kernels if BY[k] > 0), key=lambda k: kernels[k]["ms"])
     step_bytes = sum(v["algorithmic_bytes"] for v in kernels.values())
     survey_bytes = sum(v["survey_bytes"] for v in kernels.values())
@@ -667,6 +681,23 @@ def run_die_b200(args):
             also["physarum_single_env_256x256_300_iters"] = small_env_leg(D, torch, device, "physarum",
                                                                          cpu_iters=0 if args.no_cpu else 20)
 
+    # ---- N = 1 only: the float32 FIELD mode of both workloads (fields in float32, agents float64; bytes counted per dtype;
+    #      float64 stays the headline dtype: it is the reference's) ---------------------------------------------------
+    if n_gpus == 1 and workload == "batch256" and not args.no_f32:
+        for f3, B3, batched3, name3 in (((256, 256), B_local, True, wl_name), ((args.field, args.field), 1, False,
+                                                                              "physarum_single_field_%dx%d" % (args.field, args.field))):
+            if not batched3 and args.no_single_field:
+                continue
+            m3 = measure(D, torch, dist, args, f3, B3, batched3, device, rank, world, want_clocks=False,
+                         field_dtype=torch.float32)
+            r3, _ = roofline_of(m3, B3, name3 + "_f32_fields")
+            also = dict(also or {})
+            also[name3 + "_f32_fields"] = {
+                "value": f3[0] * f3[1] * B3 / (m3["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m3["ms_per_step"],
+                "dtype": "f32 fields (medium, consumed_field), f64 agents / actions / headings", "roofline": r3}
+            del m3
+            torch.cuda.empty_cache()
+
     # ---- N > 1: the single 32768x32768 field split into row slabs over the ranks (BASELINE.json configs[4]) ----------
     if n_gpus > 1 and workload == "batch256" and not args.no_slab:
         try:
@@ -813,6 +844,7 @@ def main():
     ap.add_argument("--no-small-env", action="store_true", help="skip the configs[0] / configs[1] legs (one 256x256 env)")
     ap.add_argument("--steady", default="300,3000", help="single field: also report ms/step in the 40 steps before these "
                                                           "total step counts ('' = off)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float32-field legs")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the configs[4] leg (one field over all ranks)")
     ap.add_argument("--slab-field", type=int, default=32768, help="side of the slab-decomposed field of the N > 1 run")
     ap.add_argument("--slab-steps", type=int, default=25)

@@ -29,7 +29,8 @@ def find_env(agents, medium):
     if env is None or env._handle is None:
         return None
     buf = env._medium_buf[0]
-    if medium.numel() != buf.numel() or medium.shape[-2:] != buf.shape[-2:] or agents.numel() != env._agents.numel():
+    if medium.numel() != buf.numel() or medium.shape[-2:] != buf.shape[-2:] or agents.numel() != env._agents.numel() \
+            or medium.dtype != buf.dtype:
         return None
     return env
 

@@ -8,6 +8,7 @@ from ._build import LIB_PATH
 DIE_MAX_RADIUS = 8
 BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
 DIFFUSE_MODES = {'wrap': 0, 'reflect': 1, 'nearest': 2, 'mirror': 3, 'constant': 4}
+FIELD_F64, FIELD_F32 = 0, 1
 FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE, FWD_STEP_ON_DEVICE = 1, 2, 4, 8
 STEP_ADOPT_MOVE, STEP_ALIVE_BITS = 1, 2
 
@@ -87,6 +88,10 @@ SIGNATURES = {
                                        C.c_uint64, C.c_uint64, _P]),
     "die_brownian_forward_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_uint64, _P, _P]),
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
+    "die_env_set_field_dtype": (C.c_int, [_P, C.c_int32]),
+    "die_env_field_dtype": (C.c_int, [_P]),
+    "die_gradient_forward_f32": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                           _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "die_gradient_forward": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "die_host_ctx_create": (C.c_int, [C.POINTER(_P)]),

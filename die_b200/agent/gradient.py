@@ -207,7 +207,7 @@ class GradientAgent(_DeviceAgent):
             agents, medium = obs
         _, _, _, B, M = _split_obs((agents, medium))
         self._check(agents)
-        self._check(medium)
+        self._check_medium(medium)
         H, W = medium.shape[-2:]
         self._lazy_init(B, M, agents.device)
         action = self._action_for(agents)
@@ -266,10 +266,15 @@ class GradientAgent(_DeviceAgent):
                 if self._step_dev is not None:
                     raise RuntimeError("the device-resident call counter (die_b200.GraphedLoop) needs the producing Env: "
                                        "pass the observation that Env.step returned and keep use_env_hints on")
-                _lib.check(self._lib.die_gradient_forward(
-                    _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
-                    prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, None, None,
-                    self._seed, self._step, stream))
+                if medium.dtype == torch.float32:           # a float32 medium without its env (hints off, or a copy)
+                    _lib.check(self._lib.die_gradient_forward_f32(
+                        _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
+                        prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, self._seed, self._step, stream))
+                else:
+                    _lib.check(self._lib.die_gradient_forward(
+                        _lib.C.byref(p), H, W, M, B, agents.data_ptr(), medium.data_ptr(), self._theta.data_ptr(),
+                        prev_ptr, action.data_ptr(), coin_ptr, noise_ptr, cells_ptr, None, None,
+                        self._seed, self._step, stream))
         # the kernel wrote `action` through its raw pointer: make that visible to torch's version counter, so a
         # stale speculation can never be mistaken for this one (two envs sharing one agent, repeated forwards)
         torch.autograd.graph.increment_version(action)

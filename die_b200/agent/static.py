@@ -43,6 +43,13 @@ class _DeviceAgent(Agent):
             raise TypeError("obs must hold contiguous float64 CUDA tensors (or numpy arrays for the host path); "
                             "die_b200 has no CPU fallback")
 
+    @staticmethod
+    def _check_medium(medium: torch.Tensor):
+        """The medium may be float32 (an Env in its float32 field mode); agents, actions and headings never are."""
+        if not (isinstance(medium, torch.Tensor) and medium.is_cuda and medium.dtype in (torch.float64, torch.float32)
+                and medium.is_contiguous()):
+            raise TypeError("obs[1] must be a contiguous float64 (or float32) CUDA tensor; die_b200 has no CPU fallback")
+
     # -- host-buffer path: numpy obs in, numpy action out ------------------------------------
     def _forward_host(self, obs) -> np.ndarray:
         agents_np, medium_np = obs

@@ -163,13 +163,14 @@ __device__ __noinline__ die_turn_t turn_exact_call(double gx, double gy, double 
 
 // np.gradient of chem at cell (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
 // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
-__device__ __forceinline__ void sample_gradient(const double* __restrict__ chem, int sx, int sy, int H, int W,
+template <typename FT>
+__device__ __forceinline__ void sample_gradient(const FT* __restrict__ chem, int sx, int sy, int H, int W,
                                                 double& gx, double& gy) {
     const int sc = sx * W + sy;
     const int xm = (sx > 0) ? -W : 0, xp = (sx < H - 1) ? W : 0;
     const int ym = (sy > 0) ? -1 : 0, yp = (sy < W - 1) ? 1 : 0;
-    gx = chem[sc + xp] - chem[sc + xm];
-    gy = chem[sc + yp] - chem[sc + ym];
+    gx = (double)chem[sc + xp] - (double)chem[sc + xm];
+    gy = (double)chem[sc + yp] - (double)chem[sc + ym];
     if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly
     if (yp - ym == 2) gy *= 0.5;
 }
@@ -179,9 +180,12 @@ __device__ __forceinline__ void sample_gradient(const double* __restrict__ chem,
 // checks and parameter reloads of the general kernel fold away.  Same arithmetic, same results.
 // G32 (LEAN only): the published gradient is the float32 one.  die_turn_quick rounds the gradient to float32 first
 // thing, so every decision it settles is the same; a slot it defers re-samples the float64 gradient from chem1.
-template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false, bool G32 = false>
+// FT: element type of the medium the agent observes (float64, or float32 in the env's float32 field mode): gathered
+// values are widened, all arithmetic stays float64.
+template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false, bool G32 = false, typename FT = double>
 __global__ void __launch_bounds__(kAgentThreads, MINB)
 gradient_forward_kernel(const GradientArgs a) {
+    static_assert(!SLAB || sizeof(FT) == 8, "the slab decomposition runs float64 fields");
     const die_gradient_params_t& p = a.p;
     const Axis ax = a.ax, ay = a.ay;
     const int64_t M = a.M;
@@ -192,8 +196,8 @@ gradient_forward_kernel(const GradientArgs a) {
 
     // per-thread base pointers, advanced by kAgentThreads per item
     const double* ag_x = a.agents + ch.b * 4 * M + first;
-    const double* food = a.medium + (ch.b * 3 + 1) * C;
-    const double* chem = a.medium + (ch.b * 3 + 2) * C;
+    const FT* food = (const FT*)a.medium + (ch.b * 3 + 1) * C;
+    const FT* chem = (const FT*)a.medium + (ch.b * 3 + 2) * C;
     double* th_p = a.theta + ch.b * M + first;
     double* ab = a.action + ch.b * 3 * M + first;
     double* pg = (!LEAN && a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M + first : nullptr;
@@ -237,7 +241,7 @@ gradient_forward_kernel(const GradientArgs a) {
         const double x = nx, y = ny, th = nth;
         // food under the agent (:113-115), issued first: independent of the turn arithmetic
         const int here = (LEAN || cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : food[here];
+        const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : (double)food[here];
         uint32_t alive_word = 0;
         if (MOVE) alive_word = bits_p[i >> 5];
         nvalid = (k + 1 < kFwdItems) && (i + kAgentThreads < left);
@@ -279,8 +283,8 @@ gradient_forward_kernel(const GradientArgs a) {
                 gx = __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + xp)) - __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + xm));
                 gy = __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + yp)) - __ldg(slab_chan(a.st.medium_in, a.sg, 2, sc + ym));
             } else {
-                gx = chem[sc + xp] - chem[sc + xm];
-                gy = chem[sc + yp] - chem[sc + ym];
+                gx = (double)chem[sc + xp] - (double)chem[sc + xm];
+                gy = (double)chem[sc + yp] - (double)chem[sc + ym];
             }
             if (xp - xm == 2 * W) gx *= 0.5;      // central difference: / 2.0 exactly (as sample_gradient)
             if (yp - ym == 2) gy *= 0.5;
@@ -431,7 +435,7 @@ constexpr int kFeedItems = 4;      // slots per thread
 struct FeedArgs {
     double* agents;
     const double* action;
-    const double* consumed_field;    // [B][C] rate_feed * food * occ of this step (the field pass wrote it)
+    const double* consumed_field;    // [B][C] rate_feed * food * occ of this step (the field pass wrote it); element type FT
     int32_t* winner;
     int32_t* cells;                  // read; DIE also resets the cached cell of a slot it puts back at (0, 0)
     double* part_gain;
@@ -447,7 +451,7 @@ struct FeedArgs {
 // DIE: Dynamics.agents_die -- Env._agent_lifecycle (core/env.py:245-250) folded in: a slot whose stock after feeding is
 // not above 1e-4 has ALL its channels zeroed (agents.where(agent_food > 1e-4, 0): dead, back at (0, 0), no stock), which
 // holds for every ghost slot every step; num_agents counts the survivors (core/env.py:118, after the lifecycle).
-template <bool SLAB, bool MOVE, bool BITS, bool DIE = false>
+template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const int64_t M = a.M;
@@ -457,7 +461,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
     double* __restrict__ ag_x = a.agents + b * 4 * M + first;  // x; y, alive, agent_food are + M, 2M, 3M
     const double* __restrict__ ac = a.action + b * 3 * M + first;
-    const double* __restrict__ cf = SLAB ? nullptr : a.consumed_field + b * a.C;
+    const FT* __restrict__ cf = SLAB ? nullptr : (const FT*)a.consumed_field + b * a.C;
     int32_t* __restrict__ win = a.winner + b * a.C;
     int32_t* __restrict__ cl = a.cells + b * M + first;
     const uint32_t* __restrict__ bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
@@ -478,7 +482,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : cf[cell[k]]) : 0.0;
+        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : (double)cf[cell[k]]) : 0.0;
         if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
         else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {

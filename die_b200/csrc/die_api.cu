@@ -66,6 +66,7 @@ struct die_env {
     double* reward_dev;    // [B] (host path)
     int64_t* alive_dev;    // [B] (host path)
     int num_sms;
+    int field_f32;                     // the field arrays (medium A/B, consumed_field) hold float32 (die_env_set_field_dtype)
     int profiling;                     // record events between the step's kernels
     int prof_steps;                    // steps recorded so far
     cudaEvent_t* prof_events;          // [DIE_MAX_PROFILED_STEPS][DIE_NUM_STEP_KERNELS + 1]
@@ -175,6 +176,20 @@ extern "C" int die_env_destroy(die_env_t* e) {
     }
     delete e;
     return DIE_OK;
+}
+
+extern "C" int die_env_set_field_dtype(die_env_t* e, int32_t dtype) {
+    DIE_REQUIRE(e != nullptr && (dtype == DIE_FIELD_F64 || dtype == DIE_FIELD_F32));
+    e->field_f32 = dtype == DIE_FIELD_F32;
+    e->grad_kind = 0;
+    return DIE_OK;
+}
+
+extern "C" int die_env_field_dtype(const die_env_t* e) { return (e && e->field_f32) ? DIE_FIELD_F32 : DIE_FIELD_F64; }
+
+// element `elems` of a field array whose element type is the env's field dtype
+static inline double* field_off(const die_env* e, const double* p, size_t elems) {
+    return e->field_f32 ? (double*)((float*)p + elems) : (double*)p + elems;
 }
 
 extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
@@ -290,7 +305,7 @@ static int g_field_vec = 0;        // 1: the 128-bit field pass wherever it appl
                                    // (a 65 % write mix at 80 % of the copy bandwidth), not by its LSU instructions.  Opt-in.
 
 template <int R, bool GRAD>
-static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
+static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st, bool f32) {
     constexpr int TH = 32, TW = 64, NT = 256, G = GRAD ? 1 : 0;
     FieldArgs a = fa;
     a.tiles_i = (a.H + TH - 1) / TH;
@@ -298,6 +313,19 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * (TW + 2 * G + 2 * R) +
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
     const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr && a.flow_frame == nullptr;
+    if (f32) {                     // float32 field arrays: the scalar tile kernel on float (blur radius 1..4)
+        if constexpr (R <= 4) {
+            auto kern = plain ? field_step_kernel<R, TH, TW, NT, GRAD, false, true, float>
+                              : field_step_kernel<R, TH, TW, NT, GRAD, false, false, float>;
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+            kern<<<(unsigned)((int64_t)a.tiles_i * a.tiles_j * B), NT, smem, st>>>(a);
+            ++g_count_field_tile;
+            return cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;        // (float32 fields: blur radius 1..4; the Python layer refuses by name)
+        }
+    }
     if (plain && g_field_vec && (a.W & 1) == 0 && ((uintptr_t)a.medium_in & 15) == 0 && ((uintptr_t)a.medium_out & 15) == 0 &&
         ((uintptr_t)a.consumed & 15) == 0 && ((uintptr_t)a.winner & 7) == 0 && ((uintptr_t)a.grad32 & 15) == 0) {
         // the default dynamics on an even row length: the 128-bit version (same tile, same arithmetic, same results)
@@ -322,9 +350,9 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st) {
 static int g_field_prefetch = 1;   // tile kernel: prefetch the output tile's food lines to L2 while staging
 
 template <int R>
-static cudaError_t launch_field(const FieldArgs& fa, int B, int num_sms, cudaStream_t st) {
+static cudaError_t launch_field(const FieldArgs& fa, int B, int num_sms, cudaStream_t st, bool f32) {
     const bool want_grad = fa.grad != nullptr || fa.grad32 != nullptr;
-    return want_grad ? launch_field_g<R, true>(fa, B, st) : launch_field_g<R, false>(fa, B, st);
+    return want_grad ? launch_field_g<R, true>(fa, B, st, f32) : launch_field_g<R, false>(fa, B, st, f32);
 }
 
 static int g_step_impl = 0;        // 0 (default) = the three kernels move_claim / field_step / agent_feed;
@@ -348,7 +376,8 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     a.medium_out = mout;
     a.winner = e->winner + b0 * C;
     a.action = action;
-    a.consumed = e->consumed + b0 * C;
+    a.consumed = field_off(e, e->consumed, (size_t)b0 * C);
+    const bool f32 = e->field_f32 != 0;
     if (e->publish_grad && e->dyn.blur_radius > 0) {
         if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
         if (publish_as_f32(e)) a.grad32 = e->grad32 + b0 * C;
@@ -383,18 +412,19 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     switch (e->dyn.blur_radius) {
         case 0: {
             const int64_t total = (int64_t)e->H * e->W * nb;
-            field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
+            if (f32) field_step_noblur_kernel<256, float><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
+            else field_step_noblur_kernel<256><<<grid_for(total, 256, e->num_sms), 256, 0, st>>>(a, total);
             err = cudaGetLastError();
             break;
         }
-        case 1: err = launch_field<1>(a, nb, e->num_sms, st); break;
-        case 2: err = launch_field<2>(a, nb, e->num_sms, st); break;
-        case 3: err = launch_field<3>(a, nb, e->num_sms, st); break;
-        case 4: err = launch_field<4>(a, nb, e->num_sms, st); break;
-        case 5: err = launch_field<5>(a, nb, e->num_sms, st); break;
-        case 6: err = launch_field<6>(a, nb, e->num_sms, st); break;
-        case 7: err = launch_field<7>(a, nb, e->num_sms, st); break;
-        case 8: err = launch_field<8>(a, nb, e->num_sms, st); break;
+        case 1: err = launch_field<1>(a, nb, e->num_sms, st, f32); break;
+        case 2: err = launch_field<2>(a, nb, e->num_sms, st, f32); break;
+        case 3: err = launch_field<3>(a, nb, e->num_sms, st, f32); break;
+        case 4: err = launch_field<4>(a, nb, e->num_sms, st, f32); break;
+        case 5: err = launch_field<5>(a, nb, e->num_sms, st, f32); break;
+        case 6: err = launch_field<6>(a, nb, e->num_sms, st, f32); break;
+        case 7: err = launch_field<7>(a, nb, e->num_sms, st, f32); break;
+        case 8: err = launch_field<8>(a, nb, e->num_sms, st, f32); break;
     }
     return err;
 }
@@ -453,7 +483,7 @@ static int try_fused_step(die_env* e, int b0, int nb, const double* medium_in, d
     *done = 0;
     const int R = e->dyn.blur_radius;
     if (e->dyn.diffuse_mode != DIE_DIFFUSE_WRAP || R < 1 || R > 4 || (e->W & 1) != 0 || e->W < R) return DIE_OK;
-    if (((uintptr_t)medium_in & 15) != 0 || alive_bits == nullptr) return DIE_OK;   // (a caller's odd view of a tensor)
+    if (((uintptr_t)medium_in & 15) != 0 || alive_bits == nullptr || e->field_f32) return DIE_OK;   // (a caller's odd view of a tensor)
     const int nt = g_fused_threads;
     const bool want_grad = e->publish_grad != 0;
     const bool plain = e->flow_rwave == nullptr && e->flow_frames == nullptr;
@@ -538,8 +568,8 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
                           double* agents, const double* action, double* reward_dev, int64_t* alive_dev,
                           bool fused, const uint32_t* alive_bits, bool profile, cudaStream_t st) {
     const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
-    medium_in += (size_t)b0 * 3 * C;
-    medium_out += (size_t)b0 * 3 * C;
+    medium_in = field_off(e, medium_in, (size_t)b0 * 3 * C);
+    medium_out = field_off(e, medium_out, (size_t)b0 * 3 * C);
     agents += (size_t)b0 * 4 * M;
     action += (size_t)b0 * 3 * M;
     int32_t* winner = e->winner + (size_t)b0 * C;
@@ -583,10 +613,16 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     auto feed = fused ? agent_feed_kernel<false, true, true>
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
     if (e->dyn.agents_die) feed = agent_feed_kernel<false, false, false, true>;
+    if (e->field_f32) {
+        if (fused) return fail(DIE_E_INVALID, "the speculative move is not available with float32 fields%s%s");
+        feed = e->dyn.agents_die ? agent_feed_kernel<false, false, false, true, float>
+                                 : (feed_bits ? agent_feed_kernel<false, false, true, false, float>
+                                              : agent_feed_kernel<false, false, false, false, float>);
+    }
     FeedArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.agents = agents; fa.action = action;
-    fa.consumed_field = e->consumed + (size_t)b0 * C;
+    fa.consumed_field = field_off(e, e->consumed, (size_t)b0 * C);
     fa.winner = winner; fa.cells = cells; fa.part_gain = part_gain; fa.part_alive = part_alive;
     fa.C = (int64_t)C; fa.M = e->M; fa.nblk = e->nblk;
     fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
@@ -678,6 +714,7 @@ static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_ou
                               double* agents_host, double* medium_host,
                               double* reward_host, int64_t* alive_host, void* stream) {
     DIE_REQUIRE(e != nullptr && (action_host != nullptr) != (action_dev != nullptr));
+    if (e->field_f32) return fail(DIE_E_INVALID, "the host-buffer step runs float64 fields only%s%s");
     DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out && agents != nullptr);
     DIE_REQUIRE(reward_host != nullptr && alive_host != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
@@ -892,7 +929,8 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
                                  const uint8_t* coin, const double* noise, int32_t* sense_cells,
                                  const double* grad_hint, const int32_t* cells_hint,
                                  uint64_t seed, uint64_t step, void* stream, int b0 = 0,
-                                 const float2* grad32_hint = nullptr, const uint64_t* step_dev = nullptr) {
+                                 const float2* grad32_hint = nullptr, const uint64_t* step_dev = nullptr,
+                                 bool field_f32 = false) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -949,6 +987,13 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
             else kern = gradient_forward_kernel<true, false, false, 4, true>;
         }
     }
+    if (field_f32) {               // the medium holds float32: the same kernels reading float (64-register variants only)
+        if (speculate) return fail(DIE_E_INVALID, "the speculative move is not available with float32 fields%s%s");
+        if (lean) kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, false, 4, true, true, float>
+                                               : gradient_forward_kernel<true, false, false, 4, true, false, float>;
+        else kern = p->discrete_turn ? gradient_forward_kernel<true, false, false, 4, false, false, float>
+                                     : gradient_forward_kernel<false, false, false, 4, false, false, float>;
+    }
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
     ++(lean ? (a.grad32 != nullptr ? g_count_fwd_lean_f32 : g_count_fwd_lean) : g_count_fwd_general);
@@ -966,6 +1011,16 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
                                     uint64_t seed, uint64_t step, void* stream) {
     return gradient_forward_impl(nullptr, false, p, H, W, M, B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
+}
+
+extern "C" int die_gradient_forward_f32(const die_gradient_params_t* p,
+                                        int32_t H, int32_t W, int64_t M, int32_t B,
+                                        const double* agents, const float* medium,
+                                        double* theta, double* prev_grad, double* action,
+                                        const uint8_t* coin, const double* noise,
+                                        int32_t* sense_cells, uint64_t seed, uint64_t step, void* stream) {
+    return gradient_forward_impl(nullptr, false, p, H, W, M, B, agents, (const double*)medium, theta, prev_grad, action,
+                                 coin, noise, sense_cells, nullptr, nullptr, seed, step, stream, 0, nullptr, nullptr, true);
 }
 
 extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_t* p,
@@ -990,7 +1045,7 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
     const uint64_t* step_dev = (flags & DIE_FWD_STEP_ON_DEVICE) ? (const uint64_t*)(uintptr_t)step : nullptr;
     return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step_dev ? 0 : step, stream, 0,
-                                 grad32_hint, step_dev);
+                                 grad32_hint, step_dev, e->field_f32 != 0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -32,8 +32,8 @@ struct BlurWeights {
 };
 
 struct FieldArgs {
-    const double* medium_in;
-    double* medium_out;
+    const double* medium_in;     // element type = the kernel's FT (float64, or float32 in the env's float32 field mode:
+    double* medium_out;          // the three field arrays medium_in / medium_out / consumed are then arrays of float)
     const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
     const double* action;        // [B][3][M]; channel 2 = deposit1
     double* consumed;            // [B][H*W] consumed_field out
@@ -119,9 +119,15 @@ __device__ __forceinline__ int extend_index(int i, int n, int mode) {
 // (register caps were tried: 40 / 48 / 56 / 72 registers give 299 / 279 / 250 / 273 us at 4096^2; the compiler's own
 //  choice without a minimum-blocks hint, 60 registers = 4 CTAs per SM, is the best at 241 us)
 // PLAIN: the reference's default dynamics (periodic diffusion, identity food flow) known at compile time.
-template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB, bool PLAIN = false>
+// FT: element type of the field arrays in HBM (medium, consumed_field).  float64 as in the reference, or float32 (the
+// env's float32 field mode): values are widened on load, every operation stays the float64 one, and
+// results are rounded once on store -- 24 instead of 48 B per cell-update.  The published gradient is formed from the
+// ROUNDED chem1 values, so it equals np.gradient of the stored field exactly (what a forward kernel that samples chem1
+// itself computes).
+template <int R, int TH, int TW, int NT, bool GRAD, bool SLAB, bool PLAIN = false, typename FT = double>
 __global__ void __launch_bounds__(NT)
 field_step_kernel(const FieldArgs a) {
+    static_assert(!SLAB || sizeof(FT) == 8, "the slab decomposition runs float64 fields");
     constexpr int G = GRAD ? 1 : 0;
     constexpr int OH = TH + 2 * G, OW = TW + 2 * G;     // blurred region
     constexpr int LW = OW + 2 * R;                      // staged row length
@@ -142,23 +148,23 @@ field_step_kernel(const FieldArgs a) {
     const int ti = t / a.tiles_j, tj = t - ti * a.tiles_j;
     const int i0 = ti * TH, j0 = tj * TW;    // LOCAL row / column of the tile
 
-    const double* min_l = SLAB ? a.st.medium_in[a.sg.rank] : a.medium_in + b * 3 * C;
-    double* mout_l = SLAB ? a.st.medium_out[a.sg.rank] : a.medium_out + b * 3 * C;
-    const double* food_in = min_l + C;
-    const double* chem_in = min_l + 2 * C;
-    double* occ_out = mout_l;
-    double* food_out = mout_l + C;
-    double* chem_out = mout_l + 2 * C;
+    const FT* min_l = SLAB ? (const FT*)a.st.medium_in[a.sg.rank] : (const FT*)a.medium_in + b * 3 * C;
+    FT* mout_l = SLAB ? (FT*)a.st.medium_out[a.sg.rank] : (FT*)a.medium_out + b * 3 * C;
+    const FT* food_in = min_l + C;
+    const FT* chem_in = min_l + 2 * C;
+    FT* occ_out = mout_l;
+    FT* food_out = mout_l + C;
+    FT* chem_out = mout_l + 2 * C;
     const int32_t* win = SLAB ? a.st.claim[a.sg.rank] : a.winner + b * C;
     const double* dep = SLAB ? nullptr : a.action + (b * 3 + 2) * a.M;
-    double* cons = SLAB ? a.st.consumed[a.sg.rank] : a.consumed + b * C;
+    FT* cons = SLAB ? (FT*)a.st.consumed[a.sg.rank] : (FT*)a.consumed + b * C;
 
     // food of the output tile is only needed by the last phase: pull its lines towards L2 now, so that
     // those loads do not start a fresh DRAM round trip after the blur (one 128-byte line per thread)
     if (a.prefetch_food) {
-        constexpr int LINES_PER_ROW = TW * 8 / 128;
+        constexpr int LINES_PER_ROW = TW * (int)sizeof(FT) / 128;
         for (int l = threadIdx.x; l < TH * LINES_PER_ROW; l += NT) {
-            const int r = l / LINES_PER_ROW, c = (l - r * LINES_PER_ROW) * 16;
+            const int r = l / LINES_PER_ROW, c = (l - r * LINES_PER_ROW) * (128 / (int)sizeof(FT));
             if (i0 + r < HL && j0 + c < W)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(food_in + (int64_t)(i0 + r) * W + j0 + c));
         }
@@ -182,7 +188,7 @@ field_step_kernel(const FieldArgs a) {
                 v[s] = __ldg(slab_chan(a.st.medium_in, a.sg, 2, g));
                 w[s] = __ldg(slab_cell(a.st.claim, a.sg, g));
             } else if (PLAIN || (gi >= 0 && gj >= 0)) {  // ('constant' extension: 0, no deposit)
-                v[s] = chem_in[g];
+                v[s] = (double)chem_in[g];
                 w[s] = win[g];
             }
         }
@@ -228,13 +234,13 @@ field_step_kernel(const FieldArgs a) {
                 double acc = p[0] * a.bw.w[R];
 #pragma unroll
                 for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
-                chem_out[g] = acc * a.keep;
+                chem_out[g] = (FT)(acc * a.keep);
                 const double occ = (win[g] >= 0) ? 1.0 : 0.0;
-                const double f = food_in[g];
+                const double f = (double)food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
-                occ_out[g] = occ;
-                cons[g] = cf;
+                food_out[g] = (FT)next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+                occ_out[g] = (FT)occ;
+                cons[g] = (FT)cf;
             }
         }
     } else {
@@ -245,7 +251,7 @@ field_step_kernel(const FieldArgs a) {
         double acc = p[0] * a.bw.w[R];
 #pragma unroll
         for (int k = R; k >= 1; --k) acc += (p[-k] + p[k]) * a.bw.w[R - k];
-        s_out[idx] = acc * a.keep;
+        s_out[idx] = (double)(FT)(acc * a.keep);         // (float32 fields: the value as it will be stored)
     }
     __syncthreads();
 
@@ -259,7 +265,7 @@ field_step_kernel(const FieldArgs a) {
         const int g = li * W + gj;
         if (li < HL && gj < W) {
             const double* q = s_out + (r + 1) * OW + (c + 1);
-            chem_out[g] = q[0];
+            chem_out[g] = (FT)q[0];
             // np.gradient: (f[i+1] - f[i-1]) / 2 inside, f[1] - f[0] / f[n-1] - f[n-2] at the edges
             const int um = (gi > 0) ? -OW : 0, up = (gi < H - 1) ? OW : 0;
             const int lm = (gj > 0) ? -1 : 0, lp = (gj < W - 1) ? 1 : 0;
@@ -271,11 +277,11 @@ field_step_kernel(const FieldArgs a) {
             else grad[g] = make_double2(gx, gy);
 
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
-            const double f = food_in[g];
+            const double f = (double)food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
-            food_out[g] = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
-            occ_out[g] = occ;
-            cons[g] = cf;
+            food_out[g] = (FT)next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+            occ_out[g] = (FT)occ;
+            cons[g] = (FT)cf;
         }
     }
     }   // GRAD
@@ -555,24 +561,24 @@ render_frames_kernel(const RenderArgs a, int64_t total) {
 }
 
 // No diffusion (blur_radius == 0): gaussian with radius 0 is the identity (w = [1]).
-template <int NT>
+template <int NT, typename FT = double>
 __global__ void __launch_bounds__(NT)
 field_step_noblur_kernel(const FieldArgs a, int64_t total) {
     const int64_t C = (int64_t)a.H * a.W;
     for (int64_t gid = (int64_t)blockIdx.x * NT + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * NT) {
         const int64_t b = gid / C, g = gid - b * C;
-        const double* min = a.medium_in + b * 3 * C;
-        double* mout = a.medium_out + b * 3 * C;
+        const FT* min = (const FT*)a.medium_in + b * 3 * C;
+        FT* mout = (FT*)a.medium_out + b * 3 * C;
         const int w = a.winner[gid];
         const double occ = (w >= 0) ? 1.0 : 0.0;
-        const double f = min[C + g];
+        const double f = (double)min[C + g];
         const double cf = (a.rate_feed * f) * occ;
-        double chem = min[2 * C + g];
+        double chem = (double)min[2 * C + g];
         if (w >= 0) chem = chem + a.action[(b * 3 + 2) * a.M + w];
-        mout[g] = occ;
-        mout[C + g] = next_food(a, f, cf, (int)(g / a.W), (int)(g % a.W), g);
-        mout[2 * C + g] = (chem * a.bw.w[0]) * a.bw.w[0] * a.keep;
-        a.consumed[gid] = cf;
+        mout[g] = (FT)occ;
+        mout[C + g] = (FT)next_food(a, f, cf, (int)(g / a.W), (int)(g % a.W), g);
+        mout[2 * C + g] = (FT)((chem * a.bw.w[0]) * a.bw.w[0] * a.keep);
+        ((FT*)a.consumed)[gid] = (FT)cf;
     }
 }
 

@@ -143,6 +143,11 @@ def _dynamics_to_c(d: Dynamics) -> _lib.DieDynamics:
     return c
 
 
+def _check_f32_dynamics(c: _lib.DieDynamics) -> None:
+    if c.blur_radius > 4:
+        raise NotImplementedError(f"float32 fields support blur radius <= 4 (this diffuse_sigma gives {c.blur_radius})")
+
+
 class Env:
     """core/env.py:64-298."""
 
@@ -155,13 +160,23 @@ class Env:
                  noise_seed: Optional[int] = None,
                  init_state: Optional[Tuple[np.ndarray, np.ndarray]] = None,
                  init: str = 'host',
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None,
+                 field_dtype: Union[torch.dtype, str] = torch.float64):
         """``init='host'`` (default) builds the initial state with numpy in the reference's draw order
         (``np.random.seed`` reproduces it); ``init='device'`` builds it on the GPU (die_b200/device_init.py:
         same arithmetic and slot order, torch's device generator seeded by ``seed``) -- the only practical
         choice for 4096^2 and beyond, where the reference's per-cell Python loop takes minutes."""
         if not torch.cuda.is_available():
             raise RuntimeError("die_b200.Env needs a CUDA device: there is no CPU fallback")
+        # float64 as in the reference (default), or the float32 FIELD mode: the medium (and the library's per-cell
+        # scratch) in float32, agents / actions / headings still float64 -- half the field bytes, results within float32
+        # rounding of the float64 ones per step (tests/test_gpu_f32_fields.py) instead of bit-exact
+        self._field_dtype = {torch.float64: torch.float64, 'float64': torch.float64, 'f64': torch.float64,
+                             torch.float32: torch.float32, 'float32': torch.float32, 'f32': torch.float32}.get(field_dtype)
+        if self._field_dtype is None:
+            raise ValueError("field_dtype must be torch.float64 or torch.float32")
+        if self._field_dtype == torch.float32 and (dynamics is not None and dynamics.apply_sense_mask):
+            raise NotImplementedError("apply_sense_mask is implemented for float64 fields only")
         self._lib = _lib.load()
         self._field_size = (int(field_size[0]), int(field_size[1]))
         self.dynamics = dynamics or Dynamics()
@@ -203,7 +218,7 @@ class Env:
             medium, agents = np.stack(mediums), np.stack(agentss)
         elif isinstance(init_state[0], torch.Tensor):
             # device (or host) tensors: no numpy round trip (large batches are assembled on the GPU)
-            medium = init_state[0].to(dtype=torch.float64).reshape(B, 3, h, w)
+            medium = init_state[0].to(dtype=self._field_dtype).reshape(B, 3, h, w)
             agents = init_state[1].to(dtype=torch.float64).reshape(B, 4, -1)
         else:
             medium, agents = (np.asarray(a, dtype=np.float64) for a in init_state)
@@ -212,16 +227,16 @@ class Env:
         self._M = int(agents.shape[-1])
         with torch.cuda.device(self.device):
             if isinstance(medium, torch.Tensor):
-                first = medium.to(self.device).contiguous()
+                first = medium.to(self.device, dtype=self._field_dtype).contiguous()
                 self._agents = agents.to(self.device).contiguous()
                 if not owned:               # never alias the caller's tensors
                     first = first.clone() if first.data_ptr() == init_state[0].data_ptr() else first
                     self._agents = self._agents.clone() if self._agents.data_ptr() == init_state[1].data_ptr() \
                         else self._agents
             else:
-                first = torch.from_numpy(np.ascontiguousarray(medium)).to(self.device)
+                first = torch.from_numpy(np.ascontiguousarray(medium)).to(self.device, dtype=self._field_dtype)
                 self._agents = torch.from_numpy(np.ascontiguousarray(agents)).to(self.device)
-            self._medium_buf = [first, torch.empty((B, 3, h, w), dtype=torch.float64, device=self.device)]
+            self._medium_buf = [first, torch.empty((B, 3, h, w), dtype=self._field_dtype, device=self.device)]
             self._cur = 0
             self._reward_dev = torch.zeros(B, dtype=torch.float64, device=self.device)
             self._alive_dev = torch.zeros(B, dtype=torch.int64, device=self.device)
@@ -233,8 +248,12 @@ class Env:
                 self._handle = None
             handle = _lib.C.c_void_p()
             cdyn = _dynamics_to_c(self.dynamics)
+            if self._field_dtype == torch.float32:
+                _check_f32_dynamics(cdyn)
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
+            if self._field_dtype == torch.float32:
+                _lib.check(self._lib.die_env_set_field_dtype(handle, _lib.FIELD_F32))
             self._dynamics_key = self._dynamics_snapshot()
             self._install_food_flow()
             # Dynamics.apply_sense_mask: the observation is a masked COPY of the medium (core/env.py:275-294)
@@ -300,6 +319,10 @@ class Env:
         if key == self._dynamics_key:
             return
         cdyn = _dynamics_to_c(self.dynamics)            # raises for what the kernels do not implement
+        if self.dynamics.apply_sense_mask and self._field_dtype != torch.float64:
+            raise NotImplementedError("apply_sense_mask is implemented for float64 fields only")
+        if self._field_dtype == torch.float32:
+            _check_f32_dynamics(cdyn)
         _lib.check(self._lib.die_env_set_dynamics(self._handle, _lib.C.byref(cdyn)))
         if key[1] is not self._dynamics_key[1]:
             self._install_food_flow()
@@ -365,6 +388,10 @@ class Env:
         return self._field_size
 
     @property
+    def field_dtype(self) -> torch.dtype:
+        return self._field_dtype
+
+    @property
     def max_agents(self) -> int:
         return self._M
 
@@ -392,7 +419,7 @@ class Env:
     def set_state(self, medium=None, agents=None) -> None:
         if medium is not None:
             src = torch.as_tensor(np.asarray(medium, dtype=np.float64)).reshape(self._medium_buf[0].shape)
-            self._medium_buf[self._cur].copy_(src)
+            self._medium_buf[self._cur].copy_(src)          # (rounds to float32 in the float32 field mode)
             if self._obs_buf is not None:
                 self._refresh_sensed_medium()
         if agents is not None:
@@ -480,7 +507,8 @@ class Env:
         the alive bitmask is rebuilt here whenever the agents tensor was edited)."""
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
-        if speculate and not self.dynamics.agents_die and agents.data_ptr() == self._agents.data_ptr() \
+        if speculate and not self.dynamics.agents_die and self._field_dtype == torch.float64 \
+                and agents.data_ptr() == self._agents.data_ptr() \
                 and agents.numel() == self._agents.numel():
             with _lib.on_device(self.device):
                 self._refresh_alive(torch.cuda.current_stream().cuda_stream)
@@ -535,6 +563,8 @@ class Env:
         return self._host
 
     def _step_host(self, action: np.ndarray):
+        if self._field_dtype != torch.float64:
+            raise NotImplementedError("the host-buffer path (numpy actions) runs float64 fields only")
         hb = self.host_buffers()
         B, M = self._B, self._M
         self._sync_dynamics()
@@ -594,6 +624,8 @@ class Env:
     def render(self, host: bool = False):
         """core/env.py:133-134: the frames of EnvRenderer.render(medium, agents) (die_b200/render.py), device tensors
         by default, numpy arrays in pinned memory with ``host=True``."""
+        if self._field_dtype != torch.float64:
+            raise NotImplementedError("render() is implemented for float64 fields only")
         if getattr(self, '_renderer', None) is None or self._renderer._B != self._B:
             from .render import EnvRenderer
             self._renderer = EnvRenderer(self._field_size, field_colors_id='rgb', batch=self._B, device=self.device)

@@ -91,6 +91,17 @@ typedef struct die_env die_env_t;
 const char* die_version(void);
 const char* die_last_error(void);
 
+/* Field dtype.  The reference computes in float64 throughout (numpy defaults) and that is the default here; in the
+ * float32 field mode the arrays that hold FIELDS in HBM -- medium A/B and the consumed_field scratch -- are float32
+ * (24 instead of 48 B per cell-update), agents / actions / headings stay float64 (cell indices stay bit-exact for a given
+ * action), values are widened on load and every operation is the float64 one, rounded once on store.  Call right after
+ * die_env_create, before the first step; every `medium` pointer of the env's entry points is then a float array.
+ * Not available in this mode: the host-buffer step, the speculative move, the cluster-fused step, blur radius > 4. */
+#define DIE_FIELD_F64 0
+#define DIE_FIELD_F32 1
+int die_env_set_field_dtype(die_env_t* env, int32_t dtype);
+int die_env_field_dtype(const die_env_t* env);
+
 /* Env.__init__ workspace (core/env.py:65-72): per-cell claim table, per-slot cell cache,
  * reduction partials.  Must be called with the target device current. */
 int die_env_create(int32_t H, int32_t W, int64_t M, int32_t B,
@@ -264,6 +275,13 @@ int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient_params_t* 
 #define DIE_FWD_USE_GRADIENT    1
 #define DIE_FWD_USE_CELLS       2
 #define DIE_FWD_SPECULATE_MOVE  4
+/* die_gradient_forward on a float32 medium (an observation that did not come from an env, or whose hints are off). */
+int die_gradient_forward_f32(const die_gradient_params_t* p, int32_t H, int32_t W, int64_t M, int32_t B,
+                             const double* agents_dev, const float* medium_dev,
+                             double* theta_dev, double* prev_grad_dev, double* action_dev,
+                             const uint8_t* coin_dev, const double* noise_dev, int32_t* sense_cells_dev,
+                             uint64_t seed, uint64_t step, void* stream);
+
 /*   DIE_FWD_STEP_ON_DEVICE  `step` is not the call counter but the DEVICE ADDRESS of a uint64 holding it: a CUDA graph
  *                           that captured this call can be replayed while something else (a captured increment) advances
  *                           the counter, so every replay draws fresh in-kernel random numbers (die_b200/graph.py) */

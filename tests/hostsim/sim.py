@@ -103,21 +103,24 @@ def gradient_params(scale=0.005, deposit=4.0, inertia=0.0, sense_offset=0.03, no
 class SimEnv:
     """die_b200.Env's call sequence on numpy arrays."""
 
-    def __init__(self, field_size, medium, agents, dynamics: Dynamics = None, batch=None):
+    def __init__(self, field_size, medium, agents, dynamics: Dynamics = None, batch=None, field_dtype=np.float64):
         self.lib = lib()
         self.h, self.w = int(field_size[0]), int(field_size[1])
         self.B = int(batch) if batch is not None else 1
         self.dynamics = dynamics or Dynamics()
         self.agents = fenced_copy(np.asarray(agents, dtype=np.float64).reshape(self.B, 4, -1))
         self.M = self.agents.shape[-1]
-        first = fenced_copy(np.asarray(medium, dtype=np.float64).reshape(self.B, 3, self.h, self.w))
-        self.medium_buf = [first, fenced(first.shape, fill=np.nan)]
+        self.field_dtype = np.dtype(field_dtype)
+        first = fenced_copy(np.asarray(medium, dtype=self.field_dtype).reshape(self.B, 3, self.h, self.w))
+        self.medium_buf = [first, fenced(first.shape, self.field_dtype, fill=np.nan)]
         self.cur = 0
         self.reward = fenced((self.B,), fill=0.0)
         self.alive = fenced((self.B,), np.int64, fill=0)
         self.handle = C.c_void_p()
         cdyn = _dynamics_to_c(self.dynamics)
         check(self.lib.die_env_create(self.h, self.w, self.M, self.B, C.byref(cdyn), C.byref(self.handle)))
+        if self.field_dtype == np.float32:
+            check(self.lib.die_env_set_field_dtype(self.handle, L.FIELD_F32))
         self.publish_grad = False
         self.hints_valid = False
         self._flow = None
