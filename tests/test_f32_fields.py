@@ -36,7 +36,7 @@ def _shadow_step_checks(ref, env, it):
         err = np.abs(med32[ch].astype(np.float64) - ref.medium[ch])
         assert (err <= EPS32 * np.abs(ref.medium[ch]) + TINY32).all(), f"{name} beyond float32 rounding at step {it}"
     assert np.array_equal(env.agents[0, :3], ref.agents[:3]), f"positions / alive differ at step {it}"
-    np.testing.assert_allclose(env.agents[0, 3], ref.agents[3], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(env.agents[0, 3], ref.agents[3], rtol=1e-6, atol=1e-7)   # (one rounding of consumed_field, <= 6e-8 absolute, also where the stock crosses 0)
     assert np.array_equal(ref_cells_linear(ref), env.cells()[0])
 
 
@@ -94,7 +94,7 @@ def test_float32_fields_brownian_free_run_bound():
         assert np.array_equal(env.agents[0, :3], ref.agents[:3])
     for ch in (1, 2):
         np.testing.assert_allclose(env.medium[0][ch].astype(np.float64), ref.medium[ch], rtol=1e-5, atol=1e-12)
-    np.testing.assert_allclose(env.agents[0, 3], ref.agents[3], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(env.agents[0, 3], ref.agents[3], rtol=1e-5, atol=1e-6)
 
 
 def test_float32_mode_refuses_what_it_does_not_implement():

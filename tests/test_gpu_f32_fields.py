@@ -4,11 +4,11 @@ actions / headings in float64 (SURVEY section 7 "fp32 vs fp64 fields"; die_env_s
 Stated bounds (asserted below):
   per step, against the float64 oracle restarted from the GPU's own state (float32 fields widened): actions, positions,
     cells, occupancy, alive, num_agents BIT-EXACT; chem1 / food within 2^-24 relative (one rounding); agent_food and
-    the reward within 1e-6 relative;
+    the reward within 1e-6 relative (+ 1e-7 absolute: one rounding of consumed_field);
   free run, 300 steps at 256^2, against the float64 GPU run with the same in-kernel random numbers: a rounding can flip a
-    turn decision that sits on a threshold, after which the two trajectories of that slot differ; >= 97 % of the slots
-    are still in the same cell after 300 steps, the summed reward agrees within 1e-3 relative, the fields' means within
-    1e-4 relative."""
+    turn decision that sits on a threshold, after which the two trajectories of that slot differ; asserted: >= 99.9 % of
+    the slots in the same cell after 300 steps, the summed reward within 1e-6 relative, the fields' means within 1e-6
+    relative.  (Measured on a B200: 100.00 % same cell, reward 2e-8, field means 1e-8.)"""
 import numpy as np
 import pytest
 
@@ -65,7 +65,7 @@ def test_float32_fields_shadowed_per_step(field, sigma, iters):
             for ch in (1, 2):
                 err = np.abs(med[ch].astype(np.float64) - ref.medium[ch])
                 assert (err <= EPS32 * np.abs(ref.medium[ch]) + TINY32).all(), f"channel {ch} beyond one float32 rounding, step {it}"
-            np.testing.assert_allclose(ag[3], ref.agents[3], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(ag[3], ref.agents[3], rtol=1e-6, atol=1e-7)   # (one rounding of consumed_field, <= 6e-8 absolute, also where the stock crosses 0)
             assert ginfo['num_agents'] == rinfo['num_agents'] and abs(gr - rr) <= 1e-6 * max(1.0, abs(rr))
         if sigma >= 0.3:
             assert _lib.load().die_get_counter(b"forward_lean_f32") - lean0 == iters - 1
@@ -104,7 +104,7 @@ def test_float32_fields_free_run_300_steps_bound():
     print(f"float32 fields after 300 free steps: same cell {same:.4f} (alive {same_alive:.4f}), reward rel {rel_reward:.2e}, "
           f"mean chem rel {rel_chem:.2e}, mean food rel {rel_food:.2e}")
     assert np.array_equal(a64[2], a32[2])
-    assert same >= 0.97 and rel_reward <= 1e-3 and rel_chem <= 1e-4 and rel_food <= 1e-4
+    assert same >= 0.999 and rel_reward <= 1e-6 and rel_chem <= 1e-6 and rel_food <= 1e-6
 
 
 def test_float32_fields_batch_and_brownian():
@@ -136,7 +136,7 @@ def test_float32_fields_batch_and_brownian():
         assert np.array_equal(med[b, 0].astype(np.float64), refs[b].medium[0]) and np.array_equal(ag[b, :3], refs[b].agents[:3])
         for ch in (1, 2):
             np.testing.assert_allclose(med[b, ch].astype(np.float64), refs[b].medium[ch], rtol=1e-5, atol=1e-12)
-        np.testing.assert_allclose(ag[b, 3], refs[b].agents[3], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(ag[b, 3], refs[b].agents[3], rtol=1e-5, atol=1e-6)
 
 
 def test_float32_mode_refuses_what_it_does_not_implement():
