@@ -130,6 +130,9 @@ struct GradientArgs {
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
     uint64_t seed, step;
     const uint64_t* step_dev;   // may be null; else the call counter is read from device memory (CUDA-graph replays)
+    double sense_guard_x, sense_guard_y;   // > 0: the sense position may be formed with the float32 sin / cos of
+                                // die_sincosf_approx; a sensed cell within this many cells of a cell boundary is re-evaluated
+                                // with die_sincos (|sense_offset| DIE_SINCOSF_ERR (n - 1) + 1e-9); 0: always die_sincos
     int b0;                     // the launch covers environments [b0, b0 + B') of a larger batch (pointers already offset):
                                 // only the in-kernel RNG needs to know, so that chunked launches draw the same numbers
     // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
@@ -252,13 +255,27 @@ gradient_forward_kernel(const GradientArgs a) {
             if (LEAN || cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
         }
 
-        // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin)
-        double sn, cs;
-        die_sincos(th, &sn, &cs);
-        const double px = x + p.sense_offset * cs;
-        const double py = y + p.sense_offset * sn;
-        // field_by_agents(grad_field, offset) (:105): nearest, CLAMPED not wrapped (Q4)
-        const int sx = nearest_cell(px, ax), sy = nearest_cell(py, ay);
+        // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin); field_by_agents(grad_field, offset) (:105): nearest,
+        // CLAMPED not wrapped (Q4).  sin / cos of the heading are needed for the sensed CELL and for the guard-banded
+        // turn decision only, so a float32 evaluation (+-4e-7) serves both wherever the cell is not within the guard of a
+        // cell boundary; elsewhere (about one slot in 10^5) the float64 die_sincos decides, as it used to for every slot.
+        float sf, cf;
+        int sx, sy;
+        bool cell_ok = false;
+        if (a.sense_guard_x > 0.0 && fabs(th) <= DIE_SINCOSF_MAX) {
+            die_sincosf_approx(th, &sf, &cf);
+            const bool okx = nearest_cell_guarded(x + p.sense_offset * (double)cf, ax, a.sense_guard_x, &sx);
+            const bool oky = nearest_cell_guarded(y + p.sense_offset * (double)sf, ay, a.sense_guard_y, &sy);
+            cell_ok = okx & oky;
+        }
+        if (!cell_ok) {
+            double sn, cs;
+            die_sincos(th, &sn, &cs);
+            sx = nearest_cell(x + p.sense_offset * cs, ax);
+            sy = nearest_cell(y + p.sense_offset * sn, ay);
+            sf = (float)sn;
+            cf = (float)cs;
+        }
 
         // np.gradient at (sx, sy): central (f[i+1] - f[i-1]) / 2 inside, one-sided f[1] - f[0] /
         // f[n-1] - f[n-2] at the edges, non-periodic (Q5): clamped neighbours give both forms
@@ -298,7 +315,7 @@ gradient_forward_kernel(const GradientArgs a) {
             // the rest (about one warp in 300) runs the reference's own arithmetic, die_turn_exact.
             die_turn_t tr;
             double dr = 1.0;
-            if (!((LEAN || a.plan.enabled) && die_turn_quick(&a.plan, gx, gy, sn, cs, th, atol, p.sense_radians, &tr))) {
+            if (!((LEAN || a.plan.enabled) && die_turn_quick_f(&a.plan, gx, gy, sf, cf, th, atol, p.sense_radians, &tr))) {
                 if (from32) sample_gradient(chem, sx, sy, H, W, gx, gy);     // the exact path wants all 53 bits
                 if (LEAN) {           // (normalised gradient: dr = 1)
                     tr = turn_exact_call(gx, gy, th, atol, p.sense_radians, 1, p.use_grad_clip, p.grad_clip);

@@ -888,6 +888,7 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
 }
 
 static int g_turn_quick = 1;       // 0: every slot runs die_turn_exact (diagnosis / A-B tests; same results)
+static int g_sense_quick = 1;      // 0: the sensed cell always comes from the float64 die_sincos (A-B tests; same results)
 static int g_fwd_lean = 1;         // use the LEAN instantiation of the forward kernel when its preconditions hold
 static int g_fwd_min_blocks = 4;   // register cap of the forward kernel (3 / 4 / 5 resident CTAs per SM)
 
@@ -899,6 +900,7 @@ extern "C" int die_set_turn_quick(int32_t on) {
 extern "C" int die_set_tuning(const char* key, int32_t value) {
     DIE_REQUIRE(key != nullptr);
     if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;
+    else if (strcmp(key, "sense_quick") == 0) g_sense_quick = value ? 1 : 0;
     else if (strcmp(key, "fwd_min_blocks") == 0) { DIE_REQUIRE(value >= 3 && value <= 5); g_fwd_min_blocks = value; }
     else if (strcmp(key, "feed_bits") == 0) g_feed_bits = value ? 1 : 0;
     else if (strcmp(key, "host_chunks") == 0) { DIE_REQUIRE(value >= 1 && value <= 64); g_host_chunks = value; }
@@ -954,6 +956,10 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
         a.grad32 = grad32_hint;
     a.seed = seed; a.step = step;
     a.step_dev = step_dev;
+    if (g_sense_quick) {           // float32 sin / cos for the sensed cell, guarded (die_device.cuh: nearest_cell_guarded)
+        a.sense_guard_x = fabs(p->sense_offset) * DIE_SINCOSF_ERR * a.ax.nm1 + 1e-9;
+        a.sense_guard_y = fabs(p->sense_offset) * DIE_SINCOSF_ERR * a.ay.nm1 + 1e-9;
+    }
     a.b0 = b0;
     const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
     cudaStream_t st = (cudaStream_t)stream;

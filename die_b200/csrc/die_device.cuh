@@ -60,6 +60,20 @@ __device__ __forceinline__ int nearest_cell(double c, const Axis& a) {
     return min(max(r, 0), a.n - 1);
 }
 
+// The same cell from a coordinate known only to +-guard cells (the sense position formed with the float32 cosine of
+// die_sincosf_approx): frac = distance of c (n-1) above the integer below it; the nearest grid coordinate changes at
+// frac = 0.5, so the answer is robust -- equal to nearest_cell of the exact coordinate -- iff |frac - 0.5| > guard
+// (nearest_cell's own comparison errs by ~1e-13 cells: `guard` includes 1e-9 for it).  Returns false where the caller
+// must evaluate the exact coordinate instead (also for NaN / absurd coordinates).
+__device__ __forceinline__ bool nearest_cell_guarded(double c, const Axis& a, double guard, int* cell) {
+    const double t = __dmul_rn(c, a.nm1);
+    const double u = __dadd_rn(__dsub_rn(t, 0.5), DIE_RINT_MAGIC);
+    const int i = __double2loint(u);
+    const double frac = __dsub_rn(t, __dsub_rn(u, DIE_RINT_MAGIC));          // in [0, 1]
+    *cell = min(max(frac < 0.5 ? i : i + 1, 0), a.n - 1);
+    return fabs(c) < 4.0 && fabs(__dsub_rn(frac, 0.5)) > guard;
+}
+
 // ---- numpy float remainder, renormalize_radians, np.angle, nan_to_num ------------------------
 // The turn-rule arithmetic lives in die_turn.h (host + device, so its guard-band logic is testable on
 // the CPU); these are the device-side names the kernels use.

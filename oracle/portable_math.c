@@ -16,6 +16,11 @@ void die_atan2_fast_array(const double* y, const double* x, double* out, long n)
     for (long i = 0; i < n; ++i) out[i] = die_atan2_fast(y[i], x[i]);
 }
 
+/* the guard-banded float32 sin / cos of the forward kernel (tests only: its error bound is checked against die_sincos) */
+void die_sincosf_approx_array(const double* x, float* sn, float* cs, long n) {
+    for (long i = 0; i < n; ++i) die_sincosf_approx(x[i], sn + i, cs + i);
+}
+
 void die_sincos_angle_array(const double* x, double* sn, double* cs, double* ang, long n) {
     for (long i = 0; i < n; ++i) die_sincos_angle(x[i], sn + i, cs + i, ang + i);
 }

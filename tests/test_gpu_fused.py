@@ -170,7 +170,7 @@ def test_one_agent_two_envs_never_adopts_the_wrong_speculation():
     _same(env_b, ref_b, ag, ag_ref)
 
 
-@pytest.mark.parametrize("key,values", [("turn_quick", (1, 0)), ("fwd_min_blocks", (4, 3, 5)), ("feed_bits", (1, 0)), ("field_prefetch", (1, 0)), ("fwd_lean", (1, 0, 5))])
+@pytest.mark.parametrize("key,values", [("turn_quick", (1, 0)), ("fwd_min_blocks", (4, 3, 5)), ("feed_bits", (1, 0)), ("field_prefetch", (1, 0)), ("fwd_lean", (1, 0, 5)), ("sense_quick", (1, 0))])
 def test_tuning_switches_do_not_change_results(key, values):
     """Free-running 60 steps (in-kernel Philox coins, identical seeds) under every setting of a switch."""
     import die_b200 as D

@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -243,7 +243,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1])])
+                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1]), ("sense_quick", [0])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
@@ -350,6 +350,43 @@ def test_fused_step_falls_back_where_it_does_not_apply(tuning):
         for it in range(2):
             env.step(ga.forward(env))
     assert S.lib().die_get_counter(b"step_fused") == fused0
+
+
+def test_sensed_cells_next_to_cell_boundaries(portable_math, tuning):
+    """sense_quick: the sense position pos + sense_offset (cos, sin)(theta) is formed with a float32 sin / cos (+-4e-7)
+    and accepted only if the sensed cell is not within the guard of a cell boundary; otherwise the float64 die_sincos
+    decides.  Adversarial slots: positions placed so that the EXACT sense coordinate lies on a boundary between two
+    cells, and 1e-12 ... 1e-6 cells to either side of it, on both axes, for headings all around the lattice."""
+    field = (40, 72)
+    np.random.seed(3)
+    ref = R.Env(field, R.Dynamics(init_agent_ratio=0.1), noise_seed=3)
+    m = ref.agents.shape[-1]
+    rng = np.random.default_rng(0)
+    so = 0.04
+    theta = (rng.integers(-6, 7, m) * np.radians(30)).astype(np.float64)
+    theta[::7] = rng.uniform(-np.pi, np.pi, theta[::7].size)
+    sn, cs = R.math_sincos(theta) if hasattr(R, "math_sincos") else (np.sin(theta), np.cos(theta))
+    deltas = np.array([0.0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-8, -3e-8, 2e-7, -2e-7, 4.5e-7, -4.5e-7, 1e-6, -1e-6])
+    for axis, (n, off) in enumerate(((field[0], so * cs), (field[1], so * sn))):
+        k = rng.integers(1, n - 2, m)
+        target = (k + 0.5 + deltas[rng.integers(0, deltas.size, m)]) / (n - 1)       # a boundary between cells k and k + 1
+        ref.agents[axis] = np.clip(target - off, 0.0, 1.0)
+    env = S.SimEnv(field, ref.medium[None], ref.agents[None], D.Dynamics(init_agent_ratio=0.1))
+    outs = []
+    for quick in (1, 0):
+        tuning("sense_quick", quick)
+        ga = S.SimGradientAgent(m, **PHYS)
+        ga.theta[0] = theta
+        ga.record_sense_cells = True
+        ga.forward(env, coin=np.zeros(m, dtype=np.int64), use_hints=False)
+        outs.append((ga.sense_cells[0].copy(), ga.action.copy(), ga.theta.copy()))
+    ra = R.PhysarumAgent(max_agents=m, prev_grad=np.ones((2, m)), **PHYS)
+    ra._direction_rads = theta.copy()
+    ra.forward(ref._get_current_obs, coin=np.zeros(m, dtype=np.int64))
+    sx, sy = ra.last_sense_cells
+    assert np.array_equal((sx * field[1] + sy).astype(np.int32), outs[0][0]), "sensed cells differ from the oracle's"
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
 
 
 def test_batched_envs_match_single_envs():

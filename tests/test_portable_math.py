@@ -96,3 +96,20 @@ def test_device_math_equals_host_build_bit_for_bit():
         ref = P.atan2(y, x, fast=bool(fast))
         got = od.cpu().numpy()
         assert np.array_equal(got, ref) and np.array_equal(np.signbit(got), np.signbit(ref))
+
+
+def test_float32_sincos_stays_within_its_stated_error():
+    """die_sincosf_approx (the forward kernel's guard-banded float32 sin / cos): |error| <= DIE_SINCOSF_ERR = 4e-7 for
+    |x| <= 64 -- every consumer budgets exactly that."""
+    import ctypes
+    from oracle import build_oracle
+    lib = ctypes.CDLL(build_oracle.build())
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-np.pi, np.pi, 1000000), rng.uniform(-64, 64, 500000), np.arange(-24, 25) * np.pi / 12,
+                        np.arange(-40, 41) * np.pi / 2 + 1e-9, np.linspace(-64, 64, 200001)])
+    s, c = np.empty(x.size, np.float32), np.empty(x.size, np.float32)
+    sd, cd = np.empty(x.size), np.empty(x.size)
+    P = lambda v, t: v.ctypes.data_as(ctypes.POINTER(t))
+    lib.die_sincosf_approx_array(P(x, ctypes.c_double), P(s, ctypes.c_float), P(c, ctypes.c_float), ctypes.c_long(x.size))
+    lib.die_sincos_array(P(x, ctypes.c_double), P(sd, ctypes.c_double), P(cd, ctypes.c_double), ctypes.c_long(x.size))
+    assert np.abs(s - sd).max() <= 2e-7 and np.abs(c - cd).max() <= 2e-7        # half the budget
