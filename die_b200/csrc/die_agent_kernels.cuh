@@ -259,6 +259,10 @@ gradient_forward_kernel(const GradientArgs a) {
         // CLAMPED not wrapped (Q4).  sin / cos of the heading are needed for the sensed CELL and for the guard-banded
         // turn decision only, so a float32 evaluation (+-4e-7) serves both wherever the cell is not within the guard of a
         // cell boundary; elsewhere (about one slot in 10^5) the float64 die_sincos decides, as it used to for every slot.
+        // (Tried in round 2 and not kept: running this float32 sense evaluation ONE ITEM AHEAD, so that the next item's
+        //  gradient gather is in flight during the current item's float64 sin / cos -- 64 registers with spills, and
+        //  slower in every regime: 4.67 vs 4.36 ms batched, 0.411 vs 0.380 ms at 4096^2 early, 0.672 vs 0.641 ms at its
+        //  steady state; profiles/r02s_forward_gather_one_item_ahead_not_kept.txt.)
         float sf, cf;
         int sx, sy;
         bool cell_ok = false;
