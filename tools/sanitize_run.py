@@ -1,6 +1,10 @@
 """A short tour of every kernel and option combination on small inputs (device init, batches, every agent, food flow +
-sense mask + 'constant' diffusion, fused move, render, chunked host path, the march field kernel).  Written to be run under
-`compute-sanitizer --tool memcheck` (closed on this pool, so it only serves as a crash / sticky-error check here)."""
+sense mask + 'constant' diffusion, speculative move, render, chunked host path, the cluster-fused step with its
+distributed-shared-memory claims and bulk copies, the 128-bit field pass, agents_die, float32 fields, the graphed loop).
+Written to be run under compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_run.py
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py      (shared-memory hazards inside a CTA)
+Where the tool is not usable it still serves as a crash / sticky-error check."""
 import os, sys
 import numpy as np
 import torch
@@ -35,12 +39,25 @@ for mode, flow, mask in (("wrap", False, False), ("constant", True, True), ("ref
         hobs, *_ = big.step(ag.forward(hobs))
     _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
     _lib.check(lib.die_set_tuning(b"host_chunks", 4))
-lib.die_set_step_impl(1)
-env = D.Env((64, 40), D.Dynamics(), init='device', seed=3)
+for key, batch in ((b"step_impl", 3), (b"field_vec", None)):             # the cluster-fused step, the 128-bit field pass
+    _lib.check(lib.die_set_tuning(key, 1))
+    env = D.Env((64, 40), D.Dynamics(), init='device', seed=3, batch=batch)
+    ag = D.PhysarumAgent(max_agents=env.max_agents, scale=0.02, sense_offset=0.06)
+    obs = env._get_current_obs
+    for _ in range(4):
+        obs, *_ = env.step(ag.forward(obs))
+    _lib.check(lib.die_set_tuning(key, 0))
+env = D.Env((48, 64), D.Dynamics(agents_die=True, rate_feed=0.02), init='device', seed=4)        # lifecycle
+ag = D.BrownianAgent(0.03, 2.0)
+obs = env._get_current_obs
+for _ in range(4):
+    obs, *_ = env.step(ag.forward(obs))
+env = D.Env((48, 64), D.Dynamics(), init='device', seed=5, field_dtype=torch.float32)            # float32 fields
 ag = D.PhysarumAgent(max_agents=env.max_agents, scale=0.02, sense_offset=0.06)
 obs = env._get_current_obs
 for _ in range(4):
     obs, *_ = env.step(ag.forward(obs))
-lib.die_set_step_impl(0)
+loop = D.GraphedLoop(D.Env((32, 32), D.Dynamics(), init='device', seed=6), D.BrownianAgent(0.02))       # CUDA graph replay
+loop.run(6)
 torch.cuda.synchronize()
 print("sanitize tour done")
