@@ -40,7 +40,7 @@ def test_ctypes_signatures_cover_the_header():
 
 def test_struct_layouts_match_header():
     from die_b200 import _lib
-    assert ctypes.sizeof(_lib.DieDynamics) == 8 * 4 + 8 * 17 + 4 * 4
+    assert ctypes.sizeof(_lib.DieDynamics) == 8 * 4 + 8 * 17 + 4 * 5 + 4          # five int32 + tail padding to 8
     assert ctypes.sizeof(_lib.DieGradientParams) == 8 * 9 + 4 * 4
 
 
