@@ -7,6 +7,7 @@
 #include "die_agent_kernels.cuh"
 #include "die_field_kernels.cuh"
 #include "die_env_fused.cuh"
+#include "die_conv_kernels.cuh"
 
 using namespace die;
 
@@ -1127,6 +1128,59 @@ extern "C" int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient
         }
     }
     DIE_CUDA(cudaStreamSynchronize(st));
+    return DIE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NeuralAutomataAgent.forward (core/agent/evo.py:117-209)
+// ------------------------------------------------------------------------------------------
+extern "C" int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
+                                       const void* medium, int32_t in_ch_total, int32_t in_ch0, int32_t cin, int32_t cout_last,
+                                       int32_t n_layers, const int32_t* kernel_sizes, const float* weights,
+                                       float* scratch_a, float* scratch_b,
+                                       const double* agents, const int32_t* cells_hint, const float* coefs,
+                                       double* action, int32_t* final_scratch, void* stream) {
+    DIE_REQUIRE(H >= 1 && W >= 1 && M >= 1 && B >= 1 && (int64_t)H * W <= 0x7fffffffLL);
+    DIE_REQUIRE(field_dtype == DIE_FIELD_F64 || field_dtype == DIE_FIELD_F32);
+    DIE_REQUIRE(medium != nullptr && weights != nullptr && scratch_a != nullptr && scratch_b != nullptr);
+    DIE_REQUIRE(kernel_sizes != nullptr && (action == nullptr || (agents != nullptr && coefs != nullptr && cout_last <= 3)));
+    DIE_REQUIRE(cin >= 1 && cin <= kConvMaxCh && cout_last >= 1 && cout_last <= kConvMaxCh);
+    DIE_REQUIRE(in_ch0 >= 0 && in_ch0 + cin <= in_ch_total);
+    DIE_REQUIRE(n_layers >= 1 && n_layers <= 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* w = weights;
+    const void* in = medium;
+    for (int l = 0; l < n_layers; ++l) {
+        const int k = kernel_sizes[l];
+        DIE_REQUIRE(k >= 1 && k <= kConvMaxK && (k & 1) == 1);
+        ConvLayerArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = in;
+        a.out = (l & 1) ? scratch_b : scratch_a;
+        a.weight = w;
+        a.H = H; a.W = W; a.k = k;
+        a.cin = cin;
+        a.cout = (l == n_layers - 1) ? cout_last : cin;
+        a.cin_total = (l == 0) ? in_ch_total : cin;
+        a.in_ch0 = (l == 0) ? in_ch0 : 0;
+        a.tiles_i = (H + kConvTile - 1) / kConvTile;
+        a.tiles_j = (W + kConvTile - 1) / kConvTile;
+        a.apply_tanh = (l == n_layers - 1) ? 1 : 0;
+        const size_t smem = sizeof(float) * ((size_t)cin * (kConvTile + k - 1) * (kConvTile + k - 1) + (size_t)a.cout * cin * k * k);
+        const unsigned grid = (unsigned)((int64_t)a.tiles_i * a.tiles_j * B);
+        if (l == 0 && field_dtype == DIE_FIELD_F64) conv_layer_kernel<double><<<grid, 256, smem, st>>>(a);
+        else conv_layer_kernel<float><<<grid, 256, smem, st>>>(a);
+        DIE_CUDA(cudaGetLastError());
+        w += (size_t)a.cout * cin * k * k;
+        in = a.out;
+    }
+    const float* sense = (const float*)in;
+    if (final_scratch != nullptr) *final_scratch = (n_layers & 1) ? 0 : 1;
+    if (action == nullptr) return DIE_OK;                  // the model alone (ConvolutionModel.forward)
+    const int64_t total = (int64_t)B * M;
+    conv_gather_kernel<<<grid_for(total, 256, 148), 256, 0, st>>>(sense, agents, cells_hint, action, make_axis(H), make_axis(W),
+                                                               M, cout_last, B, coefs[0], coefs[1], coefs[2]);
+    DIE_CUDA(cudaGetLastError());
     return DIE_OK;
 }
 

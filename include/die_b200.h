@@ -373,6 +373,23 @@ int die_slab_corner_refresh(die_slab_t* slab, int32_t cur, int32_t with_grad, vo
  * (CTAs of 512 threads; 256 threads with twice the registers measured 45 % slower.) */
 int die_set_step_impl(int32_t impl);
 
+/* NeuralAutomataAgent.forward, core/agent/evo.py:117-209 (+ ConvolutionModel, :45-118): a stack of n_layers small circular
+ * convolutions (Conv2d, padding 'same', padding_mode 'circular', no bias) over `cin` channels of the medium starting at channel
+ * in_ch0 (all three, or env_food + chem1), in float32 as the reference casts them, Tanh after the last layer; every slot's
+ * action = model output at the agent's nearest cell (all M slots, core/utils.py:56-65) times coefs_host[3] = (scale, scale,
+ * deposit).  kernel_sizes_host[n_layers] (odd, <= 7); weights_dev = the layers' weights back to back, each [cout][cin][k][k]
+ * float32 (torch's layout; cout = cin except cout_last for the last layer); scratch_a / scratch_b: float [B][cin or cout_last]
+ * [H][W] work buffers -- *final_scratch tells which of them (0 / 1) holds the model output afterwards (what render() shows);
+ * cells_hint_dev: die_env_cells of the env that produced the observation, or NULL to resolve cells from agents_dev.
+ * medium_dev has in_ch_total channels per environment (3 for an env's medium); action_dev == NULL runs the model alone
+ * (ConvolutionModel.forward on any [B][in_ch_total][H][W] input; cout_last <= 4 then). */
+int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
+                            const void* medium_dev, int32_t in_ch_total, int32_t in_ch0, int32_t cin, int32_t cout_last,
+                            int32_t n_layers, const int32_t* kernel_sizes_host, const float* weights_dev,
+                            float* scratch_a_dev, float* scratch_b_dev,
+                            const double* agents_dev, const int32_t* cells_hint_dev, const float* coefs_host,
+                            double* action_dev, int32_t* final_scratch, void* stream);
+
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
  * to device arrays, so tests can check the device results equal the host build of the same
  * source bit-for-bit.  fast != 0 selects die_atan2_fast. */

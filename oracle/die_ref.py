@@ -669,6 +669,45 @@ class PhysarumAgent(GradientAgent):
 # Rendering (core/render.py) -- the frames before any matplotlib colour map
 # --------------------------------------------------------------------------------------
 
+class NeuralAutomataAgent:
+    """core/agent/evo.py:117-209 (+ ConvolutionModel, :45-118) in index form.  The convolutions are torch's own
+    (the library the reference's arithmetic bottoms out in here, as numpy / scipy / pandas are elsewhere): circular padding
+    by k // 2 on every side, ``conv2d`` without bias per layer, Tanh once at the end, all in float32; then every slot's
+    action = model output at the agent's nearest cell (``tensor_by_agents(only_alive=False)``, core/utils.py:56-65) times
+    (scale, scale, deposit) as float32 products (``_rescale``, core/agent/evo.py:183-186).  ``weights``: the layers'
+    Conv2d weights [cout, cin, k, k]."""
+
+    def __init__(self, weights, scale: float = 0.1, deposit: float = 1.0, with_agent_channel: bool = True):
+        import torch
+        self._torch = torch
+        self.weights = [torch.as_tensor(np.asarray(w), dtype=torch.float32) for w in weights]
+        self.with_agent_channel = with_agent_channel
+        self.action_coefs = torch.tensor([scale, scale, deposit]).reshape((-1, 1))
+        self.sense_output = None
+
+    def model(self, x):
+        """ConvolutionModel.forward (core/agent/evo.py:112-118) with p_agent_dropout = 0 on a [1, C, H, W] float32 tensor."""
+        F = self._torch.nn.functional
+        for w in self.weights:
+            p = w.shape[-1] // 2
+            x = F.conv2d(F.pad(x, (p, p, p, p), mode='circular') if p else x, w)
+        return self._torch.tanh(x)
+
+    def forward(self, obs) -> np.ndarray:
+        agents, medium = obs
+        torch = self._torch
+        med = medium if self.with_agent_channel else medium[1:]
+        x = torch.as_tensor(np.ascontiguousarray(med), dtype=torch.float32)[None]      # medium2tensor, :187-199
+        sense = self.model(x)
+        self.sense_output = sense
+        h, w = medium.shape[-2:]
+        ix = nearest_index(agents[AG_X], h)
+        iy = nearest_index(agents[AG_Y], w)
+        per_agent = sense[0][:, torch.as_tensor(ix), torch.as_tensor(iy)]              # [3, M]
+        per_agent = per_agent * self.action_coefs
+        return per_agent.detach().numpy()                                              # float32, as the reference's action
+
+
 class EnvRenderer:
     """core/render.py:76-132 + FieldTrace (:9-29) + RendererBase._set_colors (:47-58)."""
 

@@ -167,6 +167,37 @@ def test_agents_die_equals_reference_with_its_indexer_rebound(kind, rate_feed, s
 
 
 @pytest.mark.skipif(not run_reference.available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("kernel_sizes,with_agent_channel,size", [((3,), True, (24, 32)), ((3, 5), True, (20, 28)),
+                                                                 ((5, 3, 3), False, (16, 40)), ((7,), True, (12, 12))])
+def test_neural_automata_agent_equals_reference_executed_live(kernel_sizes, with_agent_channel, size):
+    """core/agent/evo.py (NeuralAutomataAgent + ConvolutionModel, the reference's own source over the stand-in packages)
+    vs the oracle's index-form restatement with the same weights: identical float32 actions and model output, step after
+    step while the env evolves under those actions."""
+    import torch as th
+    ref = run_reference.load()
+    import core.agent.evo as evo
+    th.manual_seed(7)
+    np.random.seed(7)
+    renv = ref.Env(size, ref.Dynamics(init_agent_ratio=0.2))
+    oenv = R.Env(size, R.Dynamics(), medium=renv.medium.values.copy(), agents=renv.agents.values.copy())
+    ra = evo.NeuralAutomataAgent(scale=0.05, deposit=0.7, with_agent_channel=with_agent_channel, kernel_sizes=kernel_sizes)
+    ra.model.init_weights()
+    weights = [k.weight.detach().numpy().copy() for k in ra.model.kernels if hasattr(k, 'weight')]
+    oa = R.NeuralAutomataAgent(weights, scale=0.05, deposit=0.7, with_agent_channel=with_agent_channel)
+    robs, oobs = renv._get_current_obs, oenv._get_current_obs
+    for it in range(6):
+        ract = ra.forward(robs)
+        oact = oa.forward(oobs)
+        assert ract.values.dtype == np.float32 and oact.dtype == np.float32
+        assert np.array_equal(ract.values, oact), it
+        assert np.array_equal(ra._sense_output.detach().numpy(), oa.sense_output.numpy())
+        robs, rr, *_ = renv.step(ract)
+        oobs, orr, *_ = oenv.step(oact)                 # float32, as the reference hands it to Env.step
+        assert rr == orr
+        assert np.array_equal(renv.medium.values, oenv.medium) and np.array_equal(renv.agents.values, oenv.agents), it
+
+
+@pytest.mark.skipif(not run_reference.available(), reason="/root/reference not present on this box")
 @pytest.mark.parametrize("colors", ['rgb', 'one', 'two'])
 def test_oracle_renderer_equals_reference_executed_live(colors):
     """core/render.py's EnvRenderer (own source, over the stand-in packages; its matplotlib colour map aside) vs the
