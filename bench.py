@@ -615,6 +615,8 @@ def run_die_b200(args):
     for kv in args.tune:
         key, val = kv.split("=")
         dlib.check(dlib.load().die_set_tuning(key.encode(), int(val)))
+    l2_prev = dlib.C.c_int32(0)
+    dlib.check(dlib.load().die_device_l2_fetch_granularity(int(args.l2_fetch), dlib.C.byref(l2_prev)))
 
     if args.workload == "slab":
         if world < 2:
@@ -859,6 +861,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32 / 64 / 128; 0 = leave the default)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

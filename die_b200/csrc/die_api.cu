@@ -898,6 +898,20 @@ extern "C" int die_set_turn_quick(int32_t on) {
     return DIE_OK;
 }
 
+// cudaLimitMaxL2FetchGranularity of the current device (32 / 64 / 128 bytes; a hint to the L2: how much a miss fetches
+// from DRAM).  Random 8-byte gathers over tables larger than L2 -- the spread-out ghost slots of one large field, DESIGN.md
+// 5.1 -- pay the full granule per gather.  Device-wide and sticky for the process: returns the previous value in *previous.
+extern "C" int die_device_l2_fetch_granularity(int32_t bytes, int32_t* previous) {
+    size_t old = 0;
+    DIE_CUDA(cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity));
+    if (previous != nullptr) *previous = (int32_t)old;
+    if (bytes > 0) {
+        DIE_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128);
+        DIE_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    }
+    return DIE_OK;
+}
+
 extern "C" int die_set_tuning(const char* key, int32_t value) {
     DIE_REQUIRE(key != nullptr);
     if (strcmp(key, "turn_quick") == 0) g_turn_quick = value ? 1 : 0;

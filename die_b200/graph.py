@@ -48,6 +48,7 @@ class GraphedLoop:
             agent._step_dev = self._counter
             step0, cur0 = agent._step, env._cur
             torch.cuda.synchronize(dev)
+            self._dynamics_key = env._dynamics_key
             self._graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(self._graph):
@@ -63,11 +64,18 @@ class GraphedLoop:
             agent._step = step0
             assert env._cur == cur0
             self._cur0 = cur0
+            self._handle_id = env._handle.value          # Env.reset() re-creates its buffers: the graph is bound to these
             self._obs = obs
 
     def run(self, iterations: int):
         """`iterations` iterations of forward + step -> (obs, reward_sum[B] over every iteration run so far, on device)."""
         env, agent = self.env, self.agent
+        if env._handle is None or env._handle.value != self._handle_id:
+            raise RuntimeError("the Env was reset (new buffers) after this GraphedLoop was captured: build a new GraphedLoop")
+        env._sync_dynamics()
+        if env._dynamics_key != self._dynamics_key:
+            raise RuntimeError("env.dynamics changed after this GraphedLoop was captured (kernel arguments are baked into "
+                               "the graph): build a new GraphedLoop")
         with torch.cuda.device(env.device):
             if iterations > 0 and env._cur != self._cur0:    # an odd run left the medium in the other buffer: step once eagerly
                 self._eager_step()

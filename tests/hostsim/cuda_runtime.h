@@ -176,6 +176,9 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }   // "2 SMs"
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
+static inline cudaError_t cudaDeviceGetLimit(size_t* v, cudaLimit) { *v = 64; return cudaSuccess; }
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

@@ -47,6 +47,21 @@ def test_graphed_loop_equals_eager_loop(kind, field, batch, iters):
         assert np.array_equal(a, b), f"{what} differs between the eager and the graphed loop"
 
 
+def test_graphed_loop_notices_a_reset_env_and_changed_dynamics():
+    import die_b200 as D
+    _, env = make_pair((32, 32), seed=1)
+    loop = D.GraphedLoop(env, D.BrownianAgent())
+    loop.run(4)
+    env.dynamics.rate_feed = 0.3
+    with pytest.raises(RuntimeError, match="dynamics changed"):
+        loop.run(2)
+    loop = D.GraphedLoop(env, D.BrownianAgent())
+    loop.run(2)
+    env.reset()
+    with pytest.raises(RuntimeError, match="reset"):
+        loop.run(2)
+
+
 def test_graphed_loop_refuses_what_it_cannot_capture():
     import die_b200 as D
     field = (32, 32)
