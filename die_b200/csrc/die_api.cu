@@ -1392,6 +1392,10 @@ extern "C" int die_slab_forward(die_slab_t* e, const die_gradient_params_t* p, i
     a.plan = plan_for(p);
     a.agents = agents; a.theta = theta; a.action = action; a.coin = coin;
     a.seed = seed; a.step = step;
+    if (g_sense_quick) {           // as the single-GPU forward: float32 sin / cos for the sensed cell, guarded
+        a.sense_guard_x = fabs(p->sense_offset) * DIE_SINCOSF_ERR * a.ax.nm1 + 1e-9;
+        a.sense_guard_y = fabs(p->sense_offset) * DIE_SINCOSF_ERR * a.ay.nm1 + 1e-9;
+    }
     a.sg = e->g;
     a.st = slab_tables(e, cur, true);
     if (!(hints & 1)) {                          // bit 0: the gradient published by the last die_slab_field
