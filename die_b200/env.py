@@ -252,6 +252,7 @@ class Env:
                 _check_f32_dynamics(cdyn)
             _lib.check(self._lib.die_env_create(h, w, self._M, B, _lib.C.byref(cdyn), _lib.C.byref(handle)))
             self._handle = handle
+            self._generation = getattr(self, '_generation', 0) + 1      # reset() re-creates every buffer
             if self._field_dtype == torch.float32:
                 _lib.check(self._lib.die_env_set_field_dtype(handle, _lib.FIELD_F32))
             self._dynamics_key = self._dynamics_snapshot()

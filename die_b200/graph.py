@@ -64,13 +64,13 @@ class GraphedLoop:
             agent._step = step0
             assert env._cur == cur0
             self._cur0 = cur0
-            self._handle_id = env._handle.value          # Env.reset() re-creates its buffers: the graph is bound to these
+            self._generation = env._generation           # Env.reset() re-creates its buffers: the graph is bound to these
             self._obs = obs
 
     def run(self, iterations: int):
         """`iterations` iterations of forward + step -> (obs, reward_sum[B] over every iteration run so far, on device)."""
         env, agent = self.env, self.agent
-        if env._handle is None or env._handle.value != self._handle_id:
+        if env._handle is None or env._generation != self._generation:
             raise RuntimeError("the Env was reset (new buffers) after this GraphedLoop was captured: build a new GraphedLoop")
         env._sync_dynamics()
         if env._dynamics_key != self._dynamics_key:
