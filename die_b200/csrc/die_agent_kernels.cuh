@@ -128,6 +128,7 @@ struct GradientArgs {
     const float2* grad32;       // may be null: the same, rounded to float32 (only offered when the gradient is used for
                                 // the guard-banded turn DECISION alone: discrete turn, plan enabled, normalised)
     const int32_t* cells;       // may be null: linear cell of every slot, cached by Env.step
+    const double* food_here;    // FH instantiation: the env_food under every slot, gathered by the last step's feed kernel
     uint64_t seed, step;
     const uint64_t* step_dev;   // may be null; else the call counter is read from device memory (CUDA-graph replays)
     double sense_guard_x, sense_guard_y;   // > 0: the sense position may be formed with the float32 sin / cos of
@@ -185,10 +186,15 @@ __device__ __forceinline__ void sample_gradient(const FT* __restrict__ chem, int
 // thing, so every decision it settles is the same; a slot it defers re-samples the float64 gradient from chem1.
 // FT: element type of the medium the agent observes (float64, or float32 in the env's float32 field mode): gathered
 // values are widened, all arithmetic stays float64.
-template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false, bool G32 = false, typename FT = double>
+// FH (LEAN only): the food under the agent comes per SLOT from the array the last step's feed kernel filled (it gathered at
+// that very cell anyway) -- a coalesced 8-byte load instead of a random gather.  For one LARGE field, whose ghost slots
+// are spread over tables far larger than L2, every random 8-byte gather costs ~80-90 B of DRAM traffic.
+template <bool DISCRETE_TURN, bool SLAB, bool MOVE, int MINB, bool LEAN = false, bool G32 = false, typename FT = double,
+          bool FH = false>
 __global__ void __launch_bounds__(kAgentThreads, MINB)
 gradient_forward_kernel(const GradientArgs a) {
     static_assert(!SLAB || sizeof(FT) == 8, "the slab decomposition runs float64 fields");
+    static_assert(!FH || LEAN, "food_here is a hint of the steady-state instantiation");
     const die_gradient_params_t& p = a.p;
     const Axis ax = a.ax, ay = a.ay;
     const int64_t M = a.M;
@@ -210,6 +216,7 @@ gradient_forward_kernel(const GradientArgs a) {
     const double2* grad = ((LEAN && !G32) || a.grad != nullptr) ? a.grad + ch.b * C : nullptr;
     const float2* grad32 = (G32 || (!LEAN && !SLAB && a.grad32 != nullptr)) ? a.grad32 + ch.b * C : nullptr;
     const int32_t* cl_p = (LEAN || a.cells != nullptr) ? a.cells + ch.b * M + first : nullptr;
+    const double* fh_p = FH ? a.food_here + ch.b * M + first : nullptr;
     int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
     int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
     // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
@@ -229,13 +236,14 @@ gradient_forward_kernel(const GradientArgs a) {
     // `first`, which the compiler otherwise rebuilds from blockIdx for every item's bounds check)
     const int left = (int)((M - first < (int64_t)kFwdItems * kAgentThreads) ? (M - first) : (int64_t)kFwdItems * kAgentThreads);
     bool nvalid = left > 0;
-    double nx = 0.0, ny = 0.0, nth = 0.0;
+    double nx = 0.0, ny = 0.0, nth = 0.0, nfh = 0.0;
     int ncell = 0;
     if (nvalid) {
         nx = ag_x[0];
         ny = ag_x[M];
         nth = th_p[0];
-        if (LEAN || cl_p != nullptr) ncell = cl_p[0];
+        if (FH) nfh = fh_p[0];
+        else if (LEAN || cl_p != nullptr) ncell = cl_p[0];
     }
 
     for (int k = 0; k < kFwdItems; ++k) {
@@ -243,8 +251,13 @@ gradient_forward_kernel(const GradientArgs a) {
         const int i = k * kAgentThreads;                       // offset from this thread's first slot
         const double x = nx, y = ny, th = nth;
         // food under the agent (:113-115), issued first: independent of the turn arithmetic
-        const int here = (LEAN || cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
-        const double food_here = SLAB ? slab_load_food(a.st, a.sg, here) : (double)food[here];
+        double food_here;
+        if (FH) {
+            food_here = nfh;
+        } else {
+            const int here = (LEAN || cl_p != nullptr) ? ncell : nearest_cell(x, ax) * W + nearest_cell(y, ay);
+            food_here = SLAB ? slab_load_food(a.st, a.sg, here) : (double)food[here];
+        }
         uint32_t alive_word = 0;
         if (MOVE) alive_word = bits_p[i >> 5];
         nvalid = (k + 1 < kFwdItems) && (i + kAgentThreads < left);
@@ -252,7 +265,8 @@ gradient_forward_kernel(const GradientArgs a) {
             nx = ag_x[i + kAgentThreads];
             ny = ag_x[M + i + kAgentThreads];
             nth = th_p[i + kAgentThreads];
-            if (LEAN || cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
+            if (FH) nfh = fh_p[i + kAgentThreads];
+            else if (LEAN || cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
         }
 
         // _sense_offset (:73-76): polar2xy(r, theta) = (r cos, r sin); field_by_agents(grad_field, offset) (:105): nearest,
@@ -457,6 +471,8 @@ struct FeedArgs {
     double* agents;
     const double* action;
     const double* consumed_field;    // [B][C] rate_feed * food * occ of this step (the field pass wrote it); element type FT
+    const double2* cell_pairs;       // PAIR: [B][C] {consumed_field, new env_food} per cell, written by the field pass instead
+    double* food_here;               // PAIR: [B][M] out: the new env_food under every slot (the next forward's food_here)
     int32_t* winner;
     int32_t* cells;                  // read; DIE also resets the cached cell of a slot it puts back at (0, 0)
     double* part_gain;
@@ -472,9 +488,12 @@ struct FeedArgs {
 // DIE: Dynamics.agents_die -- Env._agent_lifecycle (core/env.py:245-250) folded in: a slot whose stock after feeding is
 // not above 1e-4 has ALL its channels zeroed (agents.where(agent_food > 1e-4, 0): dead, back at (0, 0), no stock), which
 // holds for every ghost slot every step; num_agents counts the survivors (core/env.py:118, after the lifecycle).
-template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double>
+// PAIR: the per-cell scratch is {consumed_field, new env_food} (16 bytes, one sector): the slot's gather brings both, and
+// the food is stored per slot for the next forward pass (see FH there).
+template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double, bool PAIR = false>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
+    static_assert(!PAIR || (!SLAB && !DIE && sizeof(FT) == 8), "the pair table serves the plain float64 step");
     const int64_t M = a.M;
     const int nblk = a.nblk;
     const int64_t b = blockIdx.x / (unsigned)nblk;
@@ -482,7 +501,9 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     const int64_t first = (int64_t)blk * (kAgentThreads * kFeedItems) + threadIdx.x;
     double* __restrict__ ag_x = a.agents + b * 4 * M + first;  // x; y, alive, agent_food are + M, 2M, 3M
     const double* __restrict__ ac = a.action + b * 3 * M + first;
-    const FT* __restrict__ cf = SLAB ? nullptr : (const FT*)a.consumed_field + b * a.C;
+    const FT* __restrict__ cf = (SLAB || PAIR) ? nullptr : (const FT*)a.consumed_field + b * a.C;
+    const double2* __restrict__ cp = PAIR ? a.cell_pairs + b * a.C : nullptr;
+    double* __restrict__ fh = PAIR ? a.food_here + b * M + first : nullptr;
     int32_t* __restrict__ win = a.winner + b * a.C;
     int32_t* __restrict__ cl = a.cells + b * M + first;
     const uint32_t* __restrict__ bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
@@ -494,6 +515,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     int cell[kFeedItems];
     double dx[kFeedItems], dy[kFeedItems], dep[kFeedItems], stock[kFeedItems], eaten[kFeedItems];
     double px[kFeedItems], py[kFeedItems];
+    double under[PAIR ? kFeedItems : 1];
     bool alive[kFeedItems], valid[kFeedItems];
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
@@ -503,7 +525,13 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
 #pragma unroll
     for (int k = 0; k < kFeedItems; ++k) {
         const int i = k * kAgentThreads;
-        eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : (double)cf[cell[k]]) : 0.0;
+        if (PAIR) {
+            const double2 pr = valid[k] ? cp[cell[k]] : make_double2(0.0, 0.0);
+            eaten[k] = pr.x;
+            under[k] = pr.y;                       // (stored after every gather of this thread is in flight)
+        } else {
+            eaten[k] = valid[k] ? (SLAB ? slab_load_consumed(st, sg, cell[k]) : (double)cf[cell[k]]) : 0.0;
+        }
         if (BITS) alive[k] = valid[k] && ((bits_p[i >> 5] >> (threadIdx.x & 31)) & 1u);
         else alive[k] = valid[k] && ag_x[2 * M + i] > 0.0;
         if (MOVE) {
@@ -521,6 +549,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     for (int k = 0; k < kFeedItems; ++k) {
         if (valid[k]) {
             const int i = k * kAgentThreads;
+            if (PAIR) fh[i] = under[k];
             if (MOVE) {
                 ag_x[i] = apply_boundary(px[k] + dx[k], boundary);
                 ag_x[M + i] = apply_boundary(py[k] + dy[k], boundary);

@@ -52,6 +52,11 @@ struct die_env {
     int64_t flow_T, flow_k;
     double flow_scale, flow_keep;
     double* consumed;      // [B][H*W]  consumed_field = rate_feed * food * occ of the current step
+    // "pair mode" (large fields, see pair_mode_for): the per-cell scratch is {consumed_field, new env_food}; the feed kernel's
+    // one gather per slot brings both and hands the food under the agent to the next forward pass per SLOT
+    double2* cell_pairs;   // [B][H*W]  (lazy)
+    double* food_here;     // [B][M]    env_food under every slot after the last step (lazy)
+    int food_here_valid;   // the last step filled food_here for the cells in cells2[cur]
     double2* grad;         // [B][H*W]  np.gradient of the current chem1 (lazy; see die_env_publish_gradient)
     float2* grad32;        // [B][H*W]  the same rounded to float32 (lazy; tuning "grad_f32")
     int grad_kind;         // which of the two the LAST field pass wrote: 0 none, 1 grad, 2 grad32
@@ -81,7 +86,7 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
@@ -91,6 +96,7 @@ extern "C" int64_t die_get_counter(const char* key) {
     if (strcmp(key, "forward_lean") == 0) return g_count_fwd_lean;
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
     if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
+    if (strcmp(key, "forward_food_here") == 0) return g_count_fwd_food_here;
     return -1;
 }
 extern "C" const char* die_last_error(void) { return g_err; }
@@ -161,6 +167,8 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->alive_bits);
     delete[] e->flow_ts;
     cudaFree(e->consumed);
+    cudaFree(e->cell_pairs);
+    cudaFree(e->food_here);
     cudaFree(e->grad);
     cudaFree(e->grad32);
     cudaFree(e->part_gain);
@@ -327,7 +335,7 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st, b
             return cudaErrorInvalidValue;        // (float32 fields: blur radius 1..4; the Python layer refuses by name)
         }
     }
-    if (plain && g_field_vec && (a.W & 1) == 0 && ((uintptr_t)a.medium_in & 15) == 0 && ((uintptr_t)a.medium_out & 15) == 0 &&
+    if (plain && g_field_vec && a.cell_pairs == nullptr && (a.W & 1) == 0 && ((uintptr_t)a.medium_in & 15) == 0 && ((uintptr_t)a.medium_out & 15) == 0 &&
         ((uintptr_t)a.consumed & 15) == 0 && ((uintptr_t)a.winner & 7) == 0 && ((uintptr_t)a.grad32 & 15) == 0) {
         // the default dynamics on an even row length: the 128-bit version (same tile, same arithmetic, same results)
         constexpr int PADL = (R + G) & 1, SW = (PADL + TW + 2 * G + 2 * R + 1) & ~1;
@@ -367,9 +375,23 @@ extern "C" int die_set_step_impl(int32_t impl) {
     return DIE_OK;
 }
 
+// Pair mode: one field whose per-cell tables are far larger than L2 -- there every random 8-byte gather of a slot costs
+// a DRAM sector plus change (77-93 B measured), so the step keeps {consumed_field, new food} in ONE 16-byte
+// pair per cell and hands the food per slot to the next forward pass: three random accesses per slot and step become
+// two.  Small fields (the batched workload) gather out of L2 and keep the 8-byte table.
+static int g_pair_mode = 1;                    // 0 never, 1 by size (pair_min_cells), 2 always (tests)
+static int64_t g_pair_min_cells = 1 << 23;     // cells per environment from which it pays.  Measured on a B200, step time at
+                                               // step 40 / step 3000: 2048^2 +6 % / +7 % (the tables still sit in L2),
+                                               // 3072^2 -4 % / -6 %, 4096^2 +-0 / -11 %, 6144^2 -1 % / -15 %, 8192^2 -5 % / -16 %
+
+static inline bool pair_mode_for(const die_env* e, bool speculative) {
+    if (g_pair_mode == 0 || speculative || e->dyn.agents_die || e->field_f32 || e->dyn.blur_radius == 0) return false;
+    return g_pair_mode == 2 || (int64_t)e->H * e->W >= g_pair_min_cells;
+}
+
 // Field pass over environments [b0, b0 + nb) of the batch; min / mout / action already point at environment b0.
 static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* min, double* mout,
-                                    const double* action, cudaStream_t st) {
+                                    const double* action, cudaStream_t st, bool pair = false) {
     const size_t C = (size_t)e->H * e->W;
     FieldArgs a;
     memset(&a, 0, sizeof(a));
@@ -378,6 +400,7 @@ static cudaError_t launch_field_any(die_env* e, int b0, int nb, const double* mi
     a.winner = e->winner + b0 * C;
     a.action = action;
     a.consumed = field_off(e, e->consumed, (size_t)b0 * C);
+    if (pair) a.cell_pairs = e->cell_pairs + (size_t)b0 * C;
     const bool f32 = e->field_f32 != 0;
     if (e->publish_grad && e->dyn.blur_radius > 0) {
         if (ensure_gradient_buffer(e) != DIE_OK) return cudaErrorMemoryAllocation;
@@ -586,8 +609,14 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
         alive_bits = nullptr;
         e->alive_valid = 0;
     }
+    const bool pair = pair_mode_for(e, fused);
+    if (pair) {
+        if (e->cell_pairs == nullptr) DIE_CUDA(cudaMalloc(&e->cell_pairs, sizeof(double2) * C * e->B));
+        if (e->food_here == nullptr) DIE_CUDA(cudaMalloc(&e->food_here, sizeof(double) * M * e->B));
+    }
+    e->food_here_valid = 0;
     if (profile) prof_mark(e, 0, st);
-    if (!fused && g_step_impl == 1) {
+    if (!fused && !pair && g_step_impl == 1) {
         int done = 0;
         if (int rc = try_fused_step(e, b0, nb, medium_in, medium_out, agents, action, reward_dev, alive_dev, alive_bits, st, &done))
             return rc;
@@ -606,7 +635,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     }
     if (profile) prof_mark(e, 1, st);
 
-    DIE_CUDA(launch_field_any(e, b0, nb, medium_in, medium_out, action, st));
+    DIE_CUDA(launch_field_any(e, b0, nb, medium_in, medium_out, action, st, pair));
     if (profile) prof_mark(e, 2, st);
 
     const unsigned fgrid = (unsigned)((int64_t)e->nblk * nb);
@@ -620,10 +649,16 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
                                  : (feed_bits ? agent_feed_kernel<false, false, true, false, float>
                                               : agent_feed_kernel<false, false, false, false, float>);
     }
+    if (pair) feed = feed_bits ? agent_feed_kernel<false, false, true, false, double, true>
+                               : agent_feed_kernel<false, false, false, false, double, true>;
     FeedArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.agents = agents; fa.action = action;
     fa.consumed_field = field_off(e, e->consumed, (size_t)b0 * C);
+    if (pair) {
+        fa.cell_pairs = e->cell_pairs + (size_t)b0 * C;
+        fa.food_here = e->food_here + (size_t)b0 * M;
+    }
     fa.winner = winner; fa.cells = cells; fa.part_gain = part_gain; fa.part_alive = part_alive;
     fa.C = (int64_t)C; fa.M = e->M; fa.nblk = e->nblk;
     fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
@@ -635,6 +670,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     finalize_stats_kernel<<<nb, kFinalThreads, 0, st>>>(part_gain, part_alive, e->nblk, reward_dev + b0, alive_dev + b0);
     DIE_CUDA(cudaGetLastError());
     if (profile) prof_mark(e, 4, st);
+    e->food_here_valid = pair ? 1 : 0;
     return DIE_OK;
 }
 
@@ -925,6 +961,8 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
+    else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }
+    else if (strcmp(key, "pair_min_cells_log2") == 0) { DIE_REQUIRE(value >= 2 && value <= 31); g_pair_min_cells = (int64_t)1 << value; }
     else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
     else return fail(DIE_E_INVALID, "die_set_tuning: unknown key %s%s", key);
     return DIE_OK;
@@ -999,7 +1037,16 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     const bool lean = g_fwd_lean && !speculate && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
                       prev_grad == nullptr && coin == nullptr && noise == nullptr && sense_cells == nullptr &&
                       (a.grad != nullptr || a.grad32 != nullptr) && a.cells != nullptr && g_fwd_min_blocks == 4;
-    if (lean) {
+    // the food under every slot, handed over by the last step's feed kernel (pair mode): valid exactly when the cell
+    // cache is (the caller proved the observation is the env's own state of that step)
+    const bool fh = lean && !field_f32 && env != nullptr && env->food_here_valid && env->food_here != nullptr &&
+                    cells_hint == env->cells2[env->cur] && g_fwd_lean != 5;
+    if (fh) {
+        a.food_here = env->food_here;
+        kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, false, 4, true, true, double, true>
+                                     : gradient_forward_kernel<true, false, false, 4, true, false, double, true>;
+        ++g_count_fwd_food_here;
+    } else if (lean) {
         if (a.grad32 != nullptr) {
             if (g_fwd_lean == 5) kern = gradient_forward_kernel<true, false, false, 5, true, true>;
             else kern = gradient_forward_kernel<true, false, false, 4, true, true>;

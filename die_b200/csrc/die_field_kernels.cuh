@@ -37,6 +37,8 @@ struct FieldArgs {
     const int32_t* winner;       // [B][H*W] claim table (read only here; the feed kernel clears it)
     const double* action;        // [B][3][M]; channel 2 = deposit1
     double* consumed;            // [B][H*W] consumed_field out
+    double2* cell_pairs;         // non-null: [B][H*W] {consumed_field, new env_food} out INSTEAD of consumed (large fields: the
+                                 // feed kernel's one gather then also brings the food the next forward pass needs)
     double2* grad;               // [B][H*W] np.gradient(chem_out) (raw d/dx, d/dy) or null
     float2* grad32;              // the same pairs rounded to float32 (tuning "grad_f32"): what the guard-banded quick turn
                                  // decision reads anyway (die_turn.h); at most one of grad / grad32 is set
@@ -259,9 +261,11 @@ field_step_kernel(const FieldArgs a) {
                 const double occ = (win[g] >= 0) ? 1.0 : 0.0;
                 const double f = (double)food_in[g];
                 const double cf = (a.rate_feed * f) * occ;      // consumed_field, core/env.py:224
-                food_out[g] = (FT)next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+                const double fnew = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+                food_out[g] = (FT)fnew;
                 occ_out[g] = (FT)occ;
-                cons[g] = (FT)cf;
+                if (!SLAB && sizeof(FT) == 8 && a.cell_pairs != nullptr) a.cell_pairs[b * C + g] = make_double2(cf, fnew);
+                else cons[g] = (FT)cf;
             }
         }
     } else {
@@ -300,9 +304,11 @@ field_step_kernel(const FieldArgs a) {
             const double occ = (win[g] >= 0) ? 1.0 : 0.0;
             const double f = (double)food_in[g];
             const double cf = (a.rate_feed * f) * occ;          // consumed_field, core/env.py:224
-            food_out[g] = (FT)next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+            const double fnew = next_food<SLAB || PLAIN>(a, f, cf, li, gj, g);
+            food_out[g] = (FT)fnew;
             occ_out[g] = (FT)occ;
-            cons[g] = (FT)cf;
+            if (!SLAB && sizeof(FT) == 8 && a.cell_pairs != nullptr) a.cell_pairs[b * C + g] = make_double2(cf, fnew);
+            else cons[g] = (FT)cf;
         }
     }
     }   // GRAD

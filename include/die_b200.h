@@ -312,14 +312,14 @@ int die_set_turn_quick(int32_t on);
 /* Performance switches that never change results (A-B timing, bench.py --tune): "turn_quick" 0/1,
  * "fwd_min_blocks" 3/4/5 (register cap of the forward kernel: resident CTAs per SM), "host_chunks" n (see die_env_step_host), "fwd_lean" 0/1 (compile-time specialised forward kernel for the
  * steady-state Physarum configuration), "feed_bits" 0/1 (feed kernel takes
- * alive-ness from the bitmask), "field_prefetch" 0/1, "field_vec" 0/1 (the 128-bit field pass where it applies), "step_impl" 0/1 (see die_set_step_impl), "grad_f32" 0/1 (see die_env_gradient_kind). */
+ * alive-ness from the bitmask), "field_prefetch" 0/1, "field_vec" 0/1 (the 128-bit field pass where it applies), "pair_mode" 0/1/2 (never / by size / always) and "pair_min_cells_log2" (default 23): {consumed_field, food} pairs + per-slot food hand-over for large fields, "step_impl" 0/1 (see die_set_step_impl), "grad_f32" 0/1 (see die_env_gradient_kind). */
 int die_set_tuning(const char* key, int32_t value);
 /* cudaLimitMaxL2FetchGranularity of the current device: bytes = 32 / 64 / 128 sets it (0 = only query); *previous gets the
  * old value.  A device-wide hint: how many bytes an L2 miss fetches from DRAM.  Matters for the random 8-byte gathers of
  * one LARGE field once the ghost slots have spread over it; result-neutral. */
 int die_device_l2_fetch_granularity(int32_t bytes, int32_t* previous);
 /* How often a kernel variant has been launched by this process (diagnostics for tests: "the variant I selected is the
- * one that ran"): "field_tile", "field_vec", "step_fused", "forward_lean", "forward_lean_f32", "forward_general";
+ * one that ran"): "field_tile", "field_vec", "step_fused", "forward_lean", "forward_lean_f32", "forward_general", "forward_food_here";
  * -1 for an unknown key. */
 int64_t die_get_counter(const char* key);
 

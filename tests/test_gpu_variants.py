@@ -154,3 +154,60 @@ def test_vectorised_field_pass_does_not_change_results(shape, sigma, batch):
         _lib.check(lib.die_set_tuning(b"field_vec", 0))
     assert lib.die_get_counter(b"field_vec") == n0 + 12, "the 128-bit kernel must be the one that ran"
     assert all(np.array_equal(a, b) for a, b in zip(*outs))
+
+
+@pytest.mark.parametrize("shape,batch", [((512, 384), None), ((200, 136), 3)])
+def test_pair_mode_does_not_change_results(shape, batch):
+    """pair_mode: {consumed_field, new food} in one 16-byte pair per cell, the food under every slot handed from the
+    feed kernel to the next forward pass -- forced here on fields below the automatic threshold."""
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    outs = []
+    for mode in (0, 2):
+        _lib.check(lib.die_set_tuning(b"pair_mode", mode))
+        try:
+            n0 = lib.die_get_counter(b"forward_food_here")
+            refs, env = make_pair(shape, seed=21, batch=batch)
+            m = env.max_agents
+            ag = D.PhysarumAgent(max_agents=m, seed=5, **PHYS)
+            obs = env._get_current_obs
+            rewards = []
+            for it in range(30):
+                obs, r, *_ = env.step(ag.forward(obs))
+                rewards.append(np.asarray(r).copy())
+            assert lib.die_get_counter(b"forward_food_here") - n0 == (29 if mode else 0)
+            outs.append((*env.get_state(), ag.get_state()[0], np.array(rewards)))
+        finally:
+            _lib.check(lib.die_set_tuning(b"pair_mode", 1))
+    for a, b, what in zip(outs[0], outs[1], ("medium", "agents", "theta", "reward")):
+        assert np.array_equal(a, b), f"{what} differs"
+
+
+def test_pair_mode_is_automatic_on_a_large_field():
+    """Automatic mode goes by the number of cells per environment (default 2^23; lowered to 2^22
+    here to keep the test small): a 2048 x 2048 field runs in pair mode, and equals the run with the mode switched off."""
+    import die_b200 as D
+    from die_b200 import _lib
+    lib = _lib.load()
+    outs = []
+    for mode in (1, 0):
+        _lib.check(lib.die_set_tuning(b"pair_mode", mode))
+        _lib.check(lib.die_set_tuning(b"pair_min_cells_log2", 22))
+        try:
+            n0 = lib.die_get_counter(b"forward_food_here")
+            env = D.Env((2048, 2048), D.Dynamics(), init='device', seed=3)
+            ag = D.PhysarumAgent(max_agents=env.max_agents, seed=5, **PHYS)
+            obs = env._get_current_obs
+            total = 0.0
+            for it in range(12):
+                obs, r, *_ = env.step(ag.forward(obs))
+                total += r
+            assert lib.die_get_counter(b"forward_food_here") - n0 == (11 if mode else 0)
+            med, agents = env.get_state()
+            outs.append((med, agents, ag.get_state()[0], total))
+            del env, ag, obs
+        finally:
+            _lib.check(lib.die_set_tuning(b"pair_mode", 1))
+            _lib.check(lib.die_set_tuning(b"pair_min_cells_log2", 23))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][:3], outs[1][:3])) and outs[0][3] == outs[1][3]

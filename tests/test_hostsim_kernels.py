@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1, pair_mode=1, pair_min_cells_log2=23)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -243,7 +243,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
-                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1]), ("sense_quick", [0])])
+                                        ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1]), ("sense_quick", [0]), ("pair_mode", [2])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
@@ -255,6 +255,62 @@ def test_tuning_switches_do_not_change_results(tuning, key, values):
         out = _philox_run((40, 72), 12)
         for a, b, what in zip(base, out, ("medium", "agents", "theta", "reward")):
             assert np.array_equal(a, b), f"{key}={v}: {what} differs"
+
+
+@pytest.mark.parametrize("shape,sigma,batch,kw", [
+    ((40, 72), 0.5, None, {}), ((33, 47), 1.0, 3, {}), ((64, 64), 0.5, 2, dict(food_infinite=True)),
+    ((24, 50), 0.8, None, dict(diffuse_mode='reflect', boundary=D.BoundaryCondition.limit)), ((6, 90), 0.3, 2, {})])
+@pytest.mark.parametrize("grad_f32", [1, 0])
+def test_pair_mode_equals_the_separate_tables(tuning, shape, sigma, batch, kw, grad_f32):
+    """pair_mode (large single fields by default, forced here): the field pass writes {consumed_field, new food} per
+    cell, the feed kernel's gather brings both and stores the food under every slot, the next LEAN forward reads it per
+    slot instead of gathering -- every output equals the three separate tables' bit for bit; a Brownian agent (no
+    gradient, no forward consumer) and an observation that is not the env's own (no hints: the general forward) too."""
+    outs = []
+    fh0 = S.lib().die_get_counter(b"forward_food_here")
+    tuning("grad_f32", grad_f32)
+    for mode in (0, 2):
+        tuning("pair_mode", mode)
+        refs, env = make_pair(shape, seed=5, dynamics_kw=dict(diffuse_sigma=sigma, **kw), batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 5 + b)[0]
+        rewards = []
+        for it in range(9):
+            if it == 4:
+                act = np.stack([S.brownian_forward(env.agents[b], move_scale=0.02, seed=4 + b, step=it) for b in range(B)])
+            elif it == 6:
+                act = ga.forward(env, use_hints=False)
+            else:
+                act = ga.forward(env)
+            rewards.append(env.step(act)[0].copy())
+        outs.append((env.medium.copy(), env.agents.copy(), ga.theta.copy(), np.array(rewards), env.cells().copy()))
+    # steps 1-3, 5, 7, 8 of the pair-mode run had valid hints + a pair-mode step before them
+    assert S.lib().die_get_counter(b"forward_food_here") == fh0 + 6
+    for a, b, what in zip(outs[0], outs[1], ("medium", "agents", "theta", "reward", "cells")):
+        assert np.array_equal(a, b), f"{what} differs"
+
+
+def test_pair_mode_is_chosen_by_field_size_and_declines_where_it_does_not_apply(tuning):
+    """Automatic mode: fields of pair_min_cells and more; never with agents_die, float32 fields, no diffusion, a
+    speculative move."""
+    fh = lambda: S.lib().die_get_counter(b"forward_food_here")
+    def run(shape, dynamics_kw=None, fuse=False):
+        refs, env = make_pair(shape, seed=3, dynamics_kw=dynamics_kw)
+        ga = S.SimGradientAgent(env.M, seed=1, **PHYS)
+        ga.fuse_move = fuse
+        n0 = fh()
+        for it in range(3):
+            env.step(ga.forward(env), flags=L.STEP_ALIVE_BITS | (L.STEP_ADOPT_MOVE if fuse else 0))
+        return fh() - n0
+    tuning("pair_min_cells_log2", 11)
+    assert run((32, 64)) == 2 and run((32, 63)) == 0
+    assert run((32, 64), dict(agents_die=True)) == 0
+    assert run((32, 64), dict(diffuse_sigma=0.1)) == 0
+    assert run((32, 64), fuse=True) == 0
+    tuning("pair_mode", 0)
+    assert run((32, 64)) == 0
 
 
 @pytest.mark.parametrize("shape,sigma,batch", [((64, 64), 0.5, None), ((40, 72), 0.5, 3), ((6, 76), 0.5, None),
