@@ -11,10 +11,11 @@ from .env import Env, Dynamics, BoundaryCondition, linear_action_cost, zero_cost
 from .data_init import WaveSequence, FieldSequence, TabulatedSequence, PerlinNoiseSequence
 from .agent import Agent, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent, ConvolutionModel, NeuralAutomataAgent
 from .graph import GraphedLoop
+from .evolve import PopulationEvaluator, PGPE
 
 _lib.load()     # fail loudly at import time if the CUDA library is missing
 
 __all__ = ['Env', 'Dynamics', 'BoundaryCondition', 'linear_action_cost', 'zero_cost',
            'Agent', 'ConstAgent', 'BrownianAgent', 'GradientAgent', 'PhysarumAgent', 'ConvolutionModel', 'NeuralAutomataAgent',
-           'GraphedLoop', 'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
+           'GraphedLoop', 'PopulationEvaluator', 'PGPE', 'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
 __version__ = '0.1.0'

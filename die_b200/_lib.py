@@ -89,6 +89,9 @@ SIGNATURES = {
     "die_brownian_forward_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_uint64, _P, _P]),
     "die_conv_policy_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_conv_policy_forward_population": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32,
+                                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int64,
+                                                     _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_device_l2_fetch_granularity": (C.c_int, [C.c_int32, _P]),
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
     "die_env_set_field_dtype": (C.c_int, [_P, C.c_int32]),

@@ -57,6 +57,7 @@ class ConvolutionModel:
             conv = torch.nn.Conv2d(self.num_obs_channels, cout, k, bias=False)
             self.kernels.append(conv.weight.detach().to(torch.float32))
         self._flat = None
+        self._population = None         # [P, num_parameters] float32 on the device: one model per environment of a batch
         self._scratch = None
         self._upload()
 
@@ -80,6 +81,31 @@ class ConvolutionModel:
                 raise ValueError(f"kernels.{l}.weight has shape {tuple(src.shape)}, expected {tuple(w.shape)}")
             w.copy_(src)
         self._upload()
+
+    @property
+    def num_parameters(self) -> int:
+        return sum(int(w.numel()) for w in self.kernels)
+
+    def set_population(self, vectors) -> None:
+        """One weight vector per environment of a batch (``[P, num_parameters]``, the layout of ``parameters_vector``):
+        ``forward`` on a batch of P environments then evaluates model p on environment p -- what a neuro-evolution
+        search scores (the reference's examples/learning_agents.py runs its candidates one after the other).  A
+        population of the same size is written IN PLACE, so a captured CUDA graph (die_b200.GraphedLoop) sees it.
+        ``None`` returns to the single model in ``kernels``."""
+        if vectors is None:
+            self._population = None
+            return
+        v = torch.as_tensor(vectors, dtype=torch.float32)
+        if v.dim() != 2 or v.shape[1] != self.num_parameters:
+            raise ValueError(f"population must be [P, {self.num_parameters}], got {tuple(v.shape)}")
+        if self._population is not None and tuple(self._population.shape) == tuple(v.shape):
+            self._population.copy_(v, non_blocking=False)
+        else:
+            self._population = v.to(self.device).contiguous().clone()
+
+    @property
+    def population(self) -> Optional[torch.Tensor]:
+        return self._population
 
     def parameters_vector(self) -> torch.Tensor:
         """All weights as one float32 vector (what a neuro-evolution search perturbs); see ``set_parameters_vector``."""
@@ -110,10 +136,16 @@ class ConvolutionModel:
         cf = (_lib.C.c_float * 3)(*(coefs or (1.0, 1.0, 1.0)))
         final = _lib.C.c_int32(0)
         dtype = _lib.FIELD_F32 if medium.dtype == torch.float32 else _lib.FIELD_F64
+        weights, stride = self._flat, 0
+        if self._population is not None:
+            if self._population.shape[0] != B:
+                raise ValueError(f"a population of {self._population.shape[0]} models needs a batch of as many "
+                                 f"environments, got {B}")
+            weights, stride = self._population, self.num_parameters
         with _lib.on_device(self.device):
-            _lib.check(self._lib.die_conv_policy_forward(
+            _lib.check(self._lib.die_conv_policy_forward_population(
                 H, W, M, B, dtype, medium.data_ptr(), in_total, in_ch0, self.num_obs_channels, self.num_act_channels,
-                len(self.kernel_sizes), ks, self._flat.data_ptr(), sa.data_ptr(), sb.data_ptr(),
+                len(self.kernel_sizes), ks, weights.data_ptr(), stride, sa.data_ptr(), sb.data_ptr(),
                 agents.data_ptr() if agents is not None else None, cells_ptr, cf,
                 action.data_ptr() if action is not None else None, _lib.C.byref(final),
                 torch.cuda.current_stream().cuda_stream))
@@ -150,6 +182,8 @@ class NeuralAutomataAgent(_DeviceAgent):
         self.action_coefs = (float(np.float32(scale)), float(np.float32(scale)), float(np.float32(deposit)))
         self._sense_output = None
         self.use_env_hints = True
+        self._step_dev = None           # (no random draws: nothing to keep on the device for a captured graph, see GraphedLoop)
+        self._rng = 'philox'
 
     @property
     def model(self) -> ConvolutionModel:
@@ -179,6 +213,10 @@ class NeuralAutomataAgent(_DeviceAgent):
         torch.autograd.graph.increment_version(action)
         self._step += 1
         return action
+
+    def set_population(self, vectors) -> None:
+        """See ``ConvolutionModel.set_population``."""
+        self._model.set_population(vectors)
 
     def render(self):
         """core/agent/evo.py:180-185: the model output with channels last."""

@@ -1195,12 +1195,14 @@ extern "C" int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient
 // ------------------------------------------------------------------------------------------
 // NeuralAutomataAgent.forward (core/agent/evo.py:117-209)
 // ------------------------------------------------------------------------------------------
-extern "C" int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
+extern "C" int die_conv_policy_forward_population(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
                                        const void* medium, int32_t in_ch_total, int32_t in_ch0, int32_t cin, int32_t cout_last,
                                        int32_t n_layers, const int32_t* kernel_sizes, const float* weights,
+                                       int64_t weight_env_stride,
                                        float* scratch_a, float* scratch_b,
                                        const double* agents, const int32_t* cells_hint, const float* coefs,
                                        double* action, int32_t* final_scratch, void* stream) {
+    DIE_REQUIRE(weight_env_stride >= 0);
     DIE_REQUIRE(H >= 1 && W >= 1 && M >= 1 && B >= 1 && (int64_t)H * W <= 0x7fffffffLL);
     DIE_REQUIRE(field_dtype == DIE_FIELD_F64 || field_dtype == DIE_FIELD_F32);
     DIE_REQUIRE(medium != nullptr && weights != nullptr && scratch_a != nullptr && scratch_b != nullptr);
@@ -1219,6 +1221,7 @@ extern "C" int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t 
         a.in = in;
         a.out = (l & 1) ? scratch_b : scratch_a;
         a.weight = w;
+        a.weight_env_stride = weight_env_stride;
         a.H = H; a.W = W; a.k = k;
         a.cin = cin;
         a.cout = (l == n_layers - 1) ? cout_last : cin;
@@ -1243,6 +1246,17 @@ extern "C" int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t 
                                                                M, cout_last, B, coefs[0], coefs[1], coefs[2]);
     DIE_CUDA(cudaGetLastError());
     return DIE_OK;
+}
+
+extern "C" int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
+                                       const void* medium, int32_t in_ch_total, int32_t in_ch0, int32_t cin, int32_t cout_last,
+                                       int32_t n_layers, const int32_t* kernel_sizes, const float* weights,
+                                       float* scratch_a, float* scratch_b,
+                                       const double* agents, const int32_t* cells_hint, const float* coefs,
+                                       double* action, int32_t* final_scratch, void* stream) {
+    return die_conv_policy_forward_population(H, W, M, B, field_dtype, medium, in_ch_total, in_ch0, cin, cout_last, n_layers,
+                                              kernel_sizes, weights, 0, scratch_a, scratch_b, agents, cells_hint, coefs,
+                                              action, final_scratch, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,6 +25,8 @@ struct ConvLayerArgs {
     const void* in;        // [B][cin_total][H][W], element type TIN; channel c of the layer = in channel (c + in_ch0)
     float* out;            // [B][cout][H][W]
     const float* weight;   // [cout][cin][k][k] (torch Conv2d layout)
+    int64_t weight_env_stride;  // floats between the weight sets of consecutive environments (0: one model for the batch;
+                                // a POPULATION of models, one per environment, otherwise)
     int H, W, cin, cout, k, cin_total, in_ch0;
     int tiles_i, tiles_j;
     int apply_tanh;
@@ -47,7 +49,8 @@ conv_layer_kernel(const ConvLayerArgs a) {
     const int i0 = ti * kConvTile, j0 = tj * kConvTile;
     const TIN* in = (const TIN*)a.in + (b * a.cin_total + a.in_ch0) * C;
 
-    for (int i = threadIdx.x; i < a.cout * a.cin * a.k * a.k; i += 256) s_w[i] = a.weight[i];
+    const float* wsrc = a.weight + b * a.weight_env_stride;
+    for (int i = threadIdx.x; i < a.cout * a.cin * a.k * a.k; i += 256) s_w[i] = wsrc[i];
     for (int idx = threadIdx.x; idx < a.cin * LH * LW; idx += 256) {
         const int c = idx / (LH * LW), rem = idx - c * (LH * LW);
         const int rr = rem / LW, cc = rem - rr * LW;

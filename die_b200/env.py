@@ -196,8 +196,9 @@ class Env:
         self._init_data(self._field_size, init_state)
 
     # -- construction ---------------------------------------------------------------------
-    def _init_data(self, field_size, init_state=None):
-        """core/env.py:74-86."""
+    def _init_data(self, field_size, init_state=None, in_place=False):
+        """core/env.py:74-86.  in_place (reset()): when the new state has the shape of the old one, it is written into the
+        existing tensors -- the library handle, every buffer address and therefore a captured GraphedLoop stay valid."""
         h, w = field_size
         B = self._B
         owned = False
@@ -224,6 +225,21 @@ class Env:
             medium, agents = (np.asarray(a, dtype=np.float64) for a in init_state)
             medium = medium.reshape(B, 3, h, w)
             agents = agents.reshape(B, 4, -1)
+        if in_place and self._handle is not None and int(agents.shape[-1]) == self._M \
+                and self._dynamics_key == self._dynamics_snapshot():
+            with torch.cuda.device(self.device):
+                to_t = (lambda a: a) if isinstance(medium, torch.Tensor) else (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
+                self._medium_buf[0].copy_(to_t(medium))
+                self._agents.copy_(to_t(agents))
+                self._cur = 0
+                self._reward_dev.zero_()
+                self._alive_dev.zero_()
+                self.invalidate_caches()
+                self.last_step_fused = False
+                if self._obs_buf is not None:
+                    self._refresh_sensed_medium()
+                _hints.publish(self, self._medium_buf[0])
+            return
         self._M = int(agents.shape[-1])
         with torch.cuda.device(self.device):
             if isinstance(medium, torch.Tensor):
@@ -368,9 +384,17 @@ class Env:
             pass
 
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None) -> Tuple[ObsType, dict]:
-        """core/env.py:94-99 (``seed`` is ignored there too)."""
-        self._init_data(self._field_size)
+        """core/env.py:94-99 (``seed`` is ignored there too).  The new state is written into the env's existing tensors
+        (tensors handed out earlier as observations now show the new state, as the reference's views of its xarray would
+        not -- copy what must survive a reset)."""
+        self._init_data(self._field_size, in_place=True)
         return self._get_current_obs, {}
+
+    def _hints_are_current(self) -> bool:
+        """The caches offered to agents (cells, gradient, food under the agent) describe the env's CURRENT tensors."""
+        st = self._hint_state
+        buf = self._medium_buf[self._cur]
+        return st is not None and st[0] == buf.data_ptr() and st[1] == buf._version and st[2] == self._agents._version
 
     # -- state access ---------------------------------------------------------------------
     def _unbatch(self, t):

@@ -77,7 +77,10 @@ class GraphedLoop:
             raise RuntimeError("env.dynamics changed after this GraphedLoop was captured (kernel arguments are baked into "
                                "the graph): build a new GraphedLoop")
         with torch.cuda.device(env.device):
-            if iterations > 0 and env._cur != self._cur0:    # an odd run left the medium in the other buffer: step once eagerly
+            # eager iterations first (at most two) while the replay's baked-in assumptions do not hold: an odd run left the
+            # medium in the other buffer; or the env's caches are stale (an in-place reset(), set_state, an edited tensor)
+            # -- the captured forward uses them as the eager one did at capture time, an eager step rebuilds them
+            while iterations > 0 and (env._cur != self._cur0 or not env._hints_are_current()):
                 self._eager_step()
                 iterations -= 1
                 self.iterations += 1

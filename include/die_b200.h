@@ -394,6 +394,17 @@ int die_conv_policy_forward(int32_t H, int32_t W, int64_t M, int32_t B, int32_t 
                             const double* agents_dev, const int32_t* cells_hint_dev, const float* coefs_host,
                             double* action_dev, int32_t* final_scratch, void* stream);
 
+/* The same with a POPULATION of models, one per environment of the batch (what a neuro-evolution search evaluates: the
+ * reference's examples/learning_agents.py scores one candidate after the other on one env): environment b uses the
+ * weights at weights_dev + b * weight_env_stride (floats; 0 = one model for every environment, as above). */
+int die_conv_policy_forward_population(int32_t H, int32_t W, int64_t M, int32_t B, int32_t field_dtype,
+                            const void* medium_dev, int32_t in_ch_total, int32_t in_ch0, int32_t cin, int32_t cout_last,
+                            int32_t n_layers, const int32_t* kernel_sizes_host, const float* weights_dev,
+                            int64_t weight_env_stride,
+                            float* scratch_a_dev, float* scratch_b_dev,
+                            const double* agents_dev, const int32_t* cells_hint_dev, const float* coefs_host,
+                            double* action_dev, int32_t* final_scratch, void* stream);
+
 /* Diagnostics: the kernels' bit-reproducible sin/cos/atan2 (die_b200/csrc/die_math.h) applied
  * to device arrays, so tests can check the device results equal the host build of the same
  * source bit-for-bit.  fast != 0 selects die_atan2_fast. */

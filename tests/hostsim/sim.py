@@ -251,11 +251,17 @@ def brownian_forward(agents, move_scale=0.01, deposit_scale=0.5, u=None, seed=0,
     return action if agents.ndim == 3 else action[0]
 
 
-def conv_policy_forward(env, weights, coefs=(0.1, 0.1, 1.0), with_agent_channel=True, use_cells=False):
-    """die_b200.NeuralAutomataAgent.forward's call on numpy arrays -> (action [B, 3, M] float64, model output [B, 3, H, W])."""
+def conv_policy_forward(env, weights, coefs=(0.1, 0.1, 1.0), with_agent_channel=True, use_cells=False, population=None):
+    """die_b200.NeuralAutomataAgent.forward's call on numpy arrays -> (action [B, 3, M] float64, model output [B, 3, H, W]).
+    population: a list of B weight lists (one model per environment) instead of `weights`."""
+    if population is not None:
+        weights = population[0]
     ks = [int(w.shape[-1]) for w in weights]
     cin = int(weights[0].shape[1])
-    flat = fenced_copy(np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights]), np.float32)
+    sets = population if population is not None else [weights]
+    rows = [np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws]) for ws in sets]
+    stride = rows[0].size if population is not None else 0
+    flat = fenced_copy(np.concatenate(rows), np.float32)
     ch = max(cin, 3)
     sa, sb = fenced((env.B, ch, env.h, env.w), np.float32, fill=np.nan), fenced((env.B, ch, env.h, env.w), np.float32, fill=np.nan)
     action = fenced((env.B, 3, env.M), fill=np.nan)
@@ -264,9 +270,10 @@ def conv_policy_forward(env, weights, coefs=(0.1, 0.1, 1.0), with_agent_channel=
     final = C.c_int32(0)
     dtype = L.FIELD_F32 if env.medium.dtype == np.float32 else L.FIELD_F64
     cells = lib().die_env_cells(env.handle) if use_cells else None
-    check(lib().die_conv_policy_forward(env.h, env.w, env.M, env.B, dtype, ptr(env.medium), 3, 0 if with_agent_channel else 1,
-                                        cin, 3, len(ks), ksa, ptr(flat), ptr(sa), ptr(sb), ptr(env.agents), cells, cf,
-                                        ptr(action), C.byref(final), None))
+    check(lib().die_conv_policy_forward_population(
+        env.h, env.w, env.M, env.B, dtype, ptr(env.medium), 3, 0 if with_agent_channel else 1,
+        cin, 3, len(ks), ksa, ptr(flat), stride, ptr(sa), ptr(sb), ptr(env.agents), cells, cf,
+        ptr(action), C.byref(final), None))
     out = (sa, sb)[final.value]
     return action, out[:, :3].copy()
 

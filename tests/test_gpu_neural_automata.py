@@ -108,3 +108,72 @@ def test_serialize():
     buf.seek(0)
     loaded = th.load(buf, weights_only=False)
     assert set(loaded) == {'params_dict', 'model_state'} and set(loaded['model_state']) == {'kernels.0.weight', 'kernels.1.weight'}
+
+
+def test_population_evaluator_equals_one_candidate_at_a_time():
+    """die_b200.PopulationEvaluator: P candidates scored at once on a batched env (one model per environment, CUDA-graph
+    replay, rewards summed on the device) == the eager batched loop == every candidate alone on a single env started
+    from the same state -- bit for bit; and the oracle's NeuralAutomataAgent + Env within the float32 tolerance."""
+    import torch
+    import die_b200 as D
+    from oracle import die_ref as R
+    from tests._parity import make_pair
+    field, P, iters = (48, 40), 4, 9
+    kw = dict(kernel_sizes=[3, 3], scale=0.01, deposit=2.0)
+    rng = np.random.default_rng(3)
+    agent = D.NeuralAutomataAgent(**kw)
+    cands = rng.uniform(-0.5, 0.5, size=(P, agent.model.num_parameters)).astype(np.float32)
+    dyn = dict(food_infinite=True)
+    scores = []
+    for graph in (True, False):
+        refs, env = make_pair(field, seed=31, ratio=0.15, dynamics_kw=dyn, batch=P)
+        ev = D.PopulationEvaluator(env, D.NeuralAutomataAgent(**kw), graph=graph)
+        if not graph:
+            ev.evaluate(cands, 2)                                    # the capture's two eager warm-up iterations
+        s1 = ev.evaluate(cands, iters)
+        s2 = ev.evaluate(cands[::-1].copy(), iters + 1)              # continues where the first left off; odd count
+        scores.append((s1, s2, *env.get_state()))
+    for a, b in zip(scores[0], scores[1]):
+        assert np.array_equal(a, b)
+    # every candidate alone, from the same initial state as its environment of the batch:
+    refs, env = make_pair(field, seed=31, ratio=0.15, dynamics_kw=dyn, batch=P)
+    singles, osum = [], []
+    for p in range(P):
+        (ref,), one = make_pair(field, seed=31 + p, ratio=0.15, dynamics_kw=dyn)
+        ag = D.NeuralAutomataAgent(**kw)
+        ag.model.set_parameters_vector(cands[p])
+        oa = R.NeuralAutomataAgent([w.numpy() for w in ag.model.kernels], scale=0.01, deposit=2.0)
+        obs, total, ototal = one._get_current_obs, 0.0, 0.0
+        robs = ref._get_current_obs
+        for _ in range(iters):
+            obs, r, *_ = one.step(ag.forward(obs))
+            total += r
+            robs, rr, *_ = ref.step(oa.forward(robs))
+            ototal += rr
+        singles.append(total)
+        osum.append(ototal)
+    ev = D.PopulationEvaluator(env, D.NeuralAutomataAgent(**kw), graph=False)
+    batch_scores = ev.evaluate(cands, iters)
+    assert np.array_equal(batch_scores, np.array(singles))
+    np.testing.assert_allclose(batch_scores, np.array(osum), rtol=2e-4)
+    with pytest.raises(ValueError):
+        ev.evaluate(cands[:2], 3)
+
+
+def test_pgpe_improves_a_population_on_the_gpu():
+    """A few generations of the search the reference's examples/learning_agents.py configures (PGPE, popsize 10, infinite
+    food): the best score of the last generations exceeds the first generation's mean."""
+    import die_b200 as D
+    env = D.Env((64, 64), D.Dynamics(init_agent_ratio=0.15, food_infinite=True), init='device', seed=5, batch=10)
+    agent = D.NeuralAutomataAgent(kernel_sizes=[3, 3], scale=0.01, deposit=2.0)
+    ev = D.PopulationEvaluator(env, agent)
+    es = D.PGPE(agent.model.num_parameters, popsize=10, radius_init=1.5, seed=1)
+    history = []
+    for gen in range(12):
+        cand = es.ask()
+        fit = ev.evaluate(cand, 20)
+        assert np.isfinite(fit).all()
+        es.tell(fit)
+        history.append(fit)
+    assert es.best[1] is not None and ev.evaluations == 12
+    assert max(h.max() for h in history[-4:]) > history[0].mean()
