@@ -12,7 +12,8 @@ arguments, so everything that varies per iteration lives on the device:
     (DIE_FWD_STEP_ON_DEVICE, die_brownian_forward_dev) and a captured `counter += 1` advances -- every replayed
     iteration draws the numbers the eager loop would have drawn, so results are bit-identical to the eager loop;
   * rewards: accumulated into `reward_sum` (and the last one kept) on the device; read them back when needed.
-Restrictions (checked): device observations, in-kernel randomness (rng='philox': host draws cannot be captured), the
+`Env.reset()` (in place), `set_state` and edits of the env's tensors between runs are fine: `run` notices stale caches and
+takes up to two eager iterations before it replays.  Restrictions (checked): device observations, in-kernel randomness (rng='philox': host draws cannot be captured), the
 identity or wave / tabulated food flow is NOT supported (its time index is host state), no speculative move.
 """
 from __future__ import annotations

@@ -55,7 +55,10 @@ def test_graphed_loop_notices_changed_dynamics_and_recreated_buffers():
     env.dynamics.rate_feed = 0.3
     with pytest.raises(RuntimeError, match="dynamics changed"):
         loop.run(2)
-    env.reset()                      # under changed dynamics the env is re-created (new handle, new buffers)
+    loop = D.GraphedLoop(env, D.BrownianAgent())
+    loop.run(2)
+    env.dynamics.rate_feed = 0.1
+    env.reset()                      # under changed dynamics reset() re-creates the env (new handle, new buffers)
     with pytest.raises(RuntimeError, match="reset"):
         loop.run(2)
 
