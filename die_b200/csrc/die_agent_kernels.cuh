@@ -205,10 +205,13 @@ gradient_forward_kernel(const GradientArgs a) {
 
     // per-thread base pointers, advanced by kAgentThreads per item
     const double* ag_x = a.agents + ch.b * 4 * M + first;
+    const double* ag_y = ag_x + M;       // (own base pointers: `ag_x[M + i]` costs a 64-bit index sum per access)
     const FT* food = (const FT*)a.medium + (ch.b * 3 + 1) * C;
     const FT* chem = (const FT*)a.medium + (ch.b * 3 + 2) * C;
     double* th_p = a.theta + ch.b * M + first;
     double* ab = a.action + ch.b * 3 * M + first;
+    double* ab_y = ab + M;
+    double* ab_dep = ab + 2 * M;
     double* pg = (!LEAN && a.prev_grad != nullptr) ? a.prev_grad + ch.b * 2 * M + first : nullptr;
     const uint8_t* coin_p = (!LEAN && a.coin != nullptr) ? a.coin + ch.b * M + first : nullptr;
     const double* nz = (!LEAN && a.noise != nullptr) ? a.noise + ch.b * 2 * M + first : nullptr;
@@ -240,7 +243,7 @@ gradient_forward_kernel(const GradientArgs a) {
     int ncell = 0;
     if (nvalid) {
         nx = ag_x[0];
-        ny = ag_x[M];
+        ny = ag_y[0];
         nth = th_p[0];
         if (FH) nfh = fh_p[0];
         else if (LEAN || cl_p != nullptr) ncell = cl_p[0];
@@ -263,7 +266,7 @@ gradient_forward_kernel(const GradientArgs a) {
         nvalid = (k + 1 < kFwdItems) && (i + kAgentThreads < left);
         if (nvalid) {                                          // next item's coalesced loads
             nx = ag_x[i + kAgentThreads];
-            ny = ag_x[M + i + kAgentThreads];
+            ny = ag_y[i + kAgentThreads];
             nth = th_p[i + kAgentThreads];
             if (FH) nfh = fh_p[i + kAgentThreads];
             else if (LEAN || cl_p != nullptr) ncell = cl_p[i + kAgentThreads];
@@ -300,9 +303,12 @@ gradient_forward_kernel(const GradientArgs a) {
         const int sc = sx * W + sy;                                // H*W < 2^31 (die_env_create)
         if (!LEAN && sc_p != nullptr) sc_p[i] = sc;
         double gx, gy;
+        float gxf = 0.f, gyf = 0.f;
         const bool from32 = G32 || (!LEAN && grad32 != nullptr);
         if (from32) {                                                    // published as float32: one 8-byte gather
             const float2 g2 = grad32[sc];
+            gxf = g2.x;
+            gyf = g2.y;
             gx = (double)g2.x;
             gy = (double)g2.y;
         } else if (LEAN || (SLAB ? a.st.grad != nullptr : grad != nullptr)) {   // published by the field pass: one 16-byte gather
@@ -333,7 +339,10 @@ gradient_forward_kernel(const GradientArgs a) {
             // the rest (about one warp in 300) runs the reference's own arithmetic, die_turn_exact.
             die_turn_t tr;
             double dr = 1.0;
-            if (!((LEAN || a.plan.enabled) && die_turn_quick_f(&a.plan, gx, gy, sf, cf, th, atol, p.sense_radians, &tr))) {
+            // (G32: the float32 pair goes to the decision as it is; die_turn_quick_f would round-trip it through double)
+            if (!((LEAN || a.plan.enabled) &&
+                  (G32 ? die_turn_quick_ff(&a.plan, gxf, gyf, sf, cf, th, atol, p.sense_radians, &tr)
+                       : die_turn_quick_f(&a.plan, gx, gy, sf, cf, th, atol, p.sense_radians, &tr)))) {
                 if (from32) sample_gradient(chem, sx, sy, H, W, gx, gy);     // the exact path wants all 53 bits
                 if (LEAN) {           // (normalised gradient: dr = 1)
                     tr = turn_exact_call(gx, gy, th, atol, p.sense_radians, 1, p.use_grad_clip, p.grad_clip);
@@ -345,8 +354,9 @@ gradient_forward_kernel(const GradientArgs a) {
                 }
             }
             const int c = (!LEAN && coin_p != nullptr) ? (coin_p[i] ? 1 : 0) : (int)((coin_bits >> k) & 1u);
-            double turn = (tr.turn != 0) ? (double)tr.turn : ((double)c - 0.5) * 2.0;
-            turn *= p.turn_radians;
+            // turn = (tr.turn != 0 ? tr.turn : ((double)c - 0.5) * 2.0) * turn_radians: the factor is exactly +-1
+            const int tsign = (tr.turn != 0) ? tr.turn : 2 * c - 1;
+            const double turn = (tsign < 0) ? -p.turn_radians : p.turn_radians;
             deposit_mask = tr.deposit_mask != 0;
             const double dirn = renormalize_radians(th + turn);
             double s2, c2;
@@ -394,8 +404,8 @@ gradient_forward_kernel(const GradientArgs a) {
 
         const double adx = gx * p.scale, ady = gy * p.scale;  // unmasked (Q8)
         ab[i] = adx;
-        ab[M + i] = ady;
-        ab[2 * M + i] = dep;
+        ab_y[i] = ady;
+        ab_dep[i] = dep;
 
         if (MOVE) {
             // Env._agent_move (core/env.py:152-172) of THIS action + cell resolution + claim: what

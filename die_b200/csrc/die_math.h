@@ -202,15 +202,17 @@ DIE_MATH_FN void die_sincosf_approx(double x, float* sn_out, float* cs_out) {
     const double kd = DIE_SUB(ku, DIE_RINT_MAGIC);                          /* rint(x 2/pi) */
     const int k = DIE_LO32(ku);
     const float r = (float)DIE_SUB(DIE_FMA(-kd, DIE_K(PIO2_1), x), DIE_MUL(kd, DIE_K(PIO2_T)));
+    /* explicit fmaf: the library is compiled without contraction (-fmad=false / -ffp-contract=off), and fmaf is the
+     * same correctly rounded operation on the host and on the device */
     const float z = r * r;
     float ps = -1.9515295891e-4f;
-    ps = ps * z + 8.3321608736e-3f;
-    ps = ps * z - 1.6666654611e-1f;
-    const float s = r + (r * z) * ps;
+    ps = fmaf(ps, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float s = fmaf(r * z, ps, r);
     float pc = 2.443315711809948e-5f;
-    pc = pc * z - 1.388731625493765e-3f;
-    pc = pc * z + 4.166664568298827e-2f;
-    const float c = (1.0f - 0.5f * z) + (z * z) * pc;
+    pc = fmaf(pc, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    const float c = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
     const float s_sel = (k & 1) ? c : s, c_sel = (k & 1) ? s : c;
     *sn_out = (k & 2) ? -s_sel : s_sel;
     *cs_out = ((k + 1) & 2) ? -c_sel : c_sel;

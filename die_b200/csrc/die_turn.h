@@ -48,10 +48,12 @@ DIE_MATH_FN double die_renormalize_radians(double r) {
     const double a = DIE_SUB(r, DIE_PI);
     double m;
     if (fabs(a) < 2.0 * DIE_TWO_PI) {
-        double f = a;
-        if (a >= DIE_TWO_PI) f = DIE_SUB(a, DIE_TWO_PI);
-        else if (a <= -DIE_TWO_PI) f = DIE_ADD(a, DIE_TWO_PI);
-        m = (f > 0.0) ? DIE_SUB(f, DIE_TWO_PI) : f;
+        /* f = a - 2pi for a >= 2pi, a + 2pi for a <= -2pi, a otherwise; m = f - 2pi for f > 0, f otherwise -- written
+         * as additions of a selected constant (x - c and x + (-c) are the same operation; x + 0.0 = x except that it
+         * turns -0. into +0., which the final + pi absorbs): two selects of a constant instead of four of a variable */
+        const double wrap = (fabs(a) >= DIE_TWO_PI) ? DIE_TWO_PI : 0.0;
+        const double f = DIE_ADD(a, copysign(wrap, -a));
+        m = DIE_ADD(f, (f > 0.0) ? -DIE_TWO_PI : 0.0);
     } else {
         m = die_np_remainder(a, -DIE_TWO_PI);
     }
@@ -168,40 +170,52 @@ static inline die_turn_plan_t die_turn_plan(int normalized, int use_clip, double
  * A clipped gradient (|g| < grad_clip: every slot far from any trail) is settled exactly instead: its
  * processed value is (+-0, +-0), so phi is 0 (undetermined_grad) or, for two negative zeros, exactly pi
  * -- and delta = renormalize(theta - pi) then sits ON the sense threshold for headings of +-90 degrees. */
+/* The decision proper on the float32 image of the gradient.  neg_both / any_zero: both components of the float64
+ * gradient carry a sign bit / one of them is a zero (only looked at for a clipped gradient). */
+#define DIE_TURN_QUICK_BODY_(NEG_BOTH, ANY_ZERO)                                                                     \
+    const float n2 = fmaf(gxf, gxf, gyf * gyf);                                                                      \
+    if (!(n2 < p->n2_max)) return 0;                        /* huge, inf or nan */                                   \
+    if (!(n2 >= p->clip2_hi)) {                                                                                      \
+        if (!(n2 <= p->clip2_lo)) return 0;                 /* too close to the clip threshold */                    \
+        if (!(NEG_BOTH)) {                                  /* a positive zero survives: phi = 0 */                  \
+            out->turn = 0;                                                                                           \
+            out->deposit_mask = 0;                                                                                   \
+            return 1;                                                                                                \
+        }                                                                                                            \
+        /* both negative: -0 only keeps its sign if norm != 0 (die_normalize_gradient), which takes the              \
+         * exact norm when a component IS zero */                                                                    \
+        if (ANY_ZERO) return 0;                                                                                      \
+        *out = die_turn_from_angle(DIE_PI, theta, atol, sense_radians);     /* angle(-0. - 0.j) = pi */              \
+        return 1;                                                                                                    \
+    }                                                                                                                \
+    if (gxf > 0.0f && fabsf(gyf) <= p->phi0_ratio * gxf) return 0;    /* phi within ~1e-8 of 0: isclose(0, phi) */   \
+    const float cd = fmaf(cf, gxf, sf * gyf);                                                                        \
+    const float sd = fmaf(sf, gxf, -(cf * gyf));                                                                     \
+    const float q = cd * fabsf(cd);                                                                                  \
+    int unseen, und_turn;                                                                                            \
+    if (q < p->ks_lo * n2) unseen = 1;                                                                               \
+    else if (q > p->ks_hi * n2) unseen = 0;                                                                          \
+    else return 0;                                                                                                   \
+    if (q > p->ka_hi * n2) und_turn = 1;                                                                             \
+    else if (q < p->ka_lo * n2) und_turn = 0;                                                                        \
+    else return 0;                                                                                                   \
+    out->deposit_mask = !und_turn;                                                                                   \
+    /* seen and determined: atol/0.99 < |delta| < sense < pi, so sin(delta) is far from 0 and has                    \
+     * the sign of delta; delta > atol turns by -1, delta < -atol by +1 (:186-187) */                                \
+    out->turn = (unseen || und_turn) ? 0 : (sd > 0.0f ? -1 : 1);                                                     \
+    return 1;
+
+/* The gradient as published in float32 (the env's float32 cache: the value IS the float64 gradient rounded once, so
+ * its signs and zeros are those of the float64 value unless that underflowed -- n2 then sits far below the clip). */
+DIE_MATH_FN int die_turn_quick_ff(const die_turn_plan_t* p, float gxf, float gyf, float sf, float cf,
+                                  double theta, double atol, double sense_radians, die_turn_t* out) {
+    DIE_TURN_QUICK_BODY_(signbit(gxf) && signbit(gyf), gxf == 0.0f || gyf == 0.0f)
+}
+
 DIE_MATH_FN int die_turn_quick_f(const die_turn_plan_t* p, double gx, double gy, float sf, float cf,
                                  double theta, double atol, double sense_radians, die_turn_t* out) {
     const float gxf = (float)gx, gyf = (float)gy;
-    const float n2 = gxf * gxf + gyf * gyf;
-    if (!(n2 < p->n2_max)) return 0;                        /* huge, inf or nan */
-    if (!(n2 >= p->clip2_hi)) {
-        if (!(n2 <= p->clip2_lo)) return 0;                 /* too close to the clip threshold */
-        if (!(signbit(gx) && signbit(gy))) {                /* a positive zero survives: phi = 0 */
-            out->turn = 0;
-            out->deposit_mask = 0;
-            return 1;
-        }
-        /* both negative: -0 only keeps its sign if norm != 0 (die_normalize_gradient), which takes the
-         * exact norm when a component IS zero */
-        if (gx == 0.0 || gy == 0.0) return 0;
-        *out = die_turn_from_angle(DIE_PI, theta, atol, sense_radians);     /* angle(-0. - 0.j) = pi */
-        return 1;
-    }
-    if (gxf > 0.0f && fabsf(gyf) <= p->phi0_ratio * gxf) return 0;    /* phi within ~1e-8 of 0: isclose(0, phi) */
-    const float cd = cf * gxf + sf * gyf;
-    const float sd = sf * gxf - cf * gyf;
-    const float q = cd * fabsf(cd);
-    int unseen, und_turn;
-    if (q < p->ks_lo * n2) unseen = 1;
-    else if (q > p->ks_hi * n2) unseen = 0;
-    else return 0;
-    if (q > p->ka_hi * n2) und_turn = 1;
-    else if (q < p->ka_lo * n2) und_turn = 0;
-    else return 0;
-    out->deposit_mask = !und_turn;
-    /* seen and determined: atol/0.99 < |delta| < sense < pi, so sin(delta) is far from 0 and has
-     * the sign of delta; delta > atol turns by -1, delta < -atol by +1 (:186-187) */
-    out->turn = (unseen || und_turn) ? 0 : (sd > 0.0f ? -1 : 1);
-    return 1;
+    DIE_TURN_QUICK_BODY_(signbit(gx) && signbit(gy), gx == 0.0 || gy == 0.0)
 }
 
 DIE_MATH_FN int die_turn_quick(const die_turn_plan_t* p, double gx, double gy, double sn, double cs,

@@ -3,6 +3,7 @@
  * bit-reproducible routines the CUDA kernels use, so free-running trajectories can be compared
  * bit-for-bit).  Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/build_oracle.py). */
 #include "../die_b200/csrc/die_math.h"
+#include "../die_b200/csrc/die_turn.h"
 
 void die_sincos_array(const double* x, double* sn, double* cs, long n) {
     for (long i = 0; i < n; ++i) die_sincos(x[i], sn + i, cs + i);
@@ -23,4 +24,10 @@ void die_sincosf_approx_array(const double* x, float* sn, float* cs, long n) {
 
 void die_sincos_angle_array(const double* x, double* sn, double* cs, double* ang, long n) {
     for (long i = 0; i < n; ++i) die_sincos_angle(x[i], sn + i, cs + i, ang + i);
+}
+
+/* renormalize_radians (core/utils.py:177-179) as the kernels spell it (die_turn.h): checked against numpy's own
+ * (r - pi) % (-2 pi) + pi bit for bit (tests/test_portable_math.py) */
+void die_renormalize_radians_array(const double* r, double* out, long n) {
+    for (long i = 0; i < n; ++i) out[i] = die_renormalize_radians(r[i]);
 }

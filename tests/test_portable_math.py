@@ -113,3 +113,30 @@ def test_float32_sincos_stays_within_its_stated_error():
     lib.die_sincosf_approx_array(P(x, ctypes.c_double), P(s, ctypes.c_float), P(c, ctypes.c_float), ctypes.c_long(x.size))
     lib.die_sincos_array(P(x, ctypes.c_double), P(sd, ctypes.c_double), P(cd, ctypes.c_double), ctypes.c_long(x.size))
     assert np.abs(s - sd).max() <= 2e-7 and np.abs(c - cd).max() <= 2e-7        # half the budget
+
+
+def test_renormalize_radians_equals_numpy_bit_for_bit():
+    """die_renormalize_radians (die_turn.h; the select-light form of round 2) against the reference's own expression
+    (core/utils.py:177-179) evaluated by numpy: headings around every multiple of pi / 12 and of 2 pi, +-ulps, +-0, the
+    branch bounds at |r - pi| = 2 pi and 4 pi, large arguments (the generic fmod branch)."""
+    import ctypes
+    from oracle import build_oracle
+    lib = ctypes.CDLL(build_oracle.build())
+    rng = np.random.default_rng(1)
+    base = np.concatenate([np.arange(-96, 97) * np.pi / 12, np.arange(-8, 9) * np.pi, np.array([0.0, -0.0]),
+                           np.pi + np.array([-4, -2, 2, 4]) * (2 * np.pi), rng.uniform(-4 * np.pi, 4 * np.pi, 200000),
+                           rng.uniform(-1e3, 1e3, 20000), rng.uniform(-1e9, 1e9, 2000)])
+    xs = [base]
+    for k in (1, 2, 3, 17):
+        up, dn = base.copy(), base.copy()
+        for _ in range(k):
+            up, dn = np.nextafter(up, np.inf), np.nextafter(dn, -np.inf)
+        xs += [up, dn]
+    turn = np.radians(30)
+    xs += [base + turn, base - turn]
+    x = np.ascontiguousarray(np.concatenate(xs))
+    out = np.empty_like(x)
+    P = lambda v: v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    lib.die_renormalize_radians_array(P(x), P(out), ctypes.c_long(x.size))
+    want = (x - np.pi) % (-2 * np.pi) + np.pi
+    assert np.array_equal(out.view(np.int64), want.view(np.int64))

@@ -1,6 +1,7 @@
 """A short tour of every kernel and option combination on small inputs (device init, batches, every agent, food flow +
 sense mask + 'constant' diffusion, speculative move, render, chunked host path, the cluster-fused step with its
-distributed-shared-memory claims and bulk copies, the 128-bit field pass, agents_die, float32 fields, the graphed loop).
+distributed-shared-memory claims and bulk copies, the 128-bit field pass, pair mode, agents_die, float32 fields, the
+graphed loop, a population of convolution policies).
 Written to be run under compute-sanitizer:
     compute-sanitizer --tool memcheck  python tools/sanitize_run.py
     compute-sanitizer --tool racecheck python tools/sanitize_run.py      (shared-memory hazards inside a CTA)
@@ -39,14 +40,14 @@ for mode, flow, mask in (("wrap", False, False), ("constant", True, True), ("ref
         hobs, *_ = big.step(ag.forward(hobs))
     _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
     _lib.check(lib.die_set_tuning(b"host_chunks", 4))
-for key, batch in ((b"step_impl", 3), (b"field_vec", None)):             # the cluster-fused step, the 128-bit field pass
-    _lib.check(lib.die_set_tuning(key, 1))
+for key, batch in ((b"step_impl", 3), (b"field_vec", None), (b"pair_mode", 2)):     # the cluster-fused step, the 128-bit
+    _lib.check(lib.die_set_tuning(key, 2 if key == b"pair_mode" else 1))            # field pass, pair mode forced
     env = D.Env((64, 40), D.Dynamics(), init='device', seed=3, batch=batch)
     ag = D.PhysarumAgent(max_agents=env.max_agents, scale=0.02, sense_offset=0.06)
     obs = env._get_current_obs
     for _ in range(4):
         obs, *_ = env.step(ag.forward(obs))
-    _lib.check(lib.die_set_tuning(key, 0))
+    _lib.check(lib.die_set_tuning(key, 1 if key == b"pair_mode" else 0))
 env = D.Env((48, 64), D.Dynamics(agents_die=True, rate_feed=0.02), init='device', seed=4)        # lifecycle
 ag = D.BrownianAgent(0.03, 2.0)
 obs = env._get_current_obs
@@ -59,5 +60,9 @@ for _ in range(4):
     obs, *_ = env.step(ag.forward(obs))
 loop = D.GraphedLoop(D.Env((32, 32), D.Dynamics(), init='device', seed=6), D.BrownianAgent(0.02))       # CUDA graph replay
 loop.run(6)
+penv = D.Env((40, 48), D.Dynamics(food_infinite=True), init='device', seed=7, batch=4)                  # one model per env
+pag = D.NeuralAutomataAgent(kernel_sizes=[3, 5], scale=0.01, deposit=2.0)
+ev = D.PopulationEvaluator(penv, pag)
+ev.evaluate(np.random.default_rng(0).uniform(-0.5, 0.5, (4, pag.model.num_parameters)).astype(np.float32), 5, reset=True)
 torch.cuda.synchronize()
 print("sanitize tour done")
