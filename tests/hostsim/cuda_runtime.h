@@ -57,6 +57,7 @@ struct ThreadCtx {
 extern ThreadCtx* cur;
 void* dyn_smem();
 void syncthreads();
+int syncthreads_or(int pred);
 void warp_exchange(uint64_t mine, uint64_t* all32);      // all32[l] = value deposited by lane l (stale if it exited)
 unsigned lane_id();
 void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
@@ -88,10 +89,16 @@ static inline double __hiloint2double(int hi, int lo) {
     const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double d; memcpy(&d, &u, 8); return d;
 }
+static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline int atomicMax(int* p, int v) { const int old = *p; if (v > old) *p = v; return old; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
+    const unsigned long long old = *p;          // (fibers switch only at barriers: a plain read-modify-write is atomic here)
+    if (old == cmp) *p = val;
+    return old;
+}
 
 // ---- warp collectives -------------------------------------------------------------------------
 template <typename T>
@@ -118,6 +125,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return w;
 }
 static inline void __syncthreads() { hostsim::syncthreads(); }
+static inline int __syncthreads_or(int pred) { return hostsim::syncthreads_or(pred); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { uint64_t all[32]; hostsim::warp_exchange(0, all); }
 static inline void __trap() { abort(); }
 

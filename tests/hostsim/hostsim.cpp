@@ -37,12 +37,14 @@ struct Fiber {
     unsigned wait_val = 0;
     int warp = 0, lane = 0;
     int blk = 0;                            // index of this thread's CTA within the running cluster
+    unsigned or_calls = 0;                  // __syncthreads_or calls so far (every thread of a CTA makes the same number)
 };
 
 struct Block {
     int alive = 0;
     int bar_count = 0;
     unsigned bar_gen = 0;
+    int or_acc[3] = {0, 0, 0};              // __syncthreads_or: call n accumulates in slot n % 3 (see syncthreads_or)
     std::vector<Warp> warps;
     std::vector<char> store;                // backing store of this CTA's dynamic shared memory
     char* smem = nullptr;                   // 128-byte aligned in every CTA: the CTAs of a cluster lay it out identically,
@@ -135,6 +137,17 @@ void* cluster_map(void* p, unsigned rank) {
 }
 
 void syncthreads() { block_wait(&g_blk.bar_gen, &g_blk.bar_count, g_blk.alive); }
+
+// __syncthreads_or: call n ORs into slot n % 3 and reads it after the barrier.  The slot of call n + 1 is cleared BEFORE
+// the barrier of call n: its last user (call n - 2) was read by everybody before they arrived at barrier n - 1, and
+// nobody writes it for call n + 1 before passing barrier n.
+int syncthreads_or(int pred) {
+    const unsigned n = g_self->or_calls++;
+    g_blk.or_acc[(n + 1) % 3] = 0;
+    if (pred) g_blk.or_acc[n % 3] = 1;
+    syncthreads();
+    return g_blk.or_acc[n % 3];
+}
 
 void warp_exchange(uint64_t mine, uint64_t* all32) {
     Warp& w = g_blk.warps[g_self->warp];
@@ -269,6 +282,7 @@ void run_grid(dim3 grid, dim3 block, unsigned cluster, size_t smem, const std::f
             Block& blk = g_blocks[q];
             blk.alive = (int)nthreads;
             blk.bar_count = 0;
+            blk.or_acc[0] = blk.or_acc[1] = blk.or_acc[2] = 0;
             blk.warps.assign(nwarps, Warp());
             blk.store.assign(smem + 16 + 128, (char)0xFF);   // NaN-poisoned: a read of unwritten shared memory shows up in the results
             blk.smem = (char*)(((uintptr_t)blk.store.data() + 127) & ~(uintptr_t)127);
@@ -280,6 +294,7 @@ void run_grid(dim3 grid, dim3 block, unsigned cluster, size_t smem, const std::f
                 Fiber& f = g_fibers[q * nthreads + t];
                 f.done = false;
                 f.wait_ptr = nullptr;
+                f.or_calls = 0;
                 f.blk = (int)q;
                 f.warp = (int)(t / 32);
                 f.lane = (int)(t % 32);

@@ -43,11 +43,24 @@ def test_brownian_uniforms_replica_matches_the_kernel():
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("field,batch", [((40, 72), None), ((24, 64), 3), ((70, 90), None)])
-def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, batch):
+@pytest.mark.parametrize("field,batch", [((40, 72), None), ((24, 64), 3), ((70, 90), None), ((48, 50), 7), ((24, 64), 21)])
+@pytest.mark.parametrize("variant", ["lean", "memo", "memo+pair"])
+def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, batch, variant):
     """Free run with in-kernel coins (the LEAN float32-gradient forward from the second step on), the oracle fed the
     replica's coins: every step bit-exact (actions, headings, cells, fields).  Slot counts beyond one CTA's 2048 and
-    batches check the (environment, CTA, thread, item) -> coin map of the replica."""
+    batches check the (environment, CTA, thread, item) -> coin map of the replica.  variant "memo": the memoised forward
+    (die_forward_memo.cuh: persistent CTAs, the float64 trigonometry of a heading looked up in a shared-memory table),
+    "memo+pair" with the food under the agent handed over per slot -- the same bits."""
+    S.set_tuning("fwd_memo", 0 if variant == "lean" else 1)
+    S.set_tuning("pair_mode", 2 if variant == "memo+pair" else 1)
+    try:
+        _benchmarked_forward_against_the_oracle(field, batch, variant)
+    finally:
+        S.set_tuning("fwd_memo", 0)
+        S.set_tuning("pair_mode", 1)
+
+
+def _benchmarked_forward_against_the_oracle(field, batch, variant):
     refs, env = make_pair(field, seed=7, batch=batch)
     B, m = env.B, env.M
     seed = 21
@@ -58,6 +71,7 @@ def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, bat
         ga.theta[b] = theta0
         ras.append(R.PhysarumAgent(max_agents=m, prev_grad=prev, **PHYS))
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
+    memo0 = S.lib().die_get_counter(b"forward_memo")
     iters = 12
     for it in range(iters):
         coin = P.physarum_coins(seed, it, B, m)
@@ -71,7 +85,10 @@ def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, bat
         for b in range(B):
             assert np.array_equal(ref_cells_linear(refs[b]), env.cells()[b])
             assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
-    assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + iters - 1, "the benchmarked instantiation must be the one compared"
+    if variant == "lean":
+        assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + iters - 1, "the benchmarked instantiation must be the one compared"
+    else:
+        assert S.lib().die_get_counter(b"forward_memo") == memo0 + iters - 1
 
 
 def test_call_counter_in_device_memory_draws_the_same_numbers():
