@@ -8,7 +8,6 @@
 #include "die_field_kernels.cuh"
 #include "die_env_fused.cuh"
 #include "die_conv_kernels.cuh"
-#include "die_forward_memo.cuh"
 
 using namespace die;
 
@@ -87,7 +86,7 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_fwd_memo = 0, g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
@@ -98,7 +97,6 @@ extern "C" int64_t die_get_counter(const char* key) {
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
     if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
     if (strcmp(key, "forward_food_here") == 0) return g_count_fwd_food_here;
-    if (strcmp(key, "forward_memo") == 0) return g_count_fwd_memo;
     return -1;
 }
 extern "C" const char* die_last_error(void) { return g_err; }
@@ -928,7 +926,6 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
 
 static int g_turn_quick = 1;       // 0: every slot runs die_turn_exact (diagnosis / A-B tests; same results)
 static int g_sense_quick = 1;      // 0: the sensed cell always comes from the float64 die_sincos (A-B tests; same results)
-static int g_fwd_memo = 0;         // the memoised forward (die_forward_memo.cuh) where it applies
 static int g_fwd_lean = 1;         // use the LEAN instantiation of the forward kernel when its preconditions hold
 static int g_fwd_min_blocks = 4;   // register cap of the forward kernel (3 / 4 / 5 resident CTAs per SM)
 
@@ -964,7 +961,6 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
-    else if (strcmp(key, "fwd_memo") == 0) g_fwd_memo = value ? 1 : 0;
     else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }
     else if (strcmp(key, "pair_min_cells_log2") == 0) { DIE_REQUIRE(value >= 2 && value <= 31); g_pair_min_cells = (int64_t)1 << value; }
     else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
@@ -1065,25 +1061,6 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
                                                : gradient_forward_kernel<true, false, false, 4, true, false, float>;
         else kern = p->discrete_turn ? gradient_forward_kernel<true, false, false, 4, false, false, float>
                                      : gradient_forward_kernel<false, false, false, 4, false, false, float>;
-    }
-    // the memoised forward (die_forward_memo.cuh): the steady-state float32-gradient configuration with the float64
-    // trigonometry of a heading looked up in a per-CTA table; needs cos(turn) away from 0 (sin / cos of the heading are
-    // recovered from the entries of theta -+ turn)
-    const bool memo = g_fwd_memo && lean && a.grad32 != nullptr && !field_f32 && g_fwd_lean != 5 &&
-                      fabs(cos(p->turn_radians)) >= 0.25 && env != nullptr;
-    if (memo) {
-        auto mk = fh ? physarum_forward_memo_kernel<true> : physarum_forward_memo_kernel<false>;
-        static bool attr_set[2] = {false, false};
-        if (!attr_set[fh ? 1 : 0]) {
-            DIE_CUDA(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMemoSmemBytes));
-            attr_set[fh ? 1 : 0] = true;
-        }
-        const int total_chunks = (int)grid;
-        const int mgrid = total_chunks < 4 * env->num_sms ? total_chunks : 4 * env->num_sms;
-        mk<<<mgrid, kAgentThreads, kMemoSmemBytes, st>>>(a, total_chunks, 1.0 / (2.0 * cos(p->turn_radians)));
-        DIE_CUDA(cudaGetLastError());
-        ++g_count_fwd_memo;
-        return DIE_OK;
     }
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());

@@ -211,30 +211,3 @@ def test_pair_mode_is_automatic_on_a_large_field():
             _lib.check(lib.die_set_tuning(b"pair_mode", 1))
             _lib.check(lib.die_set_tuning(b"pair_min_cells_log2", 23))
     assert all(np.array_equal(a, b) for a, b in zip(outs[0][:3], outs[1][:3])) and outs[0][3] == outs[1][3]
-
-
-@pytest.mark.parametrize("shape,batch,steps", [((256, 256), 3, 60), ((200, 136), None, 300), ((1024, 768), None, 25)])
-def test_memoised_forward_does_not_change_results(shape, batch, steps):
-    """fwd_memo: the forward kernel with the float64 trigonometry of a heading looked up in a per-CTA shared-memory table
-    (die_forward_memo.cuh; persistent CTAs, tables filled on the fly, 300 steps let the set of distinct headings grow)."""
-    import die_b200 as D
-    from die_b200 import _lib
-    lib = _lib.load()
-    outs = []
-    for memo in (0, 1):
-        _lib.check(lib.die_set_tuning(b"fwd_memo", memo))
-        try:
-            n0 = lib.die_get_counter(b"forward_memo")
-            refs, env = make_pair(shape, seed=17, batch=batch)
-            ag = D.PhysarumAgent(max_agents=env.max_agents, seed=5, **PHYS)
-            obs = env._get_current_obs
-            rewards = []
-            for it in range(steps):
-                obs, r, *_ = env.step(ag.forward(obs))
-                rewards.append(np.asarray(r).copy())
-            assert lib.die_get_counter(b"forward_memo") - n0 == ((steps - 1) if memo else 0)
-            outs.append((*env.get_state(), ag.get_state()[0], np.array(rewards)))
-        finally:
-            _lib.check(lib.die_set_tuning(b"fwd_memo", 0))
-    for a, b, what in zip(outs[0], outs[1], ("medium", "agents", "theta", "reward")):
-        assert np.array_equal(a, b), f"{what} differs"

@@ -44,19 +44,16 @@ def test_brownian_uniforms_replica_matches_the_kernel():
 
 
 @pytest.mark.parametrize("field,batch", [((40, 72), None), ((24, 64), 3), ((70, 90), None), ((48, 50), 7), ((24, 64), 21)])
-@pytest.mark.parametrize("variant", ["lean", "memo", "memo+pair"])
+@pytest.mark.parametrize("variant", ["lean", "lean+pair"])
 def test_benchmarked_forward_kernel_against_the_oracle(portable_math, field, batch, variant):
     """Free run with in-kernel coins (the LEAN float32-gradient forward from the second step on), the oracle fed the
     replica's coins: every step bit-exact (actions, headings, cells, fields).  Slot counts beyond one CTA's 2048 and
-    batches check the (environment, CTA, thread, item) -> coin map of the replica.  variant "memo": the memoised forward
-    (die_forward_memo.cuh: persistent CTAs, the float64 trigonometry of a heading looked up in a shared-memory table),
-    "memo+pair" with the food under the agent handed over per slot -- the same bits."""
-    S.set_tuning("fwd_memo", 0 if variant == "lean" else 1)
-    S.set_tuning("pair_mode", 2 if variant == "memo+pair" else 1)
+    batches check the (environment, CTA, thread, item) -> coin map of the replica.  variant "lean+pair": pair mode forced,
+    the food under the agent handed over per slot by the feed kernel -- the same bits."""
+    S.set_tuning("pair_mode", 2 if variant == "lean+pair" else 1)
     try:
         _benchmarked_forward_against_the_oracle(field, batch, variant)
     finally:
-        S.set_tuning("fwd_memo", 0)
         S.set_tuning("pair_mode", 1)
 
 
@@ -71,7 +68,7 @@ def _benchmarked_forward_against_the_oracle(field, batch, variant):
         ga.theta[b] = theta0
         ras.append(R.PhysarumAgent(max_agents=m, prev_grad=prev, **PHYS))
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
-    memo0 = S.lib().die_get_counter(b"forward_memo")
+    fh0 = S.lib().die_get_counter(b"forward_food_here")
     iters = 12
     for it in range(iters):
         coin = P.physarum_coins(seed, it, B, m)
@@ -85,10 +82,8 @@ def _benchmarked_forward_against_the_oracle(field, batch, variant):
         for b in range(B):
             assert np.array_equal(ref_cells_linear(refs[b]), env.cells()[b])
             assert_state_equal(refs[b], env.medium[b], env.agents[b], float_exact=True)
-    if variant == "lean":
-        assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + iters - 1, "the benchmarked instantiation must be the one compared"
-    else:
-        assert S.lib().die_get_counter(b"forward_memo") == memo0 + iters - 1
+    assert S.lib().die_get_counter(b"forward_lean_f32") == lean0 + iters - 1, "the benchmarked instantiation must be the one compared"
+    assert S.lib().die_get_counter(b"forward_food_here") == fh0 + ((iters - 1) if variant == "lean+pair" else 0)
 
 
 def test_call_counter_in_device_memory_draws_the_same_numbers():
