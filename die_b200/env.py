@@ -161,13 +161,20 @@ class Env:
                  init_state: Optional[Tuple[np.ndarray, np.ndarray]] = None,
                  init: str = 'host',
                  seed: Optional[int] = None,
-                 field_dtype: Union[torch.dtype, str] = torch.float64):
+                 field_dtype: Union[torch.dtype, str] = torch.float64,
+                 verify_caches: bool = False):
         """``init='host'`` (default) builds the initial state with numpy in the reference's draw order
         (``np.random.seed`` reproduces it); ``init='device'`` builds it on the GPU (die_b200/device_init.py:
         same arithmetic and slot order, torch's device generator seeded by ``seed``) -- the only practical
         choice for 4096^2 and beyond, where the reference's per-cell Python loop takes minutes."""
         if not torch.cuda.is_available():
             raise RuntimeError("die_b200.Env needs a CUDA device: there is no CPU fallback")
+        # verify_caches (a DEBUG mode, slow: it reads every tensor twice per step and synchronises): the caches below are
+        # validated by torch's version counters, which a write through tensor.data, a DLPack / CuPy / Numba view or a
+        # user kernel does not bump.  With this switch every cache carries a checksum of the bytes it was built from and
+        # a mismatch raises instead of silently stepping on stale cells / alive bits (see invalidate_caches).
+        self._verify_caches = bool(verify_caches)
+        self._checksums = None
         # float64 as in the reference (default), or the float32 FIELD mode: the medium (and the library's per-cell
         # scratch) in float32, agents / actions / headings still float64 -- half the field bytes, results within float32
         # rounding of the float64 ones per step (tests/test_gpu_f32_fields.py) instead of bit-exact
@@ -362,6 +369,7 @@ class Env:
         self._alive_version = None
         self._hint_state = None
         self._speculation = None
+        self._checksums = None
         with _lib.on_device(self.device):
             _lib.check(self._lib.die_env_discard_move(self._handle, torch.cuda.current_stream().cuda_stream))
 
@@ -475,6 +483,8 @@ class Env:
         as device tensors, everything enqueued on the current stream."""
         action = self._check_action(action)
         self._sync_dynamics()
+        if self._verify_caches:
+            self._verify()
         nxt = 1 - self._cur
         # a gradient agent may have evaluated this very action's move + claims already (see _forward_flags):
         # adopt them iff the action tensor and the agents are provably untouched since
@@ -504,9 +514,30 @@ class Env:
             self._refresh_sensed_medium()
         buf = self._medium_buf[self._cur]
         self._hint_state = (buf.data_ptr(), buf._version, self._agents._version, self._publish_grad)
+        if self._verify_caches:
+            self._checksums = (buf._version, self._agents._version, self._checksum(buf), self._checksum(self._agents))
         _hints.publish(self, buf)
 
+    @staticmethod
+    def _checksum(t: torch.Tensor) -> int:
+        return int(t.view(torch.int64 if t.element_size() == 8 else torch.int32).sum().item())
+
+    def _verify(self) -> None:
+        """verify_caches: the env's tensors still hold the bytes the caches were built from, unless torch saw the write."""
+        cs = self._checksums
+        if cs is None:
+            return
+        buf = self._medium_buf[self._cur]
+        if buf._version == cs[0] and self._checksum(buf) != cs[2]:
+            raise RuntimeError("verify_caches: the env's medium was written without torch noticing (tensor.data, a DLPack / "
+                               "CuPy / Numba view, a user kernel): call env.invalidate_caches() after such a write")
+        if self._agents._version == cs[1] and self._checksum(self._agents) != cs[3]:
+            raise RuntimeError("verify_caches: the env's agents tensor was written without torch noticing (tensor.data, a "
+                               "DLPack / CuPy / Numba view, a user kernel): call env.invalidate_caches() after such a write")
+
     def _hints_for(self, agents, medium, want_gradient: bool):
+        if self._verify_caches:
+            self._verify()
         if want_gradient and not self._publish_grad:
             # a gradient agent is acting on this env: publish np.gradient(chem1) from the next step on
             _lib.check(self._lib.die_env_publish_gradient(self._handle, 1))

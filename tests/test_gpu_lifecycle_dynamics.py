@@ -119,3 +119,39 @@ def test_food_frames_that_cannot_fit_are_refused_by_name():
     seq = Huge((4096, 4096), dt=0.01, t_bounds=(0, 10))
     with pytest.raises(MemoryError, match="tabulating"):
         D.Env((4096, 4096), D.Dynamics(op_food_flow=seq.get_flow_operator(scale=0.5, decay=0.5)), init="device")
+
+
+def test_verify_caches_catches_a_write_torch_does_not_see():
+    """Env(verify_caches=True), a debug mode: every cache carries a checksum of the bytes it was built from; a write
+    through tensor.data (no version bump) is reported instead of stepping on a stale alive mask / cell cache, and after
+    invalidate_caches() the run continues exactly like one that was told about the write."""
+    import torch
+    import die_b200 as D
+    outs = []
+    for verify in (True, False):
+        env = D.Env((32, 48), D.Dynamics(init_agent_ratio=0.2), init='device', seed=1, verify_caches=verify)
+        ag = D.PhysarumAgent(max_agents=env.max_agents, seed=3, scale=0.02, turn_angle=30, sense_offset=0.05)
+        obs = env._get_current_obs
+        for _ in range(3):
+            obs, *_ = env.step(ag.forward(obs))
+        v0 = env.agents._version
+        env.agents.data[2, :40] = 0.0                    # kills 40 agents behind torch's back
+        env.agents.data[0, :40] = 0.9
+        assert env.agents._version == v0
+        if verify:
+            with pytest.raises(RuntimeError, match="verify_caches"):
+                ag.forward(obs)
+            with pytest.raises(RuntimeError, match="verify_caches"):
+                env.step(ag._action)
+        env.invalidate_caches()
+        for _ in range(3):
+            obs, *_ = env.step(ag.forward(obs))
+        outs.append((*env.get_state(), ag.get_state()[0]))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    env.medium.data[2].mul_(0.5)                         # the same for the medium (verify=False here: nothing is raised)
+    env2 = D.Env((32, 48), D.Dynamics(init_agent_ratio=0.2), init='device', seed=1, verify_caches=True)
+    obs = env2._get_current_obs
+    obs, *_ = env2.step(ag.forward(obs))
+    env2.medium.data[2].mul_(0.5)
+    with pytest.raises(RuntimeError, match="medium was written"):
+        ag.forward(obs)
