@@ -65,18 +65,24 @@ def main():
     print(f'{steps} env iterations in {dt:.2f} s = {steps * args.field ** 2 / dt / 1e6:.1f} M cell-updates/s')
 
     agent.set_population(None)
+    # the learned distribution's centre and the best single candidate seen (evotorch's "pop_best", what the reference's
+    # example saves), each on a fresh single env as the reference's example does at its end
+    single_dyn = dynamics
+    results = {}
+    for name, vec in (('center', searcher.center), ('pop_best', searcher.best[1])):
+        agent.model.set_parameters_vector(vec)
+        single = Env(field_size, single_dyn, init='device', seed=args.seed + 1)
+        obs, total = single._get_current_obs, 0.
+        for _ in range(args.epoch_iters):
+            obs, reward, _, _, stats = single.step(agent.forward(obs))
+            total += reward
+        results[name] = total
+        print(f'Reward of {name} over {args.epoch_iters} iterations on a fresh env: {np.round(total, 3)}  {stats}')
     agent.model.set_parameters_vector(searcher.best[1])
     if args.out:
         os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
         agent.save(args.out)                 # the reference's TorchAgent file format: loads in the reference, too
         print(f'saved the best agent to {args.out}')
-    # the best solution on a fresh single env, as the reference's example does at its end
-    single = Env(field_size, dynamics, init='device', seed=args.seed + 1)
-    obs, total = single._get_current_obs, 0.
-    for _ in range(args.epoch_iters):
-        obs, reward, _, _, stats = single.step(agent.forward(obs))
-        total += reward
-    print(f'Final reward of the best solution over {args.epoch_iters} iterations: {np.round(total, 3)}  {stats}')
 
 
 if __name__ == '__main__':
