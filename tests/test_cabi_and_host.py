@@ -210,3 +210,14 @@ def test_import_fails_loudly_without_the_cuda_library(tmp_path):
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "no CPU / PyTorch fallback" in out.stdout
+
+
+def test_examples_and_tools_compile(tmp_path):
+    """The example scripts and tools are not imported by any CPU test (they need a GPU to run): at least they parse."""
+    import glob
+    import py_compile
+    files = glob.glob(os.path.join(ROOT, "examples", "*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py")) \
+        + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) >= 10
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=str(tmp_path / (os.path.basename(f) + 'c')))
