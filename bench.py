@@ -859,7 +859,7 @@ def main():
                     help="caller threads of the host-buffer (e2e) leg, each stepping its own share of the envs (1 = one thread)")
     ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
-                    help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, field_impl=1")
+                    help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, pair_mode=0, step_impl=1")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (32 / 64 / 128; 0 = leave the default)")
     args = ap.parse_args()
