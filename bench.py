@@ -58,6 +58,11 @@ SURVEY_BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "agent_feed": 40.0
 # positions (W{x,y}, 16 B) are committed by the feed kernel.  Same 240 B per cell-update in total.
 BYTES_FUSED = {"physarum_forward": 72.0 + 40.0, "move_claim": 0.0, "agent_feed": 40.0 + 16.0, "field_step": 48.0,
                "finalize_stats": 0.0}
+# committed move (`--fuse commit`, the run-loop contract of DIE_FWD_COMMIT_MOVE): the forward kernel is the move --
+# R{x,y,theta} W{theta,dx,dy,dep,x,y} + gathers{gradient pair, food} = 88 B / slot; no move_claim launch; the feed
+# kernel is the plain one.  72 + 16 + 40 + 48 = 176 B per cell-update: the 40 B that move_claim re-reads are gone.
+BYTES_COMMIT = {"physarum_forward": 72.0 + 16.0, "move_claim": 0.0, "agent_feed": 40.0, "field_step": 48.0,
+                "finalize_stats": 0.0}
 ALIVE_EXTRA = {"field_step": 24.0, "env_step_fused": 24.0}
 # float32 FIELD mode (Env(field_dtype=torch.float32): medium + consumed_field in float32, agents / actions float64), bytes
 # counted per dtype (SURVEY 8d with s_f = 4, s_a = 8: 189 B per cell-update):
@@ -198,7 +203,7 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
     M = env.max_agents
     agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
     agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
-    agent.fuse_move = bool(ARGS.fuse)
+    agent.fuse_move = {'': False, 'spec': True, 'commit': 'commit'}[ARGS.fuse or '']
     return env, agent, alive
 
 
@@ -262,6 +267,7 @@ def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     return dict(env=env, agent=agent, obs=obs, steps_done=args.warmup + args.steps + n_prof,
                 ms_per_step=ms_per_step, kernel_ms=kernel_ms, clocks=clocks,
                 alive_local=alive_local, M=M, C=C, fused=bool(env.last_step_fused), grad_kind=int(grad_kind),
+                committed=bool(getattr(agent, 'last_committed', False)),
                 f32=(field_dtype is not None and field_dtype == torch.float32))
 
 
@@ -491,7 +497,7 @@ def roofline_of(meas, B_local, wl_name):
     M, C, alive_local = meas["M"], meas["C"], meas["alive_local"]
     slots_local, cells_local = M * B_local, C * B_local
     kernels = {}
-    BY = dict(BYTES_FUSED if meas.get("fused") else BYTES)
+    BY = dict(BYTES_COMMIT if meas.get("committed") else (BYTES_FUSED if meas.get("fused") else BYTES))
     SV, AX = SURVEY_BYTES, ALIVE_EXTRA
     if meas.get("f32"):
         BY, SV, AX = dict(BYTES_F32), SURVEY_BYTES_F32, ALIVE_EXTRA_F32
@@ -738,7 +744,7 @@ def run_die_b200(args):
             "alive_agent_steps_per_s": alive_local * n_gpus / (ms_per_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "also": also,
             "gpu_launches": args.steps * launches, "launches_per_step": launches,
-            "fused_move": meas["fused"], "tuning": ARGS.tune, "clocks": meas["clocks"],
+            "fused_move": ("commit" if meas.get("committed") else meas["fused"]), "tuning": ARGS.tune, "clocks": meas["clocks"],
             "host": {"cpus": os.cpu_count(), "rank0_bound_to_cpus": bound_cpus},
             "setup_s": round(setup_s, 1),
         }
@@ -857,7 +863,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=4,
                     help="caller threads of the host-buffer (e2e) leg, each stepping its own share of the envs (1 = one thread)")
-    ap.add_argument("--fuse", action="store_true", help="A-B: agent.forward evaluates the move speculatively (opt-in path)")
+    ap.add_argument("--fuse", nargs="?", const="spec", default="", choices=["", "spec", "commit"],
+                    help="agent.forward also evaluates the move of its action: 'spec' speculatively (the feed kernel commits "
+                         "the positions once Env.step adopts it), 'commit' under the run-loop contract (DIE_FWD_COMMIT_MOVE: "
+                         "forward stores the positions, Env.step must receive that very action)")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
                     help="die_set_tuning switch (result-neutral), e.g. fwd_min_blocks=5, turn_quick=0, pair_mode=0, step_impl=1")
     ap.add_argument("--no-cpu", action="store_true")

@@ -73,9 +73,15 @@ class GradientAgent(_DeviceAgent):
         # opt-in: evaluate the move + claim of the action in the same launch, for Env.step to adopt
         # (bit-identical; measured SLOWER on B200 at 4096^2 -- 1.084 vs 1.033 ms per step -- because the
         # forward kernel is instruction bound and move_claim already runs at 80 % of the HBM peak)
+        # 'commit': the run-loop contract -- `action = agent.forward(obs); obs, ... = env.step(action)` with nothing in
+        # between (examples/minimal_run.py:21-25 of the reference).  The forward launch then also MOVES the agents (the
+        # env's positions are advanced when forward returns), Env.step runs the field pass and the feed kernel only:
+        # one launch and 56 B per slot less per iteration, results bit-identical.  Anything else than stepping exactly
+        # the returned tensor raises.  Active only once the env's caches are valid (from the second iteration on).
         self.fuse_move = False
         self.last_hints = (False, False)
         self.last_speculated = False
+        self.last_committed = False
 
     # -- state ------------------------------------------------------------------------------
     def _needs_prev(self) -> bool:
@@ -280,8 +286,9 @@ class GradientAgent(_DeviceAgent):
         torch.autograd.graph.increment_version(action)
         self.last_hints = (bool(flags & _lib.FWD_USE_GRADIENT), bool(flags & _lib.FWD_USE_CELLS))
         self.last_speculated = bool(flags & _lib.FWD_SPECULATE_MOVE)
+        self.last_committed = bool(flags & _lib.FWD_COMMIT_MOVE)
         if self.last_speculated:
-            env._note_speculation(action)
+            env._note_speculation(action, self.last_committed)
         self._step += 1
         return action
 

@@ -139,6 +139,9 @@ struct GradientArgs {
     // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
     int32_t* winner;            // [B][H*W] claim table
     int32_t* cells_out;         // [B][M] post-move cell of every slot (the env's OTHER cell buffer)
+    double* commit_xy;          // null: the move stays speculative (the feed kernel commits the positions once the step
+                                // adopts it).  Else = `agents`, writable: the moved x, y are stored in place by THIS
+                                // launch (DIE_FWD_COMMIT_MOVE: the caller promises that very action to the next step)
     const uint32_t* alive_bits; // [B][Mw] bit i&31 of word i>>5 = (alive[i] > 0)
     int64_t Mw;
     int boundary;
@@ -222,6 +225,7 @@ gradient_forward_kernel(const GradientArgs a) {
     const double* fh_p = FH ? a.food_here + ch.b * M + first : nullptr;
     int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
     int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
+    double* cx_p = (MOVE && a.commit_xy != nullptr) ? a.commit_xy + ch.b * 4 * M + first : nullptr;
     // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
     const uint32_t* bits_p = MOVE ? a.alive_bits + ch.b * a.Mw + (first >> 5) : nullptr;
 
@@ -415,6 +419,10 @@ gradient_forward_kernel(const GradientArgs a) {
             const double my = apply_boundary(y + ady, a.boundary);
             const int cell = nearest_cell(mx, ax) * W + nearest_cell(my, ay);
             co_p[i] = cell;
+            if (cx_p != nullptr) {                 // committed move: this thread alone reads and writes its slots' x, y
+                cx_p[i] = mx;
+                cx_p[M + i] = my;
+            }
             if ((alive_word >> (threadIdx.x & 31)) & 1u) atomicMax(win + cell, (int32_t)(first + i));
         }
     }

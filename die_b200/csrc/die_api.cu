@@ -42,7 +42,8 @@ struct die_env {
     uint32_t* alive_bits;  // [B][Mw]   (alive > 0) per slot, one bit each (die_env_refresh_alive)
     int64_t Mw;
     int alive_valid;
-    int pending_move;      // a speculative move (cells2[1-cur] + claims) waits for a step with DIE_STEP_ADOPT_MOVE
+    int pending_move;      // 1: a speculative move (cells2[1-cur] + claims) waits for a step with DIE_STEP_ADOPT_MOVE;
+                           // 2: a COMMITTED one (DIE_FWD_COMMIT_MOVE: the positions are already stored)
     // op_food_flow = WaveSequence flow operator (die_env_set_food_flow); borrowed device tables, host copy of ts
     const double* flow_rwave;
     const double* flow_col;    // [T][W]
@@ -86,7 +87,8 @@ static inline void prof_mark(die_env* e, int k, cudaStream_t st) {
 extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
-static int64_t g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0;
+static int64_t g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0,
+               g_count_step_committed = 0, g_count_fwd_lean_move = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
@@ -97,6 +99,8 @@ extern "C" int64_t die_get_counter(const char* key) {
     if (strcmp(key, "forward_lean_f32") == 0) return g_count_fwd_lean_f32;
     if (strcmp(key, "forward_general") == 0) return g_count_fwd_general;
     if (strcmp(key, "forward_food_here") == 0) return g_count_fwd_food_here;
+    if (strcmp(key, "forward_lean_move") == 0) return g_count_fwd_lean_move;
+    if (strcmp(key, "step_committed") == 0) return g_count_step_committed;
     return -1;
 }
 extern "C" const char* die_last_error(void) { return g_err; }
@@ -590,7 +594,10 @@ static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitm
 // refers to the WHOLE batch; the range is resolved here (all per-env arrays are contiguous per environment).
 static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, double* medium_out,
                           double* agents, const double* action, double* reward_dev, int64_t* alive_dev,
-                          bool fused, const uint32_t* alive_bits, bool profile, cudaStream_t st) {
+                          bool fused, const uint32_t* alive_bits, bool profile, cudaStream_t st,
+                          bool committed = false) {
+    // fused: cells + claims of this action are in place (the forward kernel's MOVE instantiation); committed: so are the
+    // positions, and the feed kernel is the plain one
     const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
     medium_in = field_off(e, medium_in, (size_t)b0 * 3 * C);
     medium_out = field_off(e, medium_out, (size_t)b0 * 3 * C);
@@ -609,7 +616,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
         alive_bits = nullptr;
         e->alive_valid = 0;
     }
-    const bool pair = pair_mode_for(e, fused);
+    const bool pair = pair_mode_for(e, fused && !committed);
     if (pair) {
         if (e->cell_pairs == nullptr) DIE_CUDA(cudaMalloc(&e->cell_pairs, sizeof(double2) * C * e->B));
         if (e->food_here == nullptr) DIE_CUDA(cudaMalloc(&e->food_here, sizeof(double) * M * e->B));
@@ -640,7 +647,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
 
     const unsigned fgrid = (unsigned)((int64_t)e->nblk * nb);
     const bool feed_bits = alive_bits != nullptr && (fused || g_feed_bits);
-    auto feed = fused ? agent_feed_kernel<false, true, true>
+    auto feed = (fused && !committed) ? agent_feed_kernel<false, true, true>
                       : (feed_bits ? agent_feed_kernel<false, false, true> : agent_feed_kernel<false, false, false>);
     if (e->dyn.agents_die) feed = agent_feed_kernel<false, false, false, true>;
     if (e->field_f32) {
@@ -687,16 +694,22 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
     if ((fused || bits) && !e->alive_valid)
         return fail(DIE_E_INVALID, "die_env_step_flags: call die_env_refresh_alive first%s%s");
     const uint32_t* alive_bits = (fused || bits) ? e->alive_bits : nullptr;
+    bool committed = false;
     if (fused) {
         // the forward kernel already resolved cells and claims for exactly this action
         if (!e->pending_move) return fail(DIE_E_INVALID, "die_env_step_flags: no speculative move is pending%s%s");
+        committed = e->pending_move == 2;
         e->cur ^= 1;
         e->pending_move = 0;
+        if (committed) ++g_count_step_committed;
+    } else if (e->pending_move == 2) {
+        return fail(DIE_E_INVALID, "die_env_step_flags: a committed move is pending (DIE_FWD_COMMIT_MOVE): the next step "
+                                   "must adopt it (DIE_STEP_ADOPT_MOVE, the very action of that forward)%s%s");
     } else if (e->pending_move) {       // abandoned speculation: its claims must not leak into this step
         if (int rc = die_env_discard_move(e, stream)) return rc;
     }
     if (int rc = env_step_range(e, 0, e->B, medium_in, medium_out, agents, action, reward_dev, alive_dev,
-                                fused, alive_bits, true, st))
+                                fused, alive_bits, true, st, committed))
         return rc;
     if (e->flow_rwave != nullptr || e->flow_frames != nullptr) ++e->flow_k;
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
@@ -759,6 +772,8 @@ static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_ou
     if (action_dev == nullptr && e->action_stage == nullptr)
         DIE_CUDA(cudaMalloc(&e->action_stage, sizeof(double) * 3 * M * e->B));
     const double* action = action_dev != nullptr ? action_dev : e->action_stage;
+    if (e->pending_move == 2)
+        return fail(DIE_E_INVALID, "the host-buffer step cannot follow a committed move (DIE_FWD_COMMIT_MOVE)%s%s");
     if (e->pending_move) {
         if (int rc = die_env_discard_move(e, stream)) return rc;
     }
@@ -977,7 +992,7 @@ static die_turn_plan_t plan_for(const die_gradient_params_t* p) {
     return plan;
 }
 
-static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradient_params_t* p,
+static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradient_params_t* p,
                                  int32_t H, int32_t W, int64_t M, int32_t B,
                                  const double* agents, const double* medium,
                                  double* theta, double* prev_grad, double* action,
@@ -990,6 +1005,9 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
     DIE_REQUIRE(agents != nullptr && medium != nullptr && theta != nullptr && action != nullptr);
+    // move_mode: 0 the action only; 1 + the move, speculatively (DIE_FWD_SPECULATE_MOVE); 2 + the move, committed
+    // (DIE_FWD_COMMIT_MOVE: x, y stored into `agents`)
+    const bool speculate = move_mode != 0;
     // prev_grad may only be omitted when it cannot influence any output
     DIE_REQUIRE(prev_grad != nullptr || (p->inertia == 0.0 && p->noise_scale == 0.0));
     GradientArgs a;
@@ -1022,6 +1040,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
         a.alive_bits = env->alive_bits;
         a.Mw = env->Mw;
         a.boundary = env->dyn.boundary;
+        if (move_mode == 2) a.commit_xy = const_cast<double*>(agents);
     }
     void (*kern)(const GradientArgs) = nullptr;
 #define DIE_PICK_FWD(MINB)                                                                               \
@@ -1034,15 +1053,24 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     else { DIE_PICK_FWD(4); }
 #undef DIE_PICK_FWD
     // the steady-state Physarum configuration has its own instantiation (see LEAN in die_agent_kernels.cuh)
-    const bool lean = g_fwd_lean && !speculate && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
+    const bool lean = g_fwd_lean && (!speculate || move_mode == 2) && p->discrete_turn && a.plan.enabled && p->normalized_grad &&
                       prev_grad == nullptr && coin == nullptr && noise == nullptr && sense_cells == nullptr &&
                       (a.grad != nullptr || a.grad32 != nullptr) && a.cells != nullptr && g_fwd_min_blocks == 4;
     // the food under every slot, handed over by the last step's feed kernel (pair mode): valid exactly when the cell
     // cache is (the caller proved the observation is the env's own state of that step)
     const bool fh = lean && !field_f32 && env != nullptr && env->food_here_valid && env->food_here != nullptr &&
                     cells_hint == env->cells2[env->cur] && g_fwd_lean != 5;
-    if (fh) {
-        a.food_here = env->food_here;
+    if (fh) a.food_here = env->food_here;
+    if (lean && speculate) {
+        // the committed move of the run loop: the steady-state instantiation + Env._agent_move in one launch (3 CTAs per
+        // SM: the move needs x, y, the axes and the alive word alive to the end of the item)
+        if (fh) kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, true, 3, true, true, double, true>
+                                             : gradient_forward_kernel<true, false, true, 3, true, false, double, true>;
+        else kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, true, 3, true, true>
+                                          : gradient_forward_kernel<true, false, true, 3, true, false>;
+        if (fh) ++g_count_fwd_food_here;
+        ++g_count_fwd_lean_move;
+    } else if (fh) {
         kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, false, 4, true, true, double, true>
                                      : gradient_forward_kernel<true, false, false, 4, true, false, double, true>;
         ++g_count_fwd_food_here;
@@ -1065,7 +1093,7 @@ static int gradient_forward_impl(die_env_t* env, bool speculate, const die_gradi
     kern<<<grid, kAgentThreads, 0, st>>>(a);
     DIE_CUDA(cudaGetLastError());
     ++(lean ? (a.grad32 != nullptr ? g_count_fwd_lean_f32 : g_count_fwd_lean) : g_count_fwd_general);
-    if (speculate) env->pending_move = 1;
+    if (speculate) env->pending_move = move_mode;
     return DIE_OK;
 }
 
@@ -1077,7 +1105,7 @@ extern "C" int die_gradient_forward(const die_gradient_params_t* p,
                                     int32_t* sense_cells,
                                     const double* grad_hint, const int32_t* cells_hint,
                                     uint64_t seed, uint64_t step, void* stream) {
-    return gradient_forward_impl(nullptr, false, p, H, W, M, B, agents, medium, theta, prev_grad, action,
+    return gradient_forward_impl(nullptr, 0, p, H, W, M, B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step, stream);
 }
 
@@ -1087,7 +1115,7 @@ extern "C" int die_gradient_forward_f32(const die_gradient_params_t* p,
                                         double* theta, double* prev_grad, double* action,
                                         const uint8_t* coin, const double* noise,
                                         int32_t* sense_cells, uint64_t seed, uint64_t step, void* stream) {
-    return gradient_forward_impl(nullptr, false, p, H, W, M, B, agents, (const double*)medium, theta, prev_grad, action,
+    return gradient_forward_impl(nullptr, 0, p, H, W, M, B, agents, (const double*)medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, nullptr, nullptr, seed, step, stream, 0, nullptr, nullptr, true);
 }
 
@@ -1097,7 +1125,13 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
                                         const uint8_t* coin, const double* noise, int32_t* sense_cells,
                                         int32_t flags, uint64_t seed, uint64_t step, void* stream) {
     DIE_REQUIRE(e != nullptr);
-    const bool speculate = (flags & DIE_FWD_SPECULATE_MOVE) != 0;
+    const bool speculate = (flags & (DIE_FWD_SPECULATE_MOVE | DIE_FWD_COMMIT_MOVE)) != 0;
+    const int move_mode = (flags & DIE_FWD_COMMIT_MOVE) ? 2 : (speculate ? 1 : 0);
+    if (e->pending_move == 2)
+        return fail(DIE_E_INVALID, "die_env_forward_gradient: a committed move is pending (DIE_FWD_COMMIT_MOVE): the env's "
+                                   "positions are already those of the next step, which must adopt it first%s%s");
+    if (move_mode == 2 && (e->dyn.agents_die || e->field_f32))
+        return fail(DIE_E_INVALID, "the committed move is not available with agents_die or float32 fields%s%s");
     if (speculate) {
         if (!e->alive_valid) return fail(DIE_E_INVALID, "die_env_forward_gradient: call die_env_refresh_alive first%s%s");
         if (e->pending_move) {          // a previous speculation was never adopted: drop its claims
@@ -1111,7 +1145,7 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
     const int32_t* cells_hint = (flags & DIE_FWD_USE_CELLS) ? e->cells2[e->cur] : nullptr;
     // DIE_FWD_STEP_ON_DEVICE: `step` is the device address of a uint64 call counter (CUDA-graph replays)
     const uint64_t* step_dev = (flags & DIE_FWD_STEP_ON_DEVICE) ? (const uint64_t*)(uintptr_t)step : nullptr;
-    return gradient_forward_impl(e, speculate, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
+    return gradient_forward_impl(e, move_mode, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step_dev ? 0 : step, stream, 0,
                                  grad32_hint, step_dev, e->field_f32 != 0);
 }

@@ -489,7 +489,12 @@ class Env:
         # a gradient agent may have evaluated this very action's move + claims already (see _forward_flags):
         # adopt them iff the action tensor and the agents are provably untouched since
         spec, self._speculation = self._speculation, None
-        fused = (spec is not None and spec == (action.data_ptr(), action._version, self._agents._version))
+        fused = (spec is not None and spec[:3] == (action.data_ptr(), action._version, self._agents._version))
+        if spec is not None and spec[3] and not fused:
+            self._speculation = spec       # (still pending: the caller may yet pass the right action)
+            raise RuntimeError("Env.step: the agent committed the move of its action (fuse_move='commit'), so this step "
+                               "must receive exactly the tensor that forward() returned, unmodified -- the positions in "
+                               "env.agents are already those of that action")
         if self.dynamics.agents_die:
             fused = False                  # (the library refuses the combination; a pending speculation is discarded)
         flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | (0 if self.dynamics.agents_die else _lib.STEP_ALIVE_BITS)
@@ -556,11 +561,14 @@ class Env:
                 grad_ptr = self._lib.die_env_gradient_kind(self._handle) or None      # 1 float64, 2 float32 cache
         return grad_ptr, cells_ptr
 
-    def _forward_flags(self, agents, medium, want_gradient: bool, speculate: bool) -> int:
+    def _forward_flags(self, agents, medium, want_gradient: bool, speculate) -> int:
         """Flags for ``die_env_forward_gradient`` (include/die_b200.h) given the observation an agent
         received: which of this env's caches are provably valid for it, and whether the agent may
         evaluate the move of its action speculatively (``obs[0]`` must be this env's own agents tensor;
         the alive bitmask is rebuilt here whenever the agents tensor was edited)."""
+        if self._speculation is not None and self._speculation[3]:
+            raise RuntimeError("Agent.forward: a committed move (fuse_move='commit') is waiting for its Env.step; the "
+                               "positions in env.agents are already those of the next step")
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
         if speculate and not self.dynamics.agents_die and self._field_dtype == torch.float64 \
@@ -569,6 +577,10 @@ class Env:
             with _lib.on_device(self.device):
                 self._refresh_alive(torch.cuda.current_stream().cuda_stream)
             flags |= _lib.FWD_SPECULATE_MOVE
+            # 'commit': the run-loop contract (include/die_b200.h, DIE_FWD_COMMIT_MOVE) -- only on the env's own, valid
+            # caches, i.e. in the steady state of `action = agent.forward(obs); obs, ... = env.step(action)`
+            if speculate == 'commit' and grad_ptr and cells_ptr and not self._verify_caches:
+                flags |= _lib.FWD_COMMIT_MOVE
         return flags
 
     def _refresh_alive(self, stream) -> None:
@@ -578,8 +590,8 @@ class Env:
             _lib.check(self._lib.die_env_refresh_alive(self._handle, self._agents.data_ptr(), stream))
             self._alive_version = self._agents._version
 
-    def _note_speculation(self, action: torch.Tensor) -> None:
-        self._speculation = (action.data_ptr(), action._version, self._agents._version)
+    def _note_speculation(self, action: torch.Tensor, committed: bool = False) -> None:
+        self._speculation = (action.data_ptr(), action._version, self._agents._version, committed)
 
     def step(self, action: ActType):
         """core/env.py:101-131 -> (obs, reward, terminated, truncated, info)."""
@@ -635,6 +647,8 @@ class Env:
         hb['flip'] ^= 1
         med_t = hb['medium'][hb['flip']]
         nxt = 1 - self._cur
+        if self._speculation is not None and self._speculation[3]:
+            raise RuntimeError("Env.step (host buffers): a committed move (fuse_move='commit') is waiting for its device step")
         self._speculation = None          # die_env_step_host runs the plain step (and discards a pending move)
         self.last_step_fused = False
         with torch.cuda.device(self.device):

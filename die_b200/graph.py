@@ -31,7 +31,8 @@ class GraphedLoop:
             raise NotImplementedError("GraphedLoop: host-side random draws (rng='numpy') cannot be captured; use rng='philox'")
         if not hasattr(agent, '_step_dev'):
             raise NotImplementedError(f"GraphedLoop: {type(agent).__name__} has no device-resident call counter")
-        if getattr(agent, 'fuse_move', False):
+        if getattr(agent, 'fuse_move', False) not in (False, 'commit'):
+            # ('commit' is fine: this loop IS the contract it needs, and the decision is taken once, at capture time)
             raise NotImplementedError("GraphedLoop: the speculative move depends on host-side version counters")
         self.env, self.agent = env, agent
         dev = env.device

@@ -270,6 +270,15 @@ int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient_params_t* 
  *                           the feed kernel commits the positions -- same results bit for bit, one launch
  *                           and ~32 B per slot less.  Any other continuation (die_env_step, another
  *                           forward) first calls die_env_discard_move, which empties the claim table.
+ *   DIE_FWD_COMMIT_MOVE     (with DIE_FWD_SPECULATE_MOVE) the run-loop contract: the caller PROMISES that the next call on
+ *                           this env is die_env_step_flags(DIE_STEP_ADOPT_MOVE) with exactly this action
+ *                           (`for ...: action = agent.forward(obs); obs, ... = env.step(action)`,
+ *                           examples/minimal_run.py:21-25).  The forward launch then also stores the moved
+ *                           positions into `agents_dev` (which it therefore WRITES: x, y of every slot), the
+ *                           adopting step runs the field pass and the plain feed kernel only: no move+claim launch
+ *                           and none of its 56 B per slot.  Same results bit for bit.  A committed move cannot be
+ *                           withdrawn: until the adopting step any other step / forward on the env fails with
+ *                           DIE_E_INVALID; die_env_discard_move (reset paths) only forgets it.
  * Needs die_env_refresh_alive() after every change of the `alive` channel (the speculative claim and
  * the fused feed read alive-ness from a bitmask). */
 #define DIE_FWD_USE_GRADIENT    1
@@ -286,6 +295,7 @@ int die_gradient_forward_f32(const die_gradient_params_t* p, int32_t H, int32_t 
  *                           that captured this call can be replayed while something else (a captured increment) advances
  *                           the counter, so every replay draws fresh in-kernel random numbers (die_b200/graph.py) */
 #define DIE_FWD_STEP_ON_DEVICE  8
+#define DIE_FWD_COMMIT_MOVE     16
 int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
                              const double* agents_dev, const double* medium_dev,
                              double* theta_dev, double* prev_grad_dev, double* action_dev,
@@ -301,7 +311,7 @@ int die_env_step_flags(die_env_t* env, double* medium_in_dev, double* medium_out
                        double* agents_dev, const double* action_dev,
                        double* reward_dev, int64_t* alive_dev, int32_t flags, void* stream);
 int die_env_discard_move(die_env_t* env, void* stream);
-int die_env_pending_move(const die_env_t* env);          /* 1 while a speculative move waits for its step */
+int die_env_pending_move(const die_env_t* env);          /* 1 while a speculative move waits for its step, 2: a committed one */
 int die_env_refresh_alive(die_env_t* env, const double* agents_dev, void* stream);
 
 /* PhysarumAgent._choose_turn has two implementations (die_b200/csrc/die_turn.h): the reference's own

@@ -227,6 +227,8 @@ class SimGradientAgent:
             if self.fuse_move:
                 check(self.lib.die_env_refresh_alive(env.handle, ptr(env.agents), None))
                 flags |= L.FWD_SPECULATE_MOVE
+                if self.fuse_move == 'commit':
+                    flags |= L.FWD_COMMIT_MOVE
             check(self.lib.die_env_forward_gradient(env.handle, C.byref(self.p), ptr(agents), ptr(medium), ptr(self.theta),
                                                     ptr(self.prev_grad), ptr(self.action), ptr(coin_a), ptr(noise_a),
                                                     ptr(sc), flags, self.seed, self.step_no, None))

@@ -986,6 +986,78 @@ def test_abandoned_speculation_leaves_no_trace():
         assert np.array_equal(a, b)
 
 
+def test_physarum_free_run_committed_move(portable_math):
+    """DIE_FWD_COMMIT_MOVE (the run-loop contract): the forward launch also stores the moved positions, the adopting step
+    runs the field pass + the plain feed kernel only.  Against the oracle, injected coins (the general MOVE kernel)."""
+    n0 = S.lib().die_get_counter(b"step_committed")
+    _physarum_free_run((40, 72), 20, dict(scale=0.02, turn_angle=30, sense_offset=0.06), seed=8, fuse='commit')
+    assert S.lib().die_get_counter(b"step_committed") == n0 + 20
+
+
+@pytest.mark.parametrize("shape,batch,kw,pair", [
+    ((40, 72), None, {}, 0), ((33, 47), 3, dict(diffuse_sigma=1.0), 0), ((64, 64), 2, {}, 2),
+    ((24, 50), None, dict(boundary=D.BoundaryCondition.limit), 0), ((6, 90), 2, dict(food_infinite=True), 2)])
+@pytest.mark.parametrize("grad_f32", [1, 0])
+def test_committed_move_equals_the_plain_loop(tuning, shape, batch, kw, pair, grad_f32):
+    """In-kernel Philox coins, the env's hints valid: the steady-state (LEAN) instantiation with the move folded in
+    (float64 / float32 gradient cache, with and without the food handed over by pair mode) -- the whole loop equals
+    forward + move_claim + field + feed bit for bit, every step."""
+    tuning("grad_f32", grad_f32)
+    tuning("pair_mode", pair)
+    outs = []
+    so = S.lib()
+    lm0, sc0 = so.die_get_counter(b"forward_lean_move"), so.die_get_counter(b"step_committed")
+    for fuse in (False, 'commit'):
+        refs, env = make_pair(shape, seed=5, dynamics_kw=kw, batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 5 + b)[0]
+        ga.fuse_move = fuse
+        trace = []
+        for it in range(10):
+            act = ga.forward(env).copy()
+            if fuse:
+                assert so.die_env_pending_move(env.handle) == 2
+            r, alive = env.step(act, flags=L.STEP_ALIVE_BITS | (L.STEP_ADOPT_MOVE if fuse else 0))
+            trace.append((act, r.copy(), alive.copy(), env.agents.copy(), env.cells().copy()))
+        outs.append((env.medium.copy(), ga.theta.copy(), trace))
+    assert so.die_get_counter(b"step_committed") == sc0 + 10
+    assert so.die_get_counter(b"forward_lean_move") == lm0 + 9       # the first forward has no hints yet: general kernel
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for it, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
+        for x, y, what in zip(a, b, ("action", "reward", "num_agents", "agents", "cells")):
+            assert np.array_equal(x, y), f"step {it}: {what} differs"
+
+
+def test_committed_move_must_be_adopted():
+    """A committed move cannot be withdrawn: a plain step, a host-buffer step or another forward on the env fail by name
+    until the adopting step has run; die_env_discard_move (the reset paths) forgets it."""
+    so = S.lib()
+    (ref,), env = make_pair((24, 32), seed=2)
+    ga = S.SimGradientAgent(env.M, seed=3, **PHYS)
+    ga.theta[0] = lattice_theta(env.M, 30, 8)[0]
+    env.step(ga.forward(env).copy())
+    ga.fuse_move = 'commit'
+    before = env.agents.copy()
+    act = ga.forward(env).copy()
+    assert so.die_env_pending_move(env.handle) == 2
+    assert not np.array_equal(before[0, :2], env.agents[0, :2])           # the positions are already those of the next step
+    assert np.array_equal(before[0, 2:], env.agents[0, 2:])
+    with pytest.raises(RuntimeError, match="committed move is pending"):
+        env.step(act)                                                       # plain step
+    with pytest.raises(RuntimeError, match="committed move is pending"):
+        ga.forward(env)                                                     # another forward
+    with pytest.raises(RuntimeError, match="committed move"):
+        env.step_host(act)
+    env.step(act, flags=L.STEP_ALIVE_BITS | L.STEP_ADOPT_MOVE)
+    assert so.die_env_pending_move(env.handle) == 0
+    ga.forward(env)
+    assert so.die_env_pending_move(env.handle) == 2
+    S.check(so.die_env_discard_move(env.handle, None))
+    assert so.die_env_pending_move(env.handle) == 0
+
+
 def test_forward_through_host_buffers_is_chunked_and_identical(tuning):
     """die_gradient_forward_host: observation uploaded / action downloaded chunk by chunk on two streams; the in-kernel
     random draws are keyed on the GLOBAL environment index, so chunking does not change them."""
