@@ -186,7 +186,7 @@ def lattice_theta_device(B, M, turn_angle, seed, device):
     return k.to(torch.float64) * tr
 
 
-def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_base, field_dtype=None):
+def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_base, field_dtype=None, fuse=None):
     """Seeded synthetic state: up to 16 distinct host-built environments, tiled on the device."""
     n_distinct = 1 if not batched else min(B_local, 16)
     med_h, ag_h = build_host_state(field, n_distinct, seed=seed_base + 1000 * rank)
@@ -203,14 +203,14 @@ def make_env_and_agent(D, torch, field, B_local, batched, device, rank, seed_bas
     M = env.max_agents
     agent = D.PhysarumAgent(max_agents=M, rng="philox", seed=1234 + rank, **PHYS)
     agent._theta = lattice_theta_device(B_local, M, PHYS["turn_angle"], 77 + rank, device)
-    agent.fuse_move = {'': False, 'spec': True, 'commit': 'commit'}[ARGS.fuse or '']
+    agent.fuse_move = {'': False, 'spec': True, 'commit': 'commit'}[(ARGS.fuse if fuse is None else fuse) or '']
     return env, agent, alive
 
 
-def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks, field_dtype=None):
+def measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks, field_dtype=None, fuse=None):
     """Warm-up, the timed region (CUDA events, barrier + synchronize on both sides, max over
     ranks), then the per-kernel breakdown.  Returns a dict of raw measurements."""
-    env, agent, alive_local = make_env_and_agent(D, torch, field, B_local, batched, device, rank, 0, field_dtype)
+    env, agent, alive_local = make_env_and_agent(D, torch, field, B_local, batched, device, rank, 0, field_dtype, fuse)
     M, C = env.max_agents, field[0] * field[1]
 
     def sync_all():
@@ -352,6 +352,23 @@ def small_env_leg(D, torch, device, agent_name, iters=300, warmup=20, cpu_iters=
                                         "captured graph, rewards accumulated on the device"}
         except Exception as exc:                     # never lose the whole bench line to the optional leg
             out["cuda_graph"] = {"error": repr(exc)}
+        if agent_name == "physarum" and "error" not in out["cuda_graph"]:
+            # the captured loop IS the run-loop contract of the committed move: 4 launches per iteration instead of 5
+            try:
+                agent.fuse_move = "commit"
+                loop = graph(env, agent)
+                loop.run(warmup)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loop.run(iters)
+                torch.cuda.synchronize()
+                dg = time.perf_counter() - t0
+                out["cuda_graph_committed_move"] = {"ms_per_iter": dg / iters * 1e3, "value": field[0] * field[1] * iters / dg,
+                                                    "unit": UNIT, "committed": bool(agent.last_committed),
+                                                    "api": "the same with agent.fuse_move = 'commit'"}
+            except Exception as exc:
+                out["cuda_graph_committed_move"] = {"error": repr(exc)}
+            agent.fuse_move = False
     if cpu_iters > 0:
         from oracle import die_ref as R
         np.random.seed(1)
@@ -706,6 +723,22 @@ def run_die_b200(args):
             del m3
             torch.cuda.empty_cache()
 
+    # ---- N = 1 only: the same workload under the run-loop contract (agent.fuse_move = 'commit', DIE_FWD_COMMIT_MOVE): the
+    #      forward launch also moves the agents, Env.step is the field pass + the feed kernel -- bit-identical, opt-in,
+    #      NOT the headline (the headline keeps forward and step independent calls, as any caller of the reference may) ---
+    if n_gpus == 1 and workload == "batch256" and not ARGS.fuse and not args.no_commit:
+        m4 = measure(D, torch, dist, args, field, B_local, batched, device, rank, world, want_clocks=False, fuse="commit")
+        r4, _ = roofline_of(m4, B_local, wl_name + "_committed_move")
+        also = dict(also or {})
+        also[wl_name + "_committed_move"] = {
+            "value": C * B_local / (m4["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": m4["ms_per_step"],
+            "committed": m4["committed"], "launches_per_step": 4,
+            "api": "agent.fuse_move = 'commit': `action = agent.forward(obs); obs, ... = env.step_async(action)` with nothing "
+                   "in between (the loop of examples/minimal_run.py:21-25); any other continuation raises",
+            "roofline": r4}
+        del m4
+        torch.cuda.empty_cache()
+
     # ---- N > 1: the single 32768x32768 field split into row slabs over the ranks (BASELINE.json configs[4]) ----------
     if n_gpus > 1 and workload == "batch256" and not args.no_slab:
         try:
@@ -853,6 +886,7 @@ def main():
     ap.add_argument("--steady", default="300,3000", help="single field: also report ms/step in the 40 steps before these "
                                                           "total step counts ('' = off)")
     ap.add_argument("--no-f32", action="store_true", help="skip the float32-field legs")
+    ap.add_argument("--no-commit", action="store_true", help="skip the committed-move leg (agent.fuse_move = 'commit')")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the configs[4] leg (one field over all ranks)")
     ap.add_argument("--slab-field", type=int, default=32768, help="side of the slab-decomposed field of the N > 1 run")
     ap.add_argument("--slab-steps", type=int, default=25)

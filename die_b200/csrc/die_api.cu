@@ -1063,7 +1063,8 @@ static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradie
     if (fh) a.food_here = env->food_here;
     if (lean && speculate) {
         // the committed move of the run loop: the steady-state instantiation + Env._agent_move in one launch (3 CTAs per
-        // SM: the move needs x, y, the axes and the alive word alive to the end of the item)
+        // SM, 73-76 registers: the move needs x, y, the axes and the alive word alive to the end of the item; capped at
+        // 64 registers it spills 32 bytes and is 6 % slower, profiles/r02zj_committed_move_ab.txt)
         if (fh) kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, true, 3, true, true, double, true>
                                              : gradient_forward_kernel<true, false, true, 3, true, false, double, true>;
         else kern = (a.grad32 != nullptr) ? gradient_forward_kernel<true, false, true, 3, true, true>

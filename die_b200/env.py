@@ -571,16 +571,17 @@ class Env:
                                "positions in env.agents are already those of the next step")
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
+        # 'commit': the run-loop contract (include/die_b200.h, DIE_FWD_COMMIT_MOVE) -- only on the env's own, valid caches,
+        # i.e. in the steady state of `action = agent.forward(obs); obs, ... = env.step(action)`; elsewhere the plain path
+        commit = speculate == 'commit'
+        if commit and not (grad_ptr and cells_ptr and not self._verify_caches):
+            return flags
         if speculate and not self.dynamics.agents_die and self._field_dtype == torch.float64 \
                 and agents.data_ptr() == self._agents.data_ptr() \
                 and agents.numel() == self._agents.numel():
             with _lib.on_device(self.device):
                 self._refresh_alive(torch.cuda.current_stream().cuda_stream)
-            flags |= _lib.FWD_SPECULATE_MOVE
-            # 'commit': the run-loop contract (include/die_b200.h, DIE_FWD_COMMIT_MOVE) -- only on the env's own, valid
-            # caches, i.e. in the steady state of `action = agent.forward(obs); obs, ... = env.step(action)`
-            if speculate == 'commit' and grad_ptr and cells_ptr and not self._verify_caches:
-                flags |= _lib.FWD_COMMIT_MOVE
+            flags |= _lib.FWD_SPECULATE_MOVE | (_lib.FWD_COMMIT_MOVE if commit else 0)
         return flags
 
     def _refresh_alive(self, stream) -> None:
