@@ -9,7 +9,8 @@ from . import _lib
 from .base_types import DataChannels, channel
 from .env import Env, Dynamics, BoundaryCondition, linear_action_cost, zero_cost
 from .data_init import WaveSequence, FieldSequence, TabulatedSequence, PerlinNoiseSequence
-from .agent import Agent, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent, ConvolutionModel, NeuralAutomataAgent
+from .agent import (Agent, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent, ConvolutionModel, NeuralAutomataAgent,
+                    JonesAgent)
 from .graph import GraphedLoop
 from .evolve import PopulationEvaluator, PGPE
 
@@ -17,5 +18,5 @@ _lib.load()     # fail loudly at import time if the CUDA library is missing
 
 __all__ = ['Env', 'Dynamics', 'BoundaryCondition', 'linear_action_cost', 'zero_cost',
            'Agent', 'ConstAgent', 'BrownianAgent', 'GradientAgent', 'PhysarumAgent', 'ConvolutionModel', 'NeuralAutomataAgent',
-           'GraphedLoop', 'PopulationEvaluator', 'PGPE', 'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
+           'JonesAgent', 'GraphedLoop', 'PopulationEvaluator', 'PGPE', 'DataChannels', 'channel', 'WaveSequence', 'FieldSequence', 'TabulatedSequence', 'PerlinNoiseSequence']
 __version__ = '0.1.0'

@@ -46,6 +46,11 @@ class DieGradientParams(C.Structure):
     ]
 
 
+class DieJonesParams(C.Structure):
+    _fields_ = [("scale", C.c_double), ("deposit", C.c_double), ("sense_offset", C.c_double),
+                ("sense_radians", C.c_double), ("turn_radians", C.c_double)]
+
+
 DIE_MAX_RANKS = 8
 
 
@@ -94,6 +99,8 @@ SIGNATURES = {
                                                      _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_device_l2_fetch_granularity": (C.c_int, [C.c_int32, _P]),
     "die_const_forward": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double, _P]),
+    "die_jones_forward": (C.c_int, [C.POINTER(DieJonesParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, C.c_int32,
+                                    _P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P]),
     "die_env_set_field_dtype": (C.c_int, [_P, C.c_int32]),
     "die_env_field_dtype": (C.c_int, [_P]),
     "die_gradient_forward_f32": (C.c_int, [C.POINTER(DieGradientParams), C.c_int32, C.c_int32, C.c_int64, C.c_int32,

@@ -98,6 +98,85 @@ const_forward_kernel(double* __restrict__ action, int64_t M, int nchunk,
 }
 
 // ---------------------------------------------------------------------------------------------
+// JonesAgent.forward -- the classic three-sensor Physarum particle (Jones 2010) on the reference's Env protocol.
+// NOT a reference class ("optional ... not parity-checkable -- the reference has none"): the
+// specification is oracle/die_ref.py:JonesAgent, whose every operation this kernel repeats in the same order --
+//   sensors FL, F, FR at heading + SA, heading, heading - SA, distance `sense_offset`, each reading chem1 at the
+//   nearest cell of its position, CLAMPED like every sense lookup of the reference (core/utils.py:39-54);
+//   F > FL and F > FR: straight on;  F < FL and F < FR: +-RA by a coin;  FL < FR: -RA;  FR < FL: +RA;  else straight on;
+//   heading' = renormalize_radians(heading + turn) (core/utils.py:177-179); action = (scale cos, scale sin) of heading',
+//   deposit * food under the agent -- unmasked, all M slots, like PhysarumAgent (core/agent/gradient.py:113-124, Q8).
+// Comparisons of float64 values gathered from identical cells: bit-exact given die_math.h's sin / cos on both sides.
+// ---------------------------------------------------------------------------------------------
+constexpr int kJonesItems = 4;
+
+struct JonesArgs {
+    Axis ax, ay;
+    int W;
+    int64_t M, C;
+    int nchunk;
+    const double* agents;       // [B][4][M]
+    const double* medium;       // [B][3][H][W] (FT elements)
+    double* theta;              // [B][M]
+    double* action;             // [B][3][M]
+    const uint8_t* coin;        // may be null -> Philox
+    double scale, deposit, sense_offset, sense_radians, turn_radians;
+    uint64_t seed, step;
+    const uint64_t* step_dev;   // may be null; else the call counter is read from device memory (CUDA-graph replays)
+};
+
+template <typename FT>
+__global__ void __launch_bounds__(kAgentThreads)
+jones_forward_kernel(const JonesArgs a) {
+    const SlotChunk ch = slot_chunk<kJonesItems>(a.nchunk);
+    const int64_t M = a.M;
+    const int W = a.W;
+    const double* ag = a.agents + ch.b * 4 * M;
+    const FT* food = (const FT*)a.medium + (ch.b * 3 + 1) * a.C;
+    const FT* chem = (const FT*)a.medium + (ch.b * 3 + 2) * a.C;
+    double* th_p = a.theta + ch.b * M;
+    double* ab = a.action + ch.b * 3 * M;
+    const uint8_t* coin_p = (a.coin != nullptr) ? a.coin + ch.b * M : nullptr;
+    const uint64_t step = (a.step_dev != nullptr) ? *a.step_dev : a.step;
+#pragma unroll 1
+    for (int k = 0; k < kJonesItems; ++k) {
+        const int64_t i = ch.base + k * kAgentThreads + threadIdx.x;
+        if (i >= M) break;
+        const double x = ag[i], y = ag[M + i], th = th_p[i];
+        const double food_here = (double)food[nearest_cell(x, a.ax) * W + nearest_cell(y, a.ay)];
+        double v[3];                                        // FL, F, FR
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const double ang = (s == 0) ? th + a.sense_radians : (s == 1 ? th : th - a.sense_radians);
+            double sn, cs;
+            die_sincos(ang, &sn, &cs);
+            const int sx = nearest_cell(x + a.sense_offset * cs, a.ax);
+            const int sy = nearest_cell(y + a.sense_offset * sn, a.ay);
+            v[s] = (double)chem[sx * W + sy];
+        }
+        double turn = 0.0;
+        if (v[1] > v[0] && v[1] > v[2]) {
+            turn = 0.0;
+        } else if (v[1] < v[0] && v[1] < v[2]) {
+            const int c = (coin_p != nullptr) ? (coin_p[i] ? 1 : 0)
+                                              : (int)(philox_draw(a.seed, step, (uint64_t)(ch.b * M + i), 5u).x & 1u);
+            turn = c ? a.turn_radians : -a.turn_radians;
+        } else if (v[0] < v[2]) {
+            turn = -a.turn_radians;
+        } else if (v[2] < v[0]) {
+            turn = a.turn_radians;
+        }
+        const double heading = renormalize_radians(th + turn);
+        double s2, c2;
+        die_sincos(heading, &s2, &c2);
+        th_p[i] = heading;
+        ab[i] = c2 * a.scale;
+        ab[M + i] = s2 * a.scale;
+        ab[2 * M + i] = a.deposit * food_here;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GradientAgent.forward / PhysarumAgent.forward  (core/agent/gradient.py:96-124)
 //
 // The reference materialises the normalised gradient of the whole chem1 field

@@ -939,6 +939,35 @@ extern "C" int die_const_forward(double* action, int64_t M, int32_t B,
     return DIE_OK;
 }
 
+// JonesAgent.forward (the classic three-sensor particle; specification: oracle/die_ref.py:JonesAgent)
+extern "C" int die_jones_forward(const die_jones_params_t* p, int32_t H, int32_t W, int64_t M, int32_t B,
+                                 const double* agents, const void* medium, int32_t medium_f32,
+                                 double* theta, double* action, const uint8_t* coin,
+                                 uint64_t seed, uint64_t step, int32_t step_on_device, void* stream) {
+    DIE_REQUIRE(p != nullptr);
+    DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
+    DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL && M <= 0x7fffffffLL);
+    DIE_REQUIRE(agents != nullptr && medium != nullptr && theta != nullptr && action != nullptr);
+    DIE_REQUIRE(p->sense_radians >= 0.0 && p->sense_radians <= DIE_PI && p->turn_radians >= 0.0 && p->turn_radians <= DIE_PI);
+    JonesArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ax = make_axis(H);
+    a.ay = make_axis(W);
+    a.W = W; a.M = M; a.C = (int64_t)H * W;
+    a.nchunk = chunks_for(M, kJonesItems);
+    a.agents = agents; a.medium = (const double*)medium; a.theta = theta; a.action = action; a.coin = coin;
+    a.scale = p->scale; a.deposit = p->deposit; a.sense_offset = p->sense_offset;
+    a.sense_radians = p->sense_radians; a.turn_radians = p->turn_radians;
+    a.seed = seed;
+    if (step_on_device) a.step_dev = (const uint64_t*)(uintptr_t)step;
+    else a.step = step;
+    const unsigned grid = (unsigned)((int64_t)a.nchunk * B);
+    if (medium_f32) jones_forward_kernel<float><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    else jones_forward_kernel<double><<<grid, kAgentThreads, 0, (cudaStream_t)stream>>>(a);
+    DIE_CUDA(cudaGetLastError());
+    return DIE_OK;
+}
+
 static int g_turn_quick = 1;       // 0: every slot runs die_turn_exact (diagnosis / A-B tests; same results)
 static int g_sense_quick = 1;      // 0: the sensed cell always comes from the float64 die_sincos (A-B tests; same results)
 static int g_fwd_lean = 1;         // use the LEAN instantiation of the forward kernel when its preconditions hold

@@ -221,6 +221,24 @@ int die_brownian_forward_dev(const double* agents_dev, double* action_dev, int64
 int die_const_forward(double* action_dev, int64_t M, int32_t B,
                       double dx, double dy, double deposit, void* stream);
 
+/* JonesAgent.forward: the classic three-sensor Physarum particle (Jones 2010, "Characteristics of pattern formation and
+ * evolution in approximations of Physarum transport networks") on the reference's Env protocol -- SURVEY.md 8(f) rank 4,
+ * "optional ... not parity-checkable": the reference has no such class, so the specification is oracle/die_ref.py:JonesAgent
+ * (sensors FL / F / FR at heading +sense, 0, -sense, `sense_offset` away, reading chem1 at the nearest cell, clamped as
+ * core/utils.py:39-54 does; F largest: straight on; F smallest: +-turn by a coin; else towards the larger side;
+ * heading' = renormalize_radians(heading + turn), core/utils.py:177-179; action = (scale cos, scale sin, deposit * food
+ * under the agent), every slot, as core/agent/gradient.py:113-124).
+ * medium_f32: the medium holds float32 elements (the env's float32 field mode).  coin_dev: [B][M] in {0,1}, or NULL for
+ * in-kernel Philox draws keyed on (seed, step, env, slot).  step_on_device: `step` is the DEVICE ADDRESS of the uint64 call
+ * counter (CUDA-graph replays, as DIE_FWD_STEP_ON_DEVICE). */
+typedef struct die_jones_params {
+    double scale, deposit, sense_offset, sense_radians, turn_radians;
+} die_jones_params_t;
+int die_jones_forward(const die_jones_params_t* p, int32_t H, int32_t W, int64_t M, int32_t B,
+                      const double* agents_dev, const void* medium_dev, int32_t medium_f32,
+                      double* theta_dev, double* action_dev, const uint8_t* coin_dev,
+                      uint64_t seed, uint64_t step, int32_t step_on_device, void* stream);
+
 /* GradientAgent.forward / PhysarumAgent.forward, core/agent/gradient.py:96-124 (+ :55-91,
  * :168-219).  theta_dev[B][M] (in/out) = _direction_rads.  prev_grad_dev[B][2][M] (in/out)
  * = _prev_grad; may be NULL when inertia == 0 and noise_scale == 0 (its value then cannot

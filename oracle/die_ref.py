@@ -665,6 +665,74 @@ class PhysarumAgent(GradientAgent):
         return self._deposit * sensed_food * mask
 
 
+class JonesAgent:
+    """The classic three-sensor Physarum particle (Jones 2010, "Characteristics of pattern formation and evolution in
+    approximations of Physarum transport networks"), on the reference's Env / Agent protocol.
+
+    NOT a restatement: the reference has no such class ("optional ... not parity-checkable").  This
+    class IS the specification that die_b200.JonesAgent / jones_forward_kernel are checked against, written with the
+    reference's own building blocks so that it composes with its Env exactly as PhysarumAgent does:
+      * sense offsets as core/agent/gradient.py:73-76 forms them (polar2xy(r, theta), core/utils.py:154-164), one per sensor:
+        FL at heading + SA, F at heading, FR at heading - SA;
+      * the field is read at the nearest cell of pos + offset, clamped not wrapped (core/utils.py:39-54, SURVEY Q3 / Q4);
+      * F > FL and F > FR: keep the heading; F < FL and F < FR: turn +-RA by a coin (np.random.randint(0, 2, M), drawn
+        for every slot like core/agent/gradient.py:181); FL < FR: turn by -RA (towards FR); FR < FL: by +RA; else keep it;
+      * heading' = renormalize_radians(heading + turn) (core/utils.py:177-179);
+      * action = (scale cos heading', scale sin heading', deposit * food under the agent), all M slots, not alive-masked
+        (core/agent/gradient.py:113-124)."""
+
+    def __init__(self, max_agents: int = 10 ** 6, scale: float = 0.005, deposit: float = 4.0,
+                 sense_offset: float = 0.03, turn_angle: float = 45, sense_angle: float = 45,
+                 theta0: Optional[np.ndarray] = None):
+        self._size = max_agents
+        self._scale, self._deposit, self._sense_offset_scale = scale, deposit, sense_offset
+        self._turn_radians = np.radians(turn_angle)
+        self._sense_radians = np.radians(sense_angle)
+        if theta0 is None:
+            prev = np.random.default_rng().normal(loc=0., scale=0.4, size=(2, max_agents))
+            theta0 = discretize(get_radians(prev), self._turn_radians)
+        self._direction_rads = np.array(theta0, dtype=np.float64)
+
+    @staticmethod
+    def _sincos(theta):
+        if _MATH == 'portable':
+            from oracle import portable_math
+            return portable_math.sincos(theta)
+        return np.sin(theta), np.cos(theta)
+
+    def forward(self, obs, coin: Optional[np.ndarray] = None):
+        agents, medium = obs
+        h, w = medium.shape[1:]
+        chem = medium[CH_CHEM]
+        th = self._direction_rads
+        sensed = []
+        for ang in (th + self._sense_radians, th, th - self._sense_radians):       # FL, F, FR
+            s, c = self._sincos(ang)
+            sx = nearest_index(agents[AG_X] + self._sense_offset_scale * c, h)
+            sy = nearest_index(agents[AG_Y] + self._sense_offset_scale * s, w)
+            sensed.append(chem[sx, sy])
+        fl, f, fr = sensed
+        if coin is None:
+            coin = np.random.randint(0, 2, th.shape)
+        random_turn = np.where(np.asarray(coin) != 0, self._turn_radians, -self._turn_radians)
+        turn = np.zeros_like(th)
+        ahead = (f > fl) & (f > fr)
+        behind = (f < fl) & (f < fr) & ~ahead
+        right = ~ahead & ~behind & (fl < fr)
+        left = ~ahead & ~behind & ~right & (fr < fl)
+        turn[behind] = random_turn[behind]
+        turn[right] = -self._turn_radians
+        turn[left] = self._turn_radians
+        self._direction_rads = renormalize_radians(th + turn)
+        s, c = self._sincos(self._direction_rads)
+        ix, iy = nearest_index(agents[AG_X], h), nearest_index(agents[AG_Y], w)
+        action = np.zeros((3, agents.shape[-1]))
+        action[AC_DX] = c * self._scale
+        action[AC_DY] = s * self._scale
+        action[AC_DEP] = self._deposit * medium[CH_FOOD][ix, iy]
+        return action
+
+
 # --------------------------------------------------------------------------------------
 # Rendering (core/render.py) -- the frames before any matplotlib colour map
 # --------------------------------------------------------------------------------------

@@ -242,6 +242,28 @@ class SimGradientAgent:
         return self.action
 
 
+class SimJonesAgent:
+    """die_b200.JonesAgent's call on numpy arrays (die_jones_forward)."""
+
+    def __init__(self, M, B=1, seed=0, scale=0.005, deposit=4.0, sense_offset=0.03, turn_angle=45, sense_angle=45):
+        self.lib = lib()
+        p = self.p = L.DieJonesParams()
+        p.scale, p.deposit, p.sense_offset = scale, deposit, sense_offset
+        p.sense_radians, p.turn_radians = float(np.radians(sense_angle)), float(np.radians(turn_angle))
+        self.M, self.B = M, B
+        self.theta = fenced((B, M), fill=0.0)
+        self.action = fenced((B, 3, M), fill=np.nan)
+        self.seed, self.step_no = seed, 0
+
+    def forward(self, env, coin=None):
+        coin_a = None if coin is None else fenced_copy(np.asarray(coin).astype(np.uint8).reshape(self.B, self.M))
+        f32 = int(env.medium.dtype == np.float32)
+        check(self.lib.die_jones_forward(C.byref(self.p), env.h, env.w, self.M, self.B, ptr(env.agents), ptr(env.medium), f32,
+                                         ptr(self.theta), ptr(self.action), ptr(coin_a), self.seed, self.step_no, 0, None))
+        self.step_no += 1
+        return self.action
+
+
 def brownian_forward(agents, move_scale=0.01, deposit_scale=0.5, u=None, seed=0, step=0):
     agents = np.ascontiguousarray(agents, dtype=np.float64)
     B = 1 if agents.ndim == 2 else agents.shape[0]

@@ -1058,6 +1058,74 @@ def test_committed_move_must_be_adopted():
     assert so.die_env_pending_move(env.handle) == 0
 
 
+# ------------------------------------------------------------------------------------------
+# JonesAgent: the classic three-sensor particle (optional); specification = oracle/die_ref.py:JonesAgent
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("field,kw,dyn", [
+    ((40, 72), dict(scale=0.02, sense_offset=0.06), {}),
+    ((33, 47), dict(scale=0.015, sense_offset=0.09, turn_angle=22.5, sense_angle=45), {}),
+    ((24, 50), dict(scale=0.03, sense_offset=0.05, turn_angle=60, sense_angle=30, deposit=2.0),
+     dict(boundary=D.BoundaryCondition.limit, diffuse_sigma=0.8))])
+def test_jones_agent_free_run(portable_math, field, kw, dyn):
+    """Free run against the oracle in its portable math backend: heading, action, and the whole env state bit-exact
+    every step; all five branches of the sensor rule occur."""
+    ref_dyn = dict(dyn)
+    if 'boundary' in ref_dyn:
+        ref_dyn['boundary'] = 'limit'
+    (ref,), env = make_pair(field, seed=6, ratio=0.25, dynamics_kw=dyn, ref_dynamics_kw=ref_dyn)
+    m = ref.agents.shape[-1]
+    tr = np.radians(kw.get('turn_angle', 45))
+    theta0 = (lattice_theta(m, 30, 6)[0] // tr) * tr
+    ra = R.JonesAgent(max_agents=m, theta0=theta0, **kw)
+    ga = S.SimJonesAgent(m, **kw)
+    ga.theta[0] = theta0
+    rng = np.random.default_rng(3)
+    robs = ref._get_current_obs
+    turns = set()
+    for it in range(25):
+        coin = rng.integers(0, 2, m)
+        before = ra._direction_rads.copy()
+        ract = ra.forward(robs, coin=coin.copy())
+        gact = ga.forward(env, coin=coin)[0]
+        assert np.array_equal(ga.theta[0], ra._direction_rads), f"heading differs at step {it}"
+        assert np.array_equal(gact, ract), f"action differs at step {it}"
+        turns |= set(np.unique(np.round(R.renormalize_radians(ra._direction_rads - before) / tr)).astype(int))
+        robs, rr, _, _, rinfo = ref.step(ract)
+        r, alive = env.step(gact)
+        assert rinfo['num_agents'] == alive[0] and _rel(rr, r[0]) < 1e-11
+        assert_state_equal(ref, env.medium[0], env.agents[0], float_exact=True)
+    assert {-1, 0, 1} <= turns
+
+
+def test_jones_agent_philox_batch_and_float32_medium():
+    """In-kernel coins: reproducible, different per environment and per call; a float32 medium is read as such."""
+    refs, env = make_pair((32, 48), seed=9, ratio=0.3, batch=2)
+    kw = dict(scale=0.02, sense_offset=0.07)
+    outs = []
+    for rep in range(2):
+        ga = S.SimJonesAgent(env.M, B=2, seed=11, **kw)
+        acts = [ga.forward(env).copy(), ga.forward(env).copy()]
+        outs.append((acts, ga.theta.copy()))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], outs[1][0])) and np.array_equal(outs[0][1], outs[1][1])
+    # a float32 medium (the env's float32 field mode) is read as float32: same result as a float64 medium holding the
+    # float32-rounded values
+    med = np.stack([r.medium for r in refs]).copy()
+    med[:, 2] = np.random.default_rng(1).random(med[:, 2].shape)          # some chem to sense
+    med32 = med.astype(np.float32)
+    ag = np.stack([r.agents for r in refs])
+    e32 = S.SimEnv((32, 48), med32, ag, D.Dynamics(), batch=2, field_dtype=np.float32)
+    e64 = S.SimEnv((32, 48), med32.astype(np.float64), ag, D.Dynamics(), batch=2)
+    g32, g64 = S.SimJonesAgent(env.M, B=2, seed=11, **kw), S.SimJonesAgent(env.M, B=2, seed=11, **kw)
+    assert np.array_equal(g32.forward(e32), g64.forward(e64)) and np.array_equal(g32.theta, g64.theta)
+    assert len(np.unique(np.round(g32.theta, 6))) >= 3
+    # two identical environments draw different coins (where the front sensor reads the smallest value)
+    med[1], ag[1] = med[0], ag[0]
+    twin = S.SimEnv((32, 48), med, ag, D.Dynamics(), batch=2)
+    gt = S.SimJonesAgent(env.M, B=2, seed=11, **kw)
+    a = gt.forward(twin).copy()
+    assert not np.array_equal(a[0], a[1]) and np.array_equal(a[:, 2], a[::-1, 2])
+
+
 def test_forward_through_host_buffers_is_chunked_and_identical(tuning):
     """die_gradient_forward_host: observation uploaded / action downloaded chunk by chunk on two streams; the in-kernel
     random draws are keyed on the GLOBAL environment index, so chunking does not change them."""
