@@ -133,3 +133,30 @@ def test_mass_conservation_of_blur_and_decay():
     before = env.medium[2].sum()
     env._medium_diffuse_decay()
     assert np.isclose(env.medium[2].sum(), 0.9 * before, rtol=1e-13)
+
+
+def test_jones_three_sensor_rule():
+    """oracle JonesAgent (the specification of die_b200.JonesAgent; the reference has no three-sensor mode): one particle at
+    the centre of a 41 x 41 field heading along +x; sensors FL / F / FR at +45 / 0 / -45 degrees, 0.25 away, i.e. cells
+    (27, 27), (30, 20), (27, 13).  The five branches of the rule, by inspection."""
+    n = 41
+    g = R.grid_coords(n)
+    ag = _agents(1, [(g[20], g[20], 1, 0.5)])
+    cells = {'FL': (27, 27), 'F': (30, 20), 'FR': (27, 13)}
+    def act(values, coin=0):
+        med = np.zeros((3, n, n))
+        med[1] = 0.25
+        for k, v in values.items():
+            med[2][cells[k]] = v
+        a = R.JonesAgent(max_agents=1, scale=0.01, deposit=4.0, sense_offset=0.25, turn_angle=45, sense_angle=45,
+                         theta0=np.zeros(1))
+        out = a.forward((ag, med), coin=np.array([coin]))
+        return np.degrees(a._direction_rads[0]), out[:, 0]
+    assert act(dict(F=3, FL=1, FR=2))[0] == 0                       # front largest: straight on
+    assert np.isclose(act(dict(F=1, FL=2, FR=3), coin=1)[0], 45)    # front smallest: by the coin
+    assert np.isclose(act(dict(F=1, FL=2, FR=3), coin=0)[0], -45)
+    assert np.isclose(act(dict(F=2, FL=1, FR=3))[0], -45)           # towards the larger side
+    assert np.isclose(act(dict(F=2, FL=3, FR=1))[0], 45)
+    assert act(dict(F=1, FL=1, FR=1))[0] == 0                       # no information: straight on
+    th, a = act(dict(F=2, FL=3, FR=1))
+    assert np.allclose(a, [0.01 * np.cos(np.pi / 4), 0.01 * np.sin(np.pi / 4), 4.0 * 0.25])
