@@ -404,7 +404,7 @@ def e2e_leg(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     Agent.forward; numpy action in, numpy observation + reward out of Env.step; every byte crosses PCIe inside the timed
     region.  On the FULL per-GPU batch (bounded only by pinned host memory; `envs_per_gpu` says what ran).
     The two calls are synchronous, so one caller thread keeps only one PCIe direction busy at a time (forward uploads
-    7 doubles per slot and downloads 3, step the reverse): `value` is therefore measured with `workers` caller threads,
+    4 doubles per slot -- the channels the policy reads -- and downloads 3, step downloads 9 or 10): `value` is therefore measured with `workers` caller threads,
     each stepping its own share of the environments through the same two calls; the single-thread figure is reported
     beside it."""
     from die_b200.sharding import max_over_ranks
@@ -415,8 +415,9 @@ def e2e_leg(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     k_e2e = max(3, min(args.steps, args.e2e_steps))
     W = max(1, min(args.e2e_workers, B_e2e))
     out = {"unit": UNIT, "steps": k_e2e, "envs_per_gpu": B_e2e,
-           "api": "numpy obs/action across Agent.forward (die_gradient_forward_host) and Env.step (die_env_step_host / "
-                  "die_env_step_host_dev: the action is not uploaded again when it is the array forward just returned), "
+           "api": "numpy obs/action across Agent.forward (die_gradient_forward_host) and Env.step ("
+                  "die_env_step_host_flags: the action is not uploaded again when it is the array forward just returned; the "
+                  "observation channels no kernel reads (forward) or writes (step: alive) stay where they are), "
                   "each call cut into chunks on two streams; pinned host memory"}
     # -- one caller thread
     env, agent, _ = make_env_and_agent(D, torch, field, B_e2e, batched, device, rank, 50)
@@ -433,8 +434,8 @@ def e2e_leg(D, torch, dist, args, field, B_local, batched, device, rank, world, 
     torch.cuda.synchronize()
     t_one = max_over_ranks(time.perf_counter() - t_start, device)
     h2d_step, d2h_step = env.host_io_bytes_per_step()
-    fwd_h2d = 8 * B_e2e * (4 * M + 3 * C)
-    fwd_d2h = 8 * B_e2e * 3 * M
+    # forward uploads the channels the policy reads (x, y; env_food, chem1) and downloads the action
+    fwd_h2d, fwd_d2h = agent.host_io_bytes_per_forward(B_e2e, M, C)
     h2d, d2h = (h2d_step + fwd_h2d) * n_gpus, (d2h_step + fwd_d2h) * n_gpus
     one = {"value": C * B_e2e * n_gpus * k_e2e / t_one, "ms_per_step": t_one / k_e2e * 1e3,
            "h2d_gbs_per_gpu": round(h2d / n_gpus / (t_one / k_e2e) / 1e9, 1),

@@ -11,6 +11,7 @@ DIFFUSE_MODES = {'wrap': 0, 'reflect': 1, 'nearest': 2, 'mirror': 3, 'constant':
 FIELD_F64, FIELD_F32 = 0, 1
 FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE, FWD_STEP_ON_DEVICE, FWD_COMMIT_MOVE = 1, 2, 4, 8, 16
 STEP_ADOPT_MOVE, STEP_ALIVE_BITS = 1, 2
+HOST_KEEP_ALIVE_CHANNEL = 1
 
 
 class DieDynamics(C.Structure):
@@ -87,6 +88,7 @@ SIGNATURES = {
     "die_env_read_stats": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "die_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "die_env_step_host_dev": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "die_env_step_host_flags": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "die_sense_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "die_render_frames": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, C.c_double, _P, _P, _P, _P]),
     "die_brownian_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_double, C.c_double, _P,

@@ -180,6 +180,12 @@ class GradientAgent(_DeviceAgent):
         return self._params_struct
 
     # -- forward ------------------------------------------------------------------------------
+    @staticmethod
+    def host_io_bytes_per_forward(B: int, M: int, C: int):
+        """(H2D, D2H) bytes of one host-path ``forward`` over B environments of M slots and C cells: the channels the
+        policy reads -- x, y and env_food, chem1 (die_gradient_forward_host) -- up, the action down."""
+        return 8 * B * (2 * M + 2 * C), 8 * B * 3 * M
+
     def _upload(self, name: str, arr: np.ndarray, shape, dtype, device):
         host, dev = getattr(self, f'_{name}_host'), getattr(self, f'_{name}_dev')
         if host is None or tuple(host.shape) != tuple(shape):

@@ -762,7 +762,9 @@ static size_t g_host_chunk_min_bytes = (size_t)32 << 20;   // below this a call 
 static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_out,
                               double* agents, const double* action_host, const double* action_dev,
                               double* agents_host, double* medium_host,
-                              double* reward_host, int64_t* alive_host, void* stream) {
+                              double* reward_host, int64_t* alive_host, void* stream, int32_t flags = 0) {
+    if ((flags & DIE_HOST_KEEP_ALIVE_CHANNEL) && e != nullptr && e->dyn.agents_die)
+        return fail(DIE_E_INVALID, "DIE_HOST_KEEP_ALIVE_CHANNEL: with agents_die the alive channel changes every step%s%s");
     DIE_REQUIRE(e != nullptr && (action_host != nullptr) != (action_dev != nullptr));
     if (e->field_f32) return fail(DIE_E_INVALID, "the host-buffer step runs float64 fields only%s%s");
     DIE_REQUIRE(medium_in != nullptr && medium_out != nullptr && medium_in != medium_out && agents != nullptr);
@@ -799,7 +801,16 @@ static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_ou
         if (int rc = env_step_range(e, b0, nb, medium_in, medium_out, agents, action, e->reward_dev, e->alive_dev,
                                     false, nullptr, false, s))
             return rc;
-        if (agents_host != nullptr)
+        if (agents_host != nullptr && (flags & DIE_HOST_KEEP_ALIVE_CHANNEL)) {
+            // the step never changes the alive channel (no lifecycle): the caller's host copy of it is still right, so only
+            // x, y (channels 0-1, contiguous per env) and agent_food (channel 3) travel -- 24 instead of 32 B per slot
+            DIE_CUDA(cudaMemcpy2DAsync(agents_host + (size_t)b0 * 4 * M, sizeof(double) * 4 * M,
+                                       agents + (size_t)b0 * 4 * M, sizeof(double) * 4 * M,
+                                       sizeof(double) * 2 * M, (size_t)nb, cudaMemcpyDeviceToHost, s));
+            DIE_CUDA(cudaMemcpy2DAsync(agents_host + (size_t)b0 * 4 * M + 3 * M, sizeof(double) * 4 * M,
+                                       agents + (size_t)b0 * 4 * M + 3 * M, sizeof(double) * 4 * M,
+                                       sizeof(double) * M, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        } else if (agents_host != nullptr)
             DIE_CUDA(cudaMemcpyAsync(agents_host + (size_t)b0 * 4 * M, agents + (size_t)b0 * 4 * M,
                                      sizeof(double) * 4 * M * nb, cudaMemcpyDeviceToHost, s));
         if (medium_host != nullptr)
@@ -833,6 +844,14 @@ extern "C" int die_env_step_host_dev(die_env_t* e, double* medium_in, double* me
                                      double* reward_host, int64_t* alive_host, void* stream) {
     return env_step_host_impl(e, medium_in, medium_out, agents, nullptr, action_dev, agents_host, medium_host,
                               reward_host, alive_host, stream);
+}
+
+extern "C" int die_env_step_host_flags(die_env_t* e, double* medium_in, double* medium_out,
+                                       double* agents, const double* action_host, const double* action_dev,
+                                       double* agents_host, double* medium_host,
+                                       double* reward_host, int64_t* alive_host, int32_t flags, void* stream) {
+    return env_step_host_impl(e, medium_in, medium_out, agents, action_host, action_dev, agents_host, medium_host,
+                              reward_host, alive_host, stream, flags);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1233,10 +1252,13 @@ extern "C" int die_gradient_forward_host(die_host_ctx_t* ctx, const die_gradient
         const int nb = b1 - b0;
         cudaStream_t s = (nchunks > 1) ? ctx->streams[k & 1] : st;
         if (nchunks > 1 && k < 2) DIE_CUDA(cudaStreamWaitEvent(s, ctx->events[2], 0));
-        DIE_CUDA(cudaMemcpyAsync(agents_stage + b0 * 4 * Ms, agents_host + b0 * 4 * Ms, sizeof(double) * 4 * Ms * nb,
-                                 cudaMemcpyHostToDevice, s));
-        DIE_CUDA(cudaMemcpyAsync(medium_stage + b0 * 3 * C, medium_host + b0 * 3 * C, sizeof(double) * 3 * C * nb,
-                                 cudaMemcpyHostToDevice, s));
+        // only what the policy reads travels: x, y (agents channels 0-1) and env_food, chem1 (medium channels 1-2), each
+        // contiguous per environment -- 32 instead of 56 B per slot; the other channels of the staging buffers (alive,
+        // agent_food, the occupancy) are never read by the forward kernel (core/agent/gradient.py:96-124 does not either)
+        DIE_CUDA(cudaMemcpy2DAsync(agents_stage + b0 * 4 * Ms, sizeof(double) * 4 * Ms, agents_host + b0 * 4 * Ms,
+                                   sizeof(double) * 4 * Ms, sizeof(double) * 2 * Ms, (size_t)nb, cudaMemcpyHostToDevice, s));
+        DIE_CUDA(cudaMemcpy2DAsync(medium_stage + b0 * 3 * C + C, sizeof(double) * 3 * C, medium_host + b0 * 3 * C + C,
+                                   sizeof(double) * 3 * C, sizeof(double) * 2 * C, (size_t)nb, cudaMemcpyHostToDevice, s));
         if (int rc = gradient_forward_impl(nullptr, false, p, H, W, M, nb, agents_stage + b0 * 4 * Ms, medium_stage + b0 * 3 * C,
                                            theta + b0 * Ms, prev_grad ? prev_grad + b0 * 2 * Ms : nullptr, action + b0 * 3 * Ms,
                                            coin ? coin + b0 * Ms : nullptr, noise ? noise + b0 * 2 * Ms : nullptr,

@@ -370,6 +370,8 @@ class Env:
         self._hint_state = None
         self._speculation = None
         self._checksums = None
+        if getattr(self, '_host', None) is not None:
+            self._host['alive_of'] = None          # the host path downloads the alive channel again
         with _lib.on_device(self.device):
             _lib.check(self._lib.die_env_discard_move(self._handle, torch.cuda.current_stream().cuda_stream))
 
@@ -652,14 +654,21 @@ class Env:
             raise RuntimeError("Env.step (host buffers): a committed move (fuse_move='commit') is waiting for its device step")
         self._speculation = None          # die_env_step_host runs the plain step (and discards a pending move)
         self.last_step_fused = False
+        # the pinned agents buffer already holds the current alive channel (a full download into it since the agents tensor
+        # was last edited, and Env.step never changes that channel without a lifecycle): 24 instead of 32 B per slot.  The
+        # array handed out is read-only, so the caller cannot have scribbled on it either.
+        keep_alive = (not self.dynamics.agents_die and hb.get('alive_of') == (self._agents._version, self._generation))
+        self.last_step_kept_alive_channel = keep_alive
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            fn = self._lib.die_env_step_host if dev_action is None else self._lib.die_env_step_host_dev
-            _lib.check(fn(
+            _lib.check(self._lib.die_env_step_host_flags(
                 self._handle, self._medium_buf[self._cur].data_ptr(), self._medium_buf[nxt].data_ptr(),
-                self._agents.data_ptr(), src.ctypes.data if dev_action is None else dev_action.data_ptr(),
+                self._agents.data_ptr(), src.ctypes.data if dev_action is None else None,
+                None if dev_action is None else dev_action.data_ptr(),
                 hb['agents'].data_ptr(), med_t.data_ptr() if self._obs_buf is None else None,
-                hb['reward'].data_ptr(), hb['alive'].data_ptr(), stream))
+                hb['reward'].data_ptr(), hb['alive'].data_ptr(),
+                _lib.HOST_KEEP_ALIVE_CHANNEL if keep_alive else 0, stream))
+        hb['alive_of'] = None if self.dynamics.agents_die else (self._agents._version, self._generation)
         self._cur = nxt
         if self._flow_tables is not None:
             self.dynamics.op_food_flow.calls += 1
@@ -668,7 +677,9 @@ class Env:
             with torch.cuda.device(self.device):
                 med_t.copy_(self._obs_buf[self._cur], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-        obs = (self._unbatch(hb['agents'].numpy()), self._unbatch(med_t.numpy()))
+        agents_np = hb['agents'].numpy()
+        agents_np.flags.writeable = False      # (a host COPY of the env's agents: writes to it never reached the env anyway)
+        obs = (self._unbatch(agents_np), self._unbatch(med_t.numpy()))
         return (obs, *self._summarise(hb['reward'].numpy().copy(), hb['alive'].numpy().copy()))
 
     def host_io_bytes_per_step(self) -> Tuple[int, int]:
@@ -676,7 +687,8 @@ class Env:
         B, M = self._B, self._M
         h, w = self._field_size
         h2d = 0 if getattr(self, 'last_step_reused_device_action', False) else 8 * B * 3 * M
-        return h2d, 8 * B * (4 * M + 3 * h * w) + 16 * B
+        agent_channels = 3 if getattr(self, 'last_step_kept_alive_channel', False) else 4
+        return h2d, 8 * B * (agent_channels * M + 3 * h * w) + 16 * B
 
     # -- measurement aid ----------------------------------------------------------------------
     STEP_KERNELS = ('move_claim', 'field_step', 'agent_feed', 'finalize_stats')

@@ -187,6 +187,17 @@ int die_env_step_host_dev(die_env_t* env, double* medium_in_dev, double* medium_
                           double* agents_host, double* medium_host,
                           double* reward_host, int64_t* alive_host, void* stream);
 
+/* Both of the above with options (exactly one of action_host / action_dev is non-NULL):
+ *   DIE_HOST_KEEP_ALIVE_CHANNEL  agents_host already holds the current `alive` channel (a full download of this env's
+ *                                agents went into that very buffer and neither the caller nor a lifecycle changed the
+ *                                channel since -- Env.step never does, core/env.py:152-243): only x, y and agent_food
+ *                                are copied, 24 instead of 32 B per slot.  Refused with Dynamics.agents_die. */
+#define DIE_HOST_KEEP_ALIVE_CHANNEL 1
+int die_env_step_host_flags(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
+                            double* agents_dev, const double* action_host, const double* action_dev,
+                            double* agents_host, double* medium_host,
+                            double* reward_host, int64_t* alive_host, int32_t flags, void* stream);
+
 /* Env._get_sensed_medium with Dynamics.apply_sense_mask (core/env.py:275-294): the observation's medium is
  *     medium.where(ceil(round(gaussian(medium['agents'], sigma=2.0), 3)), other=0.)
  * i.e. every channel zeroed outside the blurred neighbourhood of the agents.  weights_host[2*radius+1] = the
@@ -258,8 +269,9 @@ int die_gradient_forward(const die_gradient_params_t* p,
                          uint64_t seed, uint64_t step, void* stream);
 
 /* GradientAgent.forward / PhysarumAgent.forward through HOST buffers: H2D of the observation (agents_host[B][4][M],
- * medium_host[B][3][H][W]) into the caller's device staging buffers, the forward kernel, D2H of the action into
- * action_host[B][3][M]; synchronises `stream` before returning.  Large batches are cut into chunks of environments that
+ * medium_host[B][3][H][W]) into the caller's device staging buffers -- of the channels the policy reads, x, y and
+ * env_food, chem1 (32 of the observation's 56 B per slot; the rest of the staging buffers is not written) --, the forward
+ * kernel, D2H of the action into action_host[B][3][M]; synchronises `stream` before returning.  Large batches are cut into chunks of environments that
  * alternate between the two streams of a die_host_ctx_t, so one chunk's action download overlaps the next chunk's
  * observation upload (both PCIe directions busy).  In-kernel random draws do not depend on the chunking. */
 typedef struct die_host_ctx die_host_ctx_t;

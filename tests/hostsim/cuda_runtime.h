@@ -181,6 +181,11 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
     memmove(d, s, n);
     return cudaSuccess;
 }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                            cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < height; ++r) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }   // "2 SMs"
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }

@@ -168,15 +168,21 @@ class SimEnv:
         self.grad_valid = self.publish_grad
         return self.reward.copy(), self.alive.copy()
 
-    def step_host(self, action):
-        """die_env_step_host: action / observation through "host" buffers, chunked over the batch."""
+    def step_host(self, action, agents_host=None, flags=0):
+        """die_env_step_host: action / observation through "host" buffers, chunked over the batch.  With `agents_host` (a
+        buffer kept from an earlier call) and flags = HOST_KEEP_ALIVE_CHANNEL: die_env_step_host_flags."""
         action = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(self.B, 3, self.M))
         nxt = 1 - self.cur
-        agents_h = np.empty_like(self.agents)
+        agents_h = np.empty_like(self.agents) if agents_host is None else agents_host
         medium_h = np.empty_like(self.medium_buf[0])
-        check(self.lib.die_env_step_host(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
-                                         ptr(self.agents), ptr(action), ptr(agents_h), ptr(medium_h),
-                                         ptr(self.reward), ptr(self.alive), None))
+        if agents_host is not None or flags:
+            check(self.lib.die_env_step_host_flags(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
+                                                   ptr(self.agents), ptr(action), None, ptr(agents_h), ptr(medium_h),
+                                                   ptr(self.reward), ptr(self.alive), flags, None))
+        else:
+            check(self.lib.die_env_step_host(self.handle, ptr(self.medium_buf[self.cur]), ptr(self.medium_buf[nxt]),
+                                             ptr(self.agents), ptr(action), ptr(agents_h), ptr(medium_h),
+                                             ptr(self.reward), ptr(self.alive), None))
         self.cur = nxt
         self.hints_valid = True
         self.grad_valid = self.publish_grad

@@ -101,6 +101,17 @@ def test_chunked_host_path_equals_device_path(agent_kind):
             hobs, hr, _, _, hi = host_env.step(hact)
             assert np.array_equal(dr, hr) and np.array_equal(di['num_agents'], hi['num_agents'])
             assert np.array_equal(dobs[0].cpu().numpy(), hobs[0]) and np.array_equal(dobs[1].cpu().numpy(), hobs[1])
+            # from the second step on the alive channel stays in the pinned buffer (DIE_HOST_KEEP_ALIVE_CHANNEL); the host
+            # observation is a read-only copy
+            assert host_env.last_step_kept_alive_channel == (it > 0) and not hobs[0].flags.writeable
+            assert host_env.host_io_bytes_per_step()[1] == 8 * B * ((3 if it > 0 else 4) * m + 3 * field[0] * field[1]) + 16 * B
+        # an edit of the agents tensor (here: half of the agents die) is followed by a full download
+        for env in (dev_env, host_env):
+            env.agents[:, 2, ::2] = 0.0
+        dobs, *_ = dev_env.step(a_dev.forward(dobs))
+        hobs, *_ = host_env.step(a_host.forward(tuple(np.array(t.cpu().numpy()) for t in host_env._get_current_obs)))
+        assert not host_env.last_step_kept_alive_channel
+        assert np.array_equal(dobs[0].cpu().numpy(), hobs[0]) and (hobs[0][:, 2, ::2] == 0).all()
     finally:
         _lib.check(lib.die_set_tuning(b"host_chunk_min_kb", 32 << 10))
         _lib.check(lib.die_set_tuning(b"host_chunks", 4))

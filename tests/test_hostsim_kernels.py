@@ -1126,6 +1126,33 @@ def test_jones_agent_philox_batch_and_float32_medium():
     assert not np.array_equal(a[0], a[1]) and np.array_equal(a[:, 2], a[::-1, 2])
 
 
+def test_host_step_keeps_the_alive_channel_where_it_is(tuning):
+    """DIE_HOST_KEEP_ALIVE_CHANNEL: x, y and agent_food are copied into the caller's buffer, the alive channel is left
+    alone (the poison written over it survives), everything else equals the full download; refused with agents_die."""
+    tuning("host_chunk_min_kb", 0)
+    try:
+        refs, env = make_pair((24, 32), seed=17, batch=9)
+        refs2, env2 = make_pair((24, 32), seed=17, batch=9)
+        rng = np.random.default_rng(0)
+        keep = None
+        for it in range(4):
+            act = np.stack([S.brownian_forward(env.agents[b], move_scale=0.02, seed=4 + b, step=it) for b in range(9)])
+            (full_agents, full_medium), r_full, _ = env2.step_host(act)
+            if keep is None:
+                (keep, med), r, _ = env.step_host(act)
+            else:
+                keep[:, 2] = -7.0                                   # poison: must not be overwritten
+                (_, med), r, _ = env.step_host(act, agents_host=keep, flags=L.HOST_KEEP_ALIVE_CHANNEL)
+                assert (keep[:, 2] == -7.0).all()
+                keep[:, 2] = full_agents[:, 2]
+            assert np.array_equal(keep, full_agents) and np.array_equal(med, full_medium) and np.array_equal(r, r_full)
+        (_,), dying = make_pair((24, 32), seed=2, dynamics_kw=dict(agents_die=True))
+        with pytest.raises(RuntimeError, match="KEEP_ALIVE"):
+            dying.step_host(np.zeros((1, 3, dying.M)), agents_host=np.empty_like(dying.agents), flags=L.HOST_KEEP_ALIVE_CHANNEL)
+    finally:
+        tuning("host_chunk_min_kb", 32 << 10)
+
+
 def test_forward_through_host_buffers_is_chunked_and_identical(tuning):
     """die_gradient_forward_host: observation uploaded / action downloaded chunk by chunk on two streams; the in-kernel
     random draws are keyed on the GLOBAL environment index, so chunking does not change them."""
