@@ -5,7 +5,7 @@ offers ('st-perlin': static food; 'dyn-pred': the WaveSequence food flow, :95-10
 the imports differ; the interactive matplotlib plotter is replaced by the frames of `Env.render` (the arrays the
 reference's EnvRenderer hands to matplotlib).  Needs a CUDA device (there is no CPU fallback).
 
-    python examples/simple_agents.py [--agent const|rand|grad|physarum] [--dynamics st-perlin|dyn-pred]
+    python examples/simple_agents.py [--agent const|rand|grad|physarum|jones] [--dynamics st-perlin|dyn-pred]
                                      [--field 156] [--iters 1000] [--ratio 0.1] [--frames-every 0]
 """
 import argparse
@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
-from die_b200 import Env, Dynamics, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent, WaveSequence
+from die_b200 import Env, Dynamics, ConstAgent, BrownianAgent, GradientAgent, PhysarumAgent, JonesAgent, WaveSequence
 
 
 def try_const_agent(**kwargs):
@@ -36,6 +36,11 @@ def try_gradient_agent(num_agents, **kwargs):
 def try_physarum_agent(num_agents, **kwargs):
     return PhysarumAgent(num_agents, turn_angle=35, sense_angle=120, sense_offset=0.03, turn_tolerance=0.05,
                          inertia=0., scale=0.0075, deposit=4.5, noise_scale=0.0, normalized_grad=True)
+
+
+def try_jones_agent(num_agents, **kwargs):
+    """Not in the reference's example: the classic three-sensor particle (die_b200.JonesAgent) with comparable parameters."""
+    return JonesAgent(num_agents, turn_angle=45, sense_angle=45, sense_offset=0.03, scale=0.0075, deposit=4.5)
 
 
 def run_agent(env, agent, iters=1000, frames_every=0):
@@ -63,6 +68,7 @@ def run_experiment(field_size=156, agent_id='rand', dynamics_id='st-perlin', ite
         'rand': try_random_agent,
         'grad': lambda: try_gradient_agent(max_agents),
         'physarum': lambda: try_physarum_agent(max_agents),
+        'jones': lambda: try_jones_agent(max_agents),
     }
     wave_flow = WaveSequence(field_size, dt=0.01).get_flow_operator(scale=0.5, decay=0.5)
     dynamics_choice = {
@@ -80,7 +86,7 @@ def run_experiment(field_size=156, agent_id='rand', dynamics_id='st-perlin', ite
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument("--agent", default="grad", choices=["const", "rand", "grad", "physarum"])
+    ap.add_argument("--agent", default="grad", choices=["const", "rand", "grad", "physarum", "jones"])
     ap.add_argument("--dynamics", default="st-perlin", choices=["st-perlin", "dyn-pred"])
     ap.add_argument("--field", type=int, default=156)
     ap.add_argument("--iters", type=int, default=1000)

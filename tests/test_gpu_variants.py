@@ -118,7 +118,8 @@ def test_tabulated_food_flow(field, sigma, batch):
 
 
 @pytest.mark.parametrize("argv", [["--agent", "const"], ["--agent", "rand"], ["--agent", "grad", "--dynamics", "dyn-pred"],
-                                  ["--agent", "physarum", "--dynamics", "dyn-pred", "--frames-every", "10"]])
+                                  ["--agent", "physarum", "--dynamics", "dyn-pred", "--frames-every", "10"],
+                                  ["--agent", "jones", "--frames-every", "10"]])
 def test_simple_agents_example(argv):
     """examples/simple_agents.py: the reference's four hand-written policies on its two dynamics (callers)."""
     import subprocess
