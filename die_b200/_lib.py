@@ -9,8 +9,8 @@ DIE_MAX_RADIUS = 8
 BOUNDARY_WRAP, BOUNDARY_LIMIT, BOUNDARY_NONE = 0, 1, 2
 DIFFUSE_MODES = {'wrap': 0, 'reflect': 1, 'nearest': 2, 'mirror': 3, 'constant': 4}
 FIELD_F64, FIELD_F32 = 0, 1
-FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE, FWD_STEP_ON_DEVICE, FWD_COMMIT_MOVE = 1, 2, 4, 8, 16
-STEP_ADOPT_MOVE, STEP_ALIVE_BITS = 1, 2
+FWD_USE_GRADIENT, FWD_USE_CELLS, FWD_SPECULATE_MOVE, FWD_STEP_ON_DEVICE, FWD_COMMIT_MOVE, FWD_WRITE_COST = 1, 2, 4, 8, 16, 32
+STEP_ADOPT_MOVE, STEP_ALIVE_BITS, STEP_USE_COST = 1, 2, 4
 HOST_KEEP_ALIVE_CHANNEL = 1
 
 

@@ -295,6 +295,8 @@ class GradientAgent(_DeviceAgent):
         self.last_committed = bool(flags & _lib.FWD_COMMIT_MOVE)
         if self.last_speculated:
             env._note_speculation(action, self.last_committed)
+        if flags & _lib.FWD_WRITE_COST:
+            env._note_cost(action)
         self._step += 1
         return action
 

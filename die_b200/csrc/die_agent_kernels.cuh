@@ -218,6 +218,8 @@ struct GradientArgs {
     // MOVE instantiation: Env._agent_move + the claim, evaluated speculatively for the action being written
     int32_t* winner;            // [B][H*W] claim table
     int32_t* cells_out;         // [B][M] post-move cell of every slot (the env's OTHER cell buffer)
+    double* burned_out;         // may be null: [B][M] out, linear_action_cost of the action being written (cost hint)
+    double cost_w_dep, cost_w_dist;
     double* commit_xy;          // null: the move stays speculative (the feed kernel commits the positions once the step
                                 // adopts it).  Else = `agents`, writable: the moved x, y are stored in place by THIS
                                 // launch (DIE_FWD_COMMIT_MOVE: the caller promises that very action to the next step)
@@ -305,6 +307,7 @@ gradient_forward_kernel(const GradientArgs a) {
     int32_t* win = MOVE ? a.winner + ch.b * C : nullptr;
     int32_t* co_p = MOVE ? a.cells_out + ch.b * M + first : nullptr;
     double* cx_p = (MOVE && a.commit_xy != nullptr) ? a.commit_xy + ch.b * 4 * M + first : nullptr;
+    double* bo_p = (a.burned_out != nullptr) ? a.burned_out + ch.b * M + first : nullptr;
     // all 32 slots of a warp-item share one word of the alive bitmask (first - lane is a multiple of 32)
     const uint32_t* bits_p = MOVE ? a.alive_bits + ch.b * a.Mw + (first >> 5) : nullptr;
 
@@ -489,6 +492,9 @@ gradient_forward_kernel(const GradientArgs a) {
         ab[i] = adx;
         ab_y[i] = ady;
         ab_dep[i] = dep;
+        // cost hint: linear_action_cost (core/env.py:29-35) of this very action, the expression of agent_feed_kernel; the
+        // step that receives the action unmodified reads these 8 bytes per slot instead of dx, dy, deposit again (24)
+        if (bo_p != nullptr) bo_p[i] = a.cost_w_dep * fabs(dep) + a.cost_w_dist * sqrt(adx * adx + ady * ady);
 
         if (MOVE) {
             // Env._agent_move (core/env.py:152-172) of THIS action + cell resolution + claim: what
@@ -580,6 +586,7 @@ struct FeedArgs {
     const uint32_t* alive_bits;
     int64_t Mw;
     int boundary;
+    const double* burned;            // COST: [B][M] linear_action_cost per slot, written by the forward kernel for this action
 };
 
 // DIE: Dynamics.agents_die -- Env._agent_lifecycle (core/env.py:245-250) folded in: a slot whose stock after feeding is
@@ -587,10 +594,13 @@ struct FeedArgs {
 // holds for every ghost slot every step; num_agents counts the survivors (core/env.py:118, after the lifecycle).
 // PAIR: the per-cell scratch is {consumed_field, new env_food} (16 bytes, one sector): the slot's gather brings both, and
 // the food is stored per slot for the next forward pass (see FH there).
-template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double, bool PAIR = false>
+// COST: the action cost of every slot comes from the array the forward kernel filled for exactly this action (the caller
+// proved the identity, as for the speculative move): one 8-byte load per slot instead of dx, dy, deposit (24 bytes).
+template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double, bool PAIR = false, bool COST = false>
 __global__ void __launch_bounds__(kAgentThreads)
 agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     static_assert(!PAIR || (!SLAB && !DIE && sizeof(FT) == 8), "the pair table serves the plain float64 step");
+    static_assert(!COST || (!SLAB && !MOVE && !DIE), "the cost hint serves the plain step (a speculative move needs dx, dy)");
     const int64_t M = a.M;
     const int nblk = a.nblk;
     const int64_t b = blockIdx.x / (unsigned)nblk;
@@ -604,6 +614,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     int32_t* __restrict__ win = a.winner + b * a.C;
     int32_t* __restrict__ cl = a.cells + b * M + first;
     const uint32_t* __restrict__ bits_p = BITS ? a.alive_bits + b * a.Mw + (first >> 5) : nullptr;
+    const double* __restrict__ bu_p = COST ? a.burned + b * M + first : nullptr;
     const double w_dep = a.w_dep, w_dist = a.w_dist;
     const int boundary = a.boundary;
     double* const part_gain = a.part_gain;
@@ -636,9 +647,14 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
             py[k] = valid[k] ? ag_x[M + i] : 0.0;
         }
         stock[k] = valid[k] ? ag_x[3 * M + i] : 0.0;
-        dx[k] = valid[k] ? ac[i] : 0.0;
-        dy[k] = valid[k] ? ac[M + i] : 0.0;
-        dep[k] = valid[k] ? ac[2 * M + i] : 0.0;
+        if (COST) {
+            dx[k] = valid[k] ? bu_p[i] : 0.0;              // (the cost itself)
+            dy[k] = dep[k] = 0.0;
+        } else {
+            dx[k] = valid[k] ? ac[i] : 0.0;
+            dy[k] = valid[k] ? ac[M + i] : 0.0;
+            dep[k] = valid[k] ? ac[2 * M + i] : 0.0;
+        }
     }
     double gain_sum = 0.0;
     int alive_cnt = 0;
@@ -651,7 +667,7 @@ agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
                 ag_x[i] = apply_boundary(px[k] + dx[k], boundary);
                 ag_x[M + i] = apply_boundary(py[k] + dy[k], boundary);
             }
-            const double burned = w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
+            const double burned = COST ? dx[k] : w_dep * fabs(dep[k]) + w_dist * sqrt(dx[k] * dx[k] + dy[k] * dy[k]);
             const double gained = eaten[k] - burned;
             const double stock_new = stock[k] + gained;
             gain_sum += gained;

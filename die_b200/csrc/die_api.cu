@@ -42,6 +42,8 @@ struct die_env {
     uint32_t* alive_bits;  // [B][Mw]   (alive > 0) per slot, one bit each (die_env_refresh_alive)
     int64_t Mw;
     int alive_valid;
+    double* burned;        // [B][M] lazily: linear_action_cost per slot of the action the last forward wrote (cost hint)
+    int cost_pending;      // that array is valid for the action of the forward that just ran (DIE_FWD_WRITE_COST)
     int pending_move;      // 1: a speculative move (cells2[1-cur] + claims) waits for a step with DIE_STEP_ADOPT_MOVE;
                            // 2: a COMMITTED one (DIE_FWD_COMMIT_MOVE: the positions are already stored)
     // op_food_flow = WaveSequence flow operator (die_env_set_food_flow); borrowed device tables, host copy of ts
@@ -88,7 +90,7 @@ extern "C" const char* die_version(void) { return "die_b200 0.1 (sm_100a)"; }
 
 // launch counters (diagnostics: tests assert that the variant they mean to exercise is the one that ran)
 static int64_t g_count_fwd_food_here = 0, g_count_field_tile = 0, g_count_field_vec = 0, g_count_step_fused = 0, g_count_fwd_lean = 0, g_count_fwd_lean_f32 = 0, g_count_fwd_general = 0,
-               g_count_step_committed = 0, g_count_fwd_lean_move = 0;
+               g_count_step_committed = 0, g_count_fwd_lean_move = 0, g_count_feed_cost = 0;
 
 extern "C" int64_t die_get_counter(const char* key) {
     if (key == nullptr) return -1;
@@ -101,6 +103,7 @@ extern "C" int64_t die_get_counter(const char* key) {
     if (strcmp(key, "forward_food_here") == 0) return g_count_fwd_food_here;
     if (strcmp(key, "forward_lean_move") == 0) return g_count_fwd_lean_move;
     if (strcmp(key, "step_committed") == 0) return g_count_step_committed;
+    if (strcmp(key, "feed_cost") == 0) return g_count_feed_cost;
     return -1;
 }
 extern "C" const char* die_last_error(void) { return g_err; }
@@ -173,6 +176,7 @@ extern "C" int die_env_destroy(die_env_t* e) {
     cudaFree(e->consumed);
     cudaFree(e->cell_pairs);
     cudaFree(e->food_here);
+    cudaFree(e->burned);
     cudaFree(e->grad);
     cudaFree(e->grad32);
     cudaFree(e->part_gain);
@@ -209,6 +213,7 @@ extern "C" int die_env_set_dynamics(die_env_t* e, const die_dynamics_t* dyn) {
     DIE_REQUIRE(e != nullptr);
     if (int rc = check_dynamics(dyn)) return rc;
     e->dyn = *dyn;
+    e->cost_pending = 0;              // (the cost weights may have changed)
     return DIE_OK;
 }
 
@@ -383,6 +388,7 @@ extern "C" int die_set_step_impl(int32_t impl) {
 // a DRAM sector plus change (77-93 B measured), so the step keeps {consumed_field, new food} in ONE 16-byte
 // pair per cell and hands the food per slot to the next forward pass: three random accesses per slot and step become
 // two.  Small fields (the batched workload) gather out of L2 and keep the 8-byte table.
+static int g_cost_hint = 1;                    // 0: the feed kernel always re-reads dx, dy, deposit (A-B timing)
 static int g_pair_mode = 1;                    // 0 never, 1 by size (pair_min_cells), 2 always (tests)
 static int64_t g_pair_min_cells = 1 << 23;     // cells per environment from which it pays.  Measured on a B200, step time at
                                                // step 40 / step 3000: 2048^2 +6 % / +7 % (the tables still sit in L2),
@@ -595,7 +601,7 @@ static int g_feed_bits = 1;        // feed kernel reads alive-ness from the bitm
 static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, double* medium_out,
                           double* agents, const double* action, double* reward_dev, int64_t* alive_dev,
                           bool fused, const uint32_t* alive_bits, bool profile, cudaStream_t st,
-                          bool committed = false) {
+                          bool committed = false, bool use_cost = false) {
     // fused: cells + claims of this action are in place (the forward kernel's MOVE instantiation); committed: so are the
     // positions, and the feed kernel is the plain one
     const size_t C = (size_t)e->H * e->W, M = (size_t)e->M;
@@ -658,6 +664,14 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     }
     if (pair) feed = feed_bits ? agent_feed_kernel<false, false, true, false, double, true>
                                : agent_feed_kernel<false, false, false, false, double, true>;
+    // cost hint: the forward kernel left linear_action_cost of exactly this action in e->burned (die_env_step_flags checked)
+    const bool cost = use_cost && feed_bits && (!fused || committed) && !e->dyn.agents_die && !e->field_f32 &&
+                      e->burned != nullptr;
+    if (cost) {
+        feed = pair ? agent_feed_kernel<false, false, true, false, double, true, true>
+                    : agent_feed_kernel<false, false, true, false, double, false, true>;
+        ++g_count_feed_cost;
+    }
     FeedArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.agents = agents; fa.action = action;
@@ -670,6 +684,7 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     fa.C = (int64_t)C; fa.M = e->M; fa.nblk = e->nblk;
     fa.w_dep = e->dyn.cost_w_deposit; fa.w_dist = e->dyn.cost_w_dist;
     fa.alive_bits = alive_bits; fa.Mw = e->Mw; fa.boundary = e->dyn.boundary;
+    if (cost) fa.burned = e->burned + (size_t)b0 * M;
     feed<<<fgrid, kAgentThreads, 0, st>>>(fa, SlabGeom(), SlabTables());
     DIE_CUDA(cudaGetLastError());
     if (profile) prof_mark(e, 3, st);
@@ -694,6 +709,9 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
     if ((fused || bits) && !e->alive_valid)
         return fail(DIE_E_INVALID, "die_env_step_flags: call die_env_refresh_alive first%s%s");
     const uint32_t* alive_bits = (fused || bits) ? e->alive_bits : nullptr;
+    // DIE_STEP_USE_COST is a permission: honoured only while the forward's cost array is still the pending one
+    const bool use_cost = (flags & DIE_STEP_USE_COST) != 0 && e->cost_pending && g_cost_hint;
+    e->cost_pending = 0;
     bool committed = false;
     if (fused) {
         // the forward kernel already resolved cells and claims for exactly this action
@@ -709,7 +727,7 @@ extern "C" int die_env_step_flags(die_env_t* e, double* medium_in, double* mediu
         if (int rc = die_env_discard_move(e, stream)) return rc;
     }
     if (int rc = env_step_range(e, 0, e->B, medium_in, medium_out, agents, action, reward_dev, alive_dev,
-                                fused, alive_bits, true, st, committed))
+                                fused, alive_bits, true, st, committed, use_cost))
         return rc;
     if (e->flow_rwave != nullptr || e->flow_frames != nullptr) ++e->flow_k;
     if (e->profiling && e->prof_steps < DIE_MAX_PROFILED_STEPS) ++e->prof_steps;
@@ -774,6 +792,7 @@ static int env_step_host_impl(die_env_t* e, double* medium_in, double* medium_ou
     if (action_dev == nullptr && e->action_stage == nullptr)
         DIE_CUDA(cudaMalloc(&e->action_stage, sizeof(double) * 3 * M * e->B));
     const double* action = action_dev != nullptr ? action_dev : e->action_stage;
+    e->cost_pending = 0;
     if (e->pending_move == 2)
         return fail(DIE_E_INVALID, "the host-buffer step cannot follow a committed move (DIE_FWD_COMMIT_MOVE)%s%s");
     if (e->pending_move) {
@@ -1024,6 +1043,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
+    else if (strcmp(key, "cost_hint") == 0) g_cost_hint = value ? 1 : 0;
     else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }
     else if (strcmp(key, "pair_min_cells_log2") == 0) { DIE_REQUIRE(value >= 2 && value <= 31); g_pair_min_cells = (int64_t)1 << value; }
     else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
@@ -1048,7 +1068,7 @@ static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradie
                                  const double* grad_hint, const int32_t* cells_hint,
                                  uint64_t seed, uint64_t step, void* stream, int b0 = 0,
                                  const float2* grad32_hint = nullptr, const uint64_t* step_dev = nullptr,
-                                 bool field_f32 = false) {
+                                 bool field_f32 = false, bool write_cost = false) {
     DIE_REQUIRE(p != nullptr);
     DIE_REQUIRE(H >= 2 && W >= 2 && M >= 1 && B >= 1);
     DIE_REQUIRE((int64_t)H * W <= 0x7fffffffLL);
@@ -1089,6 +1109,12 @@ static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradie
         a.Mw = env->Mw;
         a.boundary = env->dyn.boundary;
         if (move_mode == 2) a.commit_xy = const_cast<double*>(agents);
+    }
+    if (write_cost && env != nullptr && g_cost_hint && !field_f32) {
+        if (env->burned == nullptr) DIE_CUDA(cudaMalloc(&env->burned, sizeof(double) * (size_t)M * B));
+        a.burned_out = env->burned;
+        a.cost_w_dep = env->dyn.cost_w_deposit;
+        a.cost_w_dist = env->dyn.cost_w_dist;
     }
     void (*kern)(const GradientArgs) = nullptr;
 #define DIE_PICK_FWD(MINB)                                                                               \
@@ -1143,6 +1169,7 @@ static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradie
     DIE_CUDA(cudaGetLastError());
     ++(lean ? (a.grad32 != nullptr ? g_count_fwd_lean_f32 : g_count_fwd_lean) : g_count_fwd_general);
     if (speculate) env->pending_move = move_mode;
+    if (env != nullptr) env->cost_pending = (a.burned_out != nullptr) ? 1 : 0;
     return DIE_OK;
 }
 
@@ -1196,7 +1223,7 @@ extern "C" int die_env_forward_gradient(die_env_t* e, const die_gradient_params_
     const uint64_t* step_dev = (flags & DIE_FWD_STEP_ON_DEVICE) ? (const uint64_t*)(uintptr_t)step : nullptr;
     return gradient_forward_impl(e, move_mode, p, e->H, e->W, e->M, e->B, agents, medium, theta, prev_grad, action,
                                  coin, noise, sense_cells, grad_hint, cells_hint, seed, step_dev ? 0 : step, stream, 0,
-                                 grad32_hint, step_dev, e->field_f32 != 0);
+                                 grad32_hint, step_dev, e->field_f32 != 0, (flags & DIE_FWD_WRITE_COST) != 0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -174,6 +174,7 @@ class Env:
         # user kernel does not bump.  With this switch every cache carries a checksum of the bytes it was built from and
         # a mismatch raises instead of silently stepping on stale cells / alive bits (see invalidate_caches).
         self._verify_caches = bool(verify_caches)
+        self.use_cost_hint = True          # a gradient agent's forward may leave the action cost for the feed kernel (DIE_FWD_WRITE_COST)
         self._checksums = None
         # float64 as in the reference (default), or the float32 FIELD mode: the medium (and the library's per-cell
         # scratch) in float32, agents / actions / headings still float64 -- half the field bytes, results within float32
@@ -289,6 +290,7 @@ class Env:
             self._publish_grad = False
             self._hint_state = None         # (medium ptr, medium version, agents version, grad published)
             self._speculation = None        # (action ptr, action version, agents version) of a pending fused move
+            self._cost_hint = None          # (action ptr, action version) the library's cost array was written for
             self._alive_version = None      # agents._version the library's alive bitmask was built for
             self.last_step_fused = False
             _hints.publish(self, first)
@@ -369,6 +371,7 @@ class Env:
         self._alive_version = None
         self._hint_state = None
         self._speculation = None
+        self._cost_hint = None
         self._checksums = None
         if getattr(self, '_host', None) is not None:
             self._host['alive_of'] = None          # the host path downloads the alive channel again
@@ -499,7 +502,10 @@ class Env:
                                "env.agents are already those of that action")
         if self.dynamics.agents_die:
             fused = False                  # (the library refuses the combination; a pending speculation is discarded)
-        flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | (0 if self.dynamics.agents_die else _lib.STEP_ALIVE_BITS)
+        cost, self._cost_hint = self._cost_hint, None
+        use_cost = cost is not None and cost == (action.data_ptr(), action._version)
+        flags = (_lib.STEP_ADOPT_MOVE if fused else 0) | (0 if self.dynamics.agents_die else _lib.STEP_ALIVE_BITS) \
+            | (_lib.STEP_USE_COST if use_cost else 0)
         with _lib.on_device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             if not self.dynamics.agents_die:
@@ -573,6 +579,10 @@ class Env:
                                "positions in env.agents are already those of the next step")
         grad_ptr, cells_ptr = self._hints_for(agents, medium, want_gradient)
         flags = (_lib.FWD_USE_GRADIENT if grad_ptr else 0) | (_lib.FWD_USE_CELLS if cells_ptr else 0)
+        # cost hint (DIE_FWD_WRITE_COST): the forward launch leaves linear_action_cost of its action for the feed kernel;
+        # Env.step uses it iff it receives that very tensor unmodified (_note_cost / step_async)
+        if not self.dynamics.agents_die and self._field_dtype == torch.float64 and self.use_cost_hint:
+            flags |= _lib.FWD_WRITE_COST
         # 'commit': the run-loop contract (include/die_b200.h, DIE_FWD_COMMIT_MOVE) -- only on the env's own, valid caches,
         # i.e. in the steady state of `action = agent.forward(obs); obs, ... = env.step(action)`; elsewhere the plain path
         commit = speculate == 'commit'
@@ -592,6 +602,9 @@ class Env:
         if self._alive_version != self._agents._version:
             _lib.check(self._lib.die_env_refresh_alive(self._handle, self._agents.data_ptr(), stream))
             self._alive_version = self._agents._version
+
+    def _note_cost(self, action: torch.Tensor) -> None:
+        self._cost_hint = (action.data_ptr(), action._version)
 
     def _note_speculation(self, action: torch.Tensor, committed: bool = False) -> None:
         self._speculation = (action.data_ptr(), action._version, self._agents._version, committed)

@@ -326,6 +326,12 @@ int die_gradient_forward_f32(const die_gradient_params_t* p, int32_t H, int32_t 
  *                           the counter, so every replay draws fresh in-kernel random numbers (die_b200/graph.py) */
 #define DIE_FWD_STEP_ON_DEVICE  8
 #define DIE_FWD_COMMIT_MOVE     16
+/*   DIE_FWD_WRITE_COST      cost hint: the launch also stores linear_action_cost (core/env.py:29-35, with the env's weights) of
+ *                           the action it writes, 8 B per slot, into a buffer of the env.  If the very next step receives
+ *                           this action unmodified (the caller's responsibility, as above) and passes DIE_STEP_USE_COST,
+ *                           the feed kernel reads that value instead of dx, dy, deposit (24 B per slot): same bits.  Any
+ *                           other step, a host-buffer step or die_env_set_dynamics drops the hint. */
+#define DIE_FWD_WRITE_COST      32
 int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
                              const double* agents_dev, const double* medium_dev,
                              double* theta_dev, double* prev_grad_dev, double* action_dev,
@@ -337,6 +343,9 @@ int die_env_forward_gradient(die_env_t* env, const die_gradient_params_t* p,
  *                        and feed kernels read alive-ness from it (1 bit instead of 8 bytes per slot). */
 #define DIE_STEP_ADOPT_MOVE  1
 #define DIE_STEP_ALIVE_BITS  2
+/*   DIE_STEP_USE_COST    `action_dev` is exactly what the last die_env_forward_gradient(DIE_FWD_WRITE_COST) on this env wrote:
+ *                        the feed kernel may take the action cost from the hint (ignored when no hint is pending). */
+#define DIE_STEP_USE_COST    4
 int die_env_step_flags(die_env_t* env, double* medium_in_dev, double* medium_out_dev,
                        double* agents_dev, const double* action_dev,
                        double* reward_dev, int64_t* alive_dev, int32_t flags, void* stream);

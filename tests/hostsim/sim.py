@@ -215,6 +215,7 @@ class SimGradientAgent:
         self.record_sense_cells = False
         self.seed, self.step_no = seed, 0
         self.fuse_move = False
+        self.write_cost = False
 
     def forward(self, env: SimEnv, coin=None, noise=None, use_hints=True, obs=None):
         """obs = (agents, medium) arrays other than the env's own disable the hints, as die_b200/_hints.py does."""
@@ -235,6 +236,8 @@ class SimGradientAgent:
                 flags |= L.FWD_SPECULATE_MOVE
                 if self.fuse_move == 'commit':
                     flags |= L.FWD_COMMIT_MOVE
+            if self.write_cost:
+                flags |= L.FWD_WRITE_COST
             check(self.lib.die_env_forward_gradient(env.handle, C.byref(self.p), ptr(agents), ptr(medium), ptr(self.theta),
                                                     ptr(self.prev_grad), ptr(self.action), ptr(coin_a), ptr(noise_a),
                                                     ptr(sc), flags, self.seed, self.step_no, None))

@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1, pair_mode=1, pair_min_cells_log2=23)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1, pair_mode=1, pair_min_cells_log2=23, cost_hint=1)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -1027,6 +1027,42 @@ def test_committed_move_equals_the_plain_loop(tuning, shape, batch, kw, pair, gr
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     for it, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
         for x, y, what in zip(a, b, ("action", "reward", "num_agents", "agents", "cells")):
+            assert np.array_equal(x, y), f"step {it}: {what} differs"
+
+
+@pytest.mark.parametrize("shape,batch,kw,pair,fuse", [
+    ((40, 72), None, {}, 0, False), ((33, 47), 3, dict(op_action_cost=D.zero_cost), 0, False), ((64, 64), 2, {}, 2, False),
+    ((24, 50), None, dict(boundary=D.BoundaryCondition.limit), 0, 'commit'), ((6, 90), 2, dict(food_infinite=True), 2, 'commit')])
+def test_cost_hint_equals_the_plain_feed(tuning, shape, batch, kw, pair, fuse):
+    """DIE_FWD_WRITE_COST / DIE_STEP_USE_COST: the forward kernel leaves linear_action_cost of its action, the feed kernel
+    reads it instead of dx, dy, deposit -- every output equal bit for bit, with pair mode and the committed move too; a step
+    with the permission but no pending hint (a Brownian action) runs the plain kernel."""
+    tuning("pair_mode", pair)
+    outs = []
+    so = S.lib()
+    n0 = so.die_get_counter(b"feed_cost")
+    for cost in (False, True):
+        refs, env = make_pair(shape, seed=5, dynamics_kw=kw, batch=batch)
+        B = env.B
+        ga = S.SimGradientAgent(env.M, B=B, seed=1, **PHYS)
+        for b in range(B):
+            ga.theta[b] = lattice_theta(env.M, 30, 5 + b)[0]
+        ga.fuse_move, ga.write_cost = fuse, cost
+        trace = []
+        for it in range(8):
+            if it == 5:
+                act = np.stack([S.brownian_forward(env.agents[b], move_scale=0.02, seed=4 + b, step=it) for b in range(B)])
+                adopt = 0
+            else:
+                act = ga.forward(env).copy()
+                adopt = L.STEP_ADOPT_MOVE if (fuse and so.die_env_pending_move(env.handle)) else 0
+            r, alive = env.step(act, flags=L.STEP_ALIVE_BITS | adopt | (L.STEP_USE_COST if cost else 0))
+            trace.append((r.copy(), alive.copy(), env.agents.copy()))
+        outs.append((env.medium.copy(), ga.theta.copy(), trace))
+    assert so.die_get_counter(b"feed_cost") == n0 + 7          # every Physarum step of the second run, not the Brownian one
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for it, (a, b) in enumerate(zip(outs[0][2], outs[1][2])):
+        for x, y, what in zip(a, b, ("reward", "num_agents", "agents")):
             assert np.array_equal(x, y), f"step {it}: {what} differs"
 
 
