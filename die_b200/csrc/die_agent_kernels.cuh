@@ -220,6 +220,7 @@ struct GradientArgs {
     int32_t* cells_out;         // [B][M] post-move cell of every slot (the env's OTHER cell buffer)
     double* burned_out;         // may be null: [B][M] out, linear_action_cost of the action being written (cost hint)
     double cost_w_dep, cost_w_dist;
+    die_sqrt_near_t cost_sqrt;  // enabled where |(dx, dy)| = |scale| to a few ulps (a unit direction): die_math.h
     double* commit_xy;          // null: the move stays speculative (the feed kernel commits the positions once the step
                                 // adopts it).  Else = `agents`, writable: the moved x, y are stored in place by THIS
                                 // launch (DIE_FWD_COMMIT_MOVE: the caller promises that very action to the next step)
@@ -494,7 +495,9 @@ gradient_forward_kernel(const GradientArgs a) {
         ab_dep[i] = dep;
         // cost hint: linear_action_cost (core/env.py:29-35) of this very action, the expression of agent_feed_kernel; the
         // step that receives the action unmodified reads these 8 bytes per slot instead of dx, dy, deposit again (24)
-        if (bo_p != nullptr) bo_p[i] = a.cost_w_dep * fabs(dep) + a.cost_w_dist * sqrt(adx * adx + ady * ady);
+        // (die_sqrt_near: the correctly rounded root from one Newton step where that is provable, sqrt() elsewhere)
+        if (bo_p != nullptr)
+            bo_p[i] = a.cost_w_dep * fabs(dep) + a.cost_w_dist * die_sqrt_near(&a.cost_sqrt, adx * adx + ady * ady);
 
         if (MOVE) {
             // Env._agent_move (core/env.py:152-172) of THIS action + cell resolution + claim: what

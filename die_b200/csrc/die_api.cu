@@ -388,6 +388,7 @@ extern "C" int die_set_step_impl(int32_t impl) {
 // a DRAM sector plus change (77-93 B measured), so the step keeps {consumed_field, new food} in ONE 16-byte
 // pair per cell and hands the food per slot to the next forward pass: three random accesses per slot and step become
 // two.  Small fields (the batched workload) gather out of L2 and keep the 8-byte table.
+static int g_cost_sqrt_near = 1;               // 0: the cost hint always evaluates sqrt() (A-B timing; same bits)
 static int g_cost_hint = 1;                    // 0: the feed kernel always re-reads dx, dy, deposit (A-B timing)
 static int g_pair_mode = 1;                    // 0 never, 1 by size (pair_min_cells), 2 always (tests)
 static int64_t g_pair_min_cells = 1 << 23;     // cells per environment from which it pays.  Measured on a B200, step time at
@@ -1044,6 +1045,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
     else if (strcmp(key, "cost_hint") == 0) g_cost_hint = value ? 1 : 0;
+    else if (strcmp(key, "cost_sqrt_near") == 0) g_cost_sqrt_near = value ? 1 : 0;
     else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }
     else if (strcmp(key, "pair_min_cells_log2") == 0) { DIE_REQUIRE(value >= 2 && value <= 31); g_pair_min_cells = (int64_t)1 << value; }
     else if (strcmp(key, "fused_threads") == 0) { DIE_REQUIRE(value == 512); g_fused_threads = value; }
@@ -1115,6 +1117,9 @@ static int gradient_forward_impl(die_env_t* env, int move_mode, const die_gradie
         a.burned_out = env->burned;
         a.cost_w_dep = env->dyn.cost_w_deposit;
         a.cost_w_dist = env->dyn.cost_w_dist;
+        // a Physarum turn on a normalised gradient with an identity momentum step writes scale * (cos d, sin d)
+        if (g_cost_sqrt_near && p->discrete_turn && p->normalized_grad && p->inertia == 0.0 && p->noise_scale == 0.0)
+            a.cost_sqrt = die_sqrt_near_plan(p->scale);
     }
     void (*kern)(const GradientArgs) = nullptr;
 #define DIE_PICK_FWD(MINB)                                                                               \

@@ -189,6 +189,47 @@ DIE_MATH_FN void die_sincos(double x, double* sn_out, double* cs_out) {
     *cs_out = DIE_NEGIF(c_sel, (o.k + 1) & 2);
 }
 
+/* ---- sqrt(s) of an s known in advance to be close to r0 * r0 ----------------------------------------------------------------
+ * The forward kernel's cost hint needs sqrt(dx*dx + dy*dy) of an action (dx, dy) = scale * (cos, sin): the root is |scale| to
+ * a few ulps.  IEEE sqrt in float64 is ~40 instructions on the GPU; one Newton step from r0 plus a check is 7:
+ *     e = s - r0*r0 (fma),  y = r0 + e * (0.5 / r0) (fma),  d = s - y*y (fma)
+ * and y is RETURNED ONLY IF it is provably the correctly rounded root: |e| < r0^2 2^-40 keeps sqrt(s) and y in r0's binade
+ * (the plan refuses an r0 within 2^-30 of a power of two), where ulp u is a constant, and |d| < r0 u (1 - 2^-20) gives
+ * |sqrt(s) - y| = |s - y*y| / (sqrt(s) + y) < u / 2 strictly, so y is the unique nearest double.  Everything else -- an s that
+ * is not near r0^2, a root within 2^-20 u of a rounding boundary, a disabled plan -- takes sqrt().  Same result bit for bit
+ * either way (tests/test_turn_quick.py::test_sqrt_near_*). */
+typedef struct die_sqrt_near {
+    double r0, half_inv, margin, elim;
+    int enabled;
+} die_sqrt_near_t;
+
+DIE_MATH_FN die_sqrt_near_t die_sqrt_near_plan(double r0) {
+    die_sqrt_near_t p;
+    memset(&p, 0, sizeof(p));
+    r0 = fabs(r0);
+    if (!(r0 > 1e-100 && r0 < 1e100)) return p;
+    int ex;
+    const double mant = frexp(r0, &ex);                      /* r0 = mant 2^ex, mant in [0.5, 1) */
+    if (mant < 0.5 * (1.0 + 9.4e-10) || mant > 1.0 - 9.4e-10) return p;     /* within 2^-30 of a binade edge */
+    const double ulp = ldexp(1.0, ex - 53);
+    p.r0 = r0;
+    p.half_inv = 0.5 / r0;
+    p.margin = r0 * ulp * (1.0 - 9.5367431640625e-07);       /* 1 - 2^-20 */
+    p.elim = r0 * r0 * 9.094947017729282e-13;                /* 2^-40 */
+    p.enabled = 1;
+    return p;
+}
+
+DIE_MATH_FN double die_sqrt_near(const die_sqrt_near_t* p, double s) {
+    if (p->enabled) {
+        const double e = DIE_FMA(-p->r0, p->r0, s);
+        const double y = DIE_FMA(e, p->half_inv, p->r0);
+        const double d = DIE_FMA(-y, y, s);
+        if (fabs(e) < p->elim && fabs(d) < p->margin) return y;
+    }
+    return sqrt(s);
+}
+
 /* sin, cos of x in float32 arithmetic, for DECISIONS WITH A GUARD BAND only: |error| <= DIE_SINCOSF_ERR absolute for
  * |x| <= DIE_SINCOSF_MAX.  Quadrant reduction in float64 (x - k pi/2 with the 33-bit head and the tail of pi/2: exact to
  * ~1e-16 for these arguments), then the classic single-precision minimax polynomials on [-pi/4, pi/4] (Cephes sinf / cosf),

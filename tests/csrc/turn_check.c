@@ -27,3 +27,21 @@ int die_turn_check(long n, const double* gx, const double* gy, const double* the
     }
     return plan.enabled;
 }
+
+/* die_sqrt_near (die_math.h) on an array: y_out[i] = its result, fast_out[i] = 1 where the Newton step was accepted.
+ * Returns whether the plan for r0 is enabled. */
+int die_sqrt_near_check(long n, const double* s, double r0, double* y_out, int* fast_out) {
+    const die_sqrt_near_t plan = die_sqrt_near_plan(r0);
+    for (long i = 0; i < n; ++i) {
+        y_out[i] = die_sqrt_near(&plan, s[i]);
+        int fast = 0;
+        if (plan.enabled) {
+            const double e = fma(-plan.r0, plan.r0, s[i]);
+            const double y = fma(e, plan.half_inv, plan.r0);
+            const double d = fma(-y, y, s[i]);
+            fast = fabs(e) < plan.elim && fabs(d) < plan.margin;
+        }
+        fast_out[i] = fast;
+    }
+    return plan.enabled;
+}

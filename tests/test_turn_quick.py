@@ -173,3 +173,57 @@ def test_magnitudes_around_the_clip_threshold(lib):
     enabled, out = run(lib, mag * np.cos(ang), mag * np.sin(ang), th)
     frac = assert_consistent(out)
     assert 0.2 < frac < 0.95                                 # the band around the threshold defers, the rest decides
+
+
+# ------------------------------------------------------------------------------------------
+# die_sqrt_near (die_math.h): the cost hint's square root -- one Newton step from |scale|, accepted only where it is
+# provably the correctly rounded root
+# ------------------------------------------------------------------------------------------
+def _sqrt_near(lib, s, r0):
+    s = np.ascontiguousarray(s, dtype=np.float64).ravel()
+    y = np.empty_like(s)
+    fast = np.zeros(s.size, dtype=np.int32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    enabled = lib.die_sqrt_near_check(ctypes.c_long(s.size), s.ctypes.data_as(dp), ctypes.c_double(r0), y.ctypes.data_as(dp),
+                                      fast.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return enabled, y, fast.astype(bool)
+
+
+@pytest.mark.parametrize("scale", [0.007, 0.005, 0.0075, 0.01, 0.02, -0.03, 0.3, 123.456, 1e-9])
+def test_sqrt_near_is_the_ieee_square_root(lib, scale):
+    """Every result equals np.sqrt bit for bit -- on the kernel's own inputs (dx*dx + dy*dy of scale * (cos, sin)), on every
+    double within +-2000 ulps of scale^2, on perturbed and on unrelated arguments -- and the Newton step is the common path."""
+    rng = np.random.default_rng(1)
+    th = np.concatenate([rng.uniform(-np.pi, np.pi, 400_000), np.arange(-12, 13) * np.radians(30.), np.arange(-8, 9) * np.radians(45.)])
+    dx, dy = np.cos(th) * scale, np.sin(th) * scale
+    real = dx * dx + dy * dy
+    enabled, y, fast = _sqrt_near(lib, real, scale)
+    assert enabled == 1
+    assert np.array_equal(y, np.sqrt(real)) and fast.mean() > 0.9999
+    r2 = scale * scale
+    near = r2 + np.arange(-2000, 2001) * np.spacing(r2)
+    _, y, fast = _sqrt_near(lib, near, scale)
+    assert np.array_equal(y, np.sqrt(near)) and fast.mean() > 0.99
+    wide = r2 * (1.0 + rng.uniform(-1e-9, 1e-9, 200_000))              # straddles the 2^-40 acceptance window
+    _, y, fast = _sqrt_near(lib, wide, scale)
+    assert np.array_equal(y, np.sqrt(wide)) and 0 < fast.mean() < 1
+    other = np.concatenate([np.exp(rng.uniform(-40, 40, 100_000)), [0.0, r2 * 4, r2 / 4, np.inf, 5e-324, 1e308]])
+    _, y, fast = _sqrt_near(lib, other, scale)
+    assert np.array_equal(y, np.sqrt(other)) and not fast.any()
+
+
+def test_sqrt_near_refuses_what_it_cannot_prove(lib):
+    """An r0 next to a power of two (the ulp changes inside the acceptance window), zero, a non-finite or absurd one: the plan
+    is disabled and sqrt() answers; adversarial arguments whose root sits next to a rounding boundary take sqrt() too."""
+    s = np.random.default_rng(2).uniform(0.1, 4.0, 1000)
+    for r0 in (1.0, 0.5, 2.0 ** -7, 1.0 + 1e-12, 1.0 - 1e-12, 0.0, np.inf, np.nan, 1e-200, 1e200):
+        enabled, y, fast = _sqrt_near(lib, s, r0)
+        assert enabled == 0 and not fast.any() and np.array_equal(y, np.sqrt(s))
+    # roots half an ulp off a double: s = (r + u/2)^2 rounded -- the check must not accept a neighbour of the true rounding
+    scale = 0.007
+    r = scale + np.arange(-50, 51) * np.spacing(scale)
+    u = np.spacing(scale)
+    mid = np.array([float((np.longdouble(a) + np.longdouble(u) / 2) ** 2) for a in r])
+    mid = np.concatenate([mid, np.nextafter(mid, 0), np.nextafter(mid, 1)])
+    _, y, fast = _sqrt_near(lib, mid, scale)
+    assert np.array_equal(y, np.sqrt(mid))
