@@ -649,6 +649,8 @@ class Env:
     def _step_host(self, action: np.ndarray):
         if self._field_dtype != torch.float64:
             raise NotImplementedError("the host-buffer path (numpy actions) runs float64 fields only")
+        if self._speculation is not None and self._speculation[3]:
+            raise RuntimeError("Env.step (host buffers): a committed move (fuse_move='commit') is waiting for its device step")
         hb = self.host_buffers()
         B, M = self._B, self._M
         self._sync_dynamics()
@@ -663,8 +665,6 @@ class Env:
         hb['flip'] ^= 1
         med_t = hb['medium'][hb['flip']]
         nxt = 1 - self._cur
-        if self._speculation is not None and self._speculation[3]:
-            raise RuntimeError("Env.step (host buffers): a committed move (fuse_move='commit') is waiting for its device step")
         self._speculation = None          # die_env_step_host runs the plain step (and discards a pending move)
         self.last_step_fused = False
         # the pinned agents buffer already holds the current alive channel (a full download into it since the agents tensor
