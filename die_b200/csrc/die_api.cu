@@ -322,9 +322,27 @@ static int g_field_vec = 0;        // 1: the 128-bit field pass wherever it appl
                                    // NO faster (3.445 vs 3.409 ms batched, 0.230 vs 0.224 ms at 4096^2) -- the pass is bound by DRAM
                                    // (a 65 % write mix at 80 % of the copy bandwidth), not by its LSU instructions.  Opt-in.
 
+static int g_field_tile = 0;       // threads per 32 x 64-cell tile.  0 = 512 (default: 4 cells and 6 staged values per thread, 32 registers,
+                                   // 4 CTAs = 2048 threads per SM); 1 = 256 (the shape until the end of round 2: 56 registers, 1024 threads per
+                                   // SM; 3.34 vs 3.05 ms batched, 0.2415 vs 0.2166 ms at 4096^2, profiles/r02zs_field_tile_ab.txt); 2 = 1024.
+                                   // 1 / 2 exist for radius 2 only.  Larger tiles (32 x 128, 64 x 64 at 512 threads: two CTAs per SM by shared
+                                   // memory) lose 7-9 %, a 16 x 64 tile of 256 threads gains less (halo 1.50x): profiles/r02zr_*.
+
+template <int R, bool GRAD, int TH, int TW, int NT>
+static cudaError_t launch_field_shape(const FieldArgs& fa, int B, cudaStream_t st, bool f32);
+
 template <int R, bool GRAD>
 static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st, bool f32) {
-    constexpr int TH = 32, TW = 64, NT = 256, G = GRAD ? 1 : 0;
+    if constexpr (R == 2) {
+        if (g_field_tile == 1 && !f32) return launch_field_shape<R, GRAD, 32, 64, 256>(fa, B, st, f32);
+        if (g_field_tile == 2 && !f32) return launch_field_shape<R, GRAD, 32, 64, 1024>(fa, B, st, f32);
+    }
+    return launch_field_shape<R, GRAD, 32, 64, 512>(fa, B, st, f32);
+}
+
+template <int R, bool GRAD, int TH, int TW, int NT>
+static cudaError_t launch_field_shape(const FieldArgs& fa, int B, cudaStream_t st, bool f32) {
+    constexpr int G = GRAD ? 1 : 0;
     FieldArgs a = fa;
     a.tiles_i = (a.H + TH - 1) / TH;
     a.tiles_j = (a.W + TW - 1) / TW;
@@ -332,7 +350,7 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st, b
                                                   (TH + 2 * G) * (TW + 2 * G + 2 * R));
     const bool plain = a.diffuse_mode == DIE_DIFFUSE_WRAP && a.flow_rwave == nullptr && a.flow_frame == nullptr;
     if (f32) {                     // float32 field arrays: the scalar tile kernel on float (blur radius 1..4)
-        if constexpr (R <= 4) {
+        if constexpr (R <= 4 && TH == 32 && TW == 64 && NT == 512) {
             auto kern = plain ? field_step_kernel<R, TH, TW, NT, GRAD, false, true, float>
                               : field_step_kernel<R, TH, TW, NT, GRAD, false, false, float>;
             cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -344,15 +362,16 @@ static cudaError_t launch_field_g(const FieldArgs& fa, int B, cudaStream_t st, b
             return cudaErrorInvalidValue;        // (float32 fields: blur radius 1..4; the Python layer refuses by name)
         }
     }
+    if constexpr (TH == 32 && TW == 64 && NT == 512)
     if (plain && g_field_vec && a.cell_pairs == nullptr && (a.W & 1) == 0 && ((uintptr_t)a.medium_in & 15) == 0 && ((uintptr_t)a.medium_out & 15) == 0 &&
         ((uintptr_t)a.consumed & 15) == 0 && ((uintptr_t)a.winner & 7) == 0 && ((uintptr_t)a.grad32 & 15) == 0) {
         // the default dynamics on an even row length: the 128-bit version (same tile, same arithmetic, same results)
         constexpr int PADL = (R + G) & 1, SW = (PADL + TW + 2 * G + 2 * R + 1) & ~1;
         const size_t vsmem = sizeof(double) * (size_t)((TH + 2 * G + 2 * R) * SW + (TH + 2 * G) * (TW + 2 * G + 2 * R));
-        auto vkern = field_step_vec_kernel<R, TH, TW, NT, GRAD>;
+        auto vkern = field_step_vec_kernel<R, TH, TW, 256, GRAD>;          // (the opt-in keeps its 256 threads per tile)
         cudaError_t verr = cudaFuncSetAttribute(vkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
         if (verr != cudaSuccess) return verr;
-        vkern<<<(unsigned)((int64_t)a.tiles_i * a.tiles_j * B), NT, vsmem, st>>>(a);
+        vkern<<<(unsigned)((int64_t)a.tiles_i * a.tiles_j * B), 256, vsmem, st>>>(a);
         ++g_count_field_vec;
         return cudaGetLastError();
     }
@@ -1044,6 +1063,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "grad_f32") == 0) g_grad_f32 = value ? 1 : 0;
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
+    else if (strcmp(key, "field_tile") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_field_tile = value; }
     else if (strcmp(key, "cost_hint") == 0) g_cost_hint = value ? 1 : 0;
     else if (strcmp(key, "cost_sqrt_near") == 0) g_cost_sqrt_near = value ? 1 : 0;
     else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }
