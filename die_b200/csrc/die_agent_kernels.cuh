@@ -599,8 +599,10 @@ struct FeedArgs {
 // the food is stored per slot for the next forward pass (see FH there).
 // COST: the action cost of every slot comes from the array the forward kernel filled for exactly this action (the caller
 // proved the identity, as for the speculative move): one 8-byte load per slot instead of dx, dy, deposit (24 bytes).
-template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double, bool PAIR = false, bool COST = false>
-__global__ void __launch_bounds__(kAgentThreads)
+// MINB: minimum resident CTAs per SM (a register cap: 6 -> 42, 8 -> 32 registers), tried on the COST instantiation only.
+template <bool SLAB, bool MOVE, bool BITS, bool DIE = false, typename FT = double, bool PAIR = false, bool COST = false,
+          int MINB = 1>
+__global__ void __launch_bounds__(kAgentThreads, MINB)
 agent_feed_kernel(const FeedArgs a, const SlabGeom sg, const SlabTables st) {
     static_assert(!PAIR || (!SLAB && !DIE && sizeof(FT) == 8), "the pair table serves the plain float64 step");
     static_assert(!COST || (!SLAB && !MOVE && !DIE), "the cost hint serves the plain step (a speculative move needs dx, dy)");

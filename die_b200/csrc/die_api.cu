@@ -408,6 +408,7 @@ extern "C" int die_set_step_impl(int32_t impl) {
 // pair per cell and hands the food per slot to the next forward pass: three random accesses per slot and step become
 // two.  Small fields (the batched workload) gather out of L2 and keep the 8-byte table.
 static int g_cost_sqrt_near = 1;               // 0: the cost hint always evaluates sqrt() (A-B timing; same bits)
+static int g_feed_min_blocks = 6;              // resident CTAs per SM asked of the COST feed kernel (0 = the compiler's choice, 48 registers)
 static int g_cost_hint = 1;                    // 0: the feed kernel always re-reads dx, dy, deposit (A-B timing)
 static int g_pair_mode = 1;                    // 0 never, 1 by size (pair_min_cells), 2 always (tests)
 static int64_t g_pair_min_cells = 1 << 23;     // cells per environment from which it pays.  Measured on a B200, step time at
@@ -690,6 +691,9 @@ static int env_step_range(die_env_t* e, int b0, int nb, double* medium_in, doubl
     if (cost) {
         feed = pair ? agent_feed_kernel<false, false, true, false, double, true, true>
                     : agent_feed_kernel<false, false, true, false, double, false, true>;
+        // six resident CTAs per SM (40 instead of 48 registers, no spills): more gathers in flight, feed 1.93 -> 1.86 ms batched;
+        // eight (32 registers, 40 bytes of spills): 2.28 ms -- profiles/r02zu_feed_min_blocks_ab.txt
+        if (!pair && g_feed_min_blocks == 6) feed = agent_feed_kernel<false, false, true, false, double, false, true, 6>;
         ++g_count_feed_cost;
     }
     FeedArgs fa;
@@ -1064,6 +1068,7 @@ extern "C" int die_set_tuning(const char* key, int32_t value) {
     else if (strcmp(key, "step_impl") == 0) return die_set_step_impl(value);
     else if (strcmp(key, "field_vec") == 0) g_field_vec = value ? 1 : 0;
     else if (strcmp(key, "field_tile") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_field_tile = value; }
+    else if (strcmp(key, "feed_min_blocks") == 0) { DIE_REQUIRE(value == 0 || value == 6); g_feed_min_blocks = value; }
     else if (strcmp(key, "cost_hint") == 0) g_cost_hint = value ? 1 : 0;
     else if (strcmp(key, "cost_sqrt_near") == 0) g_cost_sqrt_near = value ? 1 : 0;
     else if (strcmp(key, "pair_mode") == 0) { DIE_REQUIRE(value >= 0 && value <= 2); g_pair_mode = value; }

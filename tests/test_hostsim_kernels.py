@@ -46,7 +46,7 @@ def portable_math():
 @pytest.fixture
 def tuning():
     """set_tuning(key, value) with every switch restored afterwards."""
-    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1, pair_mode=1, pair_min_cells_log2=23, cost_hint=1, cost_sqrt_near=1, field_tile=0)
+    defaults = dict(turn_quick=1, fwd_min_blocks=4, feed_bits=1, fwd_lean=1, field_prefetch=1, grad_f32=1, step_impl=0, fused_threads=512, field_vec=0, sense_quick=1, pair_mode=1, pair_min_cells_log2=23, cost_hint=1, cost_sqrt_near=1, field_tile=0, feed_min_blocks=6)
     yield S.set_tuning
     for k, v in defaults.items():
         S.set_tuning(k, v)
@@ -244,7 +244,7 @@ def _philox_run(field, iters, seed=11, batch=None, agent_kw=PHYS, record=False):
 
 @pytest.mark.parametrize("key,values", [("fwd_lean", [0, 5]), ("turn_quick", [0]), ("fwd_min_blocks", [3, 5]),
                                         ("feed_bits", [0]), ("field_prefetch", [0]), ("grad_f32", [0]), ("step_impl", [1]), ("field_vec", [1]), ("sense_quick", [0]), ("pair_mode", [2]),
-                                        ("field_tile", [1, 2]), ("cost_hint", [0]), ("cost_sqrt_near", [0])])
+                                        ("field_tile", [1, 2]), ("cost_hint", [0]), ("cost_sqrt_near", [0]), ("feed_min_blocks", [0])])
 def test_tuning_switches_do_not_change_results(tuning, key, values):
     lean0 = S.lib().die_get_counter(b"forward_lean_f32")
     base = _philox_run((40, 72), 12)
