@@ -48,8 +48,9 @@ UNIT = "cell-updates/s"
 #   env_step_fused    the cluster-fused step: R{x,y,dx,dy,dep,agent_food} W{x,y,agent_food}, chem R+W, food R+W,
 #                     occupancy W = 112 B / cell-update (alive from 1 bit, occupancy / claims / the food under a slot
 #                     never leave the chip, dx / dy are read once from HBM)
-# Implementation extras (4 B/slot cell cache, 8 B/cell published gradient, 4 B/cell claim table of the three-kernel path)
-# are NOT counted as achieved.
+# Implementation extras (4 B/slot cell cache, 8 B/cell published gradient, 4 B/cell claim table of the three-kernel path,
+# the 8 B/slot cost hint the forward kernel leaves for the feed kernel -- which then reads it in place of `dep`, so
+# agent_feed stays at 40 B) are NOT counted as achieved.
 BYTES = {"physarum_forward": 72.0, "move_claim": 56.0, "agent_feed": 40.0, "field_step": 48.0,
          "env_step_fused": 112.0, "finalize_stats": 0.0}
 SURVEY_BYTES = {"physarum_forward": 96.0, "move_claim": 56.0, "agent_feed": 40.0, "field_step": 48.0,
