@@ -1568,6 +1568,7 @@ def test_results_do_not_depend_on_block_or_thread_order():
     env = dict(os.environ, HOSTSIM_BLOCK_ORDER="shuffle", HOSTSIM_THREAD_ORDER="reverse", DIE_SWEEP_SEEDS="12")
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "tests/test_hostsim_kernels.py",
                           "-k", "brownian_free_run or with_env_hints or fused_move or bulk_field_kernel_equals or "
-                                "slab_world_equals or golden or random_configurations or tuning_switches"],
+                                "slab_world_equals or golden or random_configurations or tuning_switches or "
+                                "committed_move_equals or cost_hint_equals or jones_agent_free_run"],
                          cwd=root, env=env, capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
