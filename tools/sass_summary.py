@@ -17,7 +17,7 @@ WANT = ("LDG", "STG", "LD.", "ST.", "LDS", "STS", "ATOM", "RED", "UBLKCP", "UTMA
 
 def main():
     pat = re.compile(sys.argv[1]) if len(sys.argv) > 1 else re.compile(
-        r"gradient_forward_kernelILb1ELb0ELb0ELi4ELb1ELb1E|move_claim_kernelILb0ELb1E|field_step_kernelILi2ELi32ELi64ELi256ELb1ELb0ELb1E"
+        r"gradient_forward_kernelILb1ELb0ELb0ELi4ELb1ELb1E|move_claim_kernelILb0ELb1E|field_step_kernelILi2ELi32ELi64ELi512ELb1ELb0ELb1E"
         r"|agent_feed_kernelILb0ELb0ELb1ELb0E|env_step_fused_kernelILi2ELi512ELb1ELb1E|brownian_forward")
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "die_b200", "libdie_sm100a.so")],
                          capture_output=True, text=True, check=True).stdout
