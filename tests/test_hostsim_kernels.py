@@ -1258,6 +1258,13 @@ def test_random_configurations_against_the_oracle(portable_math, tuning, seed):
     ra = R.PhysarumAgent(max_agents=m, prev_grad=prev, **agent_kw)
     ga = S.SimGradientAgent(m, **agent_kw)
     ga.theta[0] = theta0
+    # (a second generator, so that the cases of the seeds above stay what they were) the round-2 variants: cost hint,
+    # committed move, threads per field tile, the feed kernel's register cap
+    extra = np.random.default_rng(9000 + seed)
+    ga.write_cost = bool(extra.random() < 0.6)
+    ga.fuse_move = 'commit' if (hints and tune['feed_bits'] and extra.random() < 0.4) else False
+    tuning("field_tile", int(extra.integers(0, 3)))
+    tuning("feed_min_blocks", int(extra.choice([0, 6])))
     rng = np.random.default_rng(seed)
     robs = ref._get_current_obs
     for it in range(4):
@@ -1267,7 +1274,9 @@ def test_random_configurations_against_the_oracle(portable_math, tuning, seed):
         assert np.array_equal(ga.theta[0], ra._direction_rads), f"theta differs at step {it}"
         assert np.array_equal(gact, ract), f"action differs at step {it}"
         robs, rr, _, _, rinfo = ref.step(ract)
-        r, alive = env.step(gact, flags=L.STEP_ALIVE_BITS if tune['feed_bits'] else 0)
+        adopt = L.STEP_ADOPT_MOVE if S.lib().die_env_pending_move(env.handle) else 0
+        r, alive = env.step(gact, flags=(L.STEP_ALIVE_BITS if tune['feed_bits'] else 0) | adopt
+                            | (L.STEP_USE_COST if ga.write_cost else 0))
         assert np.array_equal(ref_cells_linear(ref), env.cells()[0]), f"cells differ at step {it}"
         assert rinfo['num_agents'] == alive[0]
         assert _rel(rr, r[0]) < 1e-10 or abs(rr - r[0]) < 1e-9
